@@ -1,0 +1,181 @@
+/* stribor_b200 -- C ABI of the B200 (sm_100a) coupling-flow kernels.
+ *
+ * This header is the drop-in boundary.  The reference (mbilos/stribor 0.2.0) is pure
+ * PyTorch and has no FFI layer; what a binding replaces is the arithmetic done inside
+ * these reference methods (paths relative to the reference checkout):
+ *
+ *   stb_layer_apply      <- Coupling.forward / inverse / log_det_jacobian
+ *                           (stribor/flows/coupling.py:69-95), with Affine
+ *                           (flows/affine.py:97-123) or Spline (flows/spline.py:89-143 ->
+ *                           util/rational_quadratic_spline.py:11-251, util/cubic_spline.py:22-247)
+ *                           and the latent MLP (net/mlp.py:46-65); also the inherited
+ *                           forward_and_/inverse_and_log_det_jacobian (flow.py:35-47) and
+ *                           ContinuousAffineCoupling (flows/coupling.py:188-213) with
+ *                           TimeLinear (net/time_net.py:18-28)
+ *   stb_flow_apply       <- NormalizingFlow.forward / inverse / *_and_log_det_jacobian
+ *                           (flow.py:99-125) and NeuralFlow.forward (flow.py:172-184)
+ *   stb_flow_log_prob    <- NormalizingFlow.log_prob (flow.py:127-130) with UnitNormal
+ *                           (dist/normal.py:40-54)
+ *   stb_layer_backward   <- what autograd derives for the above in the NLL training step
+ *   stb_pack_layer       <- (new) one-off repack of nn.Linear weights for the tcgen05 path
+ *
+ * Conventions: plain C, no C++ types, no exceptions.  Every function returns 0 on success
+ * or a negative STB_E* code; stb_last_error() gives a thread-local message.  The CALLER owns
+ * every buffer (device pointers unless stated), the library never allocates device memory,
+ * never synchronises and keeps no global mutable state, so calls are re-entrant across
+ * streams, devices and host threads.  All tensors are fp32, row-major, rows contiguous:
+ * x/y [rows, dim], latent [rows, latent_dim], t [rows, 1], ldj/lp [rows].
+ */
+#ifndef STRIBOR_B200_H_
+#define STRIBOR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STB_ABI_VERSION 1
+#define STB_MAX_LINEAR 8
+
+/* error codes */
+#define STB_OK 0
+#define STB_EINVAL (-1)      /* bad argument / unsupported configuration  */
+#define STB_ECUDA (-2)       /* CUDA runtime error (launch, attribute)     */
+#define STB_ENOTSUP (-3)     /* valid in the reference, not built here yet */
+
+/* transform kinds (flows/affine.py, flows/spline.py, flows/coupling.py:98) */
+enum { STB_AFFINE = 0, STB_RQS = 1, STB_CUBIC = 2, STB_CONT_AFFINE = 3 };
+
+/* activations by torch.nn class name (net/mlp.py:38-41) */
+enum { STB_ACT_NONE = 0, STB_ACT_TANH = 1, STB_ACT_RELU = 2, STB_ACT_SIGMOID = 3, STB_ACT_ELU = 4,
+       STB_ACT_SOFTPLUS = 5, STB_ACT_LEAKY_RELU = 6, STB_ACT_SILU = 7, STB_ACT_GELU = 8 };
+
+/* directions */
+enum { STB_FORWARD = 0, STB_INVERSE = 1 };
+
+/* what to do with the per-row log|det J| of a layer */
+enum { STB_LDJ_NONE = 0,      /* not computed                                          */
+       STB_LDJ_SET = 1,       /* ldj[row]  = value                                     */
+       STB_LDJ_ADD = 2 };     /* ldj[row] += value                                     */
+
+/* Latent network: Linear -> (act -> Linear)* [-> final act]   (net/mlp.py:46-58)
+ * W[i] is nn.Linear layout [dims[i+1], dims[i]] row-major, b[i] is [dims[i+1]]. */
+typedef struct stb_mlp {
+    int32_t n_linear;                  /* 0 = no network: `const_out` below is used     */
+    int32_t activation;
+    int32_t final_activation;
+    int32_t dims[STB_MAX_LINEAR + 1];
+    const float* W[STB_MAX_LINEAR];
+    const float* b[STB_MAX_LINEAR];
+} stb_mlp;
+
+/* One invertible layer.
+ *   cond_x = 1: a Coupling -- the network input is [x*mask | latent | t?]; dims with
+ *               mask 0 are transformed, dims with mask 1 pass through.
+ *   cond_x = 0: a stand-alone element-wise transform -- the network input is [latent];
+ *               every dim is transformed (`mask` ignored).
+ * Network output layout (flows/affine.py:66, flows/spline.py:82-86):
+ *   affine / cont-affine: [log_scale(dim) | shift(dim)]
+ *   rqs:   per dim [widths(K) | heights(K) | derivatives(K-1)]
+ *   cubic: per dim [widths(K) | heights(K) | left, right derivative]
+ */
+typedef struct stb_layer {
+    int32_t kind;
+    int32_t dim;
+    int32_t latent_dim;
+    int32_t cond_x;
+    int32_t time_input;        /* cont-affine: t is the last network input                */
+    int32_t n_bins;
+    int32_t inverse_ldj_own;   /* inverse: 1 = log-derivative of the inverse map itself
+                                  (Spline.inverse_and_log_det_jacobian, spline.py:119-123);
+                                  0 = -(forward log-derivative at the recovered point),
+                                  the inherited default (flow.py:42-47) Coupling uses      */
+    int32_t zero_cond;         /* dim == 1: conditioning on x is multiplied by 0
+                                  (coupling.py:62-63)                                      */
+    float lower, upper;        /* spline box: domain == codomain == [lower, upper]        */
+    float left, right;         /* rqs only, used when has_box != 0: domain [left, right]  */
+    float bottom, top;         /*   and codomain [bottom, top]
+                                  (rational_quadratic_spline.py:55-64)                     */
+    int32_t has_box;
+    int32_t reserved0;
+    const uint8_t* mask;       /* device, [dim], 1 = pass through / conditions            */
+    const float* const_out;    /* device, network-output-shaped vector when n_linear == 0 */
+    const float* row_out;      /* device, [rows, out_width]: a precomputed network output
+                                  PER ROW (n_linear == 0; takes precedence over const_out) */
+    const float* time_scale;   /* device, [2*dim] TimeLinear.scale (cont-affine)          */
+    stb_mlp net;
+    const void* packed;        /* device, from stb_pack_layer (NULL = generic path only)  */
+    uint64_t packed_bytes;
+} stb_layer;
+
+int stb_abi_version(void);
+uint64_t stb_sizeof_layer(void);          /* sizeof(stb_layer), for binding self-checks */
+const char* stb_last_error(void);
+
+/* y = T(x) (STB_FORWARD) or T^-1(x) (STB_INVERSE) for one layer; optionally the per-row
+ * log|det J| with the reference's sign conventions (see inverse_ldj_own).  x and y may
+ * alias.  `base_log_prob` != 0 additionally adds the UnitNormal log-density of the OUTPUT
+ * row to ldj (used for the last layer of log_prob). */
+int stb_layer_apply(const stb_layer* layer, int direction, const float* x, const float* latent,
+                    const float* t, float* y, float* ldj, int ldj_mode, int base_log_prob,
+                    int64_t rows, void* stream);
+
+/* Element-wise variant: additionally writes the per-dimension log-derivative
+ * ldiag [rows, dim] (0 for pass-through dims) -- ElementwiseTransform.log_diag_jacobian
+ * (flow.py:50-69, affine.py:115-123, spline.py:135-143). */
+int stb_layer_apply_diag(const stb_layer* layer, int direction, const float* x, const float* latent,
+                         const float* t, float* y, float* ldiag, int64_t rows, void* stream);
+
+/* Chain of layers, applied first-to-last (STB_FORWARD) or last-to-first with each layer
+ * inverted (STB_INVERSE).  `out` may alias `x`.  ldj (nullable) receives the summed
+ * log|det J| according to ldj_mode. */
+int stb_flow_apply(const stb_layer* layers, int n_layers, int direction, const float* x,
+                   const float* latent, const float* t, float* out, float* ldj, int ldj_mode,
+                   int64_t rows, void* stream);
+
+/* lp[row] = log N(x; 0, I) + sum_layers ldj, x = inverse chain of y  (flow.py:127-130).
+ * `x_out` must be a [rows, dim] scratch buffer (it receives the latent x). */
+int stb_flow_log_prob(const stb_layer* layers, int n_layers, const float* y, const float* latent,
+                      const float* t, float* x_out, float* lp, int64_t rows, void* stream);
+
+/* lp[row] (+)= sum_j -x_j^2/2 - log(sqrt(2 pi))   (dist/normal.py:37) */
+int stb_unit_normal_log_prob(const float* x, float* lp, int accumulate, int32_t dim, int64_t rows,
+                             void* stream);
+
+/* Gradient of one layer application, recomputing the layer from its saved INPUT `x`
+ * (the tensor stb_layer_apply was called with).  g_out [rows,dim] and g_ldj [rows]
+ * (nullable) are the incoming gradients of the layer's outputs; g_x [rows,dim],
+ * g_latent, g_t (nullable) receive input gradients; gW[i]/gb[i] (same shapes as the
+ * weights; accumulated into, caller zeroes) receive parameter gradients;
+ * g_const_out / g_time_scale likewise.  `workspace` must hold
+ * stb_layer_backward_workspace_bytes(layer, rows) bytes. */
+typedef struct stb_layer_grads {
+    float* gW[STB_MAX_LINEAR];
+    float* gb[STB_MAX_LINEAR];
+    float* g_const_out;
+    float* g_time_scale;
+} stb_layer_grads;
+
+uint64_t stb_layer_backward_workspace_bytes(const stb_layer* layer, int64_t rows);
+int stb_layer_backward(const stb_layer* layer, int direction, const float* x, const float* latent,
+                       const float* t, const float* g_out, const float* g_ldj, float* g_x,
+                       float* g_latent, float* g_t, const stb_layer_grads* grads, void* workspace,
+                       int64_t rows, void* stream);
+
+/* tcgen05 path: size of / build the packed weight image for a layer (0 bytes = this layer
+ * configuration only runs on the generic path). */
+uint64_t stb_packed_bytes(const stb_layer* layer);
+int stb_pack_layer(const stb_layer* layer, void* packed_out, void* stream);
+
+/* 1 if stb_layer_apply would take the tcgen05 path for this (packed) layer. */
+int stb_layer_uses_tensor_path(const stb_layer* layer);
+
+/* number of kernels this library has launched from the calling thread (bench bookkeeping) */
+uint64_t stb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STRIBOR_B200_H_ */

@@ -1,0 +1,271 @@
+"""torch.library custom ops in front of the C ABI.
+
+Python owns the tensors (allocation, streams, autograd graph); the arithmetic happens in
+libstribor_b200.so.  Three ops:
+
+  stribor_b200::layer_apply     one layer, one direction (+ log|det J|), differentiable
+  stribor_b200::layer_backward  its gradient (recompute-from-input)
+  stribor_b200::flow_chain      a whole chain of layers in one C call (inference fast path:
+                                forward / inverse / log_prob incl. the UnitNormal term)
+
+A layer is described by plain data so that it can cross the op boundary:
+  meta  = [kind, dim, latent_dim, cond_x, time_input, n_bins, inverse_ldj_own, zero_cond,
+           activation, final_activation, n_linear, n_params, has_box, row_mode, dims[0..n_linear]]
+  fmeta = [lower, upper, left, right, bottom, top]
+  params = [W0, b0, W1, b1, ...] (+ [time_scale]) or [const_out]   (row_mode: const_out is a
+           per-row [rows, out_width] tensor -> stb_layer.row_out)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+META_HEADER = 14
+FMETA_LEN = 6
+
+
+def _check_cuda(x: Tensor, what: str):
+    if not x.is_cuda:
+        raise RuntimeError(
+            f'stribor_b200: {what} is on {x.device}; this package runs its transforms in CUDA '
+            'kernels only (sm_100a) and has no CPU fallback -- move the module and inputs to a GPU.')
+    if x.dtype != torch.float32:
+        raise TypeError(f'stribor_b200: {what} must be float32, got {x.dtype}')
+
+
+def _dp(t: Optional[Tensor]):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _stream(x: Tensor):
+    return torch.cuda.current_stream(x.device).cuda_stream
+
+
+def _fill_struct(L: _lib.StbLayer, meta: Sequence[int], fmeta: Sequence[float], mask: Optional[Tensor],
+                 params: Sequence[Tensor], packed: Optional[Tensor]):
+    (kind, dim, latent_dim, cond_x, time_input, n_bins, inv_own, zero_cond, act, fact, n_linear,
+     n_params, has_box, row_mode) = meta[:META_HEADER]
+    L.kind, L.dim, L.latent_dim, L.cond_x = kind, dim, latent_dim, cond_x
+    L.time_input, L.n_bins, L.inverse_ldj_own, L.zero_cond = time_input, n_bins, inv_own, zero_cond
+    L.lower, L.upper = float(fmeta[0]), float(fmeta[1])
+    L.left, L.right, L.bottom, L.top = (float(v) for v in fmeta[2:6])
+    L.has_box = has_box
+    L.mask = _dp(mask)
+    L.net.n_linear = n_linear
+    L.net.activation = act
+    L.net.final_activation = fact
+    assert len(params) == n_params, (len(params), n_params)
+    if n_linear > 0:
+        dims = meta[META_HEADER:META_HEADER + n_linear + 1]
+        for i, v in enumerate(dims):
+            L.net.dims[i] = v
+        for i in range(n_linear):
+            w, b = params[2 * i], params[2 * i + 1]
+            assert w.is_contiguous() and b.is_contiguous()
+            assert tuple(w.shape) == (dims[i + 1], dims[i]), (tuple(w.shape), dims)
+            L.net.W[i] = w.data_ptr()
+            L.net.b[i] = b.data_ptr()
+        rest = params[2 * n_linear:]
+        L.const_out = None
+        L.row_out = None
+    else:
+        assert params[0].is_contiguous()
+        L.const_out = None if row_mode else params[0].data_ptr()
+        L.row_out = params[0].data_ptr() if row_mode else None
+        rest = params[1:]
+    L.time_scale = rest[0].data_ptr() if kind == _lib.CONT_AFFINE else None
+    if packed is not None and packed.numel() > 0:
+        L.packed = packed.data_ptr()
+        L.packed_bytes = packed.numel() * packed.element_size()
+    else:
+        L.packed = None
+        L.packed_bytes = 0
+
+
+def make_struct(meta, fmeta, mask, params, packed=None) -> _lib.StbLayer:
+    L = _lib.StbLayer()
+    _fill_struct(L, meta, fmeta, mask, params, packed)
+    return L
+
+
+def meta_len(meta: Sequence[int], off: int = 0) -> int:
+    n_linear = meta[off + 10]
+    return META_HEADER + (n_linear + 1 if n_linear > 0 else 0)
+
+
+# ----------------------------------------------------------------------------------------------
+# one layer
+# ----------------------------------------------------------------------------------------------
+@torch.library.custom_op('stribor_b200::layer_apply', mutates_args=(), device_types='cuda')
+def layer_apply(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mask: Optional[Tensor],
+                params: List[Tensor], packed: Optional[Tensor], meta: List[int], fmeta: List[float],
+                direction: int, want_ldj: bool, base_lp: bool) -> Tuple[Tensor, Tensor]:
+    """x [rows, dim] -> (y [rows, dim], ldj [rows] or empty)."""
+    rows, dim = x.shape
+    y = torch.empty_like(x)
+    ldj = torch.empty(rows if want_ldj else 0, dtype=x.dtype, device=x.device)
+    if rows == 0:
+        return y, ldj
+    L = make_struct(meta, fmeta, mask, params, packed)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().stb_layer_apply(C.byref(L), direction, x.data_ptr(), _dp(latent), _dp(t),
+                                        y.data_ptr(), _dp(ldj), _lib.LDJ_SET if want_ldj else _lib.LDJ_NONE,
+                                        int(base_lp), rows, _stream(x))
+    _lib.check(rc)
+    return y, ldj
+
+
+@layer_apply.register_fake
+def _(x, latent, t, mask, params, packed, meta, fmeta, direction, want_ldj, base_lp):
+    return torch.empty_like(x), x.new_empty(x.shape[0] if want_ldj else 0)
+
+
+@torch.library.custom_op('stribor_b200::layer_apply_diag', mutates_args=(), device_types='cuda')
+def layer_apply_diag(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mask: Optional[Tensor],
+                     params: List[Tensor], meta: List[int], fmeta: List[float], direction: int
+                     ) -> Tuple[Tensor, Tensor]:
+    """x [rows, dim] -> (y [rows, dim], per-dimension log-derivative [rows, dim]).  Not differentiable."""
+    rows, dim = x.shape
+    y = torch.empty_like(x)
+    ldiag = torch.empty_like(x)
+    if rows == 0:
+        return y, ldiag
+    L = make_struct(meta, fmeta, mask, params, None)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().stb_layer_apply_diag(C.byref(L), direction, x.data_ptr(), _dp(latent), _dp(t),
+                                             y.data_ptr(), ldiag.data_ptr(), rows, _stream(x))
+    _lib.check(rc)
+    return y, ldiag
+
+
+@layer_apply_diag.register_fake
+def _(x, latent, t, mask, params, meta, fmeta, direction):
+    return torch.empty_like(x), torch.empty_like(x)
+
+
+@torch.library.custom_op('stribor_b200::layer_backward', mutates_args=(), device_types='cuda')
+def layer_backward(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mask: Optional[Tensor],
+                   params: List[Tensor], meta: List[int], fmeta: List[float], direction: int,
+                   g_y: Tensor, g_ldj: Optional[Tensor], need_latent: bool, need_t: bool
+                   ) -> List[Tensor]:
+    """-> [g_x, g_latent (or empty), g_t (or empty), *g_params]."""
+    rows, dim = x.shape
+    g_x = torch.empty_like(x)
+    g_latent = torch.empty_like(latent) if (need_latent and latent is not None) else x.new_empty(0)
+    g_t = torch.empty_like(t) if (need_t and t is not None) else x.new_empty(0)
+    g_params = [torch.zeros_like(p) for p in params]
+    if rows == 0:
+        g_x.zero_()
+        return [g_x, g_latent, g_t] + g_params
+    L = make_struct(meta, fmeta, mask, params, None)
+    G = _lib.StbLayerGrads()
+    n_linear = meta[10]
+    for i in range(n_linear):
+        G.gW[i] = g_params[2 * i].data_ptr()
+        G.gb[i] = g_params[2 * i + 1].data_ptr()
+    rest = g_params[2 * n_linear:]
+    if n_linear == 0:
+        G.g_const_out = rest[0].data_ptr()
+        rest = rest[1:]
+    if meta[0] == _lib.CONT_AFFINE:
+        G.g_time_scale = rest[0].data_ptr()
+    lib = _lib.lib()
+    with torch.cuda.device(x.device):
+        ws_bytes = lib.stb_layer_backward_workspace_bytes(C.byref(L), rows)
+        ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=x.device)
+        rc = lib.stb_layer_backward(C.byref(L), direction, x.data_ptr(), _dp(latent), _dp(t),
+                                    g_y.data_ptr(), _dp(g_ldj), g_x.data_ptr(), _dp(g_latent), _dp(g_t),
+                                    C.byref(G), ws.data_ptr(), rows, _stream(x))
+    _lib.check(rc)
+    return [g_x, g_latent, g_t] + g_params
+
+
+@layer_backward.register_fake
+def _(x, latent, t, mask, params, meta, fmeta, direction, g_y, g_ldj, need_latent, need_t):
+    gl = torch.empty_like(latent) if (need_latent and latent is not None) else x.new_empty(0)
+    gt = torch.empty_like(t) if (need_t and t is not None) else x.new_empty(0)
+    return [torch.empty_like(x), gl, gt] + [torch.empty_like(p) for p in params]
+
+
+def _setup_ctx(ctx, inputs, output):
+    x, latent, t, mask, params, packed, meta, fmeta, direction, want_ldj, base_lp = inputs
+    if base_lp:
+        raise RuntimeError('base_lp is an inference-only fusion')
+    ctx.save_for_backward(x, latent, t, mask, *params)
+    ctx.n_params = len(params)
+    ctx.meta, ctx.fmeta, ctx.direction, ctx.want_ldj = list(meta), list(fmeta), direction, want_ldj
+    ctx.has_latent, ctx.has_t = latent is not None, t is not None
+
+
+def _backward(ctx, g_y, g_ldj):
+    saved = ctx.saved_tensors
+    x, latent, t, mask = saved[:4]
+    params = list(saved[4:])
+    need = ctx.needs_input_grad
+    g_y = g_y.contiguous() if g_y is not None else torch.zeros_like(x)
+    gl = g_ldj.contiguous() if (ctx.want_ldj and g_ldj is not None) else None
+    outs = layer_backward(x, latent, t, mask, params, ctx.meta, ctx.fmeta, ctx.direction, g_y, gl,
+                          bool(ctx.has_latent and need[1]), bool(ctx.has_t and need[2]))
+    g_x, g_latent, g_t = outs[:3]
+    g_params = list(outs[3:])
+    return (g_x, g_latent if (ctx.has_latent and need[1]) else None,
+            g_t if (ctx.has_t and need[2]) else None, None, g_params, None, None, None, None, None, None)
+
+
+layer_apply.register_autograd(_backward, setup_context=_setup_ctx)
+
+
+# ----------------------------------------------------------------------------------------------
+# whole chain in one C call (no autograd)
+# ----------------------------------------------------------------------------------------------
+CHAIN_FORWARD, CHAIN_INVERSE, CHAIN_LOG_PROB = 0, 1, 2
+
+
+@torch.library.custom_op('stribor_b200::flow_chain', mutates_args=(), device_types='cuda')
+def flow_chain(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], masks: List[Tensor],
+               params: List[Tensor], packed: List[Tensor], meta: List[int], fmeta: List[float],
+               mode: int, want_ldj: bool) -> Tuple[Tensor, Tensor]:
+    """mode FORWARD/INVERSE: (out [rows,dim], ldj [rows] or empty);
+    mode LOG_PROB: (latent x [rows,dim], log_prob [rows])."""
+    rows, dim = x.shape
+    n_layers = len(masks)
+    out = torch.empty_like(x)
+    need_vec = want_ldj or mode == CHAIN_LOG_PROB
+    ldj = torch.empty(rows if need_vec else 0, dtype=x.dtype, device=x.device)
+    if rows == 0:
+        return out, ldj
+    arr = (_lib.StbLayer * n_layers)()
+    mo = po = 0
+    for i in range(n_layers):
+        ml = meta_len(meta, mo)
+        m = meta[mo:mo + ml]
+        npar = m[11]
+        _fill_struct(arr[i], m, fmeta[FMETA_LEN * i:FMETA_LEN * (i + 1)], masks[i], params[po:po + npar], packed[i])
+        mo += ml
+        po += npar
+    lib = _lib.lib()
+    with torch.cuda.device(x.device):
+        if mode == CHAIN_LOG_PROB:
+            rc = lib.stb_flow_log_prob(arr, n_layers, x.data_ptr(), _dp(latent), _dp(t), out.data_ptr(),
+                                       ldj.data_ptr(), rows, _stream(x))
+        else:
+            rc = lib.stb_flow_apply(arr, n_layers, _lib.FORWARD if mode == CHAIN_FORWARD else _lib.INVERSE,
+                                    x.data_ptr(), _dp(latent), _dp(t), out.data_ptr(), _dp(ldj),
+                                    _lib.LDJ_SET if want_ldj else _lib.LDJ_NONE, rows, _stream(x))
+    _lib.check(rc)
+    return out, ldj
+
+
+@flow_chain.register_fake
+def _(x, latent, t, masks, params, packed, meta, fmeta, mode, want_ldj):
+    need_vec = want_ldj or mode == CHAIN_LOG_PROB
+    return torch.empty_like(x), x.new_empty(x.shape[0] if need_vec else 0)
+
+
+def launch_count() -> int:
+    return int(_lib.lib().stb_launch_count())

@@ -1,0 +1,35 @@
+// Host-side plumbing shared by the translation units of libstribor_b200.so:
+// thread-local error text, launch counter, internal entry points.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/stribor_b200.h"
+
+namespace stb {
+
+int set_error(int code, const char* fmt, ...);
+void count_launch();
+
+int validate_layer(const stb_layer* L);
+
+int generic_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent,
+                        const float* t, float* y, float* ldj, int ldj_mode, int base_log_prob,
+                        float* ldiag, int64_t rows, cudaStream_t stream);
+int unit_normal_apply(const float* x, float* lp, int accumulate, int dim, int64_t rows,
+                      cudaStream_t stream);
+
+// tcgen05 path (tc_layer.cu)
+bool tc_layer_supported(const stb_layer* L);
+uint64_t tc_packed_bytes(const stb_layer* L);
+int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
+int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj,
+                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
+
+// backward (backward.cu)
+uint64_t layer_backward_workspace_bytes(const stb_layer* L, int64_t rows);
+int layer_backward(const stb_layer* L, int direction, const float* x, const float* latent,
+                   const float* t, const float* g_out, const float* g_ldj, float* g_x,
+                   float* g_latent, float* g_t, const stb_layer_grads* grads, void* workspace,
+                   int64_t rows, cudaStream_t stream);
+
+}  // namespace stb

@@ -1,0 +1,3 @@
+from .affine import *
+from .coupling import *
+from .spline import *

@@ -1,0 +1,70 @@
+"""Shared host-side description of a fused layer (see _ops.py for the wire format)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from .. import _lib, _ops
+from ..net.mlp import MLP
+
+
+def net_meta(net):
+    """-> (dims, act, final_act, params) for an MLP conditioner, or raise NotImplementedError."""
+    if not isinstance(net, MLP):
+        raise NotImplementedError(
+            f'latent_net of type {type(net).__name__} is not fused; use stribor_b200.net.MLP')
+    return net.describe()
+
+
+def build_meta(kind, dim, latent_dim, cond_x, time_input, n_bins, inv_own, zero_cond, net, n_extra,
+               has_box=0):
+    if net is None:
+        dims, act, fact, params = [], 0, 0, None
+        n_linear = 0
+    else:
+        dims, act, fact, params = net_meta(net)
+        n_linear = len(dims) - 1
+    n_params = (2 * n_linear if n_linear else 1) + n_extra
+    meta = [kind, dim, latent_dim, int(cond_x), int(time_input), n_bins, int(inv_own), int(zero_cond),
+            act, fact, n_linear, n_params, int(has_box), 0] + list(dims)
+    return meta, params
+
+
+class PackedCache:
+    """Device image of a layer's weights for the tcgen05 kernel, rebuilt when they change."""
+
+    def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def get(self, meta, fmeta, mask, params):
+        if not params or not params[0].is_cuda or os.environ.get('STRIBOR_B200_FORCE_GENERIC') == '1':
+            return None
+        key = (tuple(meta), tuple(fmeta), tuple((p.data_ptr(), p._version) for p in params))
+        if key == self.key:
+            return self.buf
+        lib = _lib.lib()
+        detached = [p.detach() for p in params]
+        L = _ops.make_struct(meta, fmeta, mask, detached, None)
+        nbytes = int(lib.stb_packed_bytes(C.byref(L)))
+        buf = None
+        if nbytes > 0:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
+            with torch.cuda.device(buf.device):
+                _lib.check(lib.stb_pack_layer(C.byref(L), buf.data_ptr(),
+                                              torch.cuda.current_stream(buf.device).cuda_stream))
+        self.key, self.buf = key, buf
+        return buf
+
+
+def device_mask(cache, mask_func, dim, device):
+    """uint8 [dim] mask on `device`, cached per (dim, device)."""
+    k = (dim, str(device))
+    if k not in cache:
+        m = mask_func(dim)
+        if m.numel() == 1 and dim != 1:
+            m = m.expand(dim)
+        cache[k] = (m != 0).to(torch.uint8).contiguous().to(device)
+    return cache[k]

@@ -1,0 +1,88 @@
+"""Element-wise affine flow (reference: stribor/flows/affine.py:13-123).
+
+``y = x * exp(log_scale) + shift`` with parameters that are learned ``[1, dim]`` tensors, fixed
+``scale`` / ``shift`` values, or the output of ``latent_net(latent)`` split as
+``[log_scale(dim) | shift(dim)]`` (affine.py:59-67).
+"""
+from __future__ import annotations
+
+from numbers import Number
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..flow import ElementwiseTransform, run_layer, run_layer_diag
+from ._native import build_meta
+
+__all__ = ['Affine']
+
+
+class Affine(ElementwiseTransform):
+    kind = _lib.AFFINE
+    n_bins = 0
+
+    def __init__(self, dim: int, *, latent_net=None, scale=None, shift=None, **kwargs):
+        super().__init__()
+        self.dim = dim
+        self.latent_net = latent_net
+        if latent_net is None:
+            if scale is None:
+                self.log_scale = nn.Parameter(torch.empty(1, dim))
+                self.shift = nn.Parameter(torch.empty(1, dim))
+                nn.init.xavier_uniform_(self.log_scale)
+                nn.init.xavier_uniform_(self.shift)
+            else:
+                if isinstance(scale, Number):
+                    scale = torch.Tensor([scale])
+                    shift = torch.Tensor([shift])
+                assert torch.all(scale > 0), '`scale` mush have positive values'
+                # fixed values: buffers (so .to(device) moves them) kept out of the state-dict
+                self.register_buffer('log_scale', scale.log(), persistent=False)
+                self.register_buffer('shift', shift.clone(), persistent=False)
+
+    def params_per_dim(self):
+        return 2
+
+    def const_out(self):
+        """[log_scale(dim) | shift(dim)] when there is no latent_net."""
+        ls = self.log_scale.reshape(-1).expand(self.dim) if self.log_scale.numel() == 1 else self.log_scale.reshape(-1)
+        sh = self.shift.reshape(-1).expand(self.dim) if self.shift.numel() == 1 else self.shift.reshape(-1)
+        return torch.cat([ls, sh]).contiguous()
+
+    def fmeta(self):
+        return [0., 1.] * 3
+
+    def describe(self, dim, latent_dim, device):
+        """Stand-alone element-wise layer: every dim transformed, network input = latent."""
+        net = self.latent_net
+        meta, params = build_meta(self.kind, dim, latent_dim if net is not None else 0, 0, 0, self.n_bins,
+                                  1, 0, net, 0)
+        if net is None:
+            params = [self.const_out()]
+        return {'meta': meta, 'fmeta': self.fmeta(), 'mask': None, 'params': list(params), 'packed': None}
+
+    def _run(self, x, latent, direction, want_ldj=True):
+        lat = latent if self.latent_net is not None else None
+        d = self.describe(x.shape[-1], 0 if lat is None else lat.shape[-1], x.device)
+        return run_layer(d, x, lat, None, direction, want_ldj)
+
+    def forward(self, x, latent=None, **kwargs):
+        return self._run(x, latent, _lib.FORWARD, False)[0]
+
+    def inverse(self, y, latent=None, **kwargs):
+        return self._run(y, latent, _lib.INVERSE, False)[0]
+
+    def forward_and_log_det_jacobian(self, x, latent=None, *, reverse=False, **kwargs):
+        return self._run(x, latent, _lib.INVERSE if reverse else _lib.FORWARD)
+
+    def inverse_and_log_det_jacobian(self, y, latent=None, **kwargs):
+        return self._run(y, latent, _lib.INVERSE)
+
+    def log_det_jacobian(self, x, y=None, latent=None, **kwargs):
+        return self._run(x, latent, _lib.FORWARD)[1]
+
+    def log_diag_jacobian(self, x, y=None, latent=None, **kwargs):
+        lat = latent if self.latent_net is not None else None
+        d = self.describe(x.shape[-1], 0 if lat is None else lat.shape[-1], x.device)
+        return run_layer_diag(d, x, lat, None, _lib.FORWARD)[1]

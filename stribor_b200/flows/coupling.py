@@ -1,0 +1,146 @@
+"""Coupling layers (reference: stribor/flows/coupling.py).
+
+``Coupling`` (coupling.py:10-95): a mask splits the coordinates; the masked part (plus an
+optional ``latent``) feeds ``transform.latent_net`` whose output parametrises the element-wise
+``transform`` (``Affine`` or ``Spline``) applied to the other part.  Gather, conditioner MLP,
+transform and the per-row log|det J| reduction run in ONE kernel per layer.
+
+``ContinuousAffineCoupling`` (coupling.py:98-213): affine coupling whose log-scale and shift
+are multiplied by a time embedding so that t = 0 gives the identity.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..flow import Transform, run_layer
+from ..net.time_net import TimeLinear
+from ..util.mask import get_mask
+from ._native import PackedCache, build_meta, device_mask
+from .affine import Affine
+from .spline import Spline
+
+__all__ = ['Coupling', 'ContinuousAffineCoupling']
+
+
+class Coupling(Transform):
+    """
+    Args:
+        transform: ``Affine`` or ``Spline`` whose ``latent_net`` maps ``dim (+ latent)`` inputs to the
+            transform parameters.
+        mask: name from ``stribor_b200.util.mask`` -- `none`, `ordered_right_half` (right half
+            conditions, left half is transformed), `ordered_left_half`, `random_half`,
+            `parity_even`, `parity_odd`.  If ``dim = 1`` use `none`.
+        set_data: mask along dim -2 instead (not built yet).
+    """
+
+    def __init__(self, transform, mask: str, set_data: bool = False, **kwargs):
+        super().__init__()
+        if not isinstance(transform, (Affine, Spline)):
+            raise NotImplementedError(
+                f'Coupling around {type(transform).__name__} is not fused; use Affine or Spline')
+        if set_data:
+            raise NotImplementedError('set_data=True (masking along dim -2) is not built yet')
+        self.transform = transform
+        self.mask_func = get_mask(mask)
+        self.mask_name = mask
+        self.set_data = set_data
+        self._masks = {}
+        self._packed = PackedCache()
+
+    def describe(self, dim, latent_dim, device):
+        tr = self.transform
+        net = tr.latent_net
+        meta, params = build_meta(tr.kind, dim, latent_dim if net is not None else 0, 1, 0, tr.n_bins,
+                                  0, dim == 1, net, 0)
+        if net is None:
+            params = [tr.const_out()]
+        params = list(params)
+        mask = device_mask(self._masks, self.mask_func, dim, device)
+        fmeta = tr.fmeta()
+        packed = self._packed.get(meta, fmeta, mask, params) if net is not None else None
+        return {'meta': meta, 'fmeta': fmeta, 'mask': mask, 'params': params, 'packed': packed}
+
+    def _run(self, x, latent, direction, want_ldj):
+        lat = latent if self.transform.latent_net is not None else None
+        d = self.describe(x.shape[-1], 0 if lat is None else lat.shape[-1], x.device)
+        return run_layer(d, x, lat, None, direction, want_ldj)
+
+    def forward(self, x, latent=None, reverse=False, **kwargs):
+        return self._run(x, latent, _lib.INVERSE if reverse else _lib.FORWARD, False)[0]
+
+    def inverse(self, y, latent=None, **kwargs):
+        return self._run(y, latent, _lib.INVERSE, False)[0]
+
+    def log_det_jacobian(self, x, y=None, latent=None, **kwargs):
+        return self._run(x, latent, _lib.FORWARD, True)[1]
+
+    # fused versions of the inherited compositions (flow.py:35-47): same values, one kernel
+    def forward_and_log_det_jacobian(self, x, latent=None, **kwargs):
+        return self._run(x, latent, _lib.FORWARD, True)
+
+    def inverse_and_log_det_jacobian(self, y, latent=None, **kwargs):
+        return self._run(y, latent, _lib.INVERSE, True)
+
+
+class ContinuousAffineCoupling(Transform):
+    """
+    Args:
+        latent_net: maps ``[x*mask | latent | t]`` to ``2 * dim`` affine parameters
+        time_net: ``TimeLinear`` with ``2 * dim`` outputs
+        mask: mask name (see ``Coupling``)
+        concatenate_time: whether ``t`` is appended to the network input
+    """
+
+    def __init__(self, latent_net: nn.Module, time_net: nn.Module, mask: str,
+                 concatenate_time: Optional[bool] = True, **kwargs):
+        super().__init__()
+        self.latent_net = latent_net
+        self.mask_func = get_mask(mask)
+        self.mask_name = mask
+        self.time_net = time_net
+        self.concatenate_time = concatenate_time
+        self._masks = {}
+        self._packed = PackedCache()
+
+    def _time_scale(self, dim):
+        if not isinstance(self.time_net, TimeLinear):
+            raise NotImplementedError(f'time_net {type(self.time_net).__name__} is not fused; use TimeLinear')
+        s = self.time_net.scale
+        n = s.shape[-1]
+        if n == 2 * dim:
+            return s.reshape(-1)
+        if n == 2:       # chunk(2) gives [..., 1] halves that broadcast over dim (README.md:94-97)
+            return s.reshape(2, 1).expand(2, dim).reshape(-1)
+        raise ValueError(f'time_net output size {n} does not match 2 * dim = {2 * dim}')
+
+    def describe(self, dim, latent_dim, device):
+        meta, params = build_meta(_lib.CONT_AFFINE, dim, latent_dim, 1, bool(self.concatenate_time), 0,
+                                  0, dim == 1, self.latent_net, 1)
+        params = list(params) + [self._time_scale(dim).contiguous()]
+        mask = device_mask(self._masks, self.mask_func, dim, device)
+        return {'meta': meta, 'fmeta': [0., 1.] * 3, 'mask': mask, 'params': params, 'packed': None}
+
+    def _run(self, x, t, latent, direction, want_ldj):
+        if t is None:
+            raise TypeError('ContinuousAffineCoupling needs the time input `t`')
+        d = self.describe(x.shape[-1], 0 if latent is None else latent.shape[-1], x.device)
+        return run_layer(d, x, latent, t, direction, want_ldj)
+
+    def forward(self, x, t=None, latent=None, **kwargs):
+        return self._run(x, t, latent, _lib.FORWARD, False)[0]
+
+    def inverse(self, y, t=None, latent=None, **kwargs):
+        return self._run(y, t, latent, _lib.INVERSE, False)[0]
+
+    def log_det_jacobian(self, x, y=None, *, t=None, latent=None, **kwargs):
+        return self._run(x, t, latent, _lib.FORWARD, True)[1]
+
+    def forward_and_log_det_jacobian(self, x, t=None, latent=None, *, reverse=False, **kwargs):
+        return self._run(x, t, latent, _lib.INVERSE if reverse else _lib.FORWARD, True)
+
+    def inverse_and_log_det_jacobian(self, y, t=None, latent=None, **kwargs):
+        return self._run(y, t, latent, _lib.INVERSE, True)

@@ -1,0 +1,140 @@
+"""CPU: host-side logic -- masks, state-dict compatibility, descriptors, the C ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from golden_util import blob
+import stribor_b200 as st
+from stribor_b200 import _lib, _ops
+from stribor_b200.spec import layers_from_spec, spec_from_layers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_masks_match_reference_vectors():
+    for k, v in blob().items():
+        if k.startswith('mask|'):
+            _, nm, d = k.split('|')
+            assert np.array_equal(st.util.get_mask(nm)(int(d)).numpy(), v), k
+    with pytest.raises(NotImplementedError):
+        st.util.get_mask('nope')
+    g = st.util.get_mask('random_half')
+    assert torch.equal(g(10), g(10)) and g(10).sum() == 5      # frozen after the first draw
+    assert torch.equal(g(1), torch.ones(1))
+
+
+def test_state_dict_keys_match_reference_layout():
+    d = 4
+    f = st.NormalizingFlow(st.UnitNormal(d), [
+        st.Coupling(st.Spline(d, 8, latent_net=st.net.MLP(d, [16, 16], d * 23), spline_type='quadratic'),
+                    mask='ordered_right_half'),
+        st.Coupling(st.Affine(d, latent_net=st.net.MLP(d, [16], 2 * d)), mask='ordered_left_half'),
+        st.ContinuousAffineCoupling(st.net.MLP(d + 1, [8], 2 * d), st.net.TimeLinear(2 * d), 'parity_odd'),
+        st.Affine(d), st.Spline(d, 3)])
+    keys = list(f.state_dict().keys())
+    assert keys == [
+        'transforms.0.transform.latent_net.net.0.weight', 'transforms.0.transform.latent_net.net.0.bias',
+        'transforms.0.transform.latent_net.net.2.weight', 'transforms.0.transform.latent_net.net.2.bias',
+        'transforms.0.transform.latent_net.net.4.weight', 'transforms.0.transform.latent_net.net.4.bias',
+        'transforms.1.transform.latent_net.net.0.weight', 'transforms.1.transform.latent_net.net.0.bias',
+        'transforms.1.transform.latent_net.net.2.weight', 'transforms.1.transform.latent_net.net.2.bias',
+        'transforms.2.latent_net.net.0.weight', 'transforms.2.latent_net.net.0.bias',
+        'transforms.2.latent_net.net.2.weight', 'transforms.2.latent_net.net.2.bias',
+        'transforms.2.time_net.scale',
+        'transforms.3.log_scale', 'transforms.3.shift',
+        'transforms.4.width', 'transforms.4.height', 'transforms.4.derivative']
+    # last Linear bias is zero-initialised (mlp.py:53)
+    assert float(f.transforms[0].transform.latent_net.net[4].bias.abs().sum()) == 0.0
+    # fixed-scale Affine holds no state (affine.py:50-57)
+    assert list(st.Affine(2, scale=2., shift=1.).state_dict().keys()) == []
+    with pytest.raises(AssertionError):
+        st.Affine(2, scale=-1., shift=0.)
+
+
+def test_descriptor_wire_format():
+    d = 6
+    c = st.Coupling(st.Spline(d, 5, latent_net=st.net.MLP(d + 3, [7, 9], d * 14), lower=-2, upper=3,
+                              spline_type='quadratic'), mask='parity_even')
+    desc = c.describe(d, 3, 'cpu')
+    m = desc['meta']
+    assert m[:_ops.META_HEADER] == [_lib.RQS, d, 3, 1, 0, 5, 0, 0, _lib.ACTIVATIONS['Tanh'], 0, 3, 6, 0, 0]
+    assert m[_ops.META_HEADER:] == [d + 3, 7, 9, d * 14]
+    assert desc['fmeta'][:2] == [-2.0, 3.0]
+    assert desc['mask'].tolist() == [0, 1, 0, 1, 0, 1] and desc['mask'].dtype == torch.uint8
+    assert [tuple(p.shape) for p in desc['params']] == [(7, 9), (7,), (9, 7), (9,), (84, 9), (84,)]
+    L = _ops.make_struct(desc['meta'], desc['fmeta'], desc['mask'], desc['params'])
+    assert (L.kind, L.dim, L.latent_dim, L.cond_x, L.n_bins, L.net.n_linear) == (_lib.RQS, d, 3, 1, 5, 3)
+    assert list(L.net.dims)[:4] == [9, 7, 9, 84]
+    assert L.net.W[2] == desc['params'][4].data_ptr() and L.mask == desc['mask'].data_ptr()
+    # d == 1 -> conditioning zeroed (coupling.py:62-63); 'none' mask -> everything transformed
+    c1 = st.Coupling(st.Affine(1, latent_net=st.net.MLP(1, [4], 2)), mask='none')
+    d1 = c1.describe(1, 0, 'cpu')
+    assert d1['meta'][7] == 1 and d1['mask'].tolist() == [0]
+    # continuous affine: time is the last network input, TimeLinear(2) broadcasts (README.md:94-97)
+    ca = st.ContinuousAffineCoupling(st.net.MLP(4 + 1, [8], 8), st.net.TimeLinear(2), 'ordered_0')
+    dc = ca.describe(4, 0, 'cpu')
+    assert dc['meta'][0] == _lib.CONT_AFFINE and dc['meta'][4] == 1 and dc['params'][-1].shape == (8,)
+    s = ca.time_net.scale.detach().view(-1)
+    assert torch.equal(dc['params'][-1].detach(), torch.stack([s[0]] * 4 + [s[1]] * 4))
+    # unsupported conditioners fail loudly instead of silently running something else
+    with pytest.raises(NotImplementedError):
+        st.Coupling(st.Affine(2, latent_net=torch.nn.Linear(2, 4)), mask='ordered_0').describe(2, 0, 'cpu')
+    with pytest.raises(NotImplementedError):
+        st.Coupling(st.Affine(2, latent_net=st.net.MLP(2, [4], 4, activation='Hardtanh')),
+                    mask='ordered_0').describe(2, 0, 'cpu')
+    with pytest.raises(NotImplementedError):
+        st.Coupling(st.Affine(2, latent_net=st.net.MLP(2, [4], 4)), mask='ordered_0', set_data=True)
+
+
+@pytest.mark.parametrize('name', ['quadratic_d5_parity', 'cubic_d7_ordered', 'neural_flow_d16_L4',
+                                  'affine_coupling_2x10_l13', 'spline_cubic_7x4x5_k3_l0'])
+def test_spec_roundtrip(name):
+    spec = cases.build_case(name)['spec']
+    back = spec_from_layers(layers_from_spec(spec))
+
+    def flat(v):
+        if isinstance(v, torch.Tensor):
+            return [v]
+        if isinstance(v, dict):
+            return [t for k in sorted(v) for t in flat(v[k])]
+        if isinstance(v, (list, tuple)):
+            return [t for u in v for t in flat(u)]
+        return []
+    a, b = flat(spec), flat(back)
+    assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
+    assert [l['type'] for l in spec] == [l['type'] for l in back]
+
+
+def test_cpu_tensors_are_refused_not_emulated():
+    f = st.Coupling(st.Affine(4, latent_net=st.net.MLP(4, [8], 8)), mask='ordered_0')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        f(torch.randn(3, 4))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        st.NormalizingFlow(st.UnitNormal(4), [f]).log_prob(torch.randn(3, 4))
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'stribor_b200.h')).read()
+    declared = set(re.findall(r'\b(stb_[a-z_0-9]+)\s*\(', header))
+    declared -= {'stb_layer', 'stb_mlp'}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    l = _lib.lib()
+    for name in declared:
+        assert hasattr(l, name), name
+    assert l.stb_abi_version() == _lib.ABI_VERSION
+    assert l.stb_sizeof_layer() == ctypes.sizeof(_lib.StbLayer)
+    assert isinstance(l.stb_last_error(), bytes)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'stribor_b200')
+    for dp, _, fs in os.walk(pkg):
+        for fn in fs:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dp, fn)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, fn
