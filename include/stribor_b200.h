@@ -101,6 +101,8 @@ typedef struct stb_layer {
     int32_t has_box;
     int32_t reserved0;
     const uint8_t* mask;       /* device, [dim], 1 = pass through / conditions            */
+    const uint8_t* mask_host;  /* HOST copy of the mask (optional; needed by stb_pack_layer
+                                  and for the tensor-core path to be selected)            */
     const float* const_out;    /* device, network-output-shaped vector when n_linear == 0 */
     const float* row_out;      /* device, [rows, out_width]: a precomputed network output
                                   PER ROW (n_linear == 0; takes precedence over const_out) */
@@ -171,6 +173,11 @@ int stb_pack_layer(const stb_layer* layer, void* packed_out, void* stream);
 
 /* 1 if stb_layer_apply would take the tcgen05 path for this (packed) layer. */
 int stb_layer_uses_tensor_path(const stb_layer* layer);
+
+/* Bring-up check of the tcgen05 building blocks: D[128,N] = A[128,K] * B[N,K]^T on one CTA.
+ * mode bit0: 0 = fp16, 1 = tf32 operands; bit1: 3-pass hi/lo split.  variant must be 0. */
+int stb_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t mode,
+                    int32_t variant, void* stream);
 
 /* number of kernels this library has launched from the calling thread (bench bookkeeping) */
 uint64_t stb_launch_count(void);

@@ -25,7 +25,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libstribor_
 EXPORTS = ['stb_abi_version', 'stb_sizeof_layer', 'stb_last_error', 'stb_layer_apply', 'stb_layer_apply_diag', 'stb_flow_apply',
            'stb_flow_log_prob', 'stb_unit_normal_log_prob', 'stb_layer_backward_workspace_bytes',
            'stb_layer_backward', 'stb_packed_bytes', 'stb_pack_layer', 'stb_layer_uses_tensor_path',
-           'stb_launch_count']
+           'stb_launch_count', 'stb_tc_selftest']
 
 
 class StbMlp(C.Structure):
@@ -41,7 +41,7 @@ class StbLayer(C.Structure):
                 ('lower', C.c_float), ('upper', C.c_float),
                 ('left', C.c_float), ('right', C.c_float), ('bottom', C.c_float), ('top', C.c_float),
                 ('has_box', C.c_int32), ('reserved0', C.c_int32),
-                ('mask', C.c_void_p), ('const_out', C.c_void_p), ('row_out', C.c_void_p),
+                ('mask', C.c_void_p), ('mask_host', C.c_void_p), ('const_out', C.c_void_p), ('row_out', C.c_void_p),
                 ('time_scale', C.c_void_p),
                 ('net', StbMlp), ('packed', C.c_void_p), ('packed_bytes', C.c_uint64)]
 
@@ -94,6 +94,8 @@ def lib():
     l.stb_pack_layer.argtypes = [LP, vp, vp]
     l.stb_layer_uses_tensor_path.restype = i32
     l.stb_layer_uses_tensor_path.argtypes = [LP]
+    l.stb_tc_selftest.restype = i32
+    l.stb_tc_selftest.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     l.stb_sizeof_layer.restype = u64
     if l.stb_sizeof_layer() != C.sizeof(StbLayer):
         raise StriborB200Error(f'stb_layer layout mismatch: C {l.stb_sizeof_layer()} vs ctypes {C.sizeof(StbLayer)}')

@@ -10,7 +10,8 @@ libstribor_b200.so.  Three ops:
 
 A layer is described by plain data so that it can cross the op boundary:
   meta  = [kind, dim, latent_dim, cond_x, time_input, n_bins, inverse_ldj_own, zero_cond,
-           activation, final_activation, n_linear, n_params, has_box, row_mode, dims[0..n_linear]]
+           activation, final_activation, n_linear, n_params, has_box, row_mode, dims[0..n_linear],
+           mask[0..dim) (only when cond_x)]
   fmeta = [lower, upper, left, right, bottom, top]
   params = [W0, b0, W1, b1, ...] (+ [time_scale]) or [const_out]   (row_mode: const_out is a
            per-row [rows, out_width] tensor -> stb_layer.row_out)
@@ -56,6 +57,13 @@ def _fill_struct(L: _lib.StbLayer, meta: Sequence[int], fmeta: Sequence[float], 
     L.left, L.right, L.bottom, L.top = (float(v) for v in fmeta[2:6])
     L.has_box = has_box
     L.mask = _dp(mask)
+    keep = None
+    if cond_x:
+        off = META_HEADER + (n_linear + 1 if n_linear > 0 else 0)
+        keep = (C.c_uint8 * dim)(*meta[off:off + dim])
+        L.mask_host = C.cast(keep, C.c_void_p)
+    else:
+        L.mask_host = None
     L.net.n_linear = n_linear
     L.net.activation = act
     L.net.final_activation = fact
@@ -85,17 +93,18 @@ def _fill_struct(L: _lib.StbLayer, meta: Sequence[int], fmeta: Sequence[float], 
     else:
         L.packed = None
         L.packed_bytes = 0
+    return keep
 
 
 def make_struct(meta, fmeta, mask, params, packed=None) -> _lib.StbLayer:
     L = _lib.StbLayer()
-    _fill_struct(L, meta, fmeta, mask, params, packed)
+    L._keepalive = _fill_struct(L, meta, fmeta, mask, params, packed)
     return L
 
 
 def meta_len(meta: Sequence[int], off: int = 0) -> int:
     n_linear = meta[off + 10]
-    return META_HEADER + (n_linear + 1 if n_linear > 0 else 0)
+    return META_HEADER + (n_linear + 1 if n_linear > 0 else 0) + (meta[off + 1] if meta[off + 3] else 0)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -240,12 +249,14 @@ def flow_chain(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], masks: 
     if rows == 0:
         return out, ldj
     arr = (_lib.StbLayer * n_layers)()
+    keep = []
     mo = po = 0
     for i in range(n_layers):
         ml = meta_len(meta, mo)
         m = meta[mo:mo + ml]
         npar = m[11]
-        _fill_struct(arr[i], m, fmeta[FMETA_LEN * i:FMETA_LEN * (i + 1)], masks[i], params[po:po + npar], packed[i])
+        keep.append(_fill_struct(arr[i], m, fmeta[FMETA_LEN * i:FMETA_LEN * (i + 1)], masks[i],
+                                 params[po:po + npar], packed[i]))
         mo += ml
         po += npar
     lib = _lib.lib()

@@ -1,11 +1,758 @@
-// tcgen05 / TMA path -- placeholder until the tensor-core kernel lands: reports "unsupported"
-// so every layer takes the generic path.
+// Tensor-core fused coupling layer for sm_100a (tcgen05 + TMEM + bulk-async copies).
+//
+// Scope of this kernel: st.Coupling(st.Spline(dim <= 64, n_bins = 16, 'quadratic' | 'cubic',
+// latent_net = MLP(dim, [64], dim * P)), mask) without latent input -- the BASELINE.json headline
+// configuration (8 of these layers, d = 64).  Everything else runs on generic_layer.cu.
+//
+// One persistent CTA per SM, 12 warps, tiles of 256 rows handled as two 128-row subtiles:
+//   warp 0      producer: streams the packed last-Linear weights (24 KB chunks = 2 transformed
+//               dims x 48 padded parameters x 64, fp16 hi | lo) L2 -> smem with cp.async.bulk
+//               through a 3-stage mbarrier ring
+//   warp 1      UMMA issuer (one lane): GEMM1  [128 x 32] x [32 x 64]  as 3xTF32 (x has fp32
+//               range), GEMM2 [128 x 64] x [64 x 96] per chunk as 3 fp16 passes
+//               (hi*hi + lo*hi + hi*lo: fp32-grade products at fp16 tensor rate); accumulators
+//               live in TMEM: 2 x 64 columns for GEMM1, 2 subtiles x 2 buffers x 96 for GEMM2
+//   warp 2      TMEM allocation
+//   warps 4-11  epilogue: warp (s, q) owns rows 32q..32q+31 of subtile s == TMEM lanes of
+//               sub-partition q; a thread is one row.  They stage the x tile, build the A
+//               operands (mask gather + hi/lo split), apply tanh to GEMM1's accumulator, and for
+//               each chunk pull 48 parameters per transformed dim out of TMEM with tcgen05.ld and
+//               evaluate the spline in registers, accumulating log|det J| per row.
+// Per layer each row makes one HBM round trip (read y, write x, read/write ldj).
+//
+// Reference semantics restated here: flows/coupling.py:53-95, flows/spline.py:76-105,
+// util/rational_quadratic_spline.py, util/cubic_spline.py, net/mlp.py:46-58, flow.py:42-47.
 #include "common.cuh"
+#include "stb_math.cuh"
+#include "tc_common.cuh"
+
 namespace stb {
-bool tc_layer_supported(const stb_layer*) { return false; }
-uint64_t tc_packed_bytes(const stb_layer*) { return 0; }
-int tc_pack_layer(const stb_layer*, void*, cudaStream_t) { return set_error(STB_ENOTSUP, "tensor path not built"); }
-int tc_layer_apply(const stb_layer*, int, const float*, float*, float*, int, int, int64_t, cudaStream_t) {
-    return set_error(STB_ENOTSUP, "tensor path not built");
+using namespace tc;
+
+namespace tcl {
+
+constexpr int kHid = 64;             // hidden width
+constexpr int kK1 = 32;              // padded number of conditioning columns (GEMM1 K)
+constexpr int kBins = 16;
+constexpr int kPPad = 48;            // parameters per dim, padded (47 rqs / 34 cubic)
+constexpr int kG = 2;                // transformed dims per weight chunk
+constexpr int kChunkN = kG * kPPad;  // 96 = UMMA N of GEMM2
+constexpr int kMaxDim = 64;
+constexpr int kMaxTr = 32;
+constexpr int kMaxChunks = kMaxTr / kG;
+constexpr int kTileRows = 256;
+constexpr int kXsStride = kMaxDim + 1;
+constexpr int kStages = 3;
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
+
+// packed image (global memory, built by tc_pack_layer)
+constexpr uint32_t kMagic = 0x53544231u;
+struct Header {                      // 1024 bytes
+    uint32_t magic;
+    int32_t kind, dim, n_cond, n_tr, n_chunks, P, act;
+    float s2;                        // power-of-two scale of the packed last-Linear weights
+    uint32_t maxbits;                // scratch: max |W2| as uint bits
+    int32_t cond_idx[kK1];
+    int32_t tr_idx[kMaxTr];
+    int32_t pad[256 - 10 - kK1 - kMaxTr];
+};
+static_assert(sizeof(Header) == 1024, "header layout");
+constexpr uint32_t kOffB1 = 1024;                                  // float[64]
+constexpr uint32_t kOffB2 = kOffB1 + kHid * 4;                     // float[kMaxChunks * 96]
+constexpr uint32_t kSmallBytes = kOffB2 + kMaxChunks * kChunkN * 4;    // 7424
+constexpr uint32_t kOffW1 = 8192;                                  // tf32 hi (8 KB) | lo (8 KB)
+constexpr uint32_t kW1Bytes = 2 * kHid * kK1 * 4;                  // 16384
+constexpr uint32_t kOffW2 = kOffW1 + kW1Bytes;                     // chunks of 24576 B
+constexpr uint32_t kChunkBytes = 2 * kChunkN * kHid * 2;           // fp16 hi (12 KB) | lo (12 KB)
+constexpr uint32_t kPackedBytes = kOffW2 + kMaxChunks * kChunkBytes;
+
+// shared memory map
+constexpr uint32_t kSmXs = 0;                                      // float [256][65]
+constexpr uint32_t kSmA = kSmXs + kTileRows * kXsStride * 4;       // 2 x 32 KB (A1 tf32 / h fp16, hi | lo)
+constexpr uint32_t kABytes = 32768;
+constexpr uint32_t kSmW1 = kSmA + 2 * kABytes;
+constexpr uint32_t kSmB = kSmW1 + kW1Bytes;
+constexpr uint32_t kSmSmall = kSmB + kStages * kChunkBytes;
+constexpr uint32_t kSmBar = (kSmSmall + kSmallBytes + 15) & ~15u;
+constexpr uint32_t kSmemBytes = kSmBar + 256;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(kSmA % 16 == 0 && kSmW1 % 16 == 0 && kSmB % 16 == 0 && kSmSmall % 16 == 0, "alignment");
+
+struct Bars {
+    uint64_t setup;
+    uint64_t b_full[kStages], b_empty[kStages];
+    uint64_t a1_ready[2], acc1_full[2], h_ready[2];
+    uint64_t acc_full[2][2], acc_empty[2][2];
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Bars) <= 256, "barrier block");
+
+// TMEM columns
+constexpr uint32_t kColAcc1 = 0;                 // + s * 64
+constexpr uint32_t kColAcc2 = 128;               // + (s * 2 + buf) * 96
+constexpr uint32_t kTmemCols = 512;
+
+struct Args {
+    const uint8_t* packed;
+    const float* x;
+    float* y;
+    float* ldj;
+    int ldj_mode;
+    int base_log_prob;
+    int inverse;
+    float lower, upper;
+    long long rows;
+    int n_tiles;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// -----------------------------------------------------------------------------------------------
+// spline evaluation with the 48 parameters of one element in registers
+// -----------------------------------------------------------------------------------------------
+// u[0..16) unnormalised -> u[i] = min_size + (1 - 16 min_size) * softmax_i, every quotient
+// e_i / sum refined to (almost) correctly rounded: the knots are cumulative sums of these and
+// their error is amplified by 1 / bin-width in the log-derivative.
+__device__ __forceinline__ void softmax16_bins(float* u, float min_size) {
+    float m = u[0];
+#pragma unroll
+    for (int i = 1; i < kBins; ++i) m = fmaxf(m, u[i]);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kBins; ++i) {
+        u[i] = expf(u[i] - m);
+        s += u[i];
+    }
+    const float inv = __frcp_rn(s);
+    const float scale = 1.f - min_size * (float)kBins;
+#pragma unroll
+    for (int i = 0; i < kBins; ++i) {
+        float q = u[i] * inv;
+        q = fmaf(fmaf(-q, s, u[i]), inv, q);         // one Newton step on the quotient
+        u[i] = fmaf(scale, q, min_size);
+    }
+}
+
+struct RqsSel {
+    float xk, xk1, yk, yk1, u0, u1;
+};
+
+// Walk the 17 knots of both axes; select the bin that holds `key` on the searched axis.
+// w[i], h[i]: normalised bin sizes; d[i]: K-1 unconstrained interior derivatives.
+// search_sorted.py:3-5 semantics: bin = #(key >= knot_i) - 1 with the last knot nudged by 1e-6.
+__device__ __forceinline__ RqsSel rqs16_walk(const float* w, const float* h, const float* d, float lo,
+                                             float hi, bool on_heights, float key) {
+    const float span = hi - lo;
+    RqsSel r;
+    r.xk = lo; r.yk = lo; r.u0 = STB_RQS_EDGE_CONST;
+    r.xk1 = hi; r.yk1 = hi; r.u1 = STB_RQS_EDGE_CONST;
+    float cw = 0.f, ch = 0.f;
+    bool prev = true;                            // key >= knot_0 for an inside key
+#pragma unroll
+    for (int i = 1; i <= kBins; ++i) {
+        cw += w[i - 1];
+        ch += h[i - 1];
+        const float kw = (i == kBins) ? hi : fmaf(span, cw, lo);       // knots forced to the box
+        const float kh = (i == kBins) ? hi : fmaf(span, ch, lo);
+        const float kk = on_heights ? kh : kw;
+        const bool ge = (i == kBins) ? (key >= kk + 1e-6f) : (key >= kk);
+        const float ud = (i == kBins) ? STB_RQS_EDGE_CONST : d[i - 1];   // derivative param AT knot i
+        if (ge) { r.xk = kw; r.yk = kh; r.u0 = ud; }
+        if (prev && !ge) { r.xk1 = kw; r.yk1 = kh; r.u1 = ud; }
+        prev = ge;
+    }
+    return r;
+}
+
+__device__ __forceinline__ RqsBin rqs16_bin(const RqsSel& s) {
+    RqsBin b;
+    b.xk = s.xk; b.wk = s.xk1 - s.xk;
+    b.yk = s.yk; b.hk = s.yk1 - s.yk;
+    b.delta = b.hk / b.wk;
+    b.d0 = STB_RQS_MIN + softplus_f(s.u0);
+    b.d1 = STB_RQS_MIN + softplus_f(s.u1);
+    return b;
+}
+
+// p[0..48): raw conditioner outputs [w(16) | h(16) | d(15) | pad].  Same contract as rqs_element
+// with own_ld = false (Coupling semantics).
+__device__ __forceinline__ void rqs16_element(float* p, float lo, float hi, bool inverse, bool want_ld,
+                                              float x, float& out, float& ld) {
+    out = x;
+    ld = 0.f;
+    if (!(x >= lo && x <= hi)) return;
+    float* w = p;
+    float* h = p + kBins;
+    const float* d = p + 2 * kBins;
+    softmax16_bins(w, STB_RQS_MIN);
+    softmax16_bins(h, STB_RQS_MIN);
+    if (!inverse) {
+        const RqsBin b = rqs16_bin(rqs16_walk(w, h, d, lo, hi, false, x));
+        rqs_forward_in_bin(b, x, out, ld);
+    } else {
+        const RqsSel sel = rqs16_walk(w, h, d, lo, hi, true, x);
+        const RqsBin b = rqs16_bin(sel);
+        float ld_own;
+        rqs_inverse_in_bin(b, x, out, ld_own);
+        if (want_ld) {
+            // -(forward log-derivative at the recovered point), flow.py:42-47
+            if (out >= lo && out <= hi) {
+                // bin K-1: its upper knot is the nudged one (search_sorted.py:4)
+                const bool same = (out >= sel.xk) && ((sel.xk1 == hi) ? (out < hi + 1e-6f) : (out < sel.xk1));
+                float y2, ldf;
+                if (same) {
+                    rqs_forward_in_bin(b, out, y2, ldf);
+                } else {                                       // rounding moved it to a neighbour bin
+                    const RqsBin b2 = rqs16_bin(rqs16_walk(w, h, d, lo, hi, false, out));
+                    rqs_forward_in_bin(b2, out, y2, ldf);
+                }
+                ld = -ldf;
+            }
+        }
+    }
+}
+
+struct CubSel {
+    float wp, wk, wn, hp, hk, hn, cw, ch;
+    int k;
+};
+
+// cubic_spline.py:140-151 bin search by running cumulative sums + neighbour gather
+__device__ __forceinline__ CubSel cubic16_walk(const float* w, const float* h, bool on_heights, float key) {
+    CubSel r;
+    r.k = 0; r.cw = 0.f; r.ch = 0.f;
+    r.wp = 0.f; r.hp = 0.f; r.wk = w[0]; r.hk = h[0]; r.wn = w[1]; r.hn = h[1];
+    float aw = 0.f, ah = 0.f;
+#pragma unroll
+    for (int i = 1; i < kBins; ++i) {
+        aw += w[i - 1];
+        ah += h[i - 1];
+        const bool ge = key >= (on_heights ? ah : aw);
+        if (ge) {
+            r.k = i; r.cw = aw; r.ch = ah;
+            r.wp = w[i - 1]; r.hp = h[i - 1]; r.wk = w[i]; r.hk = h[i];
+            r.wn = (i + 1 < kBins) ? w[i + 1] : 0.f;
+            r.hn = (i + 1 < kBins) ? h[i + 1] : 0.f;
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float ur) {
+    const float sk = s.hk / s.wk;
+    float dl, dr;
+    if (s.k == 0) {
+        dl = sigmoid_f(ul) * 3.f * sk;
+    } else {
+        const float sp = s.hp / s.wp;
+        dl = fminf(fminf(fabsf(sp), fabsf(sk)), 0.5f * (s.wk * sp + s.wp * sk) / (s.wp + s.wk)) *
+             (sign_f(sp) + sign_f(sk));
+    }
+    if (s.k == kBins - 1) {
+        dr = sigmoid_f(ur) * 3.f * sk;
+    } else {
+        const float sn = s.hn / s.wn;
+        dr = fminf(fminf(fabsf(sk), fabsf(sn)), 0.5f * (s.wn * sk + s.wk * sn) / (s.wk + s.wn)) *
+             (sign_f(sk) + sign_f(sn));
+    }
+    CubBin r;
+    r.a = (dl + dr - 2.f * sk) / (s.wk * s.wk);
+    r.b = (3.f * sk - 2.f * dl - dr) / s.wk;
+    r.c = dl;
+    r.d = s.ch;
+    r.xl = s.cw;
+    r.xr = (s.k == kBins - 1) ? 1.f : s.cw + s.wk;
+    return r;
+}
+
+// p[0..48): [w(16) | h(16) | left, right | pad]
+__device__ __forceinline__ void cubic16_element(float* p, float lo, float hi, bool inverse, bool want_ld,
+                                                float x, float& out, float& ld) {
+    out = x;
+    ld = 0.f;
+    if (!(x >= lo && x <= hi)) return;
+    float* w = p;
+    float* h = p + kBins;
+    const float ul = p[2 * kBins], ur = p[2 * kBins + 1];
+    softmax16_bins(w, STB_CUB_MIN);
+    softmax16_bins(h, STB_CUB_MIN);
+    const float span = hi - lo;
+    const float u = (x - lo) / span;
+    if (!inverse) {
+        const CubBin b = cubic16_bin(cubic16_walk(w, h, false, u), ul, ur);
+        out = cubic_forward_in_bin(b, u, ld) * span + lo;
+    } else {
+        const CubSel s = cubic16_walk(w, h, true, u);
+        const CubBin b = cubic16_bin(s, ul, ur);
+        float ld_own;
+        out = cubic_inverse_in_bin(b, u, ld_own) * span + lo;
+        if (want_ld && out >= lo && out <= hi) {
+            const float u2 = (out - lo) / span;
+            const bool same = (u2 >= b.xl) && (s.k == kBins - 1 || u2 < b.xr);
+            float ldf;
+            if (same) {
+                (void)cubic_forward_in_bin(b, u2, ldf);
+            } else {
+                const CubBin b2 = cubic16_bin(cubic16_walk(w, h, false, u2), ul, ur);
+                (void)cubic_forward_in_bin(b2, u2, ldf);
+            }
+            ld = -ldf;
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// the kernel
+// -----------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* xs = reinterpret_cast<float*>(smem + kSmXs);
+    uint8_t* abuf = smem + kSmA;
+    uint8_t* w1s = smem + kSmW1;
+    uint8_t* bst = smem + kSmB;
+    const Header* hdr = reinterpret_cast<const Header*>(smem + kSmSmall);
+    const float* b1s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB1);
+    const float* b2s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB2);
+    Bars* bars = reinterpret_cast<Bars*>(smem + kSmBar);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // ---- one-time setup ------------------------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&bars->setup, 1);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->a1_ready[s], 4);
+            mbar_init(&bars->acc1_full[s], 1);
+            mbar_init(&bars->h_ready[s], 4);
+            for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[s][b], 1); mbar_init(&bars->acc_empty[s][b], 4); }
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(&bars->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (tid == 0) {                               // header + biases + packed first Linear
+        mbar_arrive_expect_tx(&bars->setup, kSmallBytes + kW1Bytes);
+        bulk_g2s(smem + kSmSmall, A.packed, kSmallBytes, &bars->setup);
+        bulk_g2s(w1s, A.packed + kOffW1, kW1Bytes, &bars->setup);
+    }
+    mbar_wait(&bars->setup, 0);
+
+    const int d = hdr->dim, n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_chunks = hdr->n_chunks;
+    const int act = hdr->act;
+    const float s2 = hdr->s2;
+    const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        // ======================= producer: last-Linear weight chunks =============================
+        if (lane == 0) {
+            uint32_t cc = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int c = 0; c < n_chunks; ++c, ++cc) {
+                    const uint32_t st = cc % kStages, use = cc / kStages;
+                    mbar_wait(&bars->b_empty[st], (use & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->b_full[st], kChunkBytes);
+                    bulk_g2s(bst + st * kChunkBytes, A.packed + kOffW2 + (size_t)c * kChunkBytes, kChunkBytes,
+                             &bars->b_full[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= UMMA issuer =====================================================
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(FMT_TF32, 128, kHid);
+            const uint32_t idesc2 = make_idesc(FMT_F16, 128, kChunkN);
+            uint32_t cc = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const uint32_t tpar = it & 1;
+                for (int s = 0; s < 2; ++s) {      // GEMM1: conditioning columns -> hidden pre-activation
+                    mbar_wait(&bars->a1_ready[s], tpar);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(abuf + s * kABytes), a_lo = a_hi + 16384;
+                    const uint32_t b_hi = smem_u32(w1s), b_lo = b_hi + 8192;
+                    const uint32_t dcol = tmem + kColAcc1 + s * kHid;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const uint32_t aa = (p == 1) ? a_lo : a_hi, bb = (p == 2) ? b_lo : b_hi;
+#pragma unroll
+                        for (int ks = 0; ks < kK1 / 8; ++ks) {
+                            umma_tf32(dcol, make_smem_desc(aa + ks * 256, 128, 1024),
+                                      make_smem_desc(bb + ks * 256, 128, 1024), idesc1, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&bars->acc1_full[s]);
+                }
+                for (int c = 0; c < n_chunks; ++c, ++cc) {
+                    const uint32_t st = cc % kStages, use = cc / kStages;
+                    mbar_wait(&bars->b_full[st], use & 1);
+                    const uint32_t buf = cc & 1, buse = cc >> 1;
+                    for (int s = 0; s < 2; ++s) {
+                        if (c == 0) mbar_wait(&bars->h_ready[s], tpar);
+                        mbar_wait(&bars->acc_empty[s][buf], (buse & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(abuf + s * kABytes), a_lo = a_hi + 16384;
+                        const uint32_t b_hi = smem_u32(bst + st * kChunkBytes), b_lo = b_hi + 12288;
+                        const uint32_t dcol = tmem + kColAcc2 + (s * 2 + buf) * kChunkN;
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) {
+                            const uint32_t aa = (p == 1) ? a_lo : a_hi, bb = (p == 2) ? b_lo : b_hi;
+#pragma unroll
+                            for (int ks = 0; ks < kHid / 16; ++ks) {
+                                umma_f16(dcol, make_smem_desc(aa + ks * 256, 128, 1024),
+                                         make_smem_desc(bb + ks * 256, 128, 1024), idesc2, acc);
+                                acc = 1;
+                            }
+                        }
+                        umma_commit(&bars->acc_full[s][buf]);
+                    }
+                    umma_commit(&bars->b_empty[st]);       // stage reusable once both subtiles' UMMAs retire
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ======================= epilogue warps ==================================================
+        const int e = warp - 4, s = e >> 2, q = warp & 3;       // q == TMEM sub-partition of this warp
+        const int etid = tid - 128;
+        const int rloc = q * 32 + lane;                         // row within the subtile
+        const int rt = s * 128 + rloc;                          // row within the tile
+        float* xrow = xs + rt * kXsStride;
+        uint8_t* a_s = abuf + s * kABytes;
+        const uint32_t a_row_off = (uint32_t)(rloc >> 3) * 1024 + (uint32_t)(rloc & 7) * 16;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const bool inverse = A.inverse != 0;
+        const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
+        uint32_t cc = 0;
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long row0 = tile * kTileRows;
+            const int nrows = (int)min((long long)kTileRows, A.rows - row0);
+            const uint32_t tpar = it & 1;
+
+            // ---- stage the x tile: coalesced global reads -> padded row-major smem ----------------
+            {
+                const float* xg = A.x + row0 * d;
+                const int n = nrows * d;
+                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0)) {
+                    const int n4 = (kTileRows * d) >> 2;
+                    for (int i0 = etid; i0 < n4; i0 += kEpiThreads * 4) {
+                        float4 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * kEpiThreads;
+                            v[u] = (i < n4 && i * 4 < n) ? __ldg(reinterpret_cast<const float4*>(xg) + i)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * kEpiThreads;
+                            if (i < n4) {
+                                const int r = (i * 4) / d, c = (i * 4) - r * d;
+                                float* dst = xs + r * kXsStride + c;
+                                dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;
+                            }
+                        }
+                    }
+                } else {
+                    for (int i = etid; i < kTileRows * d; i += kEpiThreads) {
+                        const int r = i / d, c = i - r * d;
+                        xs[r * kXsStride + c] = (i < n) ? __ldg(xg + i) : 0.f;
+                    }
+                }
+            }
+            named_bar_sync(1, kEpiThreads);
+
+            // ---- A1: this row's conditioning columns, tf32 hi | lo, core-matrix layout -------------
+            {
+#pragma unroll
+                for (int kc = 0; kc < kK1 / 4; ++kc) {
+                    float hi[4], lo[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = kc * 4 + u;
+                        const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : 0.f;
+                        split_tf32(v, hi[u], lo[u]);
+                    }
+                    *reinterpret_cast<float4*>(a_s + a_row_off + kc * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(a_s + 16384 + a_row_off + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a1_ready[s]);
+            }
+
+            // ---- hidden layer: h = act(acc1 + b1) -> fp16 hi | lo A operand of GEMM2 ---------------
+            mbar_wait(&bars->acc1_full[s], tpar);
+            tc_fence_after();
+            {
+#pragma unroll
+                for (int c0 = 0; c0 < kHid; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem + lane_sel + kColAcc1 + s * kHid + c0, v);
+                    tmem_ld_wait();
+                    __half hh[16], hl[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) split_f16(activate(act, v[i] + b1s[c0 + i]), hh[i], hl[i]);
+#pragma unroll
+                    for (int half8 = 0; half8 < 2; ++half8) {
+                        const int kc = (c0 >> 3) + half8;
+                        uint4 ph, pl;
+                        const __half2* h2 = reinterpret_cast<const __half2*>(hh + half8 * 8);
+                        const __half2* l2 = reinterpret_cast<const __half2*>(hl + half8 * 8);
+                        ph.x = *reinterpret_cast<const uint32_t*>(&h2[0]); ph.y = *reinterpret_cast<const uint32_t*>(&h2[1]);
+                        ph.z = *reinterpret_cast<const uint32_t*>(&h2[2]); ph.w = *reinterpret_cast<const uint32_t*>(&h2[3]);
+                        pl.x = *reinterpret_cast<const uint32_t*>(&l2[0]); pl.y = *reinterpret_cast<const uint32_t*>(&l2[1]);
+                        pl.z = *reinterpret_cast<const uint32_t*>(&l2[2]); pl.w = *reinterpret_cast<const uint32_t*>(&l2[3]);
+                        *reinterpret_cast<uint4*>(a_s + a_row_off + kc * 128) = ph;
+                        *reinterpret_cast<uint4*>(a_s + 16384 + a_row_off + kc * 128) = pl;
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->h_ready[s]);
+            }
+
+            // ---- last Linear chunks out of TMEM + spline in registers ---------------------------------
+            float ld_acc = 0.f;
+            for (int c = 0; c < n_chunks; ++c, ++cc) {
+                const uint32_t buf = cc & 1, buse = cc >> 1;
+                mbar_wait(&bars->acc_full[s][buf], buse & 1);
+                tc_fence_after();
+                const uint32_t col0 = tmem + lane_sel + kColAcc2 + (s * 2 + buf) * kChunkN;
+#pragma unroll 1
+                for (int g = 0; g < kG; ++g) {
+                    const int ji = c * kG + g;
+                    float p[kPPad];
+                    tmem_ld16(col0 + g * kPPad, p);
+                    tmem_ld16(col0 + g * kPPad + 16, p + 16);
+                    tmem_ld16(col0 + g * kPPad + 32, p + 32);
+                    tmem_ld_wait();
+                    if (ji < n_tr) {
+                        const float* bb = b2s + (c * kG + g) * kPPad;
+#pragma unroll
+                        for (int i = 0; i < kPPad; ++i) p[i] = fmaf(p[i], s2, bb[i]);
+                        const int j = hdr->tr_idx[ji];
+                        float out, ld;
+                        if (KIND == STB_RQS) rqs16_element(p, A.lower, A.upper, inverse, want_ld, xrow[j], out, ld);
+                        else cubic16_element(p, A.lower, A.upper, inverse, want_ld, xrow[j], out, ld);
+                        xrow[j] = out;
+                        ld_acc += ld;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[s][buf]);
+            }
+
+            // ---- per-row log|det J| (+ UnitNormal log-density of the output row) ------------------------
+            if (A.base_log_prob) {
+                float b = 0.f;
+                for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
+                ld_acc += b;
+            }
+            if (want_ld && rt < nrows) {
+                float* dst = A.ldj + row0 + rt;
+                *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + ld_acc) : ld_acc;
+            }
+            named_bar_sync(1, kEpiThreads);
+
+            // ---- y tile out (coalesced) --------------------------------------------------------------------
+            {
+                float* yg = A.y + row0 * d;
+                const int n = nrows * d;
+                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
+                    const int n4 = n >> 2;
+                    for (int i = etid; i < n4; i += kEpiThreads) {
+                        const int r = (i * 4) / d, c = (i * 4) - r * d;
+                        const float* src = xs + r * kXsStride + c;
+                        reinterpret_cast<float4*>(yg)[i] = make_float4(src[0], src[1], src[2], src[3]);
+                    }
+                } else {
+                    for (int i = etid; i < n; i += kEpiThreads) {
+                        const int r = i / d, c = i - r * d;
+                        yg[i] = xs[r * kXsStride + c];
+                    }
+                }
+            }
+            named_bar_sync(1, kEpiThreads);
+        }
+    }
+
+    // ---- teardown --------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+}
+
+// -----------------------------------------------------------------------------------------------
+// packing
+// -----------------------------------------------------------------------------------------------
+struct PackArgs {
+    const float *W1, *b1, *W2, *b2;
+    uint8_t* out;
+    int kind, dim, n_cond, n_tr, n_chunks, P, act;
+    int cond_idx[kK1];
+    int tr_idx[kMaxTr];
+};
+
+__global__ void tc_maxabs_kernel(const PackArgs a) {
+    float m = 0.f;
+    const int total = a.n_tr * a.P * kHid;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i % kHid, rp = i / kHid, p = rp % a.P, ji = rp / a.P;
+        m = fmaxf(m, fabsf(a.W2[((size_t)a.tr_idx[ji] * a.P + p) * kHid + k]));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&reinterpret_cast<Header*>(a.out)->maxbits, __float_as_uint(m));
+}
+
+__device__ __forceinline__ uint32_t core_off(int r, int k, int K, int elem) {
+    const int epc = 16 / elem, chunks = K / epc;
+    return (uint32_t)((r >> 3) * (chunks * 128) + (k / epc) * 128 + (r & 7) * 16 + (k % epc) * elem);
+}
+
+__global__ void tc_pack_kernel(const PackArgs a) {
+    Header* hdr = reinterpret_cast<Header*>(a.out);
+    const float mx = __uint_as_float(hdr->maxbits);
+    // power of two >= max |W2|, so W2 / s2 is exact and within [-1, 1]
+    float s2 = 1.f;
+    if (mx > 0.f && isfinite(mx)) {
+        int ex;
+        const float fr = frexpf(mx, &ex);            // mx = fr * 2^ex, fr in [0.5, 1)
+        s2 = ldexpf(1.f, (fr == 0.5f) ? ex - 1 : ex);
+    }
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (gtid == 0) {
+        hdr->magic = kMagic; hdr->kind = a.kind; hdr->dim = a.dim; hdr->n_cond = a.n_cond; hdr->n_tr = a.n_tr;
+        hdr->n_chunks = a.n_chunks; hdr->P = a.P; hdr->act = a.act; hdr->s2 = s2;
+        for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
+        for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
+    }
+    float* b1 = reinterpret_cast<float*>(a.out + kOffB1);
+    float* b2 = reinterpret_cast<float*>(a.out + kOffB2);
+    for (int i = gtid; i < kHid; i += gsz) b1[i] = a.b1[i];
+    for (int i = gtid; i < kMaxChunks * kChunkN; i += gsz) {
+        const int ji = i / kPPad, p = i % kPPad;
+        b2[i] = (ji < a.n_tr && p < a.P) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
+    }
+    // first Linear, conditioning columns only: [64][32] tf32 hi | lo
+    for (int i = gtid; i < kHid * kK1; i += gsz) {
+        const int n = i / kK1, k = i % kK1;
+        const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.dim + a.cond_idx[k]] : 0.f;
+        float hi, lo;
+        split_tf32(v, hi, lo);
+        const uint32_t off = core_off(n, k, kK1, 4);
+        *reinterpret_cast<float*>(a.out + kOffW1 + off) = hi;
+        *reinterpret_cast<float*>(a.out + kOffW1 + 8192 + off) = lo;
+    }
+    // last Linear, rows of the transformed dims, padded to 48 per dim, 2 dims per chunk
+    const float inv = 1.f / s2;
+    for (int i = gtid; i < kMaxChunks * kChunkN * kHid; i += gsz) {
+        const int k = i % kHid, rn = i / kHid, n = rn % kChunkN, c = rn / kChunkN;
+        const int ji = c * kG + n / kPPad, p = n % kPPad;
+        float v = 0.f;
+        if (c < a.n_chunks && ji < a.n_tr && p < a.P) v = a.W2[((size_t)a.tr_idx[ji] * a.P + p) * kHid + k] * inv;
+        __half hi, lo;
+        split_f16(v, hi, lo);
+        const uint32_t off = kOffW2 + (uint32_t)c * kChunkBytes + core_off(n, k, kHid, 2);
+        *reinterpret_cast<__half*>(a.out + off) = hi;
+        *reinterpret_cast<__half*>(a.out + off + 12288) = lo;
+    }
+}
+
+static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
+    if (!L->mask_host) return false;
+    a.n_cond = a.n_tr = 0;
+    for (int j = 0; j < L->dim; ++j) {
+        if (L->mask_host[j]) { if (a.n_cond >= kK1) return false; a.cond_idx[a.n_cond++] = j; }
+        else { if (a.n_tr >= kMaxTr) return false; a.tr_idx[a.n_tr++] = j; }
+    }
+    for (int i = a.n_cond; i < kK1; ++i) a.cond_idx[i] = 0;
+    for (int i = a.n_tr; i < kMaxTr; ++i) a.tr_idx[i] = 0;
+    if (a.n_tr < 1) return false;
+    a.n_chunks = (a.n_tr + kG - 1) / kG;
+    a.kind = L->kind; a.dim = L->dim; a.P = L->kind == STB_RQS ? 3 * kBins - 1 : 2 * kBins + 2;
+    a.act = L->net.activation;
+    a.W1 = L->net.W[0]; a.b1 = L->net.b[0]; a.W2 = L->net.W[1]; a.b2 = L->net.b[1];
+    return true;
+}
+
+}  // namespace tcl
+
+bool tc_layer_supported(const stb_layer* L) {
+    using namespace tcl;
+    if (L->kind != STB_RQS && L->kind != STB_CUBIC) return false;
+    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim != 0 || L->time_input) return false;
+    if (L->has_box || L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
+    const stb_mlp& N = L->net;
+    if (N.n_linear != 2 || N.dims[1] != kHid || N.final_activation != STB_ACT_NONE) return false;
+    PackArgs a;
+    return fill_pack_args(L, a);
+}
+
+uint64_t tc_packed_bytes(const stb_layer*) { return tcl::kPackedBytes; }
+
+int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
+    using namespace tcl;
+    PackArgs a;
+    if (!fill_pack_args(L, a)) return set_error(STB_ENOTSUP, "layer has no tensor-core path");
+    a.out = static_cast<uint8_t*>(out);
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(Header), stream);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "memset: %s", cudaGetErrorString(e));
+    tc_maxabs_kernel<<<64, 256, 0, stream>>>(a);
+    count_launch();
+    tc_pack_kernel<<<296, 256, 0, stream>>>(a);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_pack launch: %s", cudaGetErrorString(e));
+    return STB_OK;
+}
+
+int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
+                   int base_log_prob, int64_t rows, cudaStream_t stream) {
+    using namespace tcl;
+    if (L->packed_bytes < kPackedBytes) return set_error(STB_EINVAL, "packed image too small");
+    Args A;
+    A.packed = static_cast<const uint8_t*>(L->packed);
+    A.x = x; A.y = y; A.ldj = ldj;
+    A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
+    A.base_log_prob = base_log_prob;
+    A.inverse = direction == STB_INVERSE;
+    A.lower = L->lower; A.upper = L->upper;
+    A.rows = rows;
+    const long long tiles = (rows + kTileRows - 1) / kTileRows;
+    if (tiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
+    A.n_tiles = (int)tiles;
+
+    static thread_local int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    void (*kern)(Args) = (L->kind == STB_RQS) ? tc_spline_layer_kernel<STB_RQS> : tc_spline_layer_kernel<STB_CUBIC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int grid = (int)min((long long)n_sm, tiles);
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(A);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_spline_layer_kernel launch: %s", cudaGetErrorString(e));
+    return STB_OK;
+}
+
 }  // namespace stb

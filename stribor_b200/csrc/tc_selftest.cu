@@ -1,0 +1,121 @@
+// Bring-up / regression check of the tcgen05 building blocks in tc_common.cuh: a single-CTA
+// GEMM  D[128, N] = A[128, K] * B[N, K]^T  that packs its operands into the no-swizzle K-major
+// core-matrix layout, issues UMMAs from one thread, and reads the accumulator back from TMEM.
+// Exposed as stb_tc_selftest (include/stribor_b200.h); tests/test_gpu_tc.py compares it with a
+// PyTorch matmul for fp16 / tf32, single-pass and the 3-pass hi/lo split the layer kernel uses.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace stb {
+using namespace tc;
+
+__device__ __forceinline__ uint32_t core_offset(int r, int k, int K, int elem) {
+    const int epc = 16 / elem, chunks = K / epc;
+    return (uint32_t)((r >> 3) * (chunks * 128) + (k / epc) * 128 + (r & 7) * 16 + (k % epc) * elem);
+}
+
+__device__ void pack_operand(uint8_t* hi_s, uint8_t* lo_s, const float* g, int rows, int K, int tf32) {
+    for (int i = threadIdx.x; i < rows * K; i += blockDim.x) {
+        const int r = i / K, k = i - r * K;
+        const float v = g[i];
+        if (tf32) {
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            const uint32_t off = core_offset(r, k, K, 4);
+            *reinterpret_cast<float*>(hi_s + off) = hi;
+            *reinterpret_cast<float*>(lo_s + off) = lo;
+        } else {
+            __half hi, lo;
+            split_f16(v, hi, lo);
+            const uint32_t off = core_offset(r, k, K, 2);
+            *reinterpret_cast<__half*>(hi_s + off) = hi;
+            *reinterpret_cast<__half*>(lo_s + off) = lo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const float* B, float* D, int K,
+                                                          int N, int mode, int variant) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tf32 = mode & 1, split = mode >> 1;
+    const int elem = tf32 ? 4 : 2, epc = 16 / elem, chunks = K / epc;
+    const uint32_t a_bytes = 128u * K * elem, b_bytes = (uint32_t)N * K * elem;
+    uint8_t* a_hi = smem;
+    uint8_t* a_lo = a_hi + a_bytes;
+    uint8_t* b_hi = a_lo + a_bytes;
+    uint8_t* b_lo = b_hi + b_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    pack_operand(a_hi, a_lo, A, 128, K, tf32);
+    pack_operand(b_hi, b_lo, B, N, K, tf32);
+    fence_proxy_async_smem();
+
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)N) ncols <<= 1;
+    if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = tmem_base_s;
+
+    if (threadIdx.x == 0) {
+        const uint32_t kstride = 128, gstride = (uint32_t)chunks * 128;
+        const uint32_t lbo = variant ? gstride : kstride, sbo = variant ? kstride : gstride;
+        const uint32_t idesc = make_idesc(tf32 ? FMT_TF32 : FMT_F16, 128, N);
+        const int ksteps = chunks / 2;
+        const int npass = split ? 3 : 1;
+        uint32_t acc = 0;
+        for (int p = 0; p < npass; ++p) {
+            const uint8_t* as = (p == 1) ? a_lo : a_hi;          // hi*hi, lo*hi, hi*lo
+            const uint8_t* bs = (p == 2) ? b_lo : b_hi;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t ad = make_smem_desc(smem_u32(as) + ks * 2 * kstride, lbo, sbo);
+                const uint64_t bd = make_smem_desc(smem_u32(bs) + ks * 2 * kstride, lbo, sbo);
+                if (tf32) umma_tf32(tbase, ad, bd, idesc, acc);
+                else umma_f16(tbase, ad, bd, idesc, acc);
+                acc = 1;
+            }
+        }
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) D[(size_t)row * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, ncols);
+}
+
+}  // namespace stb
+
+extern "C" int stb_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t mode,
+                               int32_t variant, void* stream) {
+    using namespace stb;
+    const int tf32 = mode & 1;
+    if (mode < 0 || mode > 3) return set_error(STB_EINVAL, "mode must be 0..3");
+    if (K < (tf32 ? 8 : 16) || K % (tf32 ? 8 : 16) || N < 16 || N > 256 || N % 16)
+        return set_error(STB_EINVAL, "K must be a multiple of the UMMA K, N a multiple of 16 <= 256");
+    const size_t smem = (size_t)(128 + N) * K * (tf32 ? 4 : 2) * 2;
+    if (smem > 200 * 1024) return set_error(STB_EINVAL, "operands too large for one CTA");
+    cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, K, N, mode, variant);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_selftest launch: %s", cudaGetErrorString(e));
+    return STB_OK;
+}

@@ -19,7 +19,7 @@ def net_meta(net):
 
 
 def build_meta(kind, dim, latent_dim, cond_x, time_input, n_bins, inv_own, zero_cond, net, n_extra,
-               has_box=0):
+               has_box=0, mask_list=None):
     if net is None:
         dims, act, fact, params = [], 0, 0, None
         n_linear = 0
@@ -29,6 +29,9 @@ def build_meta(kind, dim, latent_dim, cond_x, time_input, n_bins, inv_own, zero_
     n_params = (2 * n_linear if n_linear else 1) + n_extra
     meta = [kind, dim, latent_dim, int(cond_x), int(time_input), n_bins, int(inv_own), int(zero_cond),
             act, fact, n_linear, n_params, int(has_box), 0] + list(dims)
+    if cond_x:
+        assert mask_list is not None and len(mask_list) == dim
+        meta += [int(v) for v in mask_list]
     return meta, params
 
 
@@ -60,11 +63,14 @@ class PackedCache:
 
 
 def device_mask(cache, mask_func, dim, device):
-    """uint8 [dim] mask on `device`, cached per (dim, device)."""
+    """(uint8 [dim] mask on `device`, the same mask as a python list), cached per (dim, device)."""
     k = (dim, str(device))
     if k not in cache:
-        m = mask_func(dim)
-        if m.numel() == 1 and dim != 1:
-            m = m.expand(dim)
-        cache[k] = (m != 0).to(torch.uint8).contiguous().to(device)
+        if ('host', dim) not in cache:
+            m = mask_func(dim)
+            if m.numel() == 1 and dim != 1:
+                m = m.expand(dim)
+            cache[('host', dim)] = (m != 0).to(torch.uint8).contiguous()
+        host = cache[('host', dim)]
+        cache[k] = (host.to(device), host.tolist())
     return cache[k]

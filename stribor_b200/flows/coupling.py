@@ -54,12 +54,12 @@ class Coupling(Transform):
     def describe(self, dim, latent_dim, device):
         tr = self.transform
         net = tr.latent_net
+        mask, mask_list = device_mask(self._masks, self.mask_func, dim, device)
         meta, params = build_meta(tr.kind, dim, latent_dim if net is not None else 0, 1, 0, tr.n_bins,
-                                  0, dim == 1, net, 0)
+                                  0, dim == 1, net, 0, mask_list=mask_list)
         if net is None:
             params = [tr.const_out()]
         params = list(params)
-        mask = device_mask(self._masks, self.mask_func, dim, device)
         fmeta = tr.fmeta()
         packed = self._packed.get(meta, fmeta, mask, params) if net is not None else None
         return {'meta': meta, 'fmeta': fmeta, 'mask': mask, 'params': params, 'packed': packed}
@@ -118,10 +118,10 @@ class ContinuousAffineCoupling(Transform):
         raise ValueError(f'time_net output size {n} does not match 2 * dim = {2 * dim}')
 
     def describe(self, dim, latent_dim, device):
+        mask, mask_list = device_mask(self._masks, self.mask_func, dim, device)
         meta, params = build_meta(_lib.CONT_AFFINE, dim, latent_dim, 1, bool(self.concatenate_time), 0,
-                                  0, dim == 1, self.latent_net, 1)
+                                  0, dim == 1, self.latent_net, 1, mask_list=mask_list)
         params = list(params) + [self._time_scale(dim).contiguous()]
-        mask = device_mask(self._masks, self.mask_func, dim, device)
         return {'meta': meta, 'fmeta': [0., 1.] * 3, 'mask': mask, 'params': params, 'packed': None}
 
     def _run(self, x, t, latent, direction, want_ldj):

@@ -63,7 +63,8 @@ def test_descriptor_wire_format():
     desc = c.describe(d, 3, 'cpu')
     m = desc['meta']
     assert m[:_ops.META_HEADER] == [_lib.RQS, d, 3, 1, 0, 5, 0, 0, _lib.ACTIVATIONS['Tanh'], 0, 3, 6, 0, 0]
-    assert m[_ops.META_HEADER:] == [d + 3, 7, 9, d * 14]
+    assert m[_ops.META_HEADER:] == [d + 3, 7, 9, d * 14] + [0, 1, 0, 1, 0, 1]
+    assert _ops.meta_len(m) == len(m)
     assert desc['fmeta'][:2] == [-2.0, 3.0]
     assert desc['mask'].tolist() == [0, 1, 0, 1, 0, 1] and desc['mask'].dtype == torch.uint8
     assert [tuple(p.shape) for p in desc['params']] == [(7, 9), (7,), (9, 7), (9,), (84, 9), (84,)]
@@ -71,6 +72,7 @@ def test_descriptor_wire_format():
     assert (L.kind, L.dim, L.latent_dim, L.cond_x, L.n_bins, L.net.n_linear) == (_lib.RQS, d, 3, 1, 5, 3)
     assert list(L.net.dims)[:4] == [9, 7, 9, 84]
     assert L.net.W[2] == desc['params'][4].data_ptr() and L.mask == desc['mask'].data_ptr()
+    assert list((ctypes.c_uint8 * d).from_address(L.mask_host)) == [0, 1, 0, 1, 0, 1]
     # d == 1 -> conditioning zeroed (coupling.py:62-63); 'none' mask -> everything transformed
     c1 = st.Coupling(st.Affine(1, latent_net=st.net.MLP(1, [4], 2)), mask='none')
     d1 = c1.describe(1, 0, 'cpu')
