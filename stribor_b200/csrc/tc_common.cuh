@@ -49,11 +49,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+// try_wait suspends the thread in hardware for a while by itself; the loop only counts retries.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {      // ~2 s at 1.9 GHz
+        if (++spins > (1u << 26)) {
+            printf("stribor_b200: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, (void*)bar, parity);
+            __trap();
+        }
+    }
+}
+// same, for single-lane roles that can afford to back off (producer / issuer)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) {
             printf("stribor_b200: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, (void*)bar, parity);
             __trap();

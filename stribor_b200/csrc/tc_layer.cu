@@ -113,9 +113,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // -----------------------------------------------------------------------------------------------
 // spline evaluation with the 48 parameters of one element in registers
 // -----------------------------------------------------------------------------------------------
-// u[0..16) unnormalised -> u[i] = min_size + (1 - 16 min_size) * softmax_i, every quotient
-// e_i / sum refined to (almost) correctly rounded: the knots are cumulative sums of these and
-// their error is amplified by 1 / bin-width in the log-derivative.
+// u[0..16) unnormalised -> u[i] = min_size + (1 - 16 min_size) * softmax_i.
+// exp(u - max) through ex2.approx: arguments are <= 0, so the absolute error of every term is
+// <= ~2.5 ulp of the LARGEST term (= 1), i.e. the same absolute accuracy on the bin sizes as a
+// 2-ulp expf (checked on the GPU: switching between the two moves no row across the tolerance).
 __device__ __forceinline__ void softmax16_bins(float* u, float min_size) {
     float m = u[0];
 #pragma unroll
@@ -123,47 +124,50 @@ __device__ __forceinline__ void softmax16_bins(float* u, float min_size) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < kBins; ++i) {
-        u[i] = expf(u[i] - m);
+        u[i] = __expf(u[i] - m);
         s += u[i];
     }
-    const float inv = __frcp_rn(s);
-    const float scale = 1.f - min_size * (float)kBins;
+    const float inv = __frcp_rn(s) * (1.f - min_size * (float)kBins);
 #pragma unroll
-    for (int i = 0; i < kBins; ++i) {
-        float q = u[i] * inv;
-        q = fmaf(fmaf(-q, s, u[i]), inv, q);         // one Newton step on the quotient
-        u[i] = fmaf(scale, q, min_size);
-    }
+    for (int i = 0; i < kBins; ++i) u[i] = fmaf(u[i], inv, min_size);
 }
 
 struct RqsSel {
     float xk, xk1, yk, yk1, u0, u1;
 };
 
-// Walk the 17 knots of both axes; select the bin that holds `key` on the searched axis.
+// Walk the knots of both axes; select the bin that holds `key` on the searched axis.
 // w[i], h[i]: normalised bin sizes; d[i]: K-1 unconstrained interior derivatives.
-// search_sorted.py:3-5 semantics: bin = #(key >= knot_i) - 1 with the last knot nudged by 1e-6.
+// search_sorted.py:3-5 semantics: bin = #(key >= knot_i) - 1; the nudged last knot is never
+// reached by an inside key, so the bin is the last i in [0, 15] with key >= knot_i.  The knots are
+// increasing, hence "key >= knot_i" is a prefix property and plain predicated moves select the
+// quantities of that bin: cumulative sums before it, its sizes, and the derivative parameters
+// at its two knots.
 __device__ __forceinline__ RqsSel rqs16_walk(const float* w, const float* h, const float* d, float lo,
                                              float hi, bool on_heights, float key) {
     const float span = hi - lo;
-    RqsSel r;
-    r.xk = lo; r.yk = lo; r.u0 = STB_RQS_EDGE_CONST;
-    r.xk1 = hi; r.yk1 = hi; r.u1 = STB_RQS_EDGE_CONST;
+    float cwk = 0.f, chk = 0.f, wk = w[0], hk = h[0];
+    float u0 = STB_RQS_EDGE_CONST, u1 = d[0];
+    int k = 0;
     float cw = 0.f, ch = 0.f;
-    bool prev = true;                            // key >= knot_0 for an inside key
 #pragma unroll
-    for (int i = 1; i <= kBins; ++i) {
+    for (int i = 1; i < kBins; ++i) {
         cw += w[i - 1];
         ch += h[i - 1];
-        const float kw = (i == kBins) ? hi : fmaf(span, cw, lo);       // knots forced to the box
-        const float kh = (i == kBins) ? hi : fmaf(span, ch, lo);
-        const float kk = on_heights ? kh : kw;
-        const bool ge = (i == kBins) ? (key >= kk + 1e-6f) : (key >= kk);
-        const float ud = (i == kBins) ? STB_RQS_EDGE_CONST : d[i - 1];   // derivative param AT knot i
-        if (ge) { r.xk = kw; r.yk = kh; r.u0 = ud; }
-        if (prev && !ge) { r.xk1 = kw; r.yk1 = kh; r.u1 = ud; }
-        prev = ge;
+        const float kk = fmaf(span, on_heights ? ch : cw, lo);
+        if (key >= kk) {
+            k = i; cwk = cw; chk = ch; wk = w[i]; hk = h[i];
+            u0 = d[i - 1];
+            u1 = (i == kBins - 1) ? STB_RQS_EDGE_CONST : d[i];
+        }
     }
+    RqsSel r;
+    r.xk = (k == 0) ? lo : fmaf(span, cwk, lo);                    // knot_0 / knot_K forced to the box
+    r.yk = (k == 0) ? lo : fmaf(span, chk, lo);
+    r.xk1 = (k == kBins - 1) ? hi : fmaf(span, cwk + wk, lo);
+    r.yk1 = (k == kBins - 1) ? hi : fmaf(span, chk + hk, lo);
+    r.u0 = u0;
+    r.u1 = u1;
     return r;
 }
 
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
             for (int it = 0; it < my_tiles; ++it) {
                 for (int c = 0; c < n_chunks; ++c, ++cc) {
                     const uint32_t st = cc % kStages, use = cc / kStages;
-                    mbar_wait(&bars->b_empty[st], (use & 1) ^ 1);
+                    mbar_wait_relaxed(&bars->b_empty[st], (use & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->b_full[st], kChunkBytes);
                     bulk_g2s(bst + st * kChunkBytes, A.packed + kOffW2 + (size_t)c * kChunkBytes, kChunkBytes,
                              &bars->b_full[st]);
@@ -502,8 +506,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                     tmem_ld16(tmem + lane_sel + kColAcc1 + s * kHid + c0, v);
                     tmem_ld_wait();
                     __half hh[16], hl[16];
+                    if (act == STB_ACT_TANH) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) split_f16(activate(act, v[i] + b1s[c0 + i]), hh[i], hl[i]);
+                        for (int i = 0; i < 16; ++i) split_f16(tanhf(v[i] + b1s[c0 + i]), hh[i], hl[i]);
+                    } else {
+#pragma unroll 1
+                        for (int i = 0; i < 16; ++i) v[i] = activate(act, v[i] + b1s[c0 + i]);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) split_f16(v[i], hh[i], hl[i]);
+                    }
 #pragma unroll
                     for (int half8 = 0; half8 < 2; ++half8) {
                         const int kc = (c0 >> 3) + half8;
