@@ -175,7 +175,8 @@ int stb_pack_layer(const stb_layer* layer, void* packed_out, void* stream);
 int stb_layer_uses_tensor_path(const stb_layer* layer);
 
 /* Bring-up check of the tcgen05 building blocks: D[128,N] = A[128,K] * B[N,K]^T on one CTA.
- * mode bit0: 0 = fp16, 1 = tf32 operands; bit1: 3-pass hi/lo split.  variant must be 0. */
+ * mode bit0: 0 = fp16, 1 = tf32 operands; bit1: 3-pass hi/lo split.  variant bit0 must be 0
+ * (descriptor bring-up switch); bit1: issue the small correction passes before hi*hi. */
 int stb_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t mode,
                     int32_t variant, void* stream);
 

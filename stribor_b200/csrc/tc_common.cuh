@@ -9,6 +9,7 @@
 // adjacent core matrix follows immediately) and SBO = (K / EPC) * 128 (next 8-row group).
 // One UMMA consumes 32 bytes of K (2 chunks): fp16 K=16, tf32 K=8.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -178,6 +179,14 @@ __device__ __forceinline__ float to_tf32_rna(float v) {
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     hi = to_tf32_rna(v);
     lo = to_tf32_rna(v - hi);
+}
+// v == b0 + b1 + b2 exactly (3 x 8 significant bits), each part bf16: fp32 range, so no
+// restriction on |v|
+__device__ __forceinline__ void split_bf16x3(float v, __nv_bfloat16& b0, __nv_bfloat16& b1, __nv_bfloat16& b2) {
+    b0 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(b0);
+    b1 = __float2bfloat16_rn(r1);
+    b2 = __float2bfloat16_rn(r1 - __bfloat162float(b1));
 }
 // v ~= hi + lo with hi, lo fp16 (|v| <= ~6e4; lo lands in the subnormal range for |v| < 0.25,
 // where its absolute resolution 2^-25 is still below fp32's for O(1) accumulations)

@@ -8,8 +8,9 @@
 //   warp 0      producer: streams the packed last-Linear weights (24 KB chunks = 2 transformed
 //               dims x 48 padded parameters x 64, fp16 hi | lo) L2 -> smem with cp.async.bulk
 //               through a 3-stage mbarrier ring
-//   warp 1      UMMA issuer (one lane): GEMM1  [128 x 32] x [32 x 64]  as 3xTF32 (x has fp32
-//               range), GEMM2 [128 x 64] x [64 x 96] per chunk as 3 fp16 passes
+//   warp 1      UMMA issuer (one lane): GEMM1  [128 x 32] x [32 x 64]  with both operands split
+//               into three bf16 parts (exact 24-bit split, fp32 range) and the 8 leading partial
+//               products; GEMM2 [128 x 64] x [64 x 96] per chunk as 3 fp16 passes
 //               (hi*hi + lo*hi + hi*lo: fp32-grade products at fp16 tensor rate); accumulators
 //               live in TMEM: 2 x 64 columns for GEMM1, 2 subtiles x 2 buffers x 96 for GEMM2
 //   warp 2      TMEM allocation
@@ -22,6 +23,7 @@
 //
 // Reference semantics restated here: flows/coupling.py:53-95, flows/spline.py:76-105,
 // util/rational_quadratic_spline.py, util/cubic_spline.py, net/mlp.py:46-58, flow.py:42-47.
+#include <stdlib.h>
 #include "common.cuh"
 #include "stb_math.cuh"
 #include "tc_common.cuh"
@@ -61,8 +63,10 @@ static_assert(sizeof(Header) == 1024, "header layout");
 constexpr uint32_t kOffB1 = 1024;                                  // float[64]
 constexpr uint32_t kOffB2 = kOffB1 + kHid * 4;                     // float[kMaxChunks * 96]
 constexpr uint32_t kSmallBytes = kOffB2 + kMaxChunks * kChunkN * 4;    // 7424
-constexpr uint32_t kOffW1 = 8192;                                  // tf32 hi (8 KB) | lo (8 KB)
-constexpr uint32_t kW1Bytes = 2 * kHid * kK1 * 4;                  // 16384
+constexpr uint32_t kOffW1 = 8192;                                  // 3 bf16 parts of [64][32], 4 KB each
+constexpr uint32_t kW1Part = kHid * kK1 * 2;                       // 4096
+constexpr uint32_t kW1Bytes = 3 * kW1Part;                         // 12288
+constexpr uint32_t kA1Part = 128 * kK1 * 2;                        // 8192: one bf16 part of a subtile's A1
 constexpr uint32_t kOffW2 = kOffW1 + kW1Bytes;                     // chunks of 24576 B
 constexpr uint32_t kChunkBytes = 2 * kChunkN * kHid * 2;           // fp16 hi (12 KB) | lo (12 KB)
 constexpr uint32_t kPackedBytes = kOffW2 + kMaxChunks * kChunkBytes;
@@ -116,7 +120,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // u[0..16) unnormalised -> u[i] = min_size + (1 - 16 min_size) * softmax_i.
 // exp(u - max) through ex2.approx: arguments are <= 0, so the absolute error of every term is
 // <= ~2.5 ulp of the LARGEST term (= 1), i.e. the same absolute accuracy on the bin sizes as a
-// 2-ulp expf (checked on the GPU: switching between the two moves no row across the tolerance).
+// 2-ulp expf.  Measured on the GPU against the fp64 oracle (profiles/r01_tc_accuracy.txt): accurate
+// expf, IEEE division and a true e_i / sum quotient change the mean log-det error by < 7 %;
+// only compensated cumulative sums help (12 %) and cost ~90 instructions per element.
 __device__ __forceinline__ void softmax16_bins(float* u, float min_size) {
     float m = u[0];
 #pragma unroll
@@ -171,20 +177,56 @@ __device__ __forceinline__ RqsSel rqs16_walk(const float* w, const float* h, con
     return r;
 }
 
-__device__ __forceinline__ RqsBin rqs16_bin(const RqsSel& s) {
-    RqsBin b;
-    b.xk = s.xk; b.wk = s.xk1 - s.xk;
+// a / b to ~1 ulp: MUFU.RCP + one residual correction (4 instructions instead of ~10 for the
+// IEEE sequence; the operands here are never subnormal / huge)
+__device__ __forceinline__ float fdiv(float a, float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    const float q = a * r;
+    return fmaf(fmaf(-q, b, a), r, q);
+}
+// sqrt(x), x >= 0, to ~1 ulp: MUFU.RSQ + one Newton step
+__device__ __forceinline__ float fsqrt(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    const float s = x * r;
+    const float h = 0.5f * r;
+    return (x > 0.f) ? fmaf(fmaf(-s, s, x), h, s) : 0.f;
+}
+// F.softplus (beta 1, threshold 20); exp through ex2.approx (relative error ~|v| * 1e-7)
+__device__ __forceinline__ float softplus_fast(float v) { return v > 20.f ? v : log1pf(__expf(v)); }
+
+struct RqsBin16 {
+    float xk, wk, yk, hk, delta, d0, d1;
+};
+
+__device__ __forceinline__ RqsBin16 rqs16_bin(const RqsSel& s) {
+    RqsBin16 b;
+    b.xk = s.xk; b.wk = s.xk1 - s.xk;                 // widths re-derived from the knots (:185)
     b.yk = s.yk; b.hk = s.yk1 - s.yk;
-    b.delta = b.hk / b.wk;
-    b.d0 = STB_RQS_MIN + softplus_f(s.u0);
-    b.d1 = STB_RQS_MIN + softplus_f(s.u1);
+    b.delta = fdiv(b.hk, b.wk);
+    b.d0 = STB_RQS_MIN + softplus_fast(s.u0);
+    b.d1 = STB_RQS_MIN + softplus_fast(s.u1);
     return b;
 }
 
-// p[0..48): raw conditioner outputs [w(16) | h(16) | d(15) | pad].  Same contract as rqs_element
-// with own_ld = false (Coupling semantics).
-__device__ __forceinline__ void rqs16_element(float* p, float lo, float hi, bool inverse, bool want_ld,
-                                              float x, float& out, float& ld) {
+// log f'(x) for x in bin b: log(delta^2 (d1 th^2 + 2 delta th(1-th) + d0 (1-th)^2) / den^2)
+// (rational_quadratic_spline.py:245-248, the two logs merged into one)
+__device__ __forceinline__ float rqs16_log_deriv(const RqsBin16& b, float theta, float tt, float den) {
+    const float omt = 1.f - theta;
+    const float dnum = b.delta * b.delta * (b.d1 * theta * theta + 2.f * b.delta * tt + b.d0 * omt * omt);
+    return logf(fdiv(dnum, den * den));
+}
+
+// p[0..48): raw conditioner outputs [w(16) | h(16) | d(15) | pad].  Coupling semantics
+// (rqs_element with own_ld = false), with ONE deliberate simplification: in the inverse
+// direction the forward log-derivative at the recovered point is evaluated in the bin the
+// inverse search found.  The reference re-searches (flow.py:42-47 -> coupling.py:84-95) and can
+// land in the neighbouring bin only when rounding puts the recovered point within an ulp of a
+// knot, where the spline is C1, so the two evaluations agree to O(ulp).
+template <bool INVERSE>
+__device__ __forceinline__ void rqs16_element(float* p, float lo, float hi, bool want_ld, float x,
+                                              float& out, float& ld) {
     out = x;
     ld = 0.f;
     if (!(x >= lo && x <= hi)) return;
@@ -193,28 +235,26 @@ __device__ __forceinline__ void rqs16_element(float* p, float lo, float hi, bool
     const float* d = p + 2 * kBins;
     softmax16_bins(w, STB_RQS_MIN);
     softmax16_bins(h, STB_RQS_MIN);
-    if (!inverse) {
-        const RqsBin b = rqs16_bin(rqs16_walk(w, h, d, lo, hi, false, x));
-        rqs_forward_in_bin(b, x, out, ld);
-    } else {
-        const RqsSel sel = rqs16_walk(w, h, d, lo, hi, true, x);
-        const RqsBin b = rqs16_bin(sel);
-        float ld_own;
-        rqs_inverse_in_bin(b, x, out, ld_own);
-        if (want_ld) {
-            // -(forward log-derivative at the recovered point), flow.py:42-47
-            if (out >= lo && out <= hi) {
-                // bin K-1: its upper knot is the nudged one (search_sorted.py:4)
-                const bool same = (out >= sel.xk) && ((sel.xk1 == hi) ? (out < hi + 1e-6f) : (out < sel.xk1));
-                float y2, ldf;
-                if (same) {
-                    rqs_forward_in_bin(b, out, y2, ldf);
-                } else {                                       // rounding moved it to a neighbour bin
-                    const RqsBin b2 = rqs16_bin(rqs16_walk(w, h, d, lo, hi, false, out));
-                    rqs_forward_in_bin(b2, out, y2, ldf);
-                }
-                ld = -ldf;
-            }
+    const RqsBin16 b = rqs16_bin(rqs16_walk(w, h, d, lo, hi, INVERSE, x));
+    const float s = b.d0 + b.d1 - 2.f * b.delta;
+    if (!INVERSE) {                                   // rational_quadratic_spline.py:236-248
+        const float theta = fdiv(x - b.xk, b.wk);
+        const float tt = theta * (1.f - theta);
+        const float den = b.delta + s * tt;
+        out = b.yk + fdiv(b.hk * (b.delta * theta * theta + b.d0 * tt), den);
+        ld = rqs16_log_deriv(b, theta, tt, den);
+    } else {                                          // rational_quadratic_spline.py:212-226
+        const float dy = x - b.yk;
+        const float qa = dy * s + b.hk * (b.delta - b.d0);
+        const float qb = b.hk * b.d0 - dy * s;
+        const float qc = -b.delta * dy;
+        const float disc = qb * qb - 4.f * qa * qc;
+        const float root = fdiv(2.f * qc, -qb - fsqrt(disc));
+        out = root * b.wk + b.xk;
+        if (want_ld && out >= lo && out <= hi) {
+            const float theta = fdiv(out - b.xk, b.wk);
+            const float tt = theta * (1.f - theta);
+            ld = -rqs16_log_deriv(b, theta, tt, b.delta + s * tt);
         }
     }
 }
@@ -273,8 +313,9 @@ __device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float u
 }
 
 // p[0..48): [w(16) | h(16) | left, right | pad]
-__device__ __forceinline__ void cubic16_element(float* p, float lo, float hi, bool inverse, bool want_ld,
-                                                float x, float& out, float& ld) {
+template <bool INVERSE>
+__device__ __forceinline__ void cubic16_element(float* p, float lo, float hi, bool want_ld, float x,
+                                                float& out, float& ld) {
     out = x;
     ld = 0.f;
     if (!(x >= lo && x <= hi)) return;
@@ -285,7 +326,7 @@ __device__ __forceinline__ void cubic16_element(float* p, float lo, float hi, bo
     softmax16_bins(h, STB_CUB_MIN);
     const float span = hi - lo;
     const float u = (x - lo) / span;
-    if (!inverse) {
+    if (!INVERSE) {
         const CubBin b = cubic16_bin(cubic16_walk(w, h, false, u), ul, ur);
         out = cubic_forward_in_bin(b, u, ld) * span + lo;
     } else {
@@ -311,7 +352,7 @@ __device__ __forceinline__ void cubic16_element(float* p, float lo, float hi, bo
 // -----------------------------------------------------------------------------------------------
 // the kernel
 // -----------------------------------------------------------------------------------------------
-template <int KIND>
+template <int KIND, bool INVERSE>
 __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem + kSmXs);
@@ -372,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
     } else if (warp == 1) {
         // ======================= UMMA issuer =====================================================
         if (lane == 0) {
-            const uint32_t idesc1 = make_idesc(FMT_TF32, 128, kHid);
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, kHid);
             const uint32_t idesc2 = make_idesc(FMT_F16, 128, kChunkN);
             uint32_t cc = 0;
             for (int it = 0; it < my_tiles; ++it) {
@@ -380,17 +421,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 for (int s = 0; s < 2; ++s) {      // GEMM1: conditioning columns -> hidden pre-activation
                     mbar_wait(&bars->a1_ready[s], tpar);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(abuf + s * kABytes), a_lo = a_hi + 16384;
-                    const uint32_t b_hi = smem_u32(w1s), b_lo = b_hi + 8192;
+                    const uint32_t a0 = smem_u32(abuf + s * kABytes), b0 = smem_u32(w1s);
                     const uint32_t dcol = tmem + kColAcc1 + s * kHid;
                     uint32_t acc = 0;
+                    // x = x0 + x1 + x2, W = W0 + W1 + W2 (bf16 parts): every product except x2*W2,
+                    // SMALLEST first -- the tensor core truncates the running accumulator at every
+                    // step (measured: tools/tc_probe.py), so the big x0*W0 term must come last.
 #pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        const uint32_t aa = (p == 1) ? a_lo : a_hi, bb = (p == 2) ? b_lo : b_hi;
+                    for (int p = 0; p < 8; ++p) {
+                        // (pa,pb): (1,2) (2,1) (0,2) (1,1) (2,0) (0,1) (1,0) (0,0)
+                        const int pa = (p == 0 || p == 3 || p == 6) ? 1 : ((p == 1 || p == 4) ? 2 : 0);
+                        const int pb = (p == 0 || p == 2) ? 2 : ((p == 1 || p == 3 || p == 5) ? 1 : 0);
 #pragma unroll
-                        for (int ks = 0; ks < kK1 / 8; ++ks) {
-                            umma_tf32(dcol, make_smem_desc(aa + ks * 256, 128, 1024),
-                                      make_smem_desc(bb + ks * 256, 128, 1024), idesc1, acc);
+                        for (int ks = 0; ks < kK1 / 16; ++ks) {
+                            umma_f16(dcol, make_smem_desc(a0 + pa * kA1Part + ks * 256, 128, 512),
+                                     make_smem_desc(b0 + pb * kW1Part + ks * 256, 128, 512), idesc1, acc);
                             acc = 1;
                         }
                     }
@@ -408,9 +453,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                         const uint32_t b_hi = smem_u32(bst + st * kChunkBytes), b_lo = b_hi + 12288;
                         const uint32_t dcol = tmem + kColAcc2 + (s * 2 + buf) * kChunkN;
                         uint32_t acc = 0;
+                        // lo*hi, hi*lo, then hi*hi: small corrections first (accumulator truncation)
 #pragma unroll
                         for (int p = 0; p < 3; ++p) {
-                            const uint32_t aa = (p == 1) ? a_lo : a_hi, bb = (p == 2) ? b_lo : b_hi;
+                            const uint32_t aa = (p == 0) ? a_lo : a_hi, bb = (p == 1) ? b_lo : b_hi;
 #pragma unroll
                             for (int ks = 0; ks < kHid / 16; ++ks) {
                                 umma_f16(dcol, make_smem_desc(aa + ks * 256, 128, 1024),
@@ -434,7 +480,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
         uint8_t* a_s = abuf + s * kABytes;
         const uint32_t a_row_off = (uint32_t)(rloc >> 3) * 1024 + (uint32_t)(rloc & 7) * 16;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-        const bool inverse = A.inverse != 0;
         const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
         uint32_t cc = 0;
 
@@ -477,19 +522,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
             }
             named_bar_sync(1, kEpiThreads);
 
-            // ---- A1: this row's conditioning columns, tf32 hi | lo, core-matrix layout -------------
+            // ---- A1: this row's conditioning columns as three bf16 parts, core-matrix layout --------
             {
+                const uint32_t a1_row_off = (uint32_t)(rloc >> 3) * 512 + (uint32_t)(rloc & 7) * 16;
 #pragma unroll
-                for (int kc = 0; kc < kK1 / 4; ++kc) {
-                    float hi[4], lo[4];
+                for (int kc = 0; kc < kK1 / 8; ++kc) {
+                    __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int k = kc * 4 + u;
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = kc * 8 + u;
                         const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : 0.f;
-                        split_tf32(v, hi[u], lo[u]);
+                        split_bf16x3(v, q0[u], q1[u], q2[u]);
                     }
-                    *reinterpret_cast<float4*>(a_s + a_row_off + kc * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(a_s + 16384 + a_row_off + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(a_s + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q0);
+                    *reinterpret_cast<uint4*>(a_s + kA1Part + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q1);
+                    *reinterpret_cast<uint4*>(a_s + 2 * kA1Part + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q2);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -505,7 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                     float v[16];
                     tmem_ld16(tmem + lane_sel + kColAcc1 + s * kHid + c0, v);
                     tmem_ld_wait();
-                    __half hh[16], hl[16];
+                    __align__(16) __half hh[16], hl[16];
                     if (act == STB_ACT_TANH) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) split_f16(tanhf(v[i] + b1s[c0 + i]), hh[i], hl[i]);
@@ -556,8 +603,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                         for (int i = 0; i < kPPad; ++i) p[i] = fmaf(p[i], s2, bb[i]);
                         const int j = hdr->tr_idx[ji];
                         float out, ld;
-                        if (KIND == STB_RQS) rqs16_element(p, A.lower, A.upper, inverse, want_ld, xrow[j], out, ld);
-                        else cubic16_element(p, A.lower, A.upper, inverse, want_ld, xrow[j], out, ld);
+                        if (KIND == STB_RQS) rqs16_element<INVERSE>(p, A.lower, A.upper, want_ld, xrow[j], out, ld);
+                        else cubic16_element<INVERSE>(p, A.lower, A.upper, want_ld, xrow[j], out, ld);
                         xrow[j] = out;
                         ld_acc += ld;
                     }
@@ -659,15 +706,16 @@ __global__ void tc_pack_kernel(const PackArgs a) {
         const int ji = i / kPPad, p = i % kPPad;
         b2[i] = (ji < a.n_tr && p < a.P) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
     }
-    // first Linear, conditioning columns only: [64][32] tf32 hi | lo
+    // first Linear, conditioning columns only: [64][32] as three bf16 parts
     for (int i = gtid; i < kHid * kK1; i += gsz) {
         const int n = i / kK1, k = i % kK1;
         const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.dim + a.cond_idx[k]] : 0.f;
-        float hi, lo;
-        split_tf32(v, hi, lo);
-        const uint32_t off = core_off(n, k, kK1, 4);
-        *reinterpret_cast<float*>(a.out + kOffW1 + off) = hi;
-        *reinterpret_cast<float*>(a.out + kOffW1 + 8192 + off) = lo;
+        __nv_bfloat16 q0, q1, q2;
+        split_bf16x3(v, q0, q1, q2);
+        const uint32_t off = kOffW1 + core_off(n, k, kK1, 2);
+        *reinterpret_cast<__nv_bfloat16*>(a.out + off) = q0;
+        *reinterpret_cast<__nv_bfloat16*>(a.out + off + kW1Part) = q1;
+        *reinterpret_cast<__nv_bfloat16*>(a.out + off + 2 * kW1Part) = q2;
     }
     // last Linear, rows of the transformed dims, padded to 48 per dim, 2 dims per chunk
     const float inv = 1.f / s2;
@@ -755,7 +803,9 @@ int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, 
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (n_sm <= 0) n_sm = 148;
     }
-    void (*kern)(Args) = (L->kind == STB_RQS) ? tc_spline_layer_kernel<STB_RQS> : tc_spline_layer_kernel<STB_CUBIC>;
+    void (*kern)(Args);
+    if (L->kind == STB_RQS) kern = A.inverse ? tc_spline_layer_kernel<STB_RQS, true> : tc_spline_layer_kernel<STB_RQS, false>;
+    else kern = A.inverse ? tc_spline_layer_kernel<STB_CUBIC, true> : tc_spline_layer_kernel<STB_CUBIC, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int grid = (int)min((long long)n_sm, tiles);

@@ -66,12 +66,14 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const 
 
     if (threadIdx.x == 0) {
         const uint32_t kstride = 128, gstride = (uint32_t)chunks * 128;
-        const uint32_t lbo = variant ? gstride : kstride, sbo = variant ? kstride : gstride;
+        const uint32_t lbo = (variant & 1) ? gstride : kstride, sbo = (variant & 1) ? kstride : gstride;
+        const bool small_first = (variant & 2) != 0;       // correction passes before hi*hi
         const uint32_t idesc = make_idesc(tf32 ? FMT_TF32 : FMT_F16, 128, N);
         const int ksteps = chunks / 2;
         const int npass = split ? 3 : 1;
         uint32_t acc = 0;
-        for (int p = 0; p < npass; ++p) {
+        for (int pp = 0; pp < npass; ++pp) {
+            const int p = (split && small_first) ? (pp + 1) % 3 : pp;   // lo*hi, hi*lo, hi*hi
             const uint8_t* as = (p == 1) ? a_lo : a_hi;          // hi*hi, lo*hi, hi*lo
             const uint8_t* bs = (p == 2) ? b_lo : b_hi;
             for (int ks = 0; ks < ksteps; ++ks) {
