@@ -123,20 +123,30 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // 2-ulp expf.  Measured on the GPU against the fp64 oracle (profiles/r01_tc_accuracy.txt): accurate
 // expf, IEEE division and a true e_i / sum quotient change the mean log-det error by < 7 %;
 // only compensated cumulative sums help (12 %) and cost ~90 instructions per element.
-__device__ __forceinline__ void softmax16_bins(float* u, float min_size) {
-    float m = u[0];
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+// t[i] = log2(e) * (unnormalised parameter i), see the packed bias table
+__device__ __forceinline__ void softmax16_bins(float* t, float min_size) {
+    float m = t[0];
 #pragma unroll
-    for (int i = 1; i < kBins; ++i) m = fmaxf(m, u[i]);
+    for (int i = 1; i < kBins; ++i) m = fmaxf(m, t[i]);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < kBins; ++i) {
-        u[i] = __expf(u[i] - m);
-        s += u[i];
+        t[i] = ex2_approx(t[i] - m);
+        s += t[i];
     }
     const float inv = __frcp_rn(s) * (1.f - min_size * (float)kBins);
 #pragma unroll
-    for (int i = 0; i < kBins; ++i) u[i] = fmaf(u[i], inv, min_size);
+    for (int i = 0; i < kBins; ++i) t[i] = fmaf(t[i], inv, min_size);
 }
+
+// tanh to ~3e-7 ABSOLUTE error: (1 - e^-2|v|) / (1 + e^-2|v|).  The result feeds a contraction
+// with O(0.1) weights, where only the absolute error matters (tanhf costs ~3x the instructions).
+__device__ __forceinline__ float tanh_fast(float v);
 
 struct RqsSel {
     float xk, xk1, yk, yk1, u0, u1;
@@ -195,6 +205,11 @@ __device__ __forceinline__ float fsqrt(float x) {
 }
 // F.softplus (beta 1, threshold 20); exp through ex2.approx (relative error ~|v| * 1e-7)
 __device__ __forceinline__ float softplus_fast(float v) { return v > 20.f ? v : log1pf(__expf(v)); }
+
+__device__ __forceinline__ float tanh_fast(float v) {
+    const float t = ex2_approx(-2.885390081777927f * fabsf(v));
+    return copysignf(fdiv(1.f - t, 1.f + t), v);
+}
 
 struct RqsBin16 {
     float xk, wk, yk, hk, delta, d0, d1;
@@ -394,6 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
     const int d = hdr->dim, n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_chunks = hdr->n_chunks;
     const int act = hdr->act;
     const float s2 = hdr->s2;
+    const float s2l = s2 * 1.4426950408889634f;
     const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
@@ -401,6 +417,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
         if (lane == 0) {
             uint32_t cc = 0;
             for (int it = 0; it < my_tiles; ++it) {
+                if (it + 1 < my_tiles) {           // pull the NEXT tile's rows into L2 while this one computes
+                    const long long nrow0 = ((long long)blockIdx.x + (long long)(it + 1) * gridDim.x) * kTileRows;
+                    const long long nb = min((long long)kTileRows, A.rows - nrow0) * d * 4;
+                    const char* src = reinterpret_cast<const char*>(A.x + nrow0 * d);
+                    if (nb >= 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(nb & ~15LL)) : "memory");
+                }
                 for (int c = 0; c < n_chunks; ++c, ++cc) {
                     const uint32_t st = cc % kStages, use = cc / kStages;
                     mbar_wait_relaxed(&bars->b_empty[st], (use & 1) ^ 1);
@@ -555,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                     __align__(16) __half hh[16], hl[16];
                     if (act == STB_ACT_TANH) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) split_f16(tanhf(v[i] + b1s[c0 + i]), hh[i], hl[i]);
+                        for (int i = 0; i < 16; ++i) split_f16(tanh_fast(v[i] + b1s[c0 + i]), hh[i], hl[i]);
                     } else {
 #pragma unroll 1
                         for (int i = 0; i < 16; ++i) v[i] = activate(act, v[i] + b1s[c0 + i]);
@@ -598,9 +621,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                     tmem_ld16(col0 + g * kPPad + 32, p + 32);
                     tmem_ld_wait();
                     if (ji < n_tr) {
+                        // widths / heights arrive pre-multiplied by log2(e) (exp2-domain softmax): the
+                        // bias table holds b * log2(e) for those 32 columns
                         const float* bb = b2s + (c * kG + g) * kPPad;
 #pragma unroll
-                        for (int i = 0; i < kPPad; ++i) p[i] = fmaf(p[i], s2, bb[i]);
+                        for (int i = 0; i < 2 * kBins; ++i) p[i] = fmaf(p[i], s2l, bb[i]);
+#pragma unroll
+                        for (int i = 2 * kBins; i < kPPad; ++i) p[i] = fmaf(p[i], s2, bb[i]);
                         const int j = hdr->tr_idx[ji];
                         float out, ld;
                         if (KIND == STB_RQS) rqs16_element<INVERSE>(p, A.lower, A.upper, want_ld, xrow[j], out, ld);
@@ -704,7 +731,8 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     for (int i = gtid; i < kHid; i += gsz) b1[i] = a.b1[i];
     for (int i = gtid; i < kMaxChunks * kChunkN; i += gsz) {
         const int ji = i / kPPad, p = i % kPPad;
-        b2[i] = (ji < a.n_tr && p < a.P) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
+        const float bv = (ji < a.n_tr && p < a.P) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
+        b2[i] = (p < 2 * kBins) ? bv * 1.4426950408889634f : bv;      // softmax columns: log2 domain
     }
     // first Linear, conditioning columns only: [64][32] as three bf16 parts
     for (int i = gtid; i < kHid * kK1; i += gsz) {

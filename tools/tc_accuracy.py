@@ -19,7 +19,7 @@ for d, rows in ((64, 8192), (2, 16384)):
         el = (ll.cpu().double() - l64).abs().view(-1); ex = (xx.cpu().double() - x64).abs()
         print(f'd={d:3d} {tag:22s} ldj err mean {el.mean():.3e} p99 {el.kthvalue(int(0.99*el.numel())).values:.3e} max {el.max():.3e} | x err mean {ex.mean():.3e} max {ex.max():.3e}', flush=True)
     stats('oracle32', x32, l32)
-    for flags, force in ((0, True), (0, False), (1, False), (2, False), (4, False), (8, False), (15, False)):
+    for flags, force in ((0, True), (0, False)):
         os.environ['STRIBOR_B200_FORCE_GENERIC'] = '1' if force else '0'
         os.environ['STRIBOR_B200_TC_FLAGS'] = str(flags)
         layers = [l.to(DEV) for l in layers_from_spec(spec)]
@@ -27,4 +27,4 @@ for d, rows in ((64, 8192), (2, 16384)):
         with torch.no_grad():
             xx, ll = f.inverse_and_log_det_jacobian(x)
         torch.cuda.synchronize()
-        stats('generic' if force else f'tensor flags={flags}', xx, ll)
+        stats('generic' if force else 'tensor', xx, ll)
