@@ -99,7 +99,8 @@ typedef struct stb_layer {
     float bottom, top;         /*   and codomain [bottom, top]
                                   (rational_quadratic_spline.py:55-64)                     */
     int32_t has_box;
-    int32_t reserved0;
+    int32_t row_compact;       /* row_out holds only the transformed dims' parameters, in mask
+                                  order: [rows, n_tr * P] (affine: [log_scale(n_tr) | shift(n_tr)]) */
     const uint8_t* mask;       /* device, [dim], 1 = pass through / conditions            */
     const uint8_t* mask_host;  /* HOST copy of the mask (optional; needed by stb_pack_layer
                                   and for the tensor-core path to be selected)            */
@@ -152,12 +153,18 @@ int stb_unit_normal_log_prob(const float* x, float* lp, int accumulate, int32_t 
  * g_latent, g_t (nullable) receive input gradients; gW[i]/gb[i] (same shapes as the
  * weights; accumulated into, caller zeroes) receive parameter gradients;
  * g_const_out / g_time_scale likewise.  `workspace` must hold
- * stb_layer_backward_workspace_bytes(layer, rows) bytes. */
+ * stb_layer_backward_workspace_bytes(layer, rows) bytes.
+ * Round 1 builds the element-wise part: layers with n_linear == 0 (row_out / const_out), for
+ * which g_x and grads->g_row_out are written; the Python layer runs the conditioner MLP through
+ * autograd (cuBLAS GEMMs) around it.  A layer with n_linear > 0 returns STB_ENOTSUP. */
 typedef struct stb_layer_grads {
     float* gW[STB_MAX_LINEAR];
     float* gb[STB_MAX_LINEAR];
     float* g_const_out;
     float* g_time_scale;
+    float* g_row_out;          /* n_linear == 0: per-row gradient wrt the network output,
+                                  [rows, out_width] in the layout of row_out (also produced for
+                                  const_out layers: the caller sums it over rows)                */
 } stb_layer_grads;
 
 uint64_t stb_layer_backward_workspace_bytes(const stb_layer* layer, int64_t rows);

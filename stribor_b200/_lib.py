@@ -40,7 +40,7 @@ class StbLayer(C.Structure):
                 ('inverse_ldj_own', C.c_int32), ('zero_cond', C.c_int32),
                 ('lower', C.c_float), ('upper', C.c_float),
                 ('left', C.c_float), ('right', C.c_float), ('bottom', C.c_float), ('top', C.c_float),
-                ('has_box', C.c_int32), ('reserved0', C.c_int32),
+                ('has_box', C.c_int32), ('row_compact', C.c_int32),
                 ('mask', C.c_void_p), ('mask_host', C.c_void_p), ('const_out', C.c_void_p), ('row_out', C.c_void_p),
                 ('time_scale', C.c_void_p),
                 ('net', StbMlp), ('packed', C.c_void_p), ('packed_bytes', C.c_uint64)]
@@ -48,7 +48,7 @@ class StbLayer(C.Structure):
 
 class StbLayerGrads(C.Structure):
     _fields_ = [('gW', C.c_void_p * STB_MAX_LINEAR), ('gb', C.c_void_p * STB_MAX_LINEAR),
-                ('g_const_out', C.c_void_p), ('g_time_scale', C.c_void_p)]
+                ('g_const_out', C.c_void_p), ('g_time_scale', C.c_void_p), ('g_row_out', C.c_void_p)]
 
 
 class StriborB200Error(RuntimeError):

@@ -14,7 +14,8 @@ A layer is described by plain data so that it can cross the op boundary:
            mask[0..dim) (only when cond_x)]
   fmeta = [lower, upper, left, right, bottom, top]
   params = [W0, b0, W1, b1, ...] (+ [time_scale]) or [const_out]   (row_mode: const_out is a
-           per-row [rows, out_width] tensor -> stb_layer.row_out)
+           per-row [rows, out_width] tensor -> stb_layer.row_out; row_mode 2 = compact: only the
+           transformed dims' parameters, [rows, n_tr * P])
 """
 from __future__ import annotations
 
@@ -56,6 +57,7 @@ def _fill_struct(L: _lib.StbLayer, meta: Sequence[int], fmeta: Sequence[float], 
     L.lower, L.upper = float(fmeta[0]), float(fmeta[1])
     L.left, L.right, L.bottom, L.top = (float(v) for v in fmeta[2:6])
     L.has_box = has_box
+    L.row_compact = 1 if row_mode == 2 else 0
     L.mask = _dp(mask)
     keep = None
     if cond_x:
@@ -164,34 +166,31 @@ def layer_backward(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mas
                    ) -> List[Tensor]:
     """-> [g_x, g_latent (or empty), g_t (or empty), *g_params]."""
     rows, dim = x.shape
+    n_linear, row_mode = meta[10], meta[13]
+    if n_linear > 0 or meta[0] == _lib.CONT_AFFINE:
+        raise NotImplementedError(
+            'stribor_b200: the fused conditioner / continuous-affine backward is not built yet '
+            '(training runs the MLP through autograd around the element-wise kernels)')
     g_x = torch.empty_like(x)
-    g_latent = torch.empty_like(latent) if (need_latent and latent is not None) else x.new_empty(0)
-    g_t = torch.empty_like(t) if (need_t and t is not None) else x.new_empty(0)
-    g_params = [torch.zeros_like(p) for p in params]
+    g_latent = x.new_empty(0)
+    g_t = x.new_empty(0)
+    p0 = params[0]
     if rows == 0:
         g_x.zero_()
-        return [g_x, g_latent, g_t] + g_params
+        return [g_x, g_latent, g_t, torch.zeros_like(p0)]
+    # per-row gradient wrt the network output; a broadcast (const) parameter sums it over rows
+    g_rows = torch.zeros_like(p0) if row_mode else x.new_zeros(rows, p0.numel())
     L = make_struct(meta, fmeta, mask, params, None)
     G = _lib.StbLayerGrads()
-    n_linear = meta[10]
-    for i in range(n_linear):
-        G.gW[i] = g_params[2 * i].data_ptr()
-        G.gb[i] = g_params[2 * i + 1].data_ptr()
-    rest = g_params[2 * n_linear:]
-    if n_linear == 0:
-        G.g_const_out = rest[0].data_ptr()
-        rest = rest[1:]
-    if meta[0] == _lib.CONT_AFFINE:
-        G.g_time_scale = rest[0].data_ptr()
+    G.g_row_out = g_rows.data_ptr()
     lib = _lib.lib()
     with torch.cuda.device(x.device):
-        ws_bytes = lib.stb_layer_backward_workspace_bytes(C.byref(L), rows)
-        ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=x.device)
         rc = lib.stb_layer_backward(C.byref(L), direction, x.data_ptr(), _dp(latent), _dp(t),
-                                    g_y.data_ptr(), _dp(g_ldj), g_x.data_ptr(), _dp(g_latent), _dp(g_t),
-                                    C.byref(G), ws.data_ptr(), rows, _stream(x))
+                                    g_y.data_ptr(), _dp(g_ldj), g_x.data_ptr(), None, None,
+                                    C.byref(G), None, rows, _stream(x))
     _lib.check(rc)
-    return [g_x, g_latent, g_t] + g_params
+    g_p = g_rows if row_mode else g_rows.sum(0).view_as(p0)
+    return [g_x, g_latent, g_t, g_p]
 
 
 @layer_backward.register_fake

@@ -197,8 +197,11 @@ __global__ void __launch_bounds__(kGenThreads) generic_layer_kernel(const GenArg
                     }
             }
         } else if (L.row_out) {
-            const float* ro = L.row_out + (size_t)(row0 + (lane < nrows ? lane : 0)) * ((size_t)d * P);
-            for (int p = 0; p < P; ++p) col[p] = __ldg(ro + out_row(KIND, d, P, j, p));
+            const bool aff = (KIND == STB_AFFINE || KIND == STB_CONT_AFFINE);
+            const size_t width = (size_t)(L.row_compact ? n_tr : d) * P;
+            const float* ro = L.row_out + (size_t)(row0 + (lane < nrows ? lane : 0)) * width;
+            for (int p = 0; p < P; ++p)
+                col[p] = __ldg(ro + (L.row_compact ? (aff ? p * n_tr + it : it * P + p) : out_row(KIND, d, P, j, p)));
         } else {
             for (int p = 0; p < P; ++p) col[p] = __ldg(L.const_out + out_row(KIND, d, P, j, p));
         }

@@ -74,3 +74,30 @@ def device_mask(cache, mask_func, dim, device):
         host = cache[('host', dim)]
         cache[k] = (host.to(device), host.tolist())
     return cache[k]
+
+
+def needs_autograd(module, *tensors) -> bool:
+    """True when a gradient could flow through this call (parameters or inputs require grad)."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+def row_params_from_net(net, z, rows_idx=None):
+    """Evaluate an MLP conditioner through autograd (training path).  With ``rows_idx`` only those
+    rows of the LAST Linear are evaluated (the transformed dims' parameters, "masked minimum")."""
+    mods = list(net.net)
+    last = max(i for i, m in enumerate(mods) if isinstance(m, torch.nn.Linear))
+    h = z
+    for m in mods[:last]:
+        h = m(h)
+    lin = mods[last]
+    if rows_idx is None:
+        out = torch.nn.functional.linear(h, lin.weight, lin.bias)
+    else:
+        out = torch.nn.functional.linear(h, lin.weight.index_select(0, rows_idx), lin.bias.index_select(0, rows_idx))
+    for m in mods[last + 1:]:
+        out = m(out)
+    return out

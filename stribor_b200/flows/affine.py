@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..flow import ElementwiseTransform, run_layer, run_layer_diag
-from ._native import build_meta
+from ._native import build_meta, needs_autograd, row_params_from_net
 
 __all__ = ['Affine']
 
@@ -64,8 +64,20 @@ class Affine(ElementwiseTransform):
 
     def _run(self, x, latent, direction, want_ldj=True):
         lat = latent if self.latent_net is not None else None
+        if lat is not None and needs_autograd(self, x, lat):
+            return run_layer(self._describe_rows(x, lat), x, None, None, direction, want_ldj)
         d = self.describe(x.shape[-1], 0 if lat is None else lat.shape[-1], x.device)
         return run_layer(d, x, lat, None, direction, want_ldj)
+
+    def _describe_rows(self, x, lat):
+        """Training path: conditioner through autograd, its output handed over per row."""
+        lead = x.shape[:-1]
+        if lat.shape[:-1] != lead:
+            lat = lat.expand(*lead, lat.shape[-1])
+        prm = row_params_from_net(self.latent_net, lat.reshape(-1, lat.shape[-1]))
+        meta, _ = build_meta(self.kind, x.shape[-1], 0, 0, 0, self.n_bins, 1, 0, None, 0)
+        meta[13] = 1
+        return {'meta': meta, 'fmeta': self.fmeta(), 'mask': None, 'params': [prm.contiguous()], 'packed': None}
 
     def forward(self, x, latent=None, **kwargs):
         return self._run(x, latent, _lib.FORWARD, False)[0]

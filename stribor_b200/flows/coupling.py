@@ -19,7 +19,7 @@ from .. import _lib
 from ..flow import Transform, run_layer
 from ..net.time_net import TimeLinear
 from ..util.mask import get_mask
-from ._native import PackedCache, build_meta, device_mask
+from ._native import PackedCache, build_meta, device_mask, needs_autograd, row_params_from_net
 from .affine import Affine
 from .spline import Spline
 
@@ -66,8 +66,43 @@ class Coupling(Transform):
 
     def _run(self, x, latent, direction, want_ldj):
         lat = latent if self.transform.latent_net is not None else None
+        if self.transform.latent_net is not None and needs_autograd(self, x, lat):
+            return self._run_autograd(x, lat, direction, want_ldj)
         d = self.describe(x.shape[-1], 0 if lat is None else lat.shape[-1], x.device)
         return run_layer(d, x, lat, None, direction, want_ldj)
+
+    def _run_autograd(self, x, latent, direction, want_ldj):
+        """Training path: the conditioner MLP runs through autograd (cuBLAS GEMMs, only the
+        transformed dims' rows of its last Linear); gather, transform and log|det J| and their
+        gradients are the element-wise CUDA kernels (``row_out`` mode of the C ABI)."""
+        tr = self.transform
+        dim = x.shape[-1]
+        lead = x.shape[:-1]
+        mask, mask_list = device_mask(self._masks, self.mask_func, dim, x.device)
+        key = ('rows', dim, str(x.device))
+        if key not in self._masks:
+            P = tr.params_per_dim()
+            tr_dims = [j for j, m in enumerate(mask_list) if m == 0]
+            if tr.kind == _lib.AFFINE:
+                idx = tr_dims + [dim + j for j in tr_dims]
+            else:
+                idx = [j * P + p for j in tr_dims for p in range(P)]
+            self._masks[key] = (torch.tensor(idx, dtype=torch.long, device=x.device),
+                                mask.to(x.dtype))
+        rows_idx, mask_f = self._masks[key]
+        if rows_idx.numel() == 0:                     # every coordinate passes through (dim == 1)
+            return x * 1, (x.new_zeros(*lead, 1) if want_ldj else None)
+        z = x * mask_f
+        if dim == 1:
+            z = z * 0
+        if latent is not None:
+            lat = latent if latent.shape[:-1] == lead else latent.expand(*lead, latent.shape[-1])
+            z = torch.cat([z, lat], -1)
+        prm = row_params_from_net(tr.latent_net, z.reshape(-1, z.shape[-1]), rows_idx)
+        meta, _ = build_meta(tr.kind, dim, 0, 1, 0, tr.n_bins, 0, 0, None, 0, mask_list=mask_list)
+        meta[13] = 2                                  # row_mode: compact per-row parameters
+        d = {'meta': meta, 'fmeta': tr.fmeta(), 'mask': mask, 'params': [prm.contiguous()], 'packed': None}
+        return run_layer(d, x, None, None, direction, want_ldj)
 
     def forward(self, x, latent=None, reverse=False, **kwargs):
         return self._run(x, latent, _lib.INVERSE if reverse else _lib.FORWARD, False)[0]
@@ -127,8 +162,42 @@ class ContinuousAffineCoupling(Transform):
     def _run(self, x, t, latent, direction, want_ldj):
         if t is None:
             raise TypeError('ContinuousAffineCoupling needs the time input `t`')
+        if needs_autograd(self, x, t, latent):
+            return self._run_autograd(x, t, latent, direction, want_ldj)
         d = self.describe(x.shape[-1], 0 if latent is None else latent.shape[-1], x.device)
         return run_layer(d, x, latent, t, direction, want_ldj)
+
+    def _run_autograd(self, x, t, latent, direction, want_ldj):
+        """Training path: conditioner and time embedding through autograd; the effective affine
+        parameters  a = log_scale * t_log_scale,  b = shift * t_shift  (coupling.py:199-205) are handed
+        per row to the affine element-wise kernels (forward and backward)."""
+        dim = x.shape[-1]
+        lead = x.shape[:-1]
+        mask, mask_list = device_mask(self._masks, self.mask_func, dim, x.device)
+        key = ('rows', dim, str(x.device))
+        if key not in self._masks:
+            tr_dims = [j for j, m in enumerate(mask_list) if m == 0]
+            self._masks[key] = (torch.tensor(tr_dims, dtype=torch.long, device=x.device), mask.to(x.dtype))
+        tr_idx, mask_f = self._masks[key]
+        if tr_idx.numel() == 0:
+            return x * 1, (x.new_zeros(*lead, 1) if want_ldj else None)
+        z = x * mask_f
+        if dim == 1:
+            z = z * 0
+        if latent is not None:
+            z = torch.cat([z, latent if latent.shape[:-1] == lead else latent.expand(*lead, latent.shape[-1])], -1)
+        tt = t if t.shape[:-1] == lead else t.expand(*lead, 1)
+        if self.concatenate_time:
+            z = torch.cat([z, tt], -1)
+        out = self.latent_net(z.reshape(-1, z.shape[-1]))
+        tn = self._time_scale(dim).view(1, -1) * tt.reshape(-1, 1)
+        a = (out[:, :dim] * tn[:, :dim]).index_select(1, tr_idx)
+        b = (out[:, dim:] * tn[:, dim:]).index_select(1, tr_idx)
+        prm = torch.cat([a, b], -1).contiguous()
+        meta, _ = build_meta(_lib.AFFINE, dim, 0, 1, 0, 0, 0, 0, None, 0, mask_list=mask_list)
+        meta[13] = 2
+        d = {'meta': meta, 'fmeta': [0., 1.] * 3, 'mask': mask, 'params': [prm], 'packed': None}
+        return run_layer(d, x, None, None, direction, want_ldj)
 
     def forward(self, x, t=None, latent=None, **kwargs):
         return self._run(x, t, latent, _lib.FORWARD, False)[0]

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..flow import ElementwiseTransform, run_layer, run_layer_diag
-from ._native import build_meta
+from ._native import build_meta, needs_autograd, row_params_from_net
 
 __all__ = ['Spline']
 
@@ -68,6 +68,16 @@ class Spline(ElementwiseTransform):
         return self.describe(x.shape[-1], 0 if lat is None else lat.shape[-1], x.device), lat
 
     def _run(self, x, latent, direction, want_ldj=True):
+        lat = latent if self.latent_net is not None else None
+        if lat is not None and needs_autograd(self, x, lat):
+            lead = x.shape[:-1]
+            if lat.shape[:-1] != lead:
+                lat = lat.expand(*lead, lat.shape[-1])
+            prm = row_params_from_net(self.latent_net, lat.reshape(-1, lat.shape[-1]))
+            meta, _ = build_meta(self.kind, x.shape[-1], 0, 0, 0, self.n_bins, 1, 0, None, 0)
+            meta[13] = 1
+            d = {'meta': meta, 'fmeta': self.fmeta(), 'mask': None, 'params': [prm.contiguous()], 'packed': None}
+            return run_layer(d, x, None, None, direction, want_ldj)
         d, lat = self._desc(x, latent)
         return run_layer(d, x, lat, None, direction, want_ldj)
 

@@ -1,0 +1,124 @@
+"""GPU: gradients of the NLL training step against the reference's autograd (golden fixtures
+recorded from the unmodified reference) and against autograd through the oracle."""
+import pytest
+import torch
+
+import cases
+from golden_util import ref, has
+from oracle import coupling_flow_oracle as O
+import stribor_b200 as st
+from stribor_b200.spec import layers_from_spec
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def _assert_grad_close(got, r32, r64, what):
+    """Gradient parity: within rtol 1e-3 of the fp64 reference, or as close to it as the reference's
+    own fp32 run (whichever is looser), on the scale of the tensor."""
+    got = got.detach().cpu().double()
+    scale = r64.abs().max().clamp_min(1e-12)
+    err = (got - r64).abs()
+    tol = 1e-3 * r64.abs() + 2e-5 * scale + 2.0 * (r32.double() - r64).abs()
+    bad = (err > tol)
+    assert bad.float().mean().item() <= 2e-3, f'{what}: {bad.float().mean().item():.3%} outside tolerance, max err {err.max().item():.3e} (scale {scale.item():.3e})'
+
+
+@pytest.mark.parametrize('name', [n for n in cases.CASES if n.startswith('grad_')])
+def test_nll_gradients_match_reference(name):
+    case = cases.build_case(name)
+    layers = [l.to(DEV) for l in layers_from_spec(case['spec'])]
+    x = case['inputs']['x'].to(DEV).requires_grad_(True)
+    flow = st.NormalizingFlow(st.UnitNormal(x.shape[-1]), layers)
+    loss = -flow.log_prob(x).mean()
+    loss.backward()
+    torch.testing.assert_close(loss.detach().cpu(), ref(name, 'nll.loss'), rtol=1e-5, atol=1e-5)
+    _assert_grad_close(x.grad, ref(name, 'nll.grad_x'), ref(name, 'nll.grad_x', 'f64'), 'grad_x')
+    for i, p in enumerate(flow.parameters()):
+        assert p.grad is not None, i
+        r32 = ref(name, f'nll.grad_p{i}')
+        r64 = ref(name, f'nll.grad_p{i}', 'f64') if has(name, f'nll.grad_p{i}', 'f64') else r32.double()
+        _assert_grad_close(p.grad, r32, r64, f'grad of parameter {i}')
+
+
+def _oracle_grads(spec, x, latent, inverse):
+    spec = O.spec_to(spec, torch.float64)
+    leaves = []
+    tr = spec[0]['transform']
+    if tr.get('net') is not None:
+        for w, b in zip(tr['net']['weights'], tr['net']['biases']):
+            leaves += [w.requires_grad_(True), b.requires_grad_(True)]
+    else:
+        leaves += [p.requires_grad_(True) for p in tr['params']]
+    xg = x.double().clone().requires_grad_(True)
+    out, ldj = O.layer_apply(spec[0], xg, inverse=inverse, latent=None if latent is None else latent.double())
+    (out.sin().sum() + (ldj * ldj).sum() + ldj.sum()).backward()
+    return xg.grad, [l.grad for l in leaves]
+
+
+@pytest.mark.parametrize('name', ['spline_quadratic_2x10_k3_l0', 'spline_quadratic_7x4x5_k10_l13',
+                                  'spline_cubic_2x10_k3_l0', 'spline_cubic_7x4x5_k10_l13',
+                                  'spline_quadratic_10x2_k1_l13', 'spline_cubic_10x2_k1_l0'])
+@pytest.mark.parametrize('inverse', [False, True])
+def test_standalone_spline_gradients_match_oracle_autograd(name, inverse):
+    """Stand-alone Spline (learned parameters or latent-conditioned): both outputs get a gradient."""
+    case = cases.build_case(name)
+    f = layers_from_spec(case['spec'])[0].to(DEV)
+    x = case['inputs']['x'].clone()
+    lo, hi = 0.0, 2.0
+    x = x.clamp(lo + 0.01, hi - 0.01) if inverse else x           # keep the inverse inside its box
+    latent = case['inputs'].get('latent')
+    gx64, gp64 = _oracle_grads(case['spec'], x, latent, inverse)
+    xg = x.to(DEV).requires_grad_(True)
+    kw = {} if latent is None else {'latent': latent.to(DEV)}
+    out, ldj = (f.inverse_and_log_det_jacobian if inverse else f.forward_and_log_det_jacobian)(xg, **kw)
+    (out.sin().sum() + (ldj * ldj).sum() + ldj.sum()).backward()
+    tol = dict(rtol=2e-3, atol=2e-4) if 'cubic' in name else dict(rtol=1e-3, atol=5e-5)
+    torch.testing.assert_close(xg.grad.cpu().double(), gx64, **tol)
+    got = [p.grad for p in f.parameters()]
+    assert len(got) == len(gp64)
+    for g, r in zip(got, gp64):
+        torch.testing.assert_close(g.cpu().double(), r, **tol)
+
+
+def test_affine_coupling_gradients_not_nan_and_match_oracle():
+    """test_coupling.py:24-26 pattern (check_gradients_not_nan) + values against the oracle."""
+    case = cases.build_case('affine_coupling_7x4x5_l13')
+    f = layers_from_spec(case['spec'])[0].to(DEV)
+    x = case['inputs']['x']
+    latent = case['inputs']['latent']
+    y = f(x.to(DEV), latent=latent.to(DEV))
+    y.mean().backward()
+    grads = [p.grad for p in f.parameters()]
+    assert all(g is not None and not torch.isnan(g).any() for g in grads)
+    spec = O.spec_to(case['spec'], torch.float64)
+    net = spec[0]['transform']['net']
+    leaves = []
+    for w, b in zip(net['weights'], net['biases']):
+        leaves += [w.requires_grad_(True), b.requires_grad_(True)]
+    O.layer_apply(spec[0], x.double(), inverse=False, latent=latent.double())[0].mean().backward()
+    for g, l in zip(grads, leaves):
+        torch.testing.assert_close(g.cpu().double(), l.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_continuous_affine_coupling_gradients_match_oracle():
+    """test_coupling.py:29-51 pattern, gradient values against autograd through the fp64 oracle."""
+    case = cases.build_case('cont_affine_7x4x5_l13')
+    f = layers_from_spec(case['spec'])[0].to(DEV)
+    x, t, latent = case['inputs']['x'], case['inputs']['t'], case['inputs']['latent']
+    xg = x.to(DEV).requires_grad_(True)
+    y, ldj = f.forward_and_log_det_jacobian(xg, t=t.to(DEV), latent=latent.to(DEV))
+    (y.sin().sum() + (ldj * ldj).sum()).backward()
+    spec = O.spec_to(case['spec'], torch.float64)
+    leaves = []
+    for w, b in zip(spec[0]['net']['weights'], spec[0]['net']['biases']):
+        leaves += [w.requires_grad_(True), b.requires_grad_(True)]
+    leaves.append(spec[0]['time_scale'].requires_grad_(True))
+    x64 = x.double().clone().requires_grad_(True)
+    yo, lo = O.layer_apply(spec[0], x64, inverse=False, latent=latent.double(), t=t.double())
+    (yo.sin().sum() + (lo * lo).sum()).backward()
+    torch.testing.assert_close(xg.grad.cpu().double(), x64.grad, rtol=1e-4, atol=1e-5)
+    got = [p.grad for p in f.parameters()]
+    assert len(got) == len(leaves)
+    for g, l in zip(got, leaves):
+        torch.testing.assert_close(g.cpu().double().view(-1), l.grad.view(-1), rtol=1e-4, atol=1e-5)
