@@ -50,6 +50,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--generic', action='store_true', help='force the CUDA-core path (no tcgen05)')
+    ap.add_argument('--workload', default='logprob', choices=['logprob', 'affine', 'neural', 'train'],
+                    help='logprob = BASELINE.json configs[2] (the headline, default); affine = configs[1]; '
+                         'neural = configs[3]; train = configs[4] (side measurements, same JSON schema)')
     return ap.parse_args()
 
 
@@ -190,12 +193,104 @@ def run_reference(args):
 
 
 # -------------------------------------------------------------------------------------------
+# side workloads (BASELINE.json configs[1], [3], [4]); the driver only runs the default one
+# -------------------------------------------------------------------------------------------
+def run_side(args):
+    import torch.distributed as dist
+    import stribor_b200 as st
+    from stribor_b200 import _ops
+    from stribor_b200.parallel import DataParallelNLL, init_from_env, shard_rows
+
+    rank, world, local = init_from_env('nccl')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(123)
+    if args.workload == 'affine':
+        d, rows_g = 64, 1 << 20
+        layers = [st.Coupling(st.Affine(d, latent_net=st.net.MLP(d, [256, 256], 2 * d)), mask=MASKS[i % 2])
+                  for i in range(LAYERS)]
+        flow = st.NormalizingFlow(st.UnitNormal(d), layers).to(dev).requires_grad_(False)
+        name = f'affine coupling flow d=64, 8 layers, MLP[256,256], log_prob + inverse, global batch {rows_g}'
+        a, b = shard_rows(rows_g, rank, world)
+        torch.manual_seed(rank)
+        y = torch.randn(b - a, d, device=dev)
+
+        def step():
+            with torch.no_grad():
+                flow.log_prob(y)
+                flow.inverse(y)
+        unit, per_step = 'samples/s (log_prob + inverse per sample)', rows_g
+    elif args.workload == 'neural':
+        d, B, T = 16, 65536, 64
+        layers = [st.ContinuousAffineCoupling(st.net.MLP(d + 1, [64], 2 * d), st.net.TimeLinear(2 * d),
+                                              ('ordered_0', 'ordered_1')[i % 2]) for i in range(4)]
+        flow = st.NeuralFlow(layers).to(dev).requires_grad_(False)
+        name = f'NeuralFlow 4x ContinuousAffineCoupling dim 16, MLP[17->64->32], TimeLinear(32), x [{B},{T},{d}], forward'
+        a, b = shard_rows(B, rank, world)
+        torch.manual_seed(rank)
+        x = torch.randn(b - a, T, d, device=dev)
+        t = torch.rand(b - a, T, 1, device=dev)
+
+        def step():
+            with torch.no_grad():
+                flow(x, t=t)
+        unit, per_step = 'rows/s', B * T
+    else:
+        d, rows_g = 128, args.batch
+        P = 3 * BINS - 1
+        layers = [st.Coupling(st.Spline(d, BINS, latent_net=st.net.MLP(d, list(args.hidden), d * P), lower=LOWER,
+                                        upper=UPPER, spline_type='quadratic'), mask=MASKS[i % 2])
+                  for i in range(LAYERS)]
+        flow = st.NormalizingFlow(st.UnitNormal(d), layers).to(dev)
+        name = (f'NLL training step (fwd+bwd, grads all-reduced) quadratic spline coupling d=128, 8 layers, 16 bins, '
+                f'MLP{list(args.hidden)}, global batch {rows_g}')
+        a, b = shard_rows(rows_g, rank, world)
+        torch.manual_seed(rank)
+        y = torch.randn(b - a, d, device=dev)
+        dp = DataParallelNLL(flow, micro_rows=1 << 16)
+
+        def step():
+            dp.step(y, rows_g)
+        unit, per_step = 'samples/s', rows_g
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    n0 = _ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    tm = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_step = tm.item() / args.steps
+    if rank == 0:
+        print(json.dumps({'metric': f'{args.workload} throughput', 'value': per_step / (ms_step * 1e-3), 'unit': unit,
+                          'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
+                          'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+                          'data': 'synthetic', 'config': {'workload': name},
+                          'gpu_launches': int(_ops.launch_count() - n0)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# -------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------
 def main():
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+        return
+    if args.workload != 'logprob':
+        run_side(args)
         return
 
     import torch.distributed as dist
