@@ -130,15 +130,22 @@ __device__ __forceinline__ float ex2_approx(float v) {
 }
 // t[i] = log2(e) * (unnormalised parameter i), see the packed bias table
 __device__ __forceinline__ void softmax16_bins(float* t, float min_size) {
-    float m = t[0];
+    // pairwise trees (depth 4) instead of 15-long dependent chains: with two warps per scheduler
+    // the chains' latency is exposed
+    float m8[8], m4[4];
 #pragma unroll
-    for (int i = 1; i < kBins; ++i) m = fmaxf(m, t[i]);
-    float s = 0.f;
+    for (int i = 0; i < 8; ++i) m8[i] = fmaxf(t[2 * i], t[2 * i + 1]);
 #pragma unroll
-    for (int i = 0; i < kBins; ++i) {
-        t[i] = ex2_approx(t[i] - m);
-        s += t[i];
-    }
+    for (int i = 0; i < 4; ++i) m4[i] = fmaxf(m8[2 * i], m8[2 * i + 1]);
+    const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+#pragma unroll
+    for (int i = 0; i < kBins; ++i) t[i] = ex2_approx(t[i] - m);
+    float s8[8], s4[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s8[i] = t[2 * i] + t[2 * i + 1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s4[i] = s8[2 * i] + s8[2 * i + 1];
+    const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     const float inv = __frcp_rn(s) * (1.f - min_size * (float)kBins);
 #pragma unroll
     for (int i = 0; i < kBins; ++i) t[i] = fmaf(t[i], inv, min_size);
@@ -442,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
             for (int it = 0; it < my_tiles; ++it) {
                 const uint32_t tpar = it & 1;
                 for (int s = 0; s < 2; ++s) {      // GEMM1: conditioning columns -> hidden pre-activation
-                    mbar_wait(&bars->a1_ready[s], tpar);
+                    mbar_wait_relaxed(&bars->a1_ready[s], tpar);
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(abuf + s * kABytes), b0 = smem_u32(w1s);
                     const uint32_t dcol = tmem + kColAcc1 + s * kHid;
@@ -466,11 +473,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 }
                 for (int c = 0; c < n_chunks; ++c, ++cc) {
                     const uint32_t st = cc % kStages, use = cc / kStages;
-                    mbar_wait(&bars->b_full[st], use & 1);
+                    mbar_wait_relaxed(&bars->b_full[st], use & 1);
                     const uint32_t buf = cc & 1, buse = cc >> 1;
                     for (int s = 0; s < 2; ++s) {
-                        if (c == 0) mbar_wait(&bars->h_ready[s], tpar);
-                        mbar_wait(&bars->acc_empty[s][buf], (buse & 1) ^ 1);
+                        if (c == 0) mbar_wait_relaxed(&bars->h_ready[s], tpar);
+                        mbar_wait_relaxed(&bars->acc_empty[s][buf], (buse & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t a_hi = smem_u32(abuf + s * kABytes), a_lo = a_hi + 16384;
                         const uint32_t b_hi = smem_u32(bst + st * kChunkBytes), b_lo = b_hi + 12288;
