@@ -4,7 +4,7 @@
 // latent_net = MLP(dim, [64], dim * P)), mask) without latent input -- the BASELINE.json headline
 // configuration (8 of these layers, d = 64).  Everything else runs on generic_layer.cu.
 //
-// One persistent CTA per SM, 12 warps, tiles of 256 rows handled as two 128-row subtiles:
+// One persistent CTA per SM, 18 warps, tiles of 256 rows handled as two 128-row subtiles:
 //   warp 0      producer: streams the packed last-Linear weights (24 KB chunks = 2 transformed
 //               dims x 48 padded parameters x 64, fp16 hi | lo) L2 -> smem with cp.async.bulk
 //               through a 3-stage mbarrier ring
@@ -13,12 +13,14 @@
 //               products; GEMM2 [128 x 64] x [64 x 96] per chunk as 3 fp16 passes
 //               (hi*hi + lo*hi + hi*lo: fp32-grade products at fp16 tensor rate); accumulators
 //               live in TMEM: 2 x 64 columns for GEMM1, 2 subtiles x 2 buffers x 96 for GEMM2
-//   warp 2      TMEM allocation
-//   warps 4-11  epilogue: warp (s, q) owns rows 32q..32q+31 of subtile s == TMEM lanes of
-//               sub-partition q; a thread is one row.  They stage the x tile, build the A
-//               operands (mask gather + hi/lo split), apply tanh to GEMM1's accumulator, and for
-//               each chunk pull 48 parameters per transformed dim out of TMEM with tcgen05.ld and
-//               evaluate the spline in registers, accumulating log|det J| per row.
+//               (this warp also allocates / frees the 512 TMEM columns)
+//   warps 2-17  epilogue, four per scheduler: warps (s, q, g) own rows 32q..32q+31 of subtile s ==
+//               TMEM lanes of sub-partition q (= warp id % 4); the two warps g = 0, 1 of a (s, q)
+//               pair take one of the chunk's two dims each (and half of the row-level work: mask
+//               gather + split for GEMM1's A operand, tanh of GEMM1's accumulator).  A thread is
+//               one row: it pulls its dim's 48 parameters out of TMEM with tcgen05.ld (32 for the
+//               softmaxes first, the derivative columns only after the bin is known, to stay under
+//               112 registers) and evaluates the spline in registers, accumulating log|det J|.
 // Per layer each row makes one HBM round trip (read y, write x, read/write ldj).
 //
 // Reference semantics restated here: flows/coupling.py:53-95, flows/spline.py:76-105,
@@ -45,8 +47,9 @@ constexpr int kMaxChunks = kMaxTr / kG;
 constexpr int kTileRows = 256;
 constexpr int kXsStride = kMaxDim + 1;
 constexpr int kStages = 3;
-constexpr int kThreads = 384;
-constexpr int kEpiThreads = 256;
+constexpr int kThreads = 576;          // producer warp, issuer warp, 16 epilogue warps
+constexpr int kEpiThreads = 512;
+constexpr int kEpiWarp0 = 2;
 
 // packed image (global memory, built by tc_pack_layer)
 constexpr uint32_t kMagic = 0x53544231u;
@@ -79,7 +82,8 @@ constexpr uint32_t kSmW1 = kSmA + 2 * kABytes;
 constexpr uint32_t kSmB = kSmW1 + kW1Bytes;
 constexpr uint32_t kSmSmall = kSmB + kStages * kChunkBytes;
 constexpr uint32_t kSmBar = (kSmSmall + kSmallBytes + 15) & ~15u;
-constexpr uint32_t kSmemBytes = kSmBar + 256;
+constexpr uint32_t kSmLd = kSmBar + 256;                           // float [256]: partner warp's log-det partials
+constexpr uint32_t kSmemBytes = kSmLd + kTileRows * 4;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 static_assert(kSmA % 16 == 0 && kSmW1 % 16 == 0 && kSmB % 16 == 0 && kSmSmall % 16 == 0, "alignment");
 
@@ -371,6 +375,109 @@ __device__ __forceinline__ void cubic16_element(float* p, float lo, float hi, bo
     }
 }
 
+// ---- split-phase variants used by the kernel: the bin is located from the 32 softmax columns
+// first; the remaining parameter columns are pulled from TMEM afterwards ------------------------
+struct RqsLoc {
+    float cwk, chk, wk, hk;
+    int k;
+};
+
+// t[0..32): log2(e)-scaled raw widths | heights (destroyed: becomes the normalised bin sizes)
+__device__ __forceinline__ RqsLoc rqs16_locate(float* t, float lo, float hi, bool on_heights, float key) {
+    float* w = t;
+    float* h = t + kBins;
+    softmax16_bins(w, STB_RQS_MIN);
+    softmax16_bins(h, STB_RQS_MIN);
+    const float span = hi - lo;
+    RqsLoc r;
+    r.k = 0; r.cwk = 0.f; r.chk = 0.f; r.wk = w[0]; r.hk = h[0];
+    float cw = 0.f, ch = 0.f;
+#pragma unroll
+    for (int i = 1; i < kBins; ++i) {
+        cw += w[i - 1];
+        ch += h[i - 1];
+        const float kk = fmaf(span, on_heights ? ch : cw, lo);
+        if (key >= kk) { r.k = i; r.cwk = cw; r.chk = ch; r.wk = w[i]; r.hk = h[i]; }
+    }
+    return r;
+}
+
+// v[idx] for idx in [0, 16) from a register array (4-level select tree)
+__device__ __forceinline__ float pick16(const float* v, int idx) {
+    float a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (idx & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = (idx & 2) ? a[2 * i + 1] : a[2 * i];
+    const float c0 = (idx & 4) ? b[1] : b[0], c1 = (idx & 4) ? b[3] : b[2];
+    return (idx & 8) ? c1 : c0;
+}
+
+// u0 / u1: (bias-added, unscaled) derivative parameters at the two knots of bin r.k
+template <bool INVERSE>
+__device__ __forceinline__ void rqs16_finish(const RqsLoc& r, float u0, float u1, float lo, float hi, bool want_ld,
+                                             float x, float& out, float& ld) {
+    const float span = hi - lo;
+    RqsSel sel;
+    sel.xk = (r.k == 0) ? lo : fmaf(span, r.cwk, lo);
+    sel.yk = (r.k == 0) ? lo : fmaf(span, r.chk, lo);
+    sel.xk1 = (r.k == kBins - 1) ? hi : fmaf(span, r.cwk + r.wk, lo);
+    sel.yk1 = (r.k == kBins - 1) ? hi : fmaf(span, r.chk + r.hk, lo);
+    sel.u0 = u0;
+    sel.u1 = u1;
+    const RqsBin16 b = rqs16_bin(sel);
+    const float s = b.d0 + b.d1 - 2.f * b.delta;
+    if (!INVERSE) {
+        const float theta = fdiv(x - b.xk, b.wk);
+        const float tt = theta * (1.f - theta);
+        const float den = b.delta + s * tt;
+        out = b.yk + fdiv(b.hk * (b.delta * theta * theta + b.d0 * tt), den);
+        ld = rqs16_log_deriv(b, theta, tt, den);
+    } else {
+        const float dy = x - b.yk;
+        const float qa = dy * s + b.hk * (b.delta - b.d0);
+        const float qb = b.hk * b.d0 - dy * s;
+        const float qc = -b.delta * dy;
+        const float disc = qb * qb - 4.f * qa * qc;
+        const float root = fdiv(2.f * qc, -qb - fsqrt(disc));
+        out = root * b.wk + b.xk;
+        ld = 0.f;
+        if (want_ld && out >= lo && out <= hi) {
+            const float theta = fdiv(out - b.xk, b.wk);
+            const float tt = theta * (1.f - theta);
+            ld = -rqs16_log_deriv(b, theta, tt, b.delta + s * tt);
+        }
+    }
+}
+
+// t[0..32): log2(e)-scaled raw widths | heights (destroyed)
+__device__ __forceinline__ CubSel cubic16_locate(float* t, bool on_heights, float u) {
+    softmax16_bins(t, STB_CUB_MIN);
+    softmax16_bins(t + kBins, STB_CUB_MIN);
+    return cubic16_walk(t, t + kBins, on_heights, u);
+}
+
+template <bool INVERSE>
+__device__ __forceinline__ void cubic16_finish(const CubSel& s, float ul, float ur, float lo, float hi, bool want_ld,
+                                               float u, float& out, float& ld) {
+    const float span = hi - lo;
+    const CubBin b = cubic16_bin(s, ul, ur);
+    if (!INVERSE) {
+        out = cubic_forward_in_bin(b, u, ld) * span + lo;
+    } else {
+        float ld_own;
+        out = cubic_inverse_in_bin(b, u, ld_own) * span + lo;
+        ld = 0.f;
+        if (want_ld && out >= lo && out <= hi) {
+            // forward log-derivative at the recovered point, in the bin the inverse search found
+            // (see rqs16_element for why the re-search is skipped)
+            float ldf;
+            (void)cubic_forward_in_bin(b, (out - lo) / span, ldf);
+            ld = -ldf;
+        }
+    }
+}
+
 // -----------------------------------------------------------------------------------------------
 // the kernel
 // -----------------------------------------------------------------------------------------------
@@ -385,6 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
     const float* b1s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB1);
     const float* b2s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB2);
     Bars* bars = reinterpret_cast<Bars*>(smem + kSmBar);
+    float* ld_s = reinterpret_cast<float*>(smem + kSmLd);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -393,14 +501,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
         mbar_init(&bars->setup, 1);
         for (int i = 0; i < kStages; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->a1_ready[s], 4);
+            mbar_init(&bars->a1_ready[s], 8);
             mbar_init(&bars->acc1_full[s], 1);
-            mbar_init(&bars->h_ready[s], 4);
-            for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[s][b], 1); mbar_init(&bars->acc_empty[s][b], 4); }
+            mbar_init(&bars->h_ready[s], 8);
+            for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[s][b], 1); mbar_init(&bars->acc_empty[s][b], 8); }
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(&bars->tmem_base, kTmemCols);
+    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -500,10 +608,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= kEpiWarp0) {
         // ======================= epilogue warps ==================================================
-        const int e = warp - 4, s = e >> 2, q = warp & 3;       // q == TMEM sub-partition of this warp
-        const int etid = tid - 128;
+        // warp id % 4 fixes the TMEM sub-partition q; the four warps of a residue class are
+        // (subtile 0, half 0), (0, 1), (1, 0), (1, 1)
+        const int q = warp & 3;
+        const int cls = (warp - ((q >= kEpiWarp0) ? q : q + 4)) >> 2;
+        const int s = cls >> 1, g = cls & 1;
+        const int etid = tid - kEpiWarp0 * 32;
         const int rloc = q * 32 + lane;                         // row within the subtile
         const int rt = s * 128 + rloc;                          // row within the tile
         float* xrow = xs + rt * kXsStride;
@@ -511,6 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
         const uint32_t a_row_off = (uint32_t)(rloc >> 3) * 1024 + (uint32_t)(rloc & 7) * 16;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
+        const float lo = A.lower, hi = A.upper;
         uint32_t cc = 0;
 
         for (int it = 0; it < my_tiles; ++it) {
@@ -552,11 +665,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
             }
             named_bar_sync(1, kEpiThreads);
 
-            // ---- A1: this row's conditioning columns as three bf16 parts, core-matrix layout --------
+            // ---- A1: this row's conditioning columns as three bf16 parts (this warp: 16 of the 32) ---
             {
                 const uint32_t a1_row_off = (uint32_t)(rloc >> 3) * 512 + (uint32_t)(rloc & 7) * 16;
 #pragma unroll
-                for (int kc = 0; kc < kK1 / 8; ++kc) {
+                for (int kk = 0; kk < kK1 / 16; ++kk) {
+                    const int kc = g * (kK1 / 16) + kk;
                     __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
@@ -573,12 +687,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 if (lane == 0) mbar_arrive(&bars->a1_ready[s]);
             }
 
-            // ---- hidden layer: h = act(acc1 + b1) -> fp16 hi | lo A operand of GEMM2 ---------------
+            // ---- hidden layer: h = act(acc1 + b1) -> fp16 hi | lo A operand of GEMM2 (32 of 64 units) --
             mbar_wait(&bars->acc1_full[s], tpar);
             tc_fence_after();
             {
 #pragma unroll
-                for (int c0 = 0; c0 < kHid; c0 += 16) {
+                for (int cb = 0; cb < kHid / 2; cb += 16) {
+                    const int c0 = g * (kHid / 2) + cb;
                     float v[16];
                     tmem_ld16(tmem + lane_sel + kColAcc1 + s * kHid + c0, v);
                     tmem_ld_wait();
@@ -595,15 +710,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
 #pragma unroll
                     for (int half8 = 0; half8 < 2; ++half8) {
                         const int kc = (c0 >> 3) + half8;
-                        uint4 ph, pl;
-                        const __half2* h2 = reinterpret_cast<const __half2*>(hh + half8 * 8);
-                        const __half2* l2 = reinterpret_cast<const __half2*>(hl + half8 * 8);
-                        ph.x = *reinterpret_cast<const uint32_t*>(&h2[0]); ph.y = *reinterpret_cast<const uint32_t*>(&h2[1]);
-                        ph.z = *reinterpret_cast<const uint32_t*>(&h2[2]); ph.w = *reinterpret_cast<const uint32_t*>(&h2[3]);
-                        pl.x = *reinterpret_cast<const uint32_t*>(&l2[0]); pl.y = *reinterpret_cast<const uint32_t*>(&l2[1]);
-                        pl.z = *reinterpret_cast<const uint32_t*>(&l2[2]); pl.w = *reinterpret_cast<const uint32_t*>(&l2[3]);
-                        *reinterpret_cast<uint4*>(a_s + a_row_off + kc * 128) = ph;
-                        *reinterpret_cast<uint4*>(a_s + 16384 + a_row_off + kc * 128) = pl;
+                        *reinterpret_cast<uint4*>(a_s + a_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hh + half8 * 8);
+                        *reinterpret_cast<uint4*>(a_s + 16384 + a_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hl + half8 * 8);
                     }
                 }
                 tc_fence_before();
@@ -612,53 +720,86 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 if (lane == 0) mbar_arrive(&bars->h_ready[s]);
             }
 
-            // ---- last Linear chunks out of TMEM + spline in registers ---------------------------------
+            // ---- last Linear chunks out of TMEM + spline in registers: this warp's dim of each chunk ----
             float ld_acc = 0.f;
             for (int c = 0; c < n_chunks; ++c, ++cc) {
                 const uint32_t buf = cc & 1, buse = cc >> 1;
+                const int ji = c * kG + g;
+                const int j = hdr->tr_idx[ji < n_tr ? ji : 0];
+                const float xv = xrow[j];
+                const bool inside = (ji < n_tr) && (xv >= lo) && (xv <= hi);
+                const float* bb = b2s + ji * kPPad;
                 mbar_wait(&bars->acc_full[s][buf], buse & 1);
                 tc_fence_after();
-                const uint32_t col0 = tmem + lane_sel + kColAcc2 + (s * 2 + buf) * kChunkN;
-#pragma unroll 1
-                for (int g = 0; g < kG; ++g) {
-                    const int ji = c * kG + g;
-                    float p[kPPad];
-                    tmem_ld16(col0 + g * kPPad, p);
-                    tmem_ld16(col0 + g * kPPad + 16, p + 16);
-                    tmem_ld16(col0 + g * kPPad + 32, p + 32);
-                    tmem_ld_wait();
-                    if (ji < n_tr) {
+                const uint32_t col0 = tmem + lane_sel + kColAcc2 + (s * 2 + buf) * kChunkN + g * kPPad;
+                float out = xv, ld = 0.f;
+                if (KIND == STB_RQS) {
+                    RqsLoc loc;
+                    {
+                        float t[2 * kBins];
+                        tmem_ld16(col0, t);
+                        tmem_ld16(col0 + 16, t + 16);
+                        tmem_ld_wait();
                         // widths / heights arrive pre-multiplied by log2(e) (exp2-domain softmax): the
                         // bias table holds b * log2(e) for those 32 columns
-                        const float* bb = b2s + (c * kG + g) * kPPad;
 #pragma unroll
-                        for (int i = 0; i < 2 * kBins; ++i) p[i] = fmaf(p[i], s2l, bb[i]);
+                        for (int i = 0; i < 2 * kBins; ++i) t[i] = fmaf(t[i], s2l, bb[i]);
+                        loc = rqs16_locate(t, lo, hi, INVERSE, xv);
+                    }
+                    float dd[16];
+                    tmem_ld16(col0 + 2 * kBins, dd);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[s][buf]);     // TMEM buffer free again
+                    if (inside) {
+                        // derivative parameter AT knot i (1..15) is column 32 + i - 1; box ends are constants
+                        const float r0 = pick16(dd, (loc.k + 15) & 15), r1 = pick16(dd, loc.k);
+                        const float u0 = (loc.k == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + loc.k - 1]);
+                        const float u1 = (loc.k == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
+                        rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
+                    }
+                } else {
+                    const float span = hi - lo;
+                    const float u = (xv - lo) / span;
+                    CubSel sel;
+                    {
+                        float t[2 * kBins];
+                        tmem_ld16(col0, t);
+                        tmem_ld16(col0 + 16, t + 16);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int i = 2 * kBins; i < kPPad; ++i) p[i] = fmaf(p[i], s2, bb[i]);
-                        const int j = hdr->tr_idx[ji];
-                        float out, ld;
-                        if (KIND == STB_RQS) rqs16_element<INVERSE>(p, A.lower, A.upper, want_ld, xrow[j], out, ld);
-                        else cubic16_element<INVERSE>(p, A.lower, A.upper, want_ld, xrow[j], out, ld);
-                        xrow[j] = out;
-                        ld_acc += ld;
+                        for (int i = 0; i < 2 * kBins; ++i) t[i] = fmaf(t[i], s2l, bb[i]);
+                        sel = cubic16_locate(t, INVERSE, u);
+                    }
+                    float dd[16];
+                    tmem_ld16(col0 + 2 * kBins, dd);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[s][buf]);
+                    if (inside) {
+                        const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
+                        cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->acc_empty[s][buf]);
+                if (ji < n_tr) xrow[j] = out;
+                ld_acc += ld;
             }
 
-            // ---- per-row log|det J| (+ UnitNormal log-density of the output row) ------------------------
-            if (A.base_log_prob) {
-                float b = 0.f;
-                for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
-                ld_acc += b;
-            }
-            if (want_ld && rt < nrows) {
-                float* dst = A.ldj + row0 + rt;
-                *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + ld_acc) : ld_acc;
-            }
+            // ---- per-row log|det J|: the pair's two partials (+ UnitNormal log-density of the output row) ---
+            if (g == 1) ld_s[rt] = ld_acc;
             named_bar_sync(1, kEpiThreads);
+            if (g == 0 && want_ld && rt < nrows) {
+                float tot = ld_acc + ld_s[rt];
+                if (A.base_log_prob) {
+                    float b = 0.f;
+                    for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
+                    tot += b;
+                }
+                float* dst = A.ldj + row0 + rt;
+                *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
+            }
 
             // ---- y tile out (coalesced) --------------------------------------------------------------------
             {
@@ -685,7 +826,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
     // ---- teardown --------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem, kTmemCols);
+    if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 
 // -----------------------------------------------------------------------------------------------
