@@ -30,6 +30,8 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     if (ldj_mode != STB_LDJ_NONE && !ldj) return set_error(STB_EINVAL, "ldj_mode set but ldj is NULL");
     if (L->packed && !ldiag && tc_layer_supported(L))
         return tc_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s);
+    if (L->packed && !ldiag && tcm_layer_supported(L))
+        return tcm_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s);
     return generic_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, ldiag, rows, s);
 }
 
@@ -118,20 +120,22 @@ int stb_layer_backward(const stb_layer* layer, int direction, const float* x, co
 
 uint64_t stb_packed_bytes(const stb_layer* layer) {
     if (validate_layer(layer)) return 0;
-    return tc_layer_supported(layer) ? tc_packed_bytes(layer) : 0;
+    if (tc_layer_supported(layer)) return tc_packed_bytes(layer);
+    return tcm_layer_supported(layer) ? tcm_packed_bytes(layer) : 0;
 }
 
 int stb_pack_layer(const stb_layer* layer, void* packed_out, void* stream) {
     int rc = validate_layer(layer);
     if (rc) return rc;
-    if (!tc_layer_supported(layer)) return set_error(STB_ENOTSUP, "layer has no tensor-core path");
     if (!packed_out) return set_error(STB_EINVAL, "packed_out is NULL");
-    return tc_pack_layer(layer, packed_out, (cudaStream_t)stream);
+    if (tc_layer_supported(layer)) return tc_pack_layer(layer, packed_out, (cudaStream_t)stream);
+    if (tcm_layer_supported(layer)) return tcm_pack_layer(layer, packed_out, (cudaStream_t)stream);
+    return set_error(STB_ENOTSUP, "layer has no tensor-core path");
 }
 
 int stb_layer_uses_tensor_path(const stb_layer* layer) {
     if (validate_layer(layer)) return 0;
-    return (layer->packed && tc_layer_supported(layer)) ? 1 : 0;
+    return (layer->packed && (tc_layer_supported(layer) || tcm_layer_supported(layer))) ? 1 : 0;
 }
 
 }  // extern "C"

@@ -1,0 +1,557 @@
+// Tensor-core fused AFFINE coupling layer with a wide conditioner (tcgen05 + TMEM + bulk copies).
+//
+// Scope: st.Coupling(st.Affine(dim <= 64, latent_net = MLP(dim, [H] or [H, H], 2 dim)), mask),
+// H in {64, 128, 192, 256}, no latent input -- BASELINE.json configs[1] (MLP[256,256]).  Here the
+// conditioner IS the work (2 * (32 H + H^2 + 64 H) flop per row-layer against 520 B), so the layout
+// is a plain chain of GEMMs with the activations kept on chip:
+//
+//   tile = 128 rows, persistent CTA per SM, 18 warps
+//   warp 0       producer: streams the packed weights in 16-wide K blocks ([N x 16] K-major,
+//                <= 16 KB) L2 -> smem through a 3-stage cp.async.bulk / mbarrier ring
+//   warp 1       UMMA issuer.  Every GEMM accumulates into TWO TMEM accumulators: the full-magnitude
+//                hi*hi products go to `main`, all correction products (lo*hi, hi*lo; for the bf16x3
+//                first layer everything but x0*W0) to `corr`, because the tensor core truncates
+//                the running accumulator at every step (profiles/r01_tc_accuracy.txt); the epilogue
+//                adds the two in fp32.
+//   warps 2-17   four per TMEM sub-partition q, each owning a quarter of the columns: stage x,
+//                mask gather + exact bf16x3 split (A operand of layer 1), tanh + fp16 hi|lo split of
+//                each hidden layer's accumulator back into the A operand of the next GEMM, and the
+//                affine transform + log|det J| from the last accumulator.
+//
+// Reference semantics: flows/coupling.py:53-95, flows/affine.py:59-109, net/mlp.py:46-58.
+#include "common.cuh"
+#include "stb_math.cuh"
+#include "tc_common.cuh"
+
+namespace stb {
+using namespace tc;
+
+namespace tcm {
+
+constexpr int kRows = 128;
+constexpr int kK1 = 32;
+constexpr int kMaxTr = 32;
+constexpr int kNOut = 64;                  // [log_scale(32) | shift(32)] of the transformed dims
+constexpr int kMaxDim = 64;
+constexpr int kMaxH = 256;
+constexpr int kXsStride = kMaxDim + 1;
+constexpr int kStages = 3;
+constexpr int kThreads = 576;
+constexpr int kEpiThreads = 512;
+constexpr int kEpiWarp0 = 2;
+constexpr uint32_t kSlotBytes = 16384;     // one K block: [<=256 x 16] fp16 hi | lo
+constexpr uint32_t kMagic = 0x53544d31u;
+
+struct Header {                            // 1024 bytes
+    uint32_t magic;
+    int32_t dim, n_cond, n_tr, H, n_hidden, act;
+    float s_mid, s_out;                    // power-of-two scales of the packed 2nd / last Linear
+    uint32_t max_mid, max_out;             // scratch (max |W| bits)
+    int32_t cond_idx[kK1];
+    int32_t tr_idx[kMaxTr];
+    int32_t pad[256 - 11 - kK1 - kMaxTr];
+};
+static_assert(sizeof(Header) == 1024, "header layout");
+// packed image: header | b1[256] | b2[256] | b3[64] | pad to 4096 | W blocks (see pack kernel)
+constexpr uint32_t kOffB1 = 1024, kOffB2 = kOffB1 + kMaxH * 4, kOffB3 = kOffB2 + kMaxH * 4;
+constexpr uint32_t kSmallBytes = kOffB3 + kNOut * 4;                 // 3328
+constexpr uint32_t kOffW = 4096;
+
+__host__ __device__ inline uint32_t w1_block_bytes(int H) { return (uint32_t)H * 32; }        // one bf16 part
+__host__ __device__ inline uint32_t w2_block_bytes(int H) { return (uint32_t)H * 64; }        // hi | lo
+__host__ __device__ inline uint32_t w3_block_bytes() { return kNOut * 64; }
+__host__ __device__ inline uint32_t packed_bytes(int H, int n_hidden) {
+    return kOffW + 6 * w1_block_bytes(H) + (n_hidden == 2 ? (H / 16) * w2_block_bytes(H) : 0) + (H / 16) * w3_block_bytes();
+}
+
+// shared memory map (A operand size depends on H)
+constexpr uint32_t kSmXs = 0;                                        // float [128][65]
+constexpr uint32_t kSmRing = kSmXs + kRows * kXsStride * 4;          // 3 x 16 KB
+constexpr uint32_t kSmSmall = kSmRing + kStages * kSlotBytes;        // header + biases
+constexpr uint32_t kSmLd = kSmSmall + 3584;                          // float [4][128] log-det partials
+constexpr uint32_t kSmBar = kSmLd + 4 * kRows * 4;
+constexpr uint32_t kSmA = kSmBar + 256;                              // A operand: 128 x H fp16 hi | lo (>= 24 KB)
+static_assert(kSmRing % 16 == 0 && kSmSmall % 16 == 0 && kSmA % 16 == 0, "alignment");
+__host__ __device__ inline uint32_t smem_bytes(int H) { return kSmA + (uint32_t)kRows * H * 4; }
+
+struct Bars {
+    uint64_t setup;
+    uint64_t full[kStages], empty[kStages];
+    uint64_t a_ready, acc_ready;
+    uint32_t tmem_base;
+};
+
+constexpr uint32_t kColMain = 0, kColCorr = 256, kTmemCols = 512;
+
+struct Args {
+    const uint8_t* packed;
+    const float* x;
+    float* y;
+    float* ldj;
+    int ldj_mode, base_log_prob, inverse;
+    long long rows;
+    int n_tiles;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float v) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fdiv(float a, float b) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    const float q = a * r;
+    return fmaf(fmaf(-q, b, a), r, q);
+}
+__device__ __forceinline__ float tanh_fast(float v) {                 // ~3e-7 absolute error
+    const float t = ex2_approx(-2.885390081777927f * fabsf(v));
+    return copysignf(fdiv(1.f - t, 1.f + t), v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* xs = reinterpret_cast<float*>(smem + kSmXs);
+    uint8_t* ring = smem + kSmRing;
+    const Header* hdr = reinterpret_cast<const Header*>(smem + kSmSmall);
+    const float* b1s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB1);
+    const float* b2s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB2);
+    const float* b3s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB3);
+    float* ld_s = reinterpret_cast<float*>(smem + kSmLd);
+    Bars* bars = reinterpret_cast<Bars*>(smem + kSmBar);
+    uint8_t* abuf = smem + kSmA;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        mbar_init(&bars->setup, 1);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        mbar_init(&bars->a_ready, 16);
+        mbar_init(&bars->acc_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars->setup, kSmallBytes);
+        bulk_g2s(smem + kSmSmall, A.packed, kSmallBytes, &bars->setup);
+    }
+    mbar_wait(&bars->setup, 0);
+
+    const int d = hdr->dim, n_tr = hdr->n_tr, n_cond = hdr->n_cond, H = hdr->H, n_hidden = hdr->n_hidden;
+    const int act = hdr->act;
+    const int kb_h = H / 16;                                   // K blocks of a GEMM whose K is H
+    const uint32_t a_part = (uint32_t)kRows * kK1 * 2;         // 8192: one bf16 part of A1
+    const uint32_t a_lo = (uint32_t)kRows * H * 2;             // byte offset of the lo half of the A operand
+    const uint32_t a_sbo = (uint32_t)(H / 8) * 128;
+    const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int blocks_per_tile = 6 + (n_hidden == 2 ? kb_h : 0) + kb_h;
+    const uint32_t w1b = w1_block_bytes(H), w2b = w2_block_bytes(H), w3b = w3_block_bytes();
+
+    if (warp == 0) {
+        // ======================= producer =========================================================
+        if (lane == 0) {
+            uint32_t cc = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                if (it + 1 < my_tiles) {
+                    const long long nrow0 = ((long long)blockIdx.x + (long long)(it + 1) * gridDim.x) * kRows;
+                    const long long nb = min((long long)kRows, A.rows - nrow0) * d * 4;
+                    const char* src = reinterpret_cast<const char*>(A.x + nrow0 * d);
+                    if (nb >= 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(nb & ~15LL)) : "memory");
+                }
+                const uint8_t* src = A.packed + kOffW;
+                for (int b = 0; b < blocks_per_tile; ++b, ++cc) {
+                    const uint32_t bytes = (b < 6) ? w1b : ((n_hidden == 2 && b < 6 + kb_h) ? w2b : w3b);
+                    const uint32_t st = cc % kStages, use = cc / kStages;
+                    mbar_wait_relaxed(&bars->empty[st], (use & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->full[st], bytes);
+                    bulk_g2s(ring + st * kSlotBytes, src, bytes, &bars->full[st]);
+                    src += bytes;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= UMMA issuer ======================================================
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, H);
+            const uint32_t idesc2 = make_idesc(FMT_F16, 128, H);
+            const uint32_t idesc3 = make_idesc(FMT_F16, 128, kNOut);
+            const uint32_t a0 = smem_u32(abuf);
+            const uint32_t dmain = tmem + kColMain, dcorr = tmem + kColCorr;
+            uint32_t cc = 0, ause = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                // ---- layer 1: bf16x3 x bf16x3, blocks ordered (pb = 2, 1, 0) x (kb = 0, 1) -------------
+                mbar_wait_relaxed(&bars->a_ready, ause & 1); ++ause;
+                tc_fence_after();
+                uint32_t acc_m = 0, acc_c = 0;
+                for (int b = 0; b < 6; ++b, ++cc) {
+                    const int pb = 2 - b / 2, kb = b & 1;
+                    const uint32_t st = cc % kStages, use = cc / kStages;
+                    mbar_wait_relaxed(&bars->full[st], use & 1);
+                    tc_fence_after();
+                    const uint64_t bd = make_smem_desc(smem_u32(ring + st * kSlotBytes), 128, 256);
+                    for (int pa = 2; pa >= 0; --pa) {
+                        if (pa == 2 && pb == 2) continue;
+                        const uint64_t ad = make_smem_desc(a0 + pa * a_part + kb * 256, 128, 512);
+                        if (pa == 0 && pb == 0) { umma_f16(dmain, ad, bd, idesc1, acc_m); acc_m = 1; }
+                        else { umma_f16(dcorr, ad, bd, idesc1, acc_c); acc_c = 1; }
+                    }
+                    umma_commit(&bars->empty[st]);
+                }
+                umma_commit(&bars->acc_ready);
+                // ---- hidden -> hidden (optional) and hidden -> output: fp16 hi | lo -------------------
+                for (int layer = (n_hidden == 2 ? 0 : 1); layer < 2; ++layer) {
+                    mbar_wait_relaxed(&bars->a_ready, ause & 1); ++ause;
+                    tc_fence_after();
+                    const bool last = (layer == 1);
+                    const uint32_t idesc = last ? idesc3 : idesc2;
+                    const uint32_t lo_off = last ? kNOut * 32 : (uint32_t)H * 32;     // lo half inside a block
+                    acc_m = acc_c = 0;
+                    for (int kb = 0; kb < kb_h; ++kb, ++cc) {
+                        const uint32_t st = cc % kStages, use = cc / kStages;
+                        mbar_wait_relaxed(&bars->full[st], use & 1);
+                        tc_fence_after();
+                        const uint32_t bb = smem_u32(ring + st * kSlotBytes);
+                        const uint64_t b_hi = make_smem_desc(bb, 128, 256), b_lo = make_smem_desc(bb + lo_off, 128, 256);
+                        const uint64_t a_hi = make_smem_desc(a0 + kb * 256, 128, a_sbo);
+                        const uint64_t a_l = make_smem_desc(a0 + a_lo + kb * 256, 128, a_sbo);
+                        umma_f16(dcorr, a_l, b_hi, idesc, acc_c); acc_c = 1;
+                        umma_f16(dcorr, a_hi, b_lo, idesc, 1);
+                        umma_f16(dmain, a_hi, b_hi, idesc, acc_m); acc_m = 1;
+                        umma_commit(&bars->empty[st]);
+                    }
+                    umma_commit(&bars->acc_ready);
+                }
+            }
+        }
+    } else {
+        // ======================= epilogue warps ====================================================
+        const int q = warp & 3;
+        const int cg = (warp - ((q >= kEpiWarp0) ? q : q + 4)) >> 2;      // column group 0..3
+        const int etid = tid - kEpiWarp0 * 32;
+        const int row = q * 32 + lane;
+        float* xrow = xs + row * kXsStride;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
+        const bool inverse = A.inverse != 0;
+        const float s_mid = hdr->s_mid, s_out = hdr->s_out;
+        uint32_t acc_use = 0;
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * kRows;
+            const int nrows = (int)min((long long)kRows, A.rows - row0);
+            // ---- stage x -----------------------------------------------------------------------------
+            {
+                const float* xg = A.x + row0 * d;
+                const int n = nrows * d;
+                for (int i = etid; i < kRows * d; i += kEpiThreads) {
+                    const int r = i / d, c = i - r * d;
+                    xs[r * kXsStride + c] = (i < n) ? __ldg(xg + i) : 0.f;
+                }
+            }
+            named_bar_sync(1, kEpiThreads);
+            // ---- A1: 8 of the 32 conditioning columns of this row, three bf16 parts ---------------------
+            {
+                const uint32_t off = (uint32_t)(row >> 3) * 512 + (uint32_t)(row & 7) * 16 + cg * 128;
+                __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = cg * 8 + u;
+                    const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : 0.f;
+                    split_bf16x3(v, q0[u], q1[u], q2[u]);
+                }
+                *reinterpret_cast<uint4*>(abuf + off) = *reinterpret_cast<const uint4*>(q0);
+                *reinterpret_cast<uint4*>(abuf + a_part + off) = *reinterpret_cast<const uint4*>(q1);
+                *reinterpret_cast<uint4*>(abuf + 2 * a_part + off) = *reinterpret_cast<const uint4*>(q2);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_ready);
+            }
+            // ---- hidden layers: h = act((main + corr) * s + b) -> fp16 hi | lo A operand -----------------
+            for (int layer = 0; layer < n_hidden; ++layer) {
+                mbar_wait(&bars->acc_ready, acc_use & 1); ++acc_use;
+                tc_fence_after();
+                const float sc = (layer == 0) ? 1.f : s_mid;
+                const float* bias = (layer == 0) ? b1s : b2s;
+                const int cols = H / 4;                          // this warp's share of the hidden units
+                const uint32_t a_row = (uint32_t)(row >> 3) * a_sbo + (uint32_t)(row & 7) * 16;
+                for (int cb = 0; cb < cols; cb += 16) {
+                    const int c0 = cg * cols + cb;
+                    float vm[16], vc[16];
+                    tmem_ld16(tmem + lane_sel + kColMain + c0, vm);
+                    tmem_ld16(tmem + lane_sel + kColCorr + c0, vc);
+                    tmem_ld_wait();
+                    __align__(16) __half hh[16], hl[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float pre = fmaf(vm[i] + vc[i], sc, bias[c0 + i]);
+                        const float hv = (act == STB_ACT_TANH) ? tanh_fast(pre) : activate(act, pre);
+                        split_f16(hv, hh[i], hl[i]);
+                    }
+#pragma unroll
+                    for (int half8 = 0; half8 < 2; ++half8) {
+                        const int kc = (c0 >> 3) + half8;
+                        *reinterpret_cast<uint4*>(abuf + a_row + kc * 128) = *reinterpret_cast<const uint4*>(hh + half8 * 8);
+                        *reinterpret_cast<uint4*>(abuf + a_lo + a_row + kc * 128) = *reinterpret_cast<const uint4*>(hl + half8 * 8);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_ready);
+            }
+            // ---- output layer: [log_scale | shift] of this warp's 8 transformed dims ---------------------
+            mbar_wait(&bars->acc_ready, acc_use & 1); ++acc_use;
+            tc_fence_after();
+            float ld_acc = 0.f;
+            {
+                float lm[8], lc[8], sm[8], sc_[8];
+                tmem_ld8(tmem + lane_sel + kColMain + cg * 8, lm);
+                tmem_ld8(tmem + lane_sel + kColCorr + cg * 8, lc);
+                tmem_ld8(tmem + lane_sel + kColMain + kMaxTr + cg * 8, sm);
+                tmem_ld8(tmem + lane_sel + kColCorr + kMaxTr + cg * 8, sc_);
+                tmem_ld_wait();
+                tc_fence_before();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int ji = cg * 8 + u;
+                    if (ji < n_tr) {
+                        const int j = hdr->tr_idx[ji];
+                        const float ls = fmaf(lm[u] + lc[u], s_out, b3s[ji]);
+                        const float sh = fmaf(sm[u] + sc_[u], s_out, b3s[kMaxTr + ji]);
+                        const float xv = xrow[j];
+                        if (inverse) { xrow[j] = (xv - sh) * expf(-ls); ld_acc -= ls; }
+                        else { xrow[j] = xv * expf(ls) + sh; ld_acc += ls; }
+                    }
+                }
+            }
+            ld_s[cg * kRows + row] = ld_acc;
+            named_bar_sync(1, kEpiThreads);
+            if (cg == 0 && want_ld && row < nrows) {
+                float tot = (ld_s[row] + ld_s[kRows + row]) + (ld_s[2 * kRows + row] + ld_s[3 * kRows + row]);
+                if (A.base_log_prob) {
+                    float b = 0.f;
+                    for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
+                    tot += b;
+                }
+                float* dst = A.ldj + row0 + row;
+                *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
+            }
+            {
+                float* yg = A.y + row0 * d;
+                const int n = nrows * d;
+                for (int i = etid; i < n; i += kEpiThreads) {
+                    const int r = i / d, c = i - r * d;
+                    yg[i] = xs[r * kXsStride + c];
+                }
+            }
+            named_bar_sync(1, kEpiThreads);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+// -----------------------------------------------------------------------------------------------
+// packing
+// -----------------------------------------------------------------------------------------------
+struct PackArgs {
+    const float *W1, *b1, *W2, *b2, *W3, *b3;
+    uint8_t* out;
+    int dim, n_cond, n_tr, H, n_hidden, act;
+    int cond_idx[kK1];
+    int tr_idx[kMaxTr];
+};
+
+__device__ __forceinline__ int out_row_affine(const PackArgs& a, int n) {     // packed output column -> Linear row
+    const int p = n / kMaxTr, ji = n % kMaxTr;
+    return (ji < a.n_tr) ? p * a.dim + a.tr_idx[ji] : -1;
+}
+
+__global__ void tcm_maxabs_kernel(const PackArgs a) {
+    Header* hdr = reinterpret_cast<Header*>(a.out);
+    float m2 = 0.f, m3 = 0.f;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (a.n_hidden == 2)
+        for (int i = gtid; i < a.H * a.H; i += gsz) m2 = fmaxf(m2, fabsf(a.W2[i]));
+    for (int i = gtid; i < kNOut * a.H; i += gsz) {
+        const int r = out_row_affine(a, i / a.H);
+        if (r >= 0) m3 = fmaxf(m3, fabsf(a.W3[(size_t)r * a.H + i % a.H]));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&hdr->max_mid, __float_as_uint(m2));
+        atomicMax(&hdr->max_out, __float_as_uint(m3));
+    }
+}
+
+__device__ __forceinline__ float pow2_scale(float mx) {
+    if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+    int ex;
+    const float fr = frexpf(mx, &ex);
+    return ldexpf(1.f, (fr == 0.5f) ? ex - 1 : ex);
+}
+// element (n, k) of an [N x 16] K-major block: 2 chunks of 8 elements per row
+__device__ __forceinline__ uint32_t blk_off(int n, int k) {
+    return (uint32_t)((n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2);
+}
+
+__global__ void tcm_pack_kernel(const PackArgs a) {
+    Header* hdr = reinterpret_cast<Header*>(a.out);
+    const float s_mid = pow2_scale(__uint_as_float(hdr->max_mid)), s_out = pow2_scale(__uint_as_float(hdr->max_out));
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    const int H = a.H;
+    if (gtid == 0) {
+        hdr->magic = kMagic; hdr->dim = a.dim; hdr->n_cond = a.n_cond; hdr->n_tr = a.n_tr; hdr->H = H;
+        hdr->n_hidden = a.n_hidden; hdr->act = a.act; hdr->s_mid = s_mid; hdr->s_out = s_out;
+        for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
+        for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
+    }
+    float* b1 = reinterpret_cast<float*>(a.out + kOffB1);
+    float* b2 = reinterpret_cast<float*>(a.out + kOffB2);
+    float* b3 = reinterpret_cast<float*>(a.out + kOffB3);
+    for (int i = gtid; i < kMaxH; i += gsz) {
+        b1[i] = (i < H) ? a.b1[i] : 0.f;
+        b2[i] = (i < H && a.n_hidden == 2) ? a.b2[i] : 0.f;
+    }
+    for (int i = gtid; i < kNOut; i += gsz) {
+        const int r = out_row_affine(a, i);
+        b3[i] = (r >= 0) ? a.b3[r] : 0.f;
+    }
+    // layer 1: blocks (pb = 2, 1, 0) x (kb = 0, 1), each [H x 16] of bf16 part pb
+    uint8_t* w = a.out + kOffW;
+    for (int i = gtid; i < H * kK1; i += gsz) {
+        const int n = i / kK1, k = i % kK1;
+        const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.dim + a.cond_idx[k]] : 0.f;
+        __nv_bfloat16 q[3];
+        split_bf16x3(v, q[0], q[1], q[2]);
+        for (int pb = 0; pb < 3; ++pb) {
+            const int b = (2 - pb) * 2 + (k >> 4);
+            *reinterpret_cast<__nv_bfloat16*>(w + (size_t)b * w1_block_bytes(H) + blk_off(n, k & 15)) = q[pb];
+        }
+    }
+    w += 6 * w1_block_bytes(H);
+    if (a.n_hidden == 2) {
+        const float inv = 1.f / s_mid;
+        for (int i = gtid; i < H * H; i += gsz) {
+            const int n = i / H, k = i % H;
+            __half hi, lo;
+            split_f16(a.W2[i] * inv, hi, lo);
+            uint8_t* blk = w + (size_t)(k >> 4) * w2_block_bytes(H);
+            *reinterpret_cast<__half*>(blk + blk_off(n, k & 15)) = hi;
+            *reinterpret_cast<__half*>(blk + H * 32 + blk_off(n, k & 15)) = lo;
+        }
+        w += (size_t)(H / 16) * w2_block_bytes(H);
+    }
+    {
+        const float inv = 1.f / s_out;
+        for (int i = gtid; i < kNOut * H; i += gsz) {
+            const int n = i / H, k = i % H;
+            const int r = out_row_affine(a, n);
+            __half hi, lo;
+            split_f16(r >= 0 ? a.W3[(size_t)r * H + k] * inv : 0.f, hi, lo);
+            uint8_t* blk = w + (size_t)(k >> 4) * w3_block_bytes();
+            *reinterpret_cast<__half*>(blk + blk_off(n, k & 15)) = hi;
+            *reinterpret_cast<__half*>(blk + kNOut * 32 + blk_off(n, k & 15)) = lo;
+        }
+    }
+}
+
+static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
+    if (!L->mask_host) return false;
+    a.n_cond = a.n_tr = 0;
+    for (int j = 0; j < L->dim; ++j) {
+        if (L->mask_host[j]) { if (a.n_cond >= kK1) return false; a.cond_idx[a.n_cond++] = j; }
+        else { if (a.n_tr >= kMaxTr) return false; a.tr_idx[a.n_tr++] = j; }
+    }
+    for (int i = a.n_cond; i < kK1; ++i) a.cond_idx[i] = 0;
+    for (int i = a.n_tr; i < kMaxTr; ++i) a.tr_idx[i] = 0;
+    if (a.n_tr < 1) return false;
+    const stb_mlp& N = L->net;
+    a.dim = L->dim; a.H = N.dims[1]; a.n_hidden = N.n_linear - 1; a.act = N.activation;
+    a.W1 = N.W[0]; a.b1 = N.b[0];
+    a.W2 = a.n_hidden == 2 ? N.W[1] : nullptr; a.b2 = a.n_hidden == 2 ? N.b[1] : nullptr;
+    a.W3 = N.W[N.n_linear - 1]; a.b3 = N.b[N.n_linear - 1];
+    return true;
+}
+
+}  // namespace tcm
+
+bool tcm_layer_supported(const stb_layer* L) {
+    using namespace tcm;
+    if (L->kind != STB_AFFINE || !L->cond_x || L->zero_cond || L->latent_dim != 0 || L->time_input) return false;
+    if (L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
+    const stb_mlp& N = L->net;
+    if ((N.n_linear != 2 && N.n_linear != 3) || N.final_activation != STB_ACT_NONE) return false;
+    const int H = N.dims[1];
+    if (H < 64 || H > kMaxH || (H % 64) != 0) return false;
+    if (N.n_linear == 3 && N.dims[2] != H) return false;
+    PackArgs a;
+    return fill_pack_args(L, a);
+}
+
+uint64_t tcm_packed_bytes(const stb_layer* L) { return tcm::packed_bytes(L->net.dims[1], L->net.n_linear - 1); }
+
+int tcm_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
+    using namespace tcm;
+    PackArgs a;
+    if (!fill_pack_args(L, a)) return set_error(STB_ENOTSUP, "layer has no tensor-core path");
+    a.out = static_cast<uint8_t*>(out);
+    cudaError_t e = cudaMemsetAsync(out, 0, kOffW, stream);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "memset: %s", cudaGetErrorString(e));
+    tcm_maxabs_kernel<<<64, 256, 0, stream>>>(a);
+    count_launch();
+    tcm_pack_kernel<<<296, 256, 0, stream>>>(a);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tcm_pack launch: %s", cudaGetErrorString(e));
+    return STB_OK;
+}
+
+int tcm_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
+                    int base_log_prob, int64_t rows, cudaStream_t stream) {
+    using namespace tcm;
+    const int H = L->net.dims[1];
+    if (L->packed_bytes < packed_bytes(H, L->net.n_linear - 1)) return set_error(STB_EINVAL, "packed image too small");
+    Args A;
+    A.packed = static_cast<const uint8_t*>(L->packed);
+    A.x = x; A.y = y; A.ldj = ldj;
+    A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
+    A.base_log_prob = base_log_prob;
+    A.inverse = direction == STB_INVERSE;
+    A.rows = rows;
+    const long long tiles = (rows + kRows - 1) / kRows;
+    if (tiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
+    A.n_tiles = (int)tiles;
+    static thread_local int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const uint32_t smem = smem_bytes(H);
+    if (smem > 227 * 1024) return set_error(STB_ENOTSUP, "hidden width %d needs %u B of shared memory", H, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_mlp_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int grid = (int)min((long long)n_sm, tiles);
+    tc_mlp_affine_kernel<<<grid, kThreads, smem, stream>>>(A);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_mlp_affine_kernel launch: %s", cudaGetErrorString(e));
+    return STB_OK;
+}
+
+}  // namespace stb

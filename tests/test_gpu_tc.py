@@ -115,6 +115,45 @@ def test_tensor_path_matches_generic_and_oracle(kind, d, masks, monkeypatch):
     assert (yf_t - yf_g).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize('d,hidden,masks', [(64, [256, 256], cases.ALT), (64, [64], ('parity_even', 'parity_odd')),
+                                            (30, [128, 128], cases.ALT), (63, [192], ('ordered_left_half', 'parity_odd')),
+                                            (2, [64, 64], cases.ALT)])
+def test_affine_tensor_path_matches_generic_and_oracle(d, hidden, masks, monkeypatch):
+    """tc_mlp.cu (affine coupling, wide conditioner on tcgen05) vs the generic kernel and the oracle."""
+    case = cases._mk_flow('affine', d, hidden, 3, 0, 700, 700 + d + len(hidden), masks=masks, scale=1.3)()
+    spec = case['spec']
+    x = case['inputs']['x'].to(DEV)
+
+    def build():
+        layers = [l.to(DEV) for l in layers_from_spec(spec)]
+        return st.NormalizingFlow(st.UnitNormal(d), layers), layers
+
+    tflow, tl = build()
+    with torch.no_grad():
+        desc = tl[0].describe(d, 0, torch.device(DEV))
+        assert desc['packed'] is not None, 'tensor path was not selected'
+        lp_t = tflow.log_prob(x)
+        xi_t, li_t = tflow.inverse_and_log_det_jacobian(x)
+        yf_t, lf_t = tflow.forward_and_log_det_jacobian(x)
+    monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', '1')
+    gflow, _ = build()
+    with torch.no_grad():
+        lp_g = gflow.log_prob(x)
+        xi_g, li_g = gflow.inverse_and_log_det_jacobian(x)
+    xc = x.cpu()
+    s64 = O.spec_to(spec, torch.float64)
+    for got, f32, f64, what in (
+            (lp_t, O.flow_log_prob(spec, xc), O.flow_log_prob(s64, xc.double()), 'log_prob'),
+            (xi_t, O.flow_inverse(spec, xc), O.flow_inverse(s64, xc.double()), 'inverse x'),
+            (li_t, O.flow_inverse(spec, xc, with_ldj=True)[1], O.flow_inverse(s64, xc.double(), with_ldj=True)[1], 'inverse ldj'),
+            (yf_t, O.flow_forward(spec, xc), O.flow_forward(s64, xc.double()), 'forward y'),
+            (lf_t, O.flow_forward(spec, xc, with_ldj=True)[1], O.flow_forward(s64, xc.double(), with_ldj=True)[1], 'forward ldj')):
+        fail, _, mx = close_or_arbitrated(got, f32, f64, 1e-5, 1e-5)
+        assert fail <= 2e-3, f'{what}: {fail:.3%} outside tolerance (max abs err {mx:.3e})'
+    assert (lp_t - lp_g).abs().max().item() < 2e-4 and (xi_t - xi_g).abs().max().item() < 2e-4
+    assert (li_t - li_g).abs().max().item() < 2e-4
+
+
 @pytest.mark.parametrize('kind', ['quadratic', 'cubic'])
 def test_tensor_path_box_ends_forward(kind):
     """x exactly on the box ends (bin 0 / bin K-1 through the nudged last knot, search_sorted.py:4)
