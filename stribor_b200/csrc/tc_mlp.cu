@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
     const uint32_t a_part = (uint32_t)kRows * kK1 * 2;         // 8192: one bf16 part of A1
     const uint32_t a_lo = (uint32_t)kRows * H * 2;             // byte offset of the lo half of the A operand
     const uint32_t a_sbo = (uint32_t)(H / 8) * 128;
+    const int dshift = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;
     const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int blocks_per_tile = 6 + (n_hidden == 2 ? kb_h : 0) + kb_h;
     const uint32_t w1b = w1_block_bytes(H), w2b = w2_block_bytes(H), w3b = w3_block_bytes();
@@ -188,13 +189,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
             uint32_t cc = 0, ause = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 // ---- layer 1: bf16x3 x bf16x3, blocks ordered (pb = 2, 1, 0) x (kb = 0, 1) -------------
-                mbar_wait_relaxed(&bars->a_ready, ause & 1); ++ause;
+                mbar_wait(&bars->a_ready, ause & 1); ++ause;
                 tc_fence_after();
                 uint32_t acc_m = 0, acc_c = 0;
                 for (int b = 0; b < 6; ++b, ++cc) {
                     const int pb = 2 - b / 2, kb = b & 1;
                     const uint32_t st = cc % kStages, use = cc / kStages;
-                    mbar_wait_relaxed(&bars->full[st], use & 1);
+                    mbar_wait(&bars->full[st], use & 1);
                     tc_fence_after();
                     const uint64_t bd = make_smem_desc(smem_u32(ring + st * kSlotBytes), 128, 256);
                     for (int pa = 2; pa >= 0; --pa) {
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                 umma_commit(&bars->acc_ready);
                 // ---- hidden -> hidden (optional) and hidden -> output: fp16 hi | lo -------------------
                 for (int layer = (n_hidden == 2 ? 0 : 1); layer < 2; ++layer) {
-                    mbar_wait_relaxed(&bars->a_ready, ause & 1); ++ause;
+                    mbar_wait(&bars->a_ready, ause & 1); ++ause;
                     tc_fence_after();
                     const bool last = (layer == 1);
                     const uint32_t idesc = last ? idesc3 : idesc2;
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                     acc_m = acc_c = 0;
                     for (int kb = 0; kb < kb_h; ++kb, ++cc) {
                         const uint32_t st = cc % kStages, use = cc / kStages;
-                        mbar_wait_relaxed(&bars->full[st], use & 1);
+                        mbar_wait(&bars->full[st], use & 1);
                         tc_fence_after();
                         const uint32_t bb = smem_u32(ring + st * kSlotBytes);
                         const uint64_t b_hi = make_smem_desc(bb, 128, 256), b_lo = make_smem_desc(bb + lo_off, 128, 256);
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                 const float* xg = A.x + row0 * d;
                 const int n = nrows * d;
                 for (int i = etid; i < kRows * d; i += kEpiThreads) {
-                    const int r = i / d, c = i - r * d;
+                    const int r = (dshift >= 0) ? (i >> dshift) : i / d, c = i - r * d;
                     xs[r * kXsStride + c] = (i < n) ? __ldg(xg + i) : 0.f;
                 }
             }
@@ -289,11 +290,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                     tmem_ld16(tmem + lane_sel + kColCorr + c0, vc);
                     tmem_ld_wait();
                     __align__(16) __half hh[16], hl[16];
+                    if (act == STB_ACT_TANH) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float pre = fmaf(vm[i] + vc[i], sc, bias[c0 + i]);
-                        const float hv = (act == STB_ACT_TANH) ? tanh_fast(pre) : activate(act, pre);
-                        split_f16(hv, hh[i], hl[i]);
+                        for (int i = 0; i < 16; ++i)
+                            split_f16(tanh_fast(fmaf(vm[i] + vc[i], sc, bias[c0 + i])), hh[i], hl[i]);
+                    } else {
+#pragma unroll 1
+                        for (int i = 0; i < 16; ++i) vm[i] = activate(act, fmaf(vm[i] + vc[i], sc, bias[c0 + i]));
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) split_f16(vm[i], hh[i], hl[i]);
                     }
 #pragma unroll
                     for (int half8 = 0; half8 < 2; ++half8) {
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                 float* yg = A.y + row0 * d;
                 const int n = nrows * d;
                 for (int i = etid; i < n; i += kEpiThreads) {
-                    const int r = i / d, c = i - r * d;
+                    const int r = (dshift >= 0) ? (i >> dshift) : i / d, c = i - r * d;
                     yg[i] = xs[r * kXsStride + c];
                 }
             }
