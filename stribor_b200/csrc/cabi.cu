@@ -31,7 +31,7 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     if (L->packed && !ldiag && tc_layer_supported(L))
         return tc_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s);
     if (L->packed && !ldiag && tcm_layer_supported(L))
-        return tcm_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s);
+        return tcm_layer_apply(L, direction, x, t, y, ldj, ldj_mode, base_lp, rows, s);
     return generic_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, ldiag, rows, s);
 }
 

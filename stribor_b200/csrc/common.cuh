@@ -29,8 +29,8 @@ int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, 
 bool tcm_layer_supported(const stb_layer* L);
 uint64_t tcm_packed_bytes(const stb_layer* L);
 int tcm_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
-int tcm_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj,
-                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
+int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const float* t, float* y,
+                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
 
 // backward (backward.cu)
 uint64_t layer_backward_workspace_bytes(const stb_layer* L, int64_t rows);

@@ -1,7 +1,10 @@
 // Tensor-core fused AFFINE coupling layer with a wide conditioner (tcgen05 + TMEM + bulk copies).
 //
 // Scope: st.Coupling(st.Affine(dim <= 64, latent_net = MLP(dim, [H] or [H, H], 2 dim)), mask),
-// H in {64, 128, 192, 256}, no latent input -- BASELINE.json configs[1] (MLP[256,256]).  Here the
+// H in {64, 128, 192, 256}, no latent input -- BASELINE.json configs[1] (MLP[256,256]) -- and
+// st.ContinuousAffineCoupling(MLP(dim (+1), [H] or [H, H], 2 dim), TimeLinear(2 dim), mask)
+// (configs[3], flows/coupling.py:188-213: the time column joins the conditioning columns, the
+// affine parameters are multiplied by scale * t in the epilogue).  Here the
 // conditioner IS the work (2 * (32 H + H^2 + 64 H) flop per row-layer against 520 B), so the layout
 // is a plain chain of GEMMs with the activations kept on chip:
 //
@@ -49,7 +52,9 @@ struct Header {                            // 1024 bytes
     uint32_t max_mid, max_out;             // scratch (max |W| bits)
     int32_t cond_idx[kK1];
     int32_t tr_idx[kMaxTr];
-    int32_t pad[256 - 11 - kK1 - kMaxTr];
+    int32_t cont, time_col;                // continuous-affine: scale by the time embedding; A1 column holding t (-1: none)
+    float ts_ls[kMaxTr], ts_sh[kMaxTr];    // TimeLinear.scale of the transformed dims (log-scale half | shift half)
+    int32_t pad[256 - 13 - kK1 - 3 * kMaxTr];
 };
 static_assert(sizeof(Header) == 1024, "header layout");
 // packed image: header | b1[256] | b2[256] | b3[64] | pad to 4096 | W blocks (see pack kernel)
@@ -69,7 +74,8 @@ constexpr uint32_t kSmXs = 0;                                        // float [1
 constexpr uint32_t kSmRing = kSmXs + kRows * kXsStride * 4;          // 3 x 16 KB
 constexpr uint32_t kSmSmall = kSmRing + kStages * kSlotBytes;        // header + biases
 constexpr uint32_t kSmLd = kSmSmall + 3584;                          // float [4][128] log-det partials
-constexpr uint32_t kSmBar = kSmLd + 4 * kRows * 4;
+constexpr uint32_t kSmT = kSmLd + 4 * kRows * 4;                     // float [128] time input
+constexpr uint32_t kSmBar = kSmT + kRows * 4;
 constexpr uint32_t kSmA = kSmBar + 256;                              // A operand: 128 x H fp16 hi | lo (>= 24 KB)
 static_assert(kSmRing % 16 == 0 && kSmSmall % 16 == 0 && kSmA % 16 == 0, "alignment");
 __host__ __device__ inline uint32_t smem_bytes(int H) { return kSmA + (uint32_t)kRows * H * 4; }
@@ -86,6 +92,7 @@ constexpr uint32_t kColMain = 0, kColCorr = 256, kTmemCols = 512;
 struct Args {
     const uint8_t* packed;
     const float* x;
+    const float* t;
     float* y;
     float* ldj;
     int ldj_mode, base_log_prob, inverse;
@@ -121,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
     const float* b2s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB2);
     const float* b3s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB3);
     float* ld_s = reinterpret_cast<float*>(smem + kSmLd);
+    float* t_s = reinterpret_cast<float*>(smem + kSmT);
     Bars* bars = reinterpret_cast<Bars*>(smem + kSmBar);
     uint8_t* abuf = smem + kSmA;
 
@@ -256,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                     const int r = (dshift >= 0) ? (i >> dshift) : i / d, c = i - r * d;
                     xs[r * kXsStride + c] = (i < n) ? __ldg(xg + i) : 0.f;
                 }
+                if (etid < kRows) t_s[etid] = (A.t != nullptr && etid < nrows) ? __ldg(A.t + row0 + etid) : 0.f;
             }
             named_bar_sync(1, kEpiThreads);
             // ---- A1: 8 of the 32 conditioning columns of this row, three bf16 parts ---------------------
@@ -265,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int k = cg * 8 + u;
-                    const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : 0.f;
+                    const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[row] : 0.f);
                     split_bf16x3(v, q0[u], q1[u], q2[u]);
                 }
                 *reinterpret_cast<uint4*>(abuf + off) = *reinterpret_cast<const uint4*>(q0);
@@ -329,8 +338,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                     const int ji = cg * 8 + u;
                     if (ji < n_tr) {
                         const int j = hdr->tr_idx[ji];
-                        const float ls = fmaf(lm[u] + lc[u], s_out, b3s[ji]);
-                        const float sh = fmaf(sm[u] + sc_[u], s_out, b3s[kMaxTr + ji]);
+                        float ls = fmaf(lm[u] + lc[u], s_out, b3s[ji]);
+                        float sh = fmaf(sm[u] + sc_[u], s_out, b3s[kMaxTr + ji]);
+                        if (hdr->cont) {                       // coupling.py:199-205
+                            const float tv = t_s[row];
+                            ls *= hdr->ts_ls[ji] * tv;
+                            sh *= hdr->ts_sh[ji] * tv;
+                        }
                         const float xv = xrow[j];
                         if (inverse) { xrow[j] = (xv - sh) * expf(-ls); ld_acc -= ls; }
                         else { xrow[j] = xv * expf(ls) + sh; ld_acc += ls; }
@@ -369,9 +383,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
 // packing
 // -----------------------------------------------------------------------------------------------
 struct PackArgs {
-    const float *W1, *b1, *W2, *b2, *W3, *b3;
+    const float *W1, *b1, *W2, *b2, *W3, *b3, *time_scale;
     uint8_t* out;
-    int dim, n_cond, n_tr, H, n_hidden, act;
+    int dim, n_cond, n_tr, H, n_hidden, act, in_dim, cont, time_col;
     int cond_idx[kK1];
     int tr_idx[kMaxTr];
 };
@@ -423,6 +437,11 @@ __global__ void tcm_pack_kernel(const PackArgs a) {
         hdr->n_hidden = a.n_hidden; hdr->act = a.act; hdr->s_mid = s_mid; hdr->s_out = s_out;
         for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
         for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
+        hdr->cont = a.cont; hdr->time_col = a.time_col;
+        for (int i = 0; i < kMaxTr; ++i) {
+            hdr->ts_ls[i] = (a.cont && i < a.n_tr) ? a.time_scale[a.tr_idx[i]] : 0.f;
+            hdr->ts_sh[i] = (a.cont && i < a.n_tr) ? a.time_scale[a.dim + a.tr_idx[i]] : 0.f;
+        }
     }
     float* b1 = reinterpret_cast<float*>(a.out + kOffB1);
     float* b2 = reinterpret_cast<float*>(a.out + kOffB2);
@@ -439,7 +458,8 @@ __global__ void tcm_pack_kernel(const PackArgs a) {
     uint8_t* w = a.out + kOffW;
     for (int i = gtid; i < H * kK1; i += gsz) {
         const int n = i / kK1, k = i % kK1;
-        const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.dim + a.cond_idx[k]] : 0.f;
+        const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.in_dim + a.cond_idx[k]]
+                                       : ((k == a.time_col) ? a.W1[(size_t)n * a.in_dim + a.in_dim - 1] : 0.f);
         __nv_bfloat16 q[3];
         split_bf16x3(v, q[0], q[1], q[2]);
         for (int pb = 0; pb < 3; ++pb) {
@@ -485,6 +505,14 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
     for (int i = a.n_tr; i < kMaxTr; ++i) a.tr_idx[i] = 0;
     if (a.n_tr < 1) return false;
     const stb_mlp& N = L->net;
+    a.in_dim = N.dims[0];
+    a.cont = L->kind == STB_CONT_AFFINE;
+    a.time_col = -1;
+    if (L->time_input) {
+        if (a.n_cond >= kK1) return false;
+        a.time_col = a.n_cond;                                  // first free A1 column
+    }
+    a.time_scale = L->time_scale;
     a.dim = L->dim; a.H = N.dims[1]; a.n_hidden = N.n_linear - 1; a.act = N.activation;
     a.W1 = N.W[0]; a.b1 = N.b[0];
     a.W2 = a.n_hidden == 2 ? N.W[1] : nullptr; a.b2 = a.n_hidden == 2 ? N.b[1] : nullptr;
@@ -496,7 +524,9 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
 
 bool tcm_layer_supported(const stb_layer* L) {
     using namespace tcm;
-    if (L->kind != STB_AFFINE || !L->cond_x || L->zero_cond || L->latent_dim != 0 || L->time_input) return false;
+    if (L->kind != STB_AFFINE && L->kind != STB_CONT_AFFINE) return false;
+    if (!L->cond_x || L->zero_cond || L->latent_dim != 0) return false;
+    if (L->kind == STB_AFFINE && L->time_input) return false;
     if (L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
     const stb_mlp& N = L->net;
     if ((N.n_linear != 2 && N.n_linear != 3) || N.final_activation != STB_ACT_NONE) return false;
@@ -525,14 +555,14 @@ int tcm_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
     return STB_OK;
 }
 
-int tcm_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
-                    int base_log_prob, int64_t rows, cudaStream_t stream) {
+int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const float* t, float* y, float* ldj,
+                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream) {
     using namespace tcm;
     const int H = L->net.dims[1];
     if (L->packed_bytes < packed_bytes(H, L->net.n_linear - 1)) return set_error(STB_EINVAL, "packed image too small");
     Args A;
     A.packed = static_cast<const uint8_t*>(L->packed);
-    A.x = x; A.y = y; A.ldj = ldj;
+    A.x = x; A.t = t; A.y = y; A.ldj = ldj;
     A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
     A.base_log_prob = base_log_prob;
     A.inverse = direction == STB_INVERSE;

@@ -157,7 +157,9 @@ class ContinuousAffineCoupling(Transform):
         meta, params = build_meta(_lib.CONT_AFFINE, dim, latent_dim, 1, bool(self.concatenate_time), 0,
                                   0, dim == 1, self.latent_net, 1, mask_list=mask_list)
         params = list(params) + [self._time_scale(dim).contiguous()]
-        return {'meta': meta, 'fmeta': [0., 1.] * 3, 'mask': mask, 'params': params, 'packed': None}
+        fmeta = [0., 1.] * 3
+        return {'meta': meta, 'fmeta': fmeta, 'mask': mask, 'params': params,
+                'packed': self._packed.get(meta, fmeta, mask, params)}
 
     def _run(self, x, t, latent, direction, want_ldj):
         if t is None:

@@ -154,6 +154,45 @@ def test_affine_tensor_path_matches_generic_and_oracle(d, hidden, masks, monkeyp
     assert (li_t - li_g).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize('concat', [True, False])
+def test_continuous_affine_tensor_path(concat, monkeypatch):
+    """NeuralFlow of ContinuousAffineCoupling layers on the tcgen05 path: oracle parity (with and
+    without t0), agreement with the generic kernel, exact identity at t = 0 (test_neural_flow.py:22-27)."""
+    import numpy as np
+    rs = np.random.RandomState(4242 + concat)
+    d = 16
+    spec = [cases.cont_affine_spec(rs, d, [64], ('ordered_0', 'ordered_1', 'parity_even')[i % 3], concatenate_time=concat)
+            for i in range(4)]
+    x = cases._x(rs, (37, 11, d)).to(DEV)
+    t = cases._x(rs, (37, 11, 1), uniform=True).to(DEV)
+    t0 = cases._x(rs, (37, 11, 1), uniform=True).to(DEV)
+
+    def build():
+        layers = [l.to(DEV) for l in layers_from_spec(spec)]
+        return st.NeuralFlow(layers), layers
+
+    nf, layers = build()
+    with torch.no_grad():
+        assert layers[0].describe(d, 0, torch.device(DEV))['packed'] is not None, 'tensor path was not selected'
+        y = nf(x, t=t)
+        y0 = nf(x, t=t, t0=t0)
+        assert (nf(x, t=torch.zeros_like(t)) == x).all()
+        assert torch.allclose(nf(x, t=t0, t0=t0), x, atol=1e-5)
+    monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', '1')
+    gnf, gl = build()
+    with torch.no_grad():
+        assert gl[0].describe(d, 0, torch.device(DEV))['packed'] is None
+        yg = gnf(x, t=t)
+    assert (y - yg).abs().max().item() < 2e-5
+    s64 = O.spec_to(spec, torch.float64)
+    xc, tc_, t0c = x.cpu(), t.cpu(), t0.cpu()
+    for got, a32, a64 in ((y, O.neural_flow_forward(spec, xc, tc_), O.neural_flow_forward(s64, xc.double(), tc_.double())),
+                          (y0, O.neural_flow_forward(spec, xc, tc_, t0c),
+                           O.neural_flow_forward(s64, xc.double(), tc_.double(), t0c.double()))):
+        fail, _, mx = close_or_arbitrated(got, a32, a64, 1e-5, 1e-5)
+        assert fail <= 1e-3, (fail, mx)
+
+
 @pytest.mark.parametrize('kind', ['quadratic', 'cubic'])
 def test_tensor_path_box_ends_forward(kind):
     """x exactly on the box ends (bin 0 / bin K-1 through the nudged last knot, search_sorted.py:4)
