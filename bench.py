@@ -396,8 +396,13 @@ def main():
     h = [D // 2] + list(args.hidden)
     flops_row = 2 * (sum(a * b for a, b in zip(h[:-1], h[1:])) + h[-1] * (D // 2) * P)
     tflops = rows * flops_row / (launch_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tpath) and args.kind == 'quadratic' and not args.generic:
+        tj = json.load(open(tpath))                             # dram__bytes_{read,write}.sum from ncu --set full
+        traffic = tj['dram_bytes_per_row'] * rows
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                 'kernel': 'fused coupling layer (one launch per layer)',
                 'bytes_per_launch': bytes_per_launch, 'launch_ms': launch_ms,
                 'note': 'BASELINE metric asks for % of HBM peak on L*(8d+8) B/sample; the kernel is '
