@@ -21,6 +21,7 @@ constexpr int kTileRows = 32;
 constexpr int kGenWarps = 4;
 constexpr int kGenThreads = kTileRows * kGenWarps;
 constexpr int kXsStride = kTileRows + 1;
+constexpr int kColStride = kGenThreads + 1;    // padded: conflict-free per-thread AND transposed access
 
 struct GenArgs {
     stb_layer L;
@@ -96,8 +97,8 @@ __global__ void __launch_bounds__(kGenThreads) generic_layer_kernel(const GenArg
     float* xs = smem;                                     // [d][33]
     float* bufA = xs + d * kXsStride;                     // [buf_rows][32]
     float* bufB = bufA + A.buf_rows * kTileRows;          // [buf_rows][32]
-    float* prm = bufB + A.buf_rows * kTileRows;           // [P][128]
-    float* ldj_s = prm + P * kGenThreads;                 // [4][32]
+    float* prm = bufB + A.buf_rows * kTileRows;           // [P][129]
+    float* ldj_s = prm + P * kColStride;                  // [4][32]
     float* t_s = ldj_s + kGenWarps * kTileRows;           // [32]
     int* tr_list = reinterpret_cast<int*>(t_s + kTileRows);   // [d]
     float* lds = reinterpret_cast<float*>(tr_list + d);       // [d][33], only with ldiag
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kGenThreads) generic_layer_kernel(const GenArg
     // ---- last linear + transform, one transformed dim at a time per warp ----------------------
     const bool inverse = (A.direction == STB_INVERSE);
     float ld_acc = 0.f;
-    SmemCol col{prm + tid, kGenThreads};
+    SmemCol col{prm + tid, kColStride};
     for (int it = warp; it < n_tr; it += kGenWarps) {
         const int j = tr_list[it];
         if (nl > 0) {
@@ -199,9 +200,32 @@ __global__ void __launch_bounds__(kGenThreads) generic_layer_kernel(const GenArg
         } else if (L.row_out) {
             const bool aff = (KIND == STB_AFFINE || KIND == STB_CONT_AFFINE);
             const size_t width = (size_t)(L.row_compact ? n_tr : d) * P;
-            const float* ro = L.row_out + (size_t)(row0 + (lane < nrows ? lane : 0)) * width;
-            for (int p = 0; p < P; ++p)
-                col[p] = __ldg(ro + (L.row_compact ? (aff ? p * n_tr + it : it * P + p) : out_row(KIND, d, P, j, p)));
+            if (!aff) {
+                // the P parameters of (row, dim) are contiguous: read row-wise (coalesced), 8 rows in
+                // flight, and transpose through the padded column block of this warp
+                float* pw = prm + warp * 32;
+                const size_t c0 = (size_t)(L.row_compact ? it : j) * P;
+                for (int r0 = 0; r0 < kTileRows; r0 += 8) {
+                    for (int pb = 0; pb < P; pb += 32) {
+                        const int p = pb + lane;
+                        float v[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int r = r0 + u;
+                            v[u] = (p < P && r < nrows) ? __ldg(L.row_out + (size_t)(row0 + r) * width + c0 + p) : 0.f;
+                        }
+                        if (p < P) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) pw[p * kColStride + r0 + u] = v[u];
+                        }
+                    }
+                }
+                __syncwarp();
+            } else {
+                const float* ro = L.row_out + (size_t)(row0 + (lane < nrows ? lane : 0)) * width;
+                for (int p = 0; p < P; ++p)
+                    col[p] = __ldg(ro + (L.row_compact ? p * n_tr + it : out_row(KIND, d, P, j, p)));
+            }
         } else {
             for (int p = 0; p < P; ++p) col[p] = __ldg(L.const_out + out_row(KIND, d, P, j, p));
         }
@@ -338,7 +362,7 @@ int generic_layer_apply(const stb_layer* L, int direction, const float* x, const
     A.x = x; A.latent = latent; A.t = t; A.y = y; A.ldj = ldj; A.ldiag = ldiag; A.rows = rows;
 
     size_t smem = sizeof(float) * ((size_t)L->dim * kXsStride + 2 * (size_t)buf_rows * kTileRows +
-                                   (size_t)A.P * kGenThreads + kGenWarps * kTileRows + kTileRows) +
+                                   (size_t)A.P * kColStride + kGenWarps * kTileRows + kTileRows) +
                   sizeof(int) * (size_t)L->dim + (ldiag ? sizeof(float) * (size_t)L->dim * kXsStride : 0);
     if (smem > 227 * 1024) return set_error(STB_ENOTSUP, "layer needs %zu B of shared memory per tile (> 227 KB)", smem);
 
