@@ -46,7 +46,11 @@ extern "C" {
 #define STB_ENOTSUP (-3)     /* valid in the reference, not built here yet */
 
 /* transform kinds (flows/affine.py, flows/spline.py, flows/coupling.py:98) */
-enum { STB_AFFINE = 0, STB_RQS = 1, STB_CUBIC = 2, STB_CONT_AFFINE = 3 };
+enum { STB_AFFINE = 0, STB_RQS = 1, STB_CUBIC = 2, STB_CONT_AFFINE = 3,
+       /* parameter-free layers that sit between couplings ("next" rows of the scope table):
+        * flows/permute.py:11-82 (Flip of the last dim is the permutation dim-1..0) and
+        * flows/sigmoid.py:9-56 */
+       STB_PERMUTE = 4, STB_SIGMOID = 5, STB_LOGIT = 6 };
 
 /* activations by torch.nn class name (net/mlp.py:38-41) */
 enum { STB_ACT_NONE = 0, STB_ACT_TANH = 1, STB_ACT_RELU = 2, STB_ACT_SIGMOID = 3, STB_ACT_ELU = 4,
@@ -108,6 +112,9 @@ typedef struct stb_layer {
     const float* row_out;      /* device, [rows, out_width]: a precomputed network output
                                   PER ROW (n_linear == 0; takes precedence over const_out) */
     const float* time_scale;   /* device, [2*dim] TimeLinear.scale (cont-affine)          */
+    const int32_t* perm;       /* device, [dim]: STB_PERMUTE forward is y[i] = x[perm[i]];
+                                  perm_inv the inverse permutation                        */
+    const int32_t* perm_inv;
     stb_mlp net;
     const void* packed;        /* device, from stb_pack_layer (NULL = generic path only)  */
     uint64_t packed_bytes;

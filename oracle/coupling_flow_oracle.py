@@ -418,6 +418,29 @@ def layer_apply(layer: Dict, x: Tensor, *, inverse: bool, latent: Optional[Tenso
     which for splines is NOT the inverse branch's own log-derivative.
     """
     typ = layer['type']
+    if typ in ('flip', 'permute'):      # flows/permute.py:11-82: index shuffle, log-det 0
+        if typ == 'flip':
+            out = torch.flip(x, [-1])
+        else:
+            perm = torch.as_tensor(layer['perm']).long()
+            if inverse:
+                inv = torch.empty_like(perm)
+                inv[perm] = torch.arange(perm.numel())
+                perm = inv
+            out = x[..., perm]
+        return out, torch.zeros_like(x[..., :1])
+    if typ in ('sigmoid', 'logit'):     # flows/sigmoid.py:9-56 with the inherited log-det defaults
+        fi = torch.finfo(x.dtype)
+        sig = lambda v: torch.clamp(torch.sigmoid(v), min=fi.tiny, max=1. - fi.eps)
+        def logit(v):
+            v = v.clamp(min=fi.tiny, max=1. - fi.eps)
+            return v.log() - (-v).log1p()
+        ld = lambda u: (-F.softplus(-u) - F.softplus(u)).sum(-1, keepdim=True)
+        to_unit = (typ == 'sigmoid') != inverse
+        if to_unit:                     # sigmoid forward / logit inverse: log-diag at the INPUT
+            return sig(x), ld(x)
+        out = logit(x)                  # sigmoid inverse / logit forward: -log-diag at the OUTPUT
+        return out, -ld(out)
     if typ == 'elementwise':            # stand-alone Affine / Spline (affine.py, spline.py)
         tr = layer['transform']
         out, ld = elementwise(tr, x, latent, inverse)

@@ -13,7 +13,7 @@ STB_MAX_LINEAR = 8
 ABI_VERSION = 1
 
 # enums (include/stribor_b200.h)
-AFFINE, RQS, CUBIC, CONT_AFFINE = 0, 1, 2, 3
+AFFINE, RQS, CUBIC, CONT_AFFINE, PERMUTE, SIGMOID, LOGIT = 0, 1, 2, 3, 4, 5, 6
 FORWARD, INVERSE = 0, 1
 LDJ_NONE, LDJ_SET, LDJ_ADD = 0, 1, 2
 ACTIVATIONS = {None: 0, 'Identity': 0, 'Tanh': 1, 'ReLU': 2, 'Sigmoid': 3, 'ELU': 4, 'Softplus': 5,
@@ -42,7 +42,7 @@ class StbLayer(C.Structure):
                 ('left', C.c_float), ('right', C.c_float), ('bottom', C.c_float), ('top', C.c_float),
                 ('has_box', C.c_int32), ('row_compact', C.c_int32),
                 ('mask', C.c_void_p), ('mask_host', C.c_void_p), ('const_out', C.c_void_p), ('row_out', C.c_void_p),
-                ('time_scale', C.c_void_p),
+                ('time_scale', C.c_void_p), ('perm', C.c_void_p), ('perm_inv', C.c_void_p),
                 ('net', StbMlp), ('packed', C.c_void_p), ('packed_bytes', C.c_uint64)]
 
 

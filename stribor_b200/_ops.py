@@ -83,12 +83,20 @@ def _fill_struct(L: _lib.StbLayer, meta: Sequence[int], fmeta: Sequence[float], 
         rest = params[2 * n_linear:]
         L.const_out = None
         L.row_out = None
+    elif kind >= _lib.PERMUTE:
+        L.const_out = L.row_out = None
+        rest = params
     else:
         assert params[0].is_contiguous()
         L.const_out = None if row_mode else params[0].data_ptr()
         L.row_out = params[0].data_ptr() if row_mode else None
         rest = params[1:]
     L.time_scale = rest[0].data_ptr() if kind == _lib.CONT_AFFINE else None
+    if kind == _lib.PERMUTE:                      # params = [perm (int32), perm_inv (int32)]
+        L.const_out = None
+        L.perm, L.perm_inv = params[0].data_ptr(), params[1].data_ptr()
+    else:
+        L.perm = L.perm_inv = None
     if packed is not None and packed.numel() > 0:
         L.packed = packed.data_ptr()
         L.packed_bytes = packed.numel() * packed.element_size()

@@ -25,6 +25,11 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     if (rows < 0) return set_error(STB_EINVAL, "rows < 0");
     if (rows == 0) return STB_OK;
     if (!x || !y) return set_error(STB_EINVAL, "x / y is NULL");
+    if (L->kind >= STB_PERMUTE) {
+        if (ldiag) return set_error(STB_ENOTSUP, "no per-dimension log-derivative for this layer kind");
+        if (ldj_mode != STB_LDJ_NONE && !ldj) return set_error(STB_EINVAL, "ldj_mode set but ldj is NULL");
+        return pointwise_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s);
+    }
     if (L->latent_dim > 0 && !latent) return set_error(STB_EINVAL, "layer expects a latent input");
     if ((L->kind == STB_CONT_AFFINE) && !t) return set_error(STB_EINVAL, "layer expects a time input");
     if (ldj_mode != STB_LDJ_NONE && !ldj) return set_error(STB_EINVAL, "ldj_mode set but ldj is NULL");
@@ -73,6 +78,8 @@ int stb_flow_apply(const stb_layer* layers, int n_layers, int direction, const f
     int mode = ldj_mode;
     for (int i = 0; i < n_layers; ++i) {
         const stb_layer* L = &layers[direction == STB_FORWARD ? i : n_layers - 1 - i];
+        if (L->kind == STB_PERMUTE && cur == out)
+            return set_error(STB_ENOTSUP, "a permutation inside a fused chain needs out != x for that hop (use the layer-by-layer path)");
         int rc = apply_one(L, direction, cur, latent, t, out, ldj, ldj ? mode : STB_LDJ_NONE, 0, rows, s);
         if (rc) return rc;
         cur = out;
@@ -90,6 +97,8 @@ int stb_flow_log_prob(const stb_layer* layers, int n_layers, const float* y, con
     for (int i = 0; i < n_layers; ++i) {
         const stb_layer* L = &layers[n_layers - 1 - i];
         const int last = (i == n_layers - 1);
+        if (L->kind == STB_PERMUTE && cur == x_out)
+            return set_error(STB_ENOTSUP, "a permutation inside a fused chain needs out != x for that hop (use the layer-by-layer path)");
         int rc = apply_one(L, STB_INVERSE, cur, latent, t, x_out, lp, i == 0 ? STB_LDJ_SET : STB_LDJ_ADD,
                            last, rows, s);
         if (rc) return rc;

@@ -15,6 +15,8 @@ int validate_layer(const stb_layer* L);
 int generic_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent,
                         const float* t, float* y, float* ldj, int ldj_mode, int base_log_prob,
                         float* ldiag, int64_t rows, cudaStream_t stream);
+int pointwise_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj,
+                          int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
 int unit_normal_apply(const float* x, float* lp, int accumulate, int dim, int64_t rows,
                       cudaStream_t stream);
 

@@ -310,13 +310,79 @@ __global__ void unit_normal_kernel(const float* __restrict__ x, float* __restric
     if (lane == 0) lp[row] = accumulate ? lp[row] + s : s;
 }
 
+// Parameter-free layers: one warp per row, lanes over dims (coalesced), shuffle-reduced log-det.
+//   STB_PERMUTE  y[i] = x[perm[i]] (inverse: perm_inv), log-det 0            flows/permute.py:47-82
+//   STB_SIGMOID  y = clamp(sigmoid(x), tiny, 1 - eps); log-diag(x) = -softplus(-x) - softplus(x);
+//                inverse x = log(y) - log1p(-y) on the clamped y              flows/sigmoid.py:9-41
+//   STB_LOGIT    the same maps with the roles swapped; its log-diag is evaluated at the LOGIT-side
+//                value, as sigmoid.py:44-56 does
+// Log-det conventions are the inherited ones (flow.py:35-47): inverse = -(forward log-det at the
+// recovered / supplied point).
+__global__ void pointwise_kernel(int kind, int direction, const float* __restrict__ x, float* __restrict__ y,
+                                 const int32_t* __restrict__ perm, float* __restrict__ ldj, int ldj_mode,
+                                 int base_log_prob, int d, long long rows) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float tiny = 1.17549435e-38f, one_m_eps = 1.f - 1.1920929e-07f;
+    const bool to_unit = (kind == STB_SIGMOID) == (direction == STB_FORWARD);   // R -> (0,1) ?
+    float ld = 0.f, lp = 0.f;
+    for (int c = lane; c < d; c += 32) {
+        float v, out;
+        if (kind == STB_PERMUTE) {
+            out = x[row * d + perm[c]];
+        } else {
+            v = x[row * d + c];
+            float u;                                       // the value on the unbounded (logit) side
+            if (to_unit) {
+                out = fminf(fmaxf(sigmoid_f(v), tiny), one_m_eps);
+                u = v;
+            } else {
+                const float yc = fminf(fmaxf(v, tiny), one_m_eps);
+                out = logf(yc) - log1pf(-yc);
+                u = out;
+            }
+            const float ldiag = -softplus_f(-u) - softplus_f(u);      // log sigmoid'(u)
+            // forward sigmoid: +ldiag; inverse sigmoid: -ldiag; logit: the opposite signs
+            ld += to_unit ? ldiag : -ldiag;
+        }
+        if (base_log_prob) lp += -0.5f * out * out - 0.91893853320467274178f;
+        y[row * d + c] = out;
+    }
+    if (ldj_mode != STB_LDJ_NONE) {
+        float s = ld + lp;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) ldj[row] = (ldj_mode == STB_LDJ_ADD) ? ldj[row] + s : s;
+    }
+}
+
+int pointwise_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
+                          int base_log_prob, int64_t rows, cudaStream_t stream) {
+    if (x == y && L->kind == STB_PERMUTE) return set_error(STB_EINVAL, "permutation cannot run in place");
+    const int32_t* perm = nullptr;
+    if (L->kind == STB_PERMUTE) {
+        perm = (direction == STB_FORWARD) ? L->perm : L->perm_inv;
+        if (!perm) return set_error(STB_EINVAL, "permutation layer without index arrays");
+    }
+    const int wpb = 8;
+    const long long blocks = (rows + wpb - 1) / wpb;
+    pointwise_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(L->kind, direction, x, y, perm, ldj,
+                                                               ldj ? ldj_mode : STB_LDJ_NONE, base_log_prob, L->dim, rows);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "pointwise_kernel launch: %s", cudaGetErrorString(e));
+    return STB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 int validate_layer(const stb_layer* L) {
     if (!L) return set_error(STB_EINVAL, "layer is NULL");
-    if (L->kind < STB_AFFINE || L->kind > STB_CONT_AFFINE) return set_error(STB_EINVAL, "unknown transform kind %d", L->kind);
+    if (L->kind < STB_AFFINE || L->kind > STB_LOGIT) return set_error(STB_EINVAL, "unknown transform kind %d", L->kind);
     if (L->dim < 1) return set_error(STB_EINVAL, "dim must be >= 1");
+    if (L->kind >= STB_PERMUTE) return STB_OK;
     if (L->cond_x && !L->mask) return set_error(STB_EINVAL, "coupling layer needs a mask");
     const stb_mlp& N = L->net;
     if (N.n_linear < 0 || N.n_linear > STB_MAX_LINEAR) return set_error(STB_EINVAL, "n_linear %d out of range", N.n_linear);

@@ -1,3 +1,4 @@
 from .affine import *
 from .coupling import *
 from .spline import *
+from .pointwise import *

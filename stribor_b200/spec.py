@@ -15,6 +15,7 @@ from . import _lib
 from .flows.affine import Affine
 from .flows.coupling import ContinuousAffineCoupling, Coupling
 from .flows.spline import Spline
+from .flows.pointwise import Flip, Permute, Sigmoid, Logit
 from .net.mlp import MLP
 from .net.time_net import TimeLinear
 
@@ -54,6 +55,18 @@ def layer_from_spec(layer: Dict) -> nn.Module:
         return _transform_from_spec(layer['transform'])
     if typ == 'coupling':
         return Coupling(_transform_from_spec(layer['transform']), mask=layer['mask'])
+    if typ == 'sigmoid':
+        return Sigmoid()
+    if typ == 'logit':
+        return Logit()
+    if typ == 'flip':
+        return Flip()
+    if typ == 'permute':
+        f = Permute(len(layer['perm']))
+        f.permutation = torch.as_tensor(layer['perm']).long()
+        f.inverse_permutation = torch.empty_like(f.permutation)
+        f.inverse_permutation[f.permutation] = torch.arange(len(layer['perm']))
+        return f
     if typ == 'cont_affine_coupling':
         tn = TimeLinear(layer['time_scale'].shape[-1])
         tn.scale.data = layer['time_scale'].detach().clone().float()
@@ -97,6 +110,14 @@ def spec_from_layers(layers) -> List[Dict]:
             out.append({'type': 'cont_affine_coupling', 'mask': f.mask_name,
                         'concatenate_time': bool(f.concatenate_time), 'net': _mlp_to_spec(f.latent_net),
                         'time_scale': f.time_net.scale.detach().cpu().clone()})
+        elif isinstance(f, Flip):
+            out.append({'type': 'flip'})
+        elif isinstance(f, Permute):
+            out.append({'type': 'permute', 'perm': f.permutation.tolist()})
+        elif isinstance(f, Logit):
+            out.append({'type': 'logit'})
+        elif isinstance(f, Sigmoid):
+            out.append({'type': 'sigmoid'})
         elif isinstance(f, (Affine, Spline)):
             out.append({'type': 'elementwise', 'transform': _transform_to_spec(f)})
         else:

@@ -190,6 +190,33 @@ CASES['cubic_d16_default_box'] = _mk_flow('cubic', 16, [32], 3, 16, 40, 32, lowe
                                            scale=0.6)
 
 
+@_reg('sigmoid_cubic_logit_d2')
+def _c_sandwich():
+    """test_normalizing_flow.py:8-34 minus the CNF layer: affine coupling, Flip, Sigmoid,
+    cubic-spline coupling on the default [0, 1] box, Logit."""
+    rs = _rs(61)
+    spec = [coupling_spec(rs, 'affine', 2, [13], 'ordered_1'), {'type': 'flip'}, {'type': 'sigmoid'},
+            coupling_spec(rs, 'cubic', 2, [13], 'ordered_0', n_bins=3), {'type': 'logit'}]
+    return {'spec': spec, 'inputs': {'x': _x(rs, (3, 4, 2))}, 'ops': ['forward_ldj', 'inverse_ldj', 'log_prob']}
+
+
+@_reg('permute_quadratic_d16')
+def _c_perm():
+    rs = _rs(62)
+    spec = []
+    for i in range(3):
+        spec.append(coupling_spec(rs, 'quadratic', 16, [32], 'ordered_right_half', n_bins=8, lower=-3., upper=3.))
+        spec.append({'type': 'permute', 'perm': rs.permutation(16).tolist()} if i % 2 == 0 else {'type': 'flip'})
+    return {'spec': spec, 'inputs': {'x': _x(rs, (29, 16))}, 'ops': ['forward_ldj', 'inverse_ldj', 'log_prob']}
+
+
+@_reg('sigmoid_logit_only_d5')
+def _c_sig():
+    rs = _rs(63)
+    return {'spec': [{'type': 'sigmoid'}, {'type': 'flip'}, {'type': 'logit'}, {'type': 'sigmoid'}],
+            'inputs': {'x': _x(rs, (11, 5), scale=3.0)}, 'ops': ['forward_ldj', 'inverse_ldj_unit']}
+
+
 @_reg('neural_flow_d16_L4')
 def _c4():
     """BASELINE.json configs[3] at fixture size: 4x ContinuousAffineCoupling, dim 16."""

@@ -60,6 +60,18 @@ def _ref_transform(tr):
 
 
 def ref_layer(layer):
+    if layer['type'] == 'sigmoid':
+        return st.Sigmoid()
+    if layer['type'] == 'logit':
+        return st.Logit()
+    if layer['type'] == 'flip':
+        return st.Flip()
+    if layer['type'] == 'permute':
+        f = st.Permute(len(layer['perm']))
+        f.permutation = torch.as_tensor(layer['perm']).long()
+        f.inverse_permutation = torch.empty_like(f.permutation)
+        f.inverse_permutation[f.permutation] = torch.arange(len(layer['perm']))
+        return f
     if layer['type'] == 'elementwise':
         return _ref_transform(layer['transform'])
     if layer['type'] == 'coupling':
@@ -111,6 +123,11 @@ def run_case(name, dtype):
             out['inverse.x'], out['inverse.ldj'] = xr, ldj
             if name.startswith('spline_') and len(capture) == 1:
                 out['inverse.bins'] = capture[0]
+        elif op == 'inverse_ldj_unit':       # inverse of a flow that ends in (0, 1): feed the forward output
+            with torch.no_grad():
+                y = flow.forward(x, **kw)
+                xr, ldj = flow.inverse_and_log_det_jacobian(y, **kw)
+            out['inverse_unit.y'], out['inverse_unit.x'], out['inverse_unit.ldj'] = y, xr, ldj
         elif op == 'log_prob':
             with torch.no_grad():
                 out['log_prob'] = flow.log_prob(x, **kw)

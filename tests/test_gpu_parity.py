@@ -62,6 +62,10 @@ def test_cuda_matches_reference(name, fused):
                 _cmp(name, 'inverse.x', xr)
                 _cmp(name, 'inverse.ldj', ldj)
                 assert torch.equal(flow.inverse(x, **kw), xr)
+            elif op == 'inverse_ldj_unit':
+                xr, ldj = flow.inverse_and_log_det_jacobian(ref(name, 'inverse_unit.y').to(DEV), **kw)
+                _cmp(name, 'inverse_unit.x', xr)
+                _cmp(name, 'inverse_unit.ldj', ldj)
             elif op == 'log_prob':
                 _cmp(name, 'log_prob', flow.log_prob(x, **kw))
             elif op == 'neural_flow':

@@ -36,6 +36,11 @@ def test_oracle_matches_reference(name, prec):
             xr, ldj = O.flow_inverse(spec, x, with_ldj=True, **kw)
             torch.testing.assert_close(xr, ref(name, 'inverse.x', prec), **tol)
             torch.testing.assert_close(ldj, ref(name, 'inverse.ldj', prec), **tol)
+        elif op == 'inverse_ldj_unit':
+            y = ref(name, 'inverse_unit.y', prec)
+            xr, ldj = O.flow_inverse(spec, y, with_ldj=True, **kw)
+            torch.testing.assert_close(xr, ref(name, 'inverse_unit.x', prec), **tol)
+            torch.testing.assert_close(ldj, ref(name, 'inverse_unit.ldj', prec), **tol)
         elif op == 'log_prob':
             lp = O.flow_log_prob(spec, x, **kw)
             torch.testing.assert_close(lp, ref(name, 'log_prob', prec), **tol)
