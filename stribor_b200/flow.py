@@ -98,7 +98,7 @@ def _chain_ok(transforms, tensors) -> bool:
     """Fused whole-chain path: every layer describable, nothing asks for gradients."""
     if not all(hasattr(f, 'describe') for f in transforms) or len(transforms) == 0:
         return False
-    if any(not getattr(f, 'in_place_ok', True) for f in transforms):
+    if any(not getattr(f, 'in_place_ok', True) or getattr(f, 'set_data', False) for f in transforms):
         return False                  # a permutation cannot run in place: layer-by-layer path
     if torch.is_grad_enabled():
         if any(v is not None and v.requires_grad for v in tensors):

@@ -42,16 +42,38 @@ class Coupling(Transform):
         if not isinstance(transform, (Affine, Spline)):
             raise NotImplementedError(
                 f'Coupling around {type(transform).__name__} is not fused; use Affine or Spline')
-        if set_data:
-            raise NotImplementedError('set_data=True (masking along dim -2) is not built yet')
         self.transform = transform
         self.mask_func = get_mask(mask)
         self.mask_name = mask
         self.set_data = set_data
         self._masks = {}
         self._packed = PackedCache()
+        # set_data: the mask selects ROWS of a set (dim -2).  Masked-out rows are transformed in all
+        # their coordinates with conditioning x*0 (+ latent) -- exactly a 'none'-mask coupling on
+        # those rows (coupling.py:49-51,61-78); kept out of the module tree (shared parameters).
+        self._rows_layer = [Coupling(transform, 'none')] if set_data else None
+
+    def _run_set(self, x, latent, direction, want_ldj):
+        *rest, n, d = x.shape
+        m = self.mask_func(n)
+        if m.numel() == 1 and n != 1:
+            m = m.expand(n)
+        sel = (m == 0).nonzero().view(-1).to(x.device)
+        y = x.clone()
+        ldj = x.new_zeros(*rest, n, 1) if want_ldj else None
+        if sel.numel():
+            lat = None
+            if latent is not None and self.transform.latent_net is not None:
+                lat = latent.expand(*rest, n, latent.shape[-1]).index_select(-2, sel)
+            out, l = self._rows_layer[0]._run(x.index_select(-2, sel), lat, direction, want_ldj)
+            y = y.index_copy(-2, sel, out)
+            if want_ldj:
+                ldj = ldj.index_copy(-2, sel, l)
+        return y, ldj
 
     def describe(self, dim, latent_dim, device):
+        if self.set_data:
+            raise NotImplementedError('set_data couplings are applied row-group-wise; not part of fused chains')
         tr = self.transform
         net = tr.latent_net
         mask, mask_list = device_mask(self._masks, self.mask_func, dim, device)
@@ -65,6 +87,8 @@ class Coupling(Transform):
         return {'meta': meta, 'fmeta': fmeta, 'mask': mask, 'params': params, 'packed': packed}
 
     def _run(self, x, latent, direction, want_ldj):
+        if self.set_data:
+            return self._run_set(x, latent, direction, want_ldj)
         lat = latent if self.transform.latent_net is not None else None
         if self.transform.latent_net is not None and needs_autograd(self, x, lat):
             return self._run_autograd(x, lat, direction, want_ldj)

@@ -89,8 +89,6 @@ def test_descriptor_wire_format():
     with pytest.raises(NotImplementedError):
         st.Coupling(st.Affine(2, latent_net=st.net.MLP(2, [4], 4, activation='Hardtanh')),
                     mask='ordered_0').describe(2, 0, 'cpu')
-    with pytest.raises(NotImplementedError):
-        st.Coupling(st.Affine(2, latent_net=st.net.MLP(2, [4], 4)), mask='ordered_0', set_data=True)
 
 
 @pytest.mark.parametrize('name', ['quadratic_d5_parity', 'cubic_d7_ordered', 'neural_flow_d16_L4',
