@@ -96,10 +96,9 @@ def run_layer_diag(desc, x, latent, t, direction):
 
 def _chain_ok(transforms, tensors) -> bool:
     """Fused whole-chain path: every layer describable, nothing asks for gradients."""
-    if not all(hasattr(f, 'describe') for f in transforms) or len(transforms) == 0:
-        return False
-    if any(not getattr(f, 'in_place_ok', True) or getattr(f, 'set_data', False) for f in transforms):
-        return False                  # a permutation cannot run in place: layer-by-layer path
+    if len(transforms) == 0 or not all(hasattr(f, 'chainable') and f.chainable() for f in transforms):
+        return False                  # foreign modules, un-fused conditioners, permutations (cannot run
+                                      # in place), set_data couplings: layer-by-layer path
     if torch.is_grad_enabled():
         if any(v is not None and v.requires_grad for v in tensors):
             return False

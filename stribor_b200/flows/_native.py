@@ -56,8 +56,10 @@ class PackedCache:
         if nbytes > 0:
             buf = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
             with torch.cuda.device(buf.device):
-                _lib.check(lib.stb_pack_layer(C.byref(L), buf.data_ptr(),
-                                              torch.cuda.current_stream(buf.device).cuda_stream))
+                stream = torch.cuda.current_stream(buf.device)
+                _lib.check(lib.stb_pack_layer(C.byref(L), buf.data_ptr(), stream.cuda_stream))
+                # one-off (weights changed): the image may be consumed from OTHER streams next
+                stream.synchronize()
         self.key, self.buf = key, buf
         return buf
 
@@ -76,6 +78,17 @@ def device_mask(cache, mask_func, dim, device):
     return cache[k]
 
 
+def fusable(net) -> bool:
+    """Can the kernels evaluate this conditioner themselves?"""
+    if not isinstance(net, MLP):
+        return False
+    try:
+        net.describe()
+        return True
+    except NotImplementedError:
+        return False
+
+
 def needs_autograd(module, *tensors) -> bool:
     """True when a gradient could flow through this call (parameters or inputs require grad)."""
     if not torch.is_grad_enabled():
@@ -86,8 +99,12 @@ def needs_autograd(module, *tensors) -> bool:
 
 
 def row_params_from_net(net, z, rows_idx=None):
-    """Evaluate an MLP conditioner through autograd (training path).  With ``rows_idx`` only those
-    rows of the LAST Linear are evaluated (the transformed dims' parameters, "masked minimum")."""
+    """Evaluate a conditioner as a PyTorch module (training path, or a conditioner the kernels do
+    not fuse).  For an ``MLP`` with ``rows_idx`` only those rows of the LAST Linear are evaluated (the
+    transformed dims' parameters, "masked minimum"); any other module is simply called."""
+    if not isinstance(net, MLP) or net._wrapped:
+        out = net(z)
+        return out if rows_idx is None else out.index_select(-1, rows_idx)
     mods = list(net.net)
     last = max(i for i, m in enumerate(mods) if isinstance(m, torch.nn.Linear))
     h = z

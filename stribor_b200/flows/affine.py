@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..flow import ElementwiseTransform, run_layer, run_layer_diag
-from ._native import build_meta, needs_autograd, row_params_from_net
+from ._native import build_meta, fusable, needs_autograd, row_params_from_net
 
 __all__ = ['Affine']
 
@@ -41,6 +41,9 @@ class Affine(ElementwiseTransform):
                 self.register_buffer('log_scale', scale.log(), persistent=False)
                 self.register_buffer('shift', shift.clone(), persistent=False)
 
+    def chainable(self):
+        return self.latent_net is None or fusable(self.latent_net)
+
     def params_per_dim(self):
         return 2
 
@@ -64,7 +67,7 @@ class Affine(ElementwiseTransform):
 
     def _run(self, x, latent, direction, want_ldj=True):
         lat = latent if self.latent_net is not None else None
-        if lat is not None and needs_autograd(self, x, lat):
+        if lat is not None and (needs_autograd(self, x, lat) or not fusable(self.latent_net)):
             return run_layer(self._describe_rows(x, lat), x, None, None, direction, want_ldj)
         d = self.describe(x.shape[-1], 0 if lat is None else lat.shape[-1], x.device)
         return run_layer(d, x, lat, None, direction, want_ldj)

@@ -19,7 +19,7 @@ from .. import _lib
 from ..flow import Transform, run_layer
 from ..net.time_net import TimeLinear
 from ..util.mask import get_mask
-from ._native import PackedCache, build_meta, device_mask, needs_autograd, row_params_from_net
+from ._native import PackedCache, build_meta, device_mask, fusable, needs_autograd, row_params_from_net
 from .affine import Affine
 from .spline import Spline
 
@@ -52,6 +52,10 @@ class Coupling(Transform):
         # their coordinates with conditioning x*0 (+ latent) -- exactly a 'none'-mask coupling on
         # those rows (coupling.py:49-51,61-78); kept out of the module tree (shared parameters).
         self._rows_layer = [Coupling(transform, 'none')] if set_data else None
+
+    def chainable(self):
+        net = self.transform.latent_net
+        return (not self.set_data) and (net is None or fusable(net))
 
     def _run_set(self, x, latent, direction, want_ldj):
         *rest, n, d = x.shape
@@ -90,7 +94,9 @@ class Coupling(Transform):
         if self.set_data:
             return self._run_set(x, latent, direction, want_ldj)
         lat = latent if self.transform.latent_net is not None else None
-        if self.transform.latent_net is not None and needs_autograd(self, x, lat):
+        net = self.transform.latent_net
+        if net is not None and (needs_autograd(self, x, lat) or not fusable(net)):
+            # gradients wanted, or a conditioner the kernels do not fuse (any nn.Module works here)
             return self._run_autograd(x, lat, direction, want_ldj)
         d = self.describe(x.shape[-1], 0 if lat is None else lat.shape[-1], x.device)
         return run_layer(d, x, lat, None, direction, want_ldj)
@@ -165,6 +171,9 @@ class ContinuousAffineCoupling(Transform):
         self._masks = {}
         self._packed = PackedCache()
 
+    def chainable(self):
+        return fusable(self.latent_net) and isinstance(self.time_net, TimeLinear)
+
     def _time_scale(self, dim):
         if not isinstance(self.time_net, TimeLinear):
             raise NotImplementedError(f'time_net {type(self.time_net).__name__} is not fused; use TimeLinear')
@@ -188,7 +197,7 @@ class ContinuousAffineCoupling(Transform):
     def _run(self, x, t, latent, direction, want_ldj):
         if t is None:
             raise TypeError('ContinuousAffineCoupling needs the time input `t`')
-        if needs_autograd(self, x, t, latent):
+        if needs_autograd(self, x, t, latent) or not fusable(self.latent_net) or not isinstance(self.time_net, TimeLinear):
             return self._run_autograd(x, t, latent, direction, want_ldj)
         d = self.describe(x.shape[-1], 0 if latent is None else latent.shape[-1], x.device)
         return run_layer(d, x, latent, t, direction, want_ldj)
@@ -216,9 +225,11 @@ class ContinuousAffineCoupling(Transform):
         if self.concatenate_time:
             z = torch.cat([z, tt], -1)
         out = self.latent_net(z.reshape(-1, z.shape[-1]))
-        tn = self._time_scale(dim).view(1, -1) * tt.reshape(-1, 1)
-        a = (out[:, :dim] * tn[:, :dim]).index_select(1, tr_idx)
-        b = (out[:, dim:] * tn[:, dim:]).index_select(1, tr_idx)
+        tn = self.time_net(tt.reshape(-1, 1))                    # any time embedding (net/time_net.py)
+        ls, sh = out.chunk(2, dim=-1)
+        tls, tsh = tn.chunk(2, dim=-1)                           # [rows, dim] or broadcastable [rows, 1]
+        a = (ls * tls).index_select(1, tr_idx)
+        b = (sh * tsh).index_select(1, tr_idx)
         prm = torch.cat([a, b], -1).contiguous()
         meta, _ = build_meta(_lib.AFFINE, dim, 0, 1, 0, 0, 0, 0, None, 0, mask_list=mask_list)
         meta[13] = 2

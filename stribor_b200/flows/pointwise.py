@@ -29,6 +29,9 @@ class _Pointwise(ElementwiseTransform):
     def _params(self, dim, device):
         return []
 
+    def chainable(self):
+        return self.in_place_ok
+
     def describe(self, dim, latent_dim, device):
         p = self._params(dim, device)
         return {'meta': _meta(self.kind, dim, len(p)), 'fmeta': [0., 1.] * 3, 'mask': None, 'params': p,

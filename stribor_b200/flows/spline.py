@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..flow import ElementwiseTransform, run_layer, run_layer_diag
-from ._native import build_meta, needs_autograd, row_params_from_net
+from ._native import build_meta, fusable, needs_autograd, row_params_from_net
 
 __all__ = ['Spline']
 
@@ -46,6 +46,9 @@ class Spline(ElementwiseTransform):
         nn.init.xavier_uniform_(self.height)
         nn.init.xavier_uniform_(self.derivative)
 
+    def chainable(self):
+        return self.latent_net is None or fusable(self.latent_net)
+
     def params_per_dim(self):
         return 2 * self.n_bins + self.derivative_dim
 
@@ -69,7 +72,7 @@ class Spline(ElementwiseTransform):
 
     def _run(self, x, latent, direction, want_ldj=True):
         lat = latent if self.latent_net is not None else None
-        if lat is not None and needs_autograd(self, x, lat):
+        if lat is not None and (needs_autograd(self, x, lat) or not fusable(self.latent_net)):
             lead = x.shape[:-1]
             if lat.shape[:-1] != lead:
                 lat = lat.expand(*lead, lat.shape[-1])

@@ -232,3 +232,57 @@ def test_set_data_coupling_matches_reference_semantics(kind):
     torch.testing.assert_close(xr.cpu(), x, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(ldj_i.cpu(), -want_l, rtol=1e-4, atol=1e-4)
     assert torch.equal(y.cpu()[:, m == 1], x[:, m == 1])
+
+
+def test_foreign_conditioner_and_time_net():
+    """A conditioner / time embedding the kernels do not fuse (any nn.Module) still runs: the module
+    is evaluated by PyTorch, gather + transform + log-det by the element-wise CUDA kernels."""
+    torch.manual_seed(3)
+    d = 6
+
+    class Net(torch.nn.Module):
+        def __init__(self, i, o):
+            super().__init__()
+            self.a = torch.nn.Linear(i, 16)
+            self.b = torch.nn.Linear(16, o)
+
+        def forward(self, z, **kw):
+            return self.b(torch.nn.functional.hardtanh(self.a(z)))
+
+    for tr in (st.Affine(d, latent_net=Net(d, 2 * d)),
+               st.Spline(d, 5, latent_net=Net(d, d * 14), lower=-3, upper=3, spline_type='quadratic')):
+        f = st.Coupling(tr, mask='parity_odd').to(DEV)
+        x = torch.randn(50, d, device=DEV)
+        with torch.no_grad():
+            y, ldj = f.forward_and_log_det_jacobian(x)
+            xr, ldi = f.inverse_and_log_det_jacobian(y)
+            m = torch.tensor([1., 0., 1., 0., 1., 0.], device=DEV)
+            prm = tr.latent_net(x * m)
+        assert torch.allclose(xr, x, atol=1e-4) and torch.allclose(ldi, -ldj, atol=1e-4)
+        assert torch.equal(y[:, 0::2], x[:, 0::2])
+        if isinstance(tr, st.Affine):
+            ls, sh = prm[:, :d], prm[:, d:]
+            want = x * torch.exp(ls) + sh
+            torch.testing.assert_close(y[:, 1::2], want[:, 1::2], rtol=1e-5, atol=1e-5)
+            torch.testing.assert_close(ldj, ls[:, 1::2].sum(-1, keepdim=True), rtol=1e-5, atol=1e-5)
+
+    class TimeTanh(torch.nn.Module):                      # net/time_net.py:31-36
+        def __init__(self, o):
+            super().__init__()
+            self.scale = torch.nn.Parameter(torch.randn(1, o))
+
+        def forward(self, t):
+            return torch.tanh(self.scale * t)
+
+    ca = st.ContinuousAffineCoupling(st.net.MLP(d + 1, [8], 2 * d), TimeTanh(2 * d), 'ordered_0').to(DEV)
+    x = torch.randn(20, d, device=DEV)
+    t = torch.rand(20, 1, device=DEV)
+    with torch.no_grad():
+        y = ca(x, t=t)
+        assert torch.allclose(ca.inverse(y, t=t), x, atol=1e-5)
+        assert (ca(x, t=torch.zeros_like(t)) == x).all()
+        m = torch.tensor([0., 0., 0., 1., 1., 1.], device=DEV)
+        out = ca.latent_net(torch.cat([x * m, t], -1))
+        tn = ca.time_net(t)
+        want = x * torch.exp(out[:, :d] * tn[:, :d]) + out[:, d:] * tn[:, d:]
+        torch.testing.assert_close(y[:, :3], want[:, :3], rtol=1e-5, atol=1e-5)

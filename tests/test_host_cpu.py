@@ -83,7 +83,8 @@ def test_descriptor_wire_format():
     assert dc['meta'][0] == _lib.CONT_AFFINE and dc['meta'][4] == 1 and dc['params'][-1].shape == (8,)
     s = ca.time_net.scale.detach().view(-1)
     assert torch.equal(dc['params'][-1].detach(), torch.stack([s[0]] * 4 + [s[1]] * 4))
-    # unsupported conditioners fail loudly instead of silently running something else
+    # conditioners the kernels cannot fuse are not describable (they run as modules around the
+    # element-wise kernels instead, see test_gpu_parity.py::test_foreign_conditioner)
     with pytest.raises(NotImplementedError):
         st.Coupling(st.Affine(2, latent_net=torch.nn.Linear(2, 4)), mask='ordered_0').describe(2, 0, 'cpu')
     with pytest.raises(NotImplementedError):

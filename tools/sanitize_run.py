@@ -1,0 +1,39 @@
+"""Small run of every kernel (ragged tails included) for compute-sanitizer memcheck."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+import torch
+import cases
+import stribor_b200 as st
+from stribor_b200.spec import layers_from_spec
+dev = 'cuda'
+def run(name, case, rows_list=(1, 255, 257, 700), grad=False):
+    layers = [l.to(dev) for l in layers_from_spec(case['spec'])]
+    d = case['inputs']['x'].shape[-1]
+    flow = st.NormalizingFlow(st.UnitNormal(d), layers)
+    for r in rows_list:
+        x = torch.randn(r, d, device=dev) * 1.5
+        with torch.no_grad():
+            lp = flow.log_prob(x); y, l = flow.forward_and_log_det_jacobian(x); xi = flow.inverse(y)
+        assert torch.isfinite(lp).all()
+    if grad:
+        x = torch.randn(77, d, device=dev, requires_grad=True)
+        (-flow.log_prob(x).mean()).backward()
+    torch.cuda.synchronize()
+    print('ok', name, flush=True)
+run('tc quadratic', cases._mk_flow('quadratic', 64, [64], 2, 16, 8, 1)(), grad=True)
+run('tc cubic d63', cases._mk_flow('cubic', 63, [64], 2, 16, 8, 2, masks=('parity_even', 'ordered_left_half'))(), grad=True)
+run('tc affine 256x256', cases._mk_flow('affine', 64, [256, 256], 2, 0, 8, 3)(), grad=True)
+run('tc affine d30 h128', cases._mk_flow('affine', 30, [128], 2, 0, 8, 4)())
+run('generic quadratic d5', cases.build_case('quadratic_d5_parity'), rows_list=(1, 33))
+run('generic cubic d7', cases.build_case('cubic_d7_ordered'), rows_list=(1, 33), grad=True)
+run('pointwise', cases.build_case('permute_quadratic_d16'), rows_list=(1, 9, 300))
+import numpy as np
+rs = np.random.RandomState(1)
+spec = [cases.cont_affine_spec(rs, 16, [64], 'ordered_0') for _ in range(2)]
+nf = st.NeuralFlow([l.to(dev) for l in layers_from_spec(spec)])
+with torch.no_grad():
+    for r in (1, 129, 300):
+        x = torch.randn(r, 16, device=dev); t = torch.rand(r, 1, device=dev)
+        nf(x, t=t, t0=t * 0.5)
+torch.cuda.synchronize(); print('ok neural tc')
