@@ -89,7 +89,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
                  '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -329,13 +329,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the start of the warm-up (identical load) to the end of the timed
+    # region, so that short timed regions (strong scaling at 8 GPUs: ~20 ms) still get samples
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    t_load0 = time.perf_counter()
     for _ in range(args.warmup):
         lp = step()
     assert torch.isfinite(lp).all().item(), 'non-finite log_prob'
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
     barrier()
     n0 = _ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -348,7 +350,13 @@ def main():
     t1 = time.perf_counter()
     launches = _ops.launch_count() - n0
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop(t0, t1)
+    if t1 - t_load0 < 0.35:                                # keep the GPU under the same load until a sample lands
+        while time.perf_counter() - t_load0 < 0.35:
+            step()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+    clocks = sampler.stop(t_load0, t1)
+    clocks['window'] = 'warm-up + timed steps (same workload)'
     tmax = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -358,7 +366,7 @@ def main():
     # ---- end to end: pinned host rows -> device -> log_prob -> host -------------------------
     e2e = None
     if not args.no_e2e:
-        pipe = HostPipeline(flow, D, dev, chunk_rows=min(rows, 1 << 19))
+        pipe = HostPipeline(flow, D, dev, chunk_rows=max(1 << 16, min(1 << 19, rows // 4)))
         y_host = torch.empty(rows, D, pin_memory=True)
         y_host.copy_(y)
         lp_host = torch.empty(rows, 1, pin_memory=True)
