@@ -33,11 +33,12 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(p) <= t for p in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """`defines` / `out`: profiling variants only (tools/build_variants.py); the product is the default."""
+    if not force and out == OUT and up_to_date():
         return OUT
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', OUT] + sources() + ['-lcuda']
+    cmd = [nvcc] + NVCC_FLAGS + [f'-D{d}' for d in defines] + ['-o', out] + sources() + ['-lcuda']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, 'build.log')
     with open(log, 'w') as f:
@@ -46,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(r.stdout)
     if r.returncode != 0:
         raise RuntimeError(f'nvcc failed ({r.returncode}); see {log}')
-    return OUT
+    return out
 
 
 if __name__ == '__main__':

@@ -63,6 +63,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
+// the same on a pre-converted shared-memory address (hot loops: saves the generic -> shared
+// conversion, which ptxas otherwise rematerialises at every use)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(1000000u)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 22)) {
+            printf("stribor_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+                   (int)threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+// keep a loop-invariant value in its register (ptxas otherwise recomputes index arithmetic from
+// threadIdx in every iteration of the hot loop)
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
+
 // same, for single-lane roles that can afford to back off (producer / issuer)
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;

@@ -47,12 +47,45 @@ constexpr int kMaxChunks = kMaxTr / kG;
 constexpr int kTileRows = 256;
 constexpr int kXsStride = kMaxDim + 1;
 constexpr int kStages = 3;
-constexpr int kThreads = 576;          // producer warp, issuer warp, 16 epilogue warps
-constexpr int kEpiThreads = 512;
-constexpr int kEpiWarp0 = 2;
+#ifndef STB_TC_EPI_PER_SUB
+#define STB_TC_EPI_PER_SUB 2
+#endif
+#ifndef STB_TC_EXP
+#define STB_TC_EXP 0                   // experiment bits (profiling builds only): 1 no finish, 2 no ex2, 4 no acc_full wait
+#endif
+#if STB_TC_EXP & 64
+#define MBAR_WAIT_SLOW mbar_wait
+#else
+#define MBAR_WAIT_SLOW mbar_wait_relaxed
+#endif
+// bit 128: per-warp phase clocks (tools/tc_phase_prof.py reads them back through stb_tc_prof_read)
+#if STB_TC_EXP & 128
+__device__ unsigned int g_tc_prof[160 * 32 * 8];
+#define PROF_DECL unsigned int _pt = clock(), _pa[6] = {0, 0, 0, 0, 0, 0};
+#define PROF(i) { const unsigned int _n = clock(); _pa[i] += _n - _pt; _pt = _n; }
+#if STB_TC_EXP & 256
+#define PROFH(i) PROF(i)
+#define PROFC(i)
+#else
+#define PROFH(i)
+#define PROFC(i) PROF(i)
+#endif
+#define PROF_FLUSH { if ((threadIdx.x & 31) == 0) for (int _i = 0; _i < 6; ++_i) g_tc_prof[(blockIdx.x * 32 + (threadIdx.x >> 5)) * 8 + _i] = _pa[_i]; }
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROFH(i)
+#define PROFC(i)
+#define PROF_FLUSH
+#endif
+constexpr int kEpiPerSub = STB_TC_EPI_PER_SUB;   // epilogue warps per (subtile, TMEM sub-partition)
+constexpr int kEpiWarps = 2 * 4 * kEpiPerSub;
+constexpr int kEpiWarp0 = 3;           // warp 0 producer, warps 1 / 2 UMMA issuers of subtile 0 / 1
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kEpiThreads = kEpiWarps * 32;
 
 // packed image (global memory, built by tc_pack_layer)
-constexpr uint32_t kMagic = 0x53544231u;
+constexpr uint32_t kMagic = 0x53544232u;
 struct Header {                      // 1024 bytes
     uint32_t magic;
     int32_t kind, dim, n_cond, n_tr, n_chunks, P, act;
@@ -60,7 +93,9 @@ struct Header {                      // 1024 bytes
     uint32_t maxbits;                // scratch: max |W2| as uint bits
     int32_t cond_idx[kK1];
     int32_t tr_idx[kMaxTr];
-    int32_t pad[256 - 10 - kK1 - kMaxTr];
+    uint32_t noshift_mask;           // bit ji: softmax logits of transformed dim ji are provably within
+                                     // +-100 (log2 units), so exp2 needs no max subtraction
+    int32_t pad[256 - 11 - kK1 - kMaxTr];
 };
 static_assert(sizeof(Header) == 1024, "header layout");
 constexpr uint32_t kOffB1 = 1024;                                  // float[64]
@@ -82,8 +117,8 @@ constexpr uint32_t kSmW1 = kSmA + 2 * kABytes;
 constexpr uint32_t kSmB = kSmW1 + kW1Bytes;
 constexpr uint32_t kSmSmall = kSmB + kStages * kChunkBytes;
 constexpr uint32_t kSmBar = (kSmSmall + kSmallBytes + 15) & ~15u;
-constexpr uint32_t kSmLd = kSmBar + 256;                           // float [256]: partner warp's log-det partials
-constexpr uint32_t kSmemBytes = kSmLd + kTileRows * 4;
+constexpr uint32_t kSmLd = kSmBar + 256;                           // float [2][256]: the other warps' log-det partials
+constexpr uint32_t kSmemBytes = kSmLd + (kEpiPerSub - 1) * kTileRows * 4;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 static_assert(kSmA % 16 == 0 && kSmW1 % 16 == 0 && kSmB % 16 == 0 && kSmSmall % 16 == 0, "alignment");
 
@@ -121,82 +156,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // -----------------------------------------------------------------------------------------------
 // spline evaluation with the 48 parameters of one element in registers
 // -----------------------------------------------------------------------------------------------
-// u[0..16) unnormalised -> u[i] = min_size + (1 - 16 min_size) * softmax_i.
-// exp(u - max) through ex2.approx: arguments are <= 0, so the absolute error of every term is
-// <= ~2.5 ulp of the LARGEST term (= 1), i.e. the same absolute accuracy on the bin sizes as a
-// 2-ulp expf.  Measured on the GPU against the fp64 oracle (profiles/r01_tc_accuracy.txt): accurate
-// expf, IEEE division and a true e_i / sum quotient change the mean log-det error by < 7 %;
-// only compensated cumulative sums help (12 %) and cost ~90 instructions per element.
+// exp through ex2.approx: with the maximum subtracted the arguments are <= 0, so the absolute
+// error of every term is <= ~2.5 ulp of the LARGEST term (= 1), i.e. the same absolute accuracy on
+// the bin sizes as a 2-ulp expf.  Measured on the GPU against the fp64 oracle
+// (profiles/r01_tc_accuracy.txt): accurate expf, IEEE division and a true e_i / sum quotient change
+// the mean log-det error by < 7 %; only compensated cumulative sums help (12 %) and cost ~90
+// instructions per element.
 __device__ __forceinline__ float ex2_approx(float v) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
-// t[i] = log2(e) * (unnormalised parameter i), see the packed bias table
-__device__ __forceinline__ void softmax16_bins(float* t, float min_size) {
-    // pairwise trees (depth 4) instead of 15-long dependent chains: with two warps per scheduler
-    // the chains' latency is exposed
-    float m8[8], m4[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m8[i] = fmaxf(t[2 * i], t[2 * i + 1]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) m4[i] = fmaxf(m8[2 * i], m8[2 * i + 1]);
-    const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-#pragma unroll
-    for (int i = 0; i < kBins; ++i) t[i] = ex2_approx(t[i] - m);
-    float s8[8], s4[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s8[i] = t[2 * i] + t[2 * i + 1];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s4[i] = s8[2 * i] + s8[2 * i + 1];
-    const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-    const float inv = __frcp_rn(s) * (1.f - min_size * (float)kBins);
-#pragma unroll
-    for (int i = 0; i < kBins; ++i) t[i] = fmaf(t[i], inv, min_size);
-}
 
 // tanh to ~3e-7 ABSOLUTE error: (1 - e^-2|v|) / (1 + e^-2|v|).  The result feeds a contraction
 // with O(0.1) weights, where only the absolute error matters (tanhf costs ~3x the instructions).
 __device__ __forceinline__ float tanh_fast(float v);
-
-struct RqsSel {
-    float xk, xk1, yk, yk1, u0, u1;
-};
-
-// Walk the knots of both axes; select the bin that holds `key` on the searched axis.
-// w[i], h[i]: normalised bin sizes; d[i]: K-1 unconstrained interior derivatives.
-// search_sorted.py:3-5 semantics: bin = #(key >= knot_i) - 1; the nudged last knot is never
-// reached by an inside key, so the bin is the last i in [0, 15] with key >= knot_i.  The knots are
-// increasing, hence "key >= knot_i" is a prefix property and plain predicated moves select the
-// quantities of that bin: cumulative sums before it, its sizes, and the derivative parameters
-// at its two knots.
-__device__ __forceinline__ RqsSel rqs16_walk(const float* w, const float* h, const float* d, float lo,
-                                             float hi, bool on_heights, float key) {
-    const float span = hi - lo;
-    float cwk = 0.f, chk = 0.f, wk = w[0], hk = h[0];
-    float u0 = STB_RQS_EDGE_CONST, u1 = d[0];
-    int k = 0;
-    float cw = 0.f, ch = 0.f;
-#pragma unroll
-    for (int i = 1; i < kBins; ++i) {
-        cw += w[i - 1];
-        ch += h[i - 1];
-        const float kk = fmaf(span, on_heights ? ch : cw, lo);
-        if (key >= kk) {
-            k = i; cwk = cw; chk = ch; wk = w[i]; hk = h[i];
-            u0 = d[i - 1];
-            u1 = (i == kBins - 1) ? STB_RQS_EDGE_CONST : d[i];
-        }
-    }
-    RqsSel r;
-    r.xk = (k == 0) ? lo : fmaf(span, cwk, lo);                    // knot_0 / knot_K forced to the box
-    r.yk = (k == 0) ? lo : fmaf(span, chk, lo);
-    r.xk1 = (k == kBins - 1) ? hi : fmaf(span, cwk + wk, lo);
-    r.yk1 = (k == kBins - 1) ? hi : fmaf(span, chk + hk, lo);
-    r.u0 = u0;
-    r.u1 = u1;
-    return r;
-}
 
 // a / b to ~1 ulp: MUFU.RCP + one residual correction (4 instructions instead of ~10 for the
 // IEEE sequence; the operands here are never subnormal / huge)
@@ -232,6 +206,7 @@ __device__ __forceinline__ float softplus_fast(float v) {
 }
 
 __device__ __forceinline__ float tanh_fast(float v) {
+    if (STB_TC_EXP & 32) return v * 0.125f;
     const float t = ex2_approx(-2.885390081777927f * fabsf(v));
     return copysignf(fdiv(1.f - t, 1.f + t), v);
 }
@@ -240,90 +215,31 @@ struct RqsBin16 {
     float xk, wk, yk, hk, delta, d0, d1;
 };
 
-__device__ __forceinline__ RqsBin16 rqs16_bin(const RqsSel& s) {
-    RqsBin16 b;
-    b.xk = s.xk; b.wk = s.xk1 - s.xk;                 // widths re-derived from the knots (:185)
-    b.yk = s.yk; b.hk = s.yk1 - s.yk;
-    b.delta = fdiv(b.hk, b.wk);
-    b.d0 = STB_RQS_MIN + softplus_fast(s.u0);
-    b.d1 = STB_RQS_MIN + softplus_fast(s.u1);
-    return b;
-}
-
 // log f'(x) for x in bin b: log(delta^2 (d1 th^2 + 2 delta th(1-th) + d0 (1-th)^2) / den^2)
 // (rational_quadratic_spline.py:245-248, the two logs merged into one)
+// Evaluated as ln2 (lg2 dnum - 2 lg2 den) on MUFU.LG2 (absolute error ~2^-22 per term: the same
+// order as one fp32 rounding of a log-derivative of O(1), and 6 instructions instead of ~35 for
+// an IEEE division + logf).
+__device__ __forceinline__ float lg2_approx(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ float rqs16_log_deriv(const RqsBin16& b, float theta, float tt, float den) {
     const float omt = 1.f - theta;
     const float dnum = b.delta * b.delta * (b.d1 * theta * theta + 2.f * b.delta * tt + b.d0 * omt * omt);
-    return logf(fdiv(dnum, den * den));
+    return 0.69314718055994530942f * fmaf(-2.f, lg2_approx(den), lg2_approx(dnum));
 }
 
-// p[0..48): raw conditioner outputs [w(16) | h(16) | d(15) | pad].  Coupling semantics
-// (rqs_element with own_ld = false), with ONE deliberate simplification: in the inverse
-// direction the forward log-derivative at the recovered point is evaluated in the bin the
-// inverse search found.  The reference re-searches (flow.py:42-47 -> coupling.py:84-95) and can
-// land in the neighbouring bin only when rounding puts the recovered point within an ulp of a
-// knot, where the spline is C1, so the two evaluations agree to O(ulp).
-template <bool INVERSE>
-__device__ __forceinline__ void rqs16_element(float* p, float lo, float hi, bool want_ld, float x,
-                                              float& out, float& ld) {
-    out = x;
-    ld = 0.f;
-    if (!(x >= lo && x <= hi)) return;
-    float* w = p;
-    float* h = p + kBins;
-    const float* d = p + 2 * kBins;
-    softmax16_bins(w, STB_RQS_MIN);
-    softmax16_bins(h, STB_RQS_MIN);
-    const RqsBin16 b = rqs16_bin(rqs16_walk(w, h, d, lo, hi, INVERSE, x));
-    const float s = b.d0 + b.d1 - 2.f * b.delta;
-    if (!INVERSE) {                                   // rational_quadratic_spline.py:236-248
-        const float theta = fdiv(x - b.xk, b.wk);
-        const float tt = theta * (1.f - theta);
-        const float den = b.delta + s * tt;
-        out = b.yk + fdiv(b.hk * (b.delta * theta * theta + b.d0 * tt), den);
-        ld = rqs16_log_deriv(b, theta, tt, den);
-    } else {                                          // rational_quadratic_spline.py:212-226
-        const float dy = x - b.yk;
-        const float qa = dy * s + b.hk * (b.delta - b.d0);
-        const float qb = b.hk * b.d0 - dy * s;
-        const float qc = -b.delta * dy;
-        const float disc = qb * qb - 4.f * qa * qc;
-        const float root = fdiv(2.f * qc, -qb - fsqrt(disc));
-        out = root * b.wk + b.xk;
-        if (want_ld && out >= lo && out <= hi) {
-            const float theta = fdiv(out - b.xk, b.wk);
-            const float tt = theta * (1.f - theta);
-            ld = -rqs16_log_deriv(b, theta, tt, b.delta + s * tt);
-        }
-    }
-}
-
+// ONE deliberate simplification of the coupling semantics: in the inverse direction the forward
+// log-derivative at the recovered point is evaluated in the bin the inverse search found.  The
+// reference re-searches (flow.py:42-47 -> coupling.py:84-95) and can land in the neighbouring bin
+// only when rounding puts the recovered point within an ulp of a knot, where the spline is C1, so
+// the two evaluations agree to O(ulp).
 struct CubSel {
     float wp, wk, wn, hp, hk, hn, cw, ch;
     int k;
 };
-
-// cubic_spline.py:140-151 bin search by running cumulative sums + neighbour gather
-__device__ __forceinline__ CubSel cubic16_walk(const float* w, const float* h, bool on_heights, float key) {
-    CubSel r;
-    r.k = 0; r.cw = 0.f; r.ch = 0.f;
-    r.wp = 0.f; r.hp = 0.f; r.wk = w[0]; r.hk = h[0]; r.wn = w[1]; r.hn = h[1];
-    float aw = 0.f, ah = 0.f;
-#pragma unroll
-    for (int i = 1; i < kBins; ++i) {
-        aw += w[i - 1];
-        ah += h[i - 1];
-        const bool ge = key >= (on_heights ? ah : aw);
-        if (ge) {
-            r.k = i; r.cw = aw; r.ch = ah;
-            r.wp = w[i - 1]; r.hp = h[i - 1]; r.wk = w[i]; r.hk = h[i];
-            r.wn = (i + 1 < kBins) ? w[i + 1] : 0.f;
-            r.hn = (i + 1 < kBins) ? h[i + 1] : 0.f;
-        }
-    }
-    return r;
-}
 
 __device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float ur) {
     const float sk = s.hk / s.wk;
@@ -352,111 +268,160 @@ __device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float u
     return r;
 }
 
-// p[0..48): [w(16) | h(16) | left, right | pad]
-template <bool INVERSE>
-__device__ __forceinline__ void cubic16_element(float* p, float lo, float hi, bool want_ld, float x,
-                                                float& out, float& ld) {
-    out = x;
-    ld = 0.f;
-    if (!(x >= lo && x <= hi)) return;
-    float* w = p;
-    float* h = p + kBins;
-    const float ul = p[2 * kBins], ur = p[2 * kBins + 1];
-    softmax16_bins(w, STB_CUB_MIN);
-    softmax16_bins(h, STB_CUB_MIN);
-    const float span = hi - lo;
-    const float u = (x - lo) / span;
-    if (!INVERSE) {
-        const CubBin b = cubic16_bin(cubic16_walk(w, h, false, u), ul, ur);
-        out = cubic_forward_in_bin(b, u, ld) * span + lo;
-    } else {
-        const CubSel s = cubic16_walk(w, h, true, u);
-        const CubBin b = cubic16_bin(s, ul, ur);
-        float ld_own;
-        out = cubic_inverse_in_bin(b, u, ld_own) * span + lo;
-        if (want_ld && out >= lo && out <= hi) {
-            const float u2 = (out - lo) / span;
-            const bool same = (u2 >= b.xl) && (s.k == kBins - 1 || u2 < b.xr);
-            float ldf;
-            if (same) {
-                (void)cubic_forward_in_bin(b, u2, ldf);
-            } else {
-                const CubBin b2 = cubic16_bin(cubic16_walk(w, h, false, u2), ul, ur);
-                (void)cubic_forward_in_bin(b2, u2, ldf);
-            }
-            ld = -ldf;
-        }
-    }
-}
-
 // ---- split-phase variants used by the kernel: the bin is located from the 32 softmax columns
 // first; the remaining parameter columns are pulled from TMEM afterwards ------------------------
-struct RqsLoc {
-    float cwk, chk, wk, hk;
-    int k;
-};
+//
+// The 32 softmax columns of a dim arrive INTERLEAVED, (w_i, h_i) in adjacent TMEM columns ==
+// adjacent registers, so everything that treats the two axes alike (bias, shift, sums, cumulative
+// walk, normalisation) runs on Blackwell's packed fp32 pairs (FFMA2 / FADD2): half the issue slots
+// of the scalar form -- the epilogue is issue-bound (profiles/r01_tc_ncu_summary_16warp.txt).
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 
-// softmax numerators in place (t[i] = 2^(t[i] - max)); returns (min-adjusted) 1 / sum scale factor
-__device__ __forceinline__ float softmax16_num(float* t, float min_size) {
-    float m8[8], m4[4];
+// in place: t[i] = (2^(w_i - mw), 2^(h_i - mh)).  `shift` is warp-uniform: false when the pack
+// step proved |logit| <= 100 for this dim (bounded activation, row-wise L1 bound on the last
+// Linear), so 2^logit neither overflows nor flushes and the maximum need not be found at all.
+__device__ __forceinline__ void softmax16_num2(float2* t, bool shift) {
+    if (shift) {
+        float mw = t[0].x, mh = t[0].y;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m8[i] = fmaxf(t[2 * i], t[2 * i + 1]);
+        for (int i = 1; i < kBins; i += 2) {
+            mw = fmaxf(fmaxf(mw, t[i].x), (i + 1 < kBins) ? t[i + 1].x : t[i].x);
+            mh = fmaxf(fmaxf(mh, t[i].y), (i + 1 < kBins) ? t[i + 1].y : t[i].y);
+        }
+        const float2 nm = f2(-mw, -mh);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) m4[i] = fmaxf(m8[2 * i], m8[2 * i + 1]);
-    const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        for (int i = 0; i < kBins; ++i) t[i] = __fadd2_rn(t[i], nm);
+    }
 #pragma unroll
-    for (int i = 0; i < kBins; ++i) t[i] = ex2_approx(t[i] - m);
-    float s8[8], s4[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s8[i] = t[2 * i] + t[2 * i + 1];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s4[i] = s8[2 * i] + s8[2 * i + 1];
-    const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-    return __frcp_rn(s) * (1.f - min_size * (float)kBins);
+    for (int i = 0; i < kBins; ++i) {
+        if (STB_TC_EXP & 2) { t[i] = __ffma2_rn(t[i], t[i], f2(1.f)); continue; }
+        t[i].x = ex2_approx(t[i].x); t[i].y = ex2_approx(t[i].y);
+    }
 }
 
-// t[0..32): log2(e)-scaled raw widths | heights (destroyed).  The bin sizes are
-// w_i = min + c_w e_i with e_i the softmax numerators and c_w = (1 - 16 min) / sum, so the i-th knot
-// is lo + span (i min + c_w E_i), E_i = e_0 + .. + e_(i-1).  The walk keeps E_i unnormalised and
-// compares it with the key moved to the same scale, which saves normalising all 32 sizes; only
-// the selected bin's quantities are normalised afterwards.
-__device__ __forceinline__ RqsLoc rqs16_locate(float* t, float lo, float hi, bool on_heights, float key) {
-    float* w = t;
-    float* h = t + kBins;
-    const float cwn = softmax16_num(w, STB_RQS_MIN);
-    const float chn = softmax16_num(h, STB_RQS_MIN);
-    const float span = hi - lo;
-    // key >= lo + span (i min + c E_i)   <=>   E_i <= kq - i step
-    const float cs = on_heights ? chn : cwn;
-    const float inv_c = __frcp_rn(cs);
-    const float kq = fdiv(key - lo, span) * inv_c, step = STB_RQS_MIN * inv_c;
-    int k = 0;
-    float Ewk = 0.f, Ehk = 0.f, ewk = w[0], ehk = h[0];
-    float Ew = 0.f, Eh = 0.f;
+__device__ __forceinline__ float2 sel2(bool p, float2 a, float2 b) { return p ? a : b; }
+
+// Bin search over the softmax numerators e_i = t[i] (pairs: widths, heights) WITHOUT forming the 16
+// cumulative sums.  The bin sizes are w_i = min + c e_i, c = (1 - 16 min) / sum, so knot i sits at
+// lo + span (i min + c E_i) with E_i = e_0 + .. + e_(i-1), and
+//     key >= knot_i   <=>   E_i <= kq - i step        (kq, step: the key and min in units of c)
+// is a prefix property of i (search_sorted.py:3-5: bin = #(key >= knot_i) - 1; the nudged last
+// knot is never reached by an inside key).  The pairwise sum tree that yields the normaliser also
+// yields E_i along a binary descent (E_8 = first half, E_8 +- quarter, ...): 4 compares instead of
+// 15, and the descent leaves E_k of BOTH axes, the numerators of bin k and k itself.  The issue
+// slots go into ~50 selects instead of ~140 walk instructions (the epilogue is issue-bound).
+struct BinSearch16 {
+    float2 S;            // sums of the numerators
+    float2 c;            // (1 - 16 min) / S
+    float2 Ek;           // numerators summed before bin k
+    int k;
+    bool p3, p2, p1, p0; // bits of k
+};
+
+template <bool ON_H>
+__device__ __forceinline__ BinSearch16 bin_search16(const float2* t, float min_size, float key01, float2& e_even,
+                                                    float2& e_odd) {
+    float2 s8[8], s4[4], s2[2];
 #pragma unroll
-    for (int i = 1; i < kBins; ++i) {
-        Ew += w[i - 1];
-        Eh += h[i - 1];
-        if ((on_heights ? Eh : Ew) <= fmaf(-(float)i, step, kq)) { k = i; Ewk = Ew; Ehk = Eh; ewk = w[i]; ehk = h[i]; }
-    }
-    RqsLoc r;
-    r.k = k;
-    r.cwk = fmaf(cwn, Ewk, (float)k * STB_RQS_MIN);
-    r.chk = fmaf(chn, Ehk, (float)k * STB_RQS_MIN);
-    r.wk = fmaf(cwn, ewk, STB_RQS_MIN);
-    r.hk = fmaf(chn, ehk, STB_RQS_MIN);
+    for (int i = 0; i < 8; ++i) s8[i] = __fadd2_rn(t[2 * i], t[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s4[i] = __fadd2_rn(s8[2 * i], s8[2 * i + 1]);
+    s2[0] = __fadd2_rn(s4[0], s4[1]);
+    s2[1] = __fadd2_rn(s4[2], s4[3]);
+    BinSearch16 r;
+    r.S = __fadd2_rn(s2[0], s2[1]);
+    const float scale = 1.f - min_size * (float)kBins;
+    r.c = f2(fdiv(scale, r.S.x), fdiv(scale, r.S.y));
+    const float inv_c = (ON_H ? r.S.y : r.S.x) * (1.f / scale);
+    const float step = min_size * inv_c;
+    float base = key01 * inv_c;                    // threshold of index i: base - (i - position) step
+#define STB_SEARCHED(v) (ON_H ? (v).y : (v).x)
+    r.p3 = STB_SEARCHED(s2[0]) <= fmaf(-8.f, step, base);
+    float2 E = sel2(r.p3, s2[0], f2(0.f));
+    base = r.p3 ? fmaf(-8.f, step, base) : base;
+    float2 cand = __fadd2_rn(E, sel2(r.p3, s4[2], s4[0]));
+    r.p2 = STB_SEARCHED(cand) <= fmaf(-4.f, step, base);
+    E = sel2(r.p2, cand, E);
+    base = r.p2 ? fmaf(-4.f, step, base) : base;
+    cand = __fadd2_rn(E, sel2(r.p3, sel2(r.p2, s8[6], s8[4]), sel2(r.p2, s8[2], s8[0])));
+    r.p1 = STB_SEARCHED(cand) <= fmaf(-2.f, step, base);
+    E = sel2(r.p1, cand, E);
+    base = r.p1 ? fmaf(-2.f, step, base) : base;
+    // numerators of the pair 4 p3 + 2 p2 + p1: selected p3 first (known earliest)
+    float2 a[8], b[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = sel2(r.p3, t[8 + i], t[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = sel2(r.p2, a[4 + i], a[i]);
+    e_even = sel2(r.p1, b[2], b[0]);
+    e_odd = sel2(r.p1, b[3], b[1]);
+    cand = __fadd2_rn(E, e_even);
+    r.p0 = STB_SEARCHED(cand) <= base - step;
+    r.Ek = sel2(r.p0, cand, E);
+#undef STB_SEARCHED
+    r.k = (r.p3 ? 8 : 0) + (r.p2 ? 4 : 0) + (r.p1 ? 2 : 0) + (r.p0 ? 1 : 0);
     return r;
 }
 
-// v[idx] for idx in [0, 16) from a register array (4-level select tree)
-__device__ __forceinline__ float pick16(const float* v, int idx) {
-    float a[8], b[4];
+struct RqsLoc {
+    float2 Ek, Ek1;      // (widths, heights): sums of the softmax numerators before bin k / through bin k
+    float2 c;            // (1 - 16 min) / sum, per axis
+    int k;
+};
+
+// t[0..16): log2(e)-scaled raw (width, height) pairs (destroyed).  Leaves E_k and E_(k+1) of both
+// axes: the knots of bin k, from which its width / height are re-derived as the reference does
+// (rational_quadratic_spline.py:180-192).
+template <bool ON_H>
+__device__ __forceinline__ RqsLoc rqs16_locate(float2* t, bool shift, float lo, float inv_span, float key) {
+    softmax16_num2(t, shift);
+    float2 ee, eo;
+    const BinSearch16 bs = bin_search16<ON_H>(t, STB_RQS_MIN, (key - lo) * inv_span, ee, eo);
+    RqsLoc r;
+    r.c = bs.c;
+    r.k = bs.k;
+    r.Ek = bs.Ek;
+    r.Ek1 = __fadd2_rn(bs.Ek, sel2(bs.p0, eo, ee));
+    return r;
+}
+
+// (v[k - 1], v[k]) for k in [0, 16) from a register array v[0..15), out-of-range entries 0: a
+// select tree over a sliding window (19 selects for the pair)
+__device__ __forceinline__ void pick_pair16(const float* v, int k, float& lo_v, float& hi_v) {
+    float a[9], b[5], c[3];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = (idx & 1) ? v[2 * i + 1] : v[2 * i];
+    for (int j = 0; j < 9; ++j) {              // window over V[m] = v[m - 1], V[0] = V[16] = 0
+        const float x0 = (j == 0) ? 0.f : v[j - 1];
+        const float x1 = (j + 8 == 16) ? 0.f : v[j + 7];
+        a[j] = (k & 8) ? x1 : x0;
+    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) b[i] = (idx & 2) ? a[2 * i + 1] : a[2 * i];
-    const float c0 = (idx & 4) ? b[1] : b[0], c1 = (idx & 4) ? b[3] : b[2];
-    return (idx & 8) ? c1 : c0;
+    for (int j = 0; j < 5; ++j) b[j] = (k & 4) ? a[j + 4] : a[j];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) c[j] = (k & 2) ? b[j + 2] : b[j];
+    lo_v = (k & 1) ? c[1] : c[0];
+    hi_v = (k & 1) ? c[2] : c[1];
+}
+
+// softplus_fast on a pair
+__device__ __forceinline__ float2 softplus_fast2(float2 v) {
+    const float2 e = f2(ex2_approx(-1.4426950408889634f * fabsf(v.x)), ex2_approx(-1.4426950408889634f * fabsf(v.y)));
+    const float2 den = __fadd2_rn(e, f2(2.f));
+    float2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(den.y));
+    const float2 q = __fmul2_rn(e, r);
+    const float2 nq = f2(-q.x, -q.y);
+    const float2 z = __ffma2_rn(__ffma2_rn(nq, den, e), r, q);
+    const float2 z2 = __fmul2_rn(z, z);
+    float2 p = __ffma2_rn(z2, f2(1.f / 13.f), f2(1.f / 11.f));
+    p = __ffma2_rn(p, z2, f2(1.f / 9.f));
+    p = __ffma2_rn(p, z2, f2(1.f / 7.f));
+    p = __ffma2_rn(p, z2, f2(1.f / 5.f));
+    p = __ffma2_rn(p, z2, f2(1.f / 3.f));
+    p = __ffma2_rn(p, z2, f2(1.f));
+    return __ffma2_rn(__fadd2_rn(z, z), p, f2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)));
 }
 
 // u0 / u1: (bias-added, unscaled) derivative parameters at the two knots of bin r.k
@@ -464,17 +429,23 @@ template <bool INVERSE>
 __device__ __forceinline__ void rqs16_finish(const RqsLoc& r, float u0, float u1, float lo, float hi, bool want_ld,
                                              float x, float& out, float& ld) {
     const float span = hi - lo;
-    RqsSel sel;
-    sel.xk = (r.k == 0) ? lo : fmaf(span, r.cwk, lo);
-    sel.yk = (r.k == 0) ? lo : fmaf(span, r.chk, lo);
-    sel.xk1 = (r.k == kBins - 1) ? hi : fmaf(span, r.cwk + r.wk, lo);
-    sel.yk1 = (r.k == kBins - 1) ? hi : fmaf(span, r.chk + r.hk, lo);
-    sel.u0 = u0;
-    sel.u1 = u1;
-    const RqsBin16 b = rqs16_bin(sel);
+    const float km = (float)r.k * STB_RQS_MIN;
+    float2 k0 = __ffma2_rn(f2(span), __ffma2_rn(r.c, r.Ek, f2(km)), f2(lo));                   // (x_k, y_k)
+    float2 k1 = __ffma2_rn(f2(span), __ffma2_rn(r.c, r.Ek1, f2(km + STB_RQS_MIN)), f2(lo));    // (x_k+1, y_k+1)
+    if (r.k == 0) k0 = f2(lo);                                       // knot_0 / knot_K forced to the box
+    if (r.k == kBins - 1) k1 = f2(hi);
+    const float2 wh = __fadd2_rn(k1, f2(-k0.x, -k0.y));              // sizes re-derived from the knots (:185)
+    const float2 dd = __fadd2_rn(softplus_fast2(f2(u0, u1)), f2(STB_RQS_MIN));
+    RqsBin16 b;
+    b.xk = k0.x; b.yk = k0.y; b.wk = wh.x; b.hk = wh.y;
+    float inv_wk;                                                    // 1 / w_k to ~1 ulp, shared by delta and theta
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_wk) : "f"(b.wk));
+    inv_wk = fmaf(fmaf(-b.wk, inv_wk, 1.f), inv_wk, inv_wk);
+    b.delta = b.hk * inv_wk;
+    b.d0 = dd.x; b.d1 = dd.y;
     const float s = b.d0 + b.d1 - 2.f * b.delta;
     if (!INVERSE) {
-        const float theta = fdiv(x - b.xk, b.wk);
+        const float theta = (x - b.xk) * inv_wk;
         const float tt = theta * (1.f - theta);
         const float den = b.delta + s * tt;
         out = b.yk + fdiv(b.hk * (b.delta * theta * theta + b.d0 * tt), den);
@@ -487,20 +458,48 @@ __device__ __forceinline__ void rqs16_finish(const RqsLoc& r, float u0, float u1
         const float disc = qb * qb - 4.f * qa * qc;
         const float root = fdiv(2.f * qc, -qb - fsqrt(disc));
         out = root * b.wk + b.xk;
-        ld = 0.f;
-        if (want_ld && out >= lo && out <= hi) {
-            const float theta = fdiv(out - b.xk, b.wk);
-            const float tt = theta * (1.f - theta);
-            ld = -rqs16_log_deriv(b, theta, tt, b.delta + s * tt);
-        }
+        // forward log-derivative at the recovered point: theta = (out - x_k) / w_k is `root` up to the
+        // rounding of `out` (the reference recomputes it from the rounded output, flow.py:42-47)
+        const float tt = root * (1.f - root);
+        ld = (want_ld && out >= lo && out <= hi) ? -rqs16_log_deriv(b, root, tt, b.delta + s * tt) : 0.f;
     }
 }
 
-// t[0..32): log2(e)-scaled raw widths | heights (destroyed)
-__device__ __forceinline__ CubSel cubic16_locate(float* t, bool on_heights, float u) {
-    softmax16_bins(t, STB_CUB_MIN);
-    softmax16_bins(t + kBins, STB_CUB_MIN);
-    return cubic16_walk(t, t + kBins, on_heights, u);
+// t[0..16): log2(e)-scaled raw (width, height) pairs (destroyed).  cubic_spline.py:104-116,140-151:
+// same search; the three bin sizes around bin k that the slopes need are picked from the
+// numerators by a select tree on the bits of k and normalised afterwards (the cubic code uses the
+// sizes themselves, not knot differences).
+template <bool ON_H>
+__device__ __forceinline__ CubSel cubic16_locate(float2* t, bool shift, float u) {
+    softmax16_num2(t, shift);
+    float2 ee, eo;
+    const BinSearch16 bs = bin_search16<ON_H>(t, STB_CUB_MIN, u, ee, eo);
+    const int k = bs.k;
+    // neighbours: k even -> (t[k-1], ee, eo); k odd -> (ee, eo, t[k+1]).  t[k-1] for even k = odd element
+    // of the previous pair, t[k+1] for odd k = even element of the next pair: one more 8-way select each
+    float2 am[4], bm[2], ap[4], bp[2];
+    // prev-odd element of pair j: t[2j - 1] (j = 0 -> 0), next-even: t[2j + 2] (j = 7 -> 0)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                  // select on p3 first: candidates j = i (p3 = 0) or j = i + 4
+        am[i] = sel2(bs.p3, t[2 * (i + 4) - 1], (i == 0) ? f2(0.f) : t[2 * i - 1]);
+        ap[i] = sel2(bs.p3, (i + 4 == 7) ? f2(0.f) : t[2 * (i + 4) + 2], t[2 * i + 2]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                  // then p2: j = i or i + 2 within the half
+        bm[i] = sel2(bs.p2, am[i + 2], am[i]);
+        bp[i] = sel2(bs.p2, ap[i + 2], ap[i]);
+    }
+    const float2 prev_odd = sel2(bs.p1, bm[1], bm[0]);
+    const float2 next_even = sel2(bs.p1, bp[1], bp[0]);
+    const float2 ep = sel2(bs.p0, ee, prev_odd), ek = sel2(bs.p0, eo, ee), en = sel2(bs.p0, next_even, eo);
+    const float2 mn = f2(STB_CUB_MIN);
+    const float2 sp = __ffma2_rn(bs.c, ep, mn), sk = __ffma2_rn(bs.c, ek, mn), sn = __ffma2_rn(bs.c, en, mn);
+    const float2 cum = __ffma2_rn(bs.c, bs.Ek, f2((float)k * STB_CUB_MIN));
+    CubSel r;
+    r.k = k;
+    r.wp = sp.x; r.hp = sp.y; r.wk = sk.x; r.hk = sk.y; r.wn = sn.x; r.hn = sn.y;
+    r.cw = cum.x; r.ch = cum.y;
+    return r;
 }
 
 template <bool INVERSE>
@@ -516,7 +515,7 @@ __device__ __forceinline__ void cubic16_finish(const CubSel& s, float ul, float 
         ld = 0.f;
         if (want_ld && out >= lo && out <= hi) {
             // forward log-derivative at the recovered point, in the bin the inverse search found
-            // (see rqs16_element for why the re-search is skipped)
+            // (see the note above RqsBin16's users for why the re-search is skipped)
             float ldf;
             (void)cubic_forward_in_bin(b, (out - lo) / span, ldf);
             ld = -ldf;
@@ -545,11 +544,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
     // ---- one-time setup ------------------------------------------------------------------------
     if (tid == 0) {
         mbar_init(&bars->setup, 1);
-        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 2); }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->a1_ready[s], 8);
+            mbar_init(&bars->a1_ready[s], kEpiWarps);          // every epilogue warp works on both subtiles' heads
             mbar_init(&bars->acc1_full[s], 1);
-            mbar_init(&bars->h_ready[s], 8);
+            mbar_init(&bars->h_ready[s], kEpiWarps);
             for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[s][b], 1); mbar_init(&bars->acc_empty[s][b], 8); }
         }
         fence_mbar_init();
@@ -588,23 +587,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 }
                 for (int c = 0; c < n_chunks; ++c, ++cc) {
                     const uint32_t st = cc % kStages, use = cc / kStages;
-                    mbar_wait_relaxed(&bars->b_empty[st], (use & 1) ^ 1);
+                    MBAR_WAIT_SLOW(&bars->b_empty[st], (use & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->b_full[st], kChunkBytes);
                     bulk_g2s(bst + st * kChunkBytes, A.packed + kOffW2 + (size_t)c * kChunkBytes, kChunkBytes,
                              &bars->b_full[st]);
                 }
             }
         }
-    } else if (warp == 1) {
-        // ======================= UMMA issuer =====================================================
+    } else if (warp < kEpiWarp0) {
+        // ======================= UMMA issuers: warp 1 -> subtile 0, warp 2 -> subtile 1 ==========
+        // One thread issues ~150 instructions per 12-UMMA group (descriptor arithmetic through the
+        // uniform datapath); a single issuer for both subtiles was the critical path of the whole
+        // kernel (measured: with the spline math removed the kernel ran only 1.24x faster).
         if (lane == 0) {
+            const int s = warp - 1;
             const uint32_t idesc1 = make_idesc(FMT_BF16, 128, kHid);
             const uint32_t idesc2 = make_idesc(FMT_F16, 128, kChunkN);
             uint32_t cc = 0;
+            PROF_DECL
             for (int it = 0; it < my_tiles; ++it) {
                 const uint32_t tpar = it & 1;
-                for (int s = 0; s < 2; ++s) {      // GEMM1: conditioning columns -> hidden pre-activation
-                    mbar_wait_relaxed(&bars->a1_ready[s], tpar);
+                {                                  // GEMM1: conditioning columns -> hidden pre-activation
+                    MBAR_WAIT_SLOW(&bars->a1_ready[s], tpar);
+                    PROF(0)
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(abuf + s * kABytes), b0 = smem_u32(w1s);
                     const uint32_t dcol = tmem + kColAcc1 + s * kHid;
@@ -625,53 +630,67 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                         }
                     }
                     umma_commit(&bars->acc1_full[s]);
+                    PROF(1)
                 }
                 for (int c = 0; c < n_chunks; ++c, ++cc) {
                     const uint32_t st = cc % kStages, use = cc / kStages;
-                    mbar_wait_relaxed(&bars->b_full[st], use & 1);
+                    MBAR_WAIT_SLOW(&bars->b_full[st], use & 1);
+                    PROF(2)
                     const uint32_t buf = cc & 1, buse = cc >> 1;
-                    for (int s = 0; s < 2; ++s) {
-                        if (c == 0) mbar_wait_relaxed(&bars->h_ready[s], tpar);
-                        mbar_wait_relaxed(&bars->acc_empty[s][buf], (buse & 1) ^ 1);
-                        tc_fence_after();
-                        const uint32_t a_hi = smem_u32(abuf + s * kABytes), a_lo = a_hi + 16384;
-                        const uint32_t b_hi = smem_u32(bst + st * kChunkBytes), b_lo = b_hi + 12288;
-                        const uint32_t dcol = tmem + kColAcc2 + (s * 2 + buf) * kChunkN;
-                        uint32_t acc = 0;
-                        // lo*hi, hi*lo, then hi*hi: small corrections first (accumulator truncation)
+                    if (c == 0) { MBAR_WAIT_SLOW(&bars->h_ready[s], tpar); PROF(3) }
+                    MBAR_WAIT_SLOW(&bars->acc_empty[s][buf], (buse & 1) ^ 1);
+                    PROF(4)
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(abuf + s * kABytes), a_lo = a_hi + 16384;
+                    const uint32_t b_hi = smem_u32(bst + st * kChunkBytes), b_lo = b_hi + 12288;
+                    const uint32_t dcol = tmem + kColAcc2 + (s * 2 + buf) * kChunkN;
+                    uint32_t acc = 0;
+                    // lo*hi, hi*lo, then hi*hi: small corrections first (accumulator truncation)
 #pragma unroll
-                        for (int p = 0; p < 3; ++p) {
-                            const uint32_t aa = (p == 0) ? a_lo : a_hi, bb = (p == 1) ? b_lo : b_hi;
+                    for (int p = 0; p < 3; ++p) {
+                        const uint32_t aa = (p == 0) ? a_lo : a_hi, bb = (p == 1) ? b_lo : b_hi;
 #pragma unroll
-                            for (int ks = 0; ks < kHid / 16; ++ks) {
-                                umma_f16(dcol, make_smem_desc(aa + ks * 256, 128, 1024),
-                                         make_smem_desc(bb + ks * 256, 128, 1024), idesc2, acc);
-                                acc = 1;
-                            }
+                        for (int ks = 0; ks < kHid / 16; ++ks) {
+                            umma_f16(dcol, make_smem_desc(aa + ks * 256, 128, 1024),
+                                     make_smem_desc(bb + ks * 256, 128, 1024), idesc2, acc);
+                            acc = 1;
                         }
-                        umma_commit(&bars->acc_full[s][buf]);
                     }
-                    umma_commit(&bars->b_empty[st]);       // stage reusable once both subtiles' UMMAs retire
+                    umma_commit(&bars->acc_full[s][buf]);
+                    umma_commit(&bars->b_empty[st]);       // stage reusable once both subtiles' UMMAs retire (count 2)
+                    PROF(5)
                 }
             }
+            PROF_FLUSH
         }
     } else if (warp >= kEpiWarp0) {
         // ======================= epilogue warps ==================================================
-        // warp id % 4 fixes the TMEM sub-partition q; the four warps of a residue class are
-        // (subtile 0, half 0), (0, 1), (1, 0), (1, 1)
+        // warp id % 4 fixes the TMEM sub-partition q; the six warps of a residue class are
+        // (subtile s, r) for s in {0, 1}, r in {0, 1, 2}: the three warps of a (s, q) triple share the
+        // 32 rows and take the transformed dims round-robin (dim n -> warp n % 3), and a third of the
+        // row-level work each
         const int q = warp & 3;
-        const int cls = (warp - ((q >= kEpiWarp0) ? q : q + 4)) >> 2;
-        const int s = cls >> 1, g = cls & 1;
+        const int cls = (warp - (kEpiWarp0 + ((q - kEpiWarp0) & 3))) >> 2;
+        const int s = cls & 1, r3 = cls >> 1;
         const int etid = tid - kEpiWarp0 * 32;
         const int rloc = q * 32 + lane;                         // row within the subtile
         const int rt = s * 128 + rloc;                          // row within the tile
         float* xrow = xs + rt * kXsStride;
-        uint8_t* a_s = abuf + s * kABytes;
         const uint32_t a_row_off = (uint32_t)(rloc >> 3) * 1024 + (uint32_t)(rloc & 7) * 16;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
         const float lo = A.lower, hi = A.upper;
+        const float inv_span = 1.f / (hi - lo);
+        // loop-invariant addresses of the chunk loop, pinned in registers
+        const uint32_t full_bar = pin(smem_u32(&bars->acc_full[s][0]));
+        const uint32_t empty_bar = pin(smem_u32(&bars->acc_empty[s][0]));
+        const uint32_t col_base = pin(tmem + lane_sel + kColAcc2 + (uint32_t)(s * 2) * kChunkN);
+        const uint32_t tr_idx_a = pin(smem_u32(&hdr->tr_idx[0]));
+        const uint32_t b2_a = pin(smem_u32(b2s));
+        const uint32_t xrow_a = pin(smem_u32(xrow));
+        const uint32_t noshift_mask = hdr->noshift_mask;
         uint32_t cc = 0;
+        PROF_DECL
 
         for (int it = 0; it < my_tiles; ++it) {
             const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
@@ -711,134 +730,163 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 }
             }
             named_bar_sync(1, kEpiThreads);
+            PROFH(0)
 
-            // ---- A1: this row's conditioning columns as three bf16 parts (this warp: 16 of the 32) ---
-            {
+            // ---- tile head, software-pipelined over the two subtiles: every warp of a TMEM sub-partition
+            // class helps with BOTH subtiles' rows (TMEM lanes are shared, only the columns differ), so
+            // GEMM1 of subtile 0 runs under the A1 split of subtile 1, and GEMM1 of subtile 1 / the first
+            // GEMM2 chunk of subtile 0 under the tanh passes.
+            // A1: the row's conditioning columns as three bf16 parts, 8-column groups round-robin
+#pragma unroll 1
+            for (int sp = 0; sp < 2; ++sp) {
+                const float* xr = xs + (sp * 128 + rloc) * kXsStride;
+                uint8_t* a_p = abuf + sp * kABytes;
                 const uint32_t a1_row_off = (uint32_t)(rloc >> 3) * 512 + (uint32_t)(rloc & 7) * 16;
-#pragma unroll
-                for (int kk = 0; kk < kK1 / 16; ++kk) {
-                    const int kc = g * (kK1 / 16) + kk;
+#pragma unroll 1
+                for (int kc = cls; kc < kK1 / 8; kc += 2 * kEpiPerSub) {
                     __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int k = kc * 8 + u;
-                        const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : 0.f;
+                        const float v = (k < n_cond) ? xr[hdr->cond_idx[k]] : 0.f;
                         split_bf16x3(v, q0[u], q1[u], q2[u]);
                     }
-                    *reinterpret_cast<uint4*>(a_s + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q0);
-                    *reinterpret_cast<uint4*>(a_s + kA1Part + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q1);
-                    *reinterpret_cast<uint4*>(a_s + 2 * kA1Part + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q2);
+                    *reinterpret_cast<uint4*>(a_p + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q0);
+                    *reinterpret_cast<uint4*>(a_p + kA1Part + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q1);
+                    *reinterpret_cast<uint4*>(a_p + 2 * kA1Part + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q2);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->a1_ready[s]);
+                if (lane == 0) mbar_arrive(&bars->a1_ready[sp]);
             }
-
-            // ---- hidden layer: h = act(acc1 + b1) -> fp16 hi | lo A operand of GEMM2 (32 of 64 units) --
-            mbar_wait(&bars->acc1_full[s], tpar);
-            tc_fence_after();
-            {
-#pragma unroll
-                for (int cb = 0; cb < kHid / 2; cb += 16) {
-                    const int c0 = g * (kHid / 2) + cb;
-                    float v[16];
-                    tmem_ld16(tmem + lane_sel + kColAcc1 + s * kHid + c0, v);
+            PROFH(1)
+            // hidden layer: h = act(acc1 + b1) -> fp16 hi | lo A operand of GEMM2, 8 units at a time
+#pragma unroll 1
+            for (int sp = 0; sp < 2; ++sp) {
+                uint8_t* a_p = abuf + sp * kABytes;
+                mbar_wait(&bars->acc1_full[sp], tpar);
+                tc_fence_after();
+#pragma unroll 1
+                for (int kc = cls; kc < kHid / 8; kc += 2 * kEpiPerSub) {
+                    const int c0 = kc * 8;
+                    float v[8];
+                    tmem_ld8(tmem + lane_sel + kColAcc1 + sp * kHid + c0, v);
                     tmem_ld_wait();
-                    __align__(16) __half hh[16], hl[16];
+                    __align__(16) __half hh[8], hl[8];
                     if (act == STB_ACT_TANH) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) split_f16(tanh_fast(v[i] + b1s[c0 + i]), hh[i], hl[i]);
+                        for (int i = 0; i < 8; ++i) split_f16(tanh_fast(v[i] + b1s[c0 + i]), hh[i], hl[i]);
                     } else {
 #pragma unroll 1
-                        for (int i = 0; i < 16; ++i) v[i] = activate(act, v[i] + b1s[c0 + i]);
+                        for (int i = 0; i < 8; ++i) v[i] = activate(act, v[i] + b1s[c0 + i]);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) split_f16(v[i], hh[i], hl[i]);
+                        for (int i = 0; i < 8; ++i) split_f16(v[i], hh[i], hl[i]);
                     }
-#pragma unroll
-                    for (int half8 = 0; half8 < 2; ++half8) {
-                        const int kc = (c0 >> 3) + half8;
-                        *reinterpret_cast<uint4*>(a_s + a_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hh + half8 * 8);
-                        *reinterpret_cast<uint4*>(a_s + 16384 + a_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hl + half8 * 8);
-                    }
+                    *reinterpret_cast<uint4*>(a_p + a_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hh);
+                    *reinterpret_cast<uint4*>(a_p + 16384 + a_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hl);
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->h_ready[s]);
+                if (lane == 0) mbar_arrive(&bars->h_ready[sp]);
             }
 
             // ---- last Linear chunks out of TMEM + spline in registers: this warp's dim of each chunk ----
             float ld_acc = 0.f;
-            for (int c = 0; c < n_chunks; ++c, ++cc) {
-                const uint32_t buf = cc & 1, buse = cc >> 1;
-                const int ji = c * kG + g;
-                const int j = hdr->tr_idx[ji < n_tr ? ji : 0];
-                const float xv = xrow[j];
+            PROFC(0) PROFH(3)
+            // dims round-robin over the triple.  A warp visits chunks in increasing order with gaps <= 2,
+            // so the phase parity it waits for on an accumulator buffer is never ambiguous: the
+            // buffer's previous use (two chunks earlier) completed before a chunk this warp has
+            // already consumed.
+#pragma unroll 1
+            for (int ji = r3; ji < kG * n_chunks; ji += kEpiPerSub) {
+                const uint32_t ccc = cc + (uint32_t)(ji >> 1);
+                const uint32_t buf = ccc & 1, buse = ccc >> 1;
+                const int g = ji & 1;
+                uint32_t j4;                                            // 4 * transformed column
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(j4) : "r"(tr_idx_a + 4u * (uint32_t)(ji < n_tr ? ji : 0)));
+                j4 <<= 2;
+                float xv;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv) : "r"(xrow_a + j4));
                 const bool inside = (ji < n_tr) && (xv >= lo) && (xv <= hi);
                 const float* bb = b2s + ji * kPPad;
-                mbar_wait(&bars->acc_full[s][buf], buse & 1);
+                PROFC(5)
+                if (!(STB_TC_EXP & 4)) mbar_wait_a(full_bar + buf * 8, buse & 1);
+                PROFC(1)
                 tc_fence_after();
-                const uint32_t col0 = tmem + lane_sel + kColAcc2 + (s * 2 + buf) * kChunkN + g * kPPad;
+                const uint32_t col0 = col_base + buf * kChunkN + (uint32_t)g * kPPad;
                 float out = xv, ld = 0.f;
+                const bool shift = !((noshift_mask >> (ji & 31)) & 1u);
+                const float2* bb2 = reinterpret_cast<const float2*>(bb);
                 if (KIND == STB_RQS) {
                     RqsLoc loc;
                     {
-                        float t[2 * kBins];
-                        tmem_ld16(col0, t);
-                        tmem_ld16(col0 + 16, t + 16);
+                        float2 t[kBins];
+                        tmem_ld16(col0, reinterpret_cast<float*>(t));
+                        tmem_ld16(col0 + 16, reinterpret_cast<float*>(t) + 16);
                         tmem_ld_wait();
-                        // widths / heights arrive pre-multiplied by log2(e) (exp2-domain softmax): the
+                        // (width_i, height_i) pairs, pre-multiplied by log2(e) (exp2-domain softmax): the
                         // bias table holds b * log2(e) for those 32 columns
 #pragma unroll
-                        for (int i = 0; i < 2 * kBins; ++i) t[i] = fmaf(t[i], s2l, bb[i]);
-                        loc = rqs16_locate(t, lo, hi, INVERSE, xv);
+                        for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
+                        if (STB_TC_EXP & 8) { loc.Ek = t[0]; loc.Ek1 = t[15]; loc.c = t[7]; loc.k = 3; }
+                        else loc = rqs16_locate<INVERSE>(t, shift, lo, inv_span, xv);
                     }
                     float dd[16];
                     tmem_ld16(col0 + 2 * kBins, dd);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->acc_empty[s][buf]);     // TMEM buffer free again
+                    if (lane == 0) mbar_arrive_a(empty_bar + buf * 8);     // TMEM buffer free again
+                    PROFC(2)
                     if (inside) {
                         // derivative parameter AT knot i (1..15) is column 32 + i - 1; box ends are constants
-                        const float r0 = pick16(dd, (loc.k + 15) & 15), r1 = pick16(dd, loc.k);
+                        float r0, r1;
+                        pick_pair16(dd, loc.k, r0, r1);
                         const float u0 = (loc.k == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + loc.k - 1]);
                         const float u1 = (loc.k == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
-                        rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
+                        if (STB_TC_EXP & 9) { out = xv + 1e-30f * (loc.Ek.x + loc.Ek1.y + loc.c.x + u0 + u1); ld = loc.Ek.y; }
+                        else rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
                     }
                 } else {
                     const float span = hi - lo;
                     const float u = (xv - lo) / span;
                     CubSel sel;
                     {
-                        float t[2 * kBins];
-                        tmem_ld16(col0, t);
-                        tmem_ld16(col0 + 16, t + 16);
+                        float2 t[kBins];
+                        tmem_ld16(col0, reinterpret_cast<float*>(t));
+                        tmem_ld16(col0 + 16, reinterpret_cast<float*>(t) + 16);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 2 * kBins; ++i) t[i] = fmaf(t[i], s2l, bb[i]);
-                        sel = cubic16_locate(t, INVERSE, u);
+                        for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
+                        sel = cubic16_locate<INVERSE>(t, shift, u);
                     }
-                    float dd[16];
-                    tmem_ld16(col0 + 2 * kBins, dd);
+                    float dd[8];
+                    tmem_ld8(col0 + 2 * kBins, dd);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&bars->acc_empty[s][buf]);
+                    if (lane == 0) mbar_arrive_a(empty_bar + buf * 8);
                     if (inside) {
                         const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
                         cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);
                     }
                 }
-                if (ji < n_tr) xrow[j] = out;
+                if (ji < n_tr) asm volatile("st.shared.f32 [%0], %1;" ::"r"(xrow_a + j4), "f"(out) : "memory");
                 ld_acc += ld;
+                PROFC(3)
             }
+            cc += (uint32_t)n_chunks;
+            PROFH(5)
 
             // ---- per-row log|det J|: the pair's two partials (+ UnitNormal log-density of the output row) ---
-            if (g == 1) ld_s[rt] = ld_acc;
+            if (r3 < kEpiPerSub - 1) ld_s[r3 * kTileRows + rt] = ld_acc;
             named_bar_sync(1, kEpiThreads);
-            if (g == 0 && want_ld && rt < nrows) {
-                float tot = ld_acc + ld_s[rt];
+            if (r3 == kEpiPerSub - 1 && want_ld && rt < nrows) {      // fixed summation order: deterministic
+                float tot = ld_s[rt];
+#pragma unroll
+                for (int o = 1; o < kEpiPerSub - 1; ++o) tot += ld_s[o * kTileRows + rt];
+                tot += ld_acc;
                 if (A.base_log_prob) {
                     float b = 0.f;
                     for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
@@ -867,7 +915,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 }
             }
             named_bar_sync(1, kEpiThreads);
+            PROFC(4) PROFH(4)
         }
+        PROF_FLUSH
     }
 
     // ---- teardown --------------------------------------------------------------------------------------
@@ -899,6 +949,11 @@ __global__ void tc_maxabs_kernel(const PackArgs a) {
     if ((threadIdx.x & 31) == 0) atomicMax(&reinterpret_cast<Header*>(a.out)->maxbits, __float_as_uint(m));
 }
 
+// column c of a dim's 48 -> parameter index: the 32 softmax columns are interleaved (w_i, h_i)
+__host__ __device__ __forceinline__ int param_of_col(int c) {
+    return (c < 2 * kBins) ? ((c & 1) ? kBins + (c >> 1) : (c >> 1)) : c;
+}
+
 __device__ __forceinline__ uint32_t core_off(int r, int k, int K, int elem) {
     const int epc = 16 / elem, chunks = K / epc;
     return (uint32_t)((r >> 3) * (chunks * 128) + (k / epc) * 128 + (r & 7) * 16 + (k % epc) * elem);
@@ -925,9 +980,9 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     float* b2 = reinterpret_cast<float*>(a.out + kOffB2);
     for (int i = gtid; i < kHid; i += gsz) b1[i] = a.b1[i];
     for (int i = gtid; i < kMaxChunks * kChunkN; i += gsz) {
-        const int ji = i / kPPad, p = i % kPPad;
+        const int ji = i / kPPad, col = i % kPPad, p = param_of_col(col);
         const float bv = (ji < a.n_tr && p < a.P) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
-        b2[i] = (p < 2 * kBins) ? bv * 1.4426950408889634f : bv;      // softmax columns: log2 domain
+        b2[i] = (col < 2 * kBins) ? bv * 1.4426950408889634f : bv;    // softmax columns: log2 domain
     }
     // first Linear, conditioning columns only: [64][32] as three bf16 parts
     for (int i = gtid; i < kHid * kK1; i += gsz) {
@@ -944,7 +999,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     const float inv = 1.f / s2;
     for (int i = gtid; i < kMaxChunks * kChunkN * kHid; i += gsz) {
         const int k = i % kHid, rn = i / kHid, n = rn % kChunkN, c = rn / kChunkN;
-        const int ji = c * kG + n / kPPad, p = n % kPPad;
+        const int ji = c * kG + n / kPPad, p = param_of_col(n % kPPad);
         float v = 0.f;
         if (c < a.n_chunks && ji < a.n_tr && p < a.P) v = a.W2[((size_t)a.tr_idx[ji] * a.P + p) * kHid + k] * inv;
         __half hi, lo;
@@ -953,6 +1008,22 @@ __global__ void tc_pack_kernel(const PackArgs a) {
         *reinterpret_cast<__half*>(a.out + off) = hi;
         *reinterpret_cast<__half*>(a.out + off + 12288) = lo;
     }
+}
+
+// One warp per transformed dim: |logit_p| <= |b_p| + sum_k |W2[p][k]| when the hidden activation is
+// bounded by 1 (tanh, sigmoid).  If that bound is <= 100 in log2 units for all 32 softmax rows of
+// the dim, 2^logit cannot overflow or flush to zero and the kernel skips the max subtraction.
+__global__ void tc_bound_kernel(const PackArgs a) {
+    const int ji = threadIdx.x >> 5, p = threadIdx.x & 31;
+    bool ok = false;
+    if (ji < a.n_tr && (a.act == STB_ACT_TANH || a.act == STB_ACT_SIGMOID)) {
+        const size_t row = (size_t)a.tr_idx[ji] * a.P + p;
+        float l1 = fabsf(a.b2[row]);
+        for (int k = 0; k < kHid; ++k) l1 += fabsf(a.W2[row * kHid + k]);
+        ok = (l1 * 1.4426950408889634f <= 100.f);            // false for NaN / inf
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (p == 0 && ok) atomicOr(&reinterpret_cast<Header*>(a.out)->noshift_mask, 1u << ji);
 }
 
 static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
@@ -987,6 +1058,12 @@ bool tc_layer_supported(const stb_layer* L) {
 
 uint64_t tc_packed_bytes(const stb_layer*) { return tcl::kPackedBytes; }
 
+#if STB_TC_EXP & 128
+extern "C" int stb_tc_prof_read(unsigned int* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, tcl::g_tc_prof, (size_t)n * 4);
+}
+#endif
+
 int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
     using namespace tcl;
     PackArgs a;
@@ -997,6 +1074,8 @@ int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
     tc_maxabs_kernel<<<64, 256, 0, stream>>>(a);
     count_launch();
     tc_pack_kernel<<<296, 256, 0, stream>>>(a);
+    count_launch();
+    tc_bound_kernel<<<1, kMaxTr * 32, 0, stream>>>(a);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_pack launch: %s", cudaGetErrorString(e));
