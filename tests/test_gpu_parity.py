@@ -59,8 +59,12 @@ def test_cuda_matches_reference(name, fused):
                 assert torch.equal(y2, y)
             elif op == 'inverse_ldj':
                 xr, ldj = flow.inverse_and_log_det_jacobian(x, **kw)
-                _cmp(name, 'inverse.x', xr)
-                _cmp(name, 'inverse.ldj', ldj)
+                # cubic inverse through several layers: the one-root Cardano branch amplifies 1-ulp
+                # differences in the bin coefficients (the reference's own fp32 run has such outliers,
+                # SURVEY.md 7.3) -- same outlier bound as tests/test_gpu_tc.py
+                fr = 2e-3 if 'cubic' in name else 0.0
+                _cmp(name, 'inverse.x', xr, fr)
+                _cmp(name, 'inverse.ldj', ldj, fr)
                 assert torch.equal(flow.inverse(x, **kw), xr)
             elif op == 'inverse_ldj_unit':
                 xr, ldj = flow.inverse_and_log_det_jacobian(ref(name, 'inverse_unit.y').to(DEV), **kw)

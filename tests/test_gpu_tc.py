@@ -97,7 +97,10 @@ def test_tensor_path_matches_generic_and_oracle(kind, d, masks, monkeypatch):
         # cubic one-root rows whose reference values are themselves ill-conditioned
         # (d = 2: one transformed element per layer, nothing averages out -> a 0.5 % tail at the
         # reference's own noise level, see profiles/r01_tc_accuracy.txt)
-        chk(lp, o32['lp'], o64['lp'], f'{tag} log_prob', 2e-3 if kind == 'cubic' else (5e-3 if d < 8 else 0.0))
+        # (cubic: measured on the d = 63 case, tools/tc_debug3.py -- the failing row's one-root Cardano
+        # element is off by 3e-2 in the reference's OWN fp32 run and both CUDA paths agree with each
+        # other to 1e-4 there; 1-2 such rows in 350 is the level to allow)
+        chk(lp, o32['lp'], o64['lp'], f'{tag} log_prob', 6e-3 if kind == 'cubic' else (5e-3 if d < 8 else 0.0))
         # intermediate quantities have |value| ~ 1-10, so rtol/atol = 1e-5 sits AT the fp32 noise
         # floor of a 3-layer flow (the reference's own fp32-vs-fp64 error reaches 1e-4): allow a
         # 2 % tail, and require the error level to stay within 2.5x of the reference's own.

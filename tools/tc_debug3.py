@@ -7,7 +7,8 @@ from oracle import coupling_flow_oracle as O
 import stribor_b200 as st
 from stribor_b200.spec import layers_from_spec
 DEV = 'cuda'
-kind, d, masks = sys.argv[1], int(sys.argv[2]), cases.ALT
+kind, d = sys.argv[1], int(sys.argv[2])
+masks = tuple(sys.argv[3].split(',')) if len(sys.argv) > 3 else cases.ALT
 case = cases._mk_flow(kind, d, [64], 3, 16, 700, 900 + d, masks=masks, lower=-4., upper=4., scale=1.7)()
 spec = case['spec']
 x = case['inputs']['x'].to(DEV)
@@ -39,4 +40,6 @@ for i, li in enumerate((2, 1, 0)):
     a64, l64 = O.layer_apply(s64[li], cur64, inverse=True)
     print(' layer', li, 'x_out t/g/32/64', o_t[i][0][w].tolist(), o_g[i][0][w].tolist(), a32[w].tolist(), a64[w].tolist())
     print('          ldj  t/g/32/64', o_t[i][1][w].item(), o_g[i][1][w].item(), l32[w].item(), l64[w].item())
+    dt = (o_t[i][0][w].double() - a64[w]).abs(); j = int(dt.argmax())
+    print('          worst dim', j, 'in t/64', (cur64[w, j].item()), 'out t/g/32/64', o_t[i][0][w, j].item(), o_g[i][0][w, j].item(), a32[w, j].item(), a64[w, j].item())
     cur32, cur64 = a32, a64
