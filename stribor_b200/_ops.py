@@ -167,17 +167,89 @@ def _(x, latent, t, mask, params, meta, fmeta, direction):
     return torch.empty_like(x), torch.empty_like(x)
 
 
+G_PAD = 48            # parameters per transformed dim in g_net (47 quadratic, padded)
+H_AUG = 72            # workspace row: hidden(64) | 1 | 0 x 7
+
+
+def fused_backward_ok(L: '_lib.StbLayer') -> bool:
+    """Does stb_layer_backward differentiate this (packed) layer with its conditioner fused?"""
+    return int(_lib.lib().stb_layer_backward_workspace_bytes(C.byref(L), 1)) > 0
+
+
+def _fused_conditioner_backward(x, mask, params, packed, meta, fmeta, direction, g_y, g_ldj):
+    """Coupling(Spline, MLP[64]) on the tensor-core path: ONE kernel recomputes the conditioner from the
+    saved input and differentiates the spline (stb_layer_backward -> tc_wide.cu), leaving
+      g_net [rows, n_tr * 48]  gradient wrt the network output of the transformed dims
+      haug  [rows, 72]         hidden activations | 1 | 0...
+    The conditioner's own gradients are then plain dense products of those two (library GEMMs):
+      [gW2 | gb2] = g_net^T haug,  g_hidden = g_net W2,  g_pre = g_hidden * act'(hidden),
+      gW1 = g_pre^T x_cond,  gb1 = sum g_pre,  g_x[cond] += g_pre W1[:, cond]."""
+    rows, dim = x.shape
+    W1, b1, W2, b2 = params
+    act = meta[8]
+    off = META_HEADER + meta[10] + 1
+    mask_list = meta[off:off + dim]
+    tr = [j for j, m in enumerate(mask_list) if m == 0]
+    cond = [j for j, m in enumerate(mask_list) if m != 0]
+    n_tr, P = len(tr), W2.shape[0] // dim
+    g_x = torch.empty_like(x)
+    gW1, gb1, gW2, gb2 = torch.zeros_like(W1), torch.zeros_like(b1), torch.zeros_like(W2), torch.zeros_like(b2)
+    if rows == 0:
+        g_x.zero_()
+        return [g_x, x.new_empty(0), x.new_empty(0), gW1, gb1, gW2, gb2]
+    L = make_struct(meta, fmeta, mask, params, packed)
+    lib = _lib.lib()
+    if packed is None or int(lib.stb_layer_backward_workspace_bytes(C.byref(L), rows)) != rows * H_AUG * 4:
+        raise NotImplementedError('stribor_b200: this layer has no fused conditioner backward '
+                                  '(quadratic spline, 16 bins, MLP[64], dim <= 128 on the tensor-core path)')
+    g_net = torch.empty(rows, n_tr * G_PAD, dtype=x.dtype, device=x.device)
+    haug = torch.empty(rows, H_AUG, dtype=x.dtype, device=x.device)
+    G = _lib.StbLayerGrads()
+    G.g_row_out = g_net.data_ptr()
+    with torch.cuda.device(x.device):
+        rc = lib.stb_layer_backward(C.byref(L), direction, x.data_ptr(), None, None, g_y.data_ptr(), _dp(g_ldj),
+                                    g_x.data_ptr(), None, None, C.byref(G), haug.data_ptr(), rows, _stream(x))
+    _lib.check(rc)
+    dev = x.device
+    tr_t = torch.tensor(tr, dtype=torch.long, device=dev)
+    cond_t = torch.tensor(cond, dtype=torch.long, device=dev)
+    hid = W2.shape[1]
+    W2p = W2.new_zeros(n_tr, G_PAD, hid)
+    W2p[:, :P] = W2.view(dim, P, hid).index_select(0, tr_t)
+    gaug = (g_net.t() @ haug).view(n_tr, G_PAD, H_AUG)          # [gW2 | gb2 | 0] of the transformed dims' rows
+    gW2.view(dim, P, hid).index_copy_(0, tr_t, gaug[:, :P, :hid].contiguous())
+    gb2.view(dim, P).index_copy_(0, tr_t, gaug[:, :P, hid].contiguous())
+    h = haug[:, :hid]
+    g_h = g_net @ W2p.view(n_tr * G_PAD, hid)
+    if act == _lib.ACTIVATIONS['Tanh']:
+        g_pre = g_h * (1.0 - h * h)
+    elif act == _lib.ACTIVATIONS['Sigmoid']:
+        g_pre = g_h * (h * (1.0 - h))
+    elif act == _lib.ACTIVATIONS['ReLU']:
+        g_pre = g_h * (h > 0).to(g_h.dtype)
+    else:
+        raise NotImplementedError('fused conditioner backward: activation not covered')
+    if cond:
+        xc = x.index_select(1, cond_t)
+        gW1.index_copy_(1, cond_t, g_pre.t() @ xc)
+        g_x.index_add_(1, cond_t, g_pre @ W1.index_select(1, cond_t))
+    gb1 = g_pre.sum(0)
+    return [g_x, x.new_empty(0), x.new_empty(0), gW1, gb1, gW2, gb2]
+
+
 @torch.library.custom_op('stribor_b200::layer_backward', mutates_args=(), device_types='cuda')
 def layer_backward(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mask: Optional[Tensor],
-                   params: List[Tensor], meta: List[int], fmeta: List[float], direction: int,
-                   g_y: Tensor, g_ldj: Optional[Tensor], need_latent: bool, need_t: bool
+                   params: List[Tensor], packed: Optional[Tensor], meta: List[int], fmeta: List[float],
+                   direction: int, g_y: Tensor, g_ldj: Optional[Tensor], need_latent: bool, need_t: bool
                    ) -> List[Tensor]:
     """-> [g_x, g_latent (or empty), g_t (or empty), *g_params]."""
     rows, dim = x.shape
     n_linear, row_mode = meta[10], meta[13]
+    if n_linear > 0 and meta[0] != _lib.CONT_AFFINE:
+        return _fused_conditioner_backward(x, mask, params, packed, meta, fmeta, direction, g_y, g_ldj)
     if n_linear > 0 or meta[0] == _lib.CONT_AFFINE:
         raise NotImplementedError(
-            'stribor_b200: the fused conditioner / continuous-affine backward is not built yet '
+            'stribor_b200: the continuous-affine conditioner backward is not built yet '
             '(training runs the MLP through autograd around the element-wise kernels)')
     g_x = torch.empty_like(x)
     g_latent = x.new_empty(0)
@@ -202,7 +274,7 @@ def layer_backward(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mas
 
 
 @layer_backward.register_fake
-def _(x, latent, t, mask, params, meta, fmeta, direction, g_y, g_ldj, need_latent, need_t):
+def _(x, latent, t, mask, params, packed, meta, fmeta, direction, g_y, g_ldj, need_latent, need_t):
     gl = torch.empty_like(latent) if (need_latent and latent is not None) else x.new_empty(0)
     gt = torch.empty_like(t) if (need_t and t is not None) else x.new_empty(0)
     return [torch.empty_like(x), gl, gt] + [torch.empty_like(p) for p in params]
@@ -212,7 +284,7 @@ def _setup_ctx(ctx, inputs, output):
     x, latent, t, mask, params, packed, meta, fmeta, direction, want_ldj, base_lp = inputs
     if base_lp:
         raise RuntimeError('base_lp is an inference-only fusion')
-    ctx.save_for_backward(x, latent, t, mask, *params)
+    ctx.save_for_backward(x, latent, t, mask, packed, *params)
     ctx.n_params = len(params)
     ctx.meta, ctx.fmeta, ctx.direction, ctx.want_ldj = list(meta), list(fmeta), direction, want_ldj
     ctx.has_latent, ctx.has_t = latent is not None, t is not None
@@ -220,12 +292,12 @@ def _setup_ctx(ctx, inputs, output):
 
 def _backward(ctx, g_y, g_ldj):
     saved = ctx.saved_tensors
-    x, latent, t, mask = saved[:4]
-    params = list(saved[4:])
+    x, latent, t, mask, packed = saved[:5]
+    params = list(saved[5:])
     need = ctx.needs_input_grad
     g_y = g_y.contiguous() if g_y is not None else torch.zeros_like(x)
     gl = g_ldj.contiguous() if (ctx.want_ldj and g_ldj is not None) else None
-    outs = layer_backward(x, latent, t, mask, params, ctx.meta, ctx.fmeta, ctx.direction, g_y, gl,
+    outs = layer_backward(x, latent, t, mask, params, packed, ctx.meta, ctx.fmeta, ctx.direction, g_y, gl,
                           bool(ctx.has_latent and need[1]), bool(ctx.has_t and need[2]))
     g_x, g_latent, g_t = outs[:3]
     g_params = list(outs[3:])

@@ -164,14 +164,29 @@ __global__ void __launch_bounds__(kBThreads) elementwise_backward_kernel(const B
     }
 }
 
-uint64_t layer_backward_workspace_bytes(const stb_layer*, int64_t) { return 0; }
+// n_linear > 0 on the tensor-core path: the workspace receives the conditioner's hidden activations,
+// augmented [rows, 72] = h(64) | 1 | 0 x 7
+uint64_t layer_backward_workspace_bytes(const stb_layer* L, int64_t rows) {
+    if (L->net.n_linear > 0 && tcw_backward_supported(L)) return (uint64_t)(rows > 0 ? rows : 0) * 72 * sizeof(float);
+    return 0;
+}
 
 int layer_backward(const stb_layer* L, int direction, const float* x, const float* latent, const float* t,
                    const float* g_out, const float* g_ldj, float* g_x, float* g_latent, float* g_t,
                    const stb_layer_grads* grads, void* workspace, int64_t rows, cudaStream_t stream) {
-    (void)latent; (void)t; (void)g_latent; (void)g_t; (void)workspace;
-    if (L->net.n_linear > 0)
-        return set_error(STB_ENOTSUP, "fused conditioner backward is not built yet: run the MLP through autograd and pass its output as row_out");
+    (void)latent; (void)t; (void)g_latent; (void)g_t;
+    if (L->net.n_linear > 0) {
+        // conditioner fused: recompute it on the tensor cores, differentiate the spline in registers
+        // (tc_wide.cu).  Outputs: g_x, grads->g_row_out = gradient wrt the network output of the
+        // transformed dims [rows, n_tr * 48], workspace = augmented hidden activations [rows, 72].
+        if (!(L->packed && tcw_backward_supported(L) && tcw_image_present(L)))
+            return set_error(STB_ENOTSUP, "fused conditioner backward needs the tensor-core path (quadratic spline, 16 bins, MLP[64], packed): run the MLP through autograd and pass its output as row_out");
+        if (direction != STB_FORWARD && direction != STB_INVERSE) return set_error(STB_EINVAL, "bad direction");
+        if (rows < 0 || !x || !g_out || !g_x || !grads || !grads->g_row_out || !workspace) return set_error(STB_EINVAL, "bad argument");
+        if (rows == 0) return STB_OK;
+        return tcw_layer_backward(L, tcw_image(L), direction, x, g_out, g_ldj, g_x, grads->g_row_out,
+                                  static_cast<float*>(workspace), rows, stream);
+    }
     if (L->kind == STB_CONT_AFFINE) return set_error(STB_ENOTSUP, "continuous-affine backward is not built yet");
     if (L->has_box) return set_error(STB_ENOTSUP, "backward with separate domain/codomain boxes is not built yet");
     if (direction != STB_FORWARD && direction != STB_INVERSE) return set_error(STB_EINVAL, "bad direction");

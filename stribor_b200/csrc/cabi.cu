@@ -35,6 +35,8 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     if (ldj_mode != STB_LDJ_NONE && !ldj) return set_error(STB_EINVAL, "ldj_mode set but ldj is NULL");
     if (L->packed && !ldiag && tc_layer_supported(L))
         return tc_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s);
+    if (L->packed && !ldiag && tcw_layer_supported(L) && tcw_image_present(L))
+        return tcw_layer_apply(L, tcw_image(L), direction, x, y, ldj, ldj_mode, base_lp, rows, s);
     if (L->packed && !ldiag && tcm_layer_supported(L))
         return tcm_layer_apply(L, direction, x, t, y, ldj, ldj_mode, base_lp, rows, s);
     return generic_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, ldiag, rows, s);
@@ -129,7 +131,8 @@ int stb_layer_backward(const stb_layer* layer, int direction, const float* x, co
 
 uint64_t stb_packed_bytes(const stb_layer* layer) {
     if (validate_layer(layer)) return 0;
-    if (tc_layer_supported(layer)) return tc_packed_bytes(layer);
+    if (tc_layer_supported(layer)) return tc_packed_bytes(layer) + tcw_packed_bytes(layer);   // both images
+    if (tcw_layer_supported(layer)) return tcw_packed_bytes(layer);
     return tcm_layer_supported(layer) ? tcm_packed_bytes(layer) : 0;
 }
 
@@ -137,14 +140,20 @@ int stb_pack_layer(const stb_layer* layer, void* packed_out, void* stream) {
     int rc = validate_layer(layer);
     if (rc) return rc;
     if (!packed_out) return set_error(STB_EINVAL, "packed_out is NULL");
-    if (tc_layer_supported(layer)) return tc_pack_layer(layer, packed_out, (cudaStream_t)stream);
+    if (tc_layer_supported(layer)) {
+        // the 256-row inference kernel's image, then the 128-row / backward kernel's (tc_wide.cu)
+        rc = tc_pack_layer(layer, packed_out, (cudaStream_t)stream);
+        if (rc) return rc;
+        return tcw_pack_layer(layer, static_cast<uint8_t*>(packed_out) + tc_packed_bytes(layer), (cudaStream_t)stream);
+    }
+    if (tcw_layer_supported(layer)) return tcw_pack_layer(layer, packed_out, (cudaStream_t)stream);
     if (tcm_layer_supported(layer)) return tcm_pack_layer(layer, packed_out, (cudaStream_t)stream);
     return set_error(STB_ENOTSUP, "layer has no tensor-core path");
 }
 
 int stb_layer_uses_tensor_path(const stb_layer* layer) {
     if (validate_layer(layer)) return 0;
-    return (layer->packed && (tc_layer_supported(layer) || tcm_layer_supported(layer))) ? 1 : 0;
+    return (layer->packed && (tc_layer_supported(layer) || tcw_layer_supported(layer) || tcm_layer_supported(layer))) ? 1 : 0;
 }
 
 }  // extern "C"

@@ -27,6 +27,24 @@ int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
 int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj,
                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
 
+// tcgen05 path for dim <= 128 and the training backward (tc_wide.cu).  `image` is the wide packed image:
+// it follows the tc_layer.cu image when the layer has both (tcw_image).
+bool tcw_layer_supported(const stb_layer* L);
+bool tcw_backward_supported(const stb_layer* L);
+uint64_t tcw_packed_bytes(const stb_layer* L);
+int tcw_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
+int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const float* x, float* y, float* ldj,
+                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
+int tcw_layer_backward(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
+                       const float* g_ldj, float* g_x, float* g_net, float* hidden, int64_t rows,
+                       cudaStream_t stream);
+inline const void* tcw_image(const stb_layer* L) {
+    return static_cast<const uint8_t*>(L->packed) + (tc_layer_supported(L) ? tc_packed_bytes(L) : 0);
+}
+inline bool tcw_image_present(const stb_layer* L) {
+    return L->packed && L->packed_bytes >= (tc_layer_supported(L) ? tc_packed_bytes(L) : 0) + tcw_packed_bytes(L);
+}
+
 // tcgen05 path for affine couplings with a wide conditioner (tc_mlp.cu)
 bool tcm_layer_supported(const stb_layer* L);
 uint64_t tcm_packed_bytes(const stb_layer* L);

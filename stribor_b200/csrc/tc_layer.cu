@@ -29,15 +29,16 @@
 #include "common.cuh"
 #include "stb_math.cuh"
 #include "tc_common.cuh"
+#include "tc_spline16.cuh"
 
 namespace stb {
 using namespace tc;
 
 namespace tcl {
+using namespace sp16;
 
 constexpr int kHid = 64;             // hidden width
 constexpr int kK1 = 32;              // padded number of conditioning columns (GEMM1 K)
-constexpr int kBins = 16;
 constexpr int kPPad = 48;            // parameters per dim, padded (47 rqs / 34 cubic)
 constexpr int kG = 2;                // transformed dims per weight chunk
 constexpr int kChunkN = kG * kPPad;  // 96 = UMMA N of GEMM2
@@ -49,9 +50,6 @@ constexpr int kXsStride = kMaxDim + 1;
 constexpr int kStages = 3;
 #ifndef STB_TC_EPI_PER_SUB
 #define STB_TC_EPI_PER_SUB 2
-#endif
-#ifndef STB_TC_EXP
-#define STB_TC_EXP 0                   // experiment bits (profiling builds only): 1 no finish, 2 no ex2, 4 no acc_full wait
 #endif
 #if STB_TC_EXP & 64
 #define MBAR_WAIT_SLOW mbar_wait
@@ -151,376 +149,6 @@ struct Args {
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// -----------------------------------------------------------------------------------------------
-// spline evaluation with the 48 parameters of one element in registers
-// -----------------------------------------------------------------------------------------------
-// exp through ex2.approx: with the maximum subtracted the arguments are <= 0, so the absolute
-// error of every term is <= ~2.5 ulp of the LARGEST term (= 1), i.e. the same absolute accuracy on
-// the bin sizes as a 2-ulp expf.  Measured on the GPU against the fp64 oracle
-// (profiles/r01_tc_accuracy.txt): accurate expf, IEEE division and a true e_i / sum quotient change
-// the mean log-det error by < 7 %; only compensated cumulative sums help (12 %) and cost ~90
-// instructions per element.
-__device__ __forceinline__ float ex2_approx(float v) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-
-// tanh to ~3e-7 ABSOLUTE error: (1 - e^-2|v|) / (1 + e^-2|v|).  The result feeds a contraction
-// with O(0.1) weights, where only the absolute error matters (tanhf costs ~3x the instructions).
-__device__ __forceinline__ float tanh_fast(float v);
-
-// a / b to ~1 ulp: MUFU.RCP + one residual correction (4 instructions instead of ~10 for the
-// IEEE sequence; the operands here are never subnormal / huge)
-__device__ __forceinline__ float fdiv(float a, float b) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-    const float q = a * r;
-    return fmaf(fmaf(-q, b, a), r, q);
-}
-// sqrt(x), x >= 0, to ~1 ulp: MUFU.RSQ + one Newton step
-__device__ __forceinline__ float fsqrt(float x) {
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    const float s = x * r;
-    const float h = 0.5f * r;
-    return (x > 0.f) ? fmaf(fmaf(-s, s, x), h, s) : 0.f;
-}
-// F.softplus (beta 1, threshold 20); exp through ex2.approx (relative error ~|v| * 1e-7)
-// softplus(v) = max(v, 0) + log1p(e), e = exp(-|v|) in (0, 1];  log1p(e) = 2 atanh(z), z = e / (2 + e)
-// in (0, 1/3]: odd series to z^13 (relative error < 3e-8 over the range) -- about half the
-// instructions of log1pf(expf(v)), same accuracy class.
-__device__ __forceinline__ float softplus_fast(float v) {
-    const float e = ex2_approx(-1.4426950408889634f * fabsf(v));
-    const float z = fdiv(e, 2.f + e);
-    const float z2 = z * z;
-    float p = fmaf(z2, 1.f / 13.f, 1.f / 11.f);
-    p = fmaf(p, z2, 1.f / 9.f);
-    p = fmaf(p, z2, 1.f / 7.f);
-    p = fmaf(p, z2, 1.f / 5.f);
-    p = fmaf(p, z2, 1.f / 3.f);
-    p = fmaf(p, z2, 1.f);
-    return fmaxf(v, 0.f) + 2.f * z * p;
-}
-
-__device__ __forceinline__ float tanh_fast(float v) {
-    if (STB_TC_EXP & 32) return v * 0.125f;
-    const float t = ex2_approx(-2.885390081777927f * fabsf(v));
-    return copysignf(fdiv(1.f - t, 1.f + t), v);
-}
-
-struct RqsBin16 {
-    float xk, wk, yk, hk, delta, d0, d1;
-};
-
-// log f'(x) for x in bin b: log(delta^2 (d1 th^2 + 2 delta th(1-th) + d0 (1-th)^2) / den^2)
-// (rational_quadratic_spline.py:245-248, the two logs merged into one)
-// Evaluated as ln2 (lg2 dnum - 2 lg2 den) on MUFU.LG2 (absolute error ~2^-22 per term: the same
-// order as one fp32 rounding of a log-derivative of O(1), and 6 instructions instead of ~35 for
-// an IEEE division + logf).
-__device__ __forceinline__ float lg2_approx(float v) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float rqs16_log_deriv(const RqsBin16& b, float theta, float tt, float den) {
-    const float omt = 1.f - theta;
-    const float dnum = b.delta * b.delta * (b.d1 * theta * theta + 2.f * b.delta * tt + b.d0 * omt * omt);
-    return 0.69314718055994530942f * fmaf(-2.f, lg2_approx(den), lg2_approx(dnum));
-}
-
-// ONE deliberate simplification of the coupling semantics: in the inverse direction the forward
-// log-derivative at the recovered point is evaluated in the bin the inverse search found.  The
-// reference re-searches (flow.py:42-47 -> coupling.py:84-95) and can land in the neighbouring bin
-// only when rounding puts the recovered point within an ulp of a knot, where the spline is C1, so
-// the two evaluations agree to O(ulp).
-struct CubSel {
-    float wp, wk, wn, hp, hk, hn, cw, ch;
-    int k;
-};
-
-__device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float ur) {
-    const float sk = s.hk / s.wk;
-    float dl, dr;
-    if (s.k == 0) {
-        dl = sigmoid_f(ul) * 3.f * sk;
-    } else {
-        const float sp = s.hp / s.wp;
-        dl = fminf(fminf(fabsf(sp), fabsf(sk)), 0.5f * (s.wk * sp + s.wp * sk) / (s.wp + s.wk)) *
-             (sign_f(sp) + sign_f(sk));
-    }
-    if (s.k == kBins - 1) {
-        dr = sigmoid_f(ur) * 3.f * sk;
-    } else {
-        const float sn = s.hn / s.wn;
-        dr = fminf(fminf(fabsf(sk), fabsf(sn)), 0.5f * (s.wn * sk + s.wk * sn) / (s.wk + s.wn)) *
-             (sign_f(sk) + sign_f(sn));
-    }
-    CubBin r;
-    r.a = (dl + dr - 2.f * sk) / (s.wk * s.wk);
-    r.b = (3.f * sk - 2.f * dl - dr) / s.wk;
-    r.c = dl;
-    r.d = s.ch;
-    r.xl = s.cw;
-    r.xr = (s.k == kBins - 1) ? 1.f : s.cw + s.wk;
-    return r;
-}
-
-// ---- split-phase variants used by the kernel: the bin is located from the 32 softmax columns
-// first; the remaining parameter columns are pulled from TMEM afterwards ------------------------
-//
-// The 32 softmax columns of a dim arrive INTERLEAVED, (w_i, h_i) in adjacent TMEM columns ==
-// adjacent registers, so everything that treats the two axes alike (bias, shift, sums, cumulative
-// walk, normalisation) runs on Blackwell's packed fp32 pairs (FFMA2 / FADD2): half the issue slots
-// of the scalar form -- the epilogue is issue-bound (profiles/r01_tc_ncu_summary_16warp.txt).
-__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
-
-// in place: t[i] = (2^(w_i - mw), 2^(h_i - mh)).  `shift` is warp-uniform: false when the pack
-// step proved |logit| <= 100 for this dim (bounded activation, row-wise L1 bound on the last
-// Linear), so 2^logit neither overflows nor flushes and the maximum need not be found at all.
-__device__ __forceinline__ void softmax16_num2(float2* t, bool shift) {
-    if (shift) {
-        float mw = t[0].x, mh = t[0].y;
-#pragma unroll
-        for (int i = 1; i < kBins; i += 2) {
-            mw = fmaxf(fmaxf(mw, t[i].x), (i + 1 < kBins) ? t[i + 1].x : t[i].x);
-            mh = fmaxf(fmaxf(mh, t[i].y), (i + 1 < kBins) ? t[i + 1].y : t[i].y);
-        }
-        const float2 nm = f2(-mw, -mh);
-#pragma unroll
-        for (int i = 0; i < kBins; ++i) t[i] = __fadd2_rn(t[i], nm);
-    }
-#pragma unroll
-    for (int i = 0; i < kBins; ++i) {
-        if (STB_TC_EXP & 2) { t[i] = __ffma2_rn(t[i], t[i], f2(1.f)); continue; }
-        t[i].x = ex2_approx(t[i].x); t[i].y = ex2_approx(t[i].y);
-    }
-}
-
-__device__ __forceinline__ float2 sel2(bool p, float2 a, float2 b) { return p ? a : b; }
-
-// Bin search over the softmax numerators e_i = t[i] (pairs: widths, heights) WITHOUT forming the 16
-// cumulative sums.  The bin sizes are w_i = min + c e_i, c = (1 - 16 min) / sum, so knot i sits at
-// lo + span (i min + c E_i) with E_i = e_0 + .. + e_(i-1), and
-//     key >= knot_i   <=>   E_i <= kq - i step        (kq, step: the key and min in units of c)
-// is a prefix property of i (search_sorted.py:3-5: bin = #(key >= knot_i) - 1; the nudged last
-// knot is never reached by an inside key).  The pairwise sum tree that yields the normaliser also
-// yields E_i along a binary descent (E_8 = first half, E_8 +- quarter, ...): 4 compares instead of
-// 15, and the descent leaves E_k of BOTH axes, the numerators of bin k and k itself.  The issue
-// slots go into ~50 selects instead of ~140 walk instructions (the epilogue is issue-bound).
-struct BinSearch16 {
-    float2 S;            // sums of the numerators
-    float2 c;            // (1 - 16 min) / S
-    float2 Ek;           // numerators summed before bin k
-    int k;
-    bool p3, p2, p1, p0; // bits of k
-};
-
-template <bool ON_H>
-__device__ __forceinline__ BinSearch16 bin_search16(const float2* t, float min_size, float key01, float2& e_even,
-                                                    float2& e_odd) {
-    float2 s8[8], s4[4], s2[2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s8[i] = __fadd2_rn(t[2 * i], t[2 * i + 1]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s4[i] = __fadd2_rn(s8[2 * i], s8[2 * i + 1]);
-    s2[0] = __fadd2_rn(s4[0], s4[1]);
-    s2[1] = __fadd2_rn(s4[2], s4[3]);
-    BinSearch16 r;
-    r.S = __fadd2_rn(s2[0], s2[1]);
-    const float scale = 1.f - min_size * (float)kBins;
-    r.c = f2(fdiv(scale, r.S.x), fdiv(scale, r.S.y));
-    const float inv_c = (ON_H ? r.S.y : r.S.x) * (1.f / scale);
-    const float step = min_size * inv_c;
-    float base = key01 * inv_c;                    // threshold of index i: base - (i - position) step
-#define STB_SEARCHED(v) (ON_H ? (v).y : (v).x)
-    r.p3 = STB_SEARCHED(s2[0]) <= fmaf(-8.f, step, base);
-    float2 E = sel2(r.p3, s2[0], f2(0.f));
-    base = r.p3 ? fmaf(-8.f, step, base) : base;
-    float2 cand = __fadd2_rn(E, sel2(r.p3, s4[2], s4[0]));
-    r.p2 = STB_SEARCHED(cand) <= fmaf(-4.f, step, base);
-    E = sel2(r.p2, cand, E);
-    base = r.p2 ? fmaf(-4.f, step, base) : base;
-    cand = __fadd2_rn(E, sel2(r.p3, sel2(r.p2, s8[6], s8[4]), sel2(r.p2, s8[2], s8[0])));
-    r.p1 = STB_SEARCHED(cand) <= fmaf(-2.f, step, base);
-    E = sel2(r.p1, cand, E);
-    base = r.p1 ? fmaf(-2.f, step, base) : base;
-    // numerators of the pair 4 p3 + 2 p2 + p1: selected p3 first (known earliest)
-    float2 a[8], b[4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = sel2(r.p3, t[8 + i], t[i]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) b[i] = sel2(r.p2, a[4 + i], a[i]);
-    e_even = sel2(r.p1, b[2], b[0]);
-    e_odd = sel2(r.p1, b[3], b[1]);
-    cand = __fadd2_rn(E, e_even);
-    r.p0 = STB_SEARCHED(cand) <= base - step;
-    r.Ek = sel2(r.p0, cand, E);
-#undef STB_SEARCHED
-    r.k = (r.p3 ? 8 : 0) + (r.p2 ? 4 : 0) + (r.p1 ? 2 : 0) + (r.p0 ? 1 : 0);
-    return r;
-}
-
-struct RqsLoc {
-    float2 Ek, Ek1;      // (widths, heights): sums of the softmax numerators before bin k / through bin k
-    float2 c;            // (1 - 16 min) / sum, per axis
-    int k;
-};
-
-// t[0..16): log2(e)-scaled raw (width, height) pairs (destroyed).  Leaves E_k and E_(k+1) of both
-// axes: the knots of bin k, from which its width / height are re-derived as the reference does
-// (rational_quadratic_spline.py:180-192).
-template <bool ON_H>
-__device__ __forceinline__ RqsLoc rqs16_locate(float2* t, bool shift, float lo, float inv_span, float key) {
-    softmax16_num2(t, shift);
-    float2 ee, eo;
-    const BinSearch16 bs = bin_search16<ON_H>(t, STB_RQS_MIN, (key - lo) * inv_span, ee, eo);
-    RqsLoc r;
-    r.c = bs.c;
-    r.k = bs.k;
-    r.Ek = bs.Ek;
-    r.Ek1 = __fadd2_rn(bs.Ek, sel2(bs.p0, eo, ee));
-    return r;
-}
-
-// (v[k - 1], v[k]) for k in [0, 16) from a register array v[0..15), out-of-range entries 0: a
-// select tree over a sliding window (19 selects for the pair)
-__device__ __forceinline__ void pick_pair16(const float* v, int k, float& lo_v, float& hi_v) {
-    float a[9], b[5], c[3];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {              // window over V[m] = v[m - 1], V[0] = V[16] = 0
-        const float x0 = (j == 0) ? 0.f : v[j - 1];
-        const float x1 = (j + 8 == 16) ? 0.f : v[j + 7];
-        a[j] = (k & 8) ? x1 : x0;
-    }
-#pragma unroll
-    for (int j = 0; j < 5; ++j) b[j] = (k & 4) ? a[j + 4] : a[j];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) c[j] = (k & 2) ? b[j + 2] : b[j];
-    lo_v = (k & 1) ? c[1] : c[0];
-    hi_v = (k & 1) ? c[2] : c[1];
-}
-
-// softplus_fast on a pair
-__device__ __forceinline__ float2 softplus_fast2(float2 v) {
-    const float2 e = f2(ex2_approx(-1.4426950408889634f * fabsf(v.x)), ex2_approx(-1.4426950408889634f * fabsf(v.y)));
-    const float2 den = __fadd2_rn(e, f2(2.f));
-    float2 r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(den.x));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(den.y));
-    const float2 q = __fmul2_rn(e, r);
-    const float2 nq = f2(-q.x, -q.y);
-    const float2 z = __ffma2_rn(__ffma2_rn(nq, den, e), r, q);
-    const float2 z2 = __fmul2_rn(z, z);
-    float2 p = __ffma2_rn(z2, f2(1.f / 13.f), f2(1.f / 11.f));
-    p = __ffma2_rn(p, z2, f2(1.f / 9.f));
-    p = __ffma2_rn(p, z2, f2(1.f / 7.f));
-    p = __ffma2_rn(p, z2, f2(1.f / 5.f));
-    p = __ffma2_rn(p, z2, f2(1.f / 3.f));
-    p = __ffma2_rn(p, z2, f2(1.f));
-    return __ffma2_rn(__fadd2_rn(z, z), p, f2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)));
-}
-
-// u0 / u1: (bias-added, unscaled) derivative parameters at the two knots of bin r.k
-template <bool INVERSE>
-__device__ __forceinline__ void rqs16_finish(const RqsLoc& r, float u0, float u1, float lo, float hi, bool want_ld,
-                                             float x, float& out, float& ld) {
-    const float span = hi - lo;
-    const float km = (float)r.k * STB_RQS_MIN;
-    float2 k0 = __ffma2_rn(f2(span), __ffma2_rn(r.c, r.Ek, f2(km)), f2(lo));                   // (x_k, y_k)
-    float2 k1 = __ffma2_rn(f2(span), __ffma2_rn(r.c, r.Ek1, f2(km + STB_RQS_MIN)), f2(lo));    // (x_k+1, y_k+1)
-    if (r.k == 0) k0 = f2(lo);                                       // knot_0 / knot_K forced to the box
-    if (r.k == kBins - 1) k1 = f2(hi);
-    const float2 wh = __fadd2_rn(k1, f2(-k0.x, -k0.y));              // sizes re-derived from the knots (:185)
-    const float2 dd = __fadd2_rn(softplus_fast2(f2(u0, u1)), f2(STB_RQS_MIN));
-    RqsBin16 b;
-    b.xk = k0.x; b.yk = k0.y; b.wk = wh.x; b.hk = wh.y;
-    float inv_wk;                                                    // 1 / w_k to ~1 ulp, shared by delta and theta
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_wk) : "f"(b.wk));
-    inv_wk = fmaf(fmaf(-b.wk, inv_wk, 1.f), inv_wk, inv_wk);
-    b.delta = b.hk * inv_wk;
-    b.d0 = dd.x; b.d1 = dd.y;
-    const float s = b.d0 + b.d1 - 2.f * b.delta;
-    if (!INVERSE) {
-        const float theta = (x - b.xk) * inv_wk;
-        const float tt = theta * (1.f - theta);
-        const float den = b.delta + s * tt;
-        out = b.yk + fdiv(b.hk * (b.delta * theta * theta + b.d0 * tt), den);
-        ld = rqs16_log_deriv(b, theta, tt, den);
-    } else {
-        const float dy = x - b.yk;
-        const float qa = dy * s + b.hk * (b.delta - b.d0);
-        const float qb = b.hk * b.d0 - dy * s;
-        const float qc = -b.delta * dy;
-        const float disc = qb * qb - 4.f * qa * qc;
-        const float root = fdiv(2.f * qc, -qb - fsqrt(disc));
-        out = root * b.wk + b.xk;
-        // forward log-derivative at the recovered point: theta = (out - x_k) / w_k is `root` up to the
-        // rounding of `out` (the reference recomputes it from the rounded output, flow.py:42-47)
-        const float tt = root * (1.f - root);
-        ld = (want_ld && out >= lo && out <= hi) ? -rqs16_log_deriv(b, root, tt, b.delta + s * tt) : 0.f;
-    }
-}
-
-// t[0..16): log2(e)-scaled raw (width, height) pairs (destroyed).  cubic_spline.py:104-116,140-151:
-// same search; the three bin sizes around bin k that the slopes need are picked from the
-// numerators by a select tree on the bits of k and normalised afterwards (the cubic code uses the
-// sizes themselves, not knot differences).
-template <bool ON_H>
-__device__ __forceinline__ CubSel cubic16_locate(float2* t, bool shift, float u) {
-    softmax16_num2(t, shift);
-    float2 ee, eo;
-    const BinSearch16 bs = bin_search16<ON_H>(t, STB_CUB_MIN, u, ee, eo);
-    const int k = bs.k;
-    // neighbours: k even -> (t[k-1], ee, eo); k odd -> (ee, eo, t[k+1]).  t[k-1] for even k = odd element
-    // of the previous pair, t[k+1] for odd k = even element of the next pair: one more 8-way select each
-    float2 am[4], bm[2], ap[4], bp[2];
-    // prev-odd element of pair j: t[2j - 1] (j = 0 -> 0), next-even: t[2j + 2] (j = 7 -> 0)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {                  // select on p3 first: candidates j = i (p3 = 0) or j = i + 4
-        am[i] = sel2(bs.p3, t[2 * (i + 4) - 1], (i == 0) ? f2(0.f) : t[2 * i - 1]);
-        ap[i] = sel2(bs.p3, (i + 4 == 7) ? f2(0.f) : t[2 * (i + 4) + 2], t[2 * i + 2]);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {                  // then p2: j = i or i + 2 within the half
-        bm[i] = sel2(bs.p2, am[i + 2], am[i]);
-        bp[i] = sel2(bs.p2, ap[i + 2], ap[i]);
-    }
-    const float2 prev_odd = sel2(bs.p1, bm[1], bm[0]);
-    const float2 next_even = sel2(bs.p1, bp[1], bp[0]);
-    const float2 ep = sel2(bs.p0, ee, prev_odd), ek = sel2(bs.p0, eo, ee), en = sel2(bs.p0, next_even, eo);
-    const float2 mn = f2(STB_CUB_MIN);
-    const float2 sp = __ffma2_rn(bs.c, ep, mn), sk = __ffma2_rn(bs.c, ek, mn), sn = __ffma2_rn(bs.c, en, mn);
-    const float2 cum = __ffma2_rn(bs.c, bs.Ek, f2((float)k * STB_CUB_MIN));
-    CubSel r;
-    r.k = k;
-    r.wp = sp.x; r.hp = sp.y; r.wk = sk.x; r.hk = sk.y; r.wn = sn.x; r.hn = sn.y;
-    r.cw = cum.x; r.ch = cum.y;
-    return r;
-}
-
-template <bool INVERSE>
-__device__ __forceinline__ void cubic16_finish(const CubSel& s, float ul, float ur, float lo, float hi, bool want_ld,
-                                               float u, float& out, float& ld) {
-    const float span = hi - lo;
-    const CubBin b = cubic16_bin(s, ul, ur);
-    if (!INVERSE) {
-        out = cubic_forward_in_bin(b, u, ld) * span + lo;
-    } else {
-        float ld_own;
-        out = cubic_inverse_in_bin(b, u, ld_own) * span + lo;
-        ld = 0.f;
-        if (want_ld && out >= lo && out <= hi) {
-            // forward log-derivative at the recovered point, in the bin the inverse search found
-            // (see the note above RqsBin16's users for why the re-search is skipped)
-            float ldf;
-            (void)cubic_forward_in_bin(b, (out - lo) / span, ldf);
-            ld = -ldf;
-        }
-    }
 }
 
 // -----------------------------------------------------------------------------------------------

@@ -1,0 +1,759 @@
+// Tensor-core coupling layer for dim <= 128 and its training backward (sm_100a, tcgen05 + TMEM).
+//
+// Scope: st.Coupling(st.Spline(dim <= 128, n_bins = 16, 'quadratic' | 'cubic',
+// latent_net = MLP(dim, [64], dim * P)), mask) with <= 64 conditioning and <= 64 transformed dims --
+// BASELINE.json configs[4] (d = 128) -- in three modes:
+//   FWD  y = T(x) or T^-1(x), per-row log|det J|          (flows/coupling.py:69-95, as tc_layer.cu)
+//   BWD  the gradient of that application from its saved input: recomputes the conditioner on the
+//        tensor cores, differentiates the spline element in registers and writes
+//          g_x  [rows, dim]          transformed dims; pass-through dims carry g_out (the conditioner's
+//                                    contribution to them is added by the caller from g_net / hidden)
+//          g_net [rows, n_tr * 48]   gradient wrt the network output of the transformed dims, natural
+//                                    parameter order [w(16) | h(16) | d(15) | 0] per dim
+//          hidden [rows, 72]         the conditioner's hidden activations | 1 | 0 x 7 (augmented so that
+//                                    g_net^T hidden = [gW | gb] of the last Linear in one product)
+//        (what autograd derives for util/rational_quadratic_spline.py + flows/coupling.py)
+//
+// One persistent CTA per SM, 18 warps, tiles of 128 rows:
+//   warp 0      producer: streams the packed first Linear (24 KB) and then the last-Linear chunks
+//               (24 KB = 2 transformed dims x 48 padded parameters x 64, fp16 hi | lo) through one
+//               3-stage cp.async.bulk ring
+//   warp 1      UMMA issuer: GEMM1 [128 x K1] x [K1 x 64] as bf16x3 split products, GEMM2
+//               [128 x 64] x [64 x 96] per chunk as 3 fp16 passes; accumulators in TMEM
+//   warps 2-17  loader + epilogue: the x tile is split on the fly (conditioning columns -> bf16x3 A
+//               operand, transformed columns -> smem), tanh of GEMM1 -> fp16 hi | lo A operand of
+//               GEMM2, then thread = row: 48 parameters of one element out of TMEM, spline (or its
+//               gradient) in registers.
+#include <stdlib.h>
+#include "common.cuh"
+#include "stb_math.cuh"
+#include "tc_common.cuh"
+#include "tc_spline16.cuh"
+
+namespace stb {
+using namespace tc;
+
+namespace tcw {
+using namespace sp16;
+
+constexpr int kHid = 64;
+constexpr int kK1 = 64;              // max conditioning columns (GEMM1 K)
+constexpr int kPPad = 48;
+constexpr int kG = 2;
+constexpr int kChunkN = kG * kPPad;  // 96
+constexpr int kMaxDim = 128;
+constexpr int kMaxTr = 64;
+constexpr int kMaxChunks = kMaxTr / kG;
+constexpr int kTileRows = 128;
+constexpr int kTrStride = kMaxTr + 1;
+constexpr int kStages = 3;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiWarp0 = 2;
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kHAug = 72;            // row of the hidden-activation output: h(64) | 1 | 0 x 7
+
+constexpr uint32_t kMagic = 0x53544257u;
+struct Header {                      // 2048 bytes
+    uint32_t magic;
+    int32_t kind, dim, n_cond, n_tr, n_chunks, P, act, k1pad;
+    float s2;
+    uint32_t maxbits;
+    uint32_t noshift_mask[2];
+    int32_t pad0[3];
+    int32_t cond_idx[kK1];           // conditioning slot -> column
+    int32_t tr_idx[kMaxTr];          // transformed slot -> column
+    int16_t colmap[kMaxDim];         // column -> slot: >= 0 conditioning slot, < 0: -(transformed slot) - 1
+    int32_t pad1[512 - 16 - kK1 - kMaxTr - kMaxDim / 2];
+};
+static_assert(sizeof(Header) == 2048, "header layout");
+constexpr uint32_t kOffB1 = 2048;                                  // float[64]
+constexpr uint32_t kOffB2 = kOffB1 + kHid * 4;                     // float[kMaxChunks * 96]
+constexpr uint32_t kSmallBytes = kOffB2 + kMaxChunks * kChunkN * 4;
+constexpr uint32_t kOffW1 = 16384;                                 // 3 bf16 parts of [64][64], 8 KB each
+constexpr uint32_t kW1Part = kHid * kK1 * 2;
+constexpr uint32_t kChunkBytes = 2 * kChunkN * kHid * 2;           // 24576
+static_assert(3 * kW1Part == kChunkBytes, "the first Linear travels through the chunk ring");
+constexpr uint32_t kOffW2 = kOffW1 + kChunkBytes;
+constexpr uint32_t kPackedBytes = kOffW2 + kMaxChunks * kChunkBytes;
+static_assert(kSmallBytes % 16 == 0 && kSmallBytes <= kOffW1, "small block");
+
+constexpr uint32_t kA1Part = kTileRows * kK1 * 2;                  // 16384
+// shared memory map
+constexpr uint32_t kSmXs = 0;                                      // float [128][65]  transformed columns of x
+constexpr uint32_t kSmGs = kSmXs + kTileRows * kTrStride * 4;      // float [128][65]  same of g_out (BWD)
+constexpr uint32_t kSmA = (kSmGs + kTileRows * kTrStride * 4 + 1023) & ~1023u;   // 48 KB: A1 bf16x3 / h fp16 hi | lo
+constexpr uint32_t kABytes = 3 * kA1Part;
+constexpr uint32_t kSmB = kSmA + kABytes;
+constexpr uint32_t kSmSmall = kSmB + kStages * kChunkBytes;
+constexpr uint32_t kSmBar = (kSmSmall + kSmallBytes + 15) & ~15u;
+constexpr uint32_t kSmLd = kSmBar + 256;                           // float [3][128]
+constexpr uint32_t kSmemBytes = kSmLd + 3 * kTileRows * 4;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+struct Bars {
+    uint64_t setup;
+    uint64_t b_full[kStages], b_empty[kStages];
+    uint64_t a1_ready, acc1_full, h_ready;
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Bars) <= 256, "barrier block");
+
+constexpr uint32_t kColAcc1 = 0;
+constexpr uint32_t kColAcc2 = 128;               // + buf * 96
+constexpr uint32_t kTmemCols = 512;
+
+struct Args {
+    const uint8_t* packed;
+    const float* x;
+    float* y;                 // FWD: output rows; BWD: g_x
+    float* ldj;
+    int ldj_mode;
+    int base_log_prob;
+    float lower, upper;
+    long long rows;
+    int n_tiles;
+    // BWD
+    const float* g_out;
+    const float* g_ldj;
+    float* g_net;
+    float* hidden;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
+template <int KIND, bool INVERSE, bool BWD>
+__global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* xs = reinterpret_cast<float*>(smem + kSmXs);
+    float* gs = reinterpret_cast<float*>(smem + kSmGs);
+    uint8_t* abuf = smem + kSmA;
+    uint8_t* bst = smem + kSmB;
+    const Header* hdr = reinterpret_cast<const Header*>(smem + kSmSmall);
+    const float* b1s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB1);
+    const float* b2s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB2);
+    Bars* bars = reinterpret_cast<Bars*>(smem + kSmBar);
+    float* ld_s = reinterpret_cast<float*>(smem + kSmLd);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        mbar_init(&bars->setup, 1);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+        mbar_init(&bars->a1_ready, kEpiWarps);
+        mbar_init(&bars->acc1_full, 1);
+        mbar_init(&bars->h_ready, kEpiWarps);
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 8); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars->setup, kSmallBytes);
+        bulk_g2s(smem + kSmSmall, A.packed, kSmallBytes, &bars->setup);
+    }
+    mbar_wait(&bars->setup, 0);
+
+    const int d = hdr->dim, n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_chunks = hdr->n_chunks;
+    const int k1pad = hdr->k1pad;
+    const int act = hdr->act;
+    const float s2 = hdr->s2;
+    const float s2l = s2 * 1.4426950408889634f;
+    const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        // ======================= producer =========================================================
+        if (lane == 0) {
+            uint32_t cc = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int c = -1; c < n_chunks; ++c, ++cc) {       // item -1: the packed first Linear
+                    const uint32_t st = cc % kStages, use = cc / kStages;
+                    mbar_wait_relaxed(&bars->b_empty[st], (use & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->b_full[st], kChunkBytes);
+                    const uint8_t* src = (c < 0) ? A.packed + kOffW1 : A.packed + kOffW2 + (size_t)c * kChunkBytes;
+                    bulk_g2s(bst + st * kChunkBytes, src, kChunkBytes, &bars->b_full[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= UMMA issuer ======================================================
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, kHid);
+            const uint32_t idesc2 = make_idesc(FMT_F16, 128, kChunkN);
+            uint32_t cc = 0, cb = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const uint32_t tpar = it & 1;
+                {
+                    const uint32_t st = cc % kStages, use = cc / kStages;
+                    mbar_wait_relaxed(&bars->b_full[st], use & 1);
+                    mbar_wait_relaxed(&bars->a1_ready, tpar);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(abuf), b0 = smem_u32(bst + st * kChunkBytes);
+                    const uint32_t dcol = tmem + kColAcc1;
+                    uint32_t acc = 0;
+                    // x = x0 + x1 + x2, W = W0 + W1 + W2 (bf16 parts): every product except x2*W2, smallest
+                    // first (the tensor core truncates the running accumulator at every step)
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const int pa = (p == 0 || p == 3 || p == 6) ? 1 : ((p == 1 || p == 4) ? 2 : 0);
+                        const int pb = (p == 0 || p == 2) ? 2 : ((p == 1 || p == 3 || p == 5) ? 1 : 0);
+                        for (int ks = 0; ks < k1pad / 16; ++ks) {
+                            umma_f16(dcol, make_smem_desc(a0 + pa * kA1Part + ks * 256, 128, 1024),
+                                     make_smem_desc(b0 + pb * kW1Part + ks * 256, 128, 1024), idesc1, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&bars->acc1_full);
+                    umma_commit(&bars->b_empty[st]);
+                    ++cc;
+                }
+                for (int c = 0; c < n_chunks; ++c, ++cc, ++cb) {
+                    const uint32_t st = cc % kStages, use = cc / kStages;
+                    mbar_wait_relaxed(&bars->b_full[st], use & 1);
+                    const uint32_t buf = cb & 1, buse = cb >> 1;
+                    if (c == 0) mbar_wait_relaxed(&bars->h_ready, tpar);
+                    mbar_wait_relaxed(&bars->acc_empty[buf], (buse & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(abuf), a_lo = a_hi + 16384;
+                    const uint32_t b_hi = smem_u32(bst + st * kChunkBytes), b_lo = b_hi + 12288;
+                    const uint32_t dcol = tmem + kColAcc2 + buf * kChunkN;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {                  // lo*hi, hi*lo, then hi*hi
+                        const uint32_t aa = (p == 0) ? a_lo : a_hi, bb = (p == 1) ? b_lo : b_hi;
+#pragma unroll
+                        for (int ks = 0; ks < kHid / 16; ++ks) {
+                            umma_f16(dcol, make_smem_desc(aa + ks * 256, 128, 1024),
+                                     make_smem_desc(bb + ks * 256, 128, 1024), idesc2, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&bars->acc_full[buf]);
+                    umma_commit(&bars->b_empty[st]);
+                }
+            }
+        }
+    } else {
+        // ======================= loader + epilogue warps ==========================================
+        const int q = warp & 3;                                  // TMEM sub-partition of this warp
+        const int r4 = (warp - kEpiWarp0) >> 2;                  // 0..3 within the sub-partition
+        const int etid = tid - kEpiWarp0 * 32;
+        const int rloc = q * 32 + lane;                          // row within the tile == TMEM lane
+        const uint32_t a_row_off = (uint32_t)(rloc >> 3) * 1024 + (uint32_t)(rloc & 7) * 16;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
+        const float lo = A.lower, hi = A.upper;
+        const float inv_span = 1.f / (hi - lo);
+        uint32_t cb = 0;
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long row0 = tile * kTileRows;
+            const int nrows = (int)min((long long)kTileRows, A.rows - row0);
+            const uint32_t tpar = it & 1;
+
+            // ---- load the tile: conditioning columns -> bf16x3 A operand, transformed columns -> smem,
+            // pass-through columns of the output copied through registers ------------------------------
+            {
+                const float* xg = A.x + row0 * d;
+                const float* gg = BWD ? A.g_out + row0 * d : nullptr;
+                float* og = A.y + row0 * d;
+                const bool copy_pass = BWD ? (static_cast<const float*>(A.y) != A.g_out)
+                                           : (static_cast<const float*>(A.y) != A.x);
+                const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0) &&
+                                 (!BWD || (reinterpret_cast<uintptr_t>(gg) & 15) == 0) &&
+                                 ((reinterpret_cast<uintptr_t>(og) & 15) == 0);
+                if (vec) {
+                    const int d4 = d >> 2, n4 = kTileRows * d4;
+                    for (int i = etid; i < n4; i += kEpiThreads) {
+                        const int r = i / d4, c = (i - r * d4) << 2;
+                        const bool live = r < nrows;
+                        float4 v = live ? __ldg(reinterpret_cast<const float4*>(xg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (BWD && live) gv = __ldg(reinterpret_cast<const float4*>(gg) + i);
+                        const int m0 = hdr->colmap[c], m1 = hdr->colmap[c + 1], m2 = hdr->colmap[c + 2], m3 = hdr->colmap[c + 3];
+                        if (m0 >= 0 && (m0 & 3) == 0 && m1 == m0 + 1 && m2 == m0 + 2 && m3 == m0 + 3) {
+                            // four consecutive conditioning slots: 8-byte stores into the core-matrix layout
+                            __align__(8) __nv_bfloat16 q0[4], q1[4], q2[4];
+                            split_bf16x3(v.x, q0[0], q1[0], q2[0]); split_bf16x3(v.y, q0[1], q1[1], q2[1]);
+                            split_bf16x3(v.z, q0[2], q1[2], q2[2]); split_bf16x3(v.w, q0[3], q1[3], q2[3]);
+                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m0 >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m0 & 7) * 2;
+                            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(q0);
+                            *reinterpret_cast<uint2*>(dst + kA1Part) = *reinterpret_cast<const uint2*>(q1);
+                            *reinterpret_cast<uint2*>(dst + 2 * kA1Part) = *reinterpret_cast<const uint2*>(q2);
+                            if (copy_pass && live) reinterpret_cast<float4*>(og)[i] = BWD ? gv : v;
+                        } else {
+                            const float vv[4] = {v.x, v.y, v.z, v.w};
+                            const float gvv[4] = {gv.x, gv.y, gv.z, gv.w};
+                            const int mm[4] = {m0, m1, m2, m3};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (mm[u] >= 0) {
+                                    __nv_bfloat16 p0, p1, p2;
+                                    split_bf16x3(vv[u], p0, p1, p2);
+                                    uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(mm[u] >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(mm[u] & 7) * 2;
+                                    *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
+                                    *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
+                                    *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                                    if (copy_pass && live) og[(size_t)r * d + c + u] = BWD ? gvv[u] : vv[u];
+                                } else {
+                                    const int sl = -mm[u] - 1;
+                                    xs[r * kTrStride + sl] = vv[u];
+                                    if (BWD) gs[r * kTrStride + sl] = gvv[u];
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    const int n = kTileRows * d;
+                    for (int i = etid; i < n; i += kEpiThreads) {
+                        const int r = i / d, c = i - r * d;
+                        const bool live = r < nrows;
+                        const float v = live ? __ldg(xg + i) : 0.f;
+                        const float gv = (BWD && live) ? __ldg(gg + i) : 0.f;
+                        const int m = hdr->colmap[c];
+                        if (m >= 0) {
+                            __nv_bfloat16 p0, p1, p2;
+                            split_bf16x3(v, p0, p1, p2);
+                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
+                            *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
+                            *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
+                            *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                            if (copy_pass && live) og[i] = BWD ? gv : v;
+                        } else {
+                            xs[r * kTrStride - m - 1] = v;
+                            if (BWD) gs[r * kTrStride - m - 1] = gv;
+                        }
+                    }
+                }
+                // zero the padded conditioning slots [n_cond, k1pad) (the buffer is reused for h every tile)
+                const int npad = k1pad - n_cond;
+                for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
+                    const int r = i / npad, m = n_cond + (i - r * npad);
+                    uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
+                    *reinterpret_cast<uint16_t*>(dst) = 0;
+                    *reinterpret_cast<uint16_t*>(dst + kA1Part) = 0;
+                    *reinterpret_cast<uint16_t*>(dst + 2 * kA1Part) = 0;
+                }
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiThreads);
+            if (lane == 0) mbar_arrive(&bars->a1_ready);
+
+            // ---- hidden layer: h = act(acc1 + b1) -> fp16 hi | lo A operand of GEMM2 --------------------
+            mbar_wait(&bars->acc1_full, tpar);
+            tc_fence_after();
+#pragma unroll 1
+            for (int kc = r4; kc < kHid / 8; kc += 4) {
+                const int c0 = kc * 8;
+                float v[8];
+                tmem_ld8(tmem + lane_sel + kColAcc1 + c0, v);
+                tmem_ld_wait();
+                __align__(16) __half hh[8], hl[8];
+                if (act == STB_ACT_TANH) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] + b1s[c0 + i]);
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 8; ++i) v[i] = activate(act, v[i] + b1s[c0 + i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split_f16(v[i], hh[i], hl[i]);
+                *reinterpret_cast<uint4*>(abuf + a_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hh);
+                *reinterpret_cast<uint4*>(abuf + 16384 + a_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hl);
+                if (BWD && rloc < nrows) stg256(A.hidden + (size_t)(row0 + rloc) * kHAug + c0, v);
+            }
+            if (BWD && r4 == 0 && rloc < nrows) {                // augmentation: g_net^T [h | 1] = [gW | gb]
+                const float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                stg256(A.hidden + (size_t)(row0 + rloc) * kHAug + kHid, one);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->h_ready);
+
+            // ---- chunks out of TMEM: this warp's dim of every second chunk ---------------------------------
+            float ld_acc = 0.f;
+            float g_ld = 0.f;
+            if (BWD && A.g_ldj != nullptr && rloc < nrows) g_ld = __ldg(A.g_ldj + row0 + rloc);
+            float* xrow = xs + rloc * kTrStride;
+            float* grow = gs + rloc * kTrStride;
+#pragma unroll 1
+            for (int ji = r4; ji < kG * n_chunks; ji += 4) {
+                const uint32_t ccc = cb + (uint32_t)(ji >> 1);
+                const uint32_t buf = ccc & 1, buse = ccc >> 1;
+                const int g = ji & 1;
+                const bool live_dim = ji < n_tr;
+                const float xv = live_dim ? xrow[ji] : 0.f;
+                const bool inside = live_dim && (xv >= lo) && (xv <= hi);
+                const float* bb = b2s + ji * kPPad;
+                const float2* bb2 = reinterpret_cast<const float2*>(bb);
+                mbar_wait(&bars->acc_full[buf], buse & 1);
+                tc_fence_after();
+                const uint32_t col0 = tmem + lane_sel + kColAcc2 + buf * kChunkN + (uint32_t)g * kPPad;
+                const bool shift = !((hdr->noshift_mask[ji >> 5] >> (ji & 31)) & 1u);
+                float out = xv, ld = 0.f;
+                if (KIND == STB_RQS) {
+                    float2 t[kBins];
+                    tmem_ld16(col0, reinterpret_cast<float*>(t));
+                    tmem_ld16(col0 + 16, reinterpret_cast<float*>(t) + 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
+                    if (!BWD) {
+                        const RqsLoc loc = rqs16_locate<INVERSE>(t, shift, lo, inv_span, xv);
+                        float dd[16];
+                        tmem_ld16(col0 + 2 * kBins, dd);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                        if (inside) {
+                            float r0, r1;
+                            pick_pair16(dd, loc.k, r0, r1);
+                            const float u0 = (loc.k == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + loc.k - 1]);
+                            const float u1 = (loc.k == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
+                            rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
+                        }
+                    } else {
+                        softmax16_num2(t, shift);
+                        float2 ee, eo;
+                        const BinSearch16 bs = bin_search16<INVERSE>(t, STB_RQS_MIN, (xv - lo) * inv_span, ee, eo);
+                        float dd[16];
+                        tmem_ld16(col0 + 2 * kBins, dd);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                        float r0, r1;
+                        pick_pair16(dd, bs.k, r0, r1);
+                        const int kk = bs.k;
+                        const float u0 = (kk == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + (kk > 0 ? kk - 1 : 0)]);
+                        const float u1 = (kk == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + (kk < kBins - 1 ? kk : 0)]);
+                        const float go = live_dim ? grow[ji] : 0.f;
+                        float gx = go, gu0 = 0.f, gu1 = 0.f;
+                        if (inside) {
+                            rqs16_backward<INVERSE>(t, bs, ee, eo, u0, u1, lo, hi, xv, go, g_ld, gx, gu0, gu1);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < kBins; ++i) t[i] = f2(0.f);
+                        }
+                        out = gx;
+                        if (live_dim && rloc < nrows) {
+                            float* gp = A.g_net + ((size_t)(row0 + rloc) * n_tr + ji) * kPPad;
+                            float w[8];
+#pragma unroll
+                            for (int b8 = 0; b8 < 2; ++b8) {               // widths, then heights
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) w[i] = t[b8 * 8 + i].x;
+                                stg256(gp + b8 * 8, w);
+                            }
+#pragma unroll
+                            for (int b8 = 0; b8 < 2; ++b8) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) w[i] = t[b8 * 8 + i].y;
+                                stg256(gp + kBins + b8 * 8, w);
+                            }
+#pragma unroll
+                            for (int b8 = 0; b8 < 2; ++b8) {               // derivative i sits at knot i + 1
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int di = b8 * 8 + i;
+                                    w[i] = (di == kk - 1) ? gu0 : ((di == kk) ? gu1 : 0.f);
+                                    if (di == kBins - 1) w[i] = 0.f;       // padding column
+                                }
+                                stg256(gp + 2 * kBins + b8 * 8, w);
+                            }
+                        }
+                    }
+                } else {
+                    const float span = hi - lo;
+                    const float u = (xv - lo) / span;
+                    float2 t[kBins];
+                    tmem_ld16(col0, reinterpret_cast<float*>(t));
+                    tmem_ld16(col0 + 16, reinterpret_cast<float*>(t) + 16);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
+                    const CubSel sel = cubic16_locate<INVERSE>(t, shift, u);
+                    float dd[8];
+                    tmem_ld8(col0 + 2 * kBins, dd);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                    if (inside) {
+                        const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
+                        cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);
+                    }
+                }
+                if (live_dim) {
+                    if (BWD) grow[ji] = out; else xrow[ji] = out;
+                }
+                ld_acc += ld;
+            }
+            cb += (uint32_t)n_chunks;
+
+            // ---- per-row log|det J| (+ UnitNormal log-density of the output row) ---------------------------
+            if (!BWD && r4 < 3) ld_s[r4 * kTileRows + rloc] = ld_acc;
+            named_bar_sync(1, kEpiThreads);
+            if (!BWD && r4 == 3 && want_ld && rloc < nrows) {           // fixed summation order: deterministic
+                float tot = ld_s[rloc] + ld_s[kTileRows + rloc] + ld_s[2 * kTileRows + rloc] + ld_acc;
+                if (A.base_log_prob) {
+                    const float* xr = A.x + (row0 + rloc) * d;            // pass-through columns: unchanged by this layer
+                    float b = 0.f;
+                    for (int c = 0; c < d; ++c) {
+                        const int m = hdr->colmap[c];
+                        const float v = (m >= 0) ? __ldg(xr + c) : xrow[-m - 1];
+                        b += -0.5f * v * v - 0.91893853320467274178f;
+                    }
+                    tot += b;
+                }
+                float* dst = A.ldj + row0 + rloc;
+                *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
+            }
+            // ---- transformed columns out ---------------------------------------------------------------------
+            {
+                float* og = A.y + row0 * d;
+                const float* src = BWD ? gs : xs;
+                for (int i = etid; i < nrows * n_tr; i += kEpiThreads) {
+                    const int r = i / n_tr, sl = i - r * n_tr;
+                    og[(size_t)r * d + hdr->tr_idx[sl]] = src[r * kTrStride + sl];
+                }
+            }
+            named_bar_sync(1, kEpiThreads);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+// -----------------------------------------------------------------------------------------------
+// packing
+// -----------------------------------------------------------------------------------------------
+struct PackArgs {
+    const float *W1, *b1, *W2, *b2;
+    uint8_t* out;
+    int kind, dim, n_cond, n_tr, n_chunks, P, act;
+    int16_t colmap[kMaxDim];
+    uint8_t cond_idx[kK1];
+    uint8_t tr_idx[kMaxTr];
+};
+
+__global__ void tcw_maxabs_kernel(const PackArgs a) {
+    float m = 0.f;
+    const int total = a.n_tr * a.P * kHid;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i % kHid, rp = i / kHid, p = rp % a.P, ji = rp / a.P;
+        m = fmaxf(m, fabsf(a.W2[((size_t)a.tr_idx[ji] * a.P + p) * kHid + k]));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&reinterpret_cast<Header*>(a.out)->maxbits, __float_as_uint(m));
+}
+
+__host__ __device__ __forceinline__ int param_of_col(int c) {
+    return (c < 2 * kBins) ? ((c & 1) ? kBins + (c >> 1) : (c >> 1)) : c;
+}
+__device__ __forceinline__ uint32_t core_off(int r, int k, int K, int elem) {
+    const int epc = 16 / elem, chunks = K / epc;
+    return (uint32_t)((r >> 3) * (chunks * 128) + (k / epc) * 128 + (r & 7) * 16 + (k % epc) * elem);
+}
+
+__global__ void tcw_pack_kernel(const PackArgs a) {
+    Header* hdr = reinterpret_cast<Header*>(a.out);
+    const float mx = __uint_as_float(hdr->maxbits);
+    float s2 = 1.f;
+    if (mx > 0.f && isfinite(mx)) {
+        int ex;
+        const float fr = frexpf(mx, &ex);
+        s2 = ldexpf(1.f, (fr == 0.5f) ? ex - 1 : ex);
+    }
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    if (gtid == 0) {
+        hdr->magic = kMagic; hdr->kind = a.kind; hdr->dim = a.dim; hdr->n_cond = a.n_cond; hdr->n_tr = a.n_tr;
+        hdr->n_chunks = a.n_chunks; hdr->P = a.P; hdr->act = a.act; hdr->s2 = s2;
+        hdr->k1pad = (a.n_cond + 15) & ~15;
+        if (hdr->k1pad == 0) hdr->k1pad = 16;
+        for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
+        for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
+        for (int i = 0; i < kMaxDim; ++i) hdr->colmap[i] = a.colmap[i];
+    }
+    float* b1 = reinterpret_cast<float*>(a.out + kOffB1);
+    float* b2 = reinterpret_cast<float*>(a.out + kOffB2);
+    for (int i = gtid; i < kHid; i += gsz) b1[i] = a.b1[i];
+    for (int i = gtid; i < kMaxChunks * kChunkN; i += gsz) {
+        const int ji = i / kPPad, col = i % kPPad, p = param_of_col(col);
+        const float bv = (ji < a.n_tr && p < a.P) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
+        b2[i] = (col < 2 * kBins) ? bv * 1.4426950408889634f : bv;
+    }
+    for (int i = gtid; i < kHid * kK1; i += gsz) {
+        const int n = i / kK1, k = i % kK1;
+        const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.dim + a.cond_idx[k]] : 0.f;
+        __nv_bfloat16 q0, q1, q2;
+        split_bf16x3(v, q0, q1, q2);
+        const uint32_t off = kOffW1 + core_off(n, k, kK1, 2);
+        *reinterpret_cast<__nv_bfloat16*>(a.out + off) = q0;
+        *reinterpret_cast<__nv_bfloat16*>(a.out + off + kW1Part) = q1;
+        *reinterpret_cast<__nv_bfloat16*>(a.out + off + 2 * kW1Part) = q2;
+    }
+    const float inv = 1.f / s2;
+    for (int i = gtid; i < kMaxChunks * kChunkN * kHid; i += gsz) {
+        const int k = i % kHid, rn = i / kHid, n = rn % kChunkN, c = rn / kChunkN;
+        const int ji = c * kG + n / kPPad, p = param_of_col(n % kPPad);
+        float v = 0.f;
+        if (c < a.n_chunks && ji < a.n_tr && p < a.P) v = a.W2[((size_t)a.tr_idx[ji] * a.P + p) * kHid + k] * inv;
+        __half hi, lo;
+        split_f16(v, hi, lo);
+        const uint32_t off = kOffW2 + (uint32_t)c * kChunkBytes + core_off(n, k, kHid, 2);
+        *reinterpret_cast<__half*>(a.out + off) = hi;
+        *reinterpret_cast<__half*>(a.out + off + 12288) = lo;
+    }
+}
+
+__global__ void tcw_bound_kernel(const PackArgs a) {
+    const int ji = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), p = threadIdx.x & 31;
+    bool ok = false;
+    if (ji < a.n_tr && (a.act == STB_ACT_TANH || a.act == STB_ACT_SIGMOID)) {
+        const size_t row = (size_t)a.tr_idx[ji] * a.P + p;
+        float l1 = fabsf(a.b2[row]);
+        for (int k = 0; k < kHid; ++k) l1 += fabsf(a.W2[row * kHid + k]);
+        ok = (l1 * 1.4426950408889634f <= 100.f);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (p == 0 && ok && ji < kMaxTr) atomicOr(&reinterpret_cast<Header*>(a.out)->noshift_mask[ji >> 5], 1u << (ji & 31));
+}
+
+static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
+    if (!L->mask_host) return false;
+    a.n_cond = a.n_tr = 0;
+    for (int j = 0; j < L->dim; ++j) {
+        if (L->mask_host[j]) {
+            if (a.n_cond >= kK1) return false;
+            a.colmap[j] = (int16_t)a.n_cond;
+            a.cond_idx[a.n_cond++] = (uint8_t)j;
+        } else {
+            if (a.n_tr >= kMaxTr) return false;
+            a.colmap[j] = (int16_t)(-a.n_tr - 1);
+            a.tr_idx[a.n_tr++] = (uint8_t)j;
+        }
+    }
+    for (int j = L->dim; j < kMaxDim; ++j) a.colmap[j] = 0;
+    for (int i = a.n_cond; i < kK1; ++i) a.cond_idx[i] = 0;
+    for (int i = a.n_tr; i < kMaxTr; ++i) a.tr_idx[i] = 0;
+    if (a.n_tr < 1) return false;
+    a.n_chunks = (a.n_tr + kG - 1) / kG;
+    a.kind = L->kind; a.dim = L->dim; a.P = L->kind == STB_RQS ? 3 * kBins - 1 : 2 * kBins + 2;
+    a.act = L->net.activation;
+    a.W1 = L->net.W[0]; a.b1 = L->net.b[0]; a.W2 = L->net.W[1]; a.b2 = L->net.b[1];
+    return true;
+}
+
+}  // namespace tcw
+
+bool tcw_layer_supported(const stb_layer* L) {
+    using namespace tcw;
+    if (L->kind != STB_RQS && L->kind != STB_CUBIC) return false;
+    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim != 0 || L->time_input) return false;
+    if (L->has_box || L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
+    const stb_mlp& N = L->net;
+    if (N.n_linear != 2 || N.dims[1] != kHid || N.final_activation != STB_ACT_NONE) return false;
+    PackArgs a;
+    return fill_pack_args(L, a);
+}
+
+uint64_t tcw_packed_bytes(const stb_layer*) { return tcw::kPackedBytes; }
+
+int tcw_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
+    using namespace tcw;
+    PackArgs a;
+    if (!fill_pack_args(L, a)) return set_error(STB_ENOTSUP, "layer has no wide tensor-core path");
+    a.out = static_cast<uint8_t*>(out);
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(Header), stream);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "memset: %s", cudaGetErrorString(e));
+    tcw_maxabs_kernel<<<64, 256, 0, stream>>>(a);
+    count_launch();
+    tcw_pack_kernel<<<296, 256, 0, stream>>>(a);
+    count_launch();
+    tcw_bound_kernel<<<(kMaxTr + 7) / 8, 256, 0, stream>>>(a);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tcw_pack launch: %s", cudaGetErrorString(e));
+    return STB_OK;
+}
+
+static int tcw_launch(void (*kern)(tcw::Args), const tcw::Args& A, long long tiles, cudaStream_t stream, const char* what) {
+    using namespace tcw;
+    static thread_local int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int grid = (int)min((long long)n_sm, tiles);
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(A);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "%s launch: %s", what, cudaGetErrorString(e));
+    return STB_OK;
+}
+
+int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const float* x, float* y, float* ldj,
+                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream) {
+    using namespace tcw;
+    Args A = {};
+    A.packed = static_cast<const uint8_t*>(image);
+    A.x = x; A.y = y; A.ldj = ldj;
+    A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
+    A.base_log_prob = base_log_prob;
+    A.lower = L->lower; A.upper = L->upper;
+    A.rows = rows;
+    const long long tiles = (rows + kTileRows - 1) / kTileRows;
+    if (tiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
+    A.n_tiles = (int)tiles;
+    const bool inv = direction == STB_INVERSE;
+    void (*kern)(Args);
+    if (L->kind == STB_RQS) kern = inv ? tc_wide_kernel<STB_RQS, true, false> : tc_wide_kernel<STB_RQS, false, false>;
+    else kern = inv ? tc_wide_kernel<STB_CUBIC, true, false> : tc_wide_kernel<STB_CUBIC, false, false>;
+    return tcw_launch(kern, A, tiles, stream, "tc_wide_kernel");
+}
+
+bool tcw_backward_supported(const stb_layer* L) { return tcw_layer_supported(L) && L->kind == STB_RQS; }
+
+int tcw_layer_backward(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
+                       const float* g_ldj, float* g_x, float* g_net, float* hidden, int64_t rows,
+                       cudaStream_t stream) {
+    using namespace tcw;
+    if (L->kind != STB_RQS) return set_error(STB_ENOTSUP, "tensor-core backward is built for the quadratic spline");
+    Args A = {};
+    A.packed = static_cast<const uint8_t*>(image);
+    A.x = x; A.y = g_x; A.ldj = nullptr;
+    A.ldj_mode = STB_LDJ_NONE;
+    A.lower = L->lower; A.upper = L->upper;
+    A.rows = rows;
+    A.g_out = g_out; A.g_ldj = g_ldj; A.g_net = g_net; A.hidden = hidden;
+    const long long tiles = (rows + kTileRows - 1) / kTileRows;
+    if (tiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
+    A.n_tiles = (int)tiles;
+    void (*kern)(Args) = (direction == STB_INVERSE) ? tc_wide_kernel<STB_RQS, true, true> : tc_wide_kernel<STB_RQS, false, true>;
+    return tcw_launch(kern, A, tiles, stream, "tc_wide_kernel (backward)");
+}
+
+}  // namespace stb

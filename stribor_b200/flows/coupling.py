@@ -15,7 +15,9 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from .. import _lib
+import os
+
+from .. import _lib, _ops
 from ..flow import Transform, run_layer
 from ..net.time_net import TimeLinear
 from ..util.mask import get_mask
@@ -95,11 +97,31 @@ class Coupling(Transform):
             return self._run_set(x, latent, direction, want_ldj)
         lat = latent if self.transform.latent_net is not None else None
         net = self.transform.latent_net
-        if net is not None and (needs_autograd(self, x, lat) or not fusable(net)):
-            # gradients wanted, or a conditioner the kernels do not fuse (any nn.Module works here)
+        if net is not None and not fusable(net):
+            # a conditioner the kernels do not fuse (any nn.Module works here)
             return self._run_autograd(x, lat, direction, want_ldj)
+        if net is not None and needs_autograd(self, x, lat):
+            d = self._fused_training_desc(x, lat)
+            if d is None:      # conditioner through autograd around the element-wise kernels
+                return self._run_autograd(x, lat, direction, want_ldj)
+            return run_layer(d, x, lat, None, direction, want_ldj)
         d = self.describe(x.shape[-1], 0 if lat is None else lat.shape[-1], x.device)
         return run_layer(d, x, lat, None, direction, want_ldj)
+
+    def _fused_training_desc(self, x, lat):
+        """The layer description when ``stb_layer_backward`` differentiates this layer with its conditioner
+        fused (tensor-core path: quadratic spline, 16 bins, MLP[64], dim <= 128), else None."""
+        if lat is not None or os.environ.get('STRIBOR_B200_TRAIN_HYBRID') == '1':
+            return None
+        d = self.describe(x.shape[-1], 0, x.device)
+        if d['packed'] is None:
+            return None
+        key = ('fused_bwd', x.shape[-1], str(x.device), tuple(d['meta']))
+        if key not in self._masks:
+            L = _ops.make_struct(d['meta'], d['fmeta'], d['mask'], [p.detach() for p in d['params']], d['packed'])
+            act_ok = d['meta'][8] in (_lib.ACTIVATIONS['Tanh'], _lib.ACTIVATIONS['Sigmoid'], _lib.ACTIVATIONS['ReLU'])
+            self._masks[key] = bool(act_ok and _ops.fused_backward_ok(L))
+        return d if self._masks[key] else None
 
     def _run_autograd(self, x, latent, direction, want_ldj):
         """Training path: the conditioner MLP runs through autograd (cuBLAS GEMMs, only the

@@ -122,3 +122,104 @@ def test_continuous_affine_coupling_gradients_match_oracle():
     assert len(got) == len(leaves)
     for g, l in zip(got, leaves):
         torch.testing.assert_close(g.cpu().double().view(-1), l.grad.view(-1), rtol=1e-4, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------------
+# fused conditioner backward (tc_wide.cu): the training step's gradient kernel
+# ----------------------------------------------------------------------------------------------
+def _nll_grads(spec, x, monkeypatch, hybrid):
+    if hybrid:
+        monkeypatch.setenv('STRIBOR_B200_TRAIN_HYBRID', '1')
+    else:
+        monkeypatch.delenv('STRIBOR_B200_TRAIN_HYBRID', raising=False)
+    layers = [l.to(DEV) for l in layers_from_spec(spec)]
+    flow = st.NormalizingFlow(st.UnitNormal(x.shape[-1]), layers)
+    xg = x.to(DEV).clone().requires_grad_(True)
+    fused = layers[0]._fused_training_desc(xg, None) is not None
+    assert fused == (not hybrid), 'fused conditioner backward was not selected' if not hybrid else 'hybrid override ignored'
+    n0 = st._ops.launch_count()
+    lp = flow.log_prob(xg)
+    loss = -lp.mean()
+    loss.backward()
+    return loss.item(), xg.grad.cpu(), [p.grad.cpu() for p in flow.parameters()], st._ops.launch_count() - n0
+
+
+@pytest.mark.parametrize('d,masks,rows', [(128, cases.ALT, 300), (64, cases.ALT, 257),
+                                          (100, ('parity_even', 'parity_odd'), 129),
+                                          (65, ('ordered_left_half', 'parity_odd'), 64)])
+def test_fused_conditioner_backward_matches_hybrid_and_oracle(d, masks, rows, monkeypatch):
+    """NLL gradients through stb_layer_backward with the conditioner fused (tensor-core recompute +
+    register-level spline gradient) vs (a) the hybrid path (autograd MLP around the element-wise
+    backward kernel) and (b) autograd through the fp64 oracle."""
+    case = cases._mk_flow('quadratic', d, [64], 2, 16, rows, 4100 + d, masks=masks, lower=-4., upper=4., scale=1.5)()
+    spec, x = case['spec'], case['inputs']['x']
+    x[1, 0] = 5.0                                            # identity-tail elements
+    x[2, d - 1] = -4.5
+    loss_f, gx_f, gp_f, n_f = _nll_grads(spec, x, monkeypatch, hybrid=False)
+    loss_h, gx_h, gp_h, n_h = _nll_grads(spec, x, monkeypatch, hybrid=True)
+    assert n_f >= 2 * len(spec), f'fused path launched {n_f} library kernels (expected forward + backward per layer)'
+    # fp64 oracle autograd
+    s64 = O.spec_to(spec, torch.float64)
+    leaves = []
+    for layer in s64:
+        net = layer['transform']['net']
+        for w, b in zip(net['weights'], net['biases']):
+            leaves += [w.requires_grad_(True), b.requires_grad_(True)]
+    x64 = x.double().clone().requires_grad_(True)
+    loss64 = -O.flow_log_prob(s64, x64).mean()
+    loss64.backward()
+    assert abs(loss_f - loss64.item()) < 1e-5 * abs(loss64.item()) + 1e-5
+    assert abs(loss_f - loss_h) < 1e-5 * abs(loss_h) + 1e-5
+
+    def close(got, want, what):
+        want = want.double()
+        scale = want.abs().max().clamp_min(1e-12)
+        err = (got.double() - want).abs()
+        bad = err > 1e-3 * want.abs() + 2e-5 * scale
+        assert bad.float().mean().item() <= 2e-3, f'{what}: {bad.float().mean().item():.3%} outside tolerance, max err {err.max().item():.3e} (scale {scale.item():.3e})'
+
+    close(gx_f, x64.grad, 'grad_x vs oracle64')
+    close(gx_f, gx_h, 'grad_x vs hybrid')
+    assert len(gp_f) == len(leaves) == len(gp_h)
+    for i, (g, l, h) in enumerate(zip(gp_f, leaves, gp_h)):
+        close(g, l.grad, f'grad of parameter {i} vs oracle64')
+        close(g, h, f'grad of parameter {i} vs hybrid')
+
+
+def test_fused_backward_forward_direction_and_output_gradient(monkeypatch):
+    """Forward direction (sampling-style objective): both outputs of the layer carry a gradient."""
+    d = 128
+    case = cases._mk_flow('quadratic', d, [64], 1, 16, 200, 5200, masks=cases.ALT, lower=-4., upper=4., scale=1.5)()
+    spec, x = case['spec'], case['inputs']['x']
+    res = {}
+    for hybrid in (False, True):
+        if hybrid:
+            monkeypatch.setenv('STRIBOR_B200_TRAIN_HYBRID', '1')
+        else:
+            monkeypatch.delenv('STRIBOR_B200_TRAIN_HYBRID', raising=False)
+        layer = layers_from_spec(spec)[0].to(DEV)
+        xg = x.to(DEV).clone().requires_grad_(True)
+        y, ldj = layer.forward_and_log_det_jacobian(xg)
+        (y.sin().sum() + (ldj * ldj).sum() + ldj.sum()).backward()
+        res[hybrid] = (xg.grad.cpu(), [p.grad.cpu() for p in layer.parameters()])
+    s64 = O.spec_to(spec, torch.float64)
+    net = s64[0]['transform']['net']
+    leaves = []
+    for w, b in zip(net['weights'], net['biases']):
+        leaves += [w.requires_grad_(True), b.requires_grad_(True)]
+    x64 = x.double().clone().requires_grad_(True)
+    y64, l64 = O.layer_apply(s64[0], x64, inverse=False)
+    (y64.sin().sum() + (l64 * l64).sum() + l64.sum()).backward()
+
+    def close(got, want, what):
+        want = want.double()
+        scale = want.abs().max().clamp_min(1e-12)
+        err = (got.double() - want).abs()
+        bad = err > 1e-3 * want.abs() + 2e-5 * scale
+        assert bad.float().mean().item() <= 2e-3, f'{what}: {bad.float().mean().item():.3%} outside, max err {err.max().item():.3e} (scale {scale.item():.3e})'
+
+    close(res[False][0], x64.grad, 'grad_x vs oracle64')
+    close(res[False][0], res[True][0], 'grad_x vs hybrid')
+    for i, (g, l, h) in enumerate(zip(res[False][1], leaves, res[True][1])):
+        close(g, l.grad, f'parameter {i} vs oracle64')
+        close(g, h, f'parameter {i} vs hybrid')

@@ -43,7 +43,10 @@ def _flows(kind, d, masks, seed, n_layers=3, lower=-4., upper=4.):
 
 @pytest.mark.parametrize('kind', ['quadratic', 'cubic'])
 @pytest.mark.parametrize('d,masks', [(64, cases.ALT), (64, ('parity_even', 'parity_odd')),
-                                     (30, cases.ALT), (63, ('ordered_left_half', 'parity_odd')), (2, cases.ALT)])
+                                     (30, cases.ALT), (63, ('ordered_left_half', 'parity_odd')), (2, cases.ALT),
+                                     # dim > 64: the 128-row kernel (tc_wide.cu), BASELINE configs[4] width
+                                     (128, cases.ALT), (100, ('parity_even', 'parity_odd')),
+                                     (65, ('ordered_left_half', 'parity_odd'))])
 def test_tensor_path_matches_generic_and_oracle(kind, d, masks, monkeypatch):
     case = _flows(kind, d, masks, seed=900 + d)
     x = case['inputs']['x'].to(DEV)
