@@ -50,6 +50,9 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--generic', action='store_true', help='force the CUDA-core path (no tcgen05)')
+    ap.add_argument('--micro-rows', type=int, default=1 << 18, help='train: rows per micro-batch')
+    ap.add_argument('--tf32', action='store_true', help='train: let the library GEMMs of the conditioner gradients use TF32')
+    ap.add_argument('--hybrid', action='store_true', help='train: conditioner through autograd around the element-wise kernels')
     ap.add_argument('--workload', default='logprob', choices=['logprob', 'affine', 'neural', 'train'],
                     help='logprob = BASELINE.json configs[2] (the headline, default); affine = configs[1]; '
                          'neural = configs[3]; train = configs[4] (side measurements, same JSON schema)')
@@ -247,7 +250,13 @@ def run_side(args):
         a, b = shard_rows(rows_g, rank, world)
         torch.manual_seed(rank)
         y = torch.randn(b - a, d, device=dev)
-        dp = DataParallelNLL(flow, micro_rows=1 << 16)
+        if args.tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True
+        if args.hybrid:
+            os.environ['STRIBOR_B200_TRAIN_HYBRID'] = '1'
+        name += (f', micro-batches of {args.micro_rows} rows, conditioner-gradient GEMMs in '
+                 f'{"tf32" if args.tf32 else "fp32"}' + (', hybrid path' if args.hybrid else ', fused backward kernel'))
+        dp = DataParallelNLL(flow, micro_rows=args.micro_rows)
 
         def step():
             dp.step(y, rows_g)

@@ -20,6 +20,7 @@ A layer is described by plain data so that it can cross the op boundary:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -171,6 +172,19 @@ G_PAD = 48            # parameters per transformed dim in g_net (47 quadratic, p
 H_AUG = 72            # workspace row: hidden(64) | 1 | 0 x 7
 
 
+_PACKED_COLS = {}
+
+
+def _packed_cols(dev):
+    """Natural parameter index [w(16) | h(16) | d(15) | pad] -> column of the kernels' packed order
+    ((w_i, h_i) interleaved, then the derivative columns)."""
+    k = str(dev)
+    if k not in _PACKED_COLS:
+        cols = [2 * p for p in range(16)] + [2 * p + 1 for p in range(16)] + list(range(32, 48))
+        _PACKED_COLS[k] = torch.tensor(cols, dtype=torch.long, device=dev)
+    return _PACKED_COLS[k]
+
+
 def fused_backward_ok(L: '_lib.StbLayer') -> bool:
     """Does stb_layer_backward differentiate this (packed) layer with its conditioner fused?"""
     return int(_lib.lib().stb_layer_backward_workspace_bytes(C.byref(L), 1)) > 0
@@ -199,36 +213,54 @@ def _fused_conditioner_backward(x, mask, params, packed, meta, fmeta, direction,
         return [g_x, x.new_empty(0), x.new_empty(0), gW1, gb1, gW2, gb2]
     L = make_struct(meta, fmeta, mask, params, packed)
     lib = _lib.lib()
-    if packed is None or int(lib.stb_layer_backward_workspace_bytes(C.byref(L), rows)) != rows * H_AUG * 4:
+    ws_bytes = int(lib.stb_layer_backward_workspace_bytes(C.byref(L), rows)) if packed is not None else 0
+    if act not in (_lib.ACTIVATIONS['Tanh'], _lib.ACTIVATIONS['Sigmoid'], _lib.ACTIVATIONS['ReLU']):
+        ws_bytes = 0
+    if ws_bytes == 0:
         raise NotImplementedError('stribor_b200: this layer has no fused conditioner backward '
                                   '(quadratic spline, 16 bins, MLP[64], dim <= 128 on the tensor-core path)')
-    g_net = torch.empty(rows, n_tr * G_PAD, dtype=x.dtype, device=x.device)
-    haug = torch.empty(rows, H_AUG, dtype=x.dtype, device=x.device)
-    G = _lib.StbLayerGrads()
-    G.g_row_out = g_net.data_ptr()
-    with torch.cuda.device(x.device):
-        rc = lib.stb_layer_backward(C.byref(L), direction, x.data_ptr(), None, None, g_y.data_ptr(), _dp(g_ldj),
-                                    g_x.data_ptr(), None, None, C.byref(G), haug.data_ptr(), rows, _stream(x))
-    _lib.check(rc)
     dev = x.device
     tr_t = torch.tensor(tr, dtype=torch.long, device=dev)
     cond_t = torch.tensor(cond, dtype=torch.long, device=dev)
     hid = W2.shape[1]
-    W2p = W2.new_zeros(n_tr, G_PAD, hid)
-    W2p[:, :P] = W2.view(dim, P, hid).index_select(0, tr_t)
-    gaug = (g_net.t() @ haug).view(n_tr, G_PAD, H_AUG)          # [gW2 | gb2 | 0] of the transformed dims' rows
-    gW2.view(dim, P, hid).index_copy_(0, tr_t, gaug[:, :P, :hid].contiguous())
-    gb2.view(dim, P).index_copy_(0, tr_t, gaug[:, :P, hid].contiguous())
-    h = haug[:, :hid]
-    g_h = g_net @ W2p.view(n_tr * G_PAD, hid)
-    if act == _lib.ACTIVATIONS['Tanh']:
-        g_pre = g_h * (1.0 - h * h)
-    elif act == _lib.ACTIVATIONS['Sigmoid']:
-        g_pre = g_h * (h * (1.0 - h))
-    elif act == _lib.ACTIVATIONS['ReLU']:
-        g_pre = g_h * (h > 0).to(g_h.dtype)
+    G = _lib.StbLayerGrads()
+    if os.environ.get('STRIBOR_B200_TRAIN_GNET') == '1':
+        # two-step variant: the kernel leaves g_net / [hidden | 1]; the last Linear's products are library GEMMs
+        g_net = torch.empty(rows, n_tr * G_PAD, dtype=x.dtype, device=dev)
+        ws = torch.empty(ws_bytes // 4, dtype=x.dtype, device=dev)
+        haug = ws[:rows * H_AUG].view(rows, H_AUG)
+        G.g_row_out = g_net.data_ptr()
+        with torch.cuda.device(dev):
+            rc = lib.stb_layer_backward(C.byref(L), direction, x.data_ptr(), None, None, g_y.data_ptr(), _dp(g_ldj),
+                                        g_x.data_ptr(), None, None, C.byref(G), ws.data_ptr(), rows, _stream(x))
+        _lib.check(rc)
+        W2p = W2.new_zeros(n_tr, G_PAD, hid)
+        W2p[:, :P] = W2.view(dim, P, hid).index_select(0, tr_t)
+        gaug = (g_net.t() @ haug).view(n_tr, G_PAD, H_AUG)      # [gW2 | gb2 | 0] of the transformed dims' rows
+        gW2.view(dim, P, hid).index_copy_(0, tr_t, gaug[:, :P, :hid].contiguous())
+        gb2.view(dim, P).index_copy_(0, tr_t, gaug[:, :P, hid].contiguous())
+        h = haug[:, :hid]
+        g_h = g_net @ W2p.view(n_tr * G_PAD, hid)
+        if act == _lib.ACTIVATIONS['Tanh']:
+            g_pre = g_h * (1.0 - h * h)
+        elif act == _lib.ACTIVATIONS['Sigmoid']:
+            g_pre = g_h * (h * (1.0 - h))
+        else:
+            g_pre = g_h * (h > 0).to(g_h.dtype)
     else:
-        raise NotImplementedError('fused conditioner backward: activation not covered')
+        # fully fused: g_pre [rows, 64] and the [gW2 | gb2] image (packed column order) come out of the kernel
+        ws = torch.empty(ws_bytes // 4, dtype=x.dtype, device=dev)
+        img = ws[rows * H_AUG:]
+        img.zero_()
+        with torch.cuda.device(dev):
+            rc = lib.stb_layer_backward(C.byref(L), direction, x.data_ptr(), None, None, g_y.data_ptr(), _dp(g_ldj),
+                                        g_x.data_ptr(), None, None, C.byref(G), ws.data_ptr(), rows, _stream(x))
+        _lib.check(rc)
+        g_pre = ws[:rows * hid].view(rows, hid)
+        n_pad = 2 * ((n_tr + 1) // 2)
+        nat = img.view(-1, G_PAD, H_AUG)[:n_pad].index_select(1, _packed_cols(dev))[:n_tr]   # natural parameter order
+        gW2.view(dim, P, hid).index_copy_(0, tr_t, nat[:, :P, :hid].contiguous())
+        gb2.view(dim, P).index_copy_(0, tr_t, nat[:, :P, hid].contiguous())
     if cond:
         xc = x.index_select(1, cond_t)
         gW1.index_copy_(1, cond_t, g_pre.t() @ xc)

@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(kBThreads) elementwise_backward_kernel(const B
 // n_linear > 0 on the tensor-core path: the workspace receives the conditioner's hidden activations,
 // augmented [rows, 72] = h(64) | 1 | 0 x 7
 uint64_t layer_backward_workspace_bytes(const stb_layer* L, int64_t rows) {
-    if (L->net.n_linear > 0 && tcw_backward_supported(L)) return (uint64_t)(rows > 0 ? rows : 0) * 72 * sizeof(float);
+    if (L->net.n_linear > 0 && tcw_backward_supported(L))
+        return tcw_train_workspace_floats(L, rows > 0 ? rows : 0) * sizeof(float);
     return 0;
 }
 
@@ -182,8 +183,15 @@ int layer_backward(const stb_layer* L, int direction, const float* x, const floa
         if (!(L->packed && tcw_backward_supported(L) && tcw_image_present(L)))
             return set_error(STB_ENOTSUP, "fused conditioner backward needs the tensor-core path (quadratic spline, 16 bins, MLP[64], packed): run the MLP through autograd and pass its output as row_out");
         if (direction != STB_FORWARD && direction != STB_INVERSE) return set_error(STB_EINVAL, "bad direction");
-        if (rows < 0 || !x || !g_out || !g_x || !grads || !grads->g_row_out || !workspace) return set_error(STB_EINVAL, "bad argument");
+        if (rows < 0 || !x || !g_out || !g_x || !workspace) return set_error(STB_EINVAL, "bad argument");
         if (rows == 0) return STB_OK;
+        if (!grads || !grads->g_row_out)
+            // fully fused: the gradient products of the last Linear run in the same kernel.  workspace =
+            // [g_pre rows x 64 (gradient wrt the hidden pre-activation) ... | at float offset rows * 72: the
+            // [n_chunks * 96, 72] image of [gW | gb] of the last Linear's transformed-dim rows in packed
+            // column order, ACCUMULATED into (caller zeroes)]
+            return tcw_layer_backward_fused(L, tcw_image(L), direction, x, g_out, g_ldj, g_x,
+                                            static_cast<float*>(workspace), rows, stream);
         return tcw_layer_backward(L, tcw_image(L), direction, x, g_out, g_ldj, g_x, grads->g_row_out,
                                   static_cast<float*>(workspace), rows, stream);
     }

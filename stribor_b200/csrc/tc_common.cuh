@@ -57,8 +57,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 22)) {
-            printf("stribor_b200: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n",
-                   (int)blockIdx.x, (int)threadIdx.x, (void*)bar, parity);
+            if ((threadIdx.x & 31) == 0)
+                printf("stribor_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
+                       (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
             __trap();
         }
     }
@@ -102,8 +103,9 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(256);
         if (++spins > (1u << 22)) {
-            printf("stribor_b200: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n",
-                   (int)blockIdx.x, (int)threadIdx.x, (void*)bar, parity);
+            if ((threadIdx.x & 31) == 0)
+                printf("stribor_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
+                       (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
             __trap();
         }
     }
@@ -183,6 +185,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
+
+// MN-major operands (the K-major core-matrix buffer of the TRANSPOSED matrix, consumed in place):
+// canonical no-swizzle form ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)) -- SBO = stride between 16-byte groups
+// along M / N, LBO = stride between 8-row groups along K
+constexpr uint32_t kIdescAMajorMN = 1u << 15;
+constexpr uint32_t kIdescBMajorMN = 1u << 16;
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

@@ -48,8 +48,14 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const 
     uint8_t* b_lo = b_hi + b_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    pack_operand(a_hi, a_lo, A, 128, K, tf32);
-    pack_operand(b_hi, b_lo, B, N, K, tf32);
+    // variant bit 2 / bit 3: A / B is given TRANSPOSED (A [K,128], B [K,N]) and consumed MN-major.  The
+    // core-matrix packing of the [K rows, M cols] matrix is the same: an MN-major view needs no copy
+    // (tc_wide.cu reuses its K-major buffers this way for the gradient products).
+    const bool a_mn = (variant & 4) != 0, b_mn = (variant & 8) != 0;
+    if (a_mn) pack_operand(a_hi, a_lo, A, K, 128, tf32);
+    else pack_operand(a_hi, a_lo, A, 128, K, tf32);
+    if (b_mn) pack_operand(b_hi, b_lo, B, K, N, tf32);
+    else pack_operand(b_hi, b_lo, B, N, K, tf32);
     fence_proxy_async_smem();
 
     uint32_t ncols = 32;
@@ -68,7 +74,9 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const 
         const uint32_t kstride = 128, gstride = (uint32_t)chunks * 128;
         const uint32_t lbo = (variant & 1) ? gstride : kstride, sbo = (variant & 1) ? kstride : gstride;
         const bool small_first = (variant & 2) != 0;       // correction passes before hi*hi
-        const uint32_t idesc = make_idesc(tf32 ? FMT_TF32 : FMT_F16, 128, N);
+        const uint32_t idesc = make_idesc(tf32 ? FMT_TF32 : FMT_F16, 128, N) | (a_mn ? kIdescAMajorMN : 0u) | (b_mn ? kIdescBMajorMN : 0u);
+        // MN-major: SBO = next 16 bytes of M / N (128 B apart), LBO = next 8 rows of K
+        const uint32_t a_lbo = (uint32_t)(128 / epc) * 128, b_lbo = (uint32_t)(N / epc) * 128;
         const int ksteps = chunks / 2;
         const int npass = split ? 3 : 1;
         uint32_t acc = 0;
@@ -77,8 +85,11 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const 
             const uint8_t* as = (p == 1) ? a_lo : a_hi;          // hi*hi, lo*hi, hi*lo
             const uint8_t* bs = (p == 2) ? b_lo : b_hi;
             for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t ad = make_smem_desc(smem_u32(as) + ks * 2 * kstride, lbo, sbo);
-                const uint64_t bd = make_smem_desc(smem_u32(bs) + ks * 2 * kstride, lbo, sbo);
+                const uint32_t kk = 32 / elem / 8;                // 8-row K groups per UMMA (fp16: 2, tf32: 1)
+                const uint64_t ad = a_mn ? make_smem_desc(smem_u32(as) + ks * kk * a_lbo, a_lbo, 128)
+                                       : make_smem_desc(smem_u32(as) + ks * 2 * kstride, lbo, sbo);
+                const uint64_t bd = b_mn ? make_smem_desc(smem_u32(bs) + ks * kk * b_lbo, b_lbo, 128)
+                                       : make_smem_desc(smem_u32(bs) + ks * 2 * kstride, lbo, sbo);
                 if (tf32) umma_tf32(tbase, ad, bd, idesc, acc);
                 else umma_f16(tbase, ad, bd, idesc, acc);
                 acc = 1;

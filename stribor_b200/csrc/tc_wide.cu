@@ -543,6 +543,561 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
 }
 
 // -----------------------------------------------------------------------------------------------
+// training backward with the conditioner's gradient products fused
+// -----------------------------------------------------------------------------------------------
+// Same recompute as BWD above; the per-element gradient g_net never leaves the SM.  Per chunk
+// (2 transformed dims x 48 parameters) the epilogue warps write it, scaled by a per-tile power of two
+// and split fp16 hi | lo, into ONE shared K-major buffer G [128 rows x 96], and the issuer runs two more
+// groups of UMMAs on it, both with operands that are MN-major VIEWS of buffers the forward needs anyway:
+//   g_hidden [128 x 64] += G [128 x 96] . W2chunk [96 x 64]      A = G K-major, B = the ring stage MN-major
+//   gW2chunk [96 x 64 | gb2] = G^T [96 x 128] . [h | 1] [128 x 80]  A = G MN-major, B = the h operand MN-major
+// g_hidden accumulates in TMEM over the tile's chunks and becomes g_pre = g_hidden * act'(h) [rows, 64];
+// the per-(tile, chunk) gW2 partials are added to a [n_chunks * 96, 72] fp32 image in global memory
+// (L2-resident, red.global.add.v4.f32) -- summation order over tiles is not deterministic.
+// Left to the caller: gW1 = g_pre^T x_cond, gb1 = sum g_pre, g_x[cond] += g_pre W1[:, cond] (K = 64 products).
+namespace train {
+constexpr int kHPad = 80;                                         // h operand columns: 64 hidden | 1 | 0 x 15
+constexpr uint32_t kHSbo = (kHPad / 8) * 128;                     // 1280: next 8 rows of the h operand
+constexpr uint32_t kHLo = kTileRows * kHPad * 2;                  // 20480: lo part
+constexpr uint32_t kGSbo = (kChunkN / 8) * 128;                   // 1536: next 8 rows of G
+constexpr uint32_t kGLo = kTileRows * kChunkN * 2;                // 24576
+constexpr int kWStride = 72;                                      // floats per row of the gW2 image
+constexpr uint32_t kSmXs = 0;
+constexpr uint32_t kSmA = (kTileRows * kTrStride * 4 + 1023) & ~1023u;
+constexpr uint32_t kSmG = kSmA + kABytes;
+constexpr uint32_t kSmB = kSmG + 2 * kGLo;
+constexpr uint32_t kSmSmall = kSmB + kStages * kChunkBytes;
+constexpr uint32_t kSmBar = (kSmSmall + kSmallBytes + 15) & ~15u;
+constexpr uint32_t kSmemBytes = kSmBar + 256;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+static_assert(2 * kHLo <= kABytes, "h operand fits the A region");
+
+struct Bars {
+    uint64_t setup;
+    uint64_t b_full[kStages], b_empty[kStages];
+    uint64_t a1_ready, acc1_full, h_ready;
+    uint64_t acc_full[2], acc_empty[2];
+    uint64_t g_ready, g_empty[2];
+    uint64_t w_full[2], w_empty[2];
+    uint64_t acch_full;
+    uint32_t tmem_base;
+    uint32_t tile_max;
+};
+static_assert(sizeof(Bars) <= 256, "barrier block");
+constexpr uint32_t kColAcc1 = 0;
+constexpr uint32_t kColAcc2 = 64;                // + buf * 96
+constexpr uint32_t kColAccH = 256;
+constexpr uint32_t kColAccW = 320;               // + wb * 80
+
+struct Args {
+    const uint8_t* packed;
+    const float* x;
+    const float* g_out;
+    const float* g_ldj;
+    float* g_x;
+    float* g_pre;            // [rows, 64]
+    float* g_w2;             // [n_chunks * 96, 72], accumulated
+    float lower, upper;
+    long long rows;
+    int n_tiles;
+};
+
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// 8 scaled gradients -> fp16 hi | lo, one 16-byte store each
+__device__ __forceinline__ void put_g8(uint8_t* dst_hi, const float* v, float sigma) {
+    __align__(16) __half hh[8], hl[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float w = fminf(fmaxf(v[i] * sigma, -60000.f), 60000.f);
+        split_f16(w, hh[i], hl[i]);
+    }
+    *reinterpret_cast<uint4*>(dst_hi) = *reinterpret_cast<const uint4*>(hh);
+    *reinterpret_cast<uint4*>(dst_hi + kGLo) = *reinterpret_cast<const uint4*>(hl);
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* xs = reinterpret_cast<float*>(smem + kSmXs);
+    uint8_t* abuf = smem + kSmA;
+    uint8_t* gbuf = smem + kSmG;
+    uint8_t* bst = smem + kSmB;
+    const Header* hdr = reinterpret_cast<const Header*>(smem + kSmSmall);
+    const float* b1s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB1);
+    const float* b2s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB2);
+    Bars* bars = reinterpret_cast<Bars*>(smem + kSmBar);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        mbar_init(&bars->setup, 1);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+        mbar_init(&bars->a1_ready, kEpiWarps);
+        mbar_init(&bars->acc1_full, 1);
+        mbar_init(&bars->h_ready, kEpiWarps);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 8);
+            mbar_init(&bars->w_full[b], 1); mbar_init(&bars->w_empty[b], 8);
+        }
+        mbar_init(&bars->g_ready, 8);
+        mbar_init(&bars->g_empty[0], 1);
+        mbar_init(&bars->g_empty[1], 1);
+        mbar_init(&bars->acch_full, 1);
+        bars->tile_max = 0;
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars->setup, kSmallBytes);
+        bulk_g2s(smem + kSmSmall, A.packed, kSmallBytes, &bars->setup);
+    }
+    mbar_wait(&bars->setup, 0);
+
+    const int d = hdr->dim, n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_chunks = hdr->n_chunks;
+    const int k1pad = hdr->k1pad;
+    const int act = hdr->act;
+    const float s2 = hdr->s2;
+    const float s2l = s2 * 1.4426950408889634f;
+    const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        // ======================= producer =========================================================
+        if (lane == 0) {
+            uint32_t cc = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int c = -1; c < n_chunks; ++c, ++cc) {
+                    const uint32_t st = cc % kStages, use = cc / kStages;
+                    mbar_wait_relaxed(&bars->b_empty[st], (use & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bars->b_full[st], kChunkBytes);
+                    const uint8_t* src = (c < 0) ? A.packed + kOffW1 : A.packed + kOffW2 + (size_t)c * kChunkBytes;
+                    bulk_g2s(bst + st * kChunkBytes, src, kChunkBytes, &bars->b_full[st]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= UMMA issuer ======================================================
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, kHid);
+            const uint32_t idesc2 = make_idesc(FMT_F16, 128, kChunkN);
+            const uint32_t idesc_h = make_idesc(FMT_F16, 128, kHid) | kIdescBMajorMN;
+            const uint32_t idesc_w = make_idesc(FMT_F16, 128, kHPad) | kIdescAMajorMN | kIdescBMajorMN;
+            const uint32_t a_hi = smem_u32(abuf), a_lo = a_hi + kHLo;
+            const uint32_t g_hi = smem_u32(gbuf), g_lo = g_hi + kGLo;
+            uint32_t cc = 0, cb = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const uint32_t tpar = it & 1;
+                {
+                    const uint32_t st = cc % kStages, use = cc / kStages;
+                    mbar_wait_relaxed(&bars->b_full[st], use & 1);
+                    mbar_wait_relaxed(&bars->a1_ready, tpar);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(abuf), b0 = smem_u32(bst + st * kChunkBytes);
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const int pa = (p == 0 || p == 3 || p == 6) ? 1 : ((p == 1 || p == 4) ? 2 : 0);
+                        const int pb = (p == 0 || p == 2) ? 2 : ((p == 1 || p == 3 || p == 5) ? 1 : 0);
+                        for (int ks = 0; ks < k1pad / 16; ++ks) {
+                            umma_f16(tmem + kColAcc1, make_smem_desc(a0 + pa * kA1Part + ks * 256, 128, 1024),
+                                     make_smem_desc(b0 + pb * kW1Part + ks * 256, 128, 1024), idesc1, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&bars->acc1_full);
+                    umma_commit(&bars->b_empty[st]);
+                    ++cc;
+                }
+                // forward recompute of chunk c (F) runs up to three chunks ahead of the gradient products (G):
+                //   F0 F1 F2 | G0 F3 | G1 F4 | ...   (stage of chunk c is released by G(c))
+                const uint32_t cc0 = cc;                        // ring index of chunk 0 of this tile
+                auto issue_f = [&](int c) {
+                    const uint32_t ci = cc0 + (uint32_t)c, st = ci % kStages, use = ci / kStages;
+                    mbar_wait_relaxed(&bars->b_full[st], use & 1);
+                    const uint32_t n = cb + (uint32_t)c, buf = n & 1, buse = n >> 1;
+                    if (c == 0) mbar_wait_relaxed(&bars->h_ready, tpar);
+                    mbar_wait_relaxed(&bars->acc_empty[buf], (buse & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(bst + st * kChunkBytes), b_lo = b_hi + 12288;
+                    const uint32_t dcol = tmem + kColAcc2 + buf * kChunkN;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const uint32_t aa = (p == 0) ? a_lo : a_hi, bb = (p == 1) ? b_lo : b_hi;
+#pragma unroll
+                        for (int ks = 0; ks < kHid / 16; ++ks) {
+                            umma_f16(dcol, make_smem_desc(aa + ks * 256, 128, kHSbo),
+                                     make_smem_desc(bb + ks * 256, 128, 1024), idesc2, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&bars->acc_full[buf]);
+                };
+                auto issue_g = [&](int c) {
+                    const uint32_t ci = cc0 + (uint32_t)c, st = ci % kStages;
+                    const uint32_t n = cb + (uint32_t)c, wb = n & 1, wuse = n >> 1;
+                    mbar_wait_relaxed(&bars->g_ready, n & 1);
+                    mbar_wait_relaxed(&bars->w_empty[wb], (wuse & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(bst + st * kChunkBytes), b_lo = b_hi + 12288;
+                    // g_hidden += G . W2chunk : K = 96 parameters, B = the stage as [K = param][N = hidden]
+                    // The tensor core truncates the running accumulator at every step and this sum runs over all
+                    // chunks of the tile: the hi*hi products go to one accumulator, the two small correction
+                    // passes to another (kColAcc1, free since the tanh pass), so the large sum takes a third of
+                    // the steps and the corrections' truncation is far below its resolution.
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const uint32_t aa = (p == 0) ? g_lo : g_hi, bb = (p == 1) ? b_lo : b_hi;
+                        const uint32_t dcol = tmem + ((p == 2) ? kColAccH : kColAcc1);
+                        uint32_t acc = (c == 0 && p != 1) ? 0u : 1u;
+#pragma unroll
+                        for (int ks = 0; ks < kChunkN / 16; ++ks) {
+                            umma_f16(dcol, make_smem_desc(aa + ks * 256, 128, kGSbo),
+                                     make_smem_desc(bb + ks * 2048, 1024, 128), idesc_h, acc);
+                            acc = 1;
+                        }
+                    }
+                    // [gW2chunk | gb2] = G^T . [h | 1] : K = 128 rows, both operands MN-major views
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        const uint32_t aa = (p == 0) ? g_lo : g_hi, bb = (p == 1) ? a_lo : a_hi;
+#pragma unroll
+                        for (int ks = 0; ks < kTileRows / 16; ++ks) {
+                            umma_f16(tmem + kColAccW + wb * kHPad, make_smem_desc(aa + ks * 2 * kGSbo, kGSbo, 128),
+                                     make_smem_desc(bb + ks * 2 * kHSbo, kHSbo, 128), idesc_w, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&bars->w_full[wb]);
+                    umma_commit(&bars->g_empty[n & 1]);
+                    umma_commit(&bars->b_empty[st]);
+                };
+                for (int c = 0; c < n_chunks && c < 3; ++c) issue_f(c);
+                for (int c = 0; c < n_chunks; ++c) {
+                    issue_g(c);
+                    if (c + 3 < n_chunks) issue_f(c + 3);
+                }
+                umma_commit(&bars->acch_full);
+                cc += (uint32_t)n_chunks;
+                cb += (uint32_t)n_chunks;
+            }
+        }
+    } else {
+        // ======================= loader + epilogue warps ==========================================
+        const int q = warp & 3;
+        const int r4 = (warp - kEpiWarp0) >> 2;
+        const int etid = tid - kEpiWarp0 * 32;
+        const int rloc = q * 32 + lane;
+        const uint32_t h_row_off = (uint32_t)(rloc >> 3) * kHSbo + (uint32_t)(rloc & 7) * 16;
+        const uint32_t g_row_off = (uint32_t)(rloc >> 3) * kGSbo + (uint32_t)(rloc & 7) * 16;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const float lo = A.lower, hi = A.upper;
+        const float inv_span = 1.f / (hi - lo);
+        uint32_t cb = 0;
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long row0 = tile * kTileRows;
+            const int nrows = (int)min((long long)kTileRows, A.rows - row0);
+            const uint32_t tpar = it & 1;
+            const bool row_live = rloc < nrows;
+
+            // ---- load the tile (as tc_wide_kernel): conditioning columns -> bf16x3 A operand, transformed
+            // columns of x -> smem, pass-through columns of g_out -> g_x; the tile's gradient scale -----------
+            float gmax = 0.f;
+            {
+                const float* xg = A.x + row0 * d;
+                const float* gg = A.g_out + row0 * d;
+                float* og = A.g_x + row0 * d;
+                const bool copy_pass = static_cast<const float*>(A.g_x) != A.g_out;
+                const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0) &&
+                                 ((reinterpret_cast<uintptr_t>(gg) & 15) == 0) && ((reinterpret_cast<uintptr_t>(og) & 15) == 0);
+                if (vec) {
+                    const int d4 = d >> 2, n4 = kTileRows * d4;
+                    for (int i = etid; i < n4; i += kEpiThreads) {
+                        const int r = i / d4, c = (i - r * d4) << 2;
+                        const bool live = r < nrows;
+                        const float4 v = live ? __ldg(reinterpret_cast<const float4*>(xg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 gv = live ? __ldg(reinterpret_cast<const float4*>(gg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(gv.x), fabsf(gv.y)), fmaxf(fabsf(gv.z), fabsf(gv.w))));
+                        const int m0 = hdr->colmap[c], m1 = hdr->colmap[c + 1], m2 = hdr->colmap[c + 2], m3 = hdr->colmap[c + 3];
+                        if (m0 >= 0 && (m0 & 3) == 0 && m1 == m0 + 1 && m2 == m0 + 2 && m3 == m0 + 3) {
+                            __align__(8) __nv_bfloat16 q0[4], q1[4], q2[4];
+                            split_bf16x3(v.x, q0[0], q1[0], q2[0]); split_bf16x3(v.y, q0[1], q1[1], q2[1]);
+                            split_bf16x3(v.z, q0[2], q1[2], q2[2]); split_bf16x3(v.w, q0[3], q1[3], q2[3]);
+                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m0 >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m0 & 7) * 2;
+                            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(q0);
+                            *reinterpret_cast<uint2*>(dst + kA1Part) = *reinterpret_cast<const uint2*>(q1);
+                            *reinterpret_cast<uint2*>(dst + 2 * kA1Part) = *reinterpret_cast<const uint2*>(q2);
+                            if (copy_pass && live) reinterpret_cast<float4*>(og)[i] = gv;
+                        } else {
+                            const float vv[4] = {v.x, v.y, v.z, v.w};
+                            const float gvv[4] = {gv.x, gv.y, gv.z, gv.w};
+                            const int mm[4] = {m0, m1, m2, m3};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (mm[u] >= 0) {
+                                    __nv_bfloat16 p0, p1, p2;
+                                    split_bf16x3(vv[u], p0, p1, p2);
+                                    uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(mm[u] >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(mm[u] & 7) * 2;
+                                    *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
+                                    *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
+                                    *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                                    if (copy_pass && live) og[(size_t)r * d + c + u] = gvv[u];
+                                } else {
+                                    xs[r * kTrStride - mm[u] - 1] = vv[u];
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    const int n = kTileRows * d;
+                    for (int i = etid; i < n; i += kEpiThreads) {
+                        const int r = i / d, c = i - r * d;
+                        const bool live = r < nrows;
+                        const float v = live ? __ldg(xg + i) : 0.f;
+                        const float gv = live ? __ldg(gg + i) : 0.f;
+                        gmax = fmaxf(gmax, fabsf(gv));
+                        const int m = hdr->colmap[c];
+                        if (m >= 0) {
+                            __nv_bfloat16 p0, p1, p2;
+                            split_bf16x3(v, p0, p1, p2);
+                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
+                            *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
+                            *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
+                            *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                            if (copy_pass && live) og[i] = gv;
+                        } else {
+                            xs[r * kTrStride - m - 1] = v;
+                        }
+                    }
+                }
+                const int npad = k1pad - n_cond;
+                for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
+                    const int r = i / npad, m = n_cond + (i - r * npad);
+                    uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
+                    *reinterpret_cast<uint16_t*>(dst) = 0;
+                    *reinterpret_cast<uint16_t*>(dst + kA1Part) = 0;
+                    *reinterpret_cast<uint16_t*>(dst + 2 * kA1Part) = 0;
+                }
+            }
+            float g_ld = 0.f;
+            if (A.g_ldj != nullptr && row_live) g_ld = __ldg(A.g_ldj + row0 + rloc);
+            gmax = fmaxf(gmax, fabsf(g_ld));
+#pragma unroll
+            for (int o = 16; o; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+            if (lane == 0) atomicMax(&bars->tile_max, __float_as_uint(gmax));
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiThreads);
+            if (lane == 0) mbar_arrive(&bars->a1_ready);
+            // per-tile scale: the largest incoming gradient maps to [2^-6, 2^-5) (fp16 head-room for the
+            // spline's amplification, 2^-24 absolute resolution of the hi | lo pair below it)
+            float sigma = 1.f, inv_sigma = 1.f;
+            {
+                const uint32_t e = (bars->tile_max >> 23) & 0xffu;
+                if (e >= 8u && e <= 240u) {
+                    sigma = __uint_as_float((248u - e) << 23);          // 2^(-6 - (e - 127))
+                    inv_sigma = __uint_as_float((e + 6u) << 23);
+                }
+            }
+
+            // ---- hidden layer: h = act(acc1 + b1) -> fp16 hi | lo, 80-column operand [h | 1 | 0] -------------
+            mbar_wait(&bars->acc1_full, tpar);
+            tc_fence_after();
+#pragma unroll 1
+            for (int kc = r4; kc < kHid / 8; kc += 4) {
+                const int c0 = kc * 8;
+                float v[8];
+                tmem_ld8(tmem + lane_sel + kColAcc1 + c0, v);
+                tmem_ld_wait();
+                __align__(16) __half hh[8], hl[8];
+                if (act == STB_ACT_TANH) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] + b1s[c0 + i]);
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 8; ++i) v[i] = activate(act, v[i] + b1s[c0 + i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split_f16(v[i], hh[i], hl[i]);
+                *reinterpret_cast<uint4*>(abuf + h_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hh);
+                *reinterpret_cast<uint4*>(abuf + kHLo + h_row_off + kc * 128) = *reinterpret_cast<const uint4*>(hl);
+            }
+            if (r4 < 2) {                                       // columns 64..79: 1, 0, ... (hi), 0 (lo)
+                const uint32_t one = row_live ? 0x3c00u : 0u;   // rows beyond the batch contribute nothing to gb2
+                *reinterpret_cast<uint4*>(abuf + h_row_off + (8 + r4) * 128) = make_uint4(r4 == 0 ? one : 0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(abuf + kHLo + h_row_off + (8 + r4) * 128) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->h_ready);
+
+            // ---- chunks: parameters out of TMEM, element gradient in registers, G into shared memory ---------
+            float* xrow = xs + rloc * kTrStride;
+            auto flush_w = [&](int c) {
+                // this group's gW2 partial of chunk c: TMEM lane = packed parameter column, 65 columns
+                const uint32_t n = cb + (uint32_t)c, wb = n & 1, wuse = n >> 1;
+                mbar_wait(&bars->w_full[wb], wuse & 1);
+                tc_fence_after();
+                const int g = r4 & 1;
+                if (q < 3) {
+                    float* dst = A.g_w2 + ((size_t)c * kChunkN + rloc) * kWStride + g * 32;
+                    const uint32_t col = tmem + lane_sel + kColAccW + wb * kHPad + (uint32_t)g * 32;
+                    float v[16];
+#pragma unroll
+                    for (int hh2 = 0; hh2 < 2; ++hh2) {
+                        tmem_ld16(col + hh2 * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            red_add4(dst + hh2 * 16 + i, v[i] * inv_sigma, v[i + 1] * inv_sigma, v[i + 2] * inv_sigma, v[i + 3] * inv_sigma);
+                    }
+                    if (g == 1) {
+                        float w8[8];
+                        tmem_ld8(tmem + lane_sel + kColAccW + wb * kHPad + kHid, w8);
+                        tmem_ld_wait();
+                        atomicAdd(A.g_w2 + ((size_t)c * kChunkN + rloc) * kWStride + kHid, w8[0] * inv_sigma);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->w_empty[wb]);
+            };
+            int prev = -1;
+#pragma unroll 1
+            for (int ji = r4; ji < kG * n_chunks; ji += 4) {
+                const int c = ji >> 1;
+                const uint32_t n = cb + (uint32_t)c;
+                const uint32_t buf = n & 1, buse = n >> 1;
+                const int g = ji & 1;
+                const bool live_dim = ji < n_tr;
+                const float xv = live_dim ? xrow[ji] : 0.f;
+                const bool inside = live_dim && row_live && (xv >= lo) && (xv <= hi);
+                const float go = (live_dim && row_live) ? __ldg(A.g_out + (size_t)(row0 + rloc) * d + hdr->tr_idx[ji]) : 0.f;
+                const float* bb = b2s + ji * kPPad;
+                const float2* bb2 = reinterpret_cast<const float2*>(bb);
+                mbar_wait(&bars->acc_full[buf], buse & 1);
+                tc_fence_after();
+                const uint32_t col0 = tmem + lane_sel + kColAcc2 + buf * kChunkN + (uint32_t)g * kPPad;
+                const bool shift = !((hdr->noshift_mask[ji >> 5] >> (ji & 31)) & 1u);
+                float2 t[kBins];
+                tmem_ld16(col0, reinterpret_cast<float*>(t));
+                tmem_ld16(col0 + 16, reinterpret_cast<float*>(t) + 16);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
+                softmax16_num2(t, shift);
+                float2 ee, eo;
+                const BinSearch16 bs = bin_search16<INVERSE>(t, STB_RQS_MIN, (xv - lo) * inv_span, ee, eo);
+                float dd[16];
+                tmem_ld16(col0 + 2 * kBins, dd);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                float r0, r1;
+                pick_pair16(dd, bs.k, r0, r1);
+                const int kk = bs.k;
+                const float u0 = (kk == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + (kk > 0 ? kk - 1 : 0)]);
+                const float u1 = (kk == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + (kk < kBins - 1 ? kk : 0)]);
+                float gx = go, gu0 = 0.f, gu1 = 0.f;
+                if (inside) {
+                    rqs16_backward<INVERSE>(t, bs, ee, eo, u0, u1, lo, hi, xv, go, g_ld, gx, gu0, gu1);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kBins; ++i) t[i] = f2(0.f);
+                }
+                if (live_dim) xrow[ji] = gx;                       // x of this element is dead: reuse for g_x
+                if (prev >= 0) flush_w(prev);
+                // G is one buffer: chunk n may be written once the products of chunk n - 1 have retired.  Two
+                // barriers alternate so that a warp (which handles every second chunk) waits on consecutive
+                // phases of ONE barrier: with a single barrier the phase it skips makes parity ambiguous.
+                if (n >= 1) mbar_wait(&bars->g_empty[(n - 1) & 1], ((n - 1) >> 1) & 1);
+                {
+                    uint8_t* gdst = gbuf + g_row_off + (uint32_t)(g * (kPPad / 8)) * 128;
+                    float w[8];
+#pragma unroll
+                    for (int b8 = 0; b8 < 4; ++b8) {               // packed column order: (w_i, h_i) interleaved
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { w[2 * i] = t[b8 * 4 + i].x; w[2 * i + 1] = t[b8 * 4 + i].y; }
+                        put_g8(gdst + b8 * 128, w, sigma);
+                    }
+#pragma unroll
+                    for (int b8 = 0; b8 < 2; ++b8) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int di = b8 * 8 + i;
+                            w[i] = (di == kk - 1) ? gu0 : ((di == kk) ? gu1 : 0.f);
+                            if (di == kBins - 1) w[i] = 0.f;
+                        }
+                        put_g8(gdst + (4 + b8) * 128, w, sigma);
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->g_ready);
+                prev = c;
+            }
+            if (prev >= 0) flush_w(prev);
+            cb += (uint32_t)n_chunks;
+
+            // ---- g_pre = g_hidden * act'(h) ----------------------------------------------------------------------
+            mbar_wait(&bars->acch_full, tpar);
+            tc_fence_after();
+            {
+                const float unscale = s2 * inv_sigma;
+#pragma unroll 1
+                for (int kc = r4; kc < kHid / 8; kc += 4) {
+                    float v[8], vc[8];
+                    tmem_ld8(tmem + lane_sel + kColAccH + kc * 8, v);
+                    tmem_ld8(tmem + lane_sel + kColAcc1 + kc * 8, vc);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += vc[i];
+                    const uint4 hh = *reinterpret_cast<const uint4*>(abuf + h_row_off + kc * 128);
+                    const uint4 hl = *reinterpret_cast<const uint4*>(abuf + kHLo + h_row_off + kc * 128);
+                    const __half* ph = reinterpret_cast<const __half*>(&hh);
+                    const __half* pl = reinterpret_cast<const __half*>(&hl);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float h = __half2float(ph[i]) + __half2float(pl[i]);
+                        const float da = (act == STB_ACT_TANH) ? (1.f - h * h)
+                                       : ((act == STB_ACT_SIGMOID) ? h * (1.f - h) : ((h > 0.f) ? 1.f : 0.f));
+                        v[i] = v[i] * unscale * da;
+                    }
+                    if (row_live) stg256(A.g_pre + (size_t)(row0 + rloc) * kHid + kc * 8, v);
+                }
+            }
+            tc_fence_before();
+            named_bar_sync(1, kEpiThreads);
+            // ---- transformed columns of g_x out ----------------------------------------------------------------
+            {
+                float* og = A.g_x + row0 * d;
+                for (int i = etid; i < nrows * n_tr; i += kEpiThreads) {
+                    const int r = i / n_tr, sl = i - r * n_tr;
+                    og[(size_t)r * d + hdr->tr_idx[sl]] = xs[r * kTrStride + sl];
+                }
+                if (etid == 0) bars->tile_max = 0;
+            }
+            named_bar_sync(1, kEpiThreads);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+}  // namespace train
+
+// -----------------------------------------------------------------------------------------------
 // packing
 // -----------------------------------------------------------------------------------------------
 struct PackArgs {
@@ -754,6 +1309,48 @@ int tcw_layer_backward(const stb_layer* L, const void* image, int direction, con
     A.n_tiles = (int)tiles;
     void (*kern)(Args) = (direction == STB_INVERSE) ? tc_wide_kernel<STB_RQS, true, true> : tc_wide_kernel<STB_RQS, false, true>;
     return tcw_launch(kern, A, tiles, stream, "tc_wide_kernel (backward)");
+}
+
+
+uint64_t tcw_train_workspace_floats(const stb_layer* L, int64_t rows) {
+    (void)L;
+    return (uint64_t)rows * tcw::kHAug + (uint64_t)tcw::kMaxChunks * tcw::kChunkN * tcw::train::kWStride;
+}
+
+// Fully fused: g_x, g_pre = workspace[0 : rows * 64], gW2 image = workspace[rows * 72 : ...] (accumulated)
+int tcw_layer_backward_fused(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
+                             const float* g_ldj, float* g_x, float* workspace, int64_t rows, cudaStream_t stream) {
+    using namespace tcw;
+    if (L->kind != STB_RQS) return set_error(STB_ENOTSUP, "tensor-core backward is built for the quadratic spline");
+    const int act = L->net.activation;
+    if (act != STB_ACT_TANH && act != STB_ACT_SIGMOID && act != STB_ACT_RELU)
+        return set_error(STB_ENOTSUP, "fused conditioner backward: Tanh / Sigmoid / ReLU hidden activation only");
+    train::Args A = {};
+    A.packed = static_cast<const uint8_t*>(image);
+    A.x = x; A.g_out = g_out; A.g_ldj = g_ldj; A.g_x = g_x;
+    A.g_pre = workspace;
+    A.g_w2 = workspace + (size_t)rows * kHAug;
+    A.lower = L->lower; A.upper = L->upper;
+    A.rows = rows;
+    const long long tiles = (rows + kTileRows - 1) / kTileRows;
+    if (tiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
+    A.n_tiles = (int)tiles;
+    void (*kern)(train::Args) = (direction == STB_INVERSE) ? train::tc_wide_train_kernel<true> : train::tc_wide_train_kernel<false>;
+    static thread_local int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train::kSmemBytes);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int grid = (int)min((long long)n_sm, tiles);
+    kern<<<grid, kThreads, train::kSmemBytes, stream>>>(A);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_wide_train_kernel launch: %s", cudaGetErrorString(e));
+    return STB_OK;
 }
 
 }  // namespace stb

@@ -35,6 +35,26 @@ def test_umma_building_blocks(mode, K, N):
         assert err < 8 * err32 + 1e-6
 
 
+@pytest.mark.parametrize('variant', [4, 8, 12])
+@pytest.mark.parametrize('mode', [0, 2])
+@pytest.mark.parametrize('K,N', [(16, 64), (96, 64), (128, 64), (128, 96)])
+def test_umma_mn_major_operands(mode, K, N, variant):
+    """Transposed operands consumed in place (MN-major descriptors): the gradient products of the
+    training kernel reuse the K-major buffers of the forward recompute this way."""
+    torch.manual_seed(K * 1000 + N + mode + variant)
+    A = torch.rand(128, K, device=DEV) * 2 - 1
+    B = torch.rand(N, K, device=DEV) * 2 - 1
+    Ain = A.t().contiguous() if variant & 4 else A
+    Bin = B.t().contiguous() if variant & 8 else B
+    D = torch.full((128, N), float('nan'), device=DEV)
+    rc = _lib.lib().stb_tc_selftest(Ain.data_ptr(), Bin.data_ptr(), D.data_ptr(), K, N, mode, variant,
+                                    torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+    ref = A.double() @ B.double().t()
+    err = (D.double() - ref).abs().max().item()
+    assert err < (2e-5 if mode >= 2 else 1e-2) * max(1.0, K / 32), err
+
+
 def _flows(kind, d, masks, seed, n_layers=3, lower=-4., upper=4.):
     case = cases._mk_flow(kind, d, [64], n_layers, 16, 700, seed, masks=masks, lower=lower, upper=upper,
                           scale=1.7)()

@@ -15,7 +15,7 @@ layers = [st.Coupling(st.Spline(d, K, latent_net=st.net.MLP(d, [64], d * 47), lo
                       mask=('ordered_right_half', 'ordered_left_half')[i % 2]) for i in range(L)]
 flow = st.NormalizingFlow(st.UnitNormal(d), layers).to(dev)
 y = torch.randn(rows, d, device=dev)
-dp = DataParallelNLL(flow, micro_rows=1 << 16)
+dp = DataParallelNLL(flow, micro_rows=1 << 18)
 dp.step(y, rows)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
