@@ -97,6 +97,22 @@ __device__ __forceinline__ uint32_t pin(uint32_t v) {
     return v;
 }
 
+// wait with a sleep between polls: for epilogue warps whose wait is long by construction (the other warp
+// group's turn, a product group in flight) -- a tight try_wait loop was 17 % of all issued instructions of
+// the training kernel, taken from the warps doing arithmetic on the same scheduler
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (++spins > (1u << 22)) {
+            if ((threadIdx.x & 31) == 0)
+                printf("stribor_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
+                       (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+
 // same, for single-lane roles that can afford to back off (producer / issuer)
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
@@ -240,6 +256,13 @@ __device__ __forceinline__ void split_bf16x3(float v, __nv_bfloat16& b0, __nv_bf
     const float r1 = v - __bfloat162float(b0);
     b1 = __float2bfloat16_rn(r1);
     b2 = __float2bfloat16_rn(r1 - __bfloat162float(b1));
+}
+// two values -> packed fp16 hi | lo, saturating (F2FP.SATFINITE.PACK_AB: one instruction per pair and part)
+__device__ __forceinline__ void split_f16x2_sat(float a, float b, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+    const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+    const float ra = a - __low2float(h), rb = b - __high2float(h);
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
 }
 // v ~= hi + lo with hi, lo fp16 (|v| <= ~6e4; lo lands in the subnormal range for |v| < 0.25,
 // where its absolute resolution 2^-25 is still below fp32's for O(1) accumulations)

@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
             if (lane == 0) mbar_arrive(&bars->a1_ready);
 
             // ---- hidden layer: h = act(acc1 + b1) -> fp16 hi | lo A operand of GEMM2 --------------------
-            mbar_wait(&bars->acc1_full, tpar);
+            mbar_wait_sleep(&bars->acc1_full, tpar, 64);
             tc_fence_after();
 #pragma unroll 1
             for (int kc = r4; kc < kHid / 8; kc += 4) {
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                 const bool inside = live_dim && (xv >= lo) && (xv <= hi);
                 const float* bb = b2s + ji * kPPad;
                 const float2* bb2 = reinterpret_cast<const float2*>(bb);
-                mbar_wait(&bars->acc_full[buf], buse & 1);
+                mbar_wait_sleep(&bars->acc_full[buf], buse & 1, 32);
                 tc_fence_after();
                 const uint32_t col0 = tmem + lane_sel + kColAcc2 + buf * kChunkN + (uint32_t)g * kPPad;
                 const bool shift = !((hdr->noshift_mask[ji >> 5] >> (ji & 31)) & 1u);
@@ -605,16 +605,15 @@ struct Args {
 __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// 8 scaled gradients -> fp16 hi | lo, one 16-byte store each
+// 8 scaled gradients -> fp16 hi | lo (saturating), one 16-byte store each
 __device__ __forceinline__ void put_g8(uint8_t* dst_hi, const float* v, float sigma) {
-    __align__(16) __half hh[8], hl[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float w = fminf(fmaxf(v[i] * sigma, -60000.f), 60000.f);
-        split_f16(w, hh[i], hl[i]);
-    }
-    *reinterpret_cast<uint4*>(dst_hi) = *reinterpret_cast<const uint4*>(hh);
-    *reinterpret_cast<uint4*>(dst_hi + kGLo) = *reinterpret_cast<const uint4*>(hl);
+    uint4 hh, hl;
+    split_f16x2_sat(v[0] * sigma, v[1] * sigma, hh.x, hl.x);
+    split_f16x2_sat(v[2] * sigma, v[3] * sigma, hh.y, hl.y);
+    split_f16x2_sat(v[4] * sigma, v[5] * sigma, hh.z, hl.z);
+    split_f16x2_sat(v[6] * sigma, v[7] * sigma, hh.w, hl.w);
+    *reinterpret_cast<uint4*>(dst_hi) = hh;
+    *reinterpret_cast<uint4*>(dst_hi + kGLo) = hl;
 }
 
 template <bool INVERSE>
@@ -909,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
             }
 
             // ---- hidden layer: h = act(acc1 + b1) -> fp16 hi | lo, 80-column operand [h | 1 | 0] -------------
-            mbar_wait(&bars->acc1_full, tpar);
+            mbar_wait_sleep(&bars->acc1_full, tpar, 64);
             tc_fence_after();
 #pragma unroll 1
             for (int kc = r4; kc < kHid / 8; kc += 4) {
@@ -945,7 +944,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
             auto flush_w = [&](int c) {
                 // this group's gW2 partial of chunk c: TMEM lane = packed parameter column, 65 columns
                 const uint32_t n = cb + (uint32_t)c, wb = n & 1, wuse = n >> 1;
-                mbar_wait(&bars->w_full[wb], wuse & 1);
+                mbar_wait_sleep(&bars->w_full[wb], wuse & 1, 64);
                 tc_fence_after();
                 const int g = r4 & 1;
                 if (q < 3) {
@@ -984,7 +983,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                 const float go = (live_dim && row_live) ? __ldg(A.g_out + (size_t)(row0 + rloc) * d + hdr->tr_idx[ji]) : 0.f;
                 const float* bb = b2s + ji * kPPad;
                 const float2* bb2 = reinterpret_cast<const float2*>(bb);
-                mbar_wait(&bars->acc_full[buf], buse & 1);
+                mbar_wait_sleep(&bars->acc_full[buf], buse & 1, 32);
                 tc_fence_after();
                 const uint32_t col0 = tmem + lane_sel + kColAcc2 + buf * kChunkN + (uint32_t)g * kPPad;
                 const bool shift = !((hdr->noshift_mask[ji >> 5] >> (ji & 31)) & 1u);
@@ -1020,7 +1019,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                 // G is one buffer: chunk n may be written once the products of chunk n - 1 have retired.  Two
                 // barriers alternate so that a warp (which handles every second chunk) waits on consecutive
                 // phases of ONE barrier: with a single barrier the phase it skips makes parity ambiguous.
-                if (n >= 1) mbar_wait(&bars->g_empty[(n - 1) & 1], ((n - 1) >> 1) & 1);
+                if (n >= 1) mbar_wait_sleep(&bars->g_empty[(n - 1) & 1], ((n - 1) >> 1) & 1, 64);
                 {
                     uint8_t* gdst = gbuf + g_row_off + (uint32_t)(g * (kPPad / 8)) * 128;
                     float w[8];
@@ -1030,15 +1029,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                         for (int i = 0; i < 4; ++i) { w[2 * i] = t[b8 * 4 + i].x; w[2 * i + 1] = t[b8 * 4 + i].y; }
                         put_g8(gdst + b8 * 128, w, sigma);
                     }
-#pragma unroll
-                    for (int b8 = 0; b8 < 2; ++b8) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int di = b8 * 8 + i;
-                            w[i] = (di == kk - 1) ? gu0 : ((di == kk) ? gu1 : 0.f);
-                            if (di == kBins - 1) w[i] = 0.f;
-                        }
-                        put_g8(gdst + (4 + b8) * 128, w, sigma);
+                    // derivative columns 32..47: zero except at the two knots of bin k
+                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(gdst + 4 * 128) = z4;
+                    *reinterpret_cast<uint4*>(gdst + 5 * 128) = z4;
+                    *reinterpret_cast<uint4*>(gdst + kGLo + 4 * 128) = z4;
+                    *reinterpret_cast<uint4*>(gdst + kGLo + 5 * 128) = z4;
+                    uint32_t dh, dl;
+                    split_f16x2_sat(gu0 * sigma, gu1 * sigma, dh, dl);
+                    if (kk > 0) {                                   // derivative kk - 1 (knot kk)
+                        uint8_t* pd = gdst + (4 + ((kk - 1) >> 3)) * 128 + ((kk - 1) & 7) * 2;
+                        *reinterpret_cast<uint16_t*>(pd) = (uint16_t)(dh & 0xffffu);
+                        *reinterpret_cast<uint16_t*>(pd + kGLo) = (uint16_t)(dl & 0xffffu);
+                    }
+                    if (kk < kBins - 1) {                           // derivative kk (knot kk + 1)
+                        uint8_t* pd = gdst + (4 + (kk >> 3)) * 128 + (kk & 7) * 2;
+                        *reinterpret_cast<uint16_t*>(pd) = (uint16_t)(dh >> 16);
+                        *reinterpret_cast<uint16_t*>(pd + kGLo) = (uint16_t)(dl >> 16);
                     }
                 }
                 fence_proxy_async_smem();
@@ -1050,7 +1057,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
             cb += (uint32_t)n_chunks;
 
             // ---- g_pre = g_hidden * act'(h) ----------------------------------------------------------------------
-            mbar_wait(&bars->acch_full, tpar);
+            mbar_wait_sleep(&bars->acch_full, tpar, 64);
             tc_fence_after();
             {
                 const float unscale = s2 * inv_sigma;
