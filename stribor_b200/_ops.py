@@ -185,6 +185,20 @@ def _packed_cols(dev):
     return _PACKED_COLS[k]
 
 
+_INDEX_CACHE = {}
+
+
+def _index_tensors(mask_tuple, dev):
+    """(transformed columns, conditioning columns) of a mask as device index tensors, cached: building them
+    per call is a blocking host-to-device copy in the middle of the backward pass."""
+    k = (mask_tuple, str(dev))
+    if k not in _INDEX_CACHE:
+        tr = [j for j, m in enumerate(mask_tuple) if m == 0]
+        cond = [j for j, m in enumerate(mask_tuple) if m != 0]
+        _INDEX_CACHE[k] = (torch.tensor(tr, dtype=torch.long, device=dev), torch.tensor(cond, dtype=torch.long, device=dev))
+    return _INDEX_CACHE[k]
+
+
 def fused_backward_ok(L: '_lib.StbLayer') -> bool:
     """Does stb_layer_backward differentiate this (packed) layer with its conditioner fused?"""
     return int(_lib.lib().stb_layer_backward_workspace_bytes(C.byref(L), 1)) > 0
@@ -220,8 +234,7 @@ def _fused_conditioner_backward(x, mask, params, packed, meta, fmeta, direction,
         raise NotImplementedError('stribor_b200: this layer has no fused conditioner backward '
                                   '(quadratic spline, 16 bins, MLP[64], dim <= 128 on the tensor-core path)')
     dev = x.device
-    tr_t = torch.tensor(tr, dtype=torch.long, device=dev)
-    cond_t = torch.tensor(cond, dtype=torch.long, device=dev)
+    tr_t, cond_t = _index_tensors(tuple(mask_list), dev)
     hid = W2.shape[1]
     G = _lib.StbLayerGrads()
     if os.environ.get('STRIBOR_B200_TRAIN_GNET') == '1':

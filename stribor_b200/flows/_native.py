@@ -41,12 +41,19 @@ class PackedCache:
     def __init__(self):
         self.key = None
         self.buf = None
+        self.event = None
+        self.seen = set()
 
     def get(self, meta, fmeta, mask, params):
         if not params or not params[0].is_cuda or os.environ.get('STRIBOR_B200_FORCE_GENERIC') == '1':
             return None
         key = (tuple(meta), tuple(fmeta), tuple((p.data_ptr(), p._version) for p in params))
         if key == self.key:
+            if self.buf is not None:
+                cur = torch.cuda.current_stream(self.buf.device)
+                if cur.cuda_stream not in self.seen:      # first use from another stream: order it after the pack
+                    cur.wait_event(self.event)
+                    self.seen.add(cur.cuda_stream)
             return self.buf
         lib = _lib.lib()
         detached = [p.detach() for p in params]
@@ -58,8 +65,11 @@ class PackedCache:
             with torch.cuda.device(buf.device):
                 stream = torch.cuda.current_stream(buf.device)
                 _lib.check(lib.stb_pack_layer(C.byref(L), buf.data_ptr(), stream.cuda_stream))
-                # one-off (weights changed): the image may be consumed from OTHER streams next
-                stream.synchronize()
+                # the image may be consumed from OTHER streams next: they wait on this event at their first
+                # use (no host synchronisation -- the training step repacks every layer after each update)
+                self.event = torch.cuda.Event()
+                self.event.record(stream)
+                self.seen = {stream.cuda_stream}
         self.key, self.buf = key, buf
         return buf
 
