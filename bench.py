@@ -37,6 +37,10 @@ METRIC = 'log_prob samples/s, 8-layer spline coupling d=64'
 L2_BYTES = 126 << 20
 
 
+# NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr: stdout carries the ONE JSON line
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)

@@ -275,9 +275,26 @@ def _fused_conditioner_backward(x, mask, params, packed, meta, fmeta, direction,
         gW2.view(dim, P, hid).index_copy_(0, tr_t, nat[:, :P, :hid].contiguous())
         gb2.view(dim, P).index_copy_(0, tr_t, nat[:, :P, hid].contiguous())
     if cond:
-        xc = x.index_select(1, cond_t)
-        gW1.index_copy_(1, cond_t, g_pre.t() @ xc)
-        g_x.index_add_(1, cond_t, g_pre @ W1.index_select(1, cond_t))
+        contiguous = cond[-1] - cond[0] + 1 == len(cond)            # ordered masks: a column range, no gathers
+        if contiguous:
+            c0, c1 = cond[0], cond[-1] + 1
+            xc, W1c = x[:, c0:c1], W1[:, c0:c1]
+        else:
+            xc, W1c = x.index_select(1, cond_t), W1.index_select(1, cond_t)
+        # g_pre^T x_cond is a [64, n_cond] product over `rows`: split the long reduction into slabs so the
+        # library GEMM fills the GPU (one [64 x 64] output tile would run on a handful of SMs)
+        slab = 4096
+        if rows >= 4 * slab and rows % slab == 0 and contiguous:
+            gw = torch.bmm(g_pre.view(rows // slab, slab, hid).transpose(1, 2),
+                           x.view(rows // slab, slab, dim)[:, :, c0:c1]).sum(0)
+        else:
+            gw = g_pre.t() @ xc
+        if contiguous:
+            gW1[:, c0:c1] = gw
+            g_x[:, c0:c1].addmm_(g_pre, W1c)
+        else:
+            gW1.index_copy_(1, cond_t, gw)
+            g_x.index_add_(1, cond_t, g_pre @ W1c)
     gb1 = g_pre.sum(0)
     return [g_x, x.new_empty(0), x.new_empty(0), gW1, gb1, gW2, gb2]
 
