@@ -237,7 +237,7 @@ def _fused_conditioner_backward(x, mask, params, packed, meta, fmeta, direction,
     tr_t, cond_t = _index_tensors(tuple(mask_list), dev)
     hid = W2.shape[1]
     G = _lib.StbLayerGrads()
-    if os.environ.get('STRIBOR_B200_TRAIN_GNET') == '1':
+    if os.environ.get('STRIBOR_B200_TRAIN_GNET') == '1' and meta[0] == _lib.RQS:
         # two-step variant: the kernel leaves g_net / [hidden | 1]; the last Linear's products are library GEMMs
         g_net = torch.empty(rows, n_tr * G_PAD, dtype=x.dtype, device=dev)
         ws = torch.empty(ws_bytes // 4, dtype=x.dtype, device=dev)

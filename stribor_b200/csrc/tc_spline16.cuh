@@ -456,5 +456,90 @@ __device__ __forceinline__ void rqs16_backward(float2* t, const BinSearch16& bs,
     g_u1 = last ? 0.f : gq[RQ_D1] * (u1 > 20.f ? 1.f : sigmoid_f(u1));
 }
 
+
+// -----------------------------------------------------------------------------------------------
+// gradient of one cubic-spline element (util/cubic_spline.py:99-151,229-238 and its inverse) in the same
+// register form.  t[0..16): softmax numerators in, gradient wrt the raw width / height logits out; ul / ur:
+// raw end-derivative parameters.  The in-bin map is differentiated with the 11-variable duals of
+// stb_grad.cuh (cubic_bin_dual: three neighbouring sizes per axis, the two cumulative sums, the end
+// derivatives); a size W_i receives  g_cw (i < k)  +  g_wp (i = k - 1)  +  g_wk (i = k)  +  g_wn (i = k + 1).
+// u: the element on the unit box; g_out / g_x refer to the un-normalised coordinate (span = hi - lo).
+template <bool INVERSE>
+__device__ __forceinline__ void cubic16_backward(float2* t, const BinSearch16& bs, float2 ee, float2 eo, float ul,
+                                                 float ur, float lo, float hi, float u, float g_out, float g_ld,
+                                                 float& g_x, float& g_ul, float& g_ur) {
+    const float span = hi - lo;
+    const int k = bs.k;
+    // numerators of bins k - 1, k, k + 1 (0 beyond the ends): same select trees as cubic16_locate
+    float2 am[4], bm[2], ap[4], bp[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        am[i] = sel2(bs.p3, t[2 * (i + 4) - 1], (i == 0) ? f2(0.f) : t[2 * i - 1]);
+        ap[i] = sel2(bs.p3, (i + 4 == 7) ? f2(0.f) : t[2 * (i + 4) + 2], t[2 * i + 2]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        bm[i] = sel2(bs.p2, am[i + 2], am[i]);
+        bp[i] = sel2(bs.p2, ap[i + 2], ap[i]);
+    }
+    const float2 prev_odd = sel2(bs.p1, bm[1], bm[0]);
+    const float2 next_even = sel2(bs.p1, bp[1], bp[0]);
+    const float2 ep = sel2(bs.p0, ee, prev_odd), ek = sel2(bs.p0, eo, ee), en = sel2(bs.p0, next_even, eo);
+    const float2 mn = f2(STB_CUB_MIN);
+    const float2 sp = __ffma2_rn(bs.c, ep, mn), sk = __ffma2_rn(bs.c, ek, mn), sn = __ffma2_rn(bs.c, en, mn);
+    const float2 cum = __ffma2_rn(bs.c, bs.Ek, f2((float)k * STB_CUB_MIN));
+    float ue = u;
+    if (INVERSE) {
+        CubSel s;
+        s.k = k; s.wp = sp.x; s.hp = sp.y; s.wk = sk.x; s.hk = sk.y; s.wn = sn.x; s.hn = sn.y; s.cw = cum.x; s.ch = cum.y;
+        const CubBin b = cubic16_bin(s, ul, ur);
+        float ld_own;
+        ue = cubic_inverse_in_bin(b, u, ld_own);
+    }
+    const bool first = (k == 0), last = (k == kBins - 1);
+    Dual<CU_N> S, L;
+    cubic_bin_dual(k, kBins, ue, first ? 1.f : sp.x, sk.x, last ? 1.f : sn.x, first ? 1.f : sp.y, sk.y,
+                   last ? 1.f : sn.y, cum.x, cum.y, ul, ur, S, L);
+    float gq[CU_N];
+    if (!INVERSE) {
+#pragma unroll
+        for (int i = 0; i < CU_N; ++i) gq[i] = g_out * span * S.d[i] + g_ld * L.d[i];
+        g_x = gq[CU_U] / span;
+    } else {
+        const float xo = ue * span + lo;
+        const float gl = (xo >= lo && xo <= hi) ? g_ld : 0.f;
+        const float gu = (g_out * span - gl * L.d[CU_U]) / S.d[CU_U];
+        gq[CU_U] = gu;
+#pragma unroll
+        for (int i = 1; i < CU_N; ++i) gq[i] = -S.d[i] * gu - gl * L.d[i];
+        g_x = gu / span;
+    }
+    const float2 g_c = f2(gq[CU_CW], gq[CU_CH]);
+    const float2 g_p = first ? f2(0.f) : f2(gq[CU_WP], gq[CU_HP]);
+    const float2 g_k = f2(gq[CU_WK], gq[CU_HK]);
+    const float2 g_n = last ? f2(0.f) : f2(gq[CU_WN], gq[CU_HN]);
+    const float2 g_cp = __fadd2_rn(g_c, g_p);                        // bin k - 1: cumulative sum and left neighbour
+    const float inv_scale = 1.f / (1.f - STB_CUB_MIN * (float)kBins);
+    // sum_j s_j g_j with s_j = e_j / sum:  E_k g_c + e_(k-1) g_p + e_k g_k + e_(k+1) g_n
+    float2 acc = __fmul2_rn(bs.Ek, g_c);
+    acc = __ffma2_rn(ep, g_p, acc);
+    acc = __ffma2_rn(ek, g_k, acc);
+    acc = __ffma2_rn(en, g_n, acc);
+    const float2 dot = __fmul2_rn(__fmul2_rn(bs.c, f2(inv_scale)), acc);
+    const float2 ndot = f2(-dot.x, -dot.y);
+    const float2 cA = __fmul2_rn(bs.c, __fadd2_rn(g_c, ndot));       // i < k - 1
+    const float2 cB = __fmul2_rn(bs.c, __fadd2_rn(g_cp, ndot));      // i = k - 1
+    const float2 cC = __fmul2_rn(bs.c, __fadd2_rn(g_k, ndot));       // i = k
+    const float2 cD = __fmul2_rn(bs.c, __fadd2_rn(g_n, ndot));       // i = k + 1
+    const float2 cE = __fmul2_rn(bs.c, ndot);                        // beyond
+#pragma unroll
+    for (int i = 0; i < kBins; ++i) {
+        const float2 cf = (i < k - 1) ? cA : ((i == k - 1) ? cB : ((i == k) ? cC : ((i == k + 1) ? cD : cE)));
+        t[i] = __fmul2_rn(t[i], cf);
+    }
+    g_ul = first ? gq[CU_UL] : 0.f;
+    g_ur = last ? gq[CU_UR] : 0.f;
+}
+
 }  // namespace sp16
 }  // namespace stb

@@ -616,7 +616,7 @@ __device__ __forceinline__ void put_g8(uint8_t* dst_hi, const float* v, float si
     *reinterpret_cast<uint4*>(dst_hi + kGLo) = hl;
 }
 
-template <bool INVERSE>
+template <int KIND, bool INVERSE>
 __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem + kSmXs);
@@ -995,24 +995,44 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                 for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
                 softmax16_num2(t, shift);
                 float2 ee, eo;
-                const BinSearch16 bs = bin_search16<INVERSE>(t, STB_RQS_MIN, (xv - lo) * inv_span, ee, eo);
-                float dd[16];
-                tmem_ld16(col0 + 2 * kBins, dd);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
-                float r0, r1;
-                pick_pair16(dd, bs.k, r0, r1);
-                const int kk = bs.k;
-                const float u0 = (kk == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + (kk > 0 ? kk - 1 : 0)]);
-                const float u1 = (kk == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + (kk < kBins - 1 ? kk : 0)]);
                 float gx = go, gu0 = 0.f, gu1 = 0.f;
-                if (inside) {
-                    rqs16_backward<INVERSE>(t, bs, ee, eo, u0, u1, lo, hi, xv, go, g_ld, gx, gu0, gu1);
-                } else {
+                int kk;
+                if (KIND == STB_RQS) {
+                    const BinSearch16 bs = bin_search16<INVERSE>(t, STB_RQS_MIN, (xv - lo) * inv_span, ee, eo);
+                    float dd[16];
+                    tmem_ld16(col0 + 2 * kBins, dd);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                    float r0, r1;
+                    pick_pair16(dd, bs.k, r0, r1);
+                    kk = bs.k;
+                    const float u0 = (kk == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + (kk > 0 ? kk - 1 : 0)]);
+                    const float u1 = (kk == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + (kk < kBins - 1 ? kk : 0)]);
+                    if (inside) {
+                        rqs16_backward<INVERSE>(t, bs, ee, eo, u0, u1, lo, hi, xv, go, g_ld, gx, gu0, gu1);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < kBins; ++i) t[i] = f2(0.f);
+                        for (int i = 0; i < kBins; ++i) t[i] = f2(0.f);
+                    }
+                } else {
+                    const float u = (xv - lo) / (hi - lo);
+                    const BinSearch16 bs = bin_search16<INVERSE>(t, STB_CUB_MIN, u, ee, eo);
+                    float dd[8];
+                    tmem_ld8(col0 + 2 * kBins, dd);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                    kk = bs.k;
+                    const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
+                    if (inside) {
+                        cubic16_backward<INVERSE>(t, bs, ee, eo, ul, ur, lo, hi, u, go, g_ld, gx, gu0, gu1);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kBins; ++i) t[i] = f2(0.f);
+                    }
                 }
                 if (live_dim) xrow[ji] = gx;                       // x of this element is dead: reuse for g_x
                 if (prev >= 0) flush_w(prev);
@@ -1037,15 +1057,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                     *reinterpret_cast<uint4*>(gdst + kGLo + 5 * 128) = z4;
                     uint32_t dh, dl;
                     split_f16x2_sat(gu0 * sigma, gu1 * sigma, dh, dl);
-                    if (kk > 0) {                                   // derivative kk - 1 (knot kk)
-                        uint8_t* pd = gdst + (4 + ((kk - 1) >> 3)) * 128 + ((kk - 1) & 7) * 2;
-                        *reinterpret_cast<uint16_t*>(pd) = (uint16_t)(dh & 0xffffu);
-                        *reinterpret_cast<uint16_t*>(pd + kGLo) = (uint16_t)(dl & 0xffffu);
-                    }
-                    if (kk < kBins - 1) {                           // derivative kk (knot kk + 1)
-                        uint8_t* pd = gdst + (4 + (kk >> 3)) * 128 + (kk & 7) * 2;
-                        *reinterpret_cast<uint16_t*>(pd) = (uint16_t)(dh >> 16);
-                        *reinterpret_cast<uint16_t*>(pd + kGLo) = (uint16_t)(dl >> 16);
+                    if (KIND == STB_RQS) {
+                        if (kk > 0) {                               // derivative kk - 1 (knot kk)
+                            uint8_t* pd = gdst + (4 + ((kk - 1) >> 3)) * 128 + ((kk - 1) & 7) * 2;
+                            *reinterpret_cast<uint16_t*>(pd) = (uint16_t)(dh & 0xffffu);
+                            *reinterpret_cast<uint16_t*>(pd + kGLo) = (uint16_t)(dl & 0xffffu);
+                        }
+                        if (kk < kBins - 1) {                       // derivative kk (knot kk + 1)
+                            uint8_t* pd = gdst + (4 + (kk >> 3)) * 128 + (kk & 7) * 2;
+                            *reinterpret_cast<uint16_t*>(pd) = (uint16_t)(dh >> 16);
+                            *reinterpret_cast<uint16_t*>(pd + kGLo) = (uint16_t)(dl >> 16);
+                        }
+                    } else {                                        // cubic: columns 32, 33 = the end derivatives
+                        *reinterpret_cast<uint32_t*>(gdst + 4 * 128) = dh;
+                        *reinterpret_cast<uint32_t*>(gdst + kGLo + 4 * 128) = dl;
                     }
                 }
                 fence_proxy_async_smem();
@@ -1297,7 +1322,7 @@ int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const 
     return tcw_launch(kern, A, tiles, stream, "tc_wide_kernel");
 }
 
-bool tcw_backward_supported(const stb_layer* L) { return tcw_layer_supported(L) && L->kind == STB_RQS; }
+bool tcw_backward_supported(const stb_layer* L) { return tcw_layer_supported(L); }   // quadratic and cubic (fused variant)
 
 int tcw_layer_backward(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
                        const float* g_ldj, float* g_x, float* g_net, float* hidden, int64_t rows,
@@ -1328,7 +1353,6 @@ uint64_t tcw_train_workspace_floats(const stb_layer* L, int64_t rows) {
 int tcw_layer_backward_fused(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
                              const float* g_ldj, float* g_x, float* workspace, int64_t rows, cudaStream_t stream) {
     using namespace tcw;
-    if (L->kind != STB_RQS) return set_error(STB_ENOTSUP, "tensor-core backward is built for the quadratic spline");
     const int act = L->net.activation;
     if (act != STB_ACT_TANH && act != STB_ACT_SIGMOID && act != STB_ACT_RELU)
         return set_error(STB_ENOTSUP, "fused conditioner backward: Tanh / Sigmoid / ReLU hidden activation only");
@@ -1342,7 +1366,10 @@ int tcw_layer_backward_fused(const stb_layer* L, const void* image, int directio
     const long long tiles = (rows + kTileRows - 1) / kTileRows;
     if (tiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
     A.n_tiles = (int)tiles;
-    void (*kern)(train::Args) = (direction == STB_INVERSE) ? train::tc_wide_train_kernel<true> : train::tc_wide_train_kernel<false>;
+    const bool inv = direction == STB_INVERSE;
+    void (*kern)(train::Args);
+    if (L->kind == STB_RQS) kern = inv ? train::tc_wide_train_kernel<STB_RQS, true> : train::tc_wide_train_kernel<STB_RQS, false>;
+    else kern = inv ? train::tc_wide_train_kernel<STB_CUBIC, true> : train::tc_wide_train_kernel<STB_CUBIC, false>;
     static thread_local int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;

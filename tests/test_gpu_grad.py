@@ -248,3 +248,39 @@ def test_fused_backward_forward_direction_and_output_gradient(monkeypatch):
     for i, (g, l, h) in enumerate(zip(res[False][1], leaves, res[True][1])):
         close(g, l.grad, f'parameter {i} vs oracle64')
         close(g, h, f'parameter {i} vs hybrid')
+
+
+@pytest.mark.parametrize('d,masks,rows', [(128, cases.ALT, 300), (64, ('parity_even', 'parity_odd'), 257), (30, cases.ALT, 130)])
+def test_fused_conditioner_backward_cubic(d, masks, rows, monkeypatch):
+    """Cubic spline couplings through the fused backward kernel (11-variable duals in registers) vs the
+    hybrid path and autograd through the fp64 oracle.  The cubic map has kinks in its parameters (min / abs
+    in the interior derivatives, cubic_spline.py:119-130) and an ill-conditioned inverse, so a
+    small fraction of elements may differ; the bulk must agree."""
+    case = cases._mk_flow('cubic', d, [64], 2, 16, rows, 6100 + d, masks=masks, lower=-4., upper=4., scale=1.5)()
+    spec, x = case['spec'], case['inputs']['x']
+    x[1, 0] = 5.0
+    loss_f, gx_f, gp_f, _ = _nll_grads(spec, x, monkeypatch, hybrid=False)
+    loss_h, gx_h, gp_h, _ = _nll_grads(spec, x, monkeypatch, hybrid=True)
+    s64 = O.spec_to(spec, torch.float64)
+    leaves = []
+    for layer in s64:
+        net = layer['transform']['net']
+        for w, b in zip(net['weights'], net['biases']):
+            leaves += [w.requires_grad_(True), b.requires_grad_(True)]
+    x64 = x.double().clone().requires_grad_(True)
+    loss64 = -O.flow_log_prob(s64, x64).mean()
+    loss64.backward()
+    assert abs(loss_f - loss_h) < 1e-4 * abs(loss_h) + 1e-4
+
+    def close(got, want, what, frac):
+        want = want.double()
+        scale = want.abs().max().clamp_min(1e-12)
+        err = (got.double() - want).abs()
+        bad = err > 2e-3 * want.abs() + 2e-4 * scale
+        assert bad.float().mean().item() <= frac, f'{what}: {bad.float().mean().item():.3%} outside tolerance, max err {err.max().item():.3e} (scale {scale.item():.3e})'
+
+    close(gx_f, gx_h, 'grad_x vs hybrid', 1e-2)
+    close(gx_f, x64.grad, 'grad_x vs oracle64', 1e-2)
+    for i, (g, l, h) in enumerate(zip(gp_f, leaves, gp_h)):
+        close(g, h, f'grad of parameter {i} vs hybrid', 1e-2)
+        close(g, l.grad, f'grad of parameter {i} vs oracle64', 1e-2)
