@@ -284,3 +284,46 @@ def test_fused_conditioner_backward_cubic(d, masks, rows, monkeypatch):
     for i, (g, l, h) in enumerate(zip(gp_f, leaves, gp_h)):
         close(g, h, f'grad of parameter {i} vs hybrid', 1e-2)
         close(g, l.grad, f'grad of parameter {i} vs oracle64', 1e-2)
+
+
+@pytest.mark.parametrize('kind', ['quadratic', 'cubic'])
+def test_wide_kernels_odd_chunk_count_many_tiles(kind, monkeypatch):
+    """33 transformed dims -> 17 weight chunks per tile, and more tiles than SMs: every CTA runs several
+    tiles, so the chunk -> (TMEM buffer, warp group, barrier phase) assignment flips from tile to tile.
+    Forward: tensor-core path == CUDA-core path; backward: fused kernel == two-step variant (same bins by
+    construction, so the comparison is tight) and == hybrid on the bulk."""
+    d, rows = 66, 45000
+    case = cases._mk_flow(kind, d, [64], 2, 16, rows, 7300, masks=('parity_even', 'parity_odd'), lower=-4., upper=4., scale=1.5)()
+    spec, x = case['spec'], case['inputs']['x']
+    # forward parity between the two CUDA paths
+    res = {}
+    for force in ('0', '1'):
+        monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', force)
+        layers = [l.to(DEV) for l in layers_from_spec(spec)]
+        flow = st.NormalizingFlow(st.UnitNormal(d), layers)
+        with torch.no_grad():
+            res[force] = flow.log_prob(x.to(DEV)).cpu()
+    monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', '0')
+    bad = ((res['0'] - res['1']).abs() > 1e-4 + 1e-5 * res['1'].abs()).float().mean().item()
+    assert bad <= (5e-3 if kind == 'cubic' else 1e-4), f'log_prob: {bad:.3%} of rows differ between the tensor-core and CUDA-core paths'
+    # gradients
+    loss_f, gx_f, gp_f, _ = _nll_grads(spec, x, monkeypatch, hybrid=False)
+    loss_h, gx_h, gp_h, _ = _nll_grads(spec, x, monkeypatch, hybrid=True)
+    assert abs(loss_f - loss_h) < 1e-4 * abs(loss_h) + 1e-4
+
+    def close(got, want, what, rtol, floor, frac):
+        want = want.double()
+        scale = want.abs().max().clamp_min(1e-12)
+        err = (got.double() - want).abs()
+        bad = err > rtol * want.abs() + floor * scale
+        assert bad.float().mean().item() <= frac, f'{what}: {bad.float().mean().item():.3%} outside tolerance, max err {err.max().item():.3e} (scale {scale.item():.3e})'
+
+    if kind == 'quadratic':
+        loss_g, gx_g, gp_g, _ = _nll_grads(spec, x, monkeypatch, hybrid=False, gnet=True)
+        close(gx_f, gx_g, 'grad_x fused vs two-step', 1e-3, 1e-4, 1e-5)
+        for i, (a, b) in enumerate(zip(gp_f, gp_g)):
+            close(a, b, f'parameter {i} fused vs two-step', 1e-3, 2e-4, 1e-5)
+    rows_bad = ((gx_f - gx_h).abs() > 1e-3 * gx_h.abs() + 1e-4 * gx_h.abs().max()).any(dim=1).float().mean().item()
+    assert rows_bad <= (2e-2 if kind == 'cubic' else 1e-3), f'{rows_bad:.3%} of rows: grad_x differs from the hybrid path'
+    for i, (a, b) in enumerate(zip(gp_f, gp_h)):
+        close(a, b, f'parameter {i} fused vs hybrid', 1e-2, 2e-2 if kind == 'cubic' else 5e-3, 1e-3)
