@@ -164,26 +164,29 @@ int stb_unit_normal_log_prob(const float* x, float* lp, int accumulate, int32_t 
  * Two families are built:
  *  (1) n_linear == 0 (row_out / const_out): the element-wise gradient -- g_x and grads->g_row_out are
  *      written; the caller runs a conditioner through autograd (library GEMMs) around it.
- *  (2) n_linear > 0 with a packed image (stb_pack_layer), quadratic spline, 16 bins, MLP[64], dim <= 128,
+ *  (2) n_linear > 0 with a packed image (stb_pack_layer), quadratic or cubic spline, 16 bins, MLP[64], dim <= 128,
  *      Tanh / Sigmoid / ReLU hidden activation: the conditioner is RECOMPUTED on the tensor cores from the
  *      saved input and the spline differentiated in registers (tc_wide.cu).  g_x receives the transformed
  *      dims' gradient and g_out for the pass-through dims (the conditioner's contribution to them is
  *      g_pre W1 over the conditioning columns, see below).  With W = stb_layer_backward_workspace_bytes:
- *        grads == NULL or grads->g_row_out == NULL  (fully fused, the training path)
- *          workspace[0 : rows*64]            g_pre: gradient wrt the hidden pre-activation
- *          workspace[rows*72 : rows*72 + 64*48*72]  ACCUMULATED (caller zeroes): image [n_tr_pad*48, 72] of
- *                                            [gW_last | gb_last | 0..] for the transformed dims' rows of the
- *                                            last Linear, 48 rows per transformed dim in packed column
- *                                            order (w_0, h_0, w_1, h_1, ... w_15, h_15, d_0..d_14, pad);
- *                                            summed over row tiles with atomics (order not deterministic)
- *        grads->g_row_out != NULL  (two-step variant, exact fp32 products left to the caller)
+ *        grads == NULL  (everything fused -- the training path): g_x is COMPLETE (pass-through dims include
+ *          the conditioner's contribution); at float offset rows*72 of the workspace, all ACCUMULATED into
+ *          (caller zeroes), summed over row tiles with atomics (order not deterministic):
+ *            [n_tr_pad*48, 72]   [gW_last | gb_last | 0..] for the transformed dims' rows of the last Linear,
+ *                                48 rows per transformed dim in packed column order
+ *                                (w_0, h_0, w_1, h_1, ... w_15, h_15, d_0..d_14 (cubic: left, right), pad)
+ *            [64, 64]            gW_first over the conditioning SLOTS (slot k = k-th pass-through dim)
+ *            [64]                gb_first
+ *        grads != NULL, grads->g_row_out == NULL: as above without the first Linear -- workspace[0 : rows*64]
+ *          receives g_pre (gradient wrt the hidden pre-activation), g_x carries g_out on the pass-through dims,
+ *          and the caller forms gW_first[:, cond] = g_pre^T x[:, cond], gb_first = sum g_pre,
+ *          g_x[:, cond] += g_pre W_first[:, cond]
+ *        grads->g_row_out != NULL  (two-step variant, quadratic only: exact fp32 products left to the caller)
  *          grads->g_row_out [rows, n_tr*48]  gradient wrt the network output of the transformed dims,
  *                                            natural order [w(16) | h(16) | d(15) | 0]
- *          workspace[0 : rows*72]            [hidden(64) | 1 | 0 x 7] per row
- *      (two-step: the caller also forms g_pre = (g_row_out W_last) * act.(hidden).)  In both cases the first
- *      Linear.s gradients are K = 64 products the caller forms:
- *      gW_first[:, cond] = g_pre^T x[:, cond], gb_first = sum g_pre, g_x[:, cond] += g_pre W_first[:, cond].
- *      gW / gb pointers of stb_layer_grads are reserved for a later round.
+ *          workspace[0 : rows*72]            [hidden(64) | 1 | 0 x 7] per row; the caller forms
+ *                                            g_pre = (g_row_out W_last) * act'(hidden) and all four products
+ *      gW / gb pointers of stb_layer_grads are not used by this family.
  *      Any other layer with n_linear > 0 returns STB_ENOTSUP. */
 typedef struct stb_layer_grads {
     float* gW[STB_MAX_LINEAR];

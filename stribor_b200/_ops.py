@@ -261,19 +261,30 @@ def _fused_conditioner_backward(x, mask, params, packed, meta, fmeta, direction,
         else:
             g_pre = g_h * (h > 0).to(g_h.dtype)
     else:
-        # fully fused: g_pre [rows, 64] and the [gW2 | gb2] image (packed column order) come out of the kernel
+        # fused: the [gW2 | gb2] image (packed column order) comes out of the kernel; by default also the first
+        # Linear's gradients and the complete g_x (STRIBOR_B200_TRAIN_W1_LIB=1: those three K = 64 products as
+        # library GEMMs from g_pre, the previous arrangement)
+        w1_in_kernel = os.environ.get('STRIBOR_B200_TRAIN_W1_LIB') != '1'
         ws = torch.empty(ws_bytes // 4, dtype=x.dtype, device=dev)
         img = ws[rows * H_AUG:]
         img.zero_()
         with torch.cuda.device(dev):
             rc = lib.stb_layer_backward(C.byref(L), direction, x.data_ptr(), None, None, g_y.data_ptr(), _dp(g_ldj),
-                                        g_x.data_ptr(), None, None, C.byref(G), ws.data_ptr(), rows, _stream(x))
+                                        g_x.data_ptr(), None, None, None if w1_in_kernel else C.byref(G),
+                                        ws.data_ptr(), rows, _stream(x))
         _lib.check(rc)
-        g_pre = ws[:rows * hid].view(rows, hid)
         n_pad = 2 * ((n_tr + 1) // 2)
-        nat = img.view(-1, G_PAD, H_AUG)[:n_pad].index_select(1, _packed_cols(dev))[:n_tr]   # natural parameter order
+        n_img = 64 * G_PAD * H_AUG
+        nat = img[:n_img].view(-1, G_PAD, H_AUG)[:n_pad].index_select(1, _packed_cols(dev))[:n_tr]   # natural parameter order
         gW2.view(dim, P, hid).index_copy_(0, tr_t, nat[:, :P, :hid].contiguous())
         gb2.view(dim, P).index_copy_(0, tr_t, nat[:, :P, hid].contiguous())
+        if w1_in_kernel:
+            w1c = img[n_img:n_img + hid * 64].view(hid, 64)
+            if cond:
+                gW1.index_copy_(1, cond_t, w1c[:, :len(cond)])
+            gb1 = img[n_img + hid * 64:n_img + hid * 64 + hid].clone()
+            return [g_x, x.new_empty(0), x.new_empty(0), gW1, gb1, gW2, gb2]
+        g_pre = ws[:rows * hid].view(rows, hid)
     if cond:
         contiguous = cond[-1] - cond[0] + 1 == len(cond)            # ordered masks: a column range, no gathers
         if contiguous:

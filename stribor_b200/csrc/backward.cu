@@ -186,12 +186,14 @@ int layer_backward(const stb_layer* L, int direction, const float* x, const floa
         if (rows < 0 || !x || !g_out || !g_x || !workspace) return set_error(STB_EINVAL, "bad argument");
         if (rows == 0) return STB_OK;
         if (!grads || !grads->g_row_out)
-            // fully fused: the gradient products of the last Linear run in the same kernel.  workspace =
-            // [g_pre rows x 64 (gradient wrt the hidden pre-activation) ... | at float offset rows * 72: the
-            // [n_chunks * 96, 72] image of [gW | gb] of the last Linear's transformed-dim rows in packed
-            // column order, ACCUMULATED into (caller zeroes)]
+            // fused variants (the training path): the last Linear's gradient products run in the same kernel.
+            //   grads == NULL: the first Linear's too -- g_x is complete; workspace at float offset rows * 72:
+            //     [n_chunks * 96, 72] image of [gW_last | gb_last] (packed column order), then gW_first over the
+            //     conditioning slots [64 hidden, 64 slots], then gb_first [64]; all ACCUMULATED (caller zeroes)
+            //   grads != NULL (g_row_out == NULL): workspace[0 : rows * 64] = g_pre and the image; the first
+            //     Linear's three K = 64 products are left to the caller
             return tcw_layer_backward_fused(L, tcw_image(L), direction, x, g_out, g_ldj, g_x,
-                                            static_cast<float*>(workspace), rows, stream);
+                                            static_cast<float*>(workspace), grads == nullptr, rows, stream);
         return tcw_layer_backward(L, tcw_image(L), direction, x, g_out, g_ldj, g_x, grads->g_row_out,
                                   static_cast<float*>(workspace), rows, stream);
     }

@@ -40,7 +40,8 @@ int tcw_layer_backward(const stb_layer* L, const void* image, int direction, con
                        cudaStream_t stream);
 uint64_t tcw_train_workspace_floats(const stb_layer* L, int64_t rows);
 int tcw_layer_backward_fused(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
-                             const float* g_ldj, float* g_x, float* workspace, int64_t rows, cudaStream_t stream);
+                             const float* g_ldj, float* g_x, float* workspace, int first_linear, int64_t rows,
+                             cudaStream_t stream);
 inline const void* tcw_image(const stb_layer* L) {
     return static_cast<const uint8_t*>(L->packed) + (tc_layer_supported(L) ? tc_packed_bytes(L) : 0);
 }

@@ -580,6 +580,7 @@ struct Bars {
     uint64_t g_ready, g_empty[2];
     uint64_t w_full[2], w_empty[2];
     uint64_t acch_full;
+    uint64_t w1_ready, d_full;
     uint32_t tmem_base;
     uint32_t tile_max;
 };
@@ -588,6 +589,7 @@ constexpr uint32_t kColAcc1 = 0;
 constexpr uint32_t kColAcc2 = 64;                // + buf * 96
 constexpr uint32_t kColAccH = 256;
 constexpr uint32_t kColAccW = 320;               // + wb * 80
+constexpr uint32_t kColD1 = 64, kColD2 = 128;    // tile end, over the (idle) chunk accumulators
 
 struct Args {
     const uint8_t* packed;
@@ -595,8 +597,10 @@ struct Args {
     const float* g_out;
     const float* g_ldj;
     float* g_x;
-    float* g_pre;            // [rows, 64]
+    float* g_pre;            // [rows, 64] (nullable when the first Linear's products run in the kernel)
     float* g_w2;             // [n_chunks * 96, 72], accumulated
+    float* g_w1;             // nullable: [64 hidden, 64 conditioning slots], accumulated -> first Linear fused too
+    float* g_b1;             // [64], accumulated (with g_w1)
     float lower, upper;
     long long rows;
     int n_tiles;
@@ -644,6 +648,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
         mbar_init(&bars->g_empty[0], 1);
         mbar_init(&bars->g_empty[1], 1);
         mbar_init(&bars->acch_full, 1);
+        mbar_init(&bars->w1_ready, kEpiWarps);
+        mbar_init(&bars->d_full, 1);
         bars->tile_max = 0;
         fence_mbar_init();
     }
@@ -665,17 +671,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
     const float s2 = hdr->s2;
     const float s2l = s2 * 1.4426950408889634f;
     const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const bool full = A.g_w1 != nullptr;                  // the first Linear's gradient products run here too
+    const int n_items = n_chunks + (full ? 1 : 0);        // ring items after the leading W1: chunks (+ W1 again)
 
     if (warp == 0) {
         // ======================= producer =========================================================
         if (lane == 0) {
             uint32_t cc = 0;
             for (int it = 0; it < my_tiles; ++it) {
-                for (int c = -1; c < n_chunks; ++c, ++cc) {
+                for (int c = -1; c < n_items; ++c, ++cc) {
                     const uint32_t st = cc % kStages, use = cc / kStages;
                     mbar_wait_relaxed(&bars->b_empty[st], (use & 1) ^ 1);
                     mbar_arrive_expect_tx(&bars->b_full[st], kChunkBytes);
-                    const uint8_t* src = (c < 0) ? A.packed + kOffW1 : A.packed + kOffW2 + (size_t)c * kChunkBytes;
+                    const uint8_t* src = (c < 0 || c == n_chunks) ? A.packed + kOffW1 : A.packed + kOffW2 + (size_t)c * kChunkBytes;
                     bulk_g2s(bst + st * kChunkBytes, src, kChunkBytes, &bars->b_full[st]);
                 }
             }
@@ -784,7 +792,40 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                     if (c + 3 < n_chunks) issue_f(c + 3);
                 }
                 umma_commit(&bars->acch_full);
-                cc += (uint32_t)n_chunks;
+                if (full) {
+                    // first Linear: g_x[cond] = g_pre . W1c and gW1c = g_pre^T . x_cond, all operands bf16x3 (exact
+                    // splits, fp32 range: no scaling), the 8 leading partial products, smallest first.
+                    //   D1 [128 x 64 slots] : A = g_pre K-major (G buffer), B = the W1 image read MN-major
+                    //   D2 [64 hid (of 128) x 64 slots] : A = g_pre MN-major, B = the re-split x_cond MN-major
+                    const uint32_t ci = cc0 + (uint32_t)n_chunks, st = ci % kStages, use = ci / kStages;
+                    mbar_wait_relaxed(&bars->b_full[st], use & 1);
+                    mbar_wait_relaxed(&bars->w1_ready, tpar);
+                    tc_fence_after();
+                    const uint32_t w1 = smem_u32(bst + st * kChunkBytes), xc = smem_u32(abuf);
+                    const uint32_t idesc_d1 = make_idesc(FMT_BF16, 128, kHid) | kIdescBMajorMN;
+                    const uint32_t idesc_d2 = make_idesc(FMT_BF16, 128, kK1) | kIdescAMajorMN | kIdescBMajorMN;
+                    uint32_t acc1 = 0, acc2 = 0;
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const int pa = (p == 0 || p == 3 || p == 6) ? 1 : ((p == 1 || p == 4) ? 2 : 0);
+                        const int pb = (p == 0 || p == 2) ? 2 : ((p == 1 || p == 3 || p == 5) ? 1 : 0);
+#pragma unroll
+                        for (int ks = 0; ks < kHid / 16; ++ks) {
+                            umma_f16(tmem + kColD1, make_smem_desc(g_hi + pa * kA1Part + ks * 256, 128, 1024),
+                                     make_smem_desc(w1 + pb * kW1Part + ks * 2048, 1024, 128), idesc_d1, acc1);
+                            acc1 = 1;
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < kTileRows / 16; ++ks) {
+                            umma_f16(tmem + kColD2, make_smem_desc(g_hi + pa * kA1Part + ks * 2048, 1024, 128),
+                                     make_smem_desc(xc + pb * kA1Part + ks * 2048, 1024, 128), idesc_d2, acc2);
+                            acc2 = 1;
+                        }
+                    }
+                    umma_commit(&bars->d_full);
+                    umma_commit(&bars->b_empty[st]);
+                }
+                cc += (uint32_t)n_items;
                 cb += (uint32_t)n_chunks;
             }
         }
@@ -815,7 +856,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                 const float* xg = A.x + row0 * d;
                 const float* gg = A.g_out + row0 * d;
                 float* og = A.g_x + row0 * d;
-                const bool copy_pass = static_cast<const float*>(A.g_x) != A.g_out;
+                const bool copy_pass = !full && static_cast<const float*>(A.g_x) != A.g_out;   // full: written at the tile end
                 const bool vec = ((d & 3) == 0) && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0) &&
                                  ((reinterpret_cast<uintptr_t>(gg) & 15) == 0) && ((reinterpret_cast<uintptr_t>(og) & 15) == 0);
                 if (vec) {
@@ -1105,11 +1146,86 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                                        : ((act == STB_ACT_SIGMOID) ? h * (1.f - h) : ((h > 0.f) ? 1.f : 0.f));
                         v[i] = v[i] * unscale * da;
                     }
-                    if (row_live) stg256(A.g_pre + (size_t)(row0 + rloc) * kHid + kc * 8, v);
+                    if (row_live && A.g_pre != nullptr) stg256(A.g_pre + (size_t)(row0 + rloc) * kHid + kc * 8, v);
+                    if (full) {
+                        // bf16x3 parts of g_pre, K-major [128 x 64] in the (now idle) G buffer
+                        __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) split_bf16x3(v[i], q0[i], q1[i], q2[i]);
+                        uint8_t* dst = gbuf + (uint32_t)(rloc >> 3) * 1024 + (uint32_t)(rloc & 7) * 16 + kc * 128;
+                        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(q0);
+                        *reinterpret_cast<uint4*>(dst + kA1Part) = *reinterpret_cast<const uint4*>(q1);
+                        *reinterpret_cast<uint4*>(dst + 2 * kA1Part) = *reinterpret_cast<const uint4*>(q2);
+                        // gb1 += column sums over the warp's 32 rows
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float sum = v[i];
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                            if (lane == i) atomicAdd(A.g_b1 + kc * 8 + i, sum);
+                        }
+                    }
                 }
             }
             tc_fence_before();
             named_bar_sync(1, kEpiThreads);
+            if (full) {
+                // ---- conditioning columns again: x_cond as bf16x3 (its buffer held h meanwhile) --------------------
+                {
+                    const float* xg = A.x + row0 * d;
+                    const int n = kTileRows * d;
+                    for (int i = etid; i < n; i += kEpiThreads) {
+                        const int r = i / d, c = i - r * d;
+                        const int m = hdr->colmap[c];
+                        if (m >= 0) {
+                            const float v = (r < nrows) ? __ldg(xg + i) : 0.f;
+                            __nv_bfloat16 p0, p1, p2;
+                            split_bf16x3(v, p0, p1, p2);
+                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
+                            *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
+                            *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
+                            *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                        }
+                    }
+                    const int npad = kK1 - n_cond;               // all 64 slots are read as N
+                    for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
+                        const int r = i / npad, m = n_cond + (i - r * npad);
+                        uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
+                        *reinterpret_cast<uint16_t*>(dst) = 0;
+                        *reinterpret_cast<uint16_t*>(dst + kA1Part) = 0;
+                        *reinterpret_cast<uint16_t*>(dst + 2 * kA1Part) = 0;
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->w1_ready);
+                mbar_wait_sleep(&bars->d_full, tpar, 64);
+                tc_fence_after();
+                {
+                    float v[16];
+                    // g_x[cond] = g_out[cond] + g_pre . W1c : thread = row, 16 conditioning slots per warp
+                    tmem_ld16(tmem + lane_sel + kColD1 + r4 * 16, v);
+                    tmem_ld_wait();
+                    if (row_live) {
+                        const float* gr = A.g_out + (size_t)(row0 + rloc) * d;
+                        float* xr = A.g_x + (size_t)(row0 + rloc) * d;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int m = r4 * 16 + i;
+                            if (m < n_cond) { const int c = hdr->cond_idx[m]; xr[c] = __ldg(gr + c) + v[i]; }
+                        }
+                    }
+                    // gW1c[hid][slot] += D2 : TMEM lane = hidden unit (64 valid), 16 slots per warp
+                    tmem_ld16(tmem + lane_sel + kColD2 + r4 * 16, v);
+                    tmem_ld_wait();
+                    if (q < 2) {
+                        float* dst = A.g_w1 + (size_t)rloc * kK1 + r4 * 16;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) red_add4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    }
+                }
+                tc_fence_before();
+            }
             // ---- transformed columns of g_x out ----------------------------------------------------------------
             {
                 float* og = A.g_x + row0 * d;
@@ -1346,12 +1462,16 @@ int tcw_layer_backward(const stb_layer* L, const void* image, int direction, con
 
 uint64_t tcw_train_workspace_floats(const stb_layer* L, int64_t rows) {
     (void)L;
-    return (uint64_t)rows * tcw::kHAug + (uint64_t)tcw::kMaxChunks * tcw::kChunkN * tcw::train::kWStride;
+    return (uint64_t)rows * tcw::kHAug + (uint64_t)tcw::kMaxChunks * tcw::kChunkN * tcw::train::kWStride +
+           (uint64_t)tcw::kHid * tcw::kK1 + tcw::kHid;
 }
 
-// Fully fused: g_x, g_pre = workspace[0 : rows * 64], gW2 image = workspace[rows * 72 : ...] (accumulated)
+// Fused: g_x; gW2 image = workspace[rows * 72 : +3072 * 72] (accumulated).  first_linear != 0: the first Linear's
+// products run in the kernel too -- g_x is complete, gW1c [64 x 64 slots] and gb1 [64] follow the image
+// (accumulated); else g_pre = workspace[0 : rows * 64] is written and those products are left to the caller.
 int tcw_layer_backward_fused(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
-                             const float* g_ldj, float* g_x, float* workspace, int64_t rows, cudaStream_t stream) {
+                             const float* g_ldj, float* g_x, float* workspace, int first_linear, int64_t rows,
+                             cudaStream_t stream) {
     using namespace tcw;
     const int act = L->net.activation;
     if (act != STB_ACT_TANH && act != STB_ACT_SIGMOID && act != STB_ACT_RELU)
@@ -1359,8 +1479,14 @@ int tcw_layer_backward_fused(const stb_layer* L, const void* image, int directio
     train::Args A = {};
     A.packed = static_cast<const uint8_t*>(image);
     A.x = x; A.g_out = g_out; A.g_ldj = g_ldj; A.g_x = g_x;
-    A.g_pre = workspace;
     A.g_w2 = workspace + (size_t)rows * kHAug;
+    if (first_linear) {
+        A.g_pre = nullptr;
+        A.g_w1 = A.g_w2 + (size_t)kMaxChunks * kChunkN * train::kWStride;
+        A.g_b1 = A.g_w1 + kHid * kK1;
+    } else {
+        A.g_pre = workspace;
+    }
     A.lower = L->lower; A.upper = L->upper;
     A.rows = rows;
     const long long tiles = (rows + kTileRows - 1) / kTileRows;

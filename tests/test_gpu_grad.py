@@ -127,7 +127,11 @@ def test_continuous_affine_coupling_gradients_match_oracle():
 # ----------------------------------------------------------------------------------------------
 # fused conditioner backward (tc_wide.cu): the training step's gradient kernel
 # ----------------------------------------------------------------------------------------------
-def _nll_grads(spec, x, monkeypatch, hybrid, gnet=False):
+def _nll_grads(spec, x, monkeypatch, hybrid, gnet=False, w1lib=False):
+    if w1lib:
+        monkeypatch.setenv('STRIBOR_B200_TRAIN_W1_LIB', '1')
+    else:
+        monkeypatch.delenv('STRIBOR_B200_TRAIN_W1_LIB', raising=False)
     if gnet:
         monkeypatch.setenv('STRIBOR_B200_TRAIN_GNET', '1')
     else:
@@ -327,3 +331,21 @@ def test_wide_kernels_odd_chunk_count_many_tiles(kind, monkeypatch):
     assert rows_bad <= (2e-2 if kind == 'cubic' else 1e-3), f'{rows_bad:.3%} of rows: grad_x differs from the hybrid path'
     for i, (a, b) in enumerate(zip(gp_f, gp_h)):
         close(a, b, f'parameter {i} fused vs hybrid', 1e-2, 2e-2 if kind == 'cubic' else 5e-3, 1e-3)
+
+
+def test_fused_backward_first_linear_in_kernel_vs_library(monkeypatch):
+    """The first Linear's gradient products inside the kernel (bf16x3 operands, MN-major views) vs the same
+    products as fp32 library GEMMs from g_pre: same bins, same g_pre -> tight agreement."""
+    d, rows = 128, 20000
+    case = cases._mk_flow('quadratic', d, [64], 2, 16, rows, 8100, masks=cases.ALT, lower=-4., upper=4., scale=1.5)()
+    spec, x = case['spec'], case['inputs']['x']
+    _, gx_k, gp_k, _ = _nll_grads(spec, x, monkeypatch, hybrid=False)
+    _, gx_l, gp_l, _ = _nll_grads(spec, x, monkeypatch, hybrid=False, w1lib=True)
+    def close(a, b, what):
+        scale = b.abs().max().clamp_min(1e-12)
+        err = (a - b).abs()
+        bad = (err > 1e-3 * b.abs() + 1e-4 * scale).float().mean().item()
+        assert bad <= 1e-5, f'{what}: {bad:.3%} differ, max err {err.max().item():.3e} (scale {scale.item():.3e})'
+    close(gx_k, gx_l, 'grad_x')
+    for i, (a, b) in enumerate(zip(gp_k, gp_l)):
+        close(a, b, f'parameter {i}')
