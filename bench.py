@@ -411,20 +411,28 @@ def main():
     else:
         hbm_peak, peak_src, tf_peak = 6650.0, 'fallback (B200_PROFILING.md)', 1400.0
     launch_ms = ms / max(launches, 1)                         # rank-local average launch duration
-    bytes_per_launch = rows * (8 * D + 8)                     # read y + write x + read/write ldj
+    # layer applications one launch performs: 1 (a launch per layer) or all L (whole flow in one launch,
+    # the tile stays in shared memory between layers -- DRAM traffic is then ~L times below the algorithmic
+    # figure, which by SURVEY 8d stays L * (8d + 8) B per sample)
+    layers_per_launch = LAYERS * args.steps / max(launches, 1)
+    bytes_per_launch = rows * (8 * D + 8) * layers_per_launch  # per layer: read y + write x + read/write ldj
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     P = 3 * BINS - 1 if args.kind == 'quadratic' else 2 * BINS + 2
     h = [D // 2] + list(args.hidden)
     flops_row = 2 * (sum(a * b for a, b in zip(h[:-1], h[1:])) + h[-1] * (D // 2) * P)
-    tflops = rows * flops_row / (launch_ms * 1e-3) / 1e12
+    tflops = rows * flops_row * layers_per_launch / (launch_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
     if os.path.exists(tpath) and args.kind == 'quadratic' and not args.generic:
         tj = json.load(open(tpath))                             # dram__bytes_{read,write}.sum from ncu --set full
-        traffic = tj['dram_bytes_per_row'] * rows
+        per_row = tj.get('dram_bytes_per_row_chain', tj['dram_bytes_per_row'] * layers_per_launch) if layers_per_launch > 1 \
+            else tj['dram_bytes_per_row']
+        traffic = per_row * rows
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
-                'kernel': 'fused coupling layer (one launch per layer)',
+                'kernel': 'fused coupling layer' + (f', {layers_per_launch:g} layers per launch (tile resident in shared memory)'
+                                                    if layers_per_launch > 1 else ' (one launch per layer)'),
+                'layers_per_launch': layers_per_launch,
                 'bytes_per_launch': bytes_per_launch, 'launch_ms': launch_ms,
                 'note': 'BASELINE metric asks for % of HBM peak on L*(8d+8) B/sample; the kernel is '
                         'bound by the conditioner contraction + spline epilogue, see tensor figure'}

@@ -1,6 +1,7 @@
 // extern "C" surface of libstribor_b200.so (see include/stribor_b200.h).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace stb {
@@ -42,6 +43,20 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     return generic_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, ldiag, rows, s);
 }
 
+// A whole flow in one launch: every layer a packed spline coupling of the 256-row tensor-core kernel, same
+// dim and kind (STRIBOR_B200_NO_CHAIN=1: one launch per layer, for comparison)
+static bool chain_fusable(const stb_layer* layers, int n) {
+    if (n < 2 || n > 8) return false;
+    static const bool off = [] { const char* e = getenv("STRIBOR_B200_NO_CHAIN"); return e && e[0] == '1'; }();
+    if (off) return false;
+    const stb_layer* p[8];
+    for (int i = 0; i < n; ++i) {
+        if (validate_layer(&layers[i])) return false;
+        p[i] = &layers[i];
+    }
+    return tc_chain_supported(p, n);
+}
+
 }  // namespace stb
 
 using namespace stb;
@@ -76,6 +91,11 @@ int stb_flow_apply(const stb_layer* layers, int n_layers, int direction, const f
     if (direction != STB_FORWARD && direction != STB_INVERSE) return set_error(STB_EINVAL, "bad direction");
     cudaStream_t s = (cudaStream_t)stream;
     if (n_layers == 0) return set_error(STB_EINVAL, "empty flow: nothing to apply");
+    if (rows > 0 && x && out && chain_fusable(layers, n_layers) && !(ldj_mode != STB_LDJ_NONE && !ldj)) {
+        const stb_layer* order[8];
+        for (int i = 0; i < n_layers; ++i) order[i] = &layers[direction == STB_FORWARD ? i : n_layers - 1 - i];
+        return tc_chain_apply(order, n_layers, direction, x, out, ldj, ldj ? ldj_mode : STB_LDJ_NONE, 0, rows, s);
+    }
     const float* cur = x;
     int mode = ldj_mode;
     for (int i = 0; i < n_layers; ++i) {
@@ -95,6 +115,11 @@ int stb_flow_log_prob(const stb_layer* layers, int n_layers, const float* y, con
     if (n_layers < 1 || !layers) return set_error(STB_EINVAL, "log_prob needs at least one layer");
     if (!x_out || !lp) return set_error(STB_EINVAL, "x_out / lp is NULL");
     cudaStream_t s = (cudaStream_t)stream;
+    if (rows > 0 && y && chain_fusable(layers, n_layers)) {
+        const stb_layer* order[8];
+        for (int i = 0; i < n_layers; ++i) order[i] = &layers[n_layers - 1 - i];
+        return tc_chain_apply(order, n_layers, STB_INVERSE, y, x_out, lp, STB_LDJ_SET, 1, rows, s);
+    }
     const float* cur = y;
     for (int i = 0; i < n_layers; ++i) {
         const stb_layer* L = &layers[n_layers - 1 - i];

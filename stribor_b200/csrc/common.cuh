@@ -27,6 +27,11 @@ int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
 int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj,
                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
 
+// several layers of one flow in one launch (tc_layer.cu, CHAIN kernels); layers[] in application order
+bool tc_chain_supported(const stb_layer* const* layers, int n);
+int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, float* y, float* ldj,
+                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
+
 // tcgen05 path for dim <= 128 and the training backward (tc_wide.cu).  `image` is the wide packed image:
 // it follows the tc_layer.cu image when the layer has both (tcw_image).
 bool tcw_layer_supported(const stb_layer* L);

@@ -48,6 +48,7 @@ constexpr int kMaxChunks = kMaxTr / kG;
 constexpr int kTileRows = 256;
 constexpr int kXsStride = kMaxDim + 1;
 constexpr int kStages = 3;
+constexpr int kMaxChain = 8;           // layers of a flow fused into one launch (CHAIN kernels)
 #ifndef STB_TC_EPI_PER_SUB
 #define STB_TC_EPI_PER_SUB 2
 #endif
@@ -106,6 +107,8 @@ constexpr uint32_t kA1Part = 128 * kK1 * 2;                        // 8192: one 
 constexpr uint32_t kOffW2 = kOffW1 + kW1Bytes;                     // chunks of 24576 B
 constexpr uint32_t kChunkBytes = 2 * kChunkN * kHid * 2;           // fp16 hi (12 KB) | lo (12 KB)
 constexpr uint32_t kPackedBytes = kOffW2 + kMaxChunks * kChunkBytes;
+constexpr uint32_t kHeadBytes = kOffW1 + kW1Bytes;                 // header | biases | first Linear: one ring item (CHAIN)
+static_assert(kHeadBytes <= kChunkBytes, "the layer head fits a ring stage");
 
 // shared memory map
 constexpr uint32_t kSmXs = 0;                                      // float [256][65]
@@ -145,6 +148,11 @@ struct Args {
     float lower, upper;
     long long rows;
     int n_tiles;
+    // CHAIN: several layers of one flow applied to a tile while it stays in shared memory
+    int n_layers, dim;
+    const uint8_t* chain_packed[kMaxChain];
+    float lower_l[kMaxChain], upper_l[kMaxChain];
+    int n_chunks_l[kMaxChain];
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -154,7 +162,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // -----------------------------------------------------------------------------------------------
 // the kernel
 // -----------------------------------------------------------------------------------------------
-template <int KIND, bool INVERSE>
+// CHAIN = true: `n_layers` coupling layers of one flow (same dim and kind, same direction) are applied to a
+// tile while it stays in shared memory -- the reference's layer loop (flow.py:104-107,118-125) inside the
+// kernel: x is read and written once per flow instead of once per layer, the running log|det J| stays in a
+// register.  Each layer's header + biases + first Linear (20 KB) travel through the weight ring as one more
+// item ahead of its chunks; the epilogue warps copy the 7 KB small block out of the stage.
+template <int KIND, bool INVERSE, bool CHAIN>
 __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem + kSmXs);
@@ -187,17 +200,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    if (tid == 0) {                               // header + biases + packed first Linear
-        mbar_arrive_expect_tx(&bars->setup, kSmallBytes + kW1Bytes);
-        bulk_g2s(smem + kSmSmall, A.packed, kSmallBytes, &bars->setup);
-        bulk_g2s(w1s, A.packed + kOffW1, kW1Bytes, &bars->setup);
+    if (!CHAIN) {
+        if (tid == 0) {                           // header + biases + packed first Linear
+            mbar_arrive_expect_tx(&bars->setup, kSmallBytes + kW1Bytes);
+            bulk_g2s(smem + kSmSmall, A.packed, kSmallBytes, &bars->setup);
+            bulk_g2s(w1s, A.packed + kOffW1, kW1Bytes, &bars->setup);
+        }
+        mbar_wait(&bars->setup, 0);
     }
-    mbar_wait(&bars->setup, 0);
 
-    const int d = hdr->dim, n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_chunks = hdr->n_chunks;
-    const int act = hdr->act;
-    const float s2 = hdr->s2;
-    const float s2l = s2 * 1.4426950408889634f;
+    const int n_layers = CHAIN ? A.n_layers : 1;
+    const int d = CHAIN ? A.dim : hdr->dim;
+    // per-layer quantities (CHAIN: re-read at every layer by the epilogue warps)
+    int n_tr = CHAIN ? 0 : hdr->n_tr, n_cond = CHAIN ? 0 : hdr->n_cond, n_chunks = CHAIN ? 0 : hdr->n_chunks;
+    int act = CHAIN ? 0 : hdr->act;
+    float s2 = CHAIN ? 1.f : hdr->s2;
+    float s2l = s2 * 1.4426950408889634f;
     const int dshift = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;       // d a power of two: divide by shifting
     const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -213,12 +231,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                     if (nb >= 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(nb & ~15LL)) : "memory");
                 }
-                for (int c = 0; c < n_chunks; ++c, ++cc) {
-                    const uint32_t st = cc % kStages, use = cc / kStages;
-                    MBAR_WAIT_SLOW(&bars->b_empty[st], (use & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bars->b_full[st], kChunkBytes);
-                    bulk_g2s(bst + st * kChunkBytes, A.packed + kOffW2 + (size_t)c * kChunkBytes, kChunkBytes,
-                             &bars->b_full[st]);
+                for (int l = 0; l < n_layers; ++l) {
+                    const uint8_t* img = CHAIN ? A.chain_packed[l] : A.packed;
+                    const int nch = CHAIN ? A.n_chunks_l[l] : n_chunks;
+                    if (CHAIN) {                   // the layer's head: header | biases | first Linear
+                        const uint32_t st = cc % kStages, use = cc / kStages;
+                        MBAR_WAIT_SLOW(&bars->b_empty[st], (use & 1) ^ 1);
+                        mbar_arrive_expect_tx(&bars->b_full[st], kHeadBytes);
+                        bulk_g2s(bst + st * kChunkBytes, img, kHeadBytes, &bars->b_full[st]);
+                        ++cc;
+                    }
+                    for (int c = 0; c < nch; ++c, ++cc) {
+                        const uint32_t st = cc % kStages, use = cc / kStages;
+                        MBAR_WAIT_SLOW(&bars->b_empty[st], (use & 1) ^ 1);
+                        mbar_arrive_expect_tx(&bars->b_full[st], kChunkBytes);
+                        bulk_g2s(bst + st * kChunkBytes, img + kOffW2 + (size_t)c * kChunkBytes, kChunkBytes,
+                                 &bars->b_full[st]);
+                    }
                 }
             }
         }
@@ -231,15 +260,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
             const int s = warp - 1;
             const uint32_t idesc1 = make_idesc(FMT_BF16, 128, kHid);
             const uint32_t idesc2 = make_idesc(FMT_F16, 128, kChunkN);
-            uint32_t cc = 0;
+            uint32_t cc = 0;                       // chunk counter (accumulator buffers)
+            uint32_t rc = 0;                       // ring item counter (== cc unless CHAIN adds the layer heads)
+            uint32_t hp = 0;                       // layer applications so far (phase of the head barriers)
             PROF_DECL
-            for (int it = 0; it < my_tiles; ++it) {
-                const uint32_t tpar = it & 1;
+            for (int it = 0; it < my_tiles; ++it)
+            for (int l = 0; l < n_layers; ++l, ++hp) {
+                const uint32_t tpar = hp & 1;
+                const int nch = CHAIN ? A.n_chunks_l[l] : n_chunks;
                 {                                  // GEMM1: conditioning columns -> hidden pre-activation
+                    uint32_t b0 = smem_u32(w1s);
+                    const uint32_t hst = rc % kStages;
+                    if (CHAIN) {
+                        MBAR_WAIT_SLOW(&bars->b_full[hst], (rc / kStages) & 1);
+                        b0 = smem_u32(bst + hst * kChunkBytes) + kOffW1;
+                    }
                     MBAR_WAIT_SLOW(&bars->a1_ready[s], tpar);
                     PROF(0)
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(abuf + s * kABytes), b0 = smem_u32(w1s);
+                    const uint32_t a0 = smem_u32(abuf + s * kABytes);
                     const uint32_t dcol = tmem + kColAcc1 + s * kHid;
                     uint32_t acc = 0;
                     // x = x0 + x1 + x2, W = W0 + W1 + W2 (bf16 parts): every product except x2*W2,
@@ -258,10 +297,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                         }
                     }
                     umma_commit(&bars->acc1_full[s]);
+                    if (CHAIN) { umma_commit(&bars->b_empty[hst]); ++rc; }
                     PROF(1)
                 }
-                for (int c = 0; c < n_chunks; ++c, ++cc) {
-                    const uint32_t st = cc % kStages, use = cc / kStages;
+                for (int c = 0; c < nch; ++c, ++cc, ++rc) {
+                    const uint32_t st = rc % kStages, use = rc / kStages;
                     MBAR_WAIT_SLOW(&bars->b_full[st], use & 1);
                     PROF(2)
                     const uint32_t buf = cc & 1, buse = cc >> 1;
@@ -307,8 +347,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
         const uint32_t a_row_off = (uint32_t)(rloc >> 3) * 1024 + (uint32_t)(rloc & 7) * 16;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
-        const float lo = A.lower, hi = A.upper;
-        const float inv_span = 1.f / (hi - lo);
+        float lo = A.lower, hi = A.upper;
+        float inv_span = 1.f / (hi - lo);
         // loop-invariant addresses of the chunk loop, pinned in registers
         const uint32_t full_bar = pin(smem_u32(&bars->acc_full[s][0]));
         const uint32_t empty_bar = pin(smem_u32(&bars->acc_empty[s][0]));
@@ -316,15 +356,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
         const uint32_t tr_idx_a = pin(smem_u32(&hdr->tr_idx[0]));
         const uint32_t b2_a = pin(smem_u32(b2s));
         const uint32_t xrow_a = pin(smem_u32(xrow));
-        const uint32_t noshift_mask = hdr->noshift_mask;
-        uint32_t cc = 0;
+        uint32_t noshift_mask = CHAIN ? 0u : hdr->noshift_mask;
+        uint32_t cc = 0, rc = 0, hp = 0;           // chunk / ring item / layer application counters (as the issuers')
         PROF_DECL
 
         for (int it = 0; it < my_tiles; ++it) {
             const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
             const long long row0 = tile * kTileRows;
             const int nrows = (int)min((long long)kTileRows, A.rows - row0);
-            const uint32_t tpar = it & 1;
 
             // ---- stage the x tile: coalesced global reads -> padded row-major smem ----------------
             {
@@ -359,6 +398,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
             }
             named_bar_sync(1, kEpiThreads);
             PROFH(0)
+            float ld_acc = 0.f;                    // running log|det J| of this thread's elements (all layers)
+#pragma unroll 1
+            for (int l = 0; l < n_layers; ++l, ++hp) {
+            const uint32_t tpar = hp & 1;
+            if (CHAIN) {
+                // this layer's header + biases out of its ring stage (the first Linear stays there for GEMM1)
+                const uint32_t hst = rc % kStages;
+                mbar_wait(&bars->b_full[hst], (rc / kStages) & 1);
+                const uint4* src = reinterpret_cast<const uint4*>(bst + hst * kChunkBytes);
+                uint4* dst = reinterpret_cast<uint4*>(smem + kSmSmall);
+                for (int i = etid; i < (int)(kSmallBytes / 16); i += kEpiThreads) dst[i] = src[i];
+                named_bar_sync(1, kEpiThreads);
+                n_tr = hdr->n_tr; n_cond = hdr->n_cond; n_chunks = hdr->n_chunks; act = hdr->act;
+                s2 = hdr->s2; s2l = s2 * 1.4426950408889634f;
+                noshift_mask = hdr->noshift_mask;
+                lo = A.lower_l[l]; hi = A.upper_l[l]; inv_span = 1.f / (hi - lo);
+                rc += 1u + (uint32_t)n_chunks;
+            }
 
             // ---- tile head, software-pipelined over the two subtiles: every warp of a TMEM sub-partition
             // class helps with BOTH subtiles' rows (TMEM lanes are shared, only the columns differ), so
@@ -420,7 +477,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
             }
 
             // ---- last Linear chunks out of TMEM + spline in registers: this warp's dim of each chunk ----
-            float ld_acc = 0.f;
             PROFC(0) PROFH(3)
             // dims round-robin over the triple.  A warp visits chunks in increasing order with gaps <= 2,
             // so the phase parity it waits for on an accumulator buffer is never ambiguous: the
@@ -506,6 +562,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
             }
             cc += (uint32_t)n_chunks;
             PROFH(5)
+            // next layer of the chain: every warp's outputs are in the tile, nobody reads this layer's biases any more
+            if (CHAIN && l + 1 < n_layers) named_bar_sync(1, kEpiThreads);
+            }   // layers
 
             // ---- per-row log|det J|: the pair's two partials (+ UnitNormal log-density of the output row) ---
             if (r3 < kEpiPerSub - 1) ld_s[r3 * kTileRows + rt] = ld_acc;
@@ -734,8 +793,8 @@ int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, 
         if (n_sm <= 0) n_sm = 148;
     }
     void (*kern)(Args);
-    if (L->kind == STB_RQS) kern = A.inverse ? tc_spline_layer_kernel<STB_RQS, true> : tc_spline_layer_kernel<STB_RQS, false>;
-    else kern = A.inverse ? tc_spline_layer_kernel<STB_CUBIC, true> : tc_spline_layer_kernel<STB_CUBIC, false>;
+    if (L->kind == STB_RQS) kern = A.inverse ? tc_spline_layer_kernel<STB_RQS, true, false> : tc_spline_layer_kernel<STB_RQS, false, false>;
+    else kern = A.inverse ? tc_spline_layer_kernel<STB_CUBIC, true, false> : tc_spline_layer_kernel<STB_CUBIC, false, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int grid = (int)min((long long)n_sm, tiles);
@@ -743,6 +802,64 @@ int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, 
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_spline_layer_kernel launch: %s", cudaGetErrorString(e));
+    return STB_OK;
+}
+
+
+// ---- a run of layers of one flow in ONE launch (flow.py:104-107 / 118-125 inside the kernel) -----------
+bool tc_chain_supported(const stb_layer* const* layers, int n) {
+    using namespace tcl;
+    if (n < 2 || n > kMaxChain) return false;
+    for (int i = 0; i < n; ++i) {
+        const stb_layer* L = layers[i];
+        if (!L->packed || L->packed_bytes < kPackedBytes || !tc_layer_supported(L)) return false;
+        if (L->kind != layers[0]->kind || L->dim != layers[0]->dim) return false;
+    }
+    return true;
+}
+
+// layers[] in APPLICATION order (the caller reverses them for the inverse direction)
+int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, float* y, float* ldj,
+                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream) {
+    using namespace tcl;
+    if (!tc_chain_supported(layers, n)) return set_error(STB_EINVAL, "layers cannot be chained");
+    Args A = {};
+    A.packed = static_cast<const uint8_t*>(layers[0]->packed);
+    A.x = x; A.y = y; A.ldj = ldj;
+    A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
+    A.base_log_prob = base_log_prob;
+    A.inverse = direction == STB_INVERSE;
+    A.lower = layers[0]->lower; A.upper = layers[0]->upper;
+    A.rows = rows;
+    A.n_layers = n;
+    A.dim = layers[0]->dim;
+    for (int i = 0; i < n; ++i) {
+        PackArgs pa;
+        if (!fill_pack_args(layers[i], pa)) return set_error(STB_EINVAL, "layer has no tensor-core path");
+        A.chain_packed[i] = static_cast<const uint8_t*>(layers[i]->packed);
+        A.lower_l[i] = layers[i]->lower; A.upper_l[i] = layers[i]->upper;
+        A.n_chunks_l[i] = pa.n_chunks;
+    }
+    const long long tiles = (rows + kTileRows - 1) / kTileRows;
+    if (tiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
+    A.n_tiles = (int)tiles;
+    static thread_local int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    void (*kern)(Args);
+    if (layers[0]->kind == STB_RQS) kern = A.inverse ? tc_spline_layer_kernel<STB_RQS, true, true> : tc_spline_layer_kernel<STB_RQS, false, true>;
+    else kern = A.inverse ? tc_spline_layer_kernel<STB_CUBIC, true, true> : tc_spline_layer_kernel<STB_CUBIC, false, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int grid = (int)min((long long)n_sm, tiles);
+    kern<<<grid, kThreads, kSmemBytes, stream>>>(A);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_spline_layer_kernel (chain) launch: %s", cudaGetErrorString(e));
     return STB_OK;
 }
 
