@@ -414,6 +414,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 s2 = hdr->s2; s2l = s2 * 1.4426950408889634f;
                 noshift_mask = hdr->noshift_mask;
                 lo = A.lower_l[l]; hi = A.upper_l[l]; inv_span = 1.f / (hi - lo);
+                // keep the three in registers: ptxas otherwise re-derives them (indexed parameter loads and
+                // the division) inside the element loop -- 2.4 % of all issued instructions, measured
+                asm volatile("" : "+f"(lo), "+f"(hi), "+f"(inv_span));
                 rc += 1u + (uint32_t)n_chunks;
             }
 
