@@ -43,18 +43,39 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     return generic_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, ldiag, rows, s);
 }
 
-// A whole flow in one launch: every layer a packed spline coupling of the 256-row tensor-core kernel, same
-// dim and kind (STRIBOR_B200_NO_CHAIN=1: one launch per layer, for comparison)
-static bool chain_fusable(const stb_layer* layers, int n) {
-    if (n < 2 || n > 8) return false;
-    static const bool off = [] { const char* e = getenv("STRIBOR_B200_NO_CHAIN"); return e && e[0] == '1'; }();
-    if (off) return false;
-    const stb_layer* p[8];
-    for (int i = 0; i < n; ++i) {
-        if (validate_layer(&layers[i])) return false;
-        p[i] = &layers[i];
+// A sequence of layers (already in application order).  Maximal runs of 2..8 packed spline couplings of the
+// 256-row tensor-core kernel with the same dim and kind go out as ONE launch each (tc_layer.cu, CHAIN: the
+// tile stays in shared memory between the layers); everything else layer by layer.
+// STRIBOR_B200_NO_CHAIN=1: one launch per layer, for comparison.
+static int apply_sequence(const stb_layer* const* seq, int n, int direction, const float* x, const float* latent,
+                          const float* t, float* out, float* ldj, int ldj_mode, int base_lp_last, int64_t rows,
+                          cudaStream_t s) {
+    static const bool chain_off = [] { const char* e = getenv("STRIBOR_B200_NO_CHAIN"); return e && e[0] == '1'; }();
+    const float* cur = x;
+    int mode = ldj_mode;
+    int i = 0;
+    while (i < n) {
+        int j = i + 1;
+        if (!chain_off && rows > 0 && x && out && !(ldj_mode != STB_LDJ_NONE && !ldj) && validate_layer(seq[i]) == 0) {
+            while (j < n && j - i < 8 && validate_layer(seq[j]) == 0 && tc_chain_supported(seq + i, j - i + 1)) ++j;
+        }
+        const int last = (j == n);
+        int rc;
+        if (j - i >= 2) {
+            rc = tc_chain_apply(seq + i, j - i, direction, cur, out, ldj, ldj ? mode : STB_LDJ_NONE,
+                                last && base_lp_last, rows, s);
+        } else {
+            if (seq[i]->kind == STB_PERMUTE && cur == out)
+                return set_error(STB_ENOTSUP, "a permutation inside a fused chain needs out != x for that hop (use the layer-by-layer path)");
+            rc = apply_one(seq[i], direction, cur, latent, t, out, ldj, ldj ? mode : STB_LDJ_NONE,
+                           last && base_lp_last, rows, s);
+        }
+        if (rc) return rc;
+        cur = out;
+        if (mode == STB_LDJ_SET) mode = STB_LDJ_ADD;       // later layers accumulate
+        i = j;
     }
-    return tc_chain_supported(p, n);
+    return STB_OK;
 }
 
 }  // namespace stb
@@ -91,23 +112,10 @@ int stb_flow_apply(const stb_layer* layers, int n_layers, int direction, const f
     if (direction != STB_FORWARD && direction != STB_INVERSE) return set_error(STB_EINVAL, "bad direction");
     cudaStream_t s = (cudaStream_t)stream;
     if (n_layers == 0) return set_error(STB_EINVAL, "empty flow: nothing to apply");
-    if (rows > 0 && x && out && chain_fusable(layers, n_layers) && !(ldj_mode != STB_LDJ_NONE && !ldj)) {
-        const stb_layer* order[8];
-        for (int i = 0; i < n_layers; ++i) order[i] = &layers[direction == STB_FORWARD ? i : n_layers - 1 - i];
-        return tc_chain_apply(order, n_layers, direction, x, out, ldj, ldj ? ldj_mode : STB_LDJ_NONE, 0, rows, s);
-    }
-    const float* cur = x;
-    int mode = ldj_mode;
-    for (int i = 0; i < n_layers; ++i) {
-        const stb_layer* L = &layers[direction == STB_FORWARD ? i : n_layers - 1 - i];
-        if (L->kind == STB_PERMUTE && cur == out)
-            return set_error(STB_ENOTSUP, "a permutation inside a fused chain needs out != x for that hop (use the layer-by-layer path)");
-        int rc = apply_one(L, direction, cur, latent, t, out, ldj, ldj ? mode : STB_LDJ_NONE, 0, rows, s);
-        if (rc) return rc;
-        cur = out;
-        if (mode == STB_LDJ_SET) mode = STB_LDJ_ADD;       // later layers accumulate
-    }
-    return STB_OK;
+    if (n_layers > 64) return set_error(STB_EINVAL, "more than 64 layers");
+    const stb_layer* order[64];
+    for (int i = 0; i < n_layers; ++i) order[i] = &layers[direction == STB_FORWARD ? i : n_layers - 1 - i];
+    return apply_sequence(order, n_layers, direction, x, latent, t, out, ldj, ldj_mode, 0, rows, s);
 }
 
 int stb_flow_log_prob(const stb_layer* layers, int n_layers, const float* y, const float* latent,
@@ -115,23 +123,10 @@ int stb_flow_log_prob(const stb_layer* layers, int n_layers, const float* y, con
     if (n_layers < 1 || !layers) return set_error(STB_EINVAL, "log_prob needs at least one layer");
     if (!x_out || !lp) return set_error(STB_EINVAL, "x_out / lp is NULL");
     cudaStream_t s = (cudaStream_t)stream;
-    if (rows > 0 && y && chain_fusable(layers, n_layers)) {
-        const stb_layer* order[8];
-        for (int i = 0; i < n_layers; ++i) order[i] = &layers[n_layers - 1 - i];
-        return tc_chain_apply(order, n_layers, STB_INVERSE, y, x_out, lp, STB_LDJ_SET, 1, rows, s);
-    }
-    const float* cur = y;
-    for (int i = 0; i < n_layers; ++i) {
-        const stb_layer* L = &layers[n_layers - 1 - i];
-        const int last = (i == n_layers - 1);
-        if (L->kind == STB_PERMUTE && cur == x_out)
-            return set_error(STB_ENOTSUP, "a permutation inside a fused chain needs out != x for that hop (use the layer-by-layer path)");
-        int rc = apply_one(L, STB_INVERSE, cur, latent, t, x_out, lp, i == 0 ? STB_LDJ_SET : STB_LDJ_ADD,
-                           last, rows, s);
-        if (rc) return rc;
-        cur = x_out;
-    }
-    return STB_OK;
+    if (n_layers > 64) return set_error(STB_EINVAL, "more than 64 layers");
+    const stb_layer* order[64];
+    for (int i = 0; i < n_layers; ++i) order[i] = &layers[n_layers - 1 - i];
+    return apply_sequence(order, n_layers, STB_INVERSE, y, latent, t, x_out, lp, STB_LDJ_SET, 1, rows, s);
 }
 
 int stb_unit_normal_log_prob(const float* x, float* lp, int accumulate, int32_t dim, int64_t rows,

@@ -260,3 +260,38 @@ def test_tensor_path_repacks_when_weights_change():
                                     spline_type='quadratic'), mask='ordered_0').to(DEV)
         ref.load_state_dict(c.state_dict())
         assert torch.equal(ref(x), y1)
+
+
+@pytest.mark.parametrize('kind', ['quadratic', 'cubic'])
+@pytest.mark.parametrize('n_layers,d,rows', [(12, 64, 1000), (3, 30, 70000), (9, 63, 513)])
+def test_whole_flow_kernel_matches_layer_by_layer(kind, n_layers, d, rows):
+    """stb_flow_log_prob / stb_flow_apply launch runs of <= 8 layers as ONE kernel (tile resident in shared
+    memory between layers, CHAIN variant).  Same arithmetic as one launch per layer: results must agree to
+    the last bit for x and to fp32 summation order for the log-dets."""
+    case = _flows(kind, d, cases.ALT if d % 2 == 0 else ('ordered_left_half', 'parity_odd'), seed=1500 + d, n_layers=n_layers)
+    torch.manual_seed(rows)
+    x = (torch.randn(rows, d) * 1.7).to(DEV)
+    layers = [l.to(DEV) for l in layers_from_spec(case['spec'])]
+    flow = st.NormalizingFlow(st.UnitNormal(d), layers)
+    n0 = _ops.launch_count()
+    with torch.no_grad():
+        lp = flow.log_prob(x)
+        n_lp = _ops.launch_count() - n0
+        xi, li = flow.inverse_and_log_det_jacobian(x)
+        yf, lf = flow.forward_and_log_det_jacobian(x)
+        # layer by layer through the single-layer entry point
+        cur, tot = x, torch.zeros(rows, 1, device=DEV)
+        for l in reversed(layers):
+            cur, ld = l.inverse_and_log_det_jacobian(cur)
+            tot = tot + ld
+        cur_f, tot_f = x, torch.zeros(rows, 1, device=DEV)
+        for l in layers:
+            cur_f, ld = l.forward_and_log_det_jacobian(cur_f)
+            tot_f = tot_f + ld
+    packs = 6 * n_layers                                   # first use packs both images of every layer
+    assert n_lp - packs == (n_layers + 7) // 8, f'{n_lp - packs} launches for {n_layers} layers'
+    assert torch.equal(xi, cur), (xi - cur).abs().max().item()
+    assert torch.equal(yf, cur_f), (yf - cur_f).abs().max().item()
+    assert (li - tot).abs().max().item() < 2e-4 and (lf - tot_f).abs().max().item() < 2e-4
+    base = (-0.5 * cur * cur - 0.9189385332046727).sum(-1, keepdim=True)
+    assert (lp - (tot + base)).abs().max().item() < 5e-4
