@@ -106,26 +106,33 @@ struct CubSel {
     int k;
 };
 
+// Divisions and square roots below use the ~1 ulp MUFU + one-Newton-step forms (fdiv / fsqrt): bin sizes are
+// >= 1e-2 and O(1), never subnormal or huge.
+__device__ __forceinline__ float sigmoid_fast(float v) { return fdiv(1.f, 1.f + ex2_approx(-1.4426950408889634f * v)); }
+
 __device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float ur) {
-    const float sk = s.hk / s.wk;
+    float inv_wk;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_wk) : "f"(s.wk));
+    inv_wk = fmaf(fmaf(-s.wk, inv_wk, 1.f), inv_wk, inv_wk);         // 1 / w_k to ~1 ulp, used three times
+    const float sk = s.hk * inv_wk;
     float dl, dr;
     if (s.k == 0) {
-        dl = sigmoid_f(ul) * 3.f * sk;
+        dl = sigmoid_fast(ul) * 3.f * sk;
     } else {
-        const float sp = s.hp / s.wp;
-        dl = fminf(fminf(fabsf(sp), fabsf(sk)), 0.5f * (s.wk * sp + s.wp * sk) / (s.wp + s.wk)) *
+        const float sp = fdiv(s.hp, s.wp);
+        dl = fminf(fminf(fabsf(sp), fabsf(sk)), fdiv(0.5f * (s.wk * sp + s.wp * sk), s.wp + s.wk)) *
              (sign_f(sp) + sign_f(sk));
     }
     if (s.k == kBins - 1) {
-        dr = sigmoid_f(ur) * 3.f * sk;
+        dr = sigmoid_fast(ur) * 3.f * sk;
     } else {
-        const float sn = s.hn / s.wn;
-        dr = fminf(fminf(fabsf(sk), fabsf(sn)), 0.5f * (s.wn * sk + s.wk * sn) / (s.wk + s.wn)) *
+        const float sn = fdiv(s.hn, s.wn);
+        dr = fminf(fminf(fabsf(sk), fabsf(sn)), fdiv(0.5f * (s.wn * sk + s.wk * sn), s.wk + s.wn)) *
              (sign_f(sk) + sign_f(sn));
     }
     CubBin r;
-    r.a = (dl + dr - 2.f * sk) / (s.wk * s.wk);
-    r.b = (3.f * sk - 2.f * dl - dr) / s.wk;
+    r.a = (dl + dr - 2.f * sk) * inv_wk * inv_wk;
+    r.b = (3.f * sk - 2.f * dl - dr) * inv_wk;
     r.c = dl;
     r.d = s.ch;
     r.xl = s.cw;
@@ -367,6 +374,51 @@ __device__ __forceinline__ CubSel cubic16_locate(float2* t, bool shift, float u)
     return r;
 }
 
+// cubic_spline.py:153-228 (Cardano: three real roots by the trigonometric form, one by cube roots, and the
+// almost-quadratic case), same branch structure as stb_math.cuh:cubic_inverse_in_bin with the cheap
+// division / square-root forms; the cube root is sign(v) 2^(log2|v| / 3) on MUFU (relative error ~2^-21,
+// the reference's own exp(log|v| / 3) in fp32 is no better once |log| > 1).
+__device__ __forceinline__ float cbrt_fast(float v) {
+    return copysignf(ex2_approx(lg2_approx(fabsf(v)) * 0.33333333333333333f), v) * ((v == 0.f) ? 0.f : 1.f);
+}
+__device__ __forceinline__ float cubic16_inverse_in_bin(const CubBin& k, float u) {
+    float inv_a;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_a) : "f"(k.a));
+    inv_a = fmaf(fmaf(-k.a, inv_a, 1.f), inv_a, inv_a);
+    const float third = 0.33333333333333333f;
+    const float b_ = (k.b * inv_a) * third;
+    const float c_ = (k.c * inv_a) * third;
+    const float d_ = (k.d - u) * inv_a;
+    const float delta_1 = -b_ * b_ + c_;
+    const float delta_2 = -c_ * b_ + d_;
+    const float delta_3 = b_ * d_ - c_ * c_;
+    const float disc = 4.f * delta_1 * delta_3 - delta_2 * delta_2;
+    const float dep_1 = -2.f * b_ * delta_1 + delta_2;
+    const float dep_2 = delta_1;
+    float out;
+    if (disc > 0.f) {
+        const float theta = atan2f(fsqrt(disc), -dep_1) * third;
+        float c1, c2;
+        sincosf(theta, &c2, &c1);
+        const float scale = 2.f * fsqrt(-dep_2);
+        const float shift = -b_ + k.xl;
+        const float r1 = c1 * scale + shift;
+        const float r2 = (-0.5f * c1 - 0.5f * 1.7320508075688772f * c2) * scale + shift;
+        const float r3 = (-0.5f * c1 + 0.5f * 1.7320508075688772f * c2) * scale + shift;
+        const float lo = k.xl - STB_CUB_EPS, hi = k.xr + STB_CUB_EPS;
+        const bool ok1 = (lo < r1) && (r1 < hi), ok2 = (lo < r2) && (r2 < hi), ok3 = (lo < r3) && (r3 < hi);
+        out = ok1 ? r1 : (ok2 ? r2 : (ok3 ? r3 : r1));
+    } else {
+        const float sq = fsqrt(-disc);
+        out = (cbrt_fast((-dep_1 + sq) * 0.5f) + cbrt_fast((-dep_1 - sq) * 0.5f)) - b_ + k.xl;
+    }
+    if (fabsf(k.a) < STB_CUB_QUAD) {
+        const float qc = k.d - u;
+        out = fdiv(-k.c + fsqrt(k.c * k.c - 4.f * k.b * qc), 2.f * k.b) + k.xl;
+    }
+    return out;
+}
+
 template <bool INVERSE>
 __device__ __forceinline__ void cubic16_finish(const CubSel& s, float ul, float ur, float lo, float hi, bool want_ld,
                                                float u, float& out, float& ld) {
@@ -375,15 +427,13 @@ __device__ __forceinline__ void cubic16_finish(const CubSel& s, float ul, float 
     if (!INVERSE) {
         out = cubic_forward_in_bin(b, u, ld) * span + lo;
     } else {
-        float ld_own;
-        out = cubic_inverse_in_bin(b, u, ld_own) * span + lo;
+        out = cubic16_inverse_in_bin(b, u) * span + lo;
         ld = 0.f;
         if (want_ld && out >= lo && out <= hi) {
             // forward log-derivative at the recovered point, in the bin the inverse search found
             // (see the note above RqsBin16's users for why the re-search is skipped)
-            float ldf;
-            (void)cubic_forward_in_bin(b, (out - lo) / span, ldf);
-            ld = -ldf;
+            const float sr = fdiv(out - lo, span) - b.xl;
+            ld = -0.69314718055994530942f * lg2_approx(fmaf(fmaf(3.f * b.a, sr, 2.f * b.b), sr, b.c));
         }
     }
 }
