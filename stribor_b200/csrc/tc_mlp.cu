@@ -163,9 +163,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
     const int blocks_per_tile = 6 + (n_hidden == 2 ? kb_h : 0) + kb_h;
     const uint32_t w1b = w1_block_bytes(H), w2b = w2_block_bytes(H), w3b = w3_block_bytes();
 
+    // Small conditioners (all weight blocks together <= the ring, e.g. MLP[64] of configs[3]): the blocks are
+    // loaded ONCE and stay resident -- streaming them per 128-row tile was several times the tile's own bytes.
+    const uint32_t w_total = 6 * w1b + (n_hidden == 2 ? kb_h * w2b : 0) + kb_h * w3b;
+    const bool resident = w_total <= kStages * kSlotBytes;
+
     if (warp == 0) {
         // ======================= producer =========================================================
-        if (lane == 0) {
+        if (lane == 0 && resident) {
+            if (my_tiles > 0) {
+                mbar_arrive_expect_tx(&bars->full[0], w_total);
+                bulk_g2s(ring, A.packed + kOffW, w_total, &bars->full[0]);
+            }
+            for (int it = 0; it + 1 < my_tiles; ++it) {
+                const long long nrow0 = ((long long)blockIdx.x + (long long)(it + 1) * gridDim.x) * kRows;
+                const long long nb = min((long long)kRows, A.rows - nrow0) * d * 4;
+                const char* src = reinterpret_cast<const char*>(A.x + nrow0 * d);
+                if (nb >= 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(nb & ~15LL)) : "memory");
+            }
+        } else if (lane == 0) {
             uint32_t cc = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 if (it + 1 < my_tiles) {
@@ -195,24 +212,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
             const uint32_t a0 = smem_u32(abuf);
             const uint32_t dmain = tmem + kColMain, dcorr = tmem + kColCorr;
             uint32_t cc = 0, ause = 0;
+            if (resident && my_tiles > 0) { mbar_wait(&bars->full[0], 0); tc_fence_after(); }
             for (int it = 0; it < my_tiles; ++it) {
                 // ---- layer 1: bf16x3 x bf16x3, blocks ordered (pb = 2, 1, 0) x (kb = 0, 1) -------------
                 mbar_wait(&bars->a_ready, ause & 1); ++ause;
                 tc_fence_after();
                 uint32_t acc_m = 0, acc_c = 0;
+                uint32_t roff = 0;                          // resident: byte offset of the block in the image
                 for (int b = 0; b < 6; ++b, ++cc) {
                     const int pb = 2 - b / 2, kb = b & 1;
                     const uint32_t st = cc % kStages, use = cc / kStages;
-                    mbar_wait(&bars->full[st], use & 1);
-                    tc_fence_after();
-                    const uint64_t bd = make_smem_desc(smem_u32(ring + st * kSlotBytes), 128, 256);
+                    if (!resident) { mbar_wait(&bars->full[st], use & 1); tc_fence_after(); }
+                    const uint64_t bd = make_smem_desc(smem_u32(ring) + (resident ? roff : st * kSlotBytes), 128, 256);
+                    roff += w1b;
                     for (int pa = 2; pa >= 0; --pa) {
                         if (pa == 2 && pb == 2) continue;
                         const uint64_t ad = make_smem_desc(a0 + pa * a_part + kb * 256, 128, 512);
                         if (pa == 0 && pb == 0) { umma_f16(dmain, ad, bd, idesc1, acc_m); acc_m = 1; }
                         else { umma_f16(dcorr, ad, bd, idesc1, acc_c); acc_c = 1; }
                     }
-                    umma_commit(&bars->empty[st]);
+                    if (!resident) umma_commit(&bars->empty[st]);
                 }
                 umma_commit(&bars->acc_ready);
                 // ---- hidden -> hidden (optional) and hidden -> output: fp16 hi | lo -------------------
@@ -225,16 +244,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                     acc_m = acc_c = 0;
                     for (int kb = 0; kb < kb_h; ++kb, ++cc) {
                         const uint32_t st = cc % kStages, use = cc / kStages;
-                        mbar_wait(&bars->full[st], use & 1);
-                        tc_fence_after();
-                        const uint32_t bb = smem_u32(ring + st * kSlotBytes);
+                        if (!resident) { mbar_wait(&bars->full[st], use & 1); tc_fence_after(); }
+                        const uint32_t bb = smem_u32(ring) + (resident ? roff : st * kSlotBytes);
+                        roff += last ? w3b : w2b;
                         const uint64_t b_hi = make_smem_desc(bb, 128, 256), b_lo = make_smem_desc(bb + lo_off, 128, 256);
                         const uint64_t a_hi = make_smem_desc(a0 + kb * 256, 128, a_sbo);
                         const uint64_t a_l = make_smem_desc(a0 + a_lo + kb * 256, 128, a_sbo);
                         umma_f16(dcorr, a_l, b_hi, idesc, acc_c); acc_c = 1;
                         umma_f16(dcorr, a_hi, b_lo, idesc, 1);
                         umma_f16(dmain, a_hi, b_hi, idesc, acc_m); acc_m = 1;
-                        umma_commit(&bars->empty[st]);
+                        if (!resident) umma_commit(&bars->empty[st]);
                     }
                     umma_commit(&bars->acc_ready);
                 }
