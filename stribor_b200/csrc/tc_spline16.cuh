@@ -474,18 +474,57 @@ __device__ __forceinline__ void rqs16_backward(float2* t, const BinSearch16& bs,
         float ld_own;
         rqs_inverse_in_bin(b, x, xe, ld_own);
     }
-    Dual<RQ_N> S, L;
-    rqs_bin_dual(xe, k0.x, k1.x, k0.y, k1.y, d0, d1, S, L);
+    // Hand-written reverse sweep through the in-bin map S and L = log dS/dx (rational_quadratic_spline.py:
+    // 236-248) instead of 7-variable forward duals: ~4x fewer instructions.  With w = x_k+1 - x_k,
+    // h = y_k+1 - y_k, delta = h / w, theta = (x - x_k) / w, tt = theta (1 - theta):
+    //   N = h (delta theta^2 + d0 tt),  D = delta + (d0 + d1 - 2 delta) tt,  S = y_k + N / D,
+    //   P = d1 theta^2 + 2 delta tt + d0 (1 - theta)^2,  M = delta^2 P,  L = log M - 2 log D.
+    // F = aS S + aL L is differentiated for the adjoint weights (aS, aL): (g_out, g_ld) in the forward
+    // direction; in the inverse direction x = S^-1(y), ld = -L(x), the implicit-function theorem gives
+    // g_y = (g_out - g_ld L_x) / S_x and the parameter gradients are those of F with (aS, aL) = (-g_y, -g_ld).
     float gq[RQ_N];
-    if (!INVERSE) {
-#pragma unroll
-        for (int i = 0; i < RQ_N; ++i) gq[i] = g_out * S.d[i] + g_ld * L.d[i];
-    } else {
-        const float gl = (xe >= lo && xe <= hi) ? g_ld : 0.f;       // recovered point outside the box: ld = 0
-        const float gy = (g_out - gl * L.d[RQ_X]) / S.d[RQ_X];
-        gq[RQ_X] = gy;
-#pragma unroll
-        for (int i = 1; i < RQ_N; ++i) gq[i] = -S.d[i] * gy - gl * L.d[i];
+    {
+        const float xk = k0.x, xk1 = k1.x, yk = k0.y, yk1 = k1.y;
+        const float w = xk1 - xk, h = yk1 - yk;
+        const float iw = 1.f / w;
+        const float delta = h * iw;
+        const float theta = (xe - xk) * iw, omt = 1.f - theta, tt = theta * omt, om2t = 1.f - 2.f * theta;
+        const float sd = d0 + d1 - 2.f * delta;
+        const float Q = delta * theta * theta + d0 * tt;              // N = h Q
+        const float N = h * Q;
+        const float D = delta + sd * tt;
+        const float P = d1 * theta * theta + 2.f * delta * tt + d0 * omt * omt;
+        const float M = delta * delta * P;
+        const float iD = 1.f / D, iM = 1.f / M;
+        // partials wrt theta (for S_x, L_x and the sweep)
+        const float N_t = h * (2.f * delta * theta + d0 * om2t);
+        const float D_t = sd * om2t;
+        const float M_t = delta * delta * (2.f * d1 * theta + 2.f * delta * om2t - 2.f * d0 * omt);
+        const float S_x = M * iD * iD;                               // dS/dx = exp(L)
+        const float L_x = (M_t * iM - 2.f * D_t * iD) * iw;
+        float aS, aL;
+        if (!INVERSE) {
+            aS = g_out; aL = g_ld;
+            gq[RQ_X] = g_out * S_x + g_ld * L_x;
+        } else {
+            const float gl = (xe >= lo && xe <= hi) ? g_ld : 0.f;       // recovered point outside the box: ld = 0
+            const float gy = (g_out - gl * L_x) / S_x;
+            gq[RQ_X] = gy;
+            aS = -gy; aL = -gl;
+        }
+        const float F_N = aS * iD;
+        const float F_D = -aS * N * iD * iD - 2.f * aL * iD;
+        const float F_M = aL * iM;
+        const float F_delta = F_N * h * theta * theta + F_D * (1.f - 2.f * tt) + F_M * (2.f * delta * P + 2.f * delta * delta * tt);
+        const float F_theta = F_N * N_t + F_D * D_t + F_M * M_t;
+        float F_h = F_N * Q + F_delta * iw;
+        const float F_w = -(F_delta * delta + F_theta * theta) * iw;
+        gq[RQ_D0] = F_N * h * tt + F_D * tt + F_M * delta * delta * omt * omt;
+        gq[RQ_D1] = F_D * tt + F_M * delta * delta * theta * theta;
+        gq[RQ_XK1] = F_w;
+        gq[RQ_XK] = -F_theta * iw - F_w;
+        gq[RQ_YK1] = F_h;
+        gq[RQ_YK] = aS - F_h;
     }
     g_x = gq[RQ_X];
     const bool first = (k == 0), last = (k == kBins - 1);
