@@ -130,6 +130,36 @@ __device__ __forceinline__ void stg256(float* p, const float* v) {
                  : "memory");
 }
 
+// One conditioning value -> its three bf16 parts at (row r, slot m) of the A1 operand (K-major core-matrix
+// layout, 64 slots: 1024 B per 8-row group, 128 B per 8-slot group)
+__device__ __forceinline__ uint8_t* a1_addr(uint8_t* abuf, int r, int m) {
+    return abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
+}
+__device__ __forceinline__ void a1_put(uint8_t* abuf, int r, int m, float v) {
+    __nv_bfloat16 p0, p1, p2;
+    split_bf16x3(v, p0, p1, p2);
+    uint8_t* dst = a1_addr(abuf, r, m);
+    *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
+    *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
+    *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+}
+// four consecutive slots (m % 4 == 0): 8-byte stores
+__device__ __forceinline__ void a1_put4(uint8_t* abuf, int r, int m, const float4& v) {
+    __align__(8) __nv_bfloat16 q0[4], q1[4], q2[4];
+    split_bf16x3(v.x, q0[0], q1[0], q2[0]); split_bf16x3(v.y, q0[1], q1[1], q2[1]);
+    split_bf16x3(v.z, q0[2], q1[2], q2[2]); split_bf16x3(v.w, q0[3], q1[3], q2[3]);
+    uint8_t* dst = a1_addr(abuf, r, m);
+    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(q0);
+    *reinterpret_cast<uint2*>(dst + kA1Part) = *reinterpret_cast<const uint2*>(q1);
+    *reinterpret_cast<uint2*>(dst + 2 * kA1Part) = *reinterpret_cast<const uint2*>(q2);
+}
+__device__ __forceinline__ void a1_zero(uint8_t* abuf, int r, int m) {
+    uint8_t* dst = a1_addr(abuf, r, m);
+    *reinterpret_cast<uint16_t*>(dst) = 0;
+    *reinterpret_cast<uint16_t*>(dst + kA1Part) = 0;
+    *reinterpret_cast<uint16_t*>(dst + 2 * kA1Part) = 0;
+}
+
 template <int KIND, bool INVERSE, bool BWD>
 __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -286,13 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                         const int m0 = hdr->colmap[c], m1 = hdr->colmap[c + 1], m2 = hdr->colmap[c + 2], m3 = hdr->colmap[c + 3];
                         if (m0 >= 0 && (m0 & 3) == 0 && m1 == m0 + 1 && m2 == m0 + 2 && m3 == m0 + 3) {
                             // four consecutive conditioning slots: 8-byte stores into the core-matrix layout
-                            __align__(8) __nv_bfloat16 q0[4], q1[4], q2[4];
-                            split_bf16x3(v.x, q0[0], q1[0], q2[0]); split_bf16x3(v.y, q0[1], q1[1], q2[1]);
-                            split_bf16x3(v.z, q0[2], q1[2], q2[2]); split_bf16x3(v.w, q0[3], q1[3], q2[3]);
-                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m0 >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m0 & 7) * 2;
-                            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(q0);
-                            *reinterpret_cast<uint2*>(dst + kA1Part) = *reinterpret_cast<const uint2*>(q1);
-                            *reinterpret_cast<uint2*>(dst + 2 * kA1Part) = *reinterpret_cast<const uint2*>(q2);
+                            a1_put4(abuf, r, m0, v);
                             if (copy_pass && live) reinterpret_cast<float4*>(og)[i] = BWD ? gv : v;
                         } else {
                             const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -301,12 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 if (mm[u] >= 0) {
-                                    __nv_bfloat16 p0, p1, p2;
-                                    split_bf16x3(vv[u], p0, p1, p2);
-                                    uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(mm[u] >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(mm[u] & 7) * 2;
-                                    *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
-                                    *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
-                                    *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                                    a1_put(abuf, r, mm[u], vv[u]);
                                     if (copy_pass && live) og[(size_t)r * d + c + u] = BWD ? gvv[u] : vv[u];
                                 } else {
                                     const int sl = -mm[u] - 1;
@@ -325,12 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                         const float gv = (BWD && live) ? __ldg(gg + i) : 0.f;
                         const int m = hdr->colmap[c];
                         if (m >= 0) {
-                            __nv_bfloat16 p0, p1, p2;
-                            split_bf16x3(v, p0, p1, p2);
-                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
-                            *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
-                            *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
-                            *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                            a1_put(abuf, r, m, v);
                             if (copy_pass && live) og[i] = BWD ? gv : v;
                         } else {
                             xs[r * kTrStride - m - 1] = v;
@@ -342,10 +356,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                 const int npad = k1pad - n_cond;
                 for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
                     const int r = i / npad, m = n_cond + (i - r * npad);
-                    uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
-                    *reinterpret_cast<uint16_t*>(dst) = 0;
-                    *reinterpret_cast<uint16_t*>(dst + kA1Part) = 0;
-                    *reinterpret_cast<uint16_t*>(dst + 2 * kA1Part) = 0;
+                    a1_zero(abuf, r, m);
                 }
             }
             fence_proxy_async_smem();
@@ -556,6 +567,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
 // (L2-resident, red.global.add.v4.f32) -- summation order over tiles is not deterministic.
 // Left to the caller: gW1 = g_pre^T x_cond, gb1 = sum g_pre, g_x[cond] += g_pre W1[:, cond] (K = 64 products).
 namespace train {
+#ifndef STB_TRAIN_EXP
+#define STB_TRAIN_EXP 0     // profiling builds only: 1 no gW2 atomics, 2 no element gradient, 4 no G products
+#endif
 constexpr int kHPad = 80;                                         // h operand columns: 64 hidden | 1 | 0 x 15
 constexpr uint32_t kHSbo = (kHPad / 8) * 128;                     // 1280: next 8 rows of the h operand
 constexpr uint32_t kHLo = kTileRows * kHPad * 2;                  // 20480: lo part
@@ -773,7 +787,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                     // [gW2chunk | gb2] = G^T . [h | 1] : K = 128 rows, both operands MN-major views
                     uint32_t acc = 0;
 #pragma unroll
-                    for (int p = 0; p < 3; ++p) {
+                    for (int p = (STB_TRAIN_EXP & 4) ? 2 : 0; p < 3; ++p) {
                         const uint32_t aa = (p == 0) ? g_lo : g_hi, bb = (p == 1) ? a_lo : a_hi;
 #pragma unroll
                         for (int ks = 0; ks < kTileRows / 16; ++ks) {
@@ -869,13 +883,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                         gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(gv.x), fabsf(gv.y)), fmaxf(fabsf(gv.z), fabsf(gv.w))));
                         const int m0 = hdr->colmap[c], m1 = hdr->colmap[c + 1], m2 = hdr->colmap[c + 2], m3 = hdr->colmap[c + 3];
                         if (m0 >= 0 && (m0 & 3) == 0 && m1 == m0 + 1 && m2 == m0 + 2 && m3 == m0 + 3) {
-                            __align__(8) __nv_bfloat16 q0[4], q1[4], q2[4];
-                            split_bf16x3(v.x, q0[0], q1[0], q2[0]); split_bf16x3(v.y, q0[1], q1[1], q2[1]);
-                            split_bf16x3(v.z, q0[2], q1[2], q2[2]); split_bf16x3(v.w, q0[3], q1[3], q2[3]);
-                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m0 >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m0 & 7) * 2;
-                            *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(q0);
-                            *reinterpret_cast<uint2*>(dst + kA1Part) = *reinterpret_cast<const uint2*>(q1);
-                            *reinterpret_cast<uint2*>(dst + 2 * kA1Part) = *reinterpret_cast<const uint2*>(q2);
+                            a1_put4(abuf, r, m0, v);
                             if (copy_pass && live) reinterpret_cast<float4*>(og)[i] = gv;
                         } else {
                             const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -884,12 +892,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 if (mm[u] >= 0) {
-                                    __nv_bfloat16 p0, p1, p2;
-                                    split_bf16x3(vv[u], p0, p1, p2);
-                                    uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(mm[u] >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(mm[u] & 7) * 2;
-                                    *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
-                                    *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
-                                    *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                                    a1_put(abuf, r, mm[u], vv[u]);
                                     if (copy_pass && live) og[(size_t)r * d + c + u] = gvv[u];
                                 } else {
                                     xs[r * kTrStride - mm[u] - 1] = vv[u];
@@ -907,12 +910,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                         gmax = fmaxf(gmax, fabsf(gv));
                         const int m = hdr->colmap[c];
                         if (m >= 0) {
-                            __nv_bfloat16 p0, p1, p2;
-                            split_bf16x3(v, p0, p1, p2);
-                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
-                            *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
-                            *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
-                            *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                            a1_put(abuf, r, m, v);
                             if (copy_pass && live) og[i] = gv;
                         } else {
                             xs[r * kTrStride - m - 1] = v;
@@ -922,10 +920,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                 const int npad = k1pad - n_cond;
                 for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
                     const int r = i / npad, m = n_cond + (i - r * npad);
-                    uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
-                    *reinterpret_cast<uint16_t*>(dst) = 0;
-                    *reinterpret_cast<uint16_t*>(dst + kA1Part) = 0;
-                    *reinterpret_cast<uint16_t*>(dst + 2 * kA1Part) = 0;
+                    a1_zero(abuf, r, m);
                 }
             }
             float g_ld = 0.f;
@@ -997,8 +992,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                         tmem_ld16(col + hh2 * 16, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
+                        for (int i = 0; i < 16; i += 4) {
+                            if (STB_TRAIN_EXP & 1) { if (v[i] == 123.456f) dst[0] = v[i + 1]; continue; }
                             red_add4(dst + hh2 * 16 + i, v[i] * inv_sigma, v[i + 1] * inv_sigma, v[i + 2] * inv_sigma, v[i + 3] * inv_sigma);
+                        }
                     }
                     if (g == 1) {
                         float w8[8];
@@ -1051,8 +1048,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                     kk = bs.k;
                     const float u0 = (kk == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + (kk > 0 ? kk - 1 : 0)]);
                     const float u1 = (kk == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + (kk < kBins - 1 ? kk : 0)]);
-                    if (inside) {
+                    if (inside && !(STB_TRAIN_EXP & 2)) {
                         rqs16_backward<INVERSE>(t, bs, ee, eo, u0, u1, lo, hi, xv, go, g_ld, gx, gu0, gu1);
+                    } else if (STB_TRAIN_EXP & 2) {
+                        gx = go + u0 * 1e-30f + u1 * 1e-30f + t[3].x * 1e-30f;
                     } else {
 #pragma unroll
                         for (int i = 0; i < kBins; ++i) t[i] = f2(0.f);
@@ -1179,21 +1178,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                         const int m = hdr->colmap[c];
                         if (m >= 0) {
                             const float v = (r < nrows) ? __ldg(xg + i) : 0.f;
-                            __nv_bfloat16 p0, p1, p2;
-                            split_bf16x3(v, p0, p1, p2);
-                            uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
-                            *reinterpret_cast<__nv_bfloat16*>(dst) = p0;
-                            *reinterpret_cast<__nv_bfloat16*>(dst + kA1Part) = p1;
-                            *reinterpret_cast<__nv_bfloat16*>(dst + 2 * kA1Part) = p2;
+                            a1_put(abuf, r, m, v);
                         }
                     }
                     const int npad = kK1 - n_cond;               // all 64 slots are read as N
                     for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
                         const int r = i / npad, m = n_cond + (i - r * npad);
-                        uint8_t* dst = abuf + (uint32_t)(r >> 3) * 1024 + (uint32_t)(m >> 3) * 128 + (uint32_t)(r & 7) * 16 + (uint32_t)(m & 7) * 2;
-                        *reinterpret_cast<uint16_t*>(dst) = 0;
-                        *reinterpret_cast<uint16_t*>(dst + kA1Part) = 0;
-                        *reinterpret_cast<uint16_t*>(dst + 2 * kA1Part) = 0;
+                        a1_zero(abuf, r, m);
                     }
                 }
                 fence_proxy_async_smem();
