@@ -37,8 +37,23 @@ METRIC = 'log_prob samples/s, 8-layer spline coupling d=64'
 L2_BYTES = 126 << 20
 
 
-# NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr: stdout carries the ONE JSON line
-os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+# stdout carries the ONE JSON line and nothing else: the process's fd 1 is pointed at stderr for the whole
+# run (NCCL's version banner / NCCL_DEBUG output, any library print) and the result goes to the saved fd.
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + '\n')
+    out.flush()
 
 
 def parse():
@@ -188,7 +203,7 @@ def run_reference(args):
     value = rows * args.steps / dt
     sample = (f'{rows} rows per step of the same workload; oracle port of the reference (torch CPU ops, '
               f'no O(N^2) domain re-check), {n_threads} threads, {cpu_model()}')
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
@@ -196,7 +211,7 @@ def run_reference(args):
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': n_threads, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+    })
 
 
 # -------------------------------------------------------------------------------------------
@@ -285,11 +300,11 @@ def run_side(args):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_step = tm.item() / args.steps
     if rank == 0:
-        print(json.dumps({'metric': f'{args.workload} throughput', 'value': per_step / (ms_step * 1e-3), 'unit': unit,
+        emit({'metric': f'{args.workload} throughput', 'value': per_step / (ms_step * 1e-3), 'unit': unit,
                           'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
                           'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
                           'data': 'synthetic', 'config': {'workload': name},
-                          'gpu_launches': int(_ops.launch_count() - n0)}))
+                          'gpu_launches': int(_ops.launch_count() - n0)})
     if world > 1:
         dist.destroy_process_group()
 
@@ -299,6 +314,7 @@ def run_side(args):
 # -------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == 'reference':
         run_reference(args)
         return
@@ -462,7 +478,7 @@ def main():
                       'unmodified reference has an O(N^2) domain re-check on the quadratic path '
                       '(57 samples/s at 256-row chunks, BASELINE.md) that the port omits'}
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
