@@ -23,6 +23,9 @@ def run(name, case, rows_list=(1, 255, 257, 700), grad=False):
     print('ok', name, flush=True)
 run('tc quadratic', cases._mk_flow('quadratic', 64, [64], 2, 16, 8, 1)(), grad=True)
 run('tc cubic d63', cases._mk_flow('cubic', 63, [64], 2, 16, 8, 2, masks=('parity_even', 'ordered_left_half'))(), grad=True)
+run('wide quadratic d128 (128-row kernel, fused backward)', cases._mk_flow('quadratic', 128, [64], 2, 16, 8, 5)(), rows_list=(1, 127, 300), grad=True)
+run('wide cubic d66 parity (odd chunk count)', cases._mk_flow('cubic', 66, [64], 2, 16, 8, 6, masks=('parity_even', 'parity_odd'))(), rows_list=(1, 130), grad=True)
+run('chain 12 layers d30', cases._mk_flow('quadratic', 30, [64], 12, 16, 8, 7)(), rows_list=(1, 255, 600))
 run('tc affine 256x256', cases._mk_flow('affine', 64, [256, 256], 2, 0, 8, 3)(), grad=True)
 run('tc affine d30 h128', cases._mk_flow('affine', 30, [128], 2, 0, 8, 4)())
 run('generic quadratic d5', cases.build_case('quadratic_d5_parity'), rows_list=(1, 33))
