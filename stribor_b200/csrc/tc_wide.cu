@@ -580,6 +580,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
 // (L2-resident, red.global.add.v4.f32) -- summation order over tiles is not deterministic.
 // Left to the caller: gW1 = g_pre^T x_cond, gb1 = sum g_pre, g_x[cond] += g_pre W1[:, cond] (K = 64 products).
 namespace train {
+constexpr int kTEpiWarp0 = 3;                                     // warp 0 producer, warps 1 / 2 UMMA issuers (F / G)
+constexpr int kTThreads = (kTEpiWarp0 + kEpiWarps) * 32;          // 608
 #ifndef STB_TRAIN_EXP
 #define STB_TRAIN_EXP 0     // profiling builds only: 1 no gW2 atomics, 2 no element gradient, 4 no G products
 #endif
@@ -648,7 +650,7 @@ __device__ __forceinline__ void put_g8(uint8_t* dst_hi, const float* v, float si
 }
 
 template <int KIND, bool INVERSE>
-__global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A) {
+__global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem + kSmXs);
     uint8_t* abuf = smem + kSmA;
@@ -716,14 +718,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
             }
         }
     } else if (warp == 1) {
-        // ======================= UMMA issuer ======================================================
+        // ======================= UMMA issuer F: the forward recompute (GEMM1, GEMM2 chunks) =======
+        // Two issuer threads: with one, a wait for the epilogue's gradients (G) held back a recompute GEMM
+        // whose operands were ready, and the other way round.
         if (lane == 0) {
             const uint32_t idesc1 = make_idesc(FMT_BF16, 128, kHid);
             const uint32_t idesc2 = make_idesc(FMT_F16, 128, kChunkN);
-            const uint32_t idesc_h = make_idesc(FMT_F16, 128, kHid) | kIdescBMajorMN;
-            const uint32_t idesc_w = make_idesc(FMT_F16, 128, kHPad) | kIdescAMajorMN | kIdescBMajorMN;
             const uint32_t a_hi = smem_u32(abuf), a_lo = a_hi + kHLo;
-            const uint32_t g_hi = smem_u32(gbuf), g_lo = g_hi + kGLo;
             uint32_t cc = 0, cb = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 const uint32_t tpar = it & 1;
@@ -748,11 +749,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                     umma_commit(&bars->b_empty[st]);
                     ++cc;
                 }
-                // forward recompute of chunk c (F) runs up to three chunks ahead of the gradient products (G):
-                //   F0 F1 F2 | G0 F3 | G1 F4 | ...   (stage of chunk c is released by G(c))
-                const uint32_t cc0 = cc;                        // ring index of chunk 0 of this tile
-                auto issue_f = [&](int c) {
-                    const uint32_t ci = cc0 + (uint32_t)c, st = ci % kStages, use = ci / kStages;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const uint32_t ci = cc + (uint32_t)c, st = ci % kStages, use = ci / kStages;
                     mbar_wait_relaxed(&bars->b_full[st], use & 1);
                     const uint32_t n = cb + (uint32_t)c, buf = n & 1, buse = n >> 1;
                     if (c == 0) mbar_wait_relaxed(&bars->h_ready, tpar);
@@ -772,8 +770,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                         }
                     }
                     umma_commit(&bars->acc_full[buf]);
-                };
-                auto issue_g = [&](int c) {
+                }
+                cc += (uint32_t)n_items;
+                cb += (uint32_t)n_chunks;
+            }
+        }
+    } else if (warp == 2) {
+        // ======================= UMMA issuer G: the gradient products ==============================
+        if (lane == 0) {
+            const uint32_t idesc_h = make_idesc(FMT_F16, 128, kHid) | kIdescBMajorMN;
+            const uint32_t idesc_w = make_idesc(FMT_F16, 128, kHPad) | kIdescAMajorMN | kIdescBMajorMN;
+            const uint32_t a_hi = smem_u32(abuf), a_lo = a_hi + kHLo;
+            const uint32_t g_hi = smem_u32(gbuf), g_lo = g_hi + kGLo;
+            uint32_t cc = 0, cb = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const uint32_t tpar = it & 1;
+                const uint32_t cc0 = cc + 1;                    // ring index of chunk 0 of this tile (after the W1 item)
+                for (int c = 0; c < n_chunks; ++c) {
                     const uint32_t ci = cc0 + (uint32_t)c, st = ci % kStages;
                     const uint32_t n = cb + (uint32_t)c, wb = n & 1, wuse = n >> 1;
                     mbar_wait_relaxed(&bars->g_ready, n & 1);
@@ -811,12 +824,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                     }
                     umma_commit(&bars->w_full[wb]);
                     umma_commit(&bars->g_empty[n & 1]);
-                    umma_commit(&bars->b_empty[st]);
-                };
-                for (int c = 0; c < n_chunks && c < 3; ++c) issue_f(c);
-                for (int c = 0; c < n_chunks; ++c) {
-                    issue_g(c);
-                    if (c + 3 < n_chunks) issue_f(c + 3);
+                    umma_commit(&bars->b_empty[st]);           // the chunk's ring stage is released here
                 }
                 umma_commit(&bars->acch_full);
                 if (full) {
@@ -852,15 +860,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_train_kernel(const Args A
                     umma_commit(&bars->d_full);
                     umma_commit(&bars->b_empty[st]);
                 }
-                cc += (uint32_t)n_items;
+                cc += 1u + (uint32_t)n_items;
                 cb += (uint32_t)n_chunks;
             }
         }
     } else {
         // ======================= loader + epilogue warps ==========================================
         const int q = warp & 3;
-        const int r4 = (warp - kEpiWarp0) >> 2;
-        const int etid = tid - kEpiWarp0 * 32;
+        const int r4 = (warp - kTEpiWarp0) >> 2;
+        const int etid = tid - kTEpiWarp0 * 32;
         const int rloc = q * 32 + lane;
         const uint32_t h_row_off = (uint32_t)(rloc >> 3) * kHSbo + (uint32_t)(rloc & 7) * 16;
         const uint32_t g_row_off = (uint32_t)(rloc >> 3) * kGSbo + (uint32_t)(rloc & 7) * 16;
@@ -1522,7 +1530,7 @@ int tcw_layer_backward_fused(const stb_layer* L, const void* image, int directio
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train::kSmemBytes);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int grid = (int)min((long long)n_sm, tiles);
-    kern<<<grid, kThreads, train::kSmemBytes, stream>>>(A);
+    kern<<<grid, train::kTThreads, train::kSmemBytes, stream>>>(A);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_wide_train_kernel launch: %s", cudaGetErrorString(e));
