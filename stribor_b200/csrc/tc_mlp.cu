@@ -37,10 +37,7 @@ constexpr int kMaxTr = 32;
 constexpr int kNOut = 64;                  // [log_scale(32) | shift(32)] of the transformed dims
 constexpr int kMaxDim = 64;
 constexpr int kMaxH = 256;
-constexpr int kXsStride = kMaxDim + 1;
 constexpr int kStages = 3;
-constexpr int kThreads = 576;
-constexpr int kEpiThreads = 512;
 constexpr int kEpiWarp0 = 2;
 constexpr uint32_t kSlotBytes = 16384;     // one K block: [<=256 x 16] fp16 hi | lo
 constexpr uint32_t kMagic = 0x53544d31u;
@@ -69,16 +66,31 @@ __host__ __device__ inline uint32_t packed_bytes(int H, int n_hidden) {
     return kOffW + 6 * w1_block_bytes(H) + (n_hidden == 2 ? (H / 16) * w2_block_bytes(H) : 0) + (H / 16) * w3_block_bytes();
 }
 
-// shared memory map (A operand size depends on H)
-constexpr uint32_t kSmXs = 0;                                        // float [128][65]
-constexpr uint32_t kSmRing = kSmXs + kRows * kXsStride * 4;          // 3 x 16 KB
-constexpr uint32_t kSmSmall = kSmRing + kStages * kSlotBytes;        // header + biases
-constexpr uint32_t kSmLd = kSmSmall + 3584;                          // float [4][128] log-det partials
-constexpr uint32_t kSmT = kSmLd + 4 * kRows * 4;                     // float [128] time input
-constexpr uint32_t kSmBar = kSmT + kRows * 4;
-constexpr uint32_t kSmA = kSmBar + 256;                              // A operand: 128 x H fp16 hi | lo (>= 24 KB)
-static_assert(kSmRing % 16 == 0 && kSmSmall % 16 == 0 && kSmA % 16 == 0, "alignment");
-__host__ __device__ inline uint32_t smem_bytes(int H) { return kSmA + (uint32_t)kRows * H * 4; }
+// Two configurations of the same kernel (NCG = epilogue warps per TMEM sub-partition = column groups):
+//   NCG = 4  16 epilogue warps, one CTA per SM, dim <= 64, H <= 256, 512 TMEM columns
+//   NCG = 2   8 epilogue warps, TWO CTAs per SM (dim <= 32, H = 64, weights resident, 256 TMEM columns):
+//             small conditioners (configs[3]) are latency-bound per tile -- a second CTA's phases fill the
+//             other's waits
+template <int NCG>
+struct Cfg {
+    static constexpr int kEpiThreads = NCG * 4 * 32;
+    // NCG = 2: padded to 12 warps -- the register file is allocated for the block rounded up to a multiple of
+    // 4 warps, and two CTAs per SM need <= 80 registers per thread at that size (ptxas derives it from here)
+    static constexpr int kThreads = (NCG == 4) ? kEpiThreads + 64 : 384;
+    static constexpr int kXs = (NCG == 4) ? kMaxDim + 1 : 33;               // row stride of the x tile
+    static constexpr uint32_t kColCorr = (NCG == 4) ? 256u : 128u;
+    static constexpr uint32_t kTmemCols = (NCG == 4) ? 512u : 256u;
+    // shared memory map (A operand size depends on H)
+    static constexpr uint32_t kSmXs = 0;                                     // float [128][kXs]
+    static constexpr uint32_t kSmRing = (kSmXs + kRows * kXs * 4 + 127) & ~127u;   // 3 x 16 KB
+    static constexpr uint32_t kSmSmall = kSmRing + kStages * kSlotBytes;     // header + biases
+    static constexpr uint32_t kSmLd = kSmSmall + 3584;                       // float [4][128] log-det partials
+    static constexpr uint32_t kSmT = kSmLd + 4 * kRows * 4;                  // float [128] time input
+    static constexpr uint32_t kSmBar = kSmT + kRows * 4;
+    static constexpr uint32_t kSmA = kSmBar + 256;                           // A operand: 128 x H fp16 hi | lo (>= 24 KB)
+    static_assert(kSmRing % 16 == 0 && kSmSmall % 16 == 0 && kSmA % 16 == 0, "alignment");
+    static constexpr uint32_t smem_bytes(int H) { return kSmA + (uint32_t)kRows * H * 4; }
+};
 
 struct Bars {
     uint64_t setup;
@@ -87,7 +99,7 @@ struct Bars {
     uint32_t tmem_base;
 };
 
-constexpr uint32_t kColMain = 0, kColCorr = 256, kTmemCols = 512;
+constexpr uint32_t kColMain = 0;
 
 struct Args {
     const uint8_t* packed;
@@ -119,25 +131,31 @@ __device__ __forceinline__ float tanh_fast(float v) {                 // ~3e-7 a
     return copysignf(fdiv(1.f - t, 1.f + t), v);
 }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A) {
+template <int NCG>
+__global__ void __launch_bounds__(Cfg<NCG>::kThreads, (NCG == 4) ? 1 : 2) tc_mlp_affine_kernel(const Args A) {
+    using C = Cfg<NCG>;
+    constexpr int kEpiThreads = C::kEpiThreads;
+    constexpr int kXsStride = C::kXs;
+    constexpr uint32_t kColCorr = C::kColCorr, kTmemCols = C::kTmemCols;
+    constexpr uint32_t kSmSmall = C::kSmSmall;
     extern __shared__ __align__(1024) uint8_t smem[];
-    float* xs = reinterpret_cast<float*>(smem + kSmXs);
-    uint8_t* ring = smem + kSmRing;
+    float* xs = reinterpret_cast<float*>(smem + C::kSmXs);
+    uint8_t* ring = smem + C::kSmRing;
     const Header* hdr = reinterpret_cast<const Header*>(smem + kSmSmall);
     const float* b1s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB1);
     const float* b2s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB2);
     const float* b3s = reinterpret_cast<const float*>(smem + kSmSmall + kOffB3);
-    float* ld_s = reinterpret_cast<float*>(smem + kSmLd);
-    float* t_s = reinterpret_cast<float*>(smem + kSmT);
-    Bars* bars = reinterpret_cast<Bars*>(smem + kSmBar);
-    uint8_t* abuf = smem + kSmA;
+    float* ld_s = reinterpret_cast<float*>(smem + C::kSmLd);
+    float* t_s = reinterpret_cast<float*>(smem + C::kSmT);
+    Bars* bars = reinterpret_cast<Bars*>(smem + C::kSmBar);
+    uint8_t* abuf = smem + C::kSmA;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         mbar_init(&bars->setup, 1);
         for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-        mbar_init(&bars->a_ready, 16);
+        mbar_init(&bars->a_ready, NCG * 4);
         mbar_init(&bars->acc_ready, 1);
         fence_mbar_init();
     }
@@ -259,10 +277,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                 }
             }
         }
-    } else {
+    } else if (warp < kEpiWarp0 + NCG * 4) {
         // ======================= epilogue warps ====================================================
         const int q = warp & 3;
-        const int cg = (warp - ((q >= kEpiWarp0) ? q : q + 4)) >> 2;      // column group 0..3
+        const int cg = (warp - ((q >= kEpiWarp0) ? q : q + 4)) >> 2;      // column group 0..NCG-1
         const int etid = tid - kEpiWarp0 * 32;
         const int row = q * 32 + lane;
         float* xrow = xs + row * kXsStride;
@@ -312,17 +330,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
             named_bar_sync(1, kEpiThreads);
             // ---- A1: 8 of the 32 conditioning columns of this row, three bf16 parts ---------------------
             {
-                const uint32_t off = (uint32_t)(row >> 3) * 512 + (uint32_t)(row & 7) * 16 + cg * 128;
-                __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
+#pragma unroll 1
+                for (int kc = cg; kc < kK1 / 8; kc += NCG) {
+                    const uint32_t off = (uint32_t)(row >> 3) * 512 + (uint32_t)(row & 7) * 16 + kc * 128;
+                    __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int k = cg * 8 + u;
-                    const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[row] : 0.f);
-                    split_bf16x3(v, q0[u], q1[u], q2[u]);
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = kc * 8 + u;
+                        const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[row] : 0.f);
+                        split_bf16x3(v, q0[u], q1[u], q2[u]);
+                    }
+                    *reinterpret_cast<uint4*>(abuf + off) = *reinterpret_cast<const uint4*>(q0);
+                    *reinterpret_cast<uint4*>(abuf + a_part + off) = *reinterpret_cast<const uint4*>(q1);
+                    *reinterpret_cast<uint4*>(abuf + 2 * a_part + off) = *reinterpret_cast<const uint4*>(q2);
                 }
-                *reinterpret_cast<uint4*>(abuf + off) = *reinterpret_cast<const uint4*>(q0);
-                *reinterpret_cast<uint4*>(abuf + a_part + off) = *reinterpret_cast<const uint4*>(q1);
-                *reinterpret_cast<uint4*>(abuf + 2 * a_part + off) = *reinterpret_cast<const uint4*>(q2);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->a_ready);
@@ -333,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                 tc_fence_after();
                 const float sc = (layer == 0) ? 1.f : s_mid;
                 const float* bias = (layer == 0) ? b1s : b2s;
-                const int cols = H / 4;                          // this warp's share of the hidden units
+                const int cols = H / NCG;                        // this warp's share of the hidden units
                 const uint32_t a_row = (uint32_t)(row >> 3) * a_sbo + (uint32_t)(row & 7) * 16;
                 for (int cb = 0; cb < cols; cb += 16) {
                     const int c0 = cg * cols + cb;
@@ -368,17 +389,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
             mbar_wait_sleep(&bars->acc_ready, acc_use & 1, 64); ++acc_use;
             tc_fence_after();
             float ld_acc = 0.f;
-            {
+#pragma unroll 1
+            for (int og = cg; og < kMaxTr / 8; og += NCG) {
                 float lm[8], lc[8], sm[8], sc_[8];
-                tmem_ld8(tmem + lane_sel + kColMain + cg * 8, lm);
-                tmem_ld8(tmem + lane_sel + kColCorr + cg * 8, lc);
-                tmem_ld8(tmem + lane_sel + kColMain + kMaxTr + cg * 8, sm);
-                tmem_ld8(tmem + lane_sel + kColCorr + kMaxTr + cg * 8, sc_);
+                tmem_ld8(tmem + lane_sel + kColMain + og * 8, lm);
+                tmem_ld8(tmem + lane_sel + kColCorr + og * 8, lc);
+                tmem_ld8(tmem + lane_sel + kColMain + kMaxTr + og * 8, sm);
+                tmem_ld8(tmem + lane_sel + kColCorr + kMaxTr + og * 8, sc_);
                 tmem_ld_wait();
-                tc_fence_before();
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int ji = cg * 8 + u;
+                    const int ji = og * 8 + u;
                     if (ji < n_tr) {
                         const int j = hdr->tr_idx[ji];
                         float ls = fmaf(lm[u] + lc[u], s_out, b3s[ji]);
@@ -394,10 +415,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_mlp_affine_kernel(const Args A
                     }
                 }
             }
+            tc_fence_before();
             ld_s[cg * kRows + row] = ld_acc;
             named_bar_sync(1, kEpiThreads);
             if (cg == 0 && want_ld && row < nrows) {
-                float tot = (ld_s[row] + ld_s[kRows + row]) + (ld_s[2 * kRows + row] + ld_s[3 * kRows + row]);
+                float tot = (NCG == 4) ? (ld_s[row] + ld_s[kRows + row]) + (ld_s[2 * kRows + row] + ld_s[3 * kRows + row])
+                                       : ld_s[row] + ld_s[kRows + row];
                 if (A.base_log_prob) {
                     float b = 0.f;
                     for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
@@ -629,12 +652,16 @@ int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const flo
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (n_sm <= 0) n_sm = 148;
     }
-    const uint32_t smem = smem_bytes(H);
+    // small conditioner on few dims (configs[3]): the 8-warp configuration, two CTAs per SM
+    const uint32_t w_total = 6 * w1_block_bytes(H) + (L->net.n_linear == 3 ? (H / 16) * w2_block_bytes(H) : 0) + (H / 16) * w3_block_bytes();
+    const bool small = (H == 64) && (L->dim <= 32) && (w_total <= kStages * kSlotBytes) && (tiles >= 2LL * n_sm);
+    const uint32_t smem = small ? Cfg<2>::smem_bytes(H) : Cfg<4>::smem_bytes(H);
     if (smem > 227 * 1024) return set_error(STB_ENOTSUP, "hidden width %d needs %u B of shared memory", H, smem);
-    cudaError_t e = cudaFuncSetAttribute(tc_mlp_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*kern)(Args) = small ? tc_mlp_affine_kernel<2> : tc_mlp_affine_kernel<4>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    const int grid = (int)min((long long)n_sm, tiles);
-    tc_mlp_affine_kernel<<<grid, kThreads, smem, stream>>>(A);
+    const int grid = (int)min((long long)(small ? 2 * n_sm : n_sm), tiles);
+    kern<<<grid, small ? Cfg<2>::kThreads : Cfg<4>::kThreads, smem, stream>>>(A);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_mlp_affine_kernel launch: %s", cudaGetErrorString(e));

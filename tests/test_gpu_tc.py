@@ -180,6 +180,35 @@ def test_affine_tensor_path_matches_generic_and_oracle(d, hidden, masks, monkeyp
     assert (li_t - li_g).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize('d,kind', [(16, 'cont'), (30, 'affine')])
+def test_small_conditioner_two_ctas_per_sm(d, kind, monkeypatch):
+    """Many rows of a small conditioner (dim <= 32, MLP[64]): the 8-warp configuration of tc_mlp.cu runs with two
+    CTAs per SM and resident weights.  Agreement with the CUDA-core kernel over every tile, ragged tail included."""
+    import numpy as np
+    rs = np.random.RandomState(977 + d)
+    rows = 2 * 148 * 128 + 12345
+    if kind == 'cont':
+        spec = [cases.cont_affine_spec(rs, d, [64], ('ordered_0', 'ordered_1')[i % 2]) for i in range(2)]
+    else:
+        spec = cases._mk_flow('affine', d, [64], 2, 0, 8, 1234)()['spec']
+    x = cases._x(rs, (rows, d)).to(DEV)
+    t = cases._x(rs, (rows, 1), uniform=True).to(DEV)
+    out = {}
+    for force in ('0', '1'):
+        monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', force)
+        layers = [l.to(DEV) for l in layers_from_spec(spec)]
+        with torch.no_grad():
+            if kind == 'cont':
+                assert (layers[0].describe(d, 0, torch.device(DEV))['packed'] is not None) == (force == '0')
+                out[force] = (st.NeuralFlow(layers)(x, t=t), None)
+            else:
+                flow = st.NormalizingFlow(st.UnitNormal(d), layers)
+                out[force] = (flow.inverse(x), flow.log_prob(x))
+    assert (out['0'][0] - out['1'][0]).abs().max().item() < 5e-5
+    if kind == 'affine':
+        assert (out['0'][1] - out['1'][1]).abs().max().item() < 2e-4
+
+
 @pytest.mark.parametrize('concat', [True, False])
 def test_continuous_affine_tensor_path(concat, monkeypatch):
     """NeuralFlow of ContinuousAffineCoupling layers on the tcgen05 path: oracle parity (with and
