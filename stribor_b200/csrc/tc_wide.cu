@@ -1233,10 +1233,18 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                     if (row_live) {
                         const float* gr = A.g_out + (size_t)(row0 + rloc) * d;
                         float* xr = A.g_x + (size_t)(row0 + rloc) * d;
+                        // all 16 loads first: load-then-store per element is a chain of exposed round trips (g_x may
+                        // alias g_out, so the compiler keeps the order)
+                        float go16[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int m = r4 * 16 + i;
-                            if (m < n_cond) { const int c = hdr->cond_idx[m]; xr[c] = __ldg(gr + c) + v[i]; }
+                            go16[i] = (m < n_cond) ? __ldg(gr + hdr->cond_idx[m]) : 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int m = r4 * 16 + i;
+                            if (m < n_cond) xr[hdr->cond_idx[m]] = go16[i] + v[i];
                         }
                     }
                     // gW1c[hid][slot] += D2 : TMEM lane = hidden unit (64 valid), 16 slots per warp
