@@ -139,3 +139,29 @@ def test_product_never_imports_oracle():
             if fn.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dp, fn)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, fn
+
+
+def test_backward_workspace_layout_constants_match_the_kernels():
+    """The Python side un-packs the fused backward's workspace (stribor_b200/_ops.py); its layout constants and the
+    packed column order must match tc_wide.cu (read from the source: no GPU needed)."""
+    import re
+    from stribor_b200 import _ops
+    src = open(os.path.join(ROOT, 'stribor_b200', 'csrc', 'tc_wide.cu')).read()
+
+    def const(name):
+        m = re.search(r'constexpr\s+int\s+' + name + r'\s*=\s*(\d+)\s*;', src)
+        assert m, name
+        return int(m.group(1))
+
+    assert _ops.G_PAD == const('kPPad') == 48
+    assert _ops.H_AUG == const('kHAug') == const('kWStride') == 72
+    # natural parameter p -> packed column (w_i, h_i interleaved, then the derivative columns): inverse of
+    # param_of_col() in the pack kernels
+    cols = _ops._packed_cols(torch.device('cpu')).tolist()
+    bins = 16
+
+    def param_of_col(c):
+        return (bins + (c >> 1) if (c & 1) else (c >> 1)) if c < 2 * bins else c
+
+    assert sorted(cols) == list(range(48))
+    assert all(param_of_col(c) == p for p, c in enumerate(cols))
