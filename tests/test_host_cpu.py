@@ -165,3 +165,50 @@ def test_backward_workspace_layout_constants_match_the_kernels():
 
     assert sorted(cols) == list(range(48))
     assert all(param_of_col(c) == p for p, c in enumerate(cols))
+
+
+def _spline_struct(dim, kind='quadratic', hidden=64, n_bins=16):
+    """stb_layer for Coupling(Spline(dim, n_bins), MLP(dim, [hidden], dim * P)) with an ordered mask; the weight
+    pointers are CPU tensors -- the host-side entry points below never dereference them."""
+    import ctypes as C
+    from stribor_b200 import _lib, _ops
+    P = 3 * n_bins - 1 if kind == 'quadratic' else 2 * n_bins + 2
+    mask_list = [0] * (dim // 2) + [1] * (dim - dim // 2)
+    meta = [_lib.RQS if kind == 'quadratic' else _lib.CUBIC, dim, 0, 1, 0, n_bins, 0, 0, _lib.ACTIVATIONS['Tanh'], 0,
+            2, 4, 0, 0, dim, hidden, dim * P] + mask_list
+    params = [torch.zeros(hidden, dim), torch.zeros(hidden), torch.zeros(dim * P, hidden), torch.zeros(dim * P)]
+    mask = torch.tensor(mask_list, dtype=torch.uint8)
+    L = _ops.make_struct(meta, [-4., 4., 0., 1., 0., 1.], mask, params, None)
+    L._keep = (params, mask)
+    return L
+
+
+def test_cabi_host_side_dispatch_without_a_gpu():
+    """Which layers get which tensor-core images / the fused backward, and argument validation: host logic of the
+    C ABI (no kernel is launched, no device pointer is touched)."""
+    import ctypes as C
+    from stribor_b200 import _lib
+    lib = _lib.lib()
+    tc_bytes = 8192 + 12288 + 16 * 24576                       # tc_layer.cu image (dim <= 64)
+    wide_bytes = 16384 + 24576 + 32 * 24576                    # tc_wide.cu image (dim <= 128)
+    ws = lambda rows: 4 * (rows * 72 + 64 * 48 * 72 + 64 * 64 + 64)
+    for kind in ('quadratic', 'cubic'):
+        L64, L128, L130 = _spline_struct(64, kind), _spline_struct(128, kind), _spline_struct(130, kind)
+        assert lib.stb_packed_bytes(C.byref(L64)) == tc_bytes + wide_bytes      # both images: 256-row inference + 128-row / backward
+        assert lib.stb_packed_bytes(C.byref(L128)) == wide_bytes
+        assert lib.stb_packed_bytes(C.byref(L130)) == 0                          # 65 transformed dims: CUDA-core kernel only
+        assert lib.stb_layer_backward_workspace_bytes(C.byref(L128), 1000) == ws(1000)
+        assert lib.stb_layer_backward_workspace_bytes(C.byref(L64), 7) == ws(7)
+        assert lib.stb_layer_backward_workspace_bytes(C.byref(L130), 1000) == 0
+    assert lib.stb_packed_bytes(C.byref(_spline_struct(64, hidden=32))) == 0     # MLP[32]: no tensor-core path
+    assert lib.stb_layer_backward_workspace_bytes(C.byref(_spline_struct(64, n_bins=8)), 10) == 0
+    # argument validation returns STB_EINVAL (-1) before anything is launched
+    L = _spline_struct(64)
+    dummy = C.c_void_p(0x1000)
+    assert lib.stb_flow_apply(C.byref(L), 0, 0, dummy, None, None, dummy, None, 0, 10, None) == _lib.E_INVAL
+    assert b'empty flow' in lib.stb_last_error()
+    assert lib.stb_layer_apply(C.byref(L), 7, dummy, None, None, dummy, None, 0, 0, 10, None) == _lib.E_INVAL
+    assert lib.stb_flow_log_prob(C.byref(L), 1, dummy, None, None, None, None, 10, None) == _lib.E_INVAL
+    # rows == 0 is a no-op that touches nothing
+    assert lib.stb_layer_apply(C.byref(L), 0, dummy, None, None, dummy, None, 0, 0, 0, None) == 0
+    assert lib.stb_flow_log_prob(C.byref(L), 1, dummy, None, None, dummy, dummy, 0, None) == 0
