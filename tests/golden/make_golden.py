@@ -155,6 +155,23 @@ def run_case(name, dtype):
 
 def main():
     blob = {}
+    only = [a for a in sys.argv[1:] if not a.startswith('-')]
+    if only:
+        # python make_golden.py CASE [CASE ...]: record just these cases and merge them into the existing file
+        path = os.path.join(HERE, 'reference_outputs.npz')
+        blob = dict(np.load(path))
+        for name in only:
+            r32 = run_case(name, torch.float32)
+            r64 = run_case(name, torch.float64)
+            for k, v in r32.items():
+                blob[f'{name}|{k}|f32'] = v
+            for k, v in r64.items():
+                if not k.endswith('.bins'):
+                    blob[f'{name}|{k}|f64'] = v
+            print(name, sorted(r32))
+        np.savez_compressed(path, **blob)
+        print('merged into', path, len(blob), 'arrays', os.path.getsize(path), 'bytes')
+        return
     for name in cases.CASES:
         r32 = run_case(name, torch.float32)
         r64 = run_case(name, torch.float64)
