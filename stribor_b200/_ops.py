@@ -205,13 +205,15 @@ def fused_backward_ok(L: '_lib.StbLayer') -> bool:
 
 
 def _fused_conditioner_backward(x, mask, params, packed, meta, fmeta, direction, g_y, g_ldj):
-    """Coupling(Spline, MLP[64]) on the tensor-core path: ONE kernel recomputes the conditioner from the
-    saved input and differentiates the spline (stb_layer_backward -> tc_wide.cu), leaving
-      g_net [rows, n_tr * 48]  gradient wrt the network output of the transformed dims
-      haug  [rows, 72]         hidden activations | 1 | 0...
-    The conditioner's own gradients are then plain dense products of those two (library GEMMs):
-      [gW2 | gb2] = g_net^T haug,  g_hidden = g_net W2,  g_pre = g_hidden * act'(hidden),
-      gW1 = g_pre^T x_cond,  gb1 = sum g_pre,  g_x[cond] += g_pre W1[:, cond]."""
+    """Coupling(Spline, MLP[64]) on the tensor-core path: ONE kernel (stb_layer_backward -> tc_wide.cu) recomputes
+    the conditioner from the saved input, differentiates the spline in registers and forms the conditioner's
+    gradient products on the tensor cores.  Three arrangements, selected by environment (default first):
+      fused           g_x complete; images of [gW2 | gb2], gW1 (conditioning slots) and gb1 come back in the
+                      workspace -- nothing left here but un-packing them
+      ..W1_LIB=1      as above without the first Linear: g_pre [rows, 64] comes back and
+                      gW1 = g_pre^T x_cond, gb1 = sum g_pre, g_x[cond] += g_pre W1[:, cond] are library GEMMs
+      ..GNET=1        two-step (quadratic only): g_net [rows, n_tr * 48] and [hidden | 1] come back, all four
+                      products are fp32 library GEMMs"""
     rows, dim = x.shape
     W1, b1, W2, b2 = params
     act = meta[8]

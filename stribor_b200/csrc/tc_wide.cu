@@ -578,7 +578,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
 // g_hidden accumulates in TMEM over the tile's chunks and becomes g_pre = g_hidden * act'(h) [rows, 64];
 // the per-(tile, chunk) gW2 partials are added to a [n_chunks * 96, 72] fp32 image in global memory
 // (L2-resident, red.global.add.v4.f32) -- summation order over tiles is not deterministic.
-// Left to the caller: gW1 = g_pre^T x_cond, gb1 = sum g_pre, g_x[cond] += g_pre W1[:, cond] (K = 64 products).
+// At the tile end the first Linear's products follow (g_w1 != NULL): g_x[cond] = g_out[cond] + g_pre W1[:, cond],
+// gW1 += g_pre^T x_cond (bf16x3 operands, MN-major views again), gb1 by warp shuffles; otherwise g_pre is written
+// and those three K = 64 products are left to the caller.
 namespace train {
 constexpr int kTEpiWarp0 = 3;                                     // warp 0 producer, warps 1 / 2 UMMA issuers (F / G)
 constexpr int kTThreads = (kTEpiWarp0 + kEpiWarps) * 32;          // 608
