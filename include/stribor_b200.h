@@ -138,6 +138,17 @@ int stb_layer_apply(const stb_layer* layer, int direction, const float* x, const
 int stb_layer_apply_diag(const stb_layer* layer, int direction, const float* x, const float* latent,
                          const float* t, float* y, float* ldiag, int64_t rows, void* stream);
 
+/* Parity instrument: stb_layer_apply that ALSO reports, per element, the bin the spline's knot search chose
+ * -- util/search_sorted.py:3-5 as called from util/rational_quadratic_spline.py:194-197 and
+ * util/cubic_spline.py:140-143 (STB_FORWARD searches the cumulative widths, STB_INVERSE the cumulative
+ * heights).  bins [rows, dim] int32: the bin index in [0, n_bins), or -1 for pass-through dims, for elements
+ * outside the spline box (identity tails) and for non-spline layers.  The call takes exactly the kernel
+ * path stb_layer_apply takes for this layer (tensor-core kernels when `packed` is set), so what it reports
+ * is the product path's own search, not a re-computation. */
+int stb_layer_apply_bins(const stb_layer* layer, int direction, const float* x, const float* latent,
+                         const float* t, float* y, float* ldj, int ldj_mode, int32_t* bins,
+                         int64_t rows, void* stream);
+
 /* Chain of layers, applied first-to-last (STB_FORWARD) or last-to-first with each layer
  * inverted (STB_INVERSE).  `out` may alias `x`.  ldj (nullable) receives the summed
  * log|det J| according to ldj_mode. */

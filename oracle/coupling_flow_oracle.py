@@ -477,6 +477,43 @@ def layer_apply(layer: Dict, x: Tensor, *, inverse: bool, latent: Optional[Tenso
     return out, (ld * (1 - mask)).sum(-1, keepdim=True)
 
 
+def layer_bins(layer: Dict, x: Tensor, *, inverse: bool, latent: Optional[Tensor] = None) -> Tensor:
+    """Bin index the knot search picks for every element of a spline layer: int64 [..., d], -1 for
+    out-of-box elements and for a coupling's pass-through dims (search_sorted.py:3-5 called at
+    rational_quadratic_spline.py:194-197 / cubic_spline.py:140-143: cumulative widths when
+    ``inverse`` is False, cumulative heights otherwise)."""
+    tr = layer['transform']
+    assert tr['kind'] in ('quadratic', 'cubic')
+    if layer['type'] == 'coupling':
+        mask = make_mask(layer['mask'], x.shape[-1]).to(x.dtype).expand_as(x)
+        cond = _conditioning(x, mask, latent)
+    else:
+        mask, cond = torch.zeros_like(x), latent
+    p = transform_params(tr, cond, x.dtype)
+    fn = rqs if tr['kind'] == 'quadratic' else cubic
+    bins = fn(x, p[0], p[1], p[2], inverse, tr.get('lower', 0), tr.get('upper', 1), return_bins=True)[2]
+    return torch.where(mask != 0, torch.full_like(bins, -1), bins)
+
+
+def layer_knots(layer: Dict, x: Tensor, *, inverse: bool, latent: Optional[Tensor] = None) -> Tensor:
+    """The knot positions ``layer_bins`` searches, in data units: [..., d, K + 1] (cumulative widths, or
+    heights when ``inverse``).  Test helper: distance of an element to the knot between two candidate bins."""
+    tr = layer['transform']
+    if layer['type'] == 'coupling':
+        mask = make_mask(layer['mask'], x.shape[-1]).to(x.dtype).expand_as(x)
+        cond = _conditioning(x, mask, latent)
+    else:
+        cond = latent
+    uw, uh, ud = transform_params(tr, cond, x.dtype)
+    lo, hi = tr.get('lower', 0), tr.get('upper', 1)
+    uw, uh, ud = (v.expand(*x.shape, -1) for v in (uw, uh, ud))
+    if tr['kind'] == 'quadratic':
+        cw, _, ch, _, _ = rqs_knots(uw, uh, ud, lo, hi, lo, hi)
+        return ch if inverse else cw
+    cw, ch = cubic_coefficients(uw, uh, ud[..., 0, None], ud[..., 1, None])[:2]
+    return (ch if inverse else cw) * (hi - lo) + lo
+
+
 def layer_log_det(layer: Dict, x: Tensor, **kw) -> Tensor:
     return layer_apply(layer, x, inverse=False, **kw)[1]
 

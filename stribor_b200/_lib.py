@@ -24,7 +24,8 @@ E_INVAL, E_CUDA, E_NOTSUP = -1, -2, -3
 LIB_PATH = os.environ.get('STRIBOR_B200_LIB') or \
     os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libstribor_b200.so')
 
-EXPORTS = ['stb_abi_version', 'stb_sizeof_layer', 'stb_last_error', 'stb_layer_apply', 'stb_layer_apply_diag', 'stb_flow_apply',
+EXPORTS = ['stb_abi_version', 'stb_sizeof_layer', 'stb_last_error', 'stb_layer_apply', 'stb_layer_apply_diag',
+           'stb_layer_apply_bins', 'stb_flow_apply',
            'stb_flow_log_prob', 'stb_unit_normal_log_prob', 'stb_layer_backward_workspace_bytes',
            'stb_layer_backward', 'stb_packed_bytes', 'stb_pack_layer', 'stb_layer_uses_tensor_path',
            'stb_launch_count', 'stb_tc_selftest']
@@ -77,6 +78,8 @@ def lib():
     l.stb_launch_count.restype = u64
     l.stb_layer_apply.restype = i32
     l.stb_layer_apply.argtypes = [LP, i32, vp, vp, vp, vp, vp, i32, i32, i64, vp]
+    l.stb_layer_apply_bins.restype = i32
+    l.stb_layer_apply_bins.argtypes = [LP, i32, vp, vp, vp, vp, vp, i32, vp, i64, vp]
     l.stb_layer_apply_diag.restype = i32
     l.stb_layer_apply_diag.argtypes = [LP, i32, vp, vp, vp, vp, vp, i64, vp]
     l.stb_flow_apply.restype = i32

@@ -168,6 +168,28 @@ def _(x, latent, t, mask, params, meta, fmeta, direction):
     return torch.empty_like(x), torch.empty_like(x)
 
 
+def layer_apply_bins(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mask: Optional[Tensor],
+                     params: List[Tensor], packed: Optional[Tensor], meta: List[int], fmeta: List[float],
+                     direction: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Parity instrument (``stb_layer_apply_bins``): x [rows, dim] -> (y, ldj [rows], bins [rows, dim] int32).
+    ``bins`` is the bin each element's knot search chose on the SAME kernel path ``layer_apply`` takes
+    (tensor-core kernels when ``packed`` is given); -1 for pass-through dims and identity tails."""
+    _check_cuda(x, 'input')
+    rows, dim = x.shape
+    y = torch.empty_like(x)
+    ldj = torch.empty(rows, dtype=x.dtype, device=x.device)
+    bins = torch.full((rows, dim), -1, dtype=torch.int32, device=x.device)
+    if rows == 0:
+        return y, ldj, bins
+    L = make_struct(meta, fmeta, mask, params, packed)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().stb_layer_apply_bins(C.byref(L), direction, x.data_ptr(), _dp(latent), _dp(t),
+                                             y.data_ptr(), ldj.data_ptr(), _lib.LDJ_SET, bins.data_ptr(),
+                                             rows, _stream(x))
+    _lib.check(rc)
+    return y, ldj, bins
+
+
 G_PAD = 48            # parameters per transformed dim in g_net (47 quadratic, padded)
 H_AUG = 72            # workspace row: hidden(64) | 1 | 0 x 7
 

@@ -20,12 +20,16 @@ void count_launch() { ++g_launches; }
 
 static int apply_one(const stb_layer* L, int direction, const float* x, const float* latent,
                      const float* t, float* y, float* ldj, int ldj_mode, int base_lp, int64_t rows,
-                     cudaStream_t s, float* ldiag = nullptr) {
+                     cudaStream_t s, float* ldiag = nullptr, int32_t* bins = nullptr) {
     int rc = validate_layer(L);
     if (rc) return rc;
     if (rows < 0) return set_error(STB_EINVAL, "rows < 0");
     if (rows == 0) return STB_OK;
     if (!x || !y) return set_error(STB_EINVAL, "x / y is NULL");
+    if (bins) {                                   // -1 everywhere the kernels do not search
+        cudaError_t e = cudaMemsetAsync(bins, 0xff, (size_t)rows * L->dim * sizeof(int32_t), s);
+        if (e != cudaSuccess) return set_error(STB_ECUDA, "memset: %s", cudaGetErrorString(e));
+    }
     if (L->kind >= STB_PERMUTE) {
         if (ldiag) return set_error(STB_ENOTSUP, "no per-dimension log-derivative for this layer kind");
         if (ldj_mode != STB_LDJ_NONE && !ldj) return set_error(STB_EINVAL, "ldj_mode set but ldj is NULL");
@@ -35,12 +39,12 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     if ((L->kind == STB_CONT_AFFINE) && !t) return set_error(STB_EINVAL, "layer expects a time input");
     if (ldj_mode != STB_LDJ_NONE && !ldj) return set_error(STB_EINVAL, "ldj_mode set but ldj is NULL");
     if (L->packed && !ldiag && tc_layer_supported(L))
-        return tc_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s);
+        return tc_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tcw_layer_supported(L) && tcw_image_present(L))
-        return tcw_layer_apply(L, tcw_image(L), direction, x, y, ldj, ldj_mode, base_lp, rows, s);
+        return tcw_layer_apply(L, tcw_image(L), direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tcm_layer_supported(L))
         return tcm_layer_apply(L, direction, x, t, y, ldj, ldj_mode, base_lp, rows, s);
-    return generic_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, ldiag, rows, s);
+    return generic_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, ldiag, rows, s, bins);
 }
 
 // A sequence of layers (already in application order).  Maximal runs of 2..8 packed spline couplings of the
@@ -95,6 +99,14 @@ int stb_layer_apply(const stb_layer* layer, int direction, const float* x, const
     if (direction != STB_FORWARD && direction != STB_INVERSE) return set_error(STB_EINVAL, "bad direction");
     return apply_one(layer, direction, x, latent, t, y, ldj, ldj_mode, base_log_prob, rows,
                      (cudaStream_t)stream);
+}
+
+int stb_layer_apply_bins(const stb_layer* layer, int direction, const float* x, const float* latent,
+                         const float* t, float* y, float* ldj, int ldj_mode, int32_t* bins,
+                         int64_t rows, void* stream) {
+    if (direction != STB_FORWARD && direction != STB_INVERSE) return set_error(STB_EINVAL, "bad direction");
+    if (!bins) return set_error(STB_EINVAL, "bins is NULL");
+    return apply_one(layer, direction, x, latent, t, y, ldj, ldj_mode, 0, rows, (cudaStream_t)stream, nullptr, bins);
 }
 
 int stb_layer_apply_diag(const stb_layer* layer, int direction, const float* x, const float* latent,

@@ -14,7 +14,7 @@ int validate_layer(const stb_layer* L);
 
 int generic_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent,
                         const float* t, float* y, float* ldj, int ldj_mode, int base_log_prob,
-                        float* ldiag, int64_t rows, cudaStream_t stream);
+                        float* ldiag, int64_t rows, cudaStream_t stream, int32_t* bins = nullptr);
 int pointwise_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj,
                           int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
 int unit_normal_apply(const float* x, float* lp, int accumulate, int dim, int64_t rows,
@@ -25,7 +25,7 @@ bool tc_layer_supported(const stb_layer* L);
 uint64_t tc_packed_bytes(const stb_layer* L);
 int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
 int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj,
-                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
+                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins = nullptr);
 
 // several layers of one flow in one launch (tc_layer.cu, CHAIN kernels); layers[] in application order
 bool tc_chain_supported(const stb_layer* const* layers, int n);
@@ -39,7 +39,7 @@ bool tcw_backward_supported(const stb_layer* L);
 uint64_t tcw_packed_bytes(const stb_layer* L);
 int tcw_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
 int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const float* x, float* y, float* ldj,
-                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
+                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins = nullptr);
 int tcw_layer_backward(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
                        const float* g_ldj, float* g_x, float* g_net, float* hidden, int64_t rows,
                        cudaStream_t stream);

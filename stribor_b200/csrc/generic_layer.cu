@@ -37,6 +37,7 @@ struct GenArgs {
     float* y;
     float* ldj;
     float* ldiag;      // optional [rows, dim] per-dimension log-derivative
+    int32_t* bins;     // optional [rows, dim] searched bin per element (pre-filled with -1 by the caller)
     long long rows;
 };
 
@@ -244,11 +245,15 @@ __global__ void __launch_bounds__(kGenThreads) generic_layer_kernel(const GenArg
             else { out = xv * expf(a) + sh; ld = a; }
         } else if (KIND == STB_RQS) {
             const bool box = L.has_box != 0;
+            int kb;
             rqs_element(col, L.n_bins, box ? L.left : L.lower, box ? L.right : L.upper,
                         box ? L.bottom : L.lower, box ? L.top : L.upper, inverse,
-                        L.inverse_ldj_own != 0, xv, out, ld);
+                        L.inverse_ldj_own != 0, xv, out, ld, &kb);
+            if (A.bins && lane < nrows) A.bins[(row0 + lane) * d + j] = kb;
         } else {
-            cubic_element(col, L.n_bins, L.lower, L.upper, inverse, L.inverse_ldj_own != 0, xv, out, ld);
+            int kb;
+            cubic_element(col, L.n_bins, L.lower, L.upper, inverse, L.inverse_ldj_own != 0, xv, out, ld, &kb);
+            if (A.bins && lane < nrows) A.bins[(row0 + lane) * d + j] = kb;
         }
         xs[j * kXsStride + lane] = out;
         if (A.ldiag) lds[j * kXsStride + lane] = ld;
@@ -414,7 +419,7 @@ int validate_layer(const stb_layer* L) {
 
 int generic_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent,
                         const float* t, float* y, float* ldj, int ldj_mode, int base_log_prob,
-                        float* ldiag, int64_t rows, cudaStream_t stream) {
+                        float* ldiag, int64_t rows, cudaStream_t stream, int32_t* bins) {
     GenArgs A;
     A.L = *L;
     A.direction = direction;
@@ -425,7 +430,7 @@ int generic_layer_apply(const stb_layer* L, int direction, const float* x, const
     int buf_rows = 1;
     for (int i = 0; i < L->net.n_linear; ++i) buf_rows = max(buf_rows, L->net.dims[i]);
     A.buf_rows = buf_rows;
-    A.x = x; A.latent = latent; A.t = t; A.y = y; A.ldj = ldj; A.ldiag = ldiag; A.rows = rows;
+    A.x = x; A.latent = latent; A.t = t; A.y = y; A.ldj = ldj; A.ldiag = ldiag; A.bins = bins; A.rows = rows;
 
     size_t smem = sizeof(float) * ((size_t)L->dim * kXsStride + 2 * (size_t)buf_rows * kTileRows +
                                    (size_t)A.P * kColStride + kGenWarps * kTileRows + kTileRows) +

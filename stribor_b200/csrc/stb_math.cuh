@@ -179,9 +179,10 @@ __device__ __forceinline__ void rqs_inverse_in_bin(const RqsBin& b, float y, flo
 template <class P>
 __device__ __forceinline__ void rqs_element(P prm, int K, float left, float right, float bottom,
                                             float top, bool inverse, bool own_ld, float x,
-                                            float& out, float& ld) {
+                                            float& out, float& ld, int* kbin = nullptr) {
     out = x;
     ld = 0.f;
+    if (kbin) *kbin = -1;                     // identity tail: no search happens (:86-91)
     const float lo = inverse ? bottom : left, hi = inverse ? top : right;
     if (!(x >= lo && x <= hi)) return;
     OffsetView<P> W{prm, 0}, H{prm, K}, D{prm, 2 * K};
@@ -191,10 +192,12 @@ __device__ __forceinline__ void rqs_element(P prm, int K, float left, float righ
     sizes_to_knots(H, K, bottom, top);
     if (!inverse) {
         int k = knot_search(W, K, left, x);
+        if (kbin) *kbin = k;
         RqsBin b = rqs_bin(W, H, D, K, k, left, bottom);
         rqs_forward_in_bin(b, x, out, ld);
     } else {
         int k = knot_search(H, K, bottom, x);
+        if (kbin) *kbin = k;
         RqsBin b = rqs_bin(W, H, D, K, k, left, bottom);
         float ld_own;
         rqs_inverse_in_bin(b, x, out, ld_own);
@@ -332,9 +335,11 @@ __device__ __forceinline__ float cubic_inverse_in_bin(const CubBin& k, float u, 
 // prm = [uw(K) | uh(K) | left, right]  (destroyed).  Same contract as rqs_element.
 template <class P>
 __device__ __forceinline__ void cubic_element(P prm, int K, float lower, float upper, bool inverse,
-                                              bool own_ld, float x, float& out, float& ld) {
+                                              bool own_ld, float x, float& out, float& ld,
+                                              int* kbin = nullptr) {
     out = x;
     ld = 0.f;
+    if (kbin) *kbin = -1;
     if (!(x >= lower && x <= upper)) return;
     OffsetView<P> W{prm, 0}, H{prm, K};
     const float ul = prm[2 * K], ur = prm[2 * K + 1];
@@ -345,11 +350,13 @@ __device__ __forceinline__ void cubic_element(P prm, int K, float lower, float u
     float cw, ch;
     if (!inverse) {
         int k = cubic_search(W, H, K, false, u, cw, ch);
+        if (kbin) *kbin = k;
         CubBin b = cubic_bin(W, H, K, k, cw, ch, ul, ur);
         float o = cubic_forward_in_bin(b, u, ld);
         out = o * span + lower;                              // :244-245 (log terms cancel: same box)
     } else {
         int k = cubic_search(W, H, K, true, u, cw, ch);
+        if (kbin) *kbin = k;
         CubBin b = cubic_bin(W, H, K, k, cw, ch, ul, ur);
         float ld_own;
         float o = cubic_inverse_in_bin(b, u, ld_own);

@@ -153,6 +153,7 @@ struct Args {
     const uint8_t* chain_packed[kMaxChain];
     float lower_l[kMaxChain], upper_l[kMaxChain];
     int n_chunks_l[kMaxChain];
+    int32_t* bins;                     // BINS kernels: [rows, dim] searched bin per element (stb_layer_apply_bins)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -167,7 +168,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // kernel: x is read and written once per flow instead of once per layer, the running log|det J| stays in a
 // register.  Each layer's header + biases + first Linear (20 KB) travel through the weight ring as one more
 // item ahead of its chunks; the epilogue warps copy the 7 KB small block out of the stage.
-template <int KIND, bool INVERSE, bool CHAIN>
+// BINS = true (parity instrument, never on the timed path): every element's searched bin goes to A.bins.
+template <int KIND, bool INVERSE, bool CHAIN, bool BINS = false>
 __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem + kSmXs);
@@ -535,6 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                         if (STB_TC_EXP & 9) { out = xv + 1e-30f * (loc.Ek.x + loc.Ek1.y + loc.c.x + u0 + u1); ld = loc.Ek.y; }
                         else rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
                     }
+                    if (BINS && ji < n_tr && rt < nrows) A.bins[(row0 + rt) * d + (j4 >> 2)] = inside ? loc.k : -1;
                 } else {
                     const float span = hi - lo;
                     const float u = (xv - lo) / span;
@@ -558,6 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                         const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
                         cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);
                     }
+                    if (BINS && ji < n_tr && rt < nrows) A.bins[(row0 + rt) * d + (j4 >> 2)] = inside ? sel.k : -1;
                 }
                 if (ji < n_tr) asm volatile("st.shared.f32 [%0], %1;" ::"r"(xrow_a + j4), "f"(out) : "memory");
                 ld_acc += ld;
@@ -773,10 +777,11 @@ int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
 }
 
 int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
-                   int base_log_prob, int64_t rows, cudaStream_t stream) {
+                   int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins) {
     using namespace tcl;
     if (L->packed_bytes < kPackedBytes) return set_error(STB_EINVAL, "packed image too small");
-    Args A;
+    Args A = {};
+    A.bins = bins;
     A.packed = static_cast<const uint8_t*>(L->packed);
     A.x = x; A.y = y; A.ldj = ldj;
     A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
@@ -798,6 +803,10 @@ int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, 
     void (*kern)(Args);
     if (L->kind == STB_RQS) kern = A.inverse ? tc_spline_layer_kernel<STB_RQS, true, false> : tc_spline_layer_kernel<STB_RQS, false, false>;
     else kern = A.inverse ? tc_spline_layer_kernel<STB_CUBIC, true, false> : tc_spline_layer_kernel<STB_CUBIC, false, false>;
+    if (bins) {
+        if (L->kind == STB_RQS) kern = A.inverse ? tc_spline_layer_kernel<STB_RQS, true, false, true> : tc_spline_layer_kernel<STB_RQS, false, false, true>;
+        else kern = A.inverse ? tc_spline_layer_kernel<STB_CUBIC, true, false, true> : tc_spline_layer_kernel<STB_CUBIC, false, false, true>;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int grid = (int)min((long long)n_sm, tiles);

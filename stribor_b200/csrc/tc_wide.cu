@@ -119,6 +119,7 @@ struct Args {
     const float* g_ldj;
     float* g_net;
     float* hidden;
+    int32_t* bins;            // FWD, optional: [rows, dim] searched bin per element (stb_layer_apply_bins)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -451,6 +452,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                             const float u1 = (loc.k == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
                             rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
                         }
+                        if (A.bins != nullptr && live_dim && rloc < nrows)
+                            A.bins[(row0 + rloc) * d + hdr->tr_idx[ji]] = inside ? loc.k : -1;
                     } else {
                         softmax16_num2(t, shift);
                         float2 ee, eo;
@@ -522,6 +525,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                         const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
                         cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);
                     }
+                    if (!BWD && A.bins != nullptr && live_dim && rloc < nrows)
+                        A.bins[(row0 + rloc) * d + hdr->tr_idx[ji]] = inside ? sel.k : -1;
                 }
                 if (live_dim) {
                     if (BWD) grow[ji] = out; else xrow[ji] = out;
@@ -1453,9 +1458,10 @@ static int tcw_launch(void (*kern)(tcw::Args), const tcw::Args& A, long long til
 }
 
 int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const float* x, float* y, float* ldj,
-                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream) {
+                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins) {
     using namespace tcw;
     Args A = {};
+    A.bins = bins;
     A.packed = static_cast<const uint8_t*>(image);
     A.x = x; A.y = y; A.ldj = ldj;
     A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;

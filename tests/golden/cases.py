@@ -246,3 +246,32 @@ CASES['grad_cubic_d8_L2'] = _mk_flow('cubic', 8, [16], 2, 8, 12, 53, lower=-3., 
                                       ops=('log_prob', 'nll_grad'))
 CASES['grad_quadratic_d64_L2_k16'] = _mk_flow('quadratic', 64, [64], 2, 16, 8, 54,
                                                ops=('log_prob', 'nll_grad'), scale=1.5)
+
+
+# ---- bin-index fixtures (tests/golden/make_golden_bins.py -> reference_bins.npz) -------------------------------
+# Per spline layer the reference's own searchsorted results are recorded: forward search on the layer input,
+# inverse search on the layer output and the forward re-search on the recovered point.  Besides every CASES
+# entry that contains a spline, these larger batches exercise the tensor-core kernels' search on many rows
+# (partial last tile included: 300 = 256 + 44 rows on the 256-row kernel, 128 + 128 + 44 on the 128-row one).
+BIN_CASES = {
+    'bins_quadratic_d64_k16_h64': _mk_flow('quadratic', 64, [64], 2, 16, 300, 71, scale=1.5),
+    'bins_cubic_d64_k16_h64': _mk_flow('cubic', 64, [64], 2, 16, 300, 72, scale=1.5),
+    'bins_quadratic_d128_k16_h64': _mk_flow('quadratic', 128, [64], 2, 16, 300, 73, scale=1.5),
+    'bins_cubic_d128_k16_h64': _mk_flow('cubic', 128, [64], 2, 16, 300, 74, scale=1.5),
+    'bins_quadratic_d48_parity': _mk_flow('quadratic', 48, [64], 2, 16, 200, 75, masks=('parity_even', 'parity_odd'),
+                                          lower=-2., upper=2., scale=1.5),
+}
+
+
+def spline_cases():
+    """names (CASES and BIN_CASES) whose spec holds at least one spline layer"""
+    out = []
+    for name, fn in list(CASES.items()) + list(BIN_CASES.items()):
+        spec = fn()['spec']
+        if any(l.get('transform', {}).get('kind') in ('quadratic', 'cubic') for l in spec):
+            out.append(name)
+    return out
+
+
+def build_bin_case(name):
+    return (CASES.get(name) or BIN_CASES[name])()
