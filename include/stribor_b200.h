@@ -215,6 +215,17 @@ int stb_layer_backward(const stb_layer* layer, int direction, const float* x, co
                        float* g_latent, float* g_t, const stb_layer_grads* grads, void* workspace,
                        int64_t rows, void* stream);
 
+/* Gradient of stb_layer_apply_diag for layers whose parameters are supplied (n_linear == 0: row_out or
+ * const_out) -- what autograd derives for ElementwiseTransform.forward_and_log_diag_jacobian
+ * (flow.py:57-69; affine.py:97-123, spline.py:101-105 -> util/rational_quadratic_spline.py:11-251 incl.
+ * the separate left/right/bottom/top boxes, util/cubic_spline.py:22-247).  g_out [rows, dim] and
+ * g_ldiag [rows, dim] (nullable) are the incoming gradients of y and of the per-dimension log-derivative;
+ * g_x [rows, dim] and grads->g_row_out (layout of row_out; also written for const_out layers, the caller
+ * sums it over rows) receive the results. */
+int stb_layer_backward_diag(const stb_layer* layer, int direction, const float* x, const float* g_out,
+                            const float* g_ldiag, float* g_x, const stb_layer_grads* grads, int64_t rows,
+                            void* stream);
+
 /* tcgen05 path: size of / build the packed weight image for a layer (0 bytes = this layer
  * configuration only runs on the generic path). */
 uint64_t stb_packed_bytes(const stb_layer* layer);

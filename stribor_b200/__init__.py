@@ -16,5 +16,6 @@ from .flows import *
 from . import util
 from . import net
 from . import _ops
+from .flows._native import invalidate_packed
 
 __version__ = '0.1.0'

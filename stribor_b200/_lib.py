@@ -27,7 +27,7 @@ LIB_PATH = os.environ.get('STRIBOR_B200_LIB') or \
 EXPORTS = ['stb_abi_version', 'stb_sizeof_layer', 'stb_last_error', 'stb_layer_apply', 'stb_layer_apply_diag',
            'stb_layer_apply_bins', 'stb_flow_apply',
            'stb_flow_log_prob', 'stb_unit_normal_log_prob', 'stb_layer_backward_workspace_bytes',
-           'stb_layer_backward', 'stb_packed_bytes', 'stb_pack_layer', 'stb_layer_uses_tensor_path',
+           'stb_layer_backward', 'stb_layer_backward_diag', 'stb_packed_bytes', 'stb_pack_layer', 'stb_layer_uses_tensor_path',
            'stb_launch_count', 'stb_tc_selftest']
 
 
@@ -93,6 +93,8 @@ def lib():
     l.stb_layer_backward.restype = i32
     l.stb_layer_backward.argtypes = [LP, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                      C.POINTER(StbLayerGrads), vp, i64, vp]
+    l.stb_layer_backward_diag.restype = i32
+    l.stb_layer_backward_diag.argtypes = [LP, i32, vp, vp, vp, vp, C.POINTER(StbLayerGrads), i64, vp]
     l.stb_packed_bytes.restype = u64
     l.stb_packed_bytes.argtypes = [LP]
     l.stb_pack_layer.restype = i32

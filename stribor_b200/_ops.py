@@ -41,6 +41,33 @@ def _check_cuda(x: Tensor, what: str):
         raise TypeError(f'stribor_b200: {what} must be float32, got {x.dtype}')
 
 
+def check_layer_tensors(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mask: Optional[Tensor],
+                        params: Sequence[Tensor], packed: Optional[Tensor] = None, int_params: bool = False):
+    """Every tensor whose raw pointer is handed to the kernels must live on x's device with the dtype the
+    kernels read: a float64 ``t`` / ``latent`` would be reinterpreted as float32, a module left on the CPU
+    (or another GPU) would hand a foreign pointer to the kernel.  Raise the reference-style Python error instead."""
+    _check_cuda(x, 'input')
+    dev = x.device
+
+    def same(v, what, dtype):
+        if v is None or v.numel() == 0:
+            return
+        if v.device != dev:
+            raise RuntimeError(f'stribor_b200: {what} is on {v.device} but the input is on {dev}; move the module '
+                               'and all inputs to the same GPU (there is no CPU fallback)')
+        if v.dtype != dtype:
+            raise TypeError(f'stribor_b200: {what} must be {dtype}, got {v.dtype}')
+        if not v.is_contiguous():
+            raise ValueError(f'stribor_b200: {what} must be contiguous')
+
+    same(latent, '`latent`', torch.float32)
+    same(t, '`t`', torch.float32)
+    same(mask, 'the coupling mask', torch.uint8)
+    for i, p in enumerate(params):
+        same(p, f'layer parameter {i}', torch.int32 if int_params else torch.float32)
+    same(packed, 'the packed weight image', torch.uint8)
+
+
 def _dp(t: Optional[Tensor]):
     return None if t is None or t.numel() == 0 else t.data_ptr()
 
@@ -149,7 +176,8 @@ def _(x, latent, t, mask, params, packed, meta, fmeta, direction, want_ldj, base
 def layer_apply_diag(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mask: Optional[Tensor],
                      params: List[Tensor], meta: List[int], fmeta: List[float], direction: int
                      ) -> Tuple[Tensor, Tensor]:
-    """x [rows, dim] -> (y [rows, dim], per-dimension log-derivative [rows, dim]).  Not differentiable."""
+    """x [rows, dim] -> (y [rows, dim], per-dimension log-derivative [rows, dim]).  Differentiable when the
+    layer's parameters are supplied (const_out / row_out), see ``layer_backward_diag``."""
     rows, dim = x.shape
     y = torch.empty_like(x)
     ldiag = torch.empty_like(x)
@@ -166,6 +194,54 @@ def layer_apply_diag(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], m
 @layer_apply_diag.register_fake
 def _(x, latent, t, mask, params, meta, fmeta, direction):
     return torch.empty_like(x), torch.empty_like(x)
+
+
+@torch.library.custom_op('stribor_b200::layer_backward_diag', mutates_args=(), device_types='cuda')
+def layer_backward_diag(x: Tensor, mask: Optional[Tensor], params: List[Tensor], meta: List[int],
+                        fmeta: List[float], direction: int, g_y: Tensor, g_ld: Optional[Tensor]) -> List[Tensor]:
+    """Gradient of ``layer_apply_diag`` (``stb_layer_backward_diag``) -> [g_x, g_param]."""
+    rows, dim = x.shape
+    n_linear, row_mode = meta[10], meta[13]
+    if n_linear > 0:
+        raise NotImplementedError('stribor_b200: the per-dimension log-derivative API is differentiable when the '
+                                  'transform parameters are tensors (learned, or a conditioner evaluated by autograd)')
+    p0 = params[0]
+    g_x = torch.empty_like(x)
+    if rows == 0:
+        return [g_x, torch.zeros_like(p0)]
+    g_rows = torch.zeros_like(p0) if row_mode else x.new_zeros(rows, p0.numel())
+    L = make_struct(meta, fmeta, mask, params, None)
+    G = _lib.StbLayerGrads()
+    G.g_row_out = g_rows.data_ptr()
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().stb_layer_backward_diag(C.byref(L), direction, x.data_ptr(), g_y.data_ptr(), _dp(g_ld),
+                                                g_x.data_ptr(), C.byref(G), rows, _stream(x))
+    _lib.check(rc)
+    return [g_x, g_rows if row_mode else g_rows.sum(0).view_as(p0)]
+
+
+@layer_backward_diag.register_fake
+def _(x, mask, params, meta, fmeta, direction, g_y, g_ld):
+    return [torch.empty_like(x), torch.empty_like(params[0])]
+
+
+def _setup_ctx_diag(ctx, inputs, output):
+    x, latent, t, mask, params, meta, fmeta, direction = inputs
+    ctx.save_for_backward(x, mask, *params)
+    ctx.meta, ctx.fmeta, ctx.direction = list(meta), list(fmeta), direction
+
+
+def _backward_diag(ctx, g_y, g_ld):
+    saved = ctx.saved_tensors
+    x, mask = saved[:2]
+    params = list(saved[2:])
+    g_y = g_y.contiguous() if g_y is not None else torch.zeros_like(x)
+    g_ld = g_ld.contiguous() if g_ld is not None else None
+    g_x, g_p = layer_backward_diag(x, mask, params, ctx.meta, ctx.fmeta, ctx.direction, g_y, g_ld)
+    return g_x, None, None, None, [g_p] + [None] * (len(params) - 1), None, None, None
+
+
+layer_apply_diag.register_autograd(_backward_diag, setup_context=_setup_ctx_diag)
 
 
 def layer_apply_bins(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mask: Optional[Tensor],

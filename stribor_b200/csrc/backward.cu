@@ -24,6 +24,7 @@ struct BwdArgs {
     const float* x;
     const float* g_out;
     const float* g_ldj;
+    const float* g_ldiag;    // optional [rows, dim]: gradient wrt the per-dimension log-derivative (stb_layer_apply_diag)
     float* g_x;
     float* g_row;
     long long rows;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kBThreads) elementwise_backward_kernel(const B
     __syncthreads();
     const int n_tr = n_tr_s;
     const bool inverse = (A.direction == STB_INVERSE);
-    const float g_ld = (A.g_ldj != nullptr && lane < nrows) ? A.g_ldj[row0 + lane] : 0.f;
+    const float g_ld_row = (A.g_ldj != nullptr && lane < nrows) ? A.g_ldj[row0 + lane] : 0.f;
     SmemCol col{prm + tid, kBColStride};
     SmemCol gcol{gpr + tid, kBColStride};
     float* pw = prm + warp * 32;                       // this warp's 32 columns
@@ -121,6 +122,8 @@ __global__ void __launch_bounds__(kBThreads) elementwise_backward_kernel(const B
         // ---- element gradient -------------------------------------------------------------------------
         const float xv = xs[j * kBXsStride + lane];
         const float go = gs[j * kBXsStride + lane];
+        float g_ld = g_ld_row;
+        if (A.g_ldiag != nullptr && lane < nrows) g_ld += A.g_ldiag[(row0 + lane) * d + j];
         float gx;
         if (KIND == STB_AFFINE) {
             const float ls = col[0], sh = col[1];
@@ -132,7 +135,9 @@ __global__ void __launch_bounds__(kBThreads) elementwise_backward_kernel(const B
                 gx = go * e; gcol[1] = go; gcol[0] = go * xv * e + g_ld;
             }
         } else if (KIND == STB_RQS) {
-            rqs_element_grad(col, gcol, L.n_bins, L.lower, L.upper, inverse, xv, go, g_ld, gx);
+            const bool box = L.has_box != 0;
+            rqs_element_grad(col, gcol, L.n_bins, box ? L.left : L.lower, box ? L.right : L.upper,
+                             box ? L.bottom : L.lower, box ? L.top : L.upper, inverse, xv, go, g_ld, gx);
         } else {
             cubic_element_grad(col, gcol, L.n_bins, L.lower, L.upper, inverse, xv, go, g_ld, gx);
         }
@@ -174,9 +179,11 @@ uint64_t layer_backward_workspace_bytes(const stb_layer* L, int64_t rows) {
 
 int layer_backward(const stb_layer* L, int direction, const float* x, const float* latent, const float* t,
                    const float* g_out, const float* g_ldj, float* g_x, float* g_latent, float* g_t,
-                   const stb_layer_grads* grads, void* workspace, int64_t rows, cudaStream_t stream) {
+                   const stb_layer_grads* grads, void* workspace, int64_t rows, cudaStream_t stream,
+                   const float* g_ldiag) {
     (void)latent; (void)t; (void)g_latent; (void)g_t;
     if (L->net.n_linear > 0) {
+        if (g_ldiag) return set_error(STB_ENOTSUP, "per-dimension log-derivative gradients need row_out / const_out parameters");
         // conditioner fused: recompute it on the tensor cores, differentiate the spline in registers
         // (tc_wide.cu).  Outputs: g_x, grads->g_row_out = gradient wrt the network output of the
         // transformed dims [rows, n_tr * 48], workspace = augmented hidden activations [rows, 72].
@@ -198,7 +205,7 @@ int layer_backward(const stb_layer* L, int direction, const float* x, const floa
                                   static_cast<float*>(workspace), rows, stream);
     }
     if (L->kind == STB_CONT_AFFINE) return set_error(STB_ENOTSUP, "continuous-affine backward is not built yet");
-    if (L->has_box) return set_error(STB_ENOTSUP, "backward with separate domain/codomain boxes is not built yet");
+    if (L->has_box && L->kind != STB_RQS) return set_error(STB_EINVAL, "separate domain/codomain boxes are rqs-only");
     if (direction != STB_FORWARD && direction != STB_INVERSE) return set_error(STB_EINVAL, "bad direction");
     if (rows < 0 || !x || !g_out || !g_x) return set_error(STB_EINVAL, "bad argument");
     if (rows == 0) return STB_OK;
@@ -215,7 +222,7 @@ int layer_backward(const stb_layer* L, int direction, const float* x, const floa
     }
     A.n_tr = n_tr;
     A.width = (L->row_compact ? n_tr : L->dim) * A.P;
-    A.x = x; A.g_out = g_out; A.g_ldj = g_ldj; A.g_x = g_x;
+    A.x = x; A.g_out = g_out; A.g_ldj = g_ldj; A.g_ldiag = g_ldiag; A.g_x = g_x;
     A.g_row = grads ? grads->g_row_out : nullptr;
     A.rows = rows;
     const size_t smem = sizeof(float) * (2 * (size_t)L->dim * kBXsStride + 2 * (size_t)A.P * kBColStride) +

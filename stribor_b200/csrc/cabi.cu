@@ -161,6 +161,17 @@ int stb_layer_backward(const stb_layer* layer, int direction, const float* x, co
                           workspace, rows, (cudaStream_t)stream);
 }
 
+int stb_layer_backward_diag(const stb_layer* layer, int direction, const float* x, const float* g_out,
+                            const float* g_ldiag, float* g_x, const stb_layer_grads* grads, int64_t rows,
+                            void* stream) {
+    int rc = validate_layer(layer);
+    if (rc) return rc;
+    if (layer->net.n_linear > 0 || layer->kind >= STB_CONT_AFFINE)
+        return set_error(STB_ENOTSUP, "stb_layer_backward_diag: affine / spline layers with row_out or const_out parameters only");
+    return layer_backward(layer, direction, x, nullptr, nullptr, g_out, nullptr, g_x, nullptr, nullptr, grads,
+                          nullptr, rows, (cudaStream_t)stream, g_ldiag);
+}
+
 uint64_t stb_packed_bytes(const stb_layer* layer) {
     if (validate_layer(layer)) return 0;
     if (tc_layer_supported(layer)) return tc_packed_bytes(layer) + tcw_packed_bytes(layer);   // both images

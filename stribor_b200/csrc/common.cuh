@@ -66,6 +66,6 @@ uint64_t layer_backward_workspace_bytes(const stb_layer* L, int64_t rows);
 int layer_backward(const stb_layer* L, int direction, const float* x, const float* latent,
                    const float* t, const float* g_out, const float* g_ldj, float* g_x,
                    float* g_latent, float* g_t, const stb_layer_grads* grads, void* workspace,
-                   int64_t rows, cudaStream_t stream);
+                   int64_t rows, cudaStream_t stream, const float* g_ldiag = nullptr);
 
 }  // namespace stb

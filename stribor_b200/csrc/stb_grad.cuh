@@ -113,32 +113,35 @@ __device__ __forceinline__ void rqs_bin_dual(float x, float xk, float xk1, float
 //   sw, sh : NORMALISED bin sizes (min + scale * softmax), K each;  ud: K-1 raw derivative params
 //   direction / own_ld as rqs_element;  x: the element's input;  g_out, g_ld: incoming gradients
 // Writes g_x and the gradient wrt the K + K + (K-1) RAW parameters into gp[] (same indexable type).
+// Domain [left, right] -> codomain [bottom, top] (rational_quadratic_spline.py:55-64); the common case is
+// left == bottom == lower, right == top == upper.
 template <class P>
-__device__ __forceinline__ void rqs_element_grad(P prm, P gp, int K, float lower, float upper, bool inverse,
-                                                 float x, float g_out, float g_ld, float& g_x) {
+__device__ __forceinline__ void rqs_element_grad(P prm, P gp, int K, float left, float right, float bottom,
+                                                 float top, bool inverse, float x, float g_out, float g_ld,
+                                                 float& g_x) {
     const int Pn = 3 * K - 1;
     for (int i = 0; i < Pn; ++i) gp[i] = 0.f;
     g_x = g_out;                                   // identity tails
-    if (!(x >= lower && x <= upper)) return;
+    if (!(x >= (inverse ? bottom : left) && x <= (inverse ? top : right))) return;
     OffsetView<P> W{prm, 0}, H{prm, K}, D{prm, 2 * K};
     OffsetView<P> GW{gp, 0}, GH{gp, K}, GD{gp, 2 * K};
     softmax_bins(W, K, STB_RQS_MIN);               // normalised sizes, kept (not turned into knots)
     softmax_bins(H, K, STB_RQS_MIN);
-    const float span = upper - lower;
+    const float spanx = right - left, spany = top - bottom;
     // bin search by running sums (same arithmetic as sizes_to_knots + knot_search)
     int k = 0;
     float cwk = 0.f, chk = 0.f, cw = 0.f, ch = 0.f;
     for (int i = 1; i < K; ++i) {
         cw += W[i - 1];
         ch += H[i - 1];
-        const float knot = span * (inverse ? ch : cw) + lower;
+        const float knot = inverse ? spany * ch + bottom : spanx * cw + left;
         if (x >= knot) { k = i; cwk = cw; chk = ch; }
     }
     const float wk_ = W[k], hk_ = H[k];
-    const float xk = (k == 0) ? lower : span * cwk + lower;
-    const float yk = (k == 0) ? lower : span * chk + lower;
-    const float xk1 = (k == K - 1) ? upper : span * (cwk + wk_) + lower;
-    const float yk1 = (k == K - 1) ? upper : span * (chk + hk_) + lower;
+    const float xk = (k == 0) ? left : spanx * cwk + left;
+    const float yk = (k == 0) ? bottom : spany * chk + bottom;
+    const float xk1 = (k == K - 1) ? right : spanx * (cwk + wk_) + left;
+    const float yk1 = (k == K - 1) ? top : spany * (chk + hk_) + bottom;
     const float u0 = (k == 0) ? STB_RQS_EDGE_CONST : D[k - 1];
     const float u1 = (k == K - 1) ? STB_RQS_EDGE_CONST : D[k];
     const float d0 = STB_RQS_MIN + softplus_f(u0), d1 = STB_RQS_MIN + softplus_f(u1);
@@ -158,7 +161,7 @@ __device__ __forceinline__ void rqs_element_grad(P prm, P gp, int K, float lower
         for (int i = 0; i < RQ_N; ++i) gq[i] = g_out * S.d[i] + g_ld * L.d[i];
     } else {
         // coupling semantics: a recovered point outside the box gets ld = 0 (no gradient through ld)
-        const float gl = (xe >= lower && xe <= upper) ? g_ld : 0.f;
+        const float gl = (xe >= left && xe <= right) ? g_ld : 0.f;
         const float gy = (g_out - gl * L.d[RQ_X]) / S.d[RQ_X];
         gq[RQ_X] = gy;
 #pragma unroll
@@ -166,10 +169,10 @@ __device__ __forceinline__ void rqs_element_grad(P prm, P gp, int K, float lower
     }
     g_x = gq[RQ_X];
     // knots -> normalised sizes (cumulative sums; the box ends are constants)
-    const float g_cw = span * ((k > 0 ? gq[RQ_XK] : 0.f) + (k < K - 1 ? gq[RQ_XK1] : 0.f));
-    const float g_wk = span * (k < K - 1 ? gq[RQ_XK1] : 0.f);
-    const float g_ch = span * ((k > 0 ? gq[RQ_YK] : 0.f) + (k < K - 1 ? gq[RQ_YK1] : 0.f));
-    const float g_hk = span * (k < K - 1 ? gq[RQ_YK1] : 0.f);
+    const float g_cw = spanx * ((k > 0 ? gq[RQ_XK] : 0.f) + (k < K - 1 ? gq[RQ_XK1] : 0.f));
+    const float g_wk = spanx * (k < K - 1 ? gq[RQ_XK1] : 0.f);
+    const float g_ch = spany * ((k > 0 ? gq[RQ_YK] : 0.f) + (k < K - 1 ? gq[RQ_YK1] : 0.f));
+    const float g_hk = spany * (k < K - 1 ? gq[RQ_YK1] : 0.f);
     // sizes -> raw (softmax backward): w_i = min + scale * s_i, s_i = (w_i - min) / scale
     const float scale = 1.f - STB_RQS_MIN * (float)K;
     float dotw = 0.f, doth = 0.f;

@@ -608,6 +608,12 @@ bool tcm_layer_supported(const stb_layer* L) {
     const int H = N.dims[1];
     if (H < 64 || H > kMaxH || (H % 64) != 0) return false;
     if (N.n_linear == 3 && N.dims[2] != H) return false;
+    // The hidden activations feed the next GEMM as fp16 hi | lo parts: only activations bounded by 1 are safe
+    // (a ReLU / ELU / ... output above 65504 would split into +inf, -inf -> NaN, where the reference and the
+    // CUDA-core kernel stay finite).  Other activations take the generic kernel.
+    if (N.activation != STB_ACT_TANH && N.activation != STB_ACT_SIGMOID) return false;
+    // the tensor-core epilogues evaluate the inverse log-det as -(forward log-derivative): the Coupling convention
+    if (L->inverse_ldj_own) return false;
     PackArgs a;
     return fill_pack_args(L, a);
 }

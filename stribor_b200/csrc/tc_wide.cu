@@ -1414,6 +1414,12 @@ bool tcw_layer_supported(const stb_layer* L) {
     if (L->has_box || L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
     const stb_mlp& N = L->net;
     if (N.n_linear != 2 || N.dims[1] != kHid || N.final_activation != STB_ACT_NONE) return false;
+    // The hidden activations feed the next GEMM as fp16 hi | lo parts: only activations bounded by 1 are safe
+    // (a ReLU / ELU / ... output above 65504 would split into +inf, -inf -> NaN, where the reference and the
+    // CUDA-core kernel stay finite).  Other activations take the generic kernel.
+    if (N.activation != STB_ACT_TANH && N.activation != STB_ACT_SIGMOID) return false;
+    // the tensor-core epilogues evaluate the inverse log-det as -(forward log-derivative): the Coupling convention
+    if (L->inverse_ldj_own) return false;
     PackArgs a;
     return fill_pack_args(L, a);
 }

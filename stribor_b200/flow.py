@@ -78,18 +78,21 @@ def _flat(v: Optional[torch.Tensor], lead, width=None):
 
 def run_layer(desc, x, latent, t, direction, want_ldj):
     """Apply one described layer to x [..., dim] -> (y [..., dim], ldj [..., 1] or None)."""
-    _ops._check_cuda(x, 'input')
     lead, dim = x.shape[:-1], x.shape[-1]
-    y, ldj = _ops.layer_apply(x.reshape(-1, dim).contiguous(), _flat(latent, lead), _flat(t, lead),
+    latent, t = _flat(latent, lead), _flat(t, lead)
+    _ops.check_layer_tensors(x, latent, t, desc['mask'], desc['params'], desc.get('packed'),
+                             int_params=desc['meta'][0] == _ops._lib.PERMUTE)
+    y, ldj = _ops.layer_apply(x.reshape(-1, dim).contiguous(), latent, t,
                               desc['mask'], desc['params'], desc.get('packed'), desc['meta'],
                               desc['fmeta'], direction, want_ldj, False)
     return y.view(*lead, dim), (ldj.view(*lead, 1) if want_ldj else None)
 
 
 def run_layer_diag(desc, x, latent, t, direction):
-    _ops._check_cuda(x, 'input')
     lead, dim = x.shape[:-1], x.shape[-1]
-    y, ld = _ops.layer_apply_diag(x.reshape(-1, dim).contiguous(), _flat(latent, lead), _flat(t, lead),
+    latent, t = _flat(latent, lead), _flat(t, lead)
+    _ops.check_layer_tensors(x, latent, t, desc['mask'], desc['params'])
+    y, ld = _ops.layer_apply_diag(x.reshape(-1, dim).contiguous(), latent, t,
                                   desc['mask'], desc['params'], desc['meta'], desc['fmeta'], direction)
     return y.view(*lead, dim), ld.view(*lead, dim)
 
@@ -113,14 +116,17 @@ def run_chain(transforms, mode, x, latent=None, t=None, want_ldj=False):
     latent_dim = 0 if latent is None else latent.shape[-1]
     masks, params, packed, meta, fmeta = [], [], [], [], []
     empty = x.new_empty(0)
+    latent, t = _flat(latent, lead), _flat(t, lead)
     for f in transforms:
         d = f.describe(dim, latent_dim, x.device)
+        _ops.check_layer_tensors(x, latent, t, d['mask'], d['params'], d.get('packed'),
+                                 int_params=d['meta'][0] == _ops._lib.PERMUTE)
         masks.append(d['mask'] if d['mask'] is not None else x.new_empty(0, dtype=torch.uint8))
         params += [p.detach() for p in d['params']]
         packed.append(d['packed'] if d.get('packed') is not None else x.new_empty(0, dtype=torch.uint8))
         meta += d['meta']
         fmeta += d['fmeta']
-    out, vec = _ops.flow_chain(x.reshape(-1, dim).contiguous(), _flat(latent, lead), _flat(t, lead),
+    out, vec = _ops.flow_chain(x.reshape(-1, dim).contiguous(), latent, t,
                                masks, params, packed, meta, fmeta, mode, want_ldj)
     out = out.view(*lead, dim)
     if want_ldj or mode == _ops.CHAIN_LOG_PROB:

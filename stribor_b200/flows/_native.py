@@ -36,13 +36,22 @@ def build_meta(kind, dim, latent_dim, cond_x, time_input, n_bins, inv_own, zero_
 
 
 class PackedCache:
-    """Device image of a layer's weights for the tcgen05 kernel, rebuilt when they change."""
+    """Device image of a layer's weights for the tcgen05 kernel, rebuilt when they change.
+
+    "Change" is detected through the parameters' storage pointers and autograd version counters, which every
+    in-place op on the parameter itself bumps (optimizer steps, ``load_state_dict``, ``p.mul_()`` under
+    ``no_grad``).  Writes through ``p.data`` (``p.data.copy_(ema)``, ``p.data.mul_()``) bypass the counter:
+    after those call ``stribor_b200.invalidate_packed(module)`` (the owning layers also invalidate on
+    ``.to()/.cuda()``, ``train()/eval()`` and ``load_state_dict``)."""
 
     def __init__(self):
         self.key = None
         self.buf = None
         self.event = None
         self.seen = set()
+
+    def invalidate(self):
+        self.key = None
 
     def get(self, meta, fmeta, mask, params):
         if not params or not params[0].is_cuda or os.environ.get('STRIBOR_B200_FORCE_GENERIC') == '1':
@@ -128,3 +137,31 @@ def row_params_from_net(net, z, rows_idx=None):
     for m in mods[last + 1:]:
         out = m(out)
     return out
+
+
+class PackedOwner:
+    """Mixin of the layers that own a ``PackedCache`` (``self._packed``): drop the image whenever the module's
+    tensors are moved / cast, its mode switches or a state dict is loaded."""
+
+    def invalidate_packed(self):
+        self._packed.invalidate()
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed.invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode: bool = True):
+        self._packed.invalidate()
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._packed.invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+
+def invalidate_packed(module: torch.nn.Module):
+    """Drop every cached tensor-core weight image under ``module``; the next call repacks from the live
+    weights.  Needed only after writes that bypass autograd's version counter (``p.data.<op>_()``)."""
+    for m in module.modules():
+        if isinstance(m, PackedOwner):
+            m.invalidate_packed()

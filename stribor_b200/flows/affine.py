@@ -34,8 +34,9 @@ class Affine(ElementwiseTransform):
                 nn.init.xavier_uniform_(self.shift)
             else:
                 if isinstance(scale, Number):
-                    scale = torch.Tensor([scale])
-                    shift = torch.Tensor([shift])
+                    scale = torch.as_tensor([scale], dtype=torch.get_default_dtype())
+                    shift = torch.as_tensor([shift], dtype=torch.get_default_dtype())
+                scale, shift = scale.float(), shift.float()
                 assert torch.all(scale > 0), '`scale` mush have positive values'
                 # fixed values: buffers (so .to(device) moves them) kept out of the state-dict
                 self.register_buffer('log_scale', scale.log(), persistent=False)
@@ -47,11 +48,14 @@ class Affine(ElementwiseTransform):
     def params_per_dim(self):
         return 2
 
-    def const_out(self):
+    def const_out(self, device=None):
         """[log_scale(dim) | shift(dim)] when there is no latent_net."""
         ls = self.log_scale.reshape(-1).expand(self.dim) if self.log_scale.numel() == 1 else self.log_scale.reshape(-1)
         sh = self.shift.reshape(-1).expand(self.dim) if self.shift.numel() == 1 else self.shift.reshape(-1)
-        return torch.cat([ls, sh]).contiguous()
+        out = torch.cat([ls, sh.to(ls.device)]).contiguous()
+        if device is not None and out.device != device and not isinstance(self.log_scale, nn.Parameter):
+            out = out.to(device)          # fixed scale / shift given on another device (the reference keeps them
+        return out                        # as plain attributes: affine.py:50-57)
 
     def fmeta(self):
         return [0., 1.] * 3
@@ -62,7 +66,7 @@ class Affine(ElementwiseTransform):
         meta, params = build_meta(self.kind, dim, latent_dim if net is not None else 0, 0, 0, self.n_bins,
                                   1, 0, net, 0)
         if net is None:
-            params = [self.const_out()]
+            params = [self.const_out(device)]
         return {'meta': meta, 'fmeta': self.fmeta(), 'mask': None, 'params': list(params), 'packed': None}
 
     def _run(self, x, latent, direction, want_ldj=True):
@@ -89,7 +93,10 @@ class Affine(ElementwiseTransform):
         return self._run(y, latent, _lib.INVERSE, False)[0]
 
     def forward_and_log_det_jacobian(self, x, latent=None, *, reverse=False, **kwargs):
-        return self._run(x, latent, _lib.INVERSE if reverse else _lib.FORWARD)
+        if reverse:      # affine.py:97-109: the inverse map together with the FORWARD log-det (+sum log_scale)
+            y, ldj = self._run(x, latent, _lib.INVERSE)
+            return y, -ldj
+        return self._run(x, latent, _lib.FORWARD)
 
     def inverse_and_log_det_jacobian(self, y, latent=None, **kwargs):
         return self._run(y, latent, _lib.INVERSE)

@@ -21,14 +21,14 @@ from .. import _lib, _ops
 from ..flow import Transform, run_layer
 from ..net.time_net import TimeLinear
 from ..util.mask import get_mask
-from ._native import PackedCache, build_meta, device_mask, fusable, needs_autograd, row_params_from_net
+from ._native import PackedCache, PackedOwner, build_meta, device_mask, fusable, needs_autograd, row_params_from_net
 from .affine import Affine
 from .spline import Spline
 
 __all__ = ['Coupling', 'ContinuousAffineCoupling']
 
 
-class Coupling(Transform):
+class Coupling(PackedOwner, Transform):
     """
     Args:
         transform: ``Affine`` or ``Spline`` whose ``latent_net`` maps ``dim (+ latent)`` inputs to the
@@ -36,14 +36,17 @@ class Coupling(Transform):
         mask: name from ``stribor_b200.util.mask`` -- `none`, `ordered_right_half` (right half
             conditions, left half is transformed), `ordered_left_half`, `random_half`,
             `parity_even`, `parity_odd`.  If ``dim = 1`` use `none`.
-        set_data: mask along dim -2 instead (not built yet).
+        set_data: the mask selects rows of a set (dim -2) instead of coordinates (coupling.py:49-51).
+
+    ``Affine`` and ``Spline`` transforms run in the fused kernels.  A ``Spline`` subclass that overrides one
+    of the reference hooks (``_get_params`` / ``spline`` / ``forward_and_log_diag_jacobian``), or any other
+    ``ElementwiseTransform``, is composed exactly as the reference does (coupling.py:69-95): conditioning,
+    ``transform(x, latent=z)``, blend, masked sum of ``log_diag_jacobian`` -- around whatever kernels that
+    transform itself uses.
     """
 
     def __init__(self, transform, mask: str, set_data: bool = False, **kwargs):
         super().__init__()
-        if not isinstance(transform, (Affine, Spline)):
-            raise NotImplementedError(
-                f'Coupling around {type(transform).__name__} is not fused; use Affine or Spline')
         self.transform = transform
         self.mask_func = get_mask(mask)
         self.mask_name = mask
@@ -55,9 +58,44 @@ class Coupling(Transform):
         # those rows (coupling.py:49-51,61-78); kept out of the module tree (shared parameters).
         self._rows_layer = [Coupling(transform, 'none')] if set_data else None
 
+    def _fusable_transform(self):
+        tr = self.transform
+        return isinstance(tr, Affine) or (isinstance(tr, Spline) and tr.plain())
+
     def chainable(self):
+        if not self._fusable_transform():
+            return False
         net = self.transform.latent_net
         return (not self.set_data) and (net is None or fusable(net))
+
+    def _run_reference(self, x, latent, direction, want_ldj):
+        """coupling.py:53-95 verbatim in structure, for transforms the kernels do not describe."""
+        tr = self.transform
+        dim = x.shape[-1]
+        mask, _ = device_mask(self._masks, self.mask_func, dim, x.device)
+        m = mask.to(x.dtype).expand_as(x)
+
+        def cond(v):
+            z = v * m
+            if dim == 1:
+                z = z * 0
+            if latent is not None:
+                lat = latent if latent.shape[:-1] == v.shape[:-1] else latent.expand(*v.shape[:-1], latent.shape[-1])
+                z = torch.cat([z, lat], -1)
+            return z
+
+        if direction == _lib.FORWARD:
+            out = tr(x, latent=cond(x)) * (1 - m) + x * m
+            point = x
+        else:
+            out = tr.inverse(x, latent=cond(x)) * (1 - m) + x * m
+            point = out
+        ldj = None
+        if want_ldj:
+            ldj = (tr.log_diag_jacobian(point, None, latent=cond(point)) * (1 - m)).sum(-1, keepdim=True)
+            if direction == _lib.INVERSE:
+                ldj = -ldj
+        return out, ldj
 
     def _run_set(self, x, latent, direction, want_ldj):
         *rest, n, d = x.shape
@@ -86,7 +124,7 @@ class Coupling(Transform):
         meta, params = build_meta(tr.kind, dim, latent_dim if net is not None else 0, 1, 0, tr.n_bins,
                                   0, dim == 1, net, 0, mask_list=mask_list)
         if net is None:
-            params = [tr.const_out()]
+            params = [tr.const_out(device) if isinstance(tr, Affine) else tr.const_out()]
         params = list(params)
         fmeta = tr.fmeta()
         packed = self._packed.get(meta, fmeta, mask, params) if net is not None else None
@@ -95,6 +133,8 @@ class Coupling(Transform):
     def _run(self, x, latent, direction, want_ldj):
         if self.set_data:
             return self._run_set(x, latent, direction, want_ldj)
+        if not self._fusable_transform():
+            return self._run_reference(x, latent, direction, want_ldj)
         lat = latent if self.transform.latent_net is not None else None
         net = self.transform.latent_net
         if net is not None and not fusable(net):
@@ -142,8 +182,14 @@ class Coupling(Transform):
             self._masks[key] = (torch.tensor(idx, dtype=torch.long, device=x.device),
                                 mask.to(x.dtype))
         rows_idx, mask_f = self._masks[key]
-        if rows_idx.numel() == 0:                     # every coordinate passes through (dim == 1)
-            return x * 1, (x.new_zeros(*lead, 1) if want_ldj else None)
+        if rows_idx.numel() == 0:
+            # every coordinate passes through (dim == 1, coupling.py:62-63): the reference still evaluates the
+            # conditioner and multiplies its result by zero, so its parameters receive zero gradients, not None
+            zin = x * 0
+            if latent is not None:
+                zin = torch.cat([zin, latent if latent.shape[:-1] == lead else latent.expand(*lead, latent.shape[-1])], -1)
+            zero = tr.latent_net(zin).sum(-1, keepdim=True) * 0
+            return x + zero, (zero if want_ldj else None)
         z = x * mask_f
         if dim == 1:
             z = z * 0
@@ -173,7 +219,7 @@ class Coupling(Transform):
         return self._run(y, latent, _lib.INVERSE, True)
 
 
-class ContinuousAffineCoupling(Transform):
+class ContinuousAffineCoupling(PackedOwner, Transform):
     """
     Args:
         latent_net: maps ``[x*mask | latent | t]`` to ``2 * dim`` affine parameters
@@ -237,7 +283,16 @@ class ContinuousAffineCoupling(Transform):
             self._masks[key] = (torch.tensor(tr_dims, dtype=torch.long, device=x.device), mask.to(x.dtype))
         tr_idx, mask_f = self._masks[key]
         if tr_idx.numel() == 0:
-            return x * 1, (x.new_zeros(*lead, 1) if want_ldj else None)
+            # nothing is transformed (dim == 1): zero -- not None -- gradients for both networks, as the
+            # reference's multiply-by-(1 - mask) gives
+            zin = x * 0
+            if latent is not None:
+                zin = torch.cat([zin, latent if latent.shape[:-1] == lead else latent.expand(*lead, latent.shape[-1])], -1)
+            tt = t if t.shape[:-1] == lead else t.expand(*lead, 1)
+            if self.concatenate_time:
+                zin = torch.cat([zin, tt], -1)
+            zero = (self.latent_net(zin).sum(-1, keepdim=True) + self.time_net(tt).sum(-1, keepdim=True)) * 0
+            return x + zero, (zero if want_ldj else None)
         z = x * mask_f
         if dim == 1:
             z = z * 0
@@ -268,7 +323,10 @@ class ContinuousAffineCoupling(Transform):
         return self._run(x, t, latent, _lib.FORWARD, True)[1]
 
     def forward_and_log_det_jacobian(self, x, t=None, latent=None, *, reverse=False, **kwargs):
-        return self._run(x, t, latent, _lib.INVERSE if reverse else _lib.FORWARD, True)
+        if reverse:      # coupling.py:188-209: the inverse map together with the FORWARD log-det
+            y, ldj = self._run(x, t, latent, _lib.INVERSE, True)
+            return y, -ldj
+        return self._run(x, t, latent, _lib.FORWARD, True)
 
     def inverse_and_log_det_jacobian(self, y, t=None, latent=None, **kwargs):
         return self._run(y, t, latent, _lib.INVERSE, True)
