@@ -68,11 +68,13 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=1 << 15, help='rows of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='headline only: skip the cubic / affine / neural / train side configs')
+    ap.add_argument('--parity-rows', type=int, default=8192, help='rows of the timed batch re-checked against the oracle')
     ap.add_argument('--generic', action='store_true', help='force the CUDA-core path (no tcgen05)')
     ap.add_argument('--micro-rows', type=int, default=1 << 18, help='train: rows per micro-batch')
     ap.add_argument('--tf32', action='store_true', help='train: let the library GEMMs of the conditioner gradients use TF32')
     ap.add_argument('--hybrid', action='store_true', help='train: conditioner through autograd around the element-wise kernels')
-    ap.add_argument('--workload', default='logprob', choices=['logprob', 'affine', 'neural', 'train'],
+    ap.add_argument('--workload', default='logprob', choices=['logprob', 'cubic', 'affine', 'neural', 'train'],
                     help='logprob = BASELINE.json configs[2] (the headline, default); affine = configs[1]; '
                          'neural = configs[3]; train = configs[4] (side measurements, same JSON schema)')
     return ap.parse_args()
@@ -215,97 +217,279 @@ def run_reference(args):
 
 
 # -------------------------------------------------------------------------------------------
-# side workloads (BASELINE.json configs[1], [3], [4]); the driver only runs the default one
+# the other BASELINE.json configs: cubic (configs[2], second half), affine (configs[1]), neural (configs[3]),
+# train (configs[4]).  The default command line reports them under the `configs` key of the ONE JSON line,
+# after the headline; `--workload X` prints X alone.
 # -------------------------------------------------------------------------------------------
-def run_side(args):
+def _peaks():
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        pk = json.load(open(peaks_path))
+        return (float(pk['hbm_gbs']), float(pk.get('bf16_tflops_sustained', pk.get('bf16_tflops', 1394.6))),
+                'measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops_sustained)')
+    return 6650.0, 1400.0, 'fallback (B200_PROFILING.md)'
+
+
+def _profile_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per row of the dominant kernel, from the committed
+    `ncu --set full` summaries (profiles/r02_traffic.json, else r01), or None"""
+    for f in ('r02_traffic.json', 'r01_traffic.json'):
+        path = os.path.join(ROOT, 'profiles', f)
+        if os.path.exists(path):
+            tj = json.load(open(path))
+            if key in tj:
+                return tj[key]
+    return None
+
+
+def _timed(step, steps, warmup, dev, world):
+    """W warm-up steps, K timed steps between barriers; CUDA events on the launching stream, max over ranks.
+    -> (ms per step, library launches inside the timed region)"""
     import torch.distributed as dist
-    import stribor_b200 as st
     from stribor_b200 import _ops
-    from stribor_b200.parallel import DataParallelNLL, init_from_env, shard_rows
-
-    rank, world, local = init_from_env('nccl')
-    dev = torch.device('cuda', local)
-    torch.cuda.set_device(dev)
-    torch.manual_seed(123)
-    if args.workload == 'affine':
-        d, rows_g = 64, 1 << 20
-        layers = [st.Coupling(st.Affine(d, latent_net=st.net.MLP(d, [256, 256], 2 * d)), mask=MASKS[i % 2])
-                  for i in range(LAYERS)]
-        flow = st.NormalizingFlow(st.UnitNormal(d), layers).to(dev).requires_grad_(False)
-        name = f'affine coupling flow d=64, 8 layers, MLP[256,256], log_prob + inverse, global batch {rows_g}'
-        a, b = shard_rows(rows_g, rank, world)
-        torch.manual_seed(rank)
-        y = torch.randn(b - a, d, device=dev)
-
-        def step():
-            with torch.no_grad():
-                flow.log_prob(y)
-                flow.inverse(y)
-        unit, per_step = 'samples/s (log_prob + inverse per sample)', rows_g
-    elif args.workload == 'neural':
-        d, B, T = 16, 65536, 64
-        layers = [st.ContinuousAffineCoupling(st.net.MLP(d + 1, [64], 2 * d), st.net.TimeLinear(2 * d),
-                                              ('ordered_0', 'ordered_1')[i % 2]) for i in range(4)]
-        flow = st.NeuralFlow(layers).to(dev).requires_grad_(False)
-        name = f'NeuralFlow 4x ContinuousAffineCoupling dim 16, MLP[17->64->32], TimeLinear(32), x [{B},{T},{d}], forward'
-        a, b = shard_rows(B, rank, world)
-        torch.manual_seed(rank)
-        x = torch.randn(b - a, T, d, device=dev)
-        t = torch.rand(b - a, T, 1, device=dev)
-
-        def step():
-            with torch.no_grad():
-                flow(x, t=t)
-        unit, per_step = 'rows/s', B * T
-    else:
-        d, rows_g = 128, args.batch
-        P = 3 * BINS - 1
-        layers = [st.Coupling(st.Spline(d, BINS, latent_net=st.net.MLP(d, list(args.hidden), d * P), lower=LOWER,
-                                        upper=UPPER, spline_type='quadratic'), mask=MASKS[i % 2])
-                  for i in range(LAYERS)]
-        flow = st.NormalizingFlow(st.UnitNormal(d), layers).to(dev)
-        name = (f'NLL training step (fwd+bwd, grads all-reduced) quadratic spline coupling d=128, 8 layers, 16 bins, '
-                f'MLP{list(args.hidden)}, global batch {rows_g}')
-        a, b = shard_rows(rows_g, rank, world)
-        torch.manual_seed(rank)
-        y = torch.randn(b - a, d, device=dev)
-        if args.tf32:
-            torch.backends.cuda.matmul.allow_tf32 = True
-        if args.hybrid:
-            os.environ['STRIBOR_B200_TRAIN_HYBRID'] = '1'
-        name += (f', micro-batches of {args.micro_rows} rows, conditioner-gradient GEMMs in '
-                 f'{"tf32" if args.tf32 else "fp32"}' + (', hybrid path' if args.hybrid else ', fused backward kernel'))
-        dp = DataParallelNLL(flow, micro_rows=args.micro_rows)
-
-        def step():
-            dp.step(y, rows_g)
-        unit, per_step = 'samples/s', rows_g
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     n0 = _ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     barrier()
     tm = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_step = tm.item() / args.steps
+    return tm.item() / steps, int(_ops.launch_count() - n0)
+
+
+def _cpu_rate(fn, units, min_seconds=0.0):
+    """`fn()` once for warm-up on a small slice is the caller's business; here: one timed call"""
+    n_threads = len(os.sched_getaffinity(0))
+    torch.set_num_threads(n_threads)
+    t = time.perf_counter()
+    fn()
+    dt = time.perf_counter() - t
+    return units / dt, n_threads, dt
+
+
+def side_config(workload, args, dev, rank, world, want_cpu):
+    """One side configuration -> its result dict (same fields as the headline: value / e2e / roofline /
+    cpu_baseline).  Rows are sharded over the ranks exactly like the headline."""
+    import stribor_b200 as st
+    from stribor_b200.host import HostPipeline
+    from stribor_b200.parallel import DataParallelNLL, shard_rows
+    from stribor_b200.spec import spec_from_layers
+    from oracle import coupling_flow_oracle as O          # cpu_baseline leg only (rank 0, N = 1)
+
+    hbm_peak, tf_peak, peak_src = _peaks()
+    steps = max(3, min(args.steps, 5))
+    warmup = max(3, min(args.warmup, 3))
+    torch.manual_seed(123)
+    res = {'steps': steps, 'warmup': warmup, 'n_gpus': world, 'higher_is_better': True, 'scaling': 'strong',
+           'dtype': 'f32', 'data': 'synthetic'}
+    cpu = None
+    if workload == 'cubic':
+        d, rows_g = D, args.batch
+        layers = build_layers('cubic', [64])
+        flow = st.NormalizingFlow(st.UnitNormal(d), layers).to(dev).requires_grad_(False)
+        a, b = shard_rows(rows_g, rank, world)
+        y = torch.randn(b - a, d, device=dev, generator=torch.Generator(dev).manual_seed(rank))
+        name = workload_name('cubic', [64], rows_g)
+
+        def step():
+            with torch.no_grad():
+                return flow.log_prob(y)
+        unit, per_step = 'samples/s', rows_g
+        ins, n_out = [y], 1
+        pipe_fn = lambda yy: flow.log_prob(yy)
+        bytes_unit, flops_unit, bound = LAYERS * (8 * d + 8), 2 * (32 * 64 + 64 * 32 * 34) * LAYERS, 'hbm'
+        traffic_key = 'cubic_dram_bytes_per_row_chain'
+        if want_cpu:
+            spec = spec_from_layers([l.cpu() for l in build_layers('cubic', [64])])
+            n = 1 << 13
+            yc = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
+            with torch.no_grad():
+                O.flow_log_prob(spec, yc[:256])
+                cpu = _cpu_rate(lambda: O.flow_log_prob(spec, yc), n) + (f'{n} rows of the same workload, one call',)
+    elif workload == 'affine':
+        d, rows_g = 64, 1 << 20
+        layers = [st.Coupling(st.Affine(d, latent_net=st.net.MLP(d, [256, 256], 2 * d)), mask=MASKS[i % 2])
+                  for i in range(LAYERS)]
+        spec = spec_from_layers(layers) if want_cpu else None
+        flow = st.NormalizingFlow(st.UnitNormal(d), layers).to(dev).requires_grad_(False)
+        name = f'affine coupling flow d=64, 8 layers alternating masks, MLP[256,256] tanh, log_prob + inverse, global batch {rows_g}'
+        a, b = shard_rows(rows_g, rank, world)
+        y = torch.randn(b - a, d, device=dev, generator=torch.Generator(dev).manual_seed(rank))
+
+        def step():
+            with torch.no_grad():
+                return flow.log_prob(y), flow.inverse(y)
+        unit, per_step = 'samples/s (log_prob + inverse per sample)', rows_g
+        ins, n_out = [y], 2
+        pipe_fn = lambda yy: (flow.log_prob(yy), flow.inverse(yy))
+        bytes_unit = LAYERS * (8 * d + 8) + LAYERS * 8 * d
+        flops_unit, bound = 2 * LAYERS * 2 * (32 * 256 + 256 * 256 + 256 * 64), 'tensor'
+        traffic_key = None
+        if want_cpu:
+            n = 1 << 15
+            yc = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
+            with torch.no_grad():
+                O.flow_log_prob(spec, yc[:256])
+                cpu = _cpu_rate(lambda: (O.flow_log_prob(spec, yc), O.flow_inverse(spec, yc)), n) + \
+                    (f'{n} rows of the same workload (log_prob + inverse), one call each',)
+    elif workload == 'neural':
+        d, B, T, nl = 16, 65536, 64, 4
+        layers = [st.ContinuousAffineCoupling(st.net.MLP(d + 1, [64], 2 * d), st.net.TimeLinear(2 * d),
+                                              ('ordered_0', 'ordered_1')[i % 2]) for i in range(nl)]
+        spec = spec_from_layers(layers) if want_cpu else None
+        flow = st.NeuralFlow(layers).to(dev).requires_grad_(False)
+        name = f'NeuralFlow 4x ContinuousAffineCoupling dim 16, MLP[17->64->32] tanh, TimeLinear(32), x [{B},{T},{d}] with per-step t, forward'
+        a, b = shard_rows(B, rank, world)
+        g = torch.Generator(dev).manual_seed(rank)
+        x = torch.randn(b - a, T, d, device=dev, generator=g)
+        t = torch.rand(b - a, T, 1, device=dev, generator=g)
+
+        def step():
+            with torch.no_grad():
+                return flow(x, t=t)
+        unit, per_step = 'rows/s', B * T
+        ins, n_out = [x, t], 1
+        pipe_fn = lambda xx, tt: flow(xx, t=tt)
+        bytes_unit, flops_unit, bound = nl * (2 * 4 * d + 4), nl * 2 * (9 * 64 + 64 * 16), 'hbm'
+        traffic_key = 'neural_dram_bytes_per_row'
+        if want_cpu:
+            n = 1 << 12
+            gc = torch.Generator().manual_seed(0)
+            xc, tc = torch.randn(n, T, d, generator=gc), torch.rand(n, T, 1, generator=gc)
+            with torch.no_grad():
+                O.neural_flow_forward(spec, xc[:8], tc[:8])
+                cpu = _cpu_rate(lambda: O.neural_flow_forward(spec, xc, tc), n * T) + \
+                    (f'x [{n},{T},{d}] of the same workload, one call',)
+    else:
+        d, rows_g = 128, args.batch
+        P = 3 * BINS - 1
+        layers = [st.Coupling(st.Spline(d, BINS, latent_net=st.net.MLP(d, list(args.hidden), d * P), lower=LOWER,
+                                        upper=UPPER, spline_type='quadratic'), mask=MASKS[i % 2])
+                  for i in range(LAYERS)]
+        spec = spec_from_layers(layers) if want_cpu else None
+        flow = st.NormalizingFlow(st.UnitNormal(d), layers).to(dev)
+        name = (f'NLL training step (fwd+bwd, gradients and loss all-reduced over NCCL) quadratic spline coupling d=128, '
+                f'8 layers, 16 bins, MLP{list(args.hidden)} tanh, global batch {rows_g}')
+        a, b = shard_rows(rows_g, rank, world)
+        y = torch.randn(b - a, d, device=dev, generator=torch.Generator(dev).manual_seed(rank))
+        if args.tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True
+        if args.hybrid:
+            os.environ['STRIBOR_B200_TRAIN_HYBRID'] = '1'
+        name += (f', micro-batches of {args.micro_rows} rows' + (', hybrid path' if args.hybrid else ', fused backward kernel'))
+        dp = DataParallelNLL(flow, micro_rows=args.micro_rows)
+        steps = 3
+
+        def step():
+            return dp.step(y, rows_g)
+        unit, per_step = 'samples/s', rows_g
+        ins, n_out = [y], 0
+        pipe_fn = None
+        bytes_unit = LAYERS * (8 * d + 8) + LAYERS * 12 * d
+        flops_unit, bound = 3 * LAYERS * 2 * (64 * 64 + 64 * 64 * P), 'tensor'
+        traffic_key = None
+        if want_cpu:
+            n = 1 << 11
+            yc = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
+            leaves = []
+            for layer in spec:
+                net = layer['transform']['net']
+                for w, bb in zip(net['weights'], net['biases']):
+                    leaves += [w.requires_grad_(True), bb.requires_grad_(True)]
+
+            def cpu_step():
+                (-O.flow_log_prob(spec, yc).mean()).backward()
+            cpu_step()
+            cpu = _cpu_rate(cpu_step, n) + (f'{n} rows, one fwd+bwd of the same flow through torch autograd on the oracle port',)
+
+    ms_step, launches = _timed(step, steps, warmup, dev, world)
+    value = per_step / (ms_step * 1e-3)
+    rows_local = ins[0].shape[0] * (ins[0].shape[1] if workload == 'neural' else 1)
+    res.update({'metric': f'{workload} throughput', 'value': value, 'unit': unit, 'ms_per_step': ms_step,
+                'config': {'workload': name, 'l2_policy': 'inputs larger than L2' if ins[0].numel() * 4 > L2_BYTES
+                           else 'inputs + outputs of one step exceed L2 together'},
+                'gpu_launches': launches})
+    # roofline of the config's dominant kernel family: algorithmic bytes (SURVEY 8d) or masked-minimum flops
+    # per unit x the units this rank processes per step / measured step time (the step is that kernel family
+    # back to back; nothing else runs in the timed region)
+    if bound == 'hbm':
+        ach = rows_local * bytes_unit / (ms_step * 1e-3) / 1e9
+        tr = _profile_traffic(traffic_key) if traffic_key else None
+        res['roofline'] = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+                           'traffic': None if tr is None else tr * rows_local / max(launches / steps, 1),
+                           'peak_source': peak_src, 'bytes_per_unit': bytes_unit,
+                           'binding': 'tensor pipe + spline epilogue (SURVEY 8d)' if workload == 'cubic' else 'hbm'}
+        res['roofline_tensor'] = {'bound': 'tensor', 'achieved': rows_local * flops_unit / (ms_step * 1e-3) / 1e12,
+                                  'peak': tf_peak, 'unit': 'TFLOP/s',
+                                  'frac': rows_local * flops_unit / (ms_step * 1e-3) / 1e12 / tf_peak,
+                                  'note': 'masked-minimum fp32-equivalent conditioner flops over the measured bf16 dense peak'}
+    else:
+        ach = rows_local * flops_unit / (ms_step * 1e-3) / 1e12
+        res['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak,
+                           'traffic': None, 'peak_source': peak_src, 'flops_per_unit': flops_unit,
+                           'note': 'masked-minimum fp32-equivalent conditioner flops (SURVEY 8d) over the measured bf16 '
+                                   'dense peak; the kernels issue kind::f16 tcgen05.mma in 3 split passes, i.e. ~3x these flops'}
+        res['roofline_hbm'] = {'bound': 'hbm', 'achieved': rows_local * bytes_unit / (ms_step * 1e-3) / 1e9,
+                               'peak': hbm_peak, 'unit': 'GB/s',
+                               'frac': rows_local * bytes_unit / (ms_step * 1e-3) / 1e9 / hbm_peak}
+    # end to end: pinned host buffers -> H2D -> the public call -> D2H, inside the timed region
+    if pipe_fn is not None and not args.no_e2e:
+        chunk = max(1 << 12, ins[0].shape[0] // 4)
+        pipe = HostPipeline(flow, d, dev, chunk_rows=chunk)
+        ins_h = [torch.empty(t_.shape, pin_memory=True).copy_(t_) for t_ in ins]
+        with torch.no_grad():
+            sample = pipe_fn(*[t_[:2] for t_ in ins])
+        sample = sample if isinstance(sample, (tuple, list)) else (sample,)
+        outs_h = [torch.empty((ins[0].shape[0],) + tuple(o.shape[1:]), pin_memory=True) for o in sample]
+        k = 3
+        ms_e, _ = _timed(lambda: pipe.map(pipe_fn, ins_h, outs_h), k, 2, dev, world)
+        res['e2e'] = {'value': per_step / (ms_e * 1e-3), 'unit': unit,
+                      'h2d_bytes_per_step': sum(t_.numel() * 4 for t_ in ins_h) * world,
+                      'd2h_bytes_per_step': sum(o.numel() * 4 for o in outs_h) * world,
+                      'how': f'pinned host tensors -> H2D -> public call -> D2H, chunks of {chunk} rows on two streams'}
+    elif workload == 'train':
+        # the training step's host traffic: the batch arrives from pinned host memory every step, the scalar loss
+        # goes back (what a data loader feeds); gradients stay on the device for the optimizer
+        y_h = torch.empty(y.shape, pin_memory=True).copy_(y)
+        ybuf = torch.empty_like(y)
+
+        def e2e_step():
+            ybuf.copy_(y_h, non_blocking=True)
+            return float(dp.step(ybuf, rows_g))
+        ms_e, _ = _timed(e2e_step, 2, 1, dev, world)
+        res['e2e'] = {'value': per_step / (ms_e * 1e-3), 'unit': unit, 'h2d_bytes_per_step': y_h.numel() * 4 * world,
+                      'd2h_bytes_per_step': 4 * world, 'how': 'pinned host batch -> H2D -> DataParallelNLL.step -> loss.item()'}
+        res['allreduce_bytes_per_step'] = int(dp.last_allreduce_bytes)
+    if cpu is not None:
+        v, cores, secs, what = cpu
+        res['cpu_baseline'] = {'value': v, 'unit': unit, 'cores': cores, 'kind': 'port',
+                               'sample': f'{what} ({secs:.1f} s); oracle port of the reference on torch CPU ops, '
+                                         f'{cores} threads, {cpu_model()}'}
+    return res
+
+
+def run_side(args):
+    from stribor_b200.parallel import init_from_env
+    rank, world, local = init_from_env('nccl')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    res = side_config(args.workload, args, dev, rank, world, want_cpu=(world == 1 and not args.no_cpu_baseline))
     if rank == 0:
-        emit({'metric': f'{args.workload} throughput', 'value': per_step / (ms_step * 1e-3), 'unit': unit,
-                          'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
-                          'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
-                          'data': 'synthetic', 'config': {'workload': name},
-                          'gpu_launches': int(_ops.launch_count() - n0)})
+        res.setdefault('vs_baseline', None)
+        emit(res)
     if world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 
@@ -418,14 +602,32 @@ def main():
                'how': f'pinned host rows -> H2D -> flow.log_prob -> D2H, chunks of {pipe.chunk_rows} rows '
                       'double-buffered on two streams'}
 
+    # ---- parity of the TIMED batch: sampled rows re-evaluated by the oracle (fp32 and fp64) -------------
+    parity = None
+    if rank == 0 and args.parity_rows > 0 and not args.no_cpu_baseline:
+        from oracle import coupling_flow_oracle as O          # the checker, after the timed region
+        from stribor_b200.spec import spec_from_layers
+        n = min(args.parity_rows, rows)
+        idx = torch.randperm(rows, generator=torch.Generator().manual_seed(7))[:n].sort().values
+        ys = y[idx.to(dev)].cpu()
+        got = lp[idx.to(dev)].cpu().double().view(-1)
+        spec = spec_from_layers([l.cpu() for l in build_layers(args.kind, args.hidden)])
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+        with torch.no_grad():
+            w32 = torch.cat([O.flow_log_prob(spec, ys[i:i + 2048]) for i in range(0, n, 2048)]).double().view(-1)
+            s64 = O.spec_to(spec, torch.float64)
+            w64 = torch.cat([O.flow_log_prob(s64, ys[i:i + 2048].double()) for i in range(0, n, 2048)]).view(-1)
+        tol = 1e-5 + 1e-5 * w64.abs()
+        c1 = (got - w32).abs() <= tol
+        c2 = (got - w64).abs() <= (w32 - w64).abs() + tol
+        parity = {'rows': int(n), 'of': 'the timed batch, rows drawn with a fixed seed', 'rtol': 1e-5, 'atol': 1e-5,
+                  'frac_outside': float(1.0 - (c1 | c2).double().mean()),
+                  'frac_needing_fp64_arbitration': float(((~c1) & c2).double().mean()),
+                  'max_abs': float((got - w64).abs().max()), 'oracle_fp32_max_abs': float((w32 - w64).abs().max()),
+                  'rule': '|new-ref32| <= atol+rtol|ref| or |new-ref64| <= |ref32-ref64| + atol+rtol|ref| (SURVEY 8c)'}
+
     # ---- roofline of the dominant kernel (one fused layer launch) ---------------------------
-    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(peaks_path):
-        pk = json.load(open(peaks_path))
-        hbm_peak, peak_src = float(pk['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
-        tf_peak = float(pk.get('bf16_tflops_sustained', pk.get('bf16_tflops', 1394.6)))
-    else:
-        hbm_peak, peak_src, tf_peak = 6650.0, 'fallback (B200_PROFILING.md)', 1400.0
+    hbm_peak, tf_peak, peak_src = _peaks()
     launch_ms = ms / max(launches, 1)                         # rank-local average launch duration
     # layer applications one launch performs: 1 (a launch per layer) or all L (whole flow in one launch,
     # the tile stays in shared memory between layers -- DRAM traffic is then ~L times below the algorithmic
@@ -438,12 +640,9 @@ def main():
     flops_row = 2 * (sum(a * b for a, b in zip(h[:-1], h[1:])) + h[-1] * (D // 2) * P)
     tflops = rows * flops_row * layers_per_launch / (launch_ms * 1e-3) / 1e12
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    if os.path.exists(tpath) and args.kind == 'quadratic' and not args.generic:
-        tj = json.load(open(tpath))                             # dram__bytes_{read,write}.sum from ncu --set full
-        per_row = tj.get('dram_bytes_per_row_chain', tj['dram_bytes_per_row'] * layers_per_launch) if layers_per_launch > 1 \
-            else tj['dram_bytes_per_row']
-        traffic = per_row * rows
+    if args.kind == 'quadratic' and not args.generic:             # dram__bytes_{read,write}.sum from ncu --set full
+        per_row = _profile_traffic('dram_bytes_per_row_chain' if layers_per_launch > 1 else 'dram_bytes_per_row')
+        traffic = None if per_row is None else per_row * rows
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                 'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
                 'kernel': 'fused coupling layer' + (f', {layers_per_launch:g} layers per launch (tile resident in shared memory)'
@@ -452,9 +651,18 @@ def main():
                 'bytes_per_launch': bytes_per_launch, 'launch_ms': launch_ms,
                 'note': 'BASELINE metric asks for % of HBM peak on L*(8d+8) B/sample; the kernel is '
                         'bound by the conditioner contraction + spline epilogue, see tensor figure'}
+    # executed tensor work: GEMM1 as 8 bf16 partial products of [rows x 32] x [32 x 64], GEMM2 as 3 fp16 passes
+    # over 48 (padded from 47 / 34) columns per transformed dim
+    exec_flops_row = 2 * (8 * 32 * 64 + 3 * 64 * (D // 2) * 48) if list(args.hidden) == [64] else None
     roofline_tensor = {'bound': 'tensor', 'achieved': tflops, 'peak': tf_peak, 'unit': 'TFLOP/s',
                        'frac': tflops / tf_peak,
-                       'note': 'masked-minimum conditioner flops (SURVEY 8d); peak = measured bf16 dense'}
+                       'note': 'numerator: masked-minimum fp32-EQUIVALENT conditioner flops (SURVEY 8d); denominator: '
+                               'measured bf16 dense peak, while the kernel issues kind::f16 tcgen05.mma (same rate) in '
+                               'split passes -- see executed_*'}
+    if exec_flops_row is not None and not args.generic:
+        ex = rows * exec_flops_row * layers_per_launch / (launch_ms * 1e-3) / 1e12
+        roofline_tensor.update({'executed_tflops': ex, 'executed_frac': ex / tf_peak,
+                                'executed_over_useful': exec_flops_row / flops_row})
 
     out = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
@@ -464,7 +672,7 @@ def main():
                    'rows_per_gpu': rows, 'l2_policy': 'inputs larger than L2 (1 GiB of rows per pass)',
                    'path': 'generic' if args.generic else 'auto'},
         'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches),
-        'roofline': roofline, 'roofline_tensor': roofline_tensor,
+        'roofline': roofline, 'roofline_tensor': roofline_tensor, 'parity': parity,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -477,6 +685,21 @@ def main():
                       f'port of the reference on torch CPU ops, {cores} threads, {cpu_model()}; the '
                       'unmodified reference has an O(N^2) domain re-check on the quadratic path '
                       '(57 samples/s at 256-row chunks, BASELINE.md) that the port omits'}
+    # ---- the other BASELINE.json configs, each with its own roofline / cpu_baseline / e2e ----------------
+    if not args.no_configs and args.kind == 'quadratic' and list(args.hidden) == [64] and not args.generic \
+            and args.batch == GLOBAL_BATCH:
+        del y, lp
+        if e2e is not None:
+            del pipe, y_host, lp_host
+        torch.cuda.empty_cache()
+        cfgs = {}
+        for w in ('cubic', 'affine', 'neural', 'train'):
+            try:
+                cfgs[w] = side_config(w, args, dev, rank, world, want_cpu=(world == 1 and not args.no_cpu_baseline))
+            except Exception as e:                             # a side config must never cost the headline line
+                cfgs[w] = {'error': f'{type(e).__name__}: {e}'}
+            torch.cuda.empty_cache()
+        out['configs'] = cfgs
     if rank == 0:
         emit(out)
     if world > 1:

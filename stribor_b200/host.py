@@ -35,3 +35,33 @@ class HostPipeline:
         for s in self.streams:
             cur.wait_stream(s)
         return lp_host
+
+    @torch.no_grad()
+    def map(self, fn, ins_host, outs_host, chunk_rows: int = None):
+        """Generic form of ``log_prob``: ``fn(*device_chunks) -> tensor or tuple`` applied chunk-wise to host
+        tensors that share their leading (row) dimension; results are copied into ``outs_host``.  Device staging
+        buffers are allocated per call shape and cached."""
+        rows = ins_host[0].shape[0]
+        chunk = int(chunk_rows or self.chunk_rows)
+        cur = torch.cuda.current_stream(self.device)
+        key = tuple((tuple(t.shape[1:]), t.dtype) for t in ins_host) + (chunk,)
+        if getattr(self, '_map_key', None) != key:
+            self._map_bufs = [[torch.empty((chunk,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+                               for t in ins_host] for _ in self.streams]
+            self._map_key = key
+        for s in self.streams:
+            s.wait_stream(cur)
+        for i, r0 in enumerate(range(0, rows, chunk)):
+            r1 = min(rows, r0 + chunk)
+            s = self.streams[i % len(self.streams)]
+            bufs = [b[: r1 - r0] for b in self._map_bufs[i % len(self.streams)]]
+            with torch.cuda.stream(s):
+                for b, h in zip(bufs, ins_host):
+                    b.copy_(h[r0:r1], non_blocking=True)
+                res = fn(*bufs)
+                res = res if isinstance(res, (tuple, list)) else (res,)
+                for o, r in zip(outs_host, res):
+                    o[r0:r1].copy_(r, non_blocking=True)
+        for s in self.streams:
+            cur.wait_stream(s)
+        return outs_host

@@ -13,6 +13,11 @@ import sys
 import pytest
 import torch
 
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (_ROOT, os.path.join(_ROOT, 'tests'), os.path.join(_ROOT, 'tests', 'golden')):     # `python tests/test_gpu_bins.py`
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
 import cases
 from oracle import coupling_flow_oracle as O
 from stribor_b200 import _lib, _ops
