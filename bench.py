@@ -416,6 +416,7 @@ def side_config(workload, args, dev, rank, world, want_cpu):
     ms_step, launches = _timed(step, steps, warmup, dev, world)
     value = per_step / (ms_step * 1e-3)
     rows_local = ins[0].shape[0] * (ins[0].shape[1] if workload == 'neural' else 1)
+    res['steps'] = steps
     res.update({'metric': f'{workload} throughput', 'value': value, 'unit': unit, 'ms_per_step': ms_step,
                 'config': {'workload': name, 'l2_policy': 'inputs larger than L2' if ins[0].numel() * 4 > L2_BYTES
                            else 'inputs + outputs of one step exceed L2 together'},
