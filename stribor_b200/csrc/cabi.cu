@@ -60,12 +60,20 @@ static int apply_sequence(const stb_layer* const* seq, int n, int direction, con
     int i = 0;
     while (i < n) {
         int j = i + 1;
+        bool mlp_chain = false;
         if (!chain_off && rows > 0 && x && out && !(ldj_mode != STB_LDJ_NONE && !ldj) && validate_layer(seq[i]) == 0) {
             while (j < n && j - i < 8 && validate_layer(seq[j]) == 0 && tc_chain_supported(seq + i, j - i + 1)) ++j;
+            if (j == i + 1) {               // affine / continuous-affine couplings with small conditioners (tc_mlp.cu)
+                while (j < n && j - i < 8 && validate_layer(seq[j]) == 0 && tcm_chain_supported(seq + i, j - i + 1)) ++j;
+                mlp_chain = j - i >= 2;
+            }
         }
         const int last = (j == n);
         int rc;
-        if (j - i >= 2) {
+        if (mlp_chain) {
+            rc = tcm_chain_apply(seq + i, j - i, direction, cur, t, out, ldj, ldj ? mode : STB_LDJ_NONE,
+                                 last && base_lp_last, rows, s);
+        } else if (j - i >= 2) {
             rc = tc_chain_apply(seq + i, j - i, direction, cur, out, ldj, ldj ? mode : STB_LDJ_NONE,
                                 last && base_lp_last, rows, s);
         } else {

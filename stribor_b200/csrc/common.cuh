@@ -61,6 +61,11 @@ int tcm_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
 int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const float* t, float* y,
                     float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
 
+// every layer of an affine / continuous-affine flow with small conditioners in one launch (tc_mlp.cu, CHAIN kernel)
+bool tcm_chain_supported(const stb_layer* const* layers, int n);
+int tcm_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, const float* t, float* y,
+                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
+
 // backward (backward.cu)
 uint64_t layer_backward_workspace_bytes(const stb_layer* L, int64_t rows);
 int layer_backward(const stb_layer* L, int direction, const float* x, const float* latent,

@@ -455,6 +455,376 @@ __global__ void __launch_bounds__(Cfg<NCG>::kThreads, (NCG == 4) ? 1 : 2) tc_mlp
 }
 
 // -----------------------------------------------------------------------------------------------
+// CHAIN: every layer of an affine / continuous-affine flow in ONE launch (flow.py:104-107, 118-125 and
+// NeuralFlow.forward, flow.py:172-184, inside the kernel)
+// -----------------------------------------------------------------------------------------------
+// Small conditioners only (H = 64, dim <= 32 -- BASELINE.json configs[3]): the weight blocks of ALL chained
+// layers (28 KB each for MLP[k -> 64 -> 2 dim]) are loaded once per CTA and stay in shared memory, a 128-row
+// tile is read once, every layer is applied to it in place, and it is written once: 132 B of DRAM traffic per
+// row for the whole flow instead of per layer.  Such a tile is latency-bound (five dependent phases per layer:
+// A1 split -> GEMM1 -> activation -> GEMM2 -> affine), so one CTA runs V independent "virtual CTAs" -- each
+// with its own tile, barriers, A-operand buffer, issuer warp, eight epilogue warps and 128 TMEM columns --
+// that share the resident weights and fill each other's waits (the per-layer kernel gets the same effect from
+// two CTAs per SM, which cannot share the weights).
+// per-warp phase clocks of the chain kernel (profiling builds: -DSTB_TCM_PROF, tools/tcm_phase_prof.py)
+#ifdef STB_TCM_PROF
+__device__ unsigned int g_tcm_prof[160 * 32 * 8];
+#define TPROF_DECL unsigned int _pt = clock(), _pa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TPROF(i) { const unsigned int _n = clock(); _pa[i] += _n - _pt; _pt = _n; }
+#define TPROF_FLUSH { if ((threadIdx.x & 31) == 0) for (int _i = 0; _i < 8; ++_i) g_tcm_prof[(blockIdx.x * 32 + (threadIdx.x >> 5)) * 8 + _i] = _pa[_i]; }
+#else
+#define TPROF_DECL
+#define TPROF(i)
+#define TPROF_FLUSH
+#endif
+
+constexpr int kMaxChainM = 8;
+constexpr int kVcThreads = 384;            // per virtual CTA: producer, issuer, 8 epilogue warps, 2 idle (register budget)
+constexpr int kChainNCG = 2;
+constexpr uint32_t kSmallSlot = 3584;      // header | biases of one layer
+constexpr uint32_t kVcCols = 128;          // TMEM columns of one virtual CTA: main [0, 64) | corr [64, 128)
+
+struct ChainArgs {
+    const uint8_t* packed[kMaxChainM];
+    uint32_t w_off[kMaxChainM], w_bytes[kMaxChainM];
+    int n_layers, dim, xs_stride;
+    uint32_t sm_w, sm_vc, vc_bytes;        // shared-memory map: resident weights, first virtual CTA, its size
+    const float* x;
+    const float* t;
+    float* y;
+    float* ldj;
+    int ldj_mode, base_log_prob, inverse;
+    long long rows;
+    int n_tiles;
+};
+
+struct VcBars {
+    uint64_t a_ready, acc_ready;
+};
+
+template <int V>
+__global__ void __launch_bounds__(V * kVcThreads, 1) tc_mlp_chain_kernel(const ChainArgs A) {
+    constexpr int NCG = kChainNCG;
+    constexpr int kEpiThreads = NCG * 4 * 32;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t w_full;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x;
+    const int vc = tid / kVcThreads, vtid = tid - vc * kVcThreads;
+    const int warp = vtid >> 5, lane = vtid & 31;
+    const int d = A.dim, L = A.n_layers, xs_stride = A.xs_stride;
+
+    uint8_t* vbase = smem + A.sm_vc + (uint32_t)vc * A.vc_bytes;
+    float* xs = reinterpret_cast<float*>(vbase);
+    const uint32_t xs_bytes = ((uint32_t)kRows * xs_stride * 4 + 127) & ~127u;
+    float* ld_s = reinterpret_cast<float*>(vbase + xs_bytes);                  // [2][128]
+    float* t_s = ld_s + NCG * kRows;                                            // [128]
+    VcBars* bars = reinterpret_cast<VcBars*>(t_s + kRows);
+    uint8_t* abuf = vbase + xs_bytes + NCG * kRows * 4 + kRows * 4 + 128;
+
+    if (tid == 0) {
+        mbar_init(&w_full, 1);
+        fence_mbar_init();
+    }
+    if (vtid == 0) {
+        mbar_init(&bars->a_ready, NCG * 4);
+        mbar_init(&bars->acc_ready, 1);
+        fence_mbar_init();
+    }
+    if (tid < 32) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s + (uint32_t)vc * kVcCols;
+    if (tid == 0) {                               // headers, biases and weight blocks of every layer: once per CTA
+        uint32_t total = 0;
+        for (int l = 0; l < L; ++l) total += kSmallBytes + A.w_bytes[l];
+        mbar_arrive_expect_tx(&w_full, total);
+        for (int l = 0; l < L; ++l) {
+            bulk_g2s(smem + (uint32_t)l * kSmallSlot, A.packed[l], kSmallBytes, &w_full);
+            bulk_g2s(smem + A.sm_w + A.w_off[l], A.packed[l] + kOffW, A.w_bytes[l], &w_full);
+        }
+    }
+    mbar_wait(&w_full, 0);
+
+    constexpr int H = 64;
+    constexpr int kb_h = H / 16;
+    constexpr uint32_t a_part = (uint32_t)kRows * kK1 * 2;
+    constexpr uint32_t a_lo = (uint32_t)kRows * H * 2;
+    constexpr uint32_t a_sbo = (uint32_t)(H / 8) * 128;
+    constexpr uint32_t w1b = (uint32_t)H * 32, w2b = (uint32_t)H * 64, w3b = kNOut * 64;
+    const int dshift = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;
+    const int n_vcta = (int)gridDim.x * V, my_vcta = (int)blockIdx.x * V + vc;
+    const int my_tiles = (A.n_tiles > my_vcta) ? (A.n_tiles - 1 - my_vcta) / n_vcta + 1 : 0;
+
+    if (warp == 0) {
+        // ---- L2 prefetch of this virtual CTA's next tiles -------------------------------------------
+        if (lane == 0)
+            for (int it = 1; it < my_tiles; ++it) {
+                const long long nrow0 = ((long long)my_vcta + (long long)it * n_vcta) * kRows;
+                const long long nb = min((long long)kRows, A.rows - nrow0) * d * 4;
+                const char* src = reinterpret_cast<const char*>(A.x + nrow0 * d);
+                if (nb >= 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(nb & ~15LL)) : "memory");
+                if (it >= 4) break;                     // a few tiles ahead is enough; the rest follows the loads
+            }
+    } else if (warp == 1) {
+        // ---- UMMA issuer of this virtual CTA -----------------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, H);
+            const uint32_t idesc2 = make_idesc(FMT_F16, 128, H);
+            const uint32_t idesc3 = make_idesc(FMT_F16, 128, kNOut);
+            const uint32_t a0 = smem_u32(abuf);
+            const uint32_t dmain = tmem, dcorr = tmem + H;
+            uint32_t ause = 0;
+            tc_fence_after();
+            TPROF_DECL
+            for (int it = 0; it < my_tiles; ++it)
+            for (int l = 0; l < L; ++l) {
+                const Header* hdr = reinterpret_cast<const Header*>(smem + (uint32_t)l * kSmallSlot);
+                const int n_hidden = hdr->n_hidden;
+                const int k1b = (hdr->n_cond + (hdr->time_col >= 0 ? 1 : 0) <= 16) ? 1 : 2;   // K blocks of layer 1 in use
+                uint32_t roff = smem_u32(smem + A.sm_w + A.w_off[l]);
+                mbar_wait(&bars->a_ready, ause & 1); ++ause;
+                TPROF(0)
+                tc_fence_after();
+                uint32_t acc_m = 0, acc_c = 0;
+                for (int b = 0; b < 6; ++b, roff += w1b) {
+                    const int pb = 2 - b / 2, kb = b & 1;
+                    if (kb >= k1b) continue;                      // all-zero K block (<= 16 conditioning inputs)
+                    const uint64_t bd = make_smem_desc(roff, 128, 256);
+                    for (int pa = 2; pa >= 0; --pa) {
+                        if (pa == 2 && pb == 2) continue;
+                        const uint64_t ad = make_smem_desc(a0 + pa * a_part + kb * 256, 128, 512);
+                        if (pa == 0 && pb == 0) { umma_f16(dmain, ad, bd, idesc1, acc_m); acc_m = 1; }
+                        else { umma_f16(dcorr, ad, bd, idesc1, acc_c); acc_c = 1; }
+                    }
+                }
+                umma_commit(&bars->acc_ready);
+                TPROF(1)
+                for (int layer = (n_hidden == 2 ? 0 : 1); layer < 2; ++layer) {
+                    mbar_wait(&bars->a_ready, ause & 1); ++ause;
+                    TPROF(2)
+                    tc_fence_after();
+                    const bool last = (layer == 1);
+                    const uint32_t idesc = last ? idesc3 : idesc2;
+                    const uint32_t lo_off = last ? kNOut * 32 : (uint32_t)H * 32;
+                    acc_m = acc_c = 0;
+                    for (int kb = 0; kb < kb_h; ++kb) {
+                        const uint64_t b_hi = make_smem_desc(roff, 128, 256), b_lo = make_smem_desc(roff + lo_off, 128, 256);
+                        roff += last ? w3b : w2b;
+                        const uint64_t a_hi = make_smem_desc(a0 + kb * 256, 128, a_sbo);
+                        const uint64_t a_l = make_smem_desc(a0 + a_lo + kb * 256, 128, a_sbo);
+                        umma_f16(dcorr, a_l, b_hi, idesc, acc_c); acc_c = 1;
+                        umma_f16(dcorr, a_hi, b_lo, idesc, 1);
+                        umma_f16(dmain, a_hi, b_hi, idesc, acc_m); acc_m = 1;
+                    }
+                    umma_commit(&bars->acc_ready);
+                    TPROF(3)
+                }
+            }
+            TPROF_FLUSH
+        }
+    } else if (warp < kEpiWarp0 + NCG * 4) {
+        // ---- epilogue warps of this virtual CTA ------------------------------------------------------------
+        const int q = warp & 3;
+        const int cg = (warp - ((q >= kEpiWarp0) ? q : q + 4)) >> 2;
+        const int etid = vtid - kEpiWarp0 * 32;
+        const int row = q * 32 + lane;
+        float* xrow = xs + row * xs_stride;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
+        const bool inverse = A.inverse != 0;
+        const int bar_id = 1 + vc;
+        uint32_t acc_use = 0;
+        TPROF_DECL
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long row0 = ((long long)my_vcta + (long long)it * n_vcta) * kRows;
+            const int nrows = (int)min((long long)kRows, A.rows - row0);
+            {   // ---- stage x (once per flow) ---------------------------------------------------------------
+                const float* xg = A.x + row0 * d;
+                const int n = nrows * d;
+                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0)) {
+                    const int n4 = (kRows * d) >> 2;
+                    for (int i0 = etid; i0 < n4; i0 += kEpiThreads * 4) {
+                        float4 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * kEpiThreads;
+                            v[u] = (i < n4 && i * 4 < n) ? __ldg(reinterpret_cast<const float4*>(xg) + i)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * kEpiThreads;
+                            if (i < n4) {
+                                const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
+                                float* dst = xs + r * xs_stride + c;
+                                dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;
+                            }
+                        }
+                    }
+                } else {
+                    for (int i = etid; i < kRows * d; i += kEpiThreads) {
+                        const int r = (dshift >= 0) ? (i >> dshift) : i / d, c = i - r * d;
+                        xs[r * xs_stride + c] = (i < n) ? __ldg(xg + i) : 0.f;
+                    }
+                }
+                if (etid < kRows) t_s[etid] = (A.t != nullptr && etid < nrows) ? __ldg(A.t + row0 + etid) : 0.f;
+            }
+            named_bar_sync(bar_id, kEpiThreads);
+            TPROF(0)
+            float ld_acc = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
+                const uint8_t* small = smem + (uint32_t)l * kSmallSlot;
+                const Header* hdr = reinterpret_cast<const Header*>(small);
+                const float* b1s = reinterpret_cast<const float*>(small + kOffB1);
+                const float* b2s = reinterpret_cast<const float*>(small + kOffB2);
+                const float* b3s = reinterpret_cast<const float*>(small + kOffB3);
+                const int n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_hidden = hdr->n_hidden, act = hdr->act;
+                const int time_col = hdr->time_col;
+                const int k1b = (n_cond + (time_col >= 0 ? 1 : 0) <= 16) ? 1 : 2;
+                // ---- A1: this row's conditioning columns (+ t) as three bf16 parts ------------------------
+#pragma unroll 1
+                for (int kc = cg; kc < 2 * k1b; kc += NCG) {
+                    const uint32_t off = (uint32_t)(row >> 3) * 512 + (uint32_t)(row & 7) * 16 + kc * 128;
+                    __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = kc * 8 + u;
+                        const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : ((k == time_col) ? t_s[row] : 0.f);
+                        split_bf16x3(v, q0[u], q1[u], q2[u]);
+                    }
+                    *reinterpret_cast<uint4*>(abuf + off) = *reinterpret_cast<const uint4*>(q0);
+                    *reinterpret_cast<uint4*>(abuf + a_part + off) = *reinterpret_cast<const uint4*>(q1);
+                    *reinterpret_cast<uint4*>(abuf + 2 * a_part + off) = *reinterpret_cast<const uint4*>(q2);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_ready);
+                TPROF(1)
+                // ---- hidden layers ------------------------------------------------------------------------
+                for (int layer = 0; layer < n_hidden; ++layer) {
+                    mbar_wait_sleep(&bars->acc_ready, acc_use & 1, 32); ++acc_use;
+                    TPROF(2)
+                    tc_fence_after();
+                    const float sc = (layer == 0) ? 1.f : hdr->s_mid;
+                    const float* bias = (layer == 0) ? b1s : b2s;
+                    constexpr int cols = H / NCG;
+                    const uint32_t a_row = (uint32_t)(row >> 3) * a_sbo + (uint32_t)(row & 7) * 16;
+#pragma unroll 1
+                    for (int cb = 0; cb < cols; cb += 16) {
+                        const int c0 = cg * cols + cb;
+                        float vm[16], vc_[16];
+                        tmem_ld16(tmem + lane_sel + c0, vm);
+                        tmem_ld16(tmem + lane_sel + H + c0, vc_);
+                        tmem_ld_wait();
+                        __align__(16) __half hh[16], hl[16];
+                        if (act == STB_ACT_TANH) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                split_f16(tanh_fast(fmaf(vm[i] + vc_[i], sc, bias[c0 + i])), hh[i], hl[i]);
+                        } else {
+#pragma unroll 1
+                            for (int i = 0; i < 16; ++i) vm[i] = activate(act, fmaf(vm[i] + vc_[i], sc, bias[c0 + i]));
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) split_f16(vm[i], hh[i], hl[i]);
+                        }
+#pragma unroll
+                        for (int half8 = 0; half8 < 2; ++half8) {
+                            const int kc = (c0 >> 3) + half8;
+                            *reinterpret_cast<uint4*>(abuf + a_row + kc * 128) = *reinterpret_cast<const uint4*>(hh + half8 * 8);
+                            *reinterpret_cast<uint4*>(abuf + a_lo + a_row + kc * 128) = *reinterpret_cast<const uint4*>(hl + half8 * 8);
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->a_ready);
+                    TPROF(3)
+                }
+                // ---- output layer: affine transform of this warp's transformed dims ---------------------------
+                mbar_wait_sleep(&bars->acc_ready, acc_use & 1, 32); ++acc_use;
+                TPROF(4)
+                tc_fence_after();
+                const float s_out = hdr->s_out;
+                const bool cont = hdr->cont != 0;
+                const float tv = t_s[row];
+#pragma unroll 1
+                for (int og = cg; og * 8 < n_tr; og += NCG) {
+                    float lm[8], lc[8], sm_[8], sc_[8];
+                    tmem_ld8(tmem + lane_sel + og * 8, lm);
+                    tmem_ld8(tmem + lane_sel + H + og * 8, lc);
+                    tmem_ld8(tmem + lane_sel + kMaxTr + og * 8, sm_);
+                    tmem_ld8(tmem + lane_sel + H + kMaxTr + og * 8, sc_);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int ji = og * 8 + u;
+                        if (ji < n_tr) {
+                            const int j = hdr->tr_idx[ji];
+                            float ls = fmaf(lm[u] + lc[u], s_out, b3s[ji]);
+                            float sh = fmaf(sm_[u] + sc_[u], s_out, b3s[kMaxTr + ji]);
+                            if (cont) {                        // coupling.py:199-205
+                                ls *= hdr->ts_ls[ji] * tv;
+                                sh *= hdr->ts_sh[ji] * tv;
+                            }
+                            const float xv = xrow[j];
+                            if (inverse) { xrow[j] = (xv - sh) * expf(-ls); ld_acc -= ls; }
+                            else { xrow[j] = xv * expf(ls) + sh; ld_acc += ls; }
+                        }
+                    }
+                }
+                tc_fence_before();
+                TPROF(5)
+                // the next layer gathers columns other warps have just written (and reuses the accumulators)
+                named_bar_sync(bar_id, kEpiThreads);
+                TPROF(6)
+            }   // layers
+
+            ld_s[cg * kRows + row] = ld_acc;
+            named_bar_sync(bar_id, kEpiThreads);
+            if (cg == 0 && want_ld && row < nrows) {
+                float tot = ld_s[row] + ld_s[kRows + row];
+                if (A.base_log_prob) {
+                    float b = 0.f;
+                    for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
+                    tot += b;
+                }
+                float* dst = A.ldj + row0 + row;
+                *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
+            }
+            {
+                float* yg = A.y + row0 * d;
+                const int n = nrows * d;
+                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
+                    const int n4 = n >> 2;
+                    for (int i = etid; i < n4; i += kEpiThreads) {
+                        const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
+                        const float* src = xs + r * xs_stride + c;
+                        reinterpret_cast<float4*>(yg)[i] = make_float4(src[0], src[1], src[2], src[3]);
+                    }
+                } else {
+                    for (int i = etid; i < n; i += kEpiThreads) {
+                        const int r = (dshift >= 0) ? (i >> dshift) : i / d, c = i - r * d;
+                        yg[i] = xs[r * xs_stride + c];
+                    }
+                }
+            }
+            named_bar_sync(bar_id, kEpiThreads);
+            TPROF(7)
+        }
+        TPROF_FLUSH
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem_base_s, 512);
+}
+
+// -----------------------------------------------------------------------------------------------
 // packing
 // -----------------------------------------------------------------------------------------------
 struct PackArgs {
@@ -671,6 +1041,80 @@ int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const flo
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_mlp_affine_kernel launch: %s", cudaGetErrorString(e));
+    return STB_OK;
+}
+
+#ifdef STB_TCM_PROF
+extern "C" int stb_tcm_prof_read(unsigned int* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, tcm::g_tcm_prof, (size_t)n * 4);
+}
+#endif
+
+// ---- a run of affine / continuous-affine couplings of one flow in ONE launch ---------------------------------
+namespace tcm {
+static uint32_t layer_w_total(const stb_layer* L) {
+    const int H = L->net.dims[1];
+    return 6 * w1_block_bytes(H) + (L->net.n_linear == 3 ? (H / 16) * w2_block_bytes(H) : 0) + (H / 16) * w3_block_bytes();
+}
+constexpr int kChainV = 2;
+static bool chain_layout(const stb_layer* const* layers, int n, ChainArgs* A, uint32_t* smem_bytes) {
+    if (n < 2 || n > kMaxChainM) return false;
+    const int d = layers[0]->dim;
+    uint32_t w = 0;
+    for (int i = 0; i < n; ++i) {
+        const stb_layer* L = layers[i];
+        if (!L->packed || !tcm_layer_supported(L) || L->dim != d || d > 32 || L->net.dims[1] != 64) return false;
+        if (L->packed_bytes < packed_bytes(64, L->net.n_linear - 1)) return false;
+        if (A) { A->w_off[i] = w; A->w_bytes[i] = layer_w_total(L); A->packed[i] = static_cast<const uint8_t*>(L->packed); }
+        w += layer_w_total(L);
+    }
+    const int xs_stride = d | 1;                                     // odd: column reads by row-threads stay conflict-free
+    const uint32_t xs_bytes = ((uint32_t)kRows * xs_stride * 4 + 127) & ~127u;
+    const uint32_t vc_bytes = (xs_bytes + kChainNCG * kRows * 4 + kRows * 4 + 128 + (uint32_t)kRows * 64 * 4 + 127) & ~127u;
+    const uint32_t sm_w = ((uint32_t)n * kSmallSlot + 127) & ~127u;
+    const uint32_t sm_vc = (sm_w + w + 127) & ~127u;
+    const uint32_t total = sm_vc + kChainV * vc_bytes;
+    if (total > 227 * 1024 - 1024) return false;                     // 1 KB: the kernel's static shared memory
+    if (A) { A->n_layers = n; A->dim = d; A->xs_stride = xs_stride; A->sm_w = sm_w; A->sm_vc = sm_vc; A->vc_bytes = vc_bytes; }
+    if (smem_bytes) *smem_bytes = total;
+    return true;
+}
+}  // namespace tcm
+
+bool tcm_chain_supported(const stb_layer* const* layers, int n) { return tcm::chain_layout(layers, n, nullptr, nullptr); }
+
+// layers[] in APPLICATION order (the caller reverses them for the inverse direction)
+int tcm_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, const float* t, float* y,
+                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream) {
+    using namespace tcm;
+    ChainArgs A = {};
+    uint32_t smem = 0;
+    if (!chain_layout(layers, n, &A, &smem)) return set_error(STB_EINVAL, "layers cannot be chained");
+    for (int i = 0; i < n; ++i)
+        if (layers[i]->kind == STB_CONT_AFFINE && !t) return set_error(STB_EINVAL, "layer expects a time input");
+    A.x = x; A.t = t; A.y = y; A.ldj = ldj;
+    A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
+    A.base_log_prob = base_log_prob;
+    A.inverse = direction == STB_INVERSE;
+    A.rows = rows;
+    const long long tiles = (rows + kRows - 1) / kRows;
+    if (tiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
+    A.n_tiles = (int)tiles;
+    static thread_local int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    void (*kern)(ChainArgs) = tc_mlp_chain_kernel<kChainV>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int grid = (int)min((long long)n_sm, (tiles + kChainV - 1) / kChainV);
+    kern<<<grid, kChainV * kVcThreads, smem, stream>>>(A);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_mlp_chain_kernel launch: %s", cudaGetErrorString(e));
     return STB_OK;
 }
 

@@ -324,3 +324,78 @@ def test_whole_flow_kernel_matches_layer_by_layer(kind, n_layers, d, rows):
     assert (li - tot).abs().max().item() < 2e-4 and (lf - tot_f).abs().max().item() < 2e-4
     base = (-0.5 * cur * cur - 0.9189385332046727).sum(-1, keepdim=True)
     assert (lp - (tot + base)).abs().max().item() < 5e-4
+
+
+def _cont_flow(d, n_layers, seed, hidden=(64,), latent=False):
+    rs = cases._rs(seed)
+    spec = [cases.cont_affine_spec(rs, d, list(hidden), ('ordered_0', 'ordered_1')[i % 2]) for i in range(n_layers)]
+    return spec
+
+
+@pytest.mark.parametrize('n_layers,d,rows', [(4, 16, 70000), (4, 16, 129), (7, 12, 5000), (2, 32, 1000), (3, 6, 300)])
+def test_affine_chain_kernel_matches_layer_by_layer(n_layers, d, rows):
+    """NeuralFlow.forward (flow.py:172-184) over ContinuousAffineCoupling + TimeLinear layers with small
+    conditioners is ONE launch (tc_mlp.cu, CHAIN kernel: weights of all layers resident in shared memory, the tile
+    stays on chip between layers).  Same arithmetic as one launch per layer: bit-identical outputs; and both
+    against the oracle."""
+    spec = _cont_flow(d, n_layers, 4000 + d)
+    layers = [l.to(DEV) for l in layers_from_spec(spec)]
+    torch.manual_seed(rows)
+    x = torch.randn(rows, d, device=DEV)
+    t = torch.rand(rows, 1, device=DEV)
+    t0 = torch.rand(rows, 1, device=DEV)
+    nf = st.NeuralFlow(layers)
+    with torch.no_grad():
+        nf(x[:8], t=t[:8])                                  # packs the weight images
+        n0 = _ops.launch_count()
+        y = nf(x, t=t)
+        n_fwd = _ops.launch_count() - n0
+        y0 = nf(x, t=t, t0=t0)
+        cur = x
+        for l in layers:
+            cur = l(cur, t=t)
+        cur0 = x
+        for l in reversed(layers):
+            cur0 = l.inverse(cur0, t=t0)
+        for l in layers:
+            cur0 = l(cur0, t=t)
+    per_launch = 4 if d <= 16 else 3                        # layers whose weights fit next to the tiles
+    assert n_fwd <= (n_layers + per_launch - 1) // per_launch + 1, f'{n_fwd} launches for {n_layers} layers'
+    assert torch.equal(y, cur), (y - cur).abs().max().item()
+    assert torch.equal(y0, cur0), (y0 - cur0).abs().max().item()
+    want = O.neural_flow_forward(O.spec_to(spec, torch.float64), x.cpu().double(), t.cpu().double())
+    assert ((y.cpu().double() - want).abs() <= 2e-5 + 1e-5 * want.abs()).all()
+    # identity at t = 0 stays exact through the chain
+    with torch.no_grad():
+        assert torch.equal(nf(x, t=torch.zeros_like(t)), x)
+
+
+@pytest.mark.parametrize('direction', ['log_prob', 'forward_ldj'])
+def test_affine_chain_kernel_log_det(direction):
+    """an affine-coupling NormalizingFlow with MLP[64] conditioners on the chain kernel: log-dets / log_prob
+    equal the layer-by-layer composition and the oracle"""
+    d, n_layers, rows = 16, 5, 3000
+    case = cases._mk_flow('affine', d, [64], n_layers, 0, rows, 4100)()
+    layers = [l.to(DEV) for l in layers_from_spec(case['spec'])]
+    flow = st.NormalizingFlow(st.UnitNormal(d), layers)
+    x = case['inputs']['x'].to(DEV)
+    with torch.no_grad():
+        if direction == 'log_prob':
+            got = flow.log_prob(x)
+            cur, tot = x, torch.zeros(rows, 1, device=DEV)
+            for l in reversed(layers):
+                cur, ld = l.inverse_and_log_det_jacobian(cur)
+                tot = tot + ld
+            ref_v = tot + (-0.5 * cur * cur - 0.9189385332046727).sum(-1, keepdim=True)
+            want = O.flow_log_prob(O.spec_to(case['spec'], torch.float64), x.cpu().double())
+        else:
+            y, got = flow.forward_and_log_det_jacobian(x)
+            cur, tot = x, torch.zeros(rows, 1, device=DEV)
+            for l in layers:
+                cur, ld = l.forward_and_log_det_jacobian(cur)
+                tot = tot + ld
+            ref_v = tot
+            assert torch.equal(y, cur)
+            want = O.flow_forward(O.spec_to(case['spec'], torch.float64), x.cpu().double(), with_ldj=True)[1]
+    assert (got - ref_v).abs().max().item() < 2e-4
+    assert ((got.cpu().double() - want).abs() <= 1e-4 + 1e-5 * want.abs()).all()
