@@ -467,8 +467,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
 #pragma unroll
                         for (int i = 0; i < 8; ++i) split_f16(tanh_fast(v[i] + b1s[c0 + i]), hh[i], hl[i]);
                     } else {
-#pragma unroll 1
-                        for (int i = 0; i < 8; ++i) v[i] = activate(act, v[i] + b1s[c0 + i]);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = sigmoid_act(v[i] + b1s[c0 + i]);      // STB_ACT_SIGMOID
 #pragma unroll
                         for (int i = 0; i < 8; ++i) split_f16(v[i], hh[i], hl[i]);
                     }

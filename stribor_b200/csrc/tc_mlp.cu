@@ -131,6 +131,51 @@ __device__ __forceinline__ float tanh_fast(float v) {                 // ~3e-7 a
     return copysignf(fdiv(1.f - t, 1.f + t), v);
 }
 
+// Hidden layer of the conditioner for TWO units at a time on Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2):
+// h = tanh((main + corr) * sc + bias) with the same arithmetic as tanh_fast, then the fp16 hi | lo split, each
+// part as one packed conversion.  Half the issue slots of the scalar form -- the activation passes were 45 % of
+// the chain kernel's clocks and ~40 % of the MLP[256,256] kernel's stall samples.
+__device__ __forceinline__ void tanh_split2(float2 vm, float2 vc, float2 sc, float2 bias, uint32_t& hi, uint32_t& lo) {
+    const float2 pre = __ffma2_rn(__fadd2_rn(vm, vc), sc, bias);
+    const float2 p = __fmul2_rn(pre, make_float2(2.885390081777927f, 2.885390081777927f));
+    float2 t;
+    t.x = ex2_approx(-fabsf(p.x));                            // the -|.| folds into the MUFU operand
+    t.y = ex2_approx(-fabsf(p.y));
+    const float2 one = make_float2(1.f, 1.f), mone = make_float2(-1.f, -1.f);
+    const float2 num = __ffma2_rn(t, mone, one);              // 1 - t
+    const float2 den = __fadd2_rn(t, one);                    // 1 + t
+    const float2 nden = __ffma2_rn(t, mone, mone);            // -(1 + t)
+    float2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(den.y));
+    const float2 q = __fmul2_rn(num, r);
+    const float2 th = __ffma2_rn(__ffma2_rn(q, nden, num), r, q);     // fdiv(num, den): one residual correction
+    const float2 h = make_float2(copysignf(th.x, pre.x), copysignf(th.y, pre.y));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(h.y), "f"(h.x));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    const float2 res = __ffma2_rn(hf, mone, h);               // h - hi: exact
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(res.y), "f"(res.x));
+}
+
+// the same for Sigmoid (the only other activation that reaches this kernel, see tcm_layer_supported)
+__device__ __forceinline__ void sigmoid_split2(float2 vm, float2 vc, float2 sc, float2 bias, uint32_t& hi, uint32_t& lo) {
+    const float2 pre = __ffma2_rn(__fadd2_rn(vm, vc), sc, bias);
+    float2 e;
+    e.x = ex2_approx(-1.4426950408889634f * fmaxf(pre.x, -80.f));
+    e.y = ex2_approx(-1.4426950408889634f * fmaxf(pre.y, -80.f));
+    const float2 one = make_float2(1.f, 1.f), mone = make_float2(-1.f, -1.f);
+    const float2 den = __fadd2_rn(e, one);
+    const float2 nden = __ffma2_rn(e, mone, mone);
+    float2 r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(den.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(den.y));
+    const float2 h = __ffma2_rn(__ffma2_rn(r, nden, one), r, r);        // 1 / den with one residual correction
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(h.y), "f"(h.x));
+    const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+    const float2 res = __ffma2_rn(hf, mone, h);
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(res.y), "f"(res.x));
+}
+
 template <int NCG>
 __global__ void __launch_bounds__(Cfg<NCG>::kThreads, (NCG == 4) ? 1 : 2) tc_mlp_affine_kernel(const Args A) {
     using C = Cfg<NCG>;
@@ -364,14 +409,19 @@ __global__ void __launch_bounds__(Cfg<NCG>::kThreads, (NCG == 4) ? 1 : 2) tc_mlp
                     tmem_ld_wait();
                     __align__(16) __half hh[16], hl[16];
                     if (act == STB_ACT_TANH) {
+                        const float2* b2p = reinterpret_cast<const float2*>(bias + c0);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            split_f16(tanh_fast(fmaf(vm[i] + vc[i], sc, bias[c0 + i])), hh[i], hl[i]);
-                    } else {
-#pragma unroll 1
-                        for (int i = 0; i < 16; ++i) vm[i] = activate(act, fmaf(vm[i] + vc[i], sc, bias[c0 + i]));
+                        for (int i = 0; i < 8; ++i)
+                            tanh_split2(make_float2(vm[2 * i], vm[2 * i + 1]), make_float2(vc[2 * i], vc[2 * i + 1]),
+                                        make_float2(sc, sc), b2p[i], reinterpret_cast<uint32_t*>(hh)[i],
+                                        reinterpret_cast<uint32_t*>(hl)[i]);
+                    } else {                                   // STB_ACT_SIGMOID
+                        const float2* b2p = reinterpret_cast<const float2*>(bias + c0);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) split_f16(vm[i], hh[i], hl[i]);
+                        for (int i = 0; i < 8; ++i)
+                            sigmoid_split2(make_float2(vm[2 * i], vm[2 * i + 1]), make_float2(vc[2 * i], vc[2 * i + 1]),
+                                           make_float2(sc, sc), b2p[i], reinterpret_cast<uint32_t*>(hh)[i],
+                                           reinterpret_cast<uint32_t*>(hl)[i]);
                     }
 #pragma unroll
                     for (int half8 = 0; half8 < 2; ++half8) {
@@ -724,14 +774,19 @@ __global__ void __launch_bounds__(V * kVcThreads, 1) tc_mlp_chain_kernel(const C
                         tmem_ld_wait();
                         __align__(16) __half hh[16], hl[16];
                         if (act == STB_ACT_TANH) {
+                            const float2* b2p = reinterpret_cast<const float2*>(bias + c0);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                split_f16(tanh_fast(fmaf(vm[i] + vc_[i], sc, bias[c0 + i])), hh[i], hl[i]);
-                        } else {
-#pragma unroll 1
-                            for (int i = 0; i < 16; ++i) vm[i] = activate(act, fmaf(vm[i] + vc_[i], sc, bias[c0 + i]));
+                            for (int i = 0; i < 8; ++i)
+                                tanh_split2(make_float2(vm[2 * i], vm[2 * i + 1]), make_float2(vc_[2 * i], vc_[2 * i + 1]),
+                                            make_float2(sc, sc), b2p[i], reinterpret_cast<uint32_t*>(hh)[i],
+                                            reinterpret_cast<uint32_t*>(hl)[i]);
+                        } else {                               // STB_ACT_SIGMOID
+                            const float2* b2p = reinterpret_cast<const float2*>(bias + c0);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) split_f16(vm[i], hh[i], hl[i]);
+                            for (int i = 0; i < 8; ++i)
+                                sigmoid_split2(make_float2(vm[2 * i], vm[2 * i + 1]), make_float2(vc_[2 * i], vc_[2 * i + 1]),
+                                               make_float2(sc, sc), b2p[i], reinterpret_cast<uint32_t*>(hh)[i],
+                                               reinterpret_cast<uint32_t*>(hl)[i]);
                         }
 #pragma unroll
                         for (int half8 = 0; half8 < 2; ++half8) {

@@ -76,6 +76,13 @@ __device__ __forceinline__ float tanh_fast(float v) {
     return copysignf(fdiv(1.f - t, 1.f + t), v);
 }
 
+// hidden activation Sigmoid on the tensor-core paths (the other bounded one; unbounded activations never reach
+// these kernels, see tc_layer_supported): clamped so that ex2 cannot overflow into rcp(inf) * inf = NaN
+__device__ __forceinline__ float sigmoid_act(float v) {
+    const float e = ex2_approx(-1.4426950408889634f * fmaxf(v, -80.f));
+    return fdiv(1.f, 1.f + e);
+}
+
 struct RqsBin16 {
     float xk, wk, yk, hk, delta, d0, d1;
 };

@@ -391,8 +391,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] + b1s[c0 + i]);
                 } else {
-#pragma unroll 1
-                    for (int i = 0; i < 8; ++i) v[i] = activate(act, v[i] + b1s[c0 + i]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = sigmoid_act(v[i] + b1s[c0 + i]);          // STB_ACT_SIGMOID
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) split_f16(v[i], hh[i], hl[i]);
@@ -997,8 +997,8 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = tanh_fast(v[i] + b1s[c0 + i]);
                 } else {
-#pragma unroll 1
-                    for (int i = 0; i < 8; ++i) v[i] = activate(act, v[i] + b1s[c0 + i]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = sigmoid_act(v[i] + b1s[c0 + i]);          // STB_ACT_SIGMOID
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) split_f16(v[i], hh[i], hl[i]);

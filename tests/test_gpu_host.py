@@ -200,3 +200,30 @@ def test_spline_subclass_hooks_reach_every_method():
         torch.testing.assert_close(x4r, x4, rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(l4r, -l4, rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(y4[:, 2:], x4[:, 2:], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize('kind,dim,hidden', [('quadratic', 64, [64]), ('cubic', 128, [64]), ('affine', 64, [128, 128]),
+                                             ('affine', 16, [64])])
+def test_sigmoid_hidden_activation_on_the_tensor_path(kind, dim, hidden):
+    """Sigmoid is the second bounded activation the tensor-core kernels evaluate themselves (clamped ex2 form);
+    large |pre-activation| must neither overflow nor lose parity"""
+    rows = 500
+    case = cases._mk_flow(kind, dim, hidden, 3, 16 if kind != 'affine' else 0, rows, 8100 + dim, lower=-4., upper=4.,
+                          scale=1.5, activation='Sigmoid')()
+    layers = [l.to(DEV) for l in layers_from_spec(case['spec'])]
+    flow = st.NormalizingFlow(st.UnitNormal(dim), layers)
+    d = layers[0].describe(dim, 0, torch.device(DEV))
+    L = _ops.make_struct(d['meta'], d['fmeta'], d['mask'], [p.detach() for p in d['params']], d['packed'])
+    assert _lib.lib().stb_layer_uses_tensor_path(L) == 1
+    x = case['inputs']['x'].clone()
+    x[:4] *= 200.0                                      # far outside the box: conditioner inputs of +-600
+    with torch.no_grad():
+        lp = flow.log_prob(x.to(DEV)).cpu()
+        xr = flow.inverse(x.to(DEV))
+        rt = (flow.forward(xr).cpu() - x).abs() / (1 + x.abs())
+    want = O.flow_log_prob(O.spec_to(case['spec'], torch.float64), x.double())
+    assert torch.isfinite(lp).all()
+    err = (lp.double() - want).abs() / (1e-5 * want.abs() + 1e-5)
+    frac = (err > 20).double().mean().item()
+    assert frac <= (0.01 if kind == 'cubic' else 0.0), (frac, err.max().item())
+    assert rt.max() < (5e-2 if kind == 'cubic' else 1e-4)
