@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define STB_ABI_VERSION 1
+#define STB_ABI_VERSION 2
 #define STB_MAX_LINEAR 8
 
 /* error codes */
@@ -118,6 +118,9 @@ typedef struct stb_layer {
     stb_mlp net;
     const void* packed;        /* device, from stb_pack_layer (NULL = generic path only)  */
     uint64_t packed_bytes;
+    const int32_t* perm_host;      /* HOST copies of perm / perm_inv (optional).  With them a permutation  */
+    const int32_t* perm_inv_host;  /* between chained couplings is folded into the neighbouring kernels'    */
+                                   /* gather / scatter index lists instead of costing an HBM pass           */
 } stb_layer;
 
 int stb_abi_version(void);
@@ -157,7 +160,10 @@ int stb_flow_apply(const stb_layer* layers, int n_layers, int direction, const f
                    int64_t rows, void* stream);
 
 /* lp[row] = log N(x; 0, I) + sum_layers ldj, x = inverse chain of y  (flow.py:127-130).
- * `x_out` must be a [rows, dim] scratch buffer (it receives the latent x). */
+ * `x_out` [rows, dim] receives the latent x and doubles as the scratch between launches.  It may be NULL when
+ * stb_flow_log_prob_needs_x_out() returns 0 -- the whole flow is one chained launch whose tile never leaves the
+ * chip -- which halves the compulsory HBM traffic of log_prob (4d + 4 instead of 8d + 4 bytes per row). */
+int stb_flow_log_prob_needs_x_out(const stb_layer* layers, int n_layers);
 int stb_flow_log_prob(const stb_layer* layers, int n_layers, const float* y, const float* latent,
                       const float* t, float* x_out, float* lp, int64_t rows, void* stream);
 

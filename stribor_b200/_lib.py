@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 STB_MAX_LINEAR = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums (include/stribor_b200.h)
 AFFINE, RQS, CUBIC, CONT_AFFINE, PERMUTE, SIGMOID, LOGIT = 0, 1, 2, 3, 4, 5, 6
@@ -26,7 +26,7 @@ LIB_PATH = os.environ.get('STRIBOR_B200_LIB') or \
 
 EXPORTS = ['stb_abi_version', 'stb_sizeof_layer', 'stb_last_error', 'stb_layer_apply', 'stb_layer_apply_diag',
            'stb_layer_apply_bins', 'stb_flow_apply',
-           'stb_flow_log_prob', 'stb_unit_normal_log_prob', 'stb_layer_backward_workspace_bytes',
+           'stb_flow_log_prob', 'stb_flow_log_prob_needs_x_out', 'stb_unit_normal_log_prob', 'stb_layer_backward_workspace_bytes',
            'stb_layer_backward', 'stb_layer_backward_diag', 'stb_packed_bytes', 'stb_pack_layer', 'stb_layer_uses_tensor_path',
            'stb_launch_count', 'stb_tc_selftest']
 
@@ -46,7 +46,8 @@ class StbLayer(C.Structure):
                 ('has_box', C.c_int32), ('row_compact', C.c_int32),
                 ('mask', C.c_void_p), ('mask_host', C.c_void_p), ('const_out', C.c_void_p), ('row_out', C.c_void_p),
                 ('time_scale', C.c_void_p), ('perm', C.c_void_p), ('perm_inv', C.c_void_p),
-                ('net', StbMlp), ('packed', C.c_void_p), ('packed_bytes', C.c_uint64)]
+                ('net', StbMlp), ('packed', C.c_void_p), ('packed_bytes', C.c_uint64),
+                ('perm_host', C.c_void_p), ('perm_inv_host', C.c_void_p)]
 
 
 class StbLayerGrads(C.Structure):
@@ -86,6 +87,8 @@ def lib():
     l.stb_flow_apply.argtypes = [LP, i32, i32, vp, vp, vp, vp, vp, i32, i64, vp]
     l.stb_flow_log_prob.restype = i32
     l.stb_flow_log_prob.argtypes = [LP, i32, vp, vp, vp, vp, vp, i64, vp]
+    l.stb_flow_log_prob_needs_x_out.restype = i32
+    l.stb_flow_log_prob_needs_x_out.argtypes = [LP, i32]
     l.stb_unit_normal_log_prob.restype = i32
     l.stb_unit_normal_log_prob.argtypes = [vp, vp, i32, C.c_int32, i64, vp]
     l.stb_layer_backward_workspace_bytes.restype = u64

@@ -120,9 +120,15 @@ def _fill_struct(L: _lib.StbLayer, meta: Sequence[int], fmeta: Sequence[float], 
         L.row_out = params[0].data_ptr() if row_mode else None
         rest = params[1:]
     L.time_scale = rest[0].data_ptr() if kind == _lib.CONT_AFFINE else None
+    L.perm_host = L.perm_inv_host = None
     if kind == _lib.PERMUTE:                      # params = [perm (int32), perm_inv (int32)]
         L.const_out = None
         L.perm, L.perm_inv = params[0].data_ptr(), params[1].data_ptr()
+        if len(meta) >= META_HEADER + 2 * dim:    # host copies ride in the meta list: [perm(dim) | perm_inv(dim)]
+            hp = (C.c_int32 * dim)(*meta[META_HEADER:META_HEADER + dim])
+            hi = (C.c_int32 * dim)(*meta[META_HEADER + dim:META_HEADER + 2 * dim])
+            L.perm_host, L.perm_inv_host = C.cast(hp, C.c_void_p), C.cast(hi, C.c_void_p)
+            keep = (hp, hi)
     else:
         L.perm = L.perm_inv = None
     if packed is not None and packed.numel() > 0:
@@ -142,7 +148,8 @@ def make_struct(meta, fmeta, mask, params, packed=None) -> _lib.StbLayer:
 
 def meta_len(meta: Sequence[int], off: int = 0) -> int:
     n_linear = meta[off + 10]
-    return META_HEADER + (n_linear + 1 if n_linear > 0 else 0) + (meta[off + 1] if meta[off + 3] else 0)
+    return META_HEADER + (n_linear + 1 if n_linear > 0 else 0) + (meta[off + 1] if meta[off + 3] else 0) + \
+        (2 * meta[off + 1] if meta[off] == _lib.PERMUTE else 0)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -484,7 +491,7 @@ layer_apply.register_autograd(_backward, setup_context=_setup_ctx)
 # ----------------------------------------------------------------------------------------------
 # whole chain in one C call (no autograd)
 # ----------------------------------------------------------------------------------------------
-CHAIN_FORWARD, CHAIN_INVERSE, CHAIN_LOG_PROB = 0, 1, 2
+CHAIN_FORWARD, CHAIN_INVERSE, CHAIN_LOG_PROB, CHAIN_LOG_PROB_ONLY = 0, 1, 2, 3
 
 
 @torch.library.custom_op('stribor_b200::flow_chain', mutates_args=(), device_types='cuda')
@@ -495,11 +502,10 @@ def flow_chain(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], masks: 
     mode LOG_PROB: (latent x [rows,dim], log_prob [rows])."""
     rows, dim = x.shape
     n_layers = len(masks)
-    out = torch.empty_like(x)
-    need_vec = want_ldj or mode == CHAIN_LOG_PROB
+    need_vec = want_ldj or mode in (CHAIN_LOG_PROB, CHAIN_LOG_PROB_ONLY)
     ldj = torch.empty(rows if need_vec else 0, dtype=x.dtype, device=x.device)
     if rows == 0:
-        return out, ldj
+        return torch.empty_like(x), ldj
     arr = (_lib.StbLayer * n_layers)()
     keep = []
     mo = po = 0
@@ -512,22 +518,29 @@ def flow_chain(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], masks: 
         mo += ml
         po += npar
     lib = _lib.lib()
+    # log_prob without the latent rows: when the whole flow is one chained launch nothing has to be written back
+    # but the log-probabilities (mode LOG_PROB_ONLY returns an empty first tensor)
+    skip_x = mode == CHAIN_LOG_PROB_ONLY and lib.stb_flow_log_prob_needs_x_out(arr, n_layers) == 0
+    out = x.new_empty(0, dim) if skip_x else torch.empty_like(x)
     with torch.cuda.device(x.device):
-        if mode == CHAIN_LOG_PROB:
-            rc = lib.stb_flow_log_prob(arr, n_layers, x.data_ptr(), _dp(latent), _dp(t), out.data_ptr(),
+        if mode in (CHAIN_LOG_PROB, CHAIN_LOG_PROB_ONLY):
+            rc = lib.stb_flow_log_prob(arr, n_layers, x.data_ptr(), _dp(latent), _dp(t), _dp(out),
                                        ldj.data_ptr(), rows, _stream(x))
         else:
             rc = lib.stb_flow_apply(arr, n_layers, _lib.FORWARD if mode == CHAIN_FORWARD else _lib.INVERSE,
                                     x.data_ptr(), _dp(latent), _dp(t), out.data_ptr(), _dp(ldj),
                                     _lib.LDJ_SET if want_ldj else _lib.LDJ_NONE, rows, _stream(x))
     _lib.check(rc)
+    if mode == CHAIN_LOG_PROB_ONLY and not skip_x:
+        out = x.new_empty(0, dim)                  # the scratch was needed (several launches) but is not returned
     return out, ldj
 
 
 @flow_chain.register_fake
 def _(x, latent, t, masks, params, packed, meta, fmeta, mode, want_ldj):
-    need_vec = want_ldj or mode == CHAIN_LOG_PROB
-    return torch.empty_like(x), x.new_empty(x.shape[0] if need_vec else 0)
+    need_vec = want_ldj or mode in (CHAIN_LOG_PROB, CHAIN_LOG_PROB_ONLY)
+    return (x.new_empty(0, x.shape[1]) if mode == CHAIN_LOG_PROB_ONLY else torch.empty_like(x)), \
+        x.new_empty(x.shape[0] if need_vec else 0)
 
 
 def launch_count() -> int:

@@ -51,6 +51,87 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
 // 256-row tensor-core kernel with the same dim and kind go out as ONE launch each (tc_layer.cu, CHAIN: the
 // tile stays in shared memory between the layers); everything else layer by layer.
 // STRIBOR_B200_NO_CHAIN=1: one launch per layer, for comparison.
+// A run of layers that goes out as ONE chained launch: 2..8 packed couplings of one tensor-core family -- spline
+// couplings of the 256-row kernel (tc_layer.cu, CHAIN) or affine / continuous-affine couplings with small conditioners
+// (tc_mlp.cu, CHAIN) -- of the same dim, with any permutations (flows/permute.py) before, between or after them folded
+// into the kernels' gather / scatter lists (ChainPerm): the tile keeps its original column order on chip.
+struct ChainRun {
+    const stb_layer* couplings[8];
+    int n;                  // couplings
+    int consumed;           // layers of the sequence covered (couplings + folded permutations)
+    bool mlp;               // tc_mlp.cu family
+    bool permuted;
+    ChainPerm perm;
+};
+
+static bool pair_ok(const stb_layer* a, const stb_layer* b, bool mlp) {
+    const stb_layer* two[2] = {a, b};
+    return mlp ? tcm_chain_supported(two, 2) : tc_chain_supported(two, 2);
+}
+
+static bool scan_run(const stb_layer* const* seq, int n, int direction, ChainRun* run) {
+    run->n = 0; run->consumed = 0; run->permuted = false; run->mlp = false;
+    int d = 0;
+    uint8_t phys[kChainPermMaxDim];
+    int k = 0, last_good = 0;
+    bool permuted = false;
+    for (; k < n; ++k) {
+        const stb_layer* L = seq[k];
+        if (validate_layer(L) != 0) break;
+        if (d == 0) {
+            d = L->dim;
+            if (d > kChainPermMaxDim) return false;
+            for (int c = 0; c < d; ++c) phys[c] = (uint8_t)c;
+        }
+        if (L->dim != d) break;
+        if (L->kind == STB_PERMUTE) {
+            const int32_t* p = (direction == STB_FORWARD) ? L->perm_host : L->perm_inv_host;
+            if (!p) break;
+            uint8_t np[kChainPermMaxDim];
+            for (int c = 0; c < d; ++c) {
+                if (p[c] < 0 || p[c] >= d) return false;
+                np[c] = phys[p[c]];                          // y[c] = x[p[c]]
+            }
+            for (int c = 0; c < d; ++c) phys[c] = np[c];
+            permuted = true;
+            if (run->n >= 2) { last_good = k + 1; for (int c = 0; c < d; ++c) run->perm.out_phys[c] = phys[c]; run->permuted = true; }
+            continue;
+        }
+        if (L->kind >= STB_PERMUTE || run->n >= 8) break;
+        if (run->n == 0) {
+            if (pair_ok(L, L, false)) run->mlp = false;
+            else if (pair_ok(L, L, true)) run->mlp = true;
+            else break;
+        } else {
+            run->couplings[run->n] = L;
+            const bool ok = run->mlp ? tcm_chain_supported(run->couplings, run->n + 1) : tc_chain_supported(run->couplings, run->n + 1);
+            if (!ok) break;
+        }
+        run->couplings[run->n] = L;
+        for (int c = 0; c < d; ++c) run->perm.phys[run->n][c] = phys[c];
+        ++run->n;
+        if (run->n >= 2) {
+            last_good = k + 1;
+            for (int c = 0; c < d; ++c) run->perm.out_phys[c] = phys[c];
+            run->permuted = permuted;
+        }
+    }
+    if (run->n < 2) return false;
+    // `last_good` is the end of the longest prefix that ends in (coupling | trailing permutation) with >= 2 couplings;
+    // couplings collected beyond it cannot exist (the loop only breaks on a non-member)
+    run->consumed = last_good;
+    return true;
+}
+
+// Is the whole sequence ONE chained launch (tile resident on chip from the first layer to the last)?  Then a
+// log_prob caller may leave out the [rows, dim] latent output: nothing needs an HBM scratch between layers.
+static bool single_chain(const stb_layer* const* seq, int n, int direction) {
+    ChainRun run;
+    return n >= 2 && scan_run(seq, n, direction, &run) && run.consumed == n;
+}
+
+// A sequence of layers (already in application order).  Maximal chainable runs (ChainRun) go out as ONE launch each;
+// everything else layer by layer.  STRIBOR_B200_NO_CHAIN=1: one launch per layer, for comparison.
 static int apply_sequence(const stb_layer* const* seq, int n, int direction, const float* x, const float* latent,
                           const float* t, float* out, float* ldj, int ldj_mode, int base_lp_last, int64_t rows,
                           cudaStream_t s) {
@@ -59,26 +140,21 @@ static int apply_sequence(const stb_layer* const* seq, int n, int direction, con
     int mode = ldj_mode;
     int i = 0;
     while (i < n) {
-        int j = i + 1;
-        bool mlp_chain = false;
-        if (!chain_off && rows > 0 && x && out && !(ldj_mode != STB_LDJ_NONE && !ldj) && validate_layer(seq[i]) == 0) {
-            while (j < n && j - i < 8 && validate_layer(seq[j]) == 0 && tc_chain_supported(seq + i, j - i + 1)) ++j;
-            if (j == i + 1) {               // affine / continuous-affine couplings with small conditioners (tc_mlp.cu)
-                while (j < n && j - i < 8 && validate_layer(seq[j]) == 0 && tcm_chain_supported(seq + i, j - i + 1)) ++j;
-                mlp_chain = j - i >= 2;
-            }
-        }
+        ChainRun run;
+        bool chained = false;
+        if (!chain_off && rows > 0 && x && !(ldj_mode != STB_LDJ_NONE && !ldj))
+            chained = scan_run(seq + i, n - i, direction, &run) && (out || (i == 0 && run.consumed == n));
+        const int j = chained ? i + run.consumed : i + 1;
         const int last = (j == n);
         int rc;
-        if (mlp_chain) {
-            rc = tcm_chain_apply(seq + i, j - i, direction, cur, t, out, ldj, ldj ? mode : STB_LDJ_NONE,
-                                 last && base_lp_last, rows, s);
-        } else if (j - i >= 2) {
-            rc = tc_chain_apply(seq + i, j - i, direction, cur, out, ldj, ldj ? mode : STB_LDJ_NONE,
-                                last && base_lp_last, rows, s);
+        if (chained) {
+            const ChainPerm* pm = run.permuted ? &run.perm : nullptr;
+            rc = run.mlp ? tcm_chain_apply(run.couplings, run.n, direction, cur, t, out, ldj, ldj ? mode : STB_LDJ_NONE,
+                                           last && base_lp_last, rows, s, pm)
+                         : tc_chain_apply(run.couplings, run.n, direction, cur, out, ldj, ldj ? mode : STB_LDJ_NONE,
+                                          last && base_lp_last, rows, s, pm);
         } else {
-            if (seq[i]->kind == STB_PERMUTE && cur == out)
-                return set_error(STB_ENOTSUP, "a permutation inside a fused chain needs out != x for that hop (use the layer-by-layer path)");
+            if (!out) return set_error(STB_EINVAL, "the output / scratch buffer is NULL but this flow needs several launches");
             rc = apply_one(seq[i], direction, cur, latent, t, out, ldj, ldj ? mode : STB_LDJ_NONE,
                            last && base_lp_last, rows, s);
         }
@@ -138,14 +214,24 @@ int stb_flow_apply(const stb_layer* layers, int n_layers, int direction, const f
     return apply_sequence(order, n_layers, direction, x, latent, t, out, ldj, ldj_mode, 0, rows, s);
 }
 
+int stb_flow_log_prob_needs_x_out(const stb_layer* layers, int n_layers) {
+    static const bool chain_off = [] { const char* e = getenv("STRIBOR_B200_NO_CHAIN"); return e && e[0] == '1'; }();
+    if (chain_off || n_layers < 2 || n_layers > 8 || !layers) return 1;
+    const stb_layer* order[8];
+    for (int i = 0; i < n_layers; ++i) order[i] = &layers[n_layers - 1 - i];
+    return single_chain(order, n_layers, STB_INVERSE) ? 0 : 1;
+}
+
 int stb_flow_log_prob(const stb_layer* layers, int n_layers, const float* y, const float* latent,
                       const float* t, float* x_out, float* lp, int64_t rows, void* stream) {
     if (n_layers < 1 || !layers) return set_error(STB_EINVAL, "log_prob needs at least one layer");
-    if (!x_out || !lp) return set_error(STB_EINVAL, "x_out / lp is NULL");
+    if (!lp) return set_error(STB_EINVAL, "lp is NULL");
     cudaStream_t s = (cudaStream_t)stream;
     if (n_layers > 64) return set_error(STB_EINVAL, "more than 64 layers");
     const stb_layer* order[64];
     for (int i = 0; i < n_layers; ++i) order[i] = &layers[n_layers - 1 - i];
+    if (!x_out && !(stb_flow_log_prob_needs_x_out(layers, n_layers) == 0))
+        return set_error(STB_EINVAL, "x_out is NULL but this flow is evaluated in several launches and needs the [rows, dim] scratch");
     return apply_sequence(order, n_layers, STB_INVERSE, y, latent, t, x_out, lp, STB_LDJ_SET, 1, rows, s);
 }
 

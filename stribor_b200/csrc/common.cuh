@@ -27,10 +27,19 @@ int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
 int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj,
                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins = nullptr);
 
+// Permutations (flows/permute.py:11-82) between chained couplings are folded into the kernels' index lists: the tile
+// keeps its ORIGINAL column order on chip, layer l gathers / scatters logical column j at physical column phys[l][j],
+// and the tile is written back as y[:, i] = tile[:, out_phys[i]].  Built by cabi.cu from stb_layer.perm_host.
+constexpr int kChainPermMaxLayers = 8, kChainPermMaxDim = 64;
+struct ChainPerm {
+    uint8_t phys[kChainPermMaxLayers][kChainPermMaxDim];
+    uint8_t out_phys[kChainPermMaxDim];
+};
+
 // several layers of one flow in one launch (tc_layer.cu, CHAIN kernels); layers[] in application order
 bool tc_chain_supported(const stb_layer* const* layers, int n);
 int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, float* y, float* ldj,
-                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
+                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, const ChainPerm* perm = nullptr);
 
 // tcgen05 path for dim <= 128 and the training backward (tc_wide.cu).  `image` is the wide packed image:
 // it follows the tc_layer.cu image when the layer has both (tcw_image).
@@ -64,7 +73,8 @@ int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const flo
 // every layer of an affine / continuous-affine flow with small conditioners in one launch (tc_mlp.cu, CHAIN kernel)
 bool tcm_chain_supported(const stb_layer* const* layers, int n);
 int tcm_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, const float* t, float* y,
-                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
+                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream,
+                    const ChainPerm* perm = nullptr);
 
 // backward (backward.cu)
 uint64_t layer_backward_workspace_bytes(const stb_layer* L, int64_t rows);

@@ -332,6 +332,18 @@ __global__ void pointwise_kernel(int kind, int direction, const float* __restric
     const float tiny = 1.17549435e-38f, one_m_eps = 1.f - 1.1920929e-07f;
     const bool to_unit = (kind == STB_SIGMOID) == (direction == STB_FORWARD);   // R -> (0,1) ?
     float ld = 0.f, lp = 0.f;
+    if (kind == STB_PERMUTE && d <= 32 * 8) {
+        // the whole row is gathered into registers before the first write: safe when y aliases x
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int c = lane + 32 * k; v[k] = (c < d) ? x[row * d + perm[c]] : 0.f; }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane + 32 * k;
+            if (c < d) { y[row * d + c] = v[k]; if (base_log_prob) lp += -0.5f * v[k] * v[k] - 0.91893853320467274178f; }
+        }
+    } else
     for (int c = lane; c < d; c += 32) {
         float v, out;
         if (kind == STB_PERMUTE) {
@@ -364,7 +376,8 @@ __global__ void pointwise_kernel(int kind, int direction, const float* __restric
 
 int pointwise_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
                           int base_log_prob, int64_t rows, cudaStream_t stream) {
-    if (x == y && L->kind == STB_PERMUTE) return set_error(STB_EINVAL, "permutation cannot run in place");
+    if (x == y && L->kind == STB_PERMUTE && L->dim > 32 * 8)
+        return set_error(STB_EINVAL, "a permutation of more than 256 dims cannot run in place");
     const int32_t* perm = nullptr;
     if (L->kind == STB_PERMUTE) {
         perm = (direction == STB_FORWARD) ? L->perm : L->perm_inv;

@@ -154,6 +154,8 @@ struct Args {
     float lower_l[kMaxChain], upper_l[kMaxChain];
     int n_chunks_l[kMaxChain];
     int32_t* bins;                     // BINS kernels: [rows, dim] searched bin per element (stb_layer_apply_bins)
+    int permuted;                      // CHAIN: permutations between the layers, folded into the index lists
+    ChainPerm perm;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -412,6 +414,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 uint4* dst = reinterpret_cast<uint4*>(smem + kSmSmall);
                 for (int i = etid; i < (int)(kSmallBytes / 16); i += kEpiThreads) dst[i] = src[i];
                 named_bar_sync(1, kEpiThreads);
+                if (A.permuted) {             // logical -> physical tile columns of this layer (warp-uniform branch)
+                    Header* h = const_cast<Header*>(hdr);
+                    if (etid < kK1) h->cond_idx[etid] = A.perm.phys[l][h->cond_idx[etid]];
+                    else if (etid < kK1 + kMaxTr) h->tr_idx[etid - kK1] = A.perm.phys[l][h->tr_idx[etid - kK1]];
+                    named_bar_sync(1, kEpiThreads);
+                }
                 n_tr = hdr->n_tr; n_cond = hdr->n_cond; n_chunks = hdr->n_chunks; act = hdr->act;
                 s2 = hdr->s2; s2l = s2 * 1.4426950408889634f;
                 noshift_mask = hdr->noshift_mask;
@@ -590,11 +598,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
             }
 
-            // ---- y tile out (coalesced) --------------------------------------------------------------------
-            {
+            // ---- y tile out (coalesced); log_prob callers that do not want the latent rows pass y == NULL -------
+            if (A.y != nullptr) {
                 float* yg = A.y + row0 * d;
                 const int n = nrows * d;
-                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
+                if (CHAIN && A.permuted) {                            // the accumulated permutation, on the way out
+                    for (int i = etid; i < n; i += kEpiThreads) {
+                        const int r = (dshift >= 0) ? (i >> dshift) : i / d, c = i - r * d;
+                        yg[i] = xs[r * kXsStride + A.perm.out_phys[c]];
+                    }
+                } else if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
                     const int n4 = n >> 2;
                     for (int i = etid; i < n4; i += kEpiThreads) {
                         const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
@@ -838,10 +851,11 @@ bool tc_chain_supported(const stb_layer* const* layers, int n) {
 
 // layers[] in APPLICATION order (the caller reverses them for the inverse direction)
 int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, float* y, float* ldj,
-                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream) {
+                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, const ChainPerm* perm) {
     using namespace tcl;
     if (!tc_chain_supported(layers, n)) return set_error(STB_EINVAL, "layers cannot be chained");
     Args A = {};
+    if (perm) { A.permuted = 1; A.perm = *perm; }
     A.packed = static_cast<const uint8_t*>(layers[0]->packed);
     A.x = x; A.y = y; A.ldj = ldj;
     A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;

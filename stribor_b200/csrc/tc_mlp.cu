@@ -546,6 +546,8 @@ struct ChainArgs {
     int ldj_mode, base_log_prob, inverse;
     long long rows;
     int n_tiles;
+    int permuted;                          // permutations between the layers, folded into the index lists
+    ChainPerm perm;
 };
 
 struct VcBars {
@@ -597,6 +599,16 @@ __global__ void __launch_bounds__(V * kVcThreads, 1) tc_mlp_chain_kernel(const C
         }
     }
     mbar_wait(&w_full, 0);
+    if (A.permuted) {                             // logical -> physical tile columns, once: the headers stay resident
+        __syncthreads();
+        for (int i = tid; i < L * (kK1 + kMaxTr); i += V * kVcThreads) {
+            const int l = i / (kK1 + kMaxTr), k = i - l * (kK1 + kMaxTr);
+            Header* h = reinterpret_cast<Header*>(smem + (uint32_t)l * kSmallSlot);
+            if (k < kK1) h->cond_idx[k] = A.perm.phys[l][h->cond_idx[k]];
+            else h->tr_idx[k - kK1] = A.perm.phys[l][h->tr_idx[k - kK1]];
+        }
+        __syncthreads();
+    }
 
     constexpr int H = 64;
     constexpr int kb_h = H / 16;
@@ -852,10 +864,15 @@ __global__ void __launch_bounds__(V * kVcThreads, 1) tc_mlp_chain_kernel(const C
                 float* dst = A.ldj + row0 + row;
                 *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
             }
-            {
+            if (A.y != nullptr) {
                 float* yg = A.y + row0 * d;
                 const int n = nrows * d;
-                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
+                if (A.permuted) {
+                    for (int i = etid; i < n; i += kEpiThreads) {
+                        const int r = (dshift >= 0) ? (i >> dshift) : i / d, c = i - r * d;
+                        yg[i] = xs[r * xs_stride + A.perm.out_phys[c]];
+                    }
+                } else if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
                     const int n4 = n >> 2;
                     for (int i = etid; i < n4; i += kEpiThreads) {
                         const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
@@ -1140,11 +1157,13 @@ bool tcm_chain_supported(const stb_layer* const* layers, int n) { return tcm::ch
 
 // layers[] in APPLICATION order (the caller reverses them for the inverse direction)
 int tcm_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, const float* t, float* y,
-                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream) {
+                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream,
+                    const ChainPerm* perm) {
     using namespace tcm;
     ChainArgs A = {};
     uint32_t smem = 0;
     if (!chain_layout(layers, n, &A, &smem)) return set_error(STB_EINVAL, "layers cannot be chained");
+    if (perm) { A.permuted = 1; A.perm = *perm; }
     for (int i = 0; i < n; ++i)
         if (layers[i]->kind == STB_CONT_AFFINE && !t) return set_error(STB_EINVAL, "layer expects a time input");
     A.x = x; A.t = t; A.y = y; A.ldj = ldj;

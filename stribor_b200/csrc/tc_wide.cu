@@ -637,6 +637,8 @@ struct Args {
     float* g_w2;             // [n_chunks * 96, 72], accumulated
     float* g_w1;             // nullable: [64 hidden, 64 conditioning slots], accumulated -> first Linear fused too
     float* g_b1;             // [64], accumulated (with g_w1)
+    uint32_t cta_stride;     // deterministic mode: floats between the per-CTA copies of the three images (0: one shared copy)
+    uint32_t b1_extra;       // deterministic mode: float offset (from g_b1) of the gb1 slots of sub-partitions 1..3
     float lower, upper;
     long long rows;
     int n_tiles;
@@ -874,6 +876,12 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
     } else {
         // ======================= loader + epilogue warps ==========================================
         const int q = warp & 3;
+        // deterministic mode (A.cta_stride != 0): this CTA accumulates into its OWN copy of the images, every address
+        // by one fixed thread, tiles in a fixed order; tcw_reduce_images_kernel then sums the copies in CTA order
+        // (the three image pointers are re-derived at their rare uses: the kernel sits at its register ceiling)
+#define STB_G_W2P (A.g_w2 + (size_t)blockIdx.x * A.cta_stride)
+#define STB_G_W1P (A.g_w1 + (size_t)blockIdx.x * A.cta_stride)
+#define STB_G_B1P (A.g_b1 + (size_t)blockIdx.x * A.cta_stride + ((A.cta_stride && q) ? A.b1_extra + (uint32_t)(q - 1) * kHid : 0u))
         const int r4 = (warp - kTEpiWarp0) >> 2;
         const int etid = tid - kTEpiWarp0 * 32;
         const int rloc = q * 32 + lane;
@@ -1024,7 +1032,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                 tc_fence_after();
                 const int g = r4 & 1;
                 if (q < 3) {
-                    float* dst = A.g_w2 + ((size_t)c * kChunkN + rloc) * kWStride + g * 32;
+                    float* dst = STB_G_W2P + ((size_t)c * kChunkN + rloc) * kWStride + g * 32;
                     const uint32_t col = tmem + lane_sel + kColAccW + wb * kHPad + (uint32_t)g * 32;
                     float v[16];
 #pragma unroll
@@ -1041,7 +1049,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                         float w8[8];
                         tmem_ld8(tmem + lane_sel + kColAccW + wb * kHPad + kHid, w8);
                         tmem_ld_wait();
-                        atomicAdd(A.g_w2 + ((size_t)c * kChunkN + rloc) * kWStride + kHid, w8[0] * inv_sigma);
+                        atomicAdd(STB_G_W2P + ((size_t)c * kChunkN + rloc) * kWStride + kHid, w8[0] * inv_sigma);
                     }
                 }
                 tc_fence_before();
@@ -1201,7 +1209,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                             float sum = v[i];
 #pragma unroll
                             for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                            if (lane == i) atomicAdd(A.g_b1 + kc * 8 + i, sum);
+                            if (lane == i) atomicAdd(STB_G_B1P + kc * 8 + i, sum);
                         }
                     }
                 }
@@ -1258,7 +1266,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                     tmem_ld16(tmem + lane_sel + kColD2 + r4 * 16, v);
                     tmem_ld_wait();
                     if (q < 2) {
-                        float* dst = A.g_w1 + (size_t)rloc * kK1 + r4 * 16;
+                        float* dst = STB_G_W1P + (size_t)rloc * kK1 + r4 * 16;
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) red_add4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
                     }
@@ -1506,10 +1514,41 @@ int tcw_layer_backward(const stb_layer* L, const void* image, int direction, con
 }
 
 
+// STRIBOR_B200_DETERMINISTIC=1: bit-reproducible parameter gradients.  The default adds every tile's partial
+// products to ONE L2-resident image with red.global.add (summation order over tiles varies run to run); in this mode
+// each CTA owns a copy of the images (single writer per address, tiles in a fixed order) and a second kernel adds
+// the copies in CTA order.
+static bool train_deterministic() {
+    static const bool on = [] { const char* e = getenv("STRIBOR_B200_DETERMINISTIC"); return e && e[0] == '1'; }();
+    return on;
+}
+namespace tcw { namespace train {
+constexpr uint32_t kImgFloats = (uint32_t)kMaxChunks * kChunkN * kWStride + kHid * kK1 + kHid;      // gW2 | gW1 | gb1
+constexpr uint32_t kCtaStride = kImgFloats + 3 * kHid;                                               // + gb1 slots of q = 1..3
+constexpr int kDetMaxCtas = 160;
+
+// image 0 (+)= images 1 .. n_cta-1, then the four gb1 slots collapse into the first: fixed order, one thread per element
+__global__ void tcw_reduce_images_kernel(float* base, int n_cta) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kCtaStride) return;
+    float acc = base[i];
+    for (int c = 1; c < n_cta; ++c) acc += base[(size_t)c * kCtaStride + i];
+    base[i] = acc;
+}
+// gb1 [64] sits at the end of the image, the slots of sub-partitions 1..3 right behind it
+__global__ void tcw_collapse_gb1_kernel(float* base) {
+    const uint32_t i = threadIdx.x;
+    if (i >= kHid) return;
+    float* b1 = base + kImgFloats - kHid;
+    b1[i] = ((b1[i] + base[kImgFloats + i]) + base[kImgFloats + kHid + i]) + base[kImgFloats + 2 * kHid + i];
+}
+}}
+
 uint64_t tcw_train_workspace_floats(const stb_layer* L, int64_t rows) {
     (void)L;
-    return (uint64_t)rows * tcw::kHAug + (uint64_t)tcw::kMaxChunks * tcw::kChunkN * tcw::train::kWStride +
-           (uint64_t)tcw::kHid * tcw::kK1 + tcw::kHid;
+    const uint64_t img = train_deterministic() ? (uint64_t)tcw::train::kDetMaxCtas * tcw::train::kCtaStride
+                                               : (uint64_t)tcw::train::kImgFloats;
+    return (uint64_t)rows * tcw::kHAug + img;
 }
 
 // Fused: g_x; gW2 image = workspace[rows * 72 : +3072 * 72] (accumulated).  first_linear != 0: the first Linear's
@@ -1551,9 +1590,23 @@ int tcw_layer_backward_fused(const stb_layer* L, const void* image, int directio
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)train::kSmemBytes);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    const int grid = (int)min((long long)n_sm, tiles);
+    int grid = (int)min((long long)n_sm, tiles);
+    const bool det = train_deterministic();
+    if (det) {
+        grid = min(grid, train::kDetMaxCtas);
+        A.cta_stride = train::kCtaStride;
+        A.b1_extra = kHid;                       // from g_b1 (the last 64 floats of an image) to the slots behind it
+    }
     kern<<<grid, train::kTThreads, train::kSmemBytes, stream>>>(A);
     count_launch();
+    if (det) {
+        train::tcw_reduce_images_kernel<<<(train::kCtaStride + 255) / 256, 256, 0, stream>>>(A.g_w2, grid);
+        count_launch();
+        if (first_linear) {
+            train::tcw_collapse_gb1_kernel<<<1, 64, 0, stream>>>(A.g_w2);
+            count_launch();
+        }
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_wide_train_kernel launch: %s", cudaGetErrorString(e));
     return STB_OK;

@@ -100,8 +100,8 @@ def run_layer_diag(desc, x, latent, t, direction):
 def _chain_ok(transforms, tensors) -> bool:
     """Fused whole-chain path: every layer describable, nothing asks for gradients."""
     if len(transforms) == 0 or not all(hasattr(f, 'chainable') and f.chainable() for f in transforms):
-        return False                  # foreign modules, un-fused conditioners, permutations (cannot run
-                                      # in place), set_data couplings: layer-by-layer path
+        return False                  # foreign modules, un-fused conditioners, set_data couplings:
+                                      # layer-by-layer path
     if torch.is_grad_enabled():
         if any(v is not None and v.requires_grad for v in tensors):
             return False
@@ -128,8 +128,8 @@ def run_chain(transforms, mode, x, latent=None, t=None, want_ldj=False):
         fmeta += d['fmeta']
     out, vec = _ops.flow_chain(x.reshape(-1, dim).contiguous(), latent, t,
                                masks, params, packed, meta, fmeta, mode, want_ldj)
-    out = out.view(*lead, dim)
-    if want_ldj or mode == _ops.CHAIN_LOG_PROB:
+    out = out.view(*lead, dim) if out.shape[0] == x.numel() // dim else None      # LOG_PROB_ONLY: no latent rows
+    if want_ldj or mode in (_ops.CHAIN_LOG_PROB, _ops.CHAIN_LOG_PROB_ONLY):
         return out, vec.view(*lead, 1)
     return out, None
 
@@ -187,7 +187,7 @@ class NormalizingFlow(Transform):
     def log_prob(self, y, **kwargs):
         """flow.py:127-130: base log-density of the inverted point plus the summed log|det J|."""
         if isinstance(self.base_dist, UnitNormal) and self._fused(y, kwargs):
-            return run_chain(self.transforms, _ops.CHAIN_LOG_PROB, y, kwargs.get('latent'), kwargs.get('t'))[1]
+            return run_chain(self.transforms, _ops.CHAIN_LOG_PROB_ONLY, y, kwargs.get('latent'), kwargs.get('t'))[1]
         x, log_det_jac = self.inverse_and_log_det_jacobian(y, **kwargs)
         return self.base_dist.log_prob(x).unsqueeze(-1) + log_det_jac
 

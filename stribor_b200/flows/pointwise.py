@@ -34,8 +34,11 @@ class _Pointwise(ElementwiseTransform):
 
     def describe(self, dim, latent_dim, device):
         p = self._params(dim, device)
-        return {'meta': _meta(self.kind, dim, len(p)), 'fmeta': [0., 1.] * 3, 'mask': None, 'params': p,
-                'packed': None}
+        return {'meta': _meta(self.kind, dim, len(p)) + self._meta_tail(dim), 'fmeta': [0., 1.] * 3, 'mask': None,
+                'params': p, 'packed': None}
+
+    def _meta_tail(self, dim):
+        return []
 
     def _run(self, x, direction, want_ldj):
         return run_layer(self.describe(x.shape[-1], 0, x.device), x, None, None, direction, want_ldj)
@@ -67,7 +70,12 @@ class _Pointwise(ElementwiseTransform):
 class Permute(_Pointwise):
     """Fixed random permutation of the last dimension (permute.py:47-82); log-det 0."""
     kind = _lib.PERMUTE
-    in_place_ok = False
+    in_place_ok = True       # the kernel reads a whole row before it writes it; between chained couplings the
+                             # permutation is folded into their index lists and costs nothing
+
+    def _meta_tail(self, dim):
+        """host copies of the index arrays (stb_layer.perm_host / perm_inv_host)"""
+        return [int(v) for v in self.permutation.tolist()] + [int(v) for v in self.inverse_permutation.tolist()]
 
     def __init__(self, dim: int):
         super().__init__()

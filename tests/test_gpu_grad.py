@@ -349,3 +349,45 @@ def test_fused_backward_first_linear_in_kernel_vs_library(monkeypatch):
     close(gx_k, gx_l, 'grad_x')
     for i, (a, b) in enumerate(zip(gp_k, gp_l)):
         close(a, b, f'parameter {i}')
+
+
+_DET_SCRIPT = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + '/tests/golden')
+import cases
+import stribor_b200 as st
+from stribor_b200.spec import layers_from_spec
+kind = sys.argv[2]
+case = cases._mk_flow(kind, 128, [64], 2, 16, 40000, 991, lower=-4., upper=4., scale=1.5)()
+x = case['inputs']['x'].cuda()
+outs = []
+for rep in range(3):
+    layers = [l.cuda() for l in layers_from_spec(case['spec'])]
+    flow = st.NormalizingFlow(st.UnitNormal(128), layers)
+    (-flow.log_prob(x).mean()).backward()
+    outs.append(torch.cat([p.grad.reshape(-1) for p in flow.parameters()]).clone())
+same = all(torch.equal(outs[0], o) for o in outs[1:])
+print('BITWISE_SAME', int(same), float((outs[0] - outs[1]).abs().max()))
+torch.save(outs[0].cpu(), sys.argv[3])
+'''
+
+
+@pytest.mark.parametrize('kind', ['quadratic', 'cubic'])
+def test_deterministic_gradient_mode_is_bit_reproducible(kind, tmp_path):
+    """STRIBOR_B200_DETERMINISTIC=1: per-CTA gradient images + ordered reduction -> identical bits run to run
+    (the default red.global.add accumulation only fixes the value up to fp32 summation order)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ('1', '0'):
+        env = dict(os.environ, STRIBOR_B200_DETERMINISTIC=mode)
+        out = tmp_path / f'g{mode}.pt'
+        r = subprocess.run([sys.executable, '-c', _DET_SCRIPT, root, kind, str(out)], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith('BITWISE_SAME')][0].split()
+        res[mode] = (int(line[1]), float(line[2]), torch.load(out))
+    assert res['1'][0] == 1, f'deterministic mode differs run to run by {res["1"][1]}'
+    g1, g0 = res['1'][2], res['0'][2]
+    scale = g0.abs().max()
+    assert ((g1 - g0).abs().max() / scale).item() < 1e-4          # same value up to summation order

@@ -399,3 +399,109 @@ def test_affine_chain_kernel_log_det(direction):
             want = O.flow_forward(O.spec_to(case['spec'], torch.float64), x.cpu().double(), with_ldj=True)[1]
     assert (got - ref_v).abs().max().item() < 2e-4
     assert ((got.cpu().double() - want).abs() <= 1e-4 + 1e-5 * want.abs()).all()
+
+
+def test_log_prob_without_latent_rows():
+    """stb_flow_log_prob(x_out = NULL): allowed exactly when the flow is one chained launch; same values"""
+    import ctypes as C
+    case = _flows('quadratic', 64, cases.ALT, seed=77, n_layers=8)
+    layers = [l.to(DEV) for l in layers_from_spec(case['spec'])]
+    flow = st.NormalizingFlow(st.UnitNormal(64), layers)
+    x = torch.randn(5000, 64, device=DEV) * 1.5
+    with torch.no_grad():
+        lp = flow.log_prob(x)                                             # CHAIN_LOG_PROB_ONLY: no latent rows written
+        xi, li = flow.inverse_and_log_det_jacobian(x)
+    want = li + (-0.5 * xi * xi - 0.9189385332046727).sum(-1, keepdim=True)
+    assert (lp - want).abs().max().item() < 5e-4
+    # through the raw ABI: 8 chainable layers need no x_out, 9 layers (two launches) do
+    def arr_of(ls):
+        descs = [l.describe(64, 0, torch.device(DEV)) for l in ls]
+        arr = (_lib.StbLayer * len(ls))()
+        keep = [_ops._fill_struct(arr[i], d['meta'], d['fmeta'], d['mask'], [p.detach() for p in d['params']], d['packed'])
+                for i, d in enumerate(descs)]
+        return arr, keep, descs
+    arr, keep, descs = arr_of(layers)
+    lib = _lib.lib()
+    assert lib.stb_flow_log_prob_needs_x_out(arr, 8) == 0
+    out = torch.empty(5000, device=DEV)
+    rc = lib.stb_flow_log_prob(arr, 8, x.data_ptr(), None, None, None, out.data_ptr(), 5000,
+                               torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+    assert torch.equal(out.view(-1, 1), lp)
+    case9 = _flows('quadratic', 64, cases.ALT, seed=78, n_layers=9)
+    layers9 = [l.to(DEV) for l in layers_from_spec(case9['spec'])]
+    arr9, keep9, descs9 = arr_of(layers9)
+    assert lib.stb_flow_log_prob_needs_x_out(arr9, 9) == 1
+    rc = lib.stb_flow_log_prob(arr9, 9, x.data_ptr(), None, None, None, out.data_ptr(), 5000,
+                               torch.cuda.current_stream().cuda_stream)
+    assert rc == _lib.E_INVAL
+    with torch.no_grad():
+        lp9 = st.NormalizingFlow(st.UnitNormal(64), layers9).log_prob(x)      # the module allocates the scratch itself
+    assert torch.isfinite(lp9).all()
+
+
+@pytest.mark.parametrize('family', ['quadratic', 'cubic', 'cont_affine'])
+def test_permutations_fold_into_the_chain(family):
+    """Flip / Permute (flows/permute.py:11-82) between chained couplings cost no launch: they are folded into the
+    chain kernels' gather / scatter lists.  Result == layer-by-layer application == oracle."""
+    rs = cases._rs(515)
+    if family == 'cont_affine':
+        d, rows = 16, 3000
+        spec = []
+        for i in range(3):
+            spec.append(cases.cont_affine_spec(rs, d, [64], ('ordered_0', 'ordered_1')[i % 2]))
+            spec.append({'type': 'permute', 'perm': rs.permutation(d).tolist()} if i % 2 == 0 else {'type': 'flip'})
+    else:
+        d, rows = 64, 3000
+        spec = [{'type': 'flip'}]
+        for i in range(4):
+            spec.append(cases.coupling_spec(rs, family, d, [64], 'ordered_right_half', n_bins=16, lower=-4., upper=4.))
+            spec.append({'type': 'permute', 'perm': rs.permutation(d).tolist()} if i % 2 == 0 else {'type': 'flip'})
+    layers = [l.to(DEV) for l in layers_from_spec(spec)]
+    torch.manual_seed(5)
+    x = torch.randn(rows, d, device=DEV) * 1.5
+    kw = {'t': torch.rand(rows, 1, device=DEV)} if family == 'cont_affine' else {}
+    flow = st.NormalizingFlow(st.UnitNormal(d), layers)
+    with torch.no_grad():
+        flow.forward(x[:4], **kw)                               # pack
+        n0 = _ops.launch_count()
+        yf, lf = flow.forward_and_log_det_jacobian(x, **kw)
+        n_fwd = _ops.launch_count() - n0
+        xi, li = flow.inverse_and_log_det_jacobian(x, **kw)
+        lp = flow.log_prob(x, **kw)
+        cur, tot = x, torch.zeros(rows, 1, device=DEV)
+        for l in layers:
+            cur, ld = l.forward_and_log_det_jacobian(cur, **kw)
+            tot = tot + ld
+        cur_i, tot_i = x, torch.zeros(rows, 1, device=DEV)
+        for l in reversed(layers):
+            cur_i, ld = l.inverse_and_log_det_jacobian(cur_i, **kw)
+            tot_i = tot_i + ld
+    assert n_fwd == 1, f'{n_fwd} launches'
+    assert torch.equal(yf, cur), (yf - cur).abs().max().item()
+    assert torch.equal(xi, cur_i), (xi - cur_i).abs().max().item()
+    assert (lf - tot).abs().max().item() < 2e-4 and (li - tot_i).abs().max().item() < 2e-4
+    base = (-0.5 * cur_i * cur_i - 0.9189385332046727).sum(-1, keepdim=True)
+    assert (lp - (tot_i + base)).abs().max().item() < 5e-4
+    okw = {k: v.cpu().double() for k, v in kw.items()}
+    want = O.flow_forward(O.spec_to(spec, torch.float64), x.cpu().double(), **okw)
+    err = (yf.cpu().double() - want).abs()
+    if family == 'cubic':
+        assert (err > 1e-3).double().mean().item() < 0.01
+    else:
+        assert err.max().item() < 2e-4, err.max().item()
+
+
+def test_permutation_in_place_between_unchained_layers():
+    """a permutation that is NOT absorbed into a chain (generic-path couplings around it) runs as its own kernel on
+    the flow's single output buffer: the row is gathered into registers before it is written"""
+    case = cases.build_case('permute_quadratic_d16')
+    layers = [l.to(DEV) for l in layers_from_spec(case['spec'])]
+    flow = st.NormalizingFlow(st.UnitNormal(16), layers)
+    x = case['inputs']['x'].to(DEV)
+    with torch.no_grad():
+        y = flow.forward(x)
+        xr = flow.inverse(y)
+    want = O.flow_forward(case['spec'], x.cpu())
+    torch.testing.assert_close(y.cpu(), want, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(xr, x, rtol=1e-4, atol=1e-4)
