@@ -463,7 +463,7 @@ def test_permutations_fold_into_the_chain(family):
     kw = {'t': torch.rand(rows, 1, device=DEV)} if family == 'cont_affine' else {}
     flow = st.NormalizingFlow(st.UnitNormal(d), layers)
     with torch.no_grad():
-        flow.forward(x[:4], **kw)                               # pack
+        flow.forward(x[:4], **{k: v[:4] for k, v in kw.items()})         # pack
         n0 = _ops.launch_count()
         yf, lf = flow.forward_and_log_det_jacobian(x, **kw)
         n_fwd = _ops.launch_count() - n0
