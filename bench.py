@@ -520,6 +520,8 @@ def main():
             raise SystemExit(f'--gpus {args.gpus} needs torchrun with {args.gpus} ranks')
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
+    from stribor_b200.parallel import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local) if world > 1 else {'bound': False, 'why': 'single process'}
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -580,7 +582,7 @@ def main():
     # ---- end to end: pinned host rows -> device -> log_prob -> host -------------------------
     e2e = None
     if not args.no_e2e:
-        pipe = HostPipeline(flow, D, dev, chunk_rows=max(1 << 16, min(1 << 19, rows // 4)))
+        pipe = HostPipeline(flow, D, dev, chunk_rows=max(1 << 16, min(1 << 18, rows // 6)), n_streams=3)
         y_host = torch.empty(rows, D, pin_memory=True)
         y_host.copy_(y)
         lp_host = torch.empty(rows, 1, pin_memory=True)
@@ -601,7 +603,7 @@ def main():
         e2e = {'value': args.batch / (te.item() / k * 1e-3), 'unit': 'samples/s',
                'h2d_bytes_per_step': rows * D * 4 * world, 'd2h_bytes_per_step': rows * 4 * world,
                'how': f'pinned host rows -> H2D -> flow.log_prob -> D2H, chunks of {pipe.chunk_rows} rows '
-                      'double-buffered on two streams'}
+                      f'on {len(pipe.streams)} streams', 'numa': numa}
 
     # ---- parity of the TIMED batch: sampled rows re-evaluated by the oracle (fp32 and fp64) -------------
     parity = None

@@ -124,11 +124,10 @@ static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 static_assert(kSmA % 16 == 0 && kSmW1 % 16 == 0 && kSmB % 16 == 0 && kSmSmall % 16 == 0, "alignment");
 
 struct Bars {
+    uint64_t acc_full[2][2], acc_empty[2][2];
     uint64_t setup;
     uint64_t b_full[kStages], b_empty[kStages];
     uint64_t a1_ready[2], acc1_full[2], h_ready[2];
-    uint64_t acc_full[2][2], acc_empty[2][2];
-    uint32_t tmem_base;
 };
 static_assert(sizeof(Bars) <= 256, "barrier block");
 
@@ -198,11 +197,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    __shared__ uint32_t tmem_base_s;      // own word: the allocator writes it, keep it away from the mbarrier block
+    if (warp == 1) tmem_alloc(&tmem_base_s, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem = tmem_base_s;
 
     if (!CHAIN) {
         if (tid == 0) {                           // header + biases + packed first Linear

@@ -185,11 +185,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
         for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 8); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    __shared__ uint32_t tmem_base_s;      // own word: the allocator writes it, keep it away from the mbarrier block
+    if (warp == 1) tmem_alloc(&tmem_base_s, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem = tmem_base_s;
 
     if (tid == 0) {
         mbar_arrive_expect_tx(&bars->setup, kSmallBytes);
@@ -691,11 +692,12 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
         bars->tile_max = 0;
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(&bars->tmem_base, kTmemCols);
+    __shared__ uint32_t tmem_base_s;      // own word: the allocator writes it, keep it away from the mbarrier block
+    if (warp == 1) tmem_alloc(&tmem_base_s, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem = tmem_base_s;
 
     if (tid == 0) {
         mbar_arrive_expect_tx(&bars->setup, kSmallBytes);

@@ -40,6 +40,50 @@ def init_from_env(backend: Optional[str] = None):
     return rank, world, local
 
 
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin this process (and therefore the pinned host buffers it allocates afterwards: first touch) to the CPU
+    cores of the NUMA node the GPU hangs off.  With 8 ranks pulling rows over PCIe at once, host buffers on the far
+    socket halve the per-GPU copy rate.  No-op when the platform does not expose the topology (returns why)."""
+    info = {'bound': False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = None
+        if all(hasattr(pr, a) for a in ('pci_domain_id', 'pci_bus_id', 'pci_device_id')):
+            bdf = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        if bdf is None:
+            import subprocess
+            out = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(local_rank)],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout.strip()
+            bdf = out.splitlines()[0].strip() if out else None
+        if not bdf:
+            info['why'] = 'no PCI bus id'
+            return info
+        bdf = bdf.lower()
+        if len(bdf.split(':')[0]) == 8:                      # nvidia-smi prints an 8-digit domain, sysfs has 4
+            bdf = bdf[4:]
+        node_path = f'/sys/bus/pci/devices/{bdf}/numa_node'
+        node = int(open(node_path).read().strip()) if os.path.exists(node_path) else -1
+        info['pci'] = bdf
+        info['numa_node'] = node
+        if node < 0:
+            info['why'] = 'numa_node not exposed'
+            return info
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            info['why'] = 'no allowed cores on that node'
+            return info
+        os.sched_setaffinity(0, cpus)
+        info.update({'bound': True, 'cores': len(cpus)})
+    except Exception as e:                                   # topology probing must never break a run
+        info['why'] = f'{type(e).__name__}: {e}'
+    return info
+
+
 def _world() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 

@@ -1,4 +1,9 @@
-"""Small run of every kernel (ragged tails included) for compute-sanitizer memcheck."""
+"""Small run of every kernel (ragged tails included) for compute-sanitizer.
+
+    compute-sanitizer --tool memcheck|synccheck|racecheck python tools/sanitize_run.py [only]
+
+`only` (optional): a substring -- run just the sections whose name contains it (one process per kernel family, so a
+tool that stops the process at its first report still covers the others)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
@@ -7,7 +12,10 @@ import cases
 import stribor_b200 as st
 from stribor_b200.spec import layers_from_spec
 dev = 'cuda'
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ''
 def run(name, case, rows_list=(1, 255, 257, 700), grad=False):
+    if ONLY and ONLY not in name:
+        return
     layers = [l.to(dev) for l in layers_from_spec(case['spec'])]
     d = case['inputs']['x'].shape[-1]
     flow = st.NormalizingFlow(st.UnitNormal(d), layers)
@@ -33,10 +41,44 @@ run('generic cubic d7', cases.build_case('cubic_d7_ordered'), rows_list=(1, 33),
 run('pointwise', cases.build_case('permute_quadratic_d16'), rows_list=(1, 9, 300))
 import numpy as np
 rs = np.random.RandomState(1)
-spec = [cases.cont_affine_spec(rs, 16, [64], 'ordered_0') for _ in range(2)]
-nf = st.NeuralFlow([l.to(dev) for l in layers_from_spec(spec)])
-with torch.no_grad():
-    for r in (1, 129, 300):
-        x = torch.randn(r, 16, device=dev); t = torch.rand(r, 1, device=dev)
-        nf(x, t=t, t0=t * 0.5)
-torch.cuda.synchronize(); print('ok neural tc')
+if not ONLY or ONLY in 'neural tc':
+    spec = [cases.cont_affine_spec(rs, 16, [64], 'ordered_0') for _ in range(2)]
+    nf = st.NeuralFlow([l.to(dev) for l in layers_from_spec(spec)])
+    with torch.no_grad():
+        for r in (1, 129, 300):
+            x = torch.randn(r, 16, device=dev); t = torch.rand(r, 1, device=dev)
+            nf(x, t=t, t0=t * 0.5)
+    torch.cuda.synchronize(); print('ok neural tc')
+# round 2: chain kernels with folded permutations, the affine / continuous-affine chain kernel, sigmoid hidden units,
+# the bin-index instrument
+rs = np.random.RandomState(2)
+spec = [{'type': 'flip'}]
+for i in range(3):
+    spec.append(cases.coupling_spec(rs, 'quadratic', 64, [64], 'ordered_right_half', n_bins=16, lower=-4., upper=4.,
+                                    activation='Sigmoid' if i == 1 else 'Tanh'))
+    spec.append({'type': 'permute', 'perm': rs.permutation(64).tolist()})
+run('spline chain with folded permutations', {'spec': spec, 'inputs': {'x': torch.zeros(1, 64)}}, rows_list=(1, 257, 600))
+spec = []
+for i in range(5):
+    spec.append(cases.cont_affine_spec(rs, 16, [64], ('ordered_0', 'ordered_1')[i % 2]))
+    spec.append({'type': 'flip'})
+if not ONLY or ONLY in 'affine chain kernel with folded permutations':
+    nf = st.NeuralFlow([l.to(dev) for l in layers_from_spec(spec)])
+    with torch.no_grad():
+        for r in (1, 129, 300, 1000):
+            x = torch.randn(r, 16, device=dev); t = torch.rand(r, 1, device=dev)
+            nf(x, t=t, t0=t * 0.5)
+    torch.cuda.synchronize(); print('ok affine chain kernel with folded permutations', flush=True)
+from stribor_b200 import _ops, _lib
+for kind, d in ((('quadratic', 64), ('cubic', 128)) if (not ONLY or ONLY in 'bins instrument') else ()):
+    case = cases._mk_flow(kind, d, [64], 1, 16, 8, 9)()
+    layer = layers_from_spec(case['spec'])[0].to(dev)
+    ds = layer.describe(d, 0, torch.device(dev))
+    for r in (1, 300):
+        x = torch.randn(r, d, device=dev)
+        for direction in (_lib.FORWARD, _lib.INVERSE):
+            _ops.layer_apply_bins(x, None, None, ds['mask'], [p.detach() for p in ds['params']], ds['packed'], ds['meta'],
+                                  ds['fmeta'], direction)
+torch.cuda.synchronize()
+if not ONLY or ONLY in 'bins instrument':
+    print('ok bins instrument', flush=True)
