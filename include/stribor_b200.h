@@ -243,7 +243,8 @@ int stb_layer_uses_tensor_path(const stb_layer* layer);
 /* Bring-up check of the tcgen05 building blocks: D[128,N] = A[128,K] * B[N,K]^T on one CTA.
  * mode bit0: 0 = fp16, 1 = tf32 operands; bit1: 3-pass hi/lo split.  variant bit0 must be 0
  * (descriptor bring-up switch); bit1: issue the small correction passes before hi*hi; bit2 / bit3:
- * A is given as [K,128] / B as [K,N] (transposed) and consumed as an MN-major operand in place. */
+ * A is given as [K,128] / B as [K,N] (transposed) and consumed as an MN-major operand in place; bit4 (fp16 modes): the
+ * A operand is written to TMEM with tcgen05.st and consumed by TMEM-sourced UMMAs (no shared-memory copy of A). */
 int stb_tc_selftest(const float* A, const float* B, float* D, int32_t K, int32_t N, int32_t mode,
                     int32_t variant, void* stream);
 

@@ -58,8 +58,12 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const 
     else pack_operand(b_hi, b_lo, B, N, K, tf32);
     fence_proxy_async_smem();
 
+    // variant bit 4: the A operand (fp16 hi | lo) lives in TMEM behind the accumulator -- lane = row, two K elements per
+    // 32-bit column -- written by its row's thread with tcgen05.st and consumed by TMEM-sourced UMMAs
+    const bool a_tmem = (variant & 16) != 0;
+    const uint32_t col_a = ((uint32_t)N + 31u) & ~31u;
     uint32_t ncols = 32;
-    while (ncols < (uint32_t)N) ncols <<= 1;
+    while (ncols < (a_tmem ? col_a + (uint32_t)K : (uint32_t)N)) ncols <<= 1;
     if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -69,6 +73,22 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const 
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = tmem_base_s;
+
+    if (a_tmem) {
+        const int row = warp * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+        for (int k0 = 0; k0 < K; k0 += 16) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_f16x2_sat(A[(size_t)row * K + k0 + 2 * j], A[(size_t)row * K + k0 + 2 * j + 1], hi[j], lo[j]);
+            tmem_st8(tbase + lane_sel + col_a + (uint32_t)(k0 / 2), hi);
+            tmem_st8(tbase + lane_sel + col_a + (uint32_t)(K / 2 + k0 / 2), lo);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     if (threadIdx.x == 0) {
         const uint32_t kstride = 128, gstride = (uint32_t)chunks * 128;
@@ -90,7 +110,8 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* A, const 
                                        : make_smem_desc(smem_u32(as) + ks * 2 * kstride, lbo, sbo);
                 const uint64_t bd = b_mn ? make_smem_desc(smem_u32(bs) + ks * kk * b_lbo, b_lbo, 128)
                                        : make_smem_desc(smem_u32(bs) + ks * 2 * kstride, lbo, sbo);
-                if (tf32) umma_tf32(tbase, ad, bd, idesc, acc);
+                if (a_tmem) umma_f16_ts(tbase, tbase + col_a + (uint32_t)((p == 1) ? K / 2 : 0) + (uint32_t)ks * 8, bd, idesc, acc);
+                else if (tf32) umma_tf32(tbase, ad, bd, idesc, acc);
                 else umma_f16(tbase, ad, bd, idesc, acc);
                 acc = 1;
             }
@@ -120,6 +141,7 @@ extern "C" int stb_tc_selftest(const float* A, const float* B, float* D, int32_t
     using namespace stb;
     const int tf32 = mode & 1;
     if (mode < 0 || mode > 3) return set_error(STB_EINVAL, "mode must be 0..3");
+    if ((variant & 16) && (tf32 || (variant & 4) || N + K > 480)) return set_error(STB_EINVAL, "TMEM-sourced A: fp16, K-major, N + K <= 480");
     if (K < (tf32 ? 8 : 16) || K % (tf32 ? 8 : 16) || N < 16 || N > 256 || N % 16)
         return set_error(STB_EINVAL, "K must be a multiple of the UMMA K, N a multiple of 16 <= 256");
     const size_t smem = (size_t)(128 + N) * K * (tf32 ? 4 : 2) * 2;

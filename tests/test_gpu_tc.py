@@ -505,3 +505,21 @@ def test_permutation_in_place_between_unchained_layers():
     want = O.flow_forward(case['spec'], x.cpu())
     torch.testing.assert_close(y.cpu(), want, rtol=1e-5, atol=2e-5)
     torch.testing.assert_close(xr, x, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('variant', [16, 18])
+@pytest.mark.parametrize('mode', [0, 2])
+@pytest.mark.parametrize('K,N', [(16, 16), (64, 16), (64, 64), (64, 96), (128, 64)])
+def test_umma_a_operand_from_tmem(mode, K, N, variant):
+    """The A operand written to TMEM with tcgen05.st (lane = row, two fp16 K elements per column) and consumed by
+    TMEM-sourced UMMAs: the building block that keeps a layer's activations on the tensor-core side."""
+    torch.manual_seed(K * 1000 + N + mode + variant)
+    A = torch.rand(128, K, device=DEV) * 2 - 1
+    B = torch.rand(N, K, device=DEV) * 2 - 1
+    D = torch.full((128, N), float('nan'), device=DEV)
+    rc = _lib.lib().stb_tc_selftest(A.data_ptr(), B.data_ptr(), D.data_ptr(), K, N, mode, variant,
+                                    torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+    ref = A.double() @ B.double().t()
+    err = (D.double() - ref).abs().max().item()
+    assert err < (2e-5 if mode >= 2 else 1e-2) * max(1.0, K / 32), err
