@@ -1119,6 +1119,279 @@ int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const flo
     return STB_OK;
 }
 
+namespace tcm {
+// -----------------------------------------------------------------------------------------------
+// CHAIN, four tiles in flight: tc_mlp_chain4_kernel
+// -----------------------------------------------------------------------------------------------
+// Same job as tc_mlp_chain_kernel for the shapes of BASELINE.json configs[3] (one hidden layer of 64 units, <= 16
+// conditioner inputs incl. t, <= 16 transformed dims, dim <= 32), restructured around what the phase clocks of that
+// kernel showed (profiles/r02_tcm_chain_phase_clocks.txt): a tile-layer is a chain of five dependent phases, so what
+// matters is how many INDEPENDENT tiles an SM holds, and shared memory (a 32 KB fp16 hi|lo A operand per tile)
+// capped that at two.  Here the hidden activations never touch shared memory: each thread (= row = TMEM lane)
+// writes its row of h straight into TMEM with tcgen05.st -- into the accumulator columns it has just consumed --
+// and GEMM2 reads its A operand from TMEM (tcgen05.mma, TMEM-sourced A).  A virtual CTA shrinks to ~21 KB and 128
+// TMEM columns, FOUR of them share the resident weights, and because a thread owns its whole row (gather, activation,
+// affine update) there is no cross-warp hazard between layers: no block barrier, no st.shared + proxy fence for h.
+//   TMEM columns of one virtual CTA:  GEMM1 main [0,64) | corr [64,128)
+//                                     h(kb): hi [16 kb, 16 kb + 8), lo [16 kb + 8, 16 kb + 16)   (over consumed main)
+//                                     GEMM2 (N = 16 twice): ls main [64,80) sh main [80,96) ls corr [96,112) sh corr [112,128)
+constexpr int kV4 = 4;
+constexpr int kV4EpiWarps = 4;                        // per virtual CTA: thread = row
+constexpr int kV4Threads = kV4 * (kV4EpiWarps + 1) * 32;        // 16 epilogue warps, then one issuer warp per virtual CTA
+constexpr uint32_t kV4A1Part = kRows * 16 * 2;        // one bf16 part of the [128 x 16] first-layer operand
+constexpr uint32_t kV4W1Bytes = 3 * 64 * 32;          // three bf16 parts of [64 x 16]
+constexpr uint32_t kV4W3Bytes = 4 * kNOut * 64;       // four K blocks of [64 x 16] fp16 hi | lo
+constexpr uint32_t kV4WBytes = kV4W1Bytes + kV4W3Bytes;
+
+template <int DUMMY>
+__global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const ChainArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t w_full;
+    __shared__ uint32_t tmem_base_s;
+    constexpr int H = 64;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_epi = warp < kV4 * kV4EpiWarps;
+    const int vc = is_epi ? warp >> 2 : warp - kV4 * kV4EpiWarps;
+    const int d = A.dim, L = A.n_layers, xs_stride = A.xs_stride;
+
+    uint8_t* vbase = smem + A.sm_vc + (uint32_t)vc * A.vc_bytes;
+    float* xs = reinterpret_cast<float*>(vbase);
+    const uint32_t xs_bytes = ((uint32_t)kRows * xs_stride * 4 + 127) & ~127u;
+    uint8_t* a1buf = vbase + xs_bytes;                                     // 3 x 4 KB
+    VcBars* bars = reinterpret_cast<VcBars*>(a1buf + 3 * kV4A1Part);
+
+    if (tid == 0) {
+        mbar_init(&w_full, 1);
+        for (int v = 0; v < kV4; ++v) {
+            VcBars* b = reinterpret_cast<VcBars*>(smem + A.sm_vc + (uint32_t)v * A.vc_bytes + xs_bytes + 3 * kV4A1Part);
+            mbar_init(&b->a_ready, kV4EpiWarps);
+            mbar_init(&b->acc_ready, 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s + (uint32_t)vc * kVcCols;
+    if (tid == 0) {                               // headers, biases and the weight blocks in use, once per CTA
+        mbar_arrive_expect_tx(&w_full, (uint32_t)L * (kSmallBytes + kV4WBytes));
+        for (int l = 0; l < L; ++l) {
+            bulk_g2s(smem + (uint32_t)l * kSmallSlot, A.packed[l], kSmallBytes, &w_full);
+            uint8_t* wdst = smem + A.sm_w + (uint32_t)l * kV4WBytes;
+            // first Linear: K block 0 of the parts pb = 2, 1, 0 (blocks 0, 2, 4 of the image; blocks 1, 3, 5 are zero)
+            for (int b = 0; b < 3; ++b) bulk_g2s(wdst + b * 2048, A.packed[l] + kOffW + (uint32_t)(2 * b) * 2048, 2048, &w_full);
+            bulk_g2s(wdst + kV4W1Bytes, A.packed[l] + kOffW + 6 * 2048, kV4W3Bytes, &w_full);
+        }
+    }
+    mbar_wait(&w_full, 0);
+    if (A.permuted) {
+        __syncthreads();
+        for (int i = tid; i < L * (kK1 + kMaxTr); i += kV4Threads) {
+            const int l = i / (kK1 + kMaxTr), k = i - l * (kK1 + kMaxTr);
+            Header* h = reinterpret_cast<Header*>(smem + (uint32_t)l * kSmallSlot);
+            if (k < kK1) h->cond_idx[k] = A.perm.phys[l][h->cond_idx[k]];
+            else h->tr_idx[k - kK1] = A.perm.phys[l][h->tr_idx[k - kK1]];
+        }
+        __syncthreads();
+    }
+
+    const int n_vcta = (int)gridDim.x * kV4, my_vcta = (int)blockIdx.x * kV4 + vc;
+    const int my_tiles = (A.n_tiles > my_vcta) ? (A.n_tiles - 1 - my_vcta) / n_vcta + 1 : 0;
+
+    if (!is_epi) {
+        // ---- UMMA issuer of this virtual CTA ---------------------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, H);
+            const uint32_t idesc3 = make_idesc(FMT_F16, 128, 16);
+            const uint32_t a0 = smem_u32(a1buf);
+            uint32_t ause = 0;
+            for (int it = 0; it < my_tiles; ++it)
+            for (int l = 0; l < L; ++l) {
+                const uint32_t w1 = smem_u32(smem + A.sm_w + (uint32_t)l * kV4WBytes), w3 = w1 + kV4W1Bytes;
+                mbar_wait(&bars->a_ready, ause & 1); ++ause;
+                tc_fence_after();
+                uint32_t acc_m = 0, acc_c = 0;
+                for (int b = 0; b < 3; ++b) {                      // bf16 parts pb = 2, 1, 0 of the first Linear
+                    const int pb = 2 - b;
+                    const uint64_t bd = make_smem_desc(w1 + (uint32_t)b * 2048, 128, 256);
+                    for (int pa = 2; pa >= 0; --pa) {
+                        if (pa == 2 && pb == 2) continue;
+                        const uint64_t ad = make_smem_desc(a0 + pa * kV4A1Part, 128, 256);
+                        if (pa == 0 && pb == 0) { umma_f16(tmem, ad, bd, idesc1, acc_m); acc_m = 1; }
+                        else { umma_f16(tmem + H, ad, bd, idesc1, acc_c); acc_c = 1; }
+                    }
+                }
+                umma_commit(&bars->acc_ready);
+                mbar_wait(&bars->a_ready, ause & 1); ++ause;
+                tc_fence_after();
+                // last Linear: A = h from TMEM; log-scale rows 0..15 and shift rows 32..47 of every K block, N = 16 each
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t dm = tmem + H + (uint32_t)half * 16, dc = dm + 32;
+                    acc_m = acc_c = 0;
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const uint32_t bb = w3 + (uint32_t)kb * (kNOut * 64) + (uint32_t)half * 1024;
+                        const uint64_t b_hi = make_smem_desc(bb, 128, 256), b_lo = make_smem_desc(bb + kNOut * 32, 128, 256);
+                        const uint32_t a_hi = tmem + (uint32_t)kb * 16, a_lo = a_hi + 8;
+                        umma_f16_ts(dc, a_lo, b_hi, idesc3, acc_c); acc_c = 1;
+                        umma_f16_ts(dc, a_hi, b_lo, idesc3, 1);
+                        umma_f16_ts(dm, a_hi, b_hi, idesc3, acc_m); acc_m = 1;
+                    }
+                }
+                umma_commit(&bars->acc_ready);
+            }
+        }
+    } else {
+        // ---- epilogue: thread = row of this virtual CTA's tile ---------------------------------------------------
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        float* xrow = xs + row * xs_stride;
+        float* xw = xs + q * 32 * xs_stride;                            // this warp's 32 rows (warp-private)
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
+        const bool inverse = A.inverse != 0;
+        const uint32_t a1_off = (uint32_t)(row >> 3) * 256 + (uint32_t)(row & 7) * 16;
+        uint32_t acc_use = 0;
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long row0 = ((long long)my_vcta + (long long)it * n_vcta) * kRows;
+            const int nrows = (int)min((long long)kRows, A.rows - row0);
+            const int wrows = max(0, min(32, nrows - q * 32));               // valid rows of this warp
+            {   // ---- stage this warp's rows (coalesced), once per flow ------------------------------------------
+                const float* xg = A.x + (row0 + q * 32) * d;
+                const int n = wrows * d;
+                for (int i = lane; i < 32 * d; i += 32) {
+                    const int r = i / d, c = i - r * d;
+                    xw[r * xs_stride + c] = (i < n) ? __ldg(xg + i) : 0.f;
+                }
+                if (it + 1 < my_tiles && lane == 0) {                    // next tile of this virtual CTA -> L2
+                    const long long nrow0 = ((long long)my_vcta + (long long)(it + 1) * n_vcta) * kRows + q * 32;
+                    const long long nb = min(32LL, A.rows - nrow0) * d * 4;
+                    const char* src = reinterpret_cast<const char*>(A.x + nrow0 * d);
+                    if (nb >= 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(nb & ~15LL)) : "memory");
+                }
+            }
+            const float tv = (A.t != nullptr && row < nrows) ? __ldg(A.t + row0 + row) : 0.f;
+            __syncwarp();
+            float ld_acc = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < L; ++l) {
+                const uint8_t* small = smem + (uint32_t)l * kSmallSlot;
+                const Header* hdr = reinterpret_cast<const Header*>(small);
+                const float* b1s = reinterpret_cast<const float*>(small + kOffB1);
+                const float* b3s = reinterpret_cast<const float*>(small + kOffB3);
+                const int n_tr = hdr->n_tr, n_cond = hdr->n_cond, act = hdr->act, time_col = hdr->time_col;
+                // ---- A1: the row's <= 16 conditioner inputs as three bf16 parts --------------------------------
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc) {
+                    __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = kc * 8 + u;
+                        const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : ((k == time_col) ? tv : 0.f);
+                        split_bf16x3(v, q0[u], q1[u], q2[u]);
+                    }
+                    *reinterpret_cast<uint4*>(a1buf + a1_off + kc * 128) = *reinterpret_cast<const uint4*>(q0);
+                    *reinterpret_cast<uint4*>(a1buf + kV4A1Part + a1_off + kc * 128) = *reinterpret_cast<const uint4*>(q1);
+                    *reinterpret_cast<uint4*>(a1buf + 2 * kV4A1Part + a1_off + kc * 128) = *reinterpret_cast<const uint4*>(q2);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_ready);
+                // ---- hidden layer: accumulators -> h, written back into the TMEM columns just consumed ----------
+                mbar_wait_sleep(&bars->acc_ready, acc_use & 1, 32); ++acc_use;
+                tc_fence_after();
+#pragma unroll 1
+                for (int kb = 0; kb < 4; ++kb) {
+                    float vm[16], vc_[16];
+                    tmem_ld16(tmem + lane_sel + (uint32_t)kb * 16, vm);
+                    tmem_ld16(tmem + lane_sel + H + (uint32_t)kb * 16, vc_);
+                    tmem_ld_wait();
+                    uint32_t hh[8], hl[8];
+                    const float2* b2p = reinterpret_cast<const float2*>(b1s + kb * 16);
+                    if (act == STB_ACT_TANH) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            tanh_split2(make_float2(vm[2 * i], vm[2 * i + 1]), make_float2(vc_[2 * i], vc_[2 * i + 1]),
+                                        make_float2(1.f, 1.f), b2p[i], hh[i], hl[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            sigmoid_split2(make_float2(vm[2 * i], vm[2 * i + 1]), make_float2(vc_[2 * i], vc_[2 * i + 1]),
+                                           make_float2(1.f, 1.f), b2p[i], hh[i], hl[i]);
+                    }
+                    tmem_st8(tmem + lane_sel + (uint32_t)kb * 16, hh);
+                    tmem_st8(tmem + lane_sel + (uint32_t)kb * 16 + 8, hl);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_ready);
+                // ---- output layer: affine transform of the row's transformed dims ------------------------------------
+                mbar_wait_sleep(&bars->acc_ready, acc_use & 1, 32); ++acc_use;
+                tc_fence_after();
+                const float s_out = hdr->s_out;
+                const bool cont = hdr->cont != 0;
+#pragma unroll 1
+                for (int og = 0; og * 8 < n_tr; ++og) {
+                    float lm[8], lc[8], sm_[8], sc_[8];
+                    tmem_ld8(tmem + lane_sel + H + og * 8, lm);
+                    tmem_ld8(tmem + lane_sel + H + 32 + og * 8, lc);
+                    tmem_ld8(tmem + lane_sel + H + 16 + og * 8, sm_);
+                    tmem_ld8(tmem + lane_sel + H + 48 + og * 8, sc_);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int ji = og * 8 + u;
+                        if (ji < n_tr) {
+                            const int j = hdr->tr_idx[ji];
+                            float ls = fmaf(lm[u] + lc[u], s_out, b3s[ji]);
+                            float sh = fmaf(sm_[u] + sc_[u], s_out, b3s[kMaxTr + ji]);
+                            if (cont) {                        // coupling.py:199-205
+                                ls *= hdr->ts_ls[ji] * tv;
+                                sh *= hdr->ts_sh[ji] * tv;
+                            }
+                            const float xv = xrow[j];
+                            if (inverse) { xrow[j] = (xv - sh) * expf(-ls); ld_acc -= ls; }
+                            else { xrow[j] = xv * expf(ls) + sh; ld_acc += ls; }
+                        }
+                    }
+                }
+                tc_fence_before();
+            }   // layers
+
+            if (want_ld && row < nrows) {
+                float tot = ld_acc;
+                if (A.base_log_prob) {
+                    float b = 0.f;
+                    for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
+                    tot += b;
+                }
+                float* dst = A.ldj + row0 + row;
+                *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
+            }
+            __syncwarp();
+            if (A.y != nullptr) {                                        // this warp's rows out (coalesced)
+                float* yg = A.y + (row0 + q * 32) * d;
+                const int n = wrows * d;
+                for (int i = lane; i < n; i += 32) {
+                    const int r = i / d, c = i - r * d;
+                    yg[i] = xw[r * xs_stride + (A.permuted ? (int)A.perm.out_phys[c] : c)];
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
+}  // namespace tcm
+
 #ifdef STB_TCM_PROF
 extern "C" int stb_tcm_prof_read(unsigned int* host, int n) {
     return (int)cudaMemcpyFromSymbol(host, tcm::g_tcm_prof, (size_t)n * 4);
@@ -1156,7 +1429,37 @@ static bool chain_layout(const stb_layer* const* layers, int n, ChainArgs* A, ui
 }
 }  // namespace tcm
 
-bool tcm_chain_supported(const stb_layer* const* layers, int n) { return tcm::chain_layout(layers, n, nullptr, nullptr); }
+namespace tcm {
+// four-tiles-in-flight variant: one hidden layer, <= 16 conditioner inputs (incl. t) and <= 16 transformed dims per layer
+static bool chain4_layout(const stb_layer* const* layers, int n, ChainArgs* A, uint32_t* smem_bytes) {
+    static const bool off = [] { const char* e = getenv("STRIBOR_B200_NO_CHAIN4"); return e && e[0] == '1'; }();
+    if (off || n < 2 || n > kMaxChainM) return false;
+    const int d = layers[0]->dim;
+    for (int i = 0; i < n; ++i) {
+        const stb_layer* L = layers[i];
+        if (!L->packed || !tcm_layer_supported(L) || L->dim != d || d > 32 || L->net.dims[1] != 64) return false;
+        if (L->net.n_linear != 2 || L->packed_bytes < packed_bytes(64, 1)) return false;
+        PackArgs pa;
+        if (!fill_pack_args(L, pa)) return false;
+        if (pa.n_cond + (pa.time_col >= 0 ? 1 : 0) > 16 || pa.n_tr > 16) return false;
+        if (A) A->packed[i] = static_cast<const uint8_t*>(L->packed);
+    }
+    const int xs_stride = d | 1;
+    const uint32_t xs_bytes = ((uint32_t)kRows * xs_stride * 4 + 127) & ~127u;
+    const uint32_t vc_bytes = (xs_bytes + 3 * kV4A1Part + 128 + 127) & ~127u;
+    const uint32_t sm_w = ((uint32_t)n * kSmallSlot + 127) & ~127u;
+    const uint32_t sm_vc = (sm_w + (uint32_t)n * kV4WBytes + 127) & ~127u;
+    const uint32_t total = sm_vc + kV4 * vc_bytes;
+    if (total > 227 * 1024 - 1024) return false;
+    if (A) { A->n_layers = n; A->dim = d; A->xs_stride = xs_stride; A->sm_w = sm_w; A->sm_vc = sm_vc; A->vc_bytes = vc_bytes; }
+    if (smem_bytes) *smem_bytes = total;
+    return true;
+}
+}  // namespace tcm
+
+bool tcm_chain_supported(const stb_layer* const* layers, int n) {
+    return tcm::chain4_layout(layers, n, nullptr, nullptr) || tcm::chain_layout(layers, n, nullptr, nullptr);
+}
 
 // layers[] in APPLICATION order (the caller reverses them for the inverse direction)
 int tcm_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, const float* t, float* y,
@@ -1165,7 +1468,8 @@ int tcm_chain_apply(const stb_layer* const* layers, int n, int direction, const 
     using namespace tcm;
     ChainArgs A = {};
     uint32_t smem = 0;
-    if (!chain_layout(layers, n, &A, &smem)) return set_error(STB_EINVAL, "layers cannot be chained");
+    const bool four = chain4_layout(layers, n, &A, &smem);
+    if (!four && !chain_layout(layers, n, &A, &smem)) return set_error(STB_EINVAL, "layers cannot be chained");
     if (perm) { A.permuted = 1; A.perm = *perm; }
     for (int i = 0; i < n; ++i)
         if (layers[i]->kind == STB_CONT_AFFINE && !t) return set_error(STB_EINVAL, "layer expects a time input");
@@ -1184,11 +1488,12 @@ int tcm_chain_apply(const stb_layer* const* layers, int n, int direction, const 
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (n_sm <= 0) n_sm = 148;
     }
-    void (*kern)(ChainArgs) = tc_mlp_chain_kernel<kChainV>;
+    void (*kern)(ChainArgs) = four ? tc_mlp_chain4_kernel<0> : tc_mlp_chain_kernel<kChainV>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    const int grid = (int)min((long long)n_sm, (tiles + kChainV - 1) / kChainV);
-    kern<<<grid, kChainV * kVcThreads, smem, stream>>>(A);
+    const int vper = four ? kV4 : kChainV;
+    const int grid = (int)min((long long)n_sm, (tiles + vper - 1) / vper);
+    kern<<<grid, four ? kV4Threads : kChainV * kVcThreads, smem, stream>>>(A);
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_mlp_chain_kernel launch: %s", cudaGetErrorString(e));
