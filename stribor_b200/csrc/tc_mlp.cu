@@ -126,6 +126,14 @@ __device__ __forceinline__ float fdiv(float a, float b) {
     const float q = a * r;
     return fmaf(fmaf(-q, b, a), r, q);
 }
+// exp(v) for the affine scale: 2^p on MUFU.EX2 with p = v log2(e), and the rounding error of that product put back
+// as a first-order correction (e ln 2) -- ~3e-7 relative like expf, 5 instructions instead of ~18
+__device__ __forceinline__ float exp_fast(float v) {
+    const float p = v * 1.4426950408889634f;
+    const float e = fmaf(v, 1.4426950408889634f, -p) + v * 1.925963033500011e-08f;     // low part of log2(e) included
+    const float r = ex2_approx(p);
+    return fmaf(r, e * 0.6931471805599453f, r);
+}
 __device__ __forceinline__ float tanh_fast(float v) {                 // ~3e-7 absolute error
     const float t = ex2_approx(-2.885390081777927f * fabsf(v));
     return copysignf(fdiv(1.f - t, 1.f + t), v);
@@ -463,8 +471,8 @@ __global__ void __launch_bounds__(Cfg<NCG>::kThreads, (NCG == 4) ? 1 : 2) tc_mlp
                             sh *= hdr->ts_sh[ji] * tv;
                         }
                         const float xv = xrow[j];
-                        if (inverse) { xrow[j] = (xv - sh) * expf(-ls); ld_acc -= ls; }
-                        else { xrow[j] = xv * expf(ls) + sh; ld_acc += ls; }
+                        if (inverse) { xrow[j] = (xv - sh) * exp_fast(-ls); ld_acc -= ls; }
+                        else { xrow[j] = xv * exp_fast(ls) + sh; ld_acc += ls; }
                     }
                 }
             }
@@ -843,8 +851,8 @@ __global__ void __launch_bounds__(V * kVcThreads, 1) tc_mlp_chain_kernel(const C
                                 sh *= hdr->ts_sh[ji] * tv;
                             }
                             const float xv = xrow[j];
-                            if (inverse) { xrow[j] = (xv - sh) * expf(-ls); ld_acc -= ls; }
-                            else { xrow[j] = xv * expf(ls) + sh; ld_acc += ls; }
+                            if (inverse) { xrow[j] = (xv - sh) * exp_fast(-ls); ld_acc -= ls; }
+                            else { xrow[j] = xv * exp_fast(ls) + sh; ld_acc += ls; }
                         }
                     }
                 }
@@ -1197,6 +1205,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
         __syncthreads();
     }
 
+    const int dshift = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;
     const int n_vcta = (int)gridDim.x * kV4, my_vcta = (int)blockIdx.x * kV4 + vc;
     const int my_tiles = (A.n_tiles > my_vcta) ? (A.n_tiles - 1 - my_vcta) / n_vcta + 1 : 0;
 
@@ -1210,7 +1219,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
             for (int it = 0; it < my_tiles; ++it)
             for (int l = 0; l < L; ++l) {
                 const uint32_t w1 = smem_u32(smem + A.sm_w + (uint32_t)l * kV4WBytes), w3 = w1 + kV4W1Bytes;
-                mbar_wait(&bars->a_ready, ause & 1); ++ause;
+                mbar_wait_sleep(&bars->a_ready, ause & 1, 96); ++ause;
                 tc_fence_after();
                 uint32_t acc_m = 0, acc_c = 0;
                 for (int b = 0; b < 3; ++b) {                      // bf16 parts pb = 2, 1, 0 of the first Linear
@@ -1224,7 +1233,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
                     }
                 }
                 umma_commit(&bars->acc_ready);
-                mbar_wait(&bars->a_ready, ause & 1); ++ause;
+                mbar_wait_sleep(&bars->a_ready, ause & 1, 96); ++ause;
                 tc_fence_after();
                 // last Linear: A = h from TMEM; log-scale rows 0..15 and shift rows 32..47 of every K block, N = 16 each
                 for (int half = 0; half < 2; ++half) {
@@ -1261,9 +1270,18 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
             {   // ---- stage this warp's rows (coalesced), once per flow ------------------------------------------
                 const float* xg = A.x + (row0 + q * 32) * d;
                 const int n = wrows * d;
-                for (int i = lane; i < 32 * d; i += 32) {
-                    const int r = i / d, c = i - r * d;
-                    xw[r * xs_stride + c] = (i < n) ? __ldg(xg + i) : 0.f;
+                if (dshift >= 2 && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0)) {      // d a power of two >= 4: 16-byte loads
+                    for (int i4 = lane; i4 < 8 * d; i4 += 32) {
+                        const float4 v = (i4 * 4 < n) ? __ldg(reinterpret_cast<const float4*>(xg) + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int r = (i4 * 4) >> dshift, c = (i4 * 4) & (d - 1);
+                        float* dst = xw + r * xs_stride + c;
+                        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+                    }
+                } else {
+                    for (int i = lane; i < 32 * d; i += 32) {
+                        const int r = i / d, c = i - r * d;
+                        xw[r * xs_stride + c] = (i < n) ? __ldg(xg + i) : 0.f;
+                    }
                 }
                 if (it + 1 < my_tiles && lane == 0) {                    // next tile of this virtual CTA -> L2
                     const long long nrow0 = ((long long)my_vcta + (long long)(it + 1) * n_vcta) * kRows + q * 32;
@@ -1302,7 +1320,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->a_ready);
                 // ---- hidden layer: accumulators -> h, written back into the TMEM columns just consumed ----------
-                mbar_wait_sleep(&bars->acc_ready, acc_use & 1, 32); ++acc_use;
+                mbar_wait_sleep(&bars->acc_ready, acc_use & 1, 64); ++acc_use;
                 tc_fence_after();
 #pragma unroll 1
                 for (int kb = 0; kb < 4; ++kb) {
@@ -1331,7 +1349,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->a_ready);
                 // ---- output layer: affine transform of the row's transformed dims ------------------------------------
-                mbar_wait_sleep(&bars->acc_ready, acc_use & 1, 32); ++acc_use;
+                mbar_wait_sleep(&bars->acc_ready, acc_use & 1, 64); ++acc_use;
                 tc_fence_after();
                 const float s_out = hdr->s_out;
                 const bool cont = hdr->cont != 0;
@@ -1355,8 +1373,8 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
                                 sh *= hdr->ts_sh[ji] * tv;
                             }
                             const float xv = xrow[j];
-                            if (inverse) { xrow[j] = (xv - sh) * expf(-ls); ld_acc -= ls; }
-                            else { xrow[j] = xv * expf(ls) + sh; ld_acc += ls; }
+                            if (inverse) { xrow[j] = (xv - sh) * exp_fast(-ls); ld_acc -= ls; }
+                            else { xrow[j] = xv * exp_fast(ls) + sh; ld_acc += ls; }
                         }
                     }
                 }
@@ -1377,9 +1395,17 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
             if (A.y != nullptr) {                                        // this warp's rows out (coalesced)
                 float* yg = A.y + (row0 + q * 32) * d;
                 const int n = wrows * d;
-                for (int i = lane; i < n; i += 32) {
-                    const int r = i / d, c = i - r * d;
-                    yg[i] = xw[r * xs_stride + (A.permuted ? (int)A.perm.out_phys[c] : c)];
+                if (dshift >= 2 && !A.permuted && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
+                    for (int i4 = lane; i4 * 4 < n; i4 += 32) {
+                        const int r = (i4 * 4) >> dshift, c = (i4 * 4) & (d - 1);
+                        const float* src = xw + r * xs_stride + c;
+                        reinterpret_cast<float4*>(yg)[i4] = make_float4(src[0], src[1], src[2], src[3]);
+                    }
+                } else {
+                    for (int i = lane; i < n; i += 32) {
+                        const int r = i / d, c = i - r * d;
+                        yg[i] = xw[r * xs_stride + (A.permuted ? (int)A.perm.out_phys[c] : c)];
+                    }
                 }
             }
             __syncwarp();
