@@ -332,13 +332,17 @@ def _cont_flow(d, n_layers, seed, hidden=(64,), latent=False):
     return spec
 
 
-@pytest.mark.parametrize('n_layers,d,rows', [(4, 16, 70000), (4, 16, 129), (7, 12, 5000), (2, 32, 1000), (3, 6, 300)])
-def test_affine_chain_kernel_matches_layer_by_layer(n_layers, d, rows):
+@pytest.mark.parametrize('n_layers,d,rows,hidden', [(4, 16, 70000, (64,)), (4, 16, 129, (64,)), (7, 12, 5000, (64,)),
+                                                    (2, 32, 1000, (64,)), (3, 6, 300, (64,)), (3, 16, 5000, (64, 64)),
+                                                    (9, 8, 40000, (64,))])
+def test_affine_chain_kernel_matches_layer_by_layer(n_layers, d, rows, hidden):
     """NeuralFlow.forward (flow.py:172-184) over ContinuousAffineCoupling + TimeLinear layers with small
     conditioners is ONE launch (tc_mlp.cu, CHAIN kernel: weights of all layers resident in shared memory, the tile
     stays on chip between layers).  Same arithmetic as one launch per layer: bit-identical outputs; and both
     against the oracle."""
-    spec = _cont_flow(d, n_layers, 4000 + d)
+    # (64,) with <= 16 inputs: tc_mlp_chain4_kernel (h in TMEM, four tiles in flight); 32 dims (17 inputs) or two hidden
+    # layers: tc_mlp_chain_kernel<2> (h through shared memory)
+    spec = _cont_flow(d, n_layers, 4000 + d, hidden=hidden)
     layers = [l.to(DEV) for l in layers_from_spec(spec)]
     torch.manual_seed(rows)
     x = torch.randn(rows, d, device=DEV)
@@ -359,7 +363,7 @@ def test_affine_chain_kernel_matches_layer_by_layer(n_layers, d, rows):
             cur0 = l.inverse(cur0, t=t0)
         for l in layers:
             cur0 = l(cur0, t=t)
-    per_launch = 4 if d <= 16 else 3                        # layers whose weights fit next to the tiles
+    per_launch = 2 if len(hidden) > 1 else (4 if d <= 16 else 3)    # layers whose weights fit next to the tiles (at least)
     assert n_fwd <= (n_layers + per_launch - 1) // per_launch + 1, f'{n_fwd} launches for {n_layers} layers'
     assert torch.equal(y, cur), (y - cur).abs().max().item()
     assert torch.equal(y0, cur0), (y0 - cur0).abs().max().item()
