@@ -42,6 +42,8 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
         return tc_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tcw_layer_supported(L) && tcw_image_present(L))
         return tcw_layer_apply(L, tcw_image(L), direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);
+    if (L->packed && !ldiag && tch_layer_supported(L))
+        return tch_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tcm_layer_supported(L))
         return tcm_layer_apply(L, direction, x, t, y, ldj, ldj_mode, base_lp, rows, s);
     return generic_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, ldiag, rows, s, bins);
@@ -270,6 +272,7 @@ uint64_t stb_packed_bytes(const stb_layer* layer) {
     if (validate_layer(layer)) return 0;
     if (tc_layer_supported(layer)) return tc_packed_bytes(layer) + tcw_packed_bytes(layer);   // both images
     if (tcw_layer_supported(layer)) return tcw_packed_bytes(layer);
+    if (tch_layer_supported(layer)) return tch_packed_bytes(layer);
     return tcm_layer_supported(layer) ? tcm_packed_bytes(layer) : 0;
 }
 
@@ -284,13 +287,15 @@ int stb_pack_layer(const stb_layer* layer, void* packed_out, void* stream) {
         return tcw_pack_layer(layer, static_cast<uint8_t*>(packed_out) + tc_packed_bytes(layer), (cudaStream_t)stream);
     }
     if (tcw_layer_supported(layer)) return tcw_pack_layer(layer, packed_out, (cudaStream_t)stream);
+    if (tch_layer_supported(layer)) return tch_pack_layer(layer, packed_out, (cudaStream_t)stream);
     if (tcm_layer_supported(layer)) return tcm_pack_layer(layer, packed_out, (cudaStream_t)stream);
     return set_error(STB_ENOTSUP, "layer has no tensor-core path");
 }
 
 int stb_layer_uses_tensor_path(const stb_layer* layer) {
     if (validate_layer(layer)) return 0;
-    return (layer->packed && (tc_layer_supported(layer) || tcw_layer_supported(layer) || tcm_layer_supported(layer))) ? 1 : 0;
+    return (layer->packed && (tc_layer_supported(layer) || tcw_layer_supported(layer) || tch_layer_supported(layer) ||
+                              tcm_layer_supported(layer))) ? 1 : 0;
 }
 
 }  // extern "C"

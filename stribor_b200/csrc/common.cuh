@@ -63,6 +63,13 @@ inline bool tcw_image_present(const stb_layer* L) {
     return L->packed && L->packed_bytes >= (tc_layer_supported(L) ? tc_packed_bytes(L) : 0) + tcw_packed_bytes(L);
 }
 
+// tcgen05 path for spline couplings with a wide conditioner, MLP[H] / MLP[H,H], H <= 256 (tc_hwide.cu)
+bool tch_layer_supported(const stb_layer* L);
+uint64_t tch_packed_bytes(const stb_layer* L);
+int tch_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
+int tch_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
+                    int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins = nullptr);
+
 // tcgen05 path for affine couplings with a wide conditioner (tc_mlp.cu)
 bool tcm_layer_supported(const stb_layer* L);
 uint64_t tcm_packed_bytes(const stb_layer* L);

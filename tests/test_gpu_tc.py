@@ -527,3 +527,57 @@ def test_umma_a_operand_from_tmem(mode, K, N, variant):
     ref = A.double() @ B.double().t()
     err = (D.double() - ref).abs().max().item()
     assert err < (2e-5 if mode >= 2 else 1e-2) * max(1.0, K / 32), err
+
+
+@pytest.mark.parametrize('kind', ['quadratic', 'cubic'])
+@pytest.mark.parametrize('d,hidden,rows', [(64, [256, 256], 700), (64, [256], 300), (64, [128, 128], 257), (64, [128], 129),
+                                           (30, [192], 300), (64, [64, 64], 300), (17, [256, 256], 1)])
+def test_wide_conditioner_spline_kernel(kind, d, hidden, rows, monkeypatch):
+    """tc_hwide.cu: spline couplings with MLP[H] / MLP[H,H] conditioners (SURVEY 8d's secondary configs[2] shape) on the
+    tensor cores -- hidden activations written back into the consumed accumulator columns (tcgen05.st) and read as the
+    next GEMM's A operand from TMEM.  Against the CUDA-core kernel and the fp64 oracle; bins against the oracle."""
+    masks = cases.ALT if d % 2 == 0 else ('ordered_left_half', 'parity_odd')
+    case = cases._mk_flow(kind, d, hidden, 2, 16, max(rows, 2), 7000 + d + len(hidden), masks=masks, lower=-4., upper=4., scale=1.6)()
+    spec = case['spec']
+    x = case['inputs']['x'][:rows].to(DEV)
+
+    def build():
+        layers = [l.to(DEV) for l in layers_from_spec(spec)]
+        return st.NormalizingFlow(st.UnitNormal(d), layers), layers
+
+    tflow, tl = build()
+    with torch.no_grad():
+        desc = tl[0].describe(d, 0, torch.device(DEV))
+        assert desc['packed'] is not None, 'tensor path was not selected'
+        L = _ops.make_struct(desc['meta'], desc['fmeta'], desc['mask'], desc['params'], desc['packed'])
+        assert _lib.lib().stb_layer_uses_tensor_path(ctypes.byref(L)) == 1
+        lp_t = tflow.log_prob(x)
+        xi_t, li_t = tflow.inverse_and_log_det_jacobian(x)
+        yf_t, lf_t = tflow.forward_and_log_det_jacobian(x)
+        rt = (tflow.forward(xi_t) - x).abs().max().item()
+        _, _, bins = _ops.layer_apply_bins(x, None, None, desc['mask'], [p.detach() for p in desc['params']], desc['packed'],
+                                           desc['meta'], desc['fmeta'], _lib.FORWARD)
+    monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', '1')
+    gflow, _ = build()
+    with torch.no_grad():
+        lp_g = gflow.log_prob(x)
+        xi_g, li_g = gflow.inverse_and_log_det_jacobian(x)
+    xc = x.cpu()
+    s64 = O.spec_to(spec, torch.float64)
+    lp32, lp64 = O.flow_log_prob(spec, xc), O.flow_log_prob(s64, xc.double())
+    fail, _, mx = close_or_arbitrated(lp_t, lp32, lp64, 1e-5, 1e-5)
+    assert fail <= (6e-3 if kind == 'cubic' else 0.0), f'log_prob: {fail:.3%} outside tolerance (max abs err {mx:.3e})'
+    f64 = O.flow_forward(s64, xc.double(), with_ldj=True)
+    f32 = O.flow_forward(spec, xc, with_ldj=True)
+    for got, a32, a64, atol in ((yf_t, f32[0], f64[0], 1e-5), (lf_t, f32[1], f64[1], 1e-4)):
+        fail, _, mx = close_or_arbitrated(got, a32, a64, 1e-5, atol)
+        assert fail <= 2e-2, f'forward: {fail:.3%} outside tolerance (max abs err {mx:.3e})'
+    if kind == 'quadratic':
+        assert rt < 1e-4, rt
+        assert (xi_t - xi_g).abs().max().item() < 1e-4 and (li_t - li_g).abs().max().item() < 5e-4
+        assert (lp_t - lp_g).abs().max().item() < 1e-3
+    else:
+        assert ((xi_t - xi_g).abs() > 1e-4).float().mean().item() < 5e-3
+    want_bins = O.layer_bins(spec[0], xc, inverse=False).to(torch.int32)
+    flips = int((bins.cpu() != want_bins).sum())
+    assert flips <= max(1, int(1e-4 * want_bins.numel())), flips
