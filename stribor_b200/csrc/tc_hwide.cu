@@ -104,6 +104,7 @@ struct Args {
     float lower, upper;
     long long rows;
     int n_tiles;
+    int cluster;             // CTAs per cluster (1, 2 or 4) sharing every weight item through TMA multicast
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
 
     if (tid == 0) {
         mbar_init(&bars->setup, 1);
-        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+        // a stage is shared by the cluster: every CTA's issuer releases it in every CTA (multicast commit)
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], (uint32_t)A.cluster); }
         mbar_init(&bars->a1_ready, kEpiWarps);
         mbar_init(&bars->acc1_full, 1);
         mbar_init(&bars->h1_ready, kEpiWarps);
@@ -176,6 +178,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    const int CL = A.cluster;
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+    if (CL > 1) cluster_sync_all();               // every CTA's mbarriers exist before a peer multicasts into them
     const uint32_t tmem = tmem_base_s;
     if (tid == 0) {
         mbar_arrive_expect_tx(&bars->setup, kSmallBytes);
@@ -190,7 +196,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
     const int n_items2 = (n_hidden == 2) ? (kb_h + 2) / 3 : 0;              // W2' items of up to 3 K blocks
     const uint32_t col_h_last = (n_hidden == 2) ? 256u : 0u;                // A operand of the chunk GEMMs
     const uint32_t col_chunk = (n_hidden == 2) ? 0u : (uint32_t)H;          // five 48-column accumulators
-    const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // every CTA of a cluster runs the same number of tiles (the weight stream is shared): the trip count is that of the
+    // cluster's FIRST CTA; a CTA whose last tile does not exist runs it as a ghost (no rows loaded, nothing stored)
+    const int first_cta = (int)blockIdx.x - (int)crank;
+    const int my_tiles = (A.n_tiles > first_cta) ? (A.n_tiles - 1 - first_cta) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
         // ======================= producer: one ring item = W1 | 3 K blocks of W2' | one dim of W3 ===================
@@ -200,13 +209,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                 const uint32_t st = rc % kStages, use = rc / kStages;
                 mbar_wait_relaxed(&bars->b_empty[st], (use & 1) ^ 1);
                 mbar_arrive_expect_tx(&bars->b_full[st], bytes);
-                bulk_g2s(ring + st * stage, src, bytes, &bars->b_full[st]);
+                if (CL == 1) {
+                    bulk_g2s(ring + st * stage, src, bytes, &bars->b_full[st]);
+                } else {                                   // this CTA fetches its 1 / CL of the item for the whole cluster
+                    const uint32_t part = bytes / (uint32_t)CL;
+                    bulk_g2s_multicast(ring + st * stage + crank * part, src + crank * part, part, &bars->b_full[st], cmask);
+                }
                 ++rc;
             };
             for (int it = 0; it < my_tiles; ++it) {
                 if (it + 1 < my_tiles) {
                     const long long nrow0 = ((long long)blockIdx.x + (long long)(it + 1) * gridDim.x) * kRows;
-                    const long long nb = min((long long)kRows, A.rows - nrow0) * d * 4;
+                    const long long nb = max(0LL, min((long long)kRows, A.rows - nrow0)) * d * 4;
                     const char* src = reinterpret_cast<const char*>(A.x + nrow0 * d);
                     if (nb >= 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(nb & ~15LL)) : "memory");
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                         }
                     }
                     umma_commit(&bars->acc1_full);
-                    umma_commit(&bars->b_empty[st]);
+                    if (CL > 1) umma_commit_multicast(&bars->b_empty[st], cmask); else umma_commit(&bars->b_empty[st]);
                     ++rc;
                 }
                 if (n_hidden == 2) {   // ---- GEMM2': A = h1 from TMEM, per K block lo*hi, hi*lo, hi*hi ---------------------
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                             umma_f16_ts(tmem + 256, a_hi, b_lo, idesc2, 1);
                             umma_f16_ts(tmem + 256, a_hi, b_hi, idesc2, 1);
                         }
-                        umma_commit(&bars->b_empty[st]);
+                        if (CL > 1) umma_commit_multicast(&bars->b_empty[st], cmask); else umma_commit(&bars->b_empty[st]);
                     }
                     umma_commit(&bars->acc2_full);
                 }
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                         }
                     }
                     umma_commit(&bars->acc_full[buf]);
-                    umma_commit(&bars->b_empty[st]);
+                    if (CL > 1) umma_commit_multicast(&bars->b_empty[st], cmask); else umma_commit(&bars->b_empty[st]);
                 }
             }
         }
@@ -318,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
 
         for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * kRows;
-            const int nrows = (int)min((long long)kRows, A.rows - row0);
+            const int nrows = (int)max(0LL, min((long long)kRows, A.rows - row0));      // 0: ghost tile
             {   // ---- stage the x tile ------------------------------------------------------------------------------------
                 const float* xg = A.x + row0 * d;
                 const int n = nrows * d;
@@ -479,6 +493,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();               // no CTA leaves while a peer may still multicast into it
     if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
@@ -697,9 +712,44 @@ int tch_layer_apply(const stb_layer* L, int direction, const float* x, float* y,
     const uint32_t smem = smem_bytes(H);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    const int grid = (int)min((long long)n_sm, tiles);
-    kern<<<grid, kThreads, smem, stream>>>(A);
+    // The weight stream (1.85 MB per 128-row tile at MLP[256,256]) is what binds this kernel: clusters of CTAs share it
+    // through TMA multicast.  STRIBOR_B200_HW_CLUSTER = 1 | 2 | 4 overrides the default.
+    static const int want_cluster = [] {
+        const char* ev = getenv("STRIBOR_B200_HW_CLUSTER");
+        const int v = ev ? atoi(ev) : 4;
+        return (v == 1 || v == 2 || v == 4) ? v : 4;
+    }();
+    int cl = want_cluster;
+    while (cl > 1 && (tiles < cl || (n_sm % cl) != 0)) cl >>= 1;
+    A.cluster = cl;
+    int grid = (int)min((long long)n_sm, tiles);
+    grid -= grid % cl;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cl > 1) {
+        // persistent kernel: every cluster must be resident at once (GPC sizes are not all multiples of the cluster size)
+        int max_clusters = 0;
+        e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+        if (e == cudaSuccess && max_clusters > 0 && max_clusters * cl < grid) {
+            grid = max_clusters * cl;
+            cfg.gridDim = dim3((unsigned)grid);
+        } else if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+        }
+    }
+    e = cudaLaunchKernelEx(&cfg, kern, A);
     count_launch();
+    if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_hw_spline_kernel launch: %s", cudaGetErrorString(e));
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(STB_ECUDA, "tc_hw_spline_kernel launch: %s", cudaGetErrorString(e));
     return STB_OK;
