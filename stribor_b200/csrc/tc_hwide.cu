@@ -45,7 +45,10 @@ constexpr int kStages = 3;
 constexpr int kNBuf = 5;                 // 48-column chunk accumulators
 constexpr int kEpiWarp0 = 2;
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kIssuers = 3;                              // UMMA issuer threads of the chunk phase (dims ji % 3): 20 warps in all,
+                                                         // the most that keeps 96 registers per thread
+constexpr int kIssuerB = kEpiWarp0 + kEpiWarps;          // issuers 1..2: warps 18..19 (issuer 0 = warp 1)
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps + kIssuers - 1) * 32;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr uint32_t kMagic = 0x53544834u;
 
@@ -201,6 +204,36 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
     const int first_cta = (int)blockIdx.x - (int)crank;
     const int my_tiles = (A.n_tiles > first_cta) ? (A.n_tiles - 1 - first_cta) / (int)gridDim.x + 1 : 0;
 
+    // ---- one transformed dim: [128 x H] x [H x 48] from ring item `rc` into accumulator buffer `cc % 5`, A = the last
+    // hidden layer in TMEM, three passes with the corrections first (lo*hi, hi*lo, hi*hi)
+    auto issue_chunk = [&](uint32_t rc, uint32_t cc) {
+        const uint32_t idesc3 = make_idesc(FMT_F16, 128, kPPad);
+        const uint32_t st = rc % kStages, use = rc / kStages;
+        mbar_wait_relaxed(&bars->b_full[st], use & 1);
+        const uint32_t buf = cc % kNBuf, buse = cc / kNBuf;
+        mbar_wait_relaxed(&bars->acc_empty[buf], (buse & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dcol = tmem + col_chunk + buf * kPPad;
+        const uint64_t bd0 = make_smem_desc(smem_u32(ring + st * stage), 128, 256);
+        const uint32_t ad0 = tmem + col_h_last;
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int p = 0; p < 3; ++p) {
+            // descriptors advance by constants: 3072 B (>> 4 in the descriptor's address field) and 16 TMEM columns
+            uint64_t bd = bd0 + ((p == 1) ? (uint64_t)((kPPad * 32) >> 4) : 0ull);
+            uint32_t ad = ad0 + ((p == 0) ? 8u : 0u);
+#pragma unroll 4
+            for (int kb = 0; kb < kb_h; ++kb) {
+                umma_f16_ts(dcol, ad, bd, idesc3, acc);
+                acc = 1;
+                bd += (uint64_t)(w3_block() >> 4);
+                ad += 16u;
+            }
+        }
+        umma_commit(&bars->acc_full[buf]);
+        if (CL > 1) umma_commit_multicast(&bars->b_empty[st], cmask); else umma_commit(&bars->b_empty[st]);
+    };
+
     if (warp == 0) {
         // ======================= producer: one ring item = W1 | 3 K blocks of W2' | one dim of W3 ===================
         if (lane == 0) {
@@ -238,7 +271,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
         if (lane == 0) {
             const uint32_t idesc1 = make_idesc(FMT_BF16, 128, H);
             const uint32_t idesc2 = make_idesc(FMT_F16, 128, H);
-            const uint32_t idesc3 = make_idesc(FMT_F16, 128, kPPad);
             const uint32_t a0 = smem_u32(a1buf);
             uint32_t rc = 0, cc = 0, tp = 0;
             for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
@@ -288,29 +320,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                     umma_commit(&bars->acc2_full);
                 }
                 mbar_wait_relaxed(n_hidden == 2 ? &bars->h2_ready : &bars->h1_ready, tp);
-                for (int ji = 0; ji < n_tr; ++ji, ++rc, ++cc) {
-                    // ---- one transformed dim: [128 x H] x [H x 48], corrections first -------------------------------
-                    const uint32_t st = rc % kStages, use = rc / kStages;
-                    mbar_wait_relaxed(&bars->b_full[st], use & 1);
-                    const uint32_t buf = cc % kNBuf, buse = cc / kNBuf;
-                    mbar_wait_relaxed(&bars->acc_empty[buf], (buse & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t bb = smem_u32(ring + st * stage);
-                    const uint32_t dcol = tmem + col_chunk + buf * kPPad;
-                    uint32_t acc = 0;
-#pragma unroll 1
-                    for (int p = 0; p < 3; ++p) {
-                        for (int kb = 0; kb < kb_h; ++kb) {
-                            const uint32_t blk = bb + (uint32_t)kb * w3_block();
-                            const uint64_t bd = make_smem_desc(blk + ((p == 1) ? kPPad * 32 : 0), 128, 256);
-                            const uint32_t ad = tmem + col_h_last + (uint32_t)kb * 16 + ((p == 0) ? 8u : 0u);
-                            umma_f16_ts(dcol, ad, bd, idesc3, acc);
-                            acc = 1;
-                        }
-                    }
-                    umma_commit(&bars->acc_full[buf]);
-                    if (CL > 1) umma_commit_multicast(&bars->b_empty[st], cmask); else umma_commit(&bars->b_empty[st]);
-                }
+                for (int ji = 0; ji < n_tr; ++ji, ++rc, ++cc)
+                    if (ji % kIssuers == 0) issue_chunk(rc, cc);                // the other dims: issuers 1..2
+            }
+        }
+    } else if (warp >= kIssuerB) {
+        // ======================= UMMA issuers 1..2: dims ji % 3 == 1, 2 ==============================================
+        // One thread spends ~8 issue slots (elect loop + descriptor arithmetic on the uniform datapath) per UMMA and a dim
+        // is 3 H / 16 of them (48 at H = 256): with one issuer that thread, not the tensor pipe, paced the chunk phase
+        // (2.8e7 samples/s with one issuer, 4.7e7 with two at MLP[256,256]).
+        if (lane == 0) {
+            const int me = warp - kIssuerB + 1;
+            uint32_t rc = 0, cc = 0, tp = 0;
+            for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
+                rc += 1u + (uint32_t)n_items2;
+                mbar_wait_relaxed(n_hidden == 2 ? &bars->h2_ready : &bars->h1_ready, tp);
+                for (int ji = 0; ji < n_tr; ++ji, ++rc, ++cc)
+                    if (ji % kIssuers == me) issue_chunk(rc, cc);
             }
         }
     } else {
@@ -712,12 +738,13 @@ int tch_layer_apply(const stb_layer* L, int direction, const float* x, float* y,
     const uint32_t smem = smem_bytes(H);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    // The weight stream (1.85 MB per 128-row tile at MLP[256,256]) is what binds this kernel: clusters of CTAs share it
-    // through TMA multicast.  STRIBOR_B200_HW_CLUSTER = 1 | 2 | 4 overrides the default.
+    // Clusters of CTAs can share the weight stream (1.85 MB per 128-row tile at MLP[256,256]) through TMA multicast:
+    // STRIBOR_B200_HW_CLUSTER = 2 | 4.  Measured at MLP[256,256] (1 M rows, 8 layers): 22.2 ms without clusters,
+    // 23.0 ms with pairs, 24.4 ms with quads (fewer resident CTAs) -- L2 delivers the stream, the default stays 1.
     static const int want_cluster = [] {
         const char* ev = getenv("STRIBOR_B200_HW_CLUSTER");
-        const int v = ev ? atoi(ev) : 4;
-        return (v == 1 || v == 2 || v == 4) ? v : 4;
+        const int v = ev ? atoi(ev) : 1;               // measured: 1 is fastest (the stream is not what binds)
+        return (v == 1 || v == 2 || v == 4) ? v : 1;
     }();
     int cl = want_cluster;
     while (cl > 1 && (tiles < cl || (n_sm % cl) != 0)) cl >>= 1;
