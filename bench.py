@@ -74,7 +74,7 @@ def parse():
     ap.add_argument('--micro-rows', type=int, default=1 << 18, help='train: rows per micro-batch')
     ap.add_argument('--tf32', action='store_true', help='train: let the library GEMMs of the conditioner gradients use TF32')
     ap.add_argument('--hybrid', action='store_true', help='train: conditioner through autograd around the element-wise kernels')
-    ap.add_argument('--workload', default='logprob', choices=['logprob', 'cubic', 'affine', 'neural', 'train'],
+    ap.add_argument('--workload', default='logprob', choices=['logprob', 'cubic', 'quadratic_h256', 'affine', 'neural', 'train'],
                     help='logprob = BASELINE.json configs[2] (the headline, default); affine = configs[1]; '
                          'neural = configs[3]; train = configs[4] (side measurements, same JSON schema)')
     return ap.parse_args()
@@ -294,13 +294,14 @@ def side_config(workload, args, dev, rank, world, want_cpu):
     res = {'steps': steps, 'warmup': warmup, 'n_gpus': world, 'higher_is_better': True, 'scaling': 'strong',
            'dtype': 'f32', 'data': 'synthetic'}
     cpu = None
-    if workload == 'cubic':
-        d, rows_g = D, args.batch
-        layers = build_layers('cubic', [64])
+    if workload in ('cubic', 'quadratic_h256'):
+        d, rows_g = D, args.batch if workload == 'cubic' else args.batch // 4
+        kind_w, hid_w = ('cubic', [64]) if workload == 'cubic' else ('quadratic', [256, 256])
+        layers = build_layers(kind_w, hid_w)
         flow = st.NormalizingFlow(st.UnitNormal(d), layers).to(dev).requires_grad_(False)
         a, b = shard_rows(rows_g, rank, world)
         y = torch.randn(b - a, d, device=dev, generator=torch.Generator(dev).manual_seed(rank))
-        name = workload_name('cubic', [64], rows_g)
+        name = workload_name(kind_w, hid_w, rows_g)
 
         def step():
             with torch.no_grad():
@@ -308,10 +309,14 @@ def side_config(workload, args, dev, rank, world, want_cpu):
         unit, per_step = 'samples/s', rows_g
         ins, n_out = [y], 1
         pipe_fn = lambda yy: flow.log_prob(yy)
-        bytes_unit, flops_unit, bound = LAYERS * (8 * d + 8), 2 * (32 * 64 + 64 * 32 * 34) * LAYERS, 'hbm'
-        traffic_key = 'cubic_dram_bytes_per_row_chain'
+        if workload == 'cubic':
+            bytes_unit, flops_unit, bound = LAYERS * (8 * d + 8), 2 * (32 * 64 + 64 * 32 * 34) * LAYERS, 'hbm'
+            traffic_key = 'cubic_dram_bytes_per_row_chain'
+        else:        # SURVEY 8d's secondary configs[2] shape: 917 504 flop per row and layer
+            bytes_unit, flops_unit, bound = LAYERS * (8 * d + 8), 2 * (32 * 256 + 256 * 256 + 256 * 32 * 47) * LAYERS, 'tensor'
+            traffic_key = None
         if want_cpu:
-            spec = spec_from_layers([l.cpu() for l in build_layers('cubic', [64])])
+            spec = spec_from_layers([l.cpu() for l in build_layers(kind_w, hid_w)])
             n = 1 << 13
             yc = torch.randn(n, d, generator=torch.Generator().manual_seed(0))
             with torch.no_grad():
@@ -696,7 +701,7 @@ def main():
             del pipe, y_host, lp_host
         torch.cuda.empty_cache()
         cfgs = {}
-        for w in ('cubic', 'affine', 'neural', 'train'):
+        for w in ('cubic', 'quadratic_h256', 'affine', 'neural', 'train'):
             try:
                 cfgs[w] = side_config(w, args, dev, rank, world, want_cpu=(world == 1 and not args.no_cpu_baseline))
             except Exception as e:                             # a side config must never cost the headline line

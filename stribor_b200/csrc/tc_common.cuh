@@ -56,7 +56,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) {
+        if (++spins > (1u << 26)) {
             if ((threadIdx.x & 31) == 0)
                 printf("stribor_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
                        (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
@@ -83,7 +83,7 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity), "r"(1000000u)
             : "memory");
         if (ok) break;
-        if (++spins > (1u << 22)) {
+        if (++spins > (1u << 26)) {
             printf("stribor_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
                    (int)threadIdx.x, bar, parity);
             __trap();
@@ -104,7 +104,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(ns);
-        if (++spins > (1u << 22)) {
+        if (++spins > (1u << 26)) {
             if ((threadIdx.x & 31) == 0)
                 printf("stribor_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
                        (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);
@@ -118,7 +118,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(256);
-        if (++spins > (1u << 22)) {
+        if (++spins > (1u << 26)) {
             if ((threadIdx.x & 31) == 0)
                 printf("stribor_b200: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
                        (int)blockIdx.x, (int)threadIdx.x, smem_u32(bar), parity);

@@ -42,12 +42,11 @@ constexpr int kMaxTr = 32;
 constexpr int kMaxH = 256;
 constexpr int kXsStride = kMaxDim + 1;
 constexpr int kStages = 3;
-constexpr int kNBuf = 5;                 // 48-column chunk accumulators
+constexpr int kNBuf = 4;                 // 48-column chunk accumulators: buffer b belongs to epilogue group b and issuer b % 2
 constexpr int kEpiWarp0 = 2;
 constexpr int kEpiWarps = 16;
-constexpr int kIssuers = 3;                              // UMMA issuer threads of the chunk phase (dims ji % 3): 20 warps in all,
-                                                         // the most that keeps 96 registers per thread
-constexpr int kIssuerB = kEpiWarp0 + kEpiWarps;          // issuers 1..2: warps 18..19 (issuer 0 = warp 1)
+constexpr int kIssuers = 2;                              // UMMA issuer threads of the chunk phase (dims ji % 2)
+constexpr int kIssuerB = kEpiWarp0 + kEpiWarps;          // issuer 1: warp 18 (issuer 0 = warp 1)
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps + kIssuers - 1) * 32;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr uint32_t kMagic = 0x53544834u;
@@ -206,11 +205,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
 
     // ---- one transformed dim: [128 x H] x [H x 48] from ring item `rc` into accumulator buffer `cc % 5`, A = the last
     // hidden layer in TMEM, three passes with the corrections first (lo*hi, hi*lo, hi*hi)
-    auto issue_chunk = [&](uint32_t rc, uint32_t cc) {
+    // Every mbarrier of the chunk phase is a PRIVATE channel, so that a waiter's successive waits are successive phases
+    // whatever the relative speed of the agents (a parity wait cannot tell "two phases behind" from "done"): accumulator
+    // buffer b = ji % 4 is written by issuer b % 2 only and read by epilogue group b only; a ring stage's successive items
+    // go to alternating issuers, each of which has consumed the item right before (filled in order by the one producer).
+    auto issue_chunk = [&](uint32_t rc, uint32_t buf, uint32_t buse) {
         const uint32_t idesc3 = make_idesc(FMT_F16, 128, kPPad);
         const uint32_t st = rc % kStages, use = rc / kStages;
         mbar_wait_relaxed(&bars->b_full[st], use & 1);
-        const uint32_t buf = cc % kNBuf, buse = cc / kNBuf;
         mbar_wait_relaxed(&bars->acc_empty[buf], (buse & 1) ^ 1);
         tc_fence_after();
         const uint32_t dcol = tmem + col_chunk + buf * kPPad;
@@ -272,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
             const uint32_t idesc1 = make_idesc(FMT_BF16, 128, H);
             const uint32_t idesc2 = make_idesc(FMT_F16, 128, H);
             const uint32_t a0 = smem_u32(a1buf);
-            uint32_t rc = 0, cc = 0, tp = 0;
+            uint32_t rc = 0, tp = 0;
+            uint32_t nuse[2] = {0, 0};             // uses so far of this issuer's buffers 0 and 2
             for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
                 {   // ---- GEMM1: 8 bf16 partial products, smallest first, one accumulator -----------------------------
                     const uint32_t st = rc % kStages, use = rc / kStages;
@@ -320,23 +323,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                     umma_commit(&bars->acc2_full);
                 }
                 mbar_wait_relaxed(n_hidden == 2 ? &bars->h2_ready : &bars->h1_ready, tp);
-                for (int ji = 0; ji < n_tr; ++ji, ++rc, ++cc)
-                    if (ji % kIssuers == 0) issue_chunk(rc, cc);                // the other dims: issuers 1..2
+                for (int ji = 0; ji < n_tr; ++ji, ++rc)
+                    if (!(ji & 1)) { issue_chunk(rc, (uint32_t)(ji & 3), nuse[(ji >> 1) & 1]); ++nuse[(ji >> 1) & 1]; }
             }
         }
     } else if (warp >= kIssuerB) {
-        // ======================= UMMA issuers 1..2: dims ji % 3 == 1, 2 ==============================================
+        // ======================= second UMMA issuer: the odd transformed dims (buffers 1 and 3) =======================
         // One thread spends ~8 issue slots (elect loop + descriptor arithmetic on the uniform datapath) per UMMA and a dim
         // is 3 H / 16 of them (48 at H = 256): with one issuer that thread, not the tensor pipe, paced the chunk phase
-        // (2.8e7 samples/s with one issuer, 4.7e7 with two at MLP[256,256]).
+        // (2.8e7 samples/s with one issuer, 4.7e7 with two at MLP[256,256]; a third changes nothing).
         if (lane == 0) {
-            const int me = warp - kIssuerB + 1;
-            uint32_t rc = 0, cc = 0, tp = 0;
+            uint32_t rc = 0, tp = 0;
+            uint32_t nuse[2] = {0, 0};
             for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
                 rc += 1u + (uint32_t)n_items2;
                 mbar_wait_relaxed(n_hidden == 2 ? &bars->h2_ready : &bars->h1_ready, tp);
-                for (int ji = 0; ji < n_tr; ++ji, ++rc, ++cc)
-                    if (ji % kIssuers == me) issue_chunk(rc, cc);
+                for (int ji = 0; ji < n_tr; ++ji, ++rc)
+                    if (ji & 1) { issue_chunk(rc, (uint32_t)(ji & 3), nuse[(ji >> 1) & 1]); ++nuse[(ji >> 1) & 1]; }
             }
         }
     } else {
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
         const float s_mid = hdr->s_mid;
         const uint32_t noshift_mask = hdr->noshift_mask;
         const int dshift = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;
-        uint32_t cc = 0, tp = 0;
+        uint32_t buse = 0, tp = 0;                  // uses so far of this group's accumulator buffer (buffer g)
 
         for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * kRows;
@@ -415,9 +418,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
             // ---- chunks: dims g, g + 4, ... of this group's 128 rows -----------------------------------------------------------
             float ld_acc = 0.f;
 #pragma unroll 1
-            for (int ji = g; ji < n_tr; ji += 4) {
-                const uint32_t ccc = cc + (uint32_t)ji;
-                const uint32_t buf = ccc % kNBuf, buse = ccc / kNBuf;
+            for (int ji = g; ji < n_tr; ji += 4, ++buse) {
+                const uint32_t buf = (uint32_t)g;
                 const int j = hdr->tr_idx[ji];
                 const float xv = xrow[j];
                 const bool inside = (xv >= lo) && (xv <= hi);
@@ -483,7 +485,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                 if (A.bins != nullptr && row < nrows) A.bins[(row0 + row) * d + j] = kbin;
                 ld_acc += ld;
             }
-            cc += (uint32_t)n_tr;
             // ---- per-row log|det J| over the four groups (+ UnitNormal log-density of the output row) -------------------------
             ld_s[g * kRows + row] = ld_acc;
             named_bar_sync(1, kEpiThreads);
