@@ -82,3 +82,14 @@ for kind, d in ((('quadratic', 64), ('cubic', 128)) if (not ONLY or ONLY in 'bin
 torch.cuda.synchronize()
 if not ONLY or ONLY in 'bins instrument':
     print('ok bins instrument', flush=True)
+# round 2, later: the wide-conditioner spline kernel (TMEM-resident activations, two issuers) and the chain4 kernel
+run('hwide quadratic 256x256', cases._mk_flow('quadratic', 64, [256, 256], 2, 16, 8, 11)(), rows_list=(1, 129, 300))
+run('hwide cubic 128 d30', cases._mk_flow('cubic', 30, [128], 2, 16, 8, 12)(), rows_list=(1, 257))
+if not ONLY or ONLY in 'chain4 neural':
+    spec = [cases.cont_affine_spec(rs, 16, [64], ('ordered_0', 'ordered_1')[i % 2]) for i in range(4)]
+    nf = st.NeuralFlow([l.to(dev) for l in layers_from_spec(spec)])
+    with torch.no_grad():
+        for r in (1, 129, 513, 2000):
+            x = torch.randn(r, 16, device=dev); t = torch.rand(r, 1, device=dev)
+            nf(x, t=t, t0=t * 0.5)
+    torch.cuda.synchronize(); print('ok chain4 neural', flush=True)
