@@ -77,6 +77,13 @@ __device__ unsigned int g_tc_prof[160 * 32 * 8];
 #define PROFC(i)
 #define PROF_FLUSH
 #endif
+// -DSTB_PLAIN_ARRIVE: release the accumulator buffers through the generic-address helper instead of the pre-converted
+// shared address (tool experiments only: compute-sanitizer synccheck, see profiles/r02_synccheck.txt)
+#ifdef STB_PLAIN_ARRIVE
+#define STB_ARRIVE_EMPTY(buf) mbar_arrive(&bars->acc_empty[s][buf])
+#else
+#define STB_ARRIVE_EMPTY(buf) mbar_arrive_a(empty_bar + (buf) * 8)
+#endif
 constexpr int kEpiPerSub = STB_TC_EPI_PER_SUB;   // epilogue warps per (subtile, TMEM sub-partition)
 constexpr int kEpiWarps = 2 * 4 * kEpiPerSub;
 constexpr int kEpiWarp0 = 3;           // warp 0 producer, warps 1 / 2 UMMA issuers of subtile 0 / 1
@@ -534,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_a(empty_bar + buf * 8);     // TMEM buffer free again
+                    if (lane == 0) STB_ARRIVE_EMPTY(buf);     // TMEM buffer free again
                     PROFC(2)
                     if (inside) {
                         // derivative parameter AT knot i (1..15) is column 32 + i - 1; box ends are constants
@@ -564,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_a(empty_bar + buf * 8);
+                    if (lane == 0) STB_ARRIVE_EMPTY(buf);
                     if (inside) {
                         const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
                         cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);

@@ -22,6 +22,7 @@
 //                affine transform + log|det J| from the last accumulator.
 //
 // Reference semantics: flows/coupling.py:53-95, flows/affine.py:59-109, net/mlp.py:46-58.
+#include <stdlib.h>
 #include "common.cuh"
 #include "stb_math.cuh"
 #include "tc_common.cuh"
@@ -513,6 +514,332 @@ __global__ void __launch_bounds__(Cfg<NCG>::kThreads, (NCG == 4) ? 1 : 2) tc_mlp
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+// -----------------------------------------------------------------------------------------------
+// Wide conditioners, pipelined: tc_mlp_pipe_kernel
+// -----------------------------------------------------------------------------------------------
+// Same layer as tc_mlp_affine_kernel<4> (BASELINE.json configs[1]: MLP[256,256]) restructured so that the tensor pipe and
+// the activation passes overlap.  In that kernel every GEMM waits for the whole previous activation pass and every
+// activation pass for the whole GEMM (40 k clocks per 128-row tile for 9.7 k clocks of tensor work) because TMEM is full
+// (main + corr accumulators of a 256-wide layer) and the next A operand lives in 128 KB of shared memory.  Here:
+//   * every GEMM uses ONE accumulator (per K block: lo*hi, hi*lo, then hi*hi -- the order tc_hwide.cu's hidden GEMM
+//     uses), so layer l's accumulator [0, H) and layer l+1's [256, 256 + H) coexist;
+//   * the hidden activations go back INTO the accumulator columns just consumed (tcgen05.st) and are read from TMEM as
+//     the next GEMM's A operand: no shared-memory A buffer, no proxy fence;
+//   * a warp (TMEM sub-partition q, column quarter g) activates its columns 16 at a time; after every such WAVE j the
+//     issuer is told (wave barrier, 16 arrivals) and runs the next GEMM over the four K blocks {g H/64 + j} that just
+//     became available, while the warps are already on wave j + 1.
+// Weights stream one 16-wide K block per ring item (<= 16 KB), in the order the issuer consumes them.
+constexpr int kPipeStages = 6;
+constexpr int kPipeThreads = (2 + 16) * 32;
+
+struct PipeBars {
+    uint64_t setup;
+    uint64_t full[kPipeStages], empty[kPipeStages];
+    uint64_t a1_ready, acc1_full, acc2_full, acc3_full;
+    uint64_t wave1[4], wave2[4];
+};
+static_assert(sizeof(PipeBars) <= 256, "barrier block");
+
+constexpr uint32_t kPipeSmXs = 0;                                            // float [128][65]
+constexpr uint32_t kPipeSmA1 = (kRows * (kMaxDim + 1) * 4 + 127) & ~127u;    // 3 x 8 KB (bf16x3 of [128 x 32])
+constexpr uint32_t kPipeSmSmall = kPipeSmA1 + 3 * kRows * kK1 * 2;
+constexpr uint32_t kPipeSmLd = kPipeSmSmall + 3584;                          // float [4][128]
+constexpr uint32_t kPipeSmT = kPipeSmLd + 4 * kRows * 4;
+constexpr uint32_t kPipeSmBar = kPipeSmT + kRows * 4;
+constexpr uint32_t kPipeSmRing = (kPipeSmBar + 256 + 127) & ~127u;
+__host__ __device__ inline uint32_t pipe_slot_bytes(int H) { return (uint32_t)H * 64; }
+__host__ __device__ inline uint32_t pipe_smem_bytes(int H) { return kPipeSmRing + kPipeStages * pipe_slot_bytes(H); }
+
+// this warp's 16 columns starting at c0 of the accumulator at `acc` -> h (fp16 hi at +0, lo at +8), in place
+__device__ __forceinline__ void pipe_activate16(uint32_t acc, int c0, float sc, const float* bias, int act) {
+    float v[16];
+    tmem_ld16(acc + c0, v);
+    tmem_ld_wait();
+    uint32_t hh[8], hl[8];
+    const float2* b2p = reinterpret_cast<const float2*>(bias + c0);
+    const float2 z = make_float2(0.f, 0.f);
+    if (act == STB_ACT_TANH) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tanh_split2(make_float2(v[2 * i], v[2 * i + 1]), z, make_float2(sc, sc), b2p[i], hh[i], hl[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sigmoid_split2(make_float2(v[2 * i], v[2 * i + 1]), z, make_float2(sc, sc), b2p[i], hh[i], hl[i]);
+    }
+    tmem_st8(acc + c0, hh);
+    tmem_st8(acc + c0 + 8, hl);
+    tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args A) {
+    constexpr int kXsStride = kMaxDim + 1;
+    constexpr int kEpiThreads = 16 * 32;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_base_s;
+    float* xs = reinterpret_cast<float*>(smem + kPipeSmXs);
+    uint8_t* a1buf = smem + kPipeSmA1;
+    const Header* hdr = reinterpret_cast<const Header*>(smem + kPipeSmSmall);
+    const float* b1s = reinterpret_cast<const float*>(smem + kPipeSmSmall + kOffB1);
+    const float* b2s = reinterpret_cast<const float*>(smem + kPipeSmSmall + kOffB2);
+    const float* b3s = reinterpret_cast<const float*>(smem + kPipeSmSmall + kOffB3);
+    float* ld_s = reinterpret_cast<float*>(smem + kPipeSmLd);
+    float* t_s = reinterpret_cast<float*>(smem + kPipeSmT);
+    PipeBars* bars = reinterpret_cast<PipeBars*>(smem + kPipeSmBar);
+    uint8_t* ring = smem + kPipeSmRing;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&bars->setup, 1);
+        for (int i = 0; i < kPipeStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        mbar_init(&bars->a1_ready, 16);
+        mbar_init(&bars->acc1_full, 1);
+        mbar_init(&bars->acc2_full, 1);
+        mbar_init(&bars->acc3_full, 1);
+        for (int j = 0; j < 4; ++j) { mbar_init(&bars->wave1[j], 16); mbar_init(&bars->wave2[j], 16); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&bars->setup, kSmallBytes);
+        bulk_g2s(smem + kPipeSmSmall, A.packed, kSmallBytes, &bars->setup);
+    }
+    mbar_wait(&bars->setup, 0);
+
+    const int d = hdr->dim, n_tr = hdr->n_tr, n_cond = hdr->n_cond, H = hdr->H, n_hidden = hdr->n_hidden, act = hdr->act;
+    const int cq = H / 4;                        // columns of a column quarter
+    const int nw = cq / 16;                      // waves = K blocks per quarter
+    const uint32_t slot = pipe_slot_bytes(H);
+    const uint32_t w1b = w1_block_bytes(H), w2b = w2_block_bytes(H), w3b = w3_block_bytes();
+    const uint32_t col_d3 = (n_hidden == 2) ? 0u : 256u;          // output accumulator: over the dead h1, or beside it
+    const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint8_t* img_w2 = A.packed + kOffW + 6 * w1b;
+    const uint8_t* img_w3 = img_w2 + (n_hidden == 2 ? (uint32_t)(H / 16) * w2b : 0u);
+
+    if (warp == 0) {
+        // ======================= producer: one K block per ring item, in consumption order =======================
+        if (lane == 0) {
+            uint32_t rc = 0;
+            auto put = [&](const uint8_t* src, uint32_t bytes) {
+                const uint32_t st = rc % kPipeStages, use = rc / kPipeStages;
+                mbar_wait_relaxed(&bars->empty[st], (use & 1) ^ 1);
+                mbar_arrive_expect_tx(&bars->full[st], bytes);
+                bulk_g2s(ring + st * slot, src, bytes, &bars->full[st]);
+                ++rc;
+            };
+            for (int it = 0; it < my_tiles; ++it) {
+                if (it + 1 < my_tiles) {
+                    const long long nrow0 = ((long long)blockIdx.x + (long long)(it + 1) * gridDim.x) * kRows;
+                    const long long nb = min((long long)kRows, A.rows - nrow0) * d * 4;
+                    const char* src = reinterpret_cast<const char*>(A.x + nrow0 * d);
+                    if (nb >= 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(nb & ~15LL)) : "memory");
+                }
+                for (int b = 0; b < 6; ++b) put(A.packed + kOffW + (uint32_t)b * w1b, w1b);
+                if (n_hidden == 2)
+                    for (int j = 0; j < nw; ++j)
+                        for (int g = 0; g < 4; ++g) put(img_w2 + (uint32_t)(g * nw + j) * w2b, w2b);
+                for (int j = 0; j < nw; ++j)
+                    for (int g = 0; g < 4; ++g) put(img_w3 + (uint32_t)(g * nw + j) * w3b, w3b);
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= UMMA issuer ===========================================================================
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, H);
+            const uint32_t idesc2 = make_idesc(FMT_F16, 128, H);
+            const uint32_t idesc3 = make_idesc(FMT_F16, 128, kNOut);
+            const uint32_t a0 = smem_u32(a1buf);
+            constexpr uint32_t a_part = (uint32_t)kRows * kK1 * 2;
+            uint32_t rc = 0, tp = 0;
+            for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
+                // ---- layer 1: bf16x3 x bf16x3 into one accumulator, blocks (pb = 2, 1, 0) x (kb = 0, 1) as they arrive ----
+                mbar_wait_relaxed(&bars->a1_ready, tp);
+                uint32_t acc = 0;
+                for (int b = 0; b < 6; ++b, ++rc) {
+                    const int pb = 2 - b / 2, kb = b & 1;
+                    const uint32_t st = rc % kPipeStages, use = rc / kPipeStages;
+                    mbar_wait_relaxed(&bars->full[st], use & 1);
+                    tc_fence_after();
+                    const uint64_t bd = make_smem_desc(smem_u32(ring + st * slot), 128, 256);
+                    for (int pa = 2; pa >= 0; --pa) {
+                        if (pa == 2 && pb == 2) continue;
+                        umma_f16(tmem, make_smem_desc(a0 + pa * a_part + kb * 256, 128, 512), bd, idesc1, acc);
+                        acc = 1;
+                    }
+                    umma_commit(&bars->empty[st]);
+                }
+                umma_commit(&bars->acc1_full);
+                // ---- hidden -> hidden (optional) and hidden -> output, four K blocks per activation wave --------------------
+                for (int layer = (n_hidden == 2 ? 0 : 1); layer < 2; ++layer) {
+                    const bool last = (layer == 1);
+                    const uint32_t a_base = tmem + ((last && n_hidden == 2) ? 256u : 0u);      // h1 at [0, H), h2 at [256, 256 + H)
+                    const uint32_t dcol = last ? tmem + col_d3 : tmem + 256u;
+                    const uint32_t idesc = last ? idesc3 : idesc2;
+                    const uint32_t lo_off = last ? kNOut * 32 : (uint32_t)H * 32;
+                    uint64_t* wave = (last && n_hidden == 2) ? bars->wave2 : bars->wave1;
+                    acc = 0;
+                    for (int j = 0; j < nw; ++j) {
+                        mbar_wait_relaxed(&wave[j], tp);
+                        for (int g = 0; g < 4; ++g, ++rc) {
+                            const int kb = g * nw + j;
+                            const uint32_t st = rc % kPipeStages, use = rc / kPipeStages;
+                            mbar_wait_relaxed(&bars->full[st], use & 1);
+                            tc_fence_after();
+                            const uint32_t bb = smem_u32(ring + st * slot);
+                            const uint64_t b_hi = make_smem_desc(bb, 128, 256), b_lo = make_smem_desc(bb + lo_off, 128, 256);
+                            const uint32_t a_hi = a_base + (uint32_t)kb * 16, a_lo = a_hi + 8;
+                            umma_f16_ts(dcol, a_lo, b_hi, idesc, acc); acc = 1;
+                            umma_f16_ts(dcol, a_hi, b_lo, idesc, 1);
+                            umma_f16_ts(dcol, a_hi, b_hi, idesc, 1);
+                            umma_commit(&bars->empty[st]);
+                        }
+                    }
+                    umma_commit(last ? &bars->acc3_full : &bars->acc2_full);
+                }
+            }
+        }
+    } else {
+        // ======================= epilogue warps ===========================================================================
+        const int q = warp & 3;
+        const int g = (warp - 2) >> 2;
+        const int etid = tid - 64;
+        const int row = q * 32 + lane;
+        float* xrow = xs + row * kXsStride;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
+        const bool inverse = A.inverse != 0;
+        const float s_mid = hdr->s_mid, s_out = hdr->s_out;
+        const int dshift = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;
+        uint32_t tp = 0;
+
+        for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * kRows;
+            const int nrows = (int)min((long long)kRows, A.rows - row0);
+            {   // ---- stage x -----------------------------------------------------------------------------------------
+                const float* xg = A.x + row0 * d;
+                const int n = nrows * d;
+                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0)) {
+                    const int n4 = (kRows * d) >> 2;
+                    for (int i = etid; i < n4; i += kEpiThreads) {
+                        const float4 v = (i * 4 < n) ? __ldg(reinterpret_cast<const float4*>(xg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
+                        float* dst = xs + r * kXsStride + c;
+                        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+                    }
+                } else {
+                    for (int i = etid; i < kRows * d; i += kEpiThreads) {
+                        const int r = i / d, c = i - r * d;
+                        xs[r * kXsStride + c] = (i < n) ? __ldg(xg + i) : 0.f;
+                    }
+                }
+                if (etid < kRows) t_s[etid] = (A.t != nullptr && etid < nrows) ? __ldg(A.t + row0 + etid) : 0.f;
+            }
+            named_bar_sync(1, kEpiThreads);
+            {   // ---- A1: 8 of the 32 conditioning columns of this row (column group g), three bf16 parts -----------------
+                const uint32_t off = (uint32_t)(row >> 3) * 512 + (uint32_t)(row & 7) * 16 + (uint32_t)g * 128;
+                constexpr uint32_t a_part = (uint32_t)kRows * kK1 * 2;
+                __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = g * 8 + u;
+                    const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[row] : 0.f);
+                    split_bf16x3(v, q0[u], q1[u], q2[u]);
+                }
+                *reinterpret_cast<uint4*>(a1buf + off) = *reinterpret_cast<const uint4*>(q0);
+                *reinterpret_cast<uint4*>(a1buf + a_part + off) = *reinterpret_cast<const uint4*>(q1);
+                *reinterpret_cast<uint4*>(a1buf + 2 * a_part + off) = *reinterpret_cast<const uint4*>(q2);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a1_ready);
+            }
+            // ---- hidden layer 1 in place, wave by wave: the next GEMM runs behind ---------------------------------------------
+            mbar_wait_sleep(&bars->acc1_full, tp, 64);
+            tc_fence_after();
+            for (int j = 0; j < nw; ++j) {
+                pipe_activate16(tmem + lane_sel, g * cq + 16 * j, 1.f, b1s, act);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->wave1[j]);
+            }
+            if (n_hidden == 2) {
+                mbar_wait_sleep(&bars->acc2_full, tp, 64);
+                tc_fence_after();
+                for (int j = 0; j < nw; ++j) {
+                    pipe_activate16(tmem + lane_sel + 256, g * cq + 16 * j, s_mid, b2s, act);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->wave2[j]);
+                }
+            }
+            // ---- output layer: [log_scale | shift] of this warp's 8 transformed dims (one accumulator) ------------------
+            mbar_wait_sleep(&bars->acc3_full, tp, 64);
+            tc_fence_after();
+            float ld_acc = 0.f;
+            if (g * 8 < n_tr) {
+                float lm[8], sm[8];
+                tmem_ld8(tmem + lane_sel + col_d3 + g * 8, lm);
+                tmem_ld8(tmem + lane_sel + col_d3 + kMaxTr + g * 8, sm);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int ji = g * 8 + u;
+                    if (ji < n_tr) {
+                        const int j = hdr->tr_idx[ji];
+                        float ls = fmaf(lm[u], s_out, b3s[ji]);
+                        float sh = fmaf(sm[u], s_out, b3s[kMaxTr + ji]);
+                        if (hdr->cont) {                       // coupling.py:199-205
+                            const float tv = t_s[row];
+                            ls *= hdr->ts_ls[ji] * tv;
+                            sh *= hdr->ts_sh[ji] * tv;
+                        }
+                        const float xv = xrow[j];
+                        if (inverse) { xrow[j] = (xv - sh) * exp_fast(-ls); ld_acc -= ls; }
+                        else { xrow[j] = xv * exp_fast(ls) + sh; ld_acc += ls; }
+                    }
+                }
+            }
+            tc_fence_before();
+            ld_s[g * kRows + row] = ld_acc;
+            named_bar_sync(1, kEpiThreads);
+            if (g == 0 && want_ld && row < nrows) {
+                float tot = (ld_s[row] + ld_s[kRows + row]) + (ld_s[2 * kRows + row] + ld_s[3 * kRows + row]);
+                if (A.base_log_prob) {
+                    float b = 0.f;
+                    for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
+                    tot += b;
+                }
+                float* dst = A.ldj + row0 + row;
+                *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
+            }
+            if (A.y != nullptr) {
+                float* yg = A.y + row0 * d;
+                const int n = nrows * d;
+                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
+                    const int n4 = n >> 2;
+                    for (int i = etid; i < n4; i += kEpiThreads) {
+                        const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
+                        const float* src = xs + r * kXsStride + c;
+                        reinterpret_cast<float4*>(yg)[i] = make_float4(src[0], src[1], src[2], src[3]);
+                    }
+                } else {
+                    for (int i = etid; i < n; i += kEpiThreads) {
+                        const int r = i / d, c = i - r * d;
+                        yg[i] = xs[r * kXsStride + c];
+                    }
+                }
+            }
+            named_bar_sync(1, kEpiThreads);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -1114,6 +1441,20 @@ int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const flo
     // small conditioner on few dims (configs[3]): the 8-warp configuration, two CTAs per SM
     const uint32_t w_total = 6 * w1_block_bytes(H) + (L->net.n_linear == 3 ? (H / 16) * w2_block_bytes(H) : 0) + (H / 16) * w3_block_bytes();
     const bool small = (H == 64) && (L->dim <= 32) && (w_total <= kStages * kSlotBytes) && (tiles >= 2LL * n_sm);
+    // wide conditioners: the pipelined kernel (TMEM-resident activations, GEMMs behind the activation waves);
+    // STRIBOR_B200_NO_MLP_PIPE=1 restores the phase-by-phase kernel
+    static const bool pipe_off = [] { const char* ev = getenv("STRIBOR_B200_NO_MLP_PIPE"); return ev && ev[0] == '1'; }();
+    if (!small && !pipe_off && H >= 128) {
+        const uint32_t psmem = pipe_smem_bytes(H);
+        cudaError_t pe = cudaFuncSetAttribute(tc_mlp_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+        if (pe != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(pe));
+        const int pgrid = (int)min((long long)n_sm, tiles);
+        tc_mlp_pipe_kernel<<<pgrid, kPipeThreads, psmem, stream>>>(A);
+        count_launch();
+        pe = cudaGetLastError();
+        if (pe != cudaSuccess) return set_error(STB_ECUDA, "tc_mlp_pipe_kernel launch: %s", cudaGetErrorString(pe));
+        return STB_OK;
+    }
     const uint32_t smem = small ? Cfg<2>::smem_bytes(H) : Cfg<4>::smem_bytes(H);
     if (smem > 227 * 1024) return set_error(STB_ENOTSUP, "hidden width %d needs %u B of shared memory", H, smem);
     void (*kern)(Args) = small ? tc_mlp_affine_kernel<2> : tc_mlp_affine_kernel<4>;
