@@ -176,7 +176,9 @@ def test_affine_tensor_path_matches_generic_and_oracle(d, hidden, masks, monkeyp
             (lf_t, O.flow_forward(spec, xc, with_ldj=True)[1], O.flow_forward(s64, xc.double(), with_ldj=True)[1], 'forward ldj')):
         fail, _, mx = close_or_arbitrated(got, f32, f64, 1e-5, 1e-5)
         assert fail <= 2e-3, f'{what}: {fail:.3%} outside tolerance (max abs err {mx:.3e})'
-    assert (lp_t - lp_g).abs().max().item() < 2e-4 and (xi_t - xi_g).abs().max().item() < 2e-4
+    # the two CUDA paths agree at fp32 noise level; log_prob reaches |lp| ~ 200 through 0.5 * |x|^2, so its bound is
+    # relative (rtol = 1e-5, the parity tolerance) on top of the absolute one
+    assert ((lp_t - lp_g).abs() <= 2e-4 + 1e-5 * lp_g.abs()).all().item() and (xi_t - xi_g).abs().max().item() < 2e-4
     assert (li_t - li_g).abs().max().item() < 2e-4
 
 

@@ -93,3 +93,4 @@ if not ONLY or ONLY in 'chain4 neural':
             x = torch.randn(r, 16, device=dev); t = torch.rand(r, 1, device=dev)
             nf(x, t=t, t0=t * 0.5)
     torch.cuda.synchronize(); print('ok chain4 neural', flush=True)
+run('tc affine d63 h192 (pipe kernel, one hidden layer, odd dim)', cases._mk_flow('affine', 63, [192], 2, 0, 8, 13, masks=('ordered_left_half', 'parity_odd'))(), rows_list=(1, 129, 300))
