@@ -529,25 +529,44 @@ __global__ void __launch_bounds__(Cfg<NCG>::kThreads, (NCG == 4) ? 1 : 2) tc_mlp
 //     the next GEMM's A operand: no shared-memory A buffer, no proxy fence;
 //   * a warp (TMEM sub-partition q, column quarter g) activates its columns 16 at a time; after every such WAVE j the
 //     issuer is told (wave barrier, 16 arrivals) and runs the next GEMM over the four K blocks {g H/64 + j} that just
-//     became available, while the warps are already on wave j + 1.
+//     became available, while the warps are already on wave j + 1 (one barrier per K block -- 4 arrivals -- measured
+//     10 % slower: the issuer's extra waits sit on the critical path);
+//   * the epilogue warps prepare tile i + 1 inside tile i's waits: its rows are staged (second xs buffer) while GEMM2's
+//     last K blocks drain, its A1 operand is split while GEMM3's drain, and its GEMM1 runs under tile i's affine
+//     output / store phase (the issuer only waits until the output accumulator has been read: d3_read).
 // Weights stream one 16-wide K block per ring item (<= 16 KB), in the order the issuer consumes them.
-constexpr int kPipeStages = 6;
+// per-warp phase clocks of the chain and pipe kernels (profiling builds: -DSTB_TCM_PROF, tools/tcm_phase_prof.py)
+#ifdef STB_TCM_PROF
+__device__ unsigned int g_tcm_prof[160 * 32 * 8];
+#define TPROF_DECL unsigned int _pt = clock(), _pa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define TPROF(i) { const unsigned int _n = clock(); _pa[i] += _n - _pt; _pt = _n; }
+#define TPROF_FLUSH { if ((threadIdx.x & 31) == 0) for (int _i = 0; _i < 8; ++_i) g_tcm_prof[(blockIdx.x * 32 + (threadIdx.x >> 5)) * 8 + _i] = _pa[_i]; }
+#else
+#define TPROF_DECL
+#define TPROF(i)
+#define TPROF_FLUSH
+#endif
+#ifndef STB_PIPE_STAGES
+#define STB_PIPE_STAGES 6
+#endif
+constexpr int kPipeStages = STB_PIPE_STAGES;
 constexpr int kPipeThreads = (2 + 16) * 32;
 
 struct PipeBars {
     uint64_t setup;
     uint64_t full[kPipeStages], empty[kPipeStages];
-    uint64_t a1_ready, acc1_full, acc2_full, acc3_full;
+    uint64_t a1_ready, acc1_full, acc2_full, acc3_full, d3_read;
     uint64_t wave1[4], wave2[4];
 };
 static_assert(sizeof(PipeBars) <= 256, "barrier block");
 
-constexpr uint32_t kPipeSmXs = 0;                                            // float [128][65]
-constexpr uint32_t kPipeSmA1 = (kRows * (kMaxDim + 1) * 4 + 127) & ~127u;    // 3 x 8 KB (bf16x3 of [128 x 32])
+constexpr uint32_t kPipeXsBytes = (kRows * (kMaxDim + 1) * 4 + 127) & ~127u; // float [128][65], one per tile in flight
+constexpr uint32_t kPipeSmXs = 0;
+constexpr uint32_t kPipeSmA1 = 2 * kPipeXsBytes;                             // 3 x 8 KB (bf16x3 of [128 x 32])
 constexpr uint32_t kPipeSmSmall = kPipeSmA1 + 3 * kRows * kK1 * 2;
 constexpr uint32_t kPipeSmLd = kPipeSmSmall + 3584;                          // float [4][128]
-constexpr uint32_t kPipeSmT = kPipeSmLd + 4 * kRows * 4;
-constexpr uint32_t kPipeSmBar = kPipeSmT + kRows * 4;
+constexpr uint32_t kPipeSmT = kPipeSmLd + 4 * kRows * 4;                     // float [2][128]
+constexpr uint32_t kPipeSmBar = kPipeSmT + 2 * kRows * 4;
 constexpr uint32_t kPipeSmRing = (kPipeSmBar + 256 + 127) & ~127u;
 __host__ __device__ inline uint32_t pipe_slot_bytes(int H) { return (uint32_t)H * 64; }
 __host__ __device__ inline uint32_t pipe_smem_bytes(int H) { return kPipeSmRing + kPipeStages * pipe_slot_bytes(H); }
@@ -596,6 +615,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args
         mbar_init(&bars->acc1_full, 1);
         mbar_init(&bars->acc2_full, 1);
         mbar_init(&bars->acc3_full, 1);
+        mbar_init(&bars->d3_read, 16);
         for (int j = 0; j < 4; ++j) { mbar_init(&bars->wave1[j], 16); mbar_init(&bars->wave2[j], 16); }
         fence_mbar_init();
     }
@@ -656,9 +676,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args
             const uint32_t a0 = smem_u32(a1buf);
             constexpr uint32_t a_part = (uint32_t)kRows * kK1 * 2;
             uint32_t rc = 0, tp = 0;
+            TPROF_DECL
             for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
                 // ---- layer 1: bf16x3 x bf16x3 into one accumulator, blocks (pb = 2, 1, 0) x (kb = 0, 1) as they arrive ----
                 mbar_wait_relaxed(&bars->a1_ready, tp);
+                if (it > 0) mbar_wait_relaxed(&bars->d3_read, tp ^ 1);      // tile it-1's output accumulator has been read
+                tc_fence_after();
+                TPROF(0)
                 uint32_t acc = 0;
                 for (int b = 0; b < 6; ++b, ++rc) {
                     const int pb = 2 - b / 2, kb = b & 1;
@@ -674,6 +698,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args
                     umma_commit(&bars->empty[st]);
                 }
                 umma_commit(&bars->acc1_full);
+                TPROF(1)
                 // ---- hidden -> hidden (optional) and hidden -> output, four K blocks per activation wave --------------------
                 for (int layer = (n_hidden == 2 ? 0 : 1); layer < 2; ++layer) {
                     const bool last = (layer == 1);
@@ -685,10 +710,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args
                     acc = 0;
                     for (int j = 0; j < nw; ++j) {
                         mbar_wait_relaxed(&wave[j], tp);
+                        TPROF(2 + 3 * layer)
                         for (int g = 0; g < 4; ++g, ++rc) {
                             const int kb = g * nw + j;
                             const uint32_t st = rc % kPipeStages, use = rc / kPipeStages;
                             mbar_wait_relaxed(&bars->full[st], use & 1);
+                            TPROF(3 + 3 * layer)
                             tc_fence_after();
                             const uint32_t bb = smem_u32(ring + st * slot);
                             const uint64_t b_hi = make_smem_desc(bb, 128, 256), b_lo = make_smem_desc(bb + lo_off, 128, 256);
@@ -697,11 +724,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args
                             umma_f16_ts(dcol, a_hi, b_lo, idesc, 1);
                             umma_f16_ts(dcol, a_hi, b_hi, idesc, 1);
                             umma_commit(&bars->empty[st]);
+                            TPROF(4 + 3 * layer)
                         }
                     }
                     umma_commit(last ? &bars->acc3_full : &bars->acc2_full);
                 }
             }
+            TPROF_FLUSH
         }
     } else {
         // ======================= epilogue warps ===========================================================================
@@ -709,102 +738,132 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args
         const int g = (warp - 2) >> 2;
         const int etid = tid - 64;
         const int row = q * 32 + lane;
-        float* xrow = xs + row * kXsStride;
         const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
         const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
         const bool inverse = A.inverse != 0;
         const float s_mid = hdr->s_mid, s_out = hdr->s_out;
         const int dshift = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;
         uint32_t tp = 0;
+        TPROF_DECL
 
+        // rows of tile `it` -> xs buffer it & 1 (zero rows past the end), t likewise
+        auto stage_x = [&](int it) {
+            const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * kRows;
+            const int nrows = (int)min((long long)kRows, A.rows - row0);
+            float* xb = xs + (it & 1) * (kPipeXsBytes / 4);
+            const float* xg = A.x + row0 * d;
+            const int n = nrows * d;
+            if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0)) {
+                const int n4 = (kRows * d) >> 2;
+                for (int i = etid; i < n4; i += kEpiThreads) {
+                    const float4 v = (i * 4 < n) ? __ldg(reinterpret_cast<const float4*>(xg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
+                    float* dst = xb + r * kXsStride + c;
+                    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+                }
+            } else {
+                for (int i = etid; i < kRows * d; i += kEpiThreads) {
+                    const int r = i / d, c = i - r * d;
+                    xb[r * kXsStride + c] = (i < n) ? __ldg(xg + i) : 0.f;
+                }
+            }
+            if (etid < kRows) t_s[(it & 1) * kRows + etid] = (A.t != nullptr && etid < nrows) ? __ldg(A.t + row0 + etid) : 0.f;
+            named_bar_sync(1, kEpiThreads);
+        };
+        // A1 of tile `it`: 8 of the 32 conditioning columns of this row (column group g), three bf16 parts
+        auto split_a1 = [&](int it) {
+            const float* xr = xs + (it & 1) * (kPipeXsBytes / 4) + row * kXsStride;
+            const uint32_t off = (uint32_t)(row >> 3) * 512 + (uint32_t)(row & 7) * 16 + (uint32_t)g * 128;
+            constexpr uint32_t a_part = (uint32_t)kRows * kK1 * 2;
+            __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int k = g * 8 + u;
+                const float v = (k < n_cond) ? xr[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[(it & 1) * kRows + row] : 0.f);
+                split_bf16x3(v, q0[u], q1[u], q2[u]);
+            }
+            *reinterpret_cast<uint4*>(a1buf + off) = *reinterpret_cast<const uint4*>(q0);
+            *reinterpret_cast<uint4*>(a1buf + a_part + off) = *reinterpret_cast<const uint4*>(q1);
+            *reinterpret_cast<uint4*>(a1buf + 2 * a_part + off) = *reinterpret_cast<const uint4*>(q2);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars->a1_ready);
+        };
+
+        if (my_tiles > 0) {
+            stage_x(0);
+            split_a1(0);       // the A1 buffer is free: nothing has been issued yet
+        }
+        TPROF(0)
         for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
             const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * kRows;
             const int nrows = (int)min((long long)kRows, A.rows - row0);
-            {   // ---- stage x -----------------------------------------------------------------------------------------
-                const float* xg = A.x + row0 * d;
-                const int n = nrows * d;
-                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0)) {
-                    const int n4 = (kRows * d) >> 2;
-                    for (int i = etid; i < n4; i += kEpiThreads) {
-                        const float4 v = (i * 4 < n) ? __ldg(reinterpret_cast<const float4*>(xg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
-                        float* dst = xs + r * kXsStride + c;
-                        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-                    }
-                } else {
-                    for (int i = etid; i < kRows * d; i += kEpiThreads) {
-                        const int r = i / d, c = i - r * d;
-                        xs[r * kXsStride + c] = (i < n) ? __ldg(xg + i) : 0.f;
-                    }
-                }
-                if (etid < kRows) t_s[etid] = (A.t != nullptr && etid < nrows) ? __ldg(A.t + row0 + etid) : 0.f;
-            }
-            named_bar_sync(1, kEpiThreads);
-            {   // ---- A1: 8 of the 32 conditioning columns of this row (column group g), three bf16 parts -----------------
-                const uint32_t off = (uint32_t)(row >> 3) * 512 + (uint32_t)(row & 7) * 16 + (uint32_t)g * 128;
-                constexpr uint32_t a_part = (uint32_t)kRows * kK1 * 2;
-                __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int k = g * 8 + u;
-                    const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[row] : 0.f);
-                    split_bf16x3(v, q0[u], q1[u], q2[u]);
-                }
-                *reinterpret_cast<uint4*>(a1buf + off) = *reinterpret_cast<const uint4*>(q0);
-                *reinterpret_cast<uint4*>(a1buf + a_part + off) = *reinterpret_cast<const uint4*>(q1);
-                *reinterpret_cast<uint4*>(a1buf + 2 * a_part + off) = *reinterpret_cast<const uint4*>(q2);
-                tc_fence_before();
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bars->a1_ready);
-            }
+            float* xrow = xs + (it & 1) * (kPipeXsBytes / 4) + row * kXsStride;
+            const bool more = it + 1 < my_tiles;
             // ---- hidden layer 1 in place, wave by wave: the next GEMM runs behind ---------------------------------------------
-            mbar_wait_sleep(&bars->acc1_full, tp, 64);
+            mbar_wait_sleep(&bars->acc1_full, tp, 32);       // GEMM1(it) done: the A1 buffer is free as well
             tc_fence_after();
+            TPROF(2)
             for (int j = 0; j < nw; ++j) {
                 pipe_activate16(tmem + lane_sel, g * cq + 16 * j, 1.f, b1s, act);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bars->wave1[j]);
             }
+            TPROF(3)
+            if (more) {                                      // while the next GEMM's last K blocks drain
+                stage_x(it + 1);
+                TPROF(0)
+            }
             if (n_hidden == 2) {
-                mbar_wait_sleep(&bars->acc2_full, tp, 64);
+                mbar_wait_sleep(&bars->acc2_full, tp, 32);
                 tc_fence_after();
+                TPROF(4)
                 for (int j = 0; j < nw; ++j) {
                     pipe_activate16(tmem + lane_sel + 256, g * cq + 16 * j, s_mid, b2s, act);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bars->wave2[j]);
                 }
+                TPROF(5)
             }
+            if (more) split_a1(it + 1);                      // the A1 buffer is free since acc1_full; GEMM3's last blocks drain
+            TPROF(1)
             // ---- output layer: [log_scale | shift] of this warp's 8 transformed dims (one accumulator) ------------------
-            mbar_wait_sleep(&bars->acc3_full, tp, 64);
+            mbar_wait_sleep(&bars->acc3_full, tp, 32);
             tc_fence_after();
+            TPROF(6)
             float ld_acc = 0.f;
-            if (g * 8 < n_tr) {
+            {
                 float lm[8], sm[8];
-                tmem_ld8(tmem + lane_sel + col_d3 + g * 8, lm);
-                tmem_ld8(tmem + lane_sel + col_d3 + kMaxTr + g * 8, sm);
-                tmem_ld_wait();
+                if (g * 8 < n_tr) {
+                    tmem_ld8(tmem + lane_sel + col_d3 + g * 8, lm);
+                    tmem_ld8(tmem + lane_sel + col_d3 + kMaxTr + g * 8, sm);
+                    tmem_ld_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->d3_read);   // GEMM1 of the next tile may overwrite the accumulator
+                if (g * 8 < n_tr) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int ji = g * 8 + u;
-                    if (ji < n_tr) {
-                        const int j = hdr->tr_idx[ji];
-                        float ls = fmaf(lm[u], s_out, b3s[ji]);
-                        float sh = fmaf(sm[u], s_out, b3s[kMaxTr + ji]);
-                        if (hdr->cont) {                       // coupling.py:199-205
-                            const float tv = t_s[row];
-                            ls *= hdr->ts_ls[ji] * tv;
-                            sh *= hdr->ts_sh[ji] * tv;
+                    for (int u = 0; u < 8; ++u) {
+                        const int ji = g * 8 + u;
+                        if (ji < n_tr) {
+                            const int j = hdr->tr_idx[ji];
+                            float ls = fmaf(lm[u], s_out, b3s[ji]);
+                            float sh = fmaf(sm[u], s_out, b3s[kMaxTr + ji]);
+                            if (hdr->cont) {                       // coupling.py:199-205
+                                const float tv = t_s[(it & 1) * kRows + row];
+                                ls *= hdr->ts_ls[ji] * tv;
+                                sh *= hdr->ts_sh[ji] * tv;
+                            }
+                            const float xv = xrow[j];
+                            if (inverse) { xrow[j] = (xv - sh) * exp_fast(-ls); ld_acc -= ls; }
+                            else { xrow[j] = xv * exp_fast(ls) + sh; ld_acc += ls; }
                         }
-                        const float xv = xrow[j];
-                        if (inverse) { xrow[j] = (xv - sh) * exp_fast(-ls); ld_acc -= ls; }
-                        else { xrow[j] = xv * exp_fast(ls) + sh; ld_acc += ls; }
                     }
                 }
             }
-            tc_fence_before();
             ld_s[g * kRows + row] = ld_acc;
             named_bar_sync(1, kEpiThreads);
             if (g == 0 && want_ld && row < nrows) {
@@ -818,24 +877,27 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args
                 *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
             }
             if (A.y != nullptr) {
+                const float* xb = xs + (it & 1) * (kPipeXsBytes / 4);
                 float* yg = A.y + row0 * d;
                 const int n = nrows * d;
                 if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
                     const int n4 = n >> 2;
                     for (int i = etid; i < n4; i += kEpiThreads) {
                         const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
-                        const float* src = xs + r * kXsStride + c;
+                        const float* src = xb + r * kXsStride + c;
                         reinterpret_cast<float4*>(yg)[i] = make_float4(src[0], src[1], src[2], src[3]);
                     }
                 } else {
                     for (int i = etid; i < n; i += kEpiThreads) {
                         const int r = i / d, c = i - r * d;
-                        yg[i] = xs[r * kXsStride + c];
+                        yg[i] = xb[r * kXsStride + c];
                     }
                 }
             }
-            named_bar_sync(1, kEpiThreads);
+            named_bar_sync(1, kEpiThreads);      // ld_s, and this xs buffer (staged again two tiles on), are free
+            TPROF(7)
         }
+        TPROF_FLUSH
     }
     tc_fence_before();
     __syncthreads();
@@ -854,17 +916,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args
 // with its own tile, barriers, A-operand buffer, issuer warp, eight epilogue warps and 128 TMEM columns --
 // that share the resident weights and fill each other's waits (the per-layer kernel gets the same effect from
 // two CTAs per SM, which cannot share the weights).
-// per-warp phase clocks of the chain kernel (profiling builds: -DSTB_TCM_PROF, tools/tcm_phase_prof.py)
-#ifdef STB_TCM_PROF
-__device__ unsigned int g_tcm_prof[160 * 32 * 8];
-#define TPROF_DECL unsigned int _pt = clock(), _pa[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define TPROF(i) { const unsigned int _n = clock(); _pa[i] += _n - _pt; _pt = _n; }
-#define TPROF_FLUSH { if ((threadIdx.x & 31) == 0) for (int _i = 0; _i < 8; ++_i) g_tcm_prof[(blockIdx.x * 32 + (threadIdx.x >> 5)) * 8 + _i] = _pa[_i]; }
-#else
-#define TPROF_DECL
-#define TPROF(i)
-#define TPROF_FLUSH
-#endif
 
 constexpr int kMaxChainM = 8;
 constexpr int kVcThreads = 384;            // per virtual CTA: producer, issuer, 8 epilogue warps, 2 idle (register budget)

@@ -14,7 +14,8 @@ from stribor_b200 import _lib
 from stribor_b200.spec import layers_from_spec
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-case = cases._mk_flow('quadratic', 64, [64], 1, 16, 16, 7, masks=cases.ALT, lower=-4., upper=4., scale=1.0)()
+NL = int(os.environ.get('L', '1'))
+case = cases._mk_flow('quadratic', 64, [64], NL, 16, 16, 7, masks=cases.ALT, lower=-4., upper=4., scale=1.0)()
 layers = [l.to('cuda') for l in layers_from_spec(case['spec'])]
 flow = st.NormalizingFlow(st.UnitNormal(64), layers)
 x = torch.randn(rows, 64, device='cuda')
@@ -27,7 +28,7 @@ e0.record()
 with torch.no_grad():
     lp = flow.log_prob(x)
 e1.record(); torch.cuda.synchronize()
-print(f'one layer, {rows} rows: {e0.elapsed_time(e1):.3f} ms')
+print(f'{NL} layer(s), {rows} rows: {e0.elapsed_time(e1):.3f} ms')
 n = 160 * 32 * 8
 buf = (ctypes.c_uint32 * n)()
 lib = _lib.lib()
@@ -40,11 +41,13 @@ else:
   names_e = ['tile head', 'wait acc_full', 'locate(ld..release)', 'finish', 'tile tail', 'chunk-loop overhead']
 names_i = ['wait a1_ready', 'issue GEMM1', 'wait b_full', 'wait h_ready', 'wait acc_empty', 'issue GEMM2+commit']
 blocks = a[:148]
+tl = rows / 256 / 148 * NL
+print(f'tile-layers per CTA: {tl:.1f}')
 tot = blocks[:, 3:nw, :6].sum(-1).mean()
 print('epilogue warps: mean total clocks', tot)
 for i, nm in enumerate(names_e):
     v = blocks[:, 3:nw, i]
-    print(f'  {nm:24s} mean {v.mean():12.0f} ({100 * v.mean() / tot:5.1f} %)  min {v.min():10.0f} max {v.max():10.0f}')
+    print(f'  {nm:24s} mean {v.mean():12.0f} ({100 * v.mean() / tot:5.1f} %)  min {v.min():10.0f} max {v.max():10.0f}  per tile-layer {v.mean() / tl:8.0f}')
 for w in (1, 2):
     tot = blocks[:, w, :6].sum(-1).mean()
     print(f'issuer warp {w}: total {tot:.0f}')
