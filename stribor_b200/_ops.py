@@ -494,10 +494,9 @@ layer_apply.register_autograd(_backward, setup_context=_setup_ctx)
 CHAIN_FORWARD, CHAIN_INVERSE, CHAIN_LOG_PROB, CHAIN_LOG_PROB_ONLY = 0, 1, 2, 3
 
 
-@torch.library.custom_op('stribor_b200::flow_chain', mutates_args=(), device_types='cuda')
-def flow_chain(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], masks: List[Tensor],
-               params: List[Tensor], packed: List[Tensor], meta: List[int], fmeta: List[float],
-               mode: int, want_ldj: bool) -> Tuple[Tensor, Tensor]:
+def flow_chain_direct(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], masks: List[Tensor],
+                      params: List[Tensor], packed: List[Tensor], meta: List[int], fmeta: List[float],
+                      mode: int, want_ldj: bool) -> Tuple[Tensor, Tensor]:
     """mode FORWARD/INVERSE: (out [rows,dim], ldj [rows] or empty);
     mode LOG_PROB: (latent x [rows,dim], log_prob [rows])."""
     rows, dim = x.shape
@@ -534,6 +533,12 @@ def flow_chain(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], masks: 
     if mode == CHAIN_LOG_PROB_ONLY and not skip_x:
         out = x.new_empty(0, dim)                  # the scratch was needed (several launches) but is not returned
     return out, ldj
+
+
+# The registered op is what torch.compile / the dispatcher see; eager callers (flow.run_chain) call
+# flow_chain_direct: the chain path never needs autograd, and the dispatcher round trip costs more host time than a
+# small batch spends on the GPU (tools/host_overhead.py).
+flow_chain = torch.library.custom_op('stribor_b200::flow_chain', mutates_args=(), device_types='cuda')(flow_chain_direct)
 
 
 @flow_chain.register_fake

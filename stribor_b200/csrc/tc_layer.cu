@@ -641,6 +641,406 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
 }
 
 // -----------------------------------------------------------------------------------------------
+// the whole-flow kernel as TWO independent CTAs per SM: tc_spline_pair_kernel
+// -----------------------------------------------------------------------------------------------
+// Same layers, same arithmetic, same packed image and the same bits out as the CHAIN kernel above, reorganised around
+// what its phase clocks show (tools/tc_phase_prof.py, 8 layers): per 256-row tile and layer the 16 epilogue warps spend
+// 8.5 k of 46.8 k clocks in the layer HEAD (A1 split -> GEMM1 -> tanh -> first chunk) with the tensor pipe idle, and the
+// issuers 26 % of theirs waiting for accumulator buffers.  One CTA cannot overlap a layer's head with anything: the next
+// layer needs every output of this one.  Two CTAs per SM, each with its own 128-row tile, do -- their heads fall into
+// each other's chunk phases.  To fit twice (114.7 KB of shared memory, 256 TMEM columns, 320 threads x 96 registers per
+// CTA) the A operands leave shared memory:
+//   * GEMM1's A operand (the row's conditioning columns as three bf16 parts, 48 columns) is written with tcgen05.st
+//     into the columns of accumulator buffer 1, which is idle between two layers, and read from there by TMEM-sourced
+//     UMMAs (the first chunk that lands in that buffer is issued after GEMM1 and executes after it);
+//   * the hidden activations go back into GEMM1's accumulator columns in place (fp16 hi at +0, lo at +8 of every
+//     16-column block) and GEMM2 reads them from there: no shared-memory A buffer, no proxy fence in the layer head.
+// Each CTA streams its own copy of the weight chunks (2 x 404 KB per 256 rows and layer, ~40 % of the L2 slices' rate).
+constexpr int kPRows = 128;
+constexpr int kPEpiWarp0 = 2;                                // warp 0 producer, warp 1 issuer
+constexpr int kPEpiWarps = 8;                                // (TMEM sub-partition q, half r3): two per scheduler
+constexpr int kPThreads = (kPEpiWarp0 + kPEpiWarps) * 32;
+constexpr int kPEpiThreads = kPEpiWarps * 32;
+constexpr uint32_t kPSmXs = 0;                                          // float [128][65]; column 64 carries log-det partials
+constexpr uint32_t kPSmB = kPRows * kXsStride * 4;
+constexpr uint32_t kPSmSmall = kPSmB + kStages * kChunkBytes;
+constexpr uint32_t kPSmBar = (kPSmSmall + kSmallBytes + 15) & ~15u;
+constexpr uint32_t kPSmemBytes = kPSmBar + 256;
+static_assert(kPSmB % 128 == 0 && kPSmSmall % 16 == 0, "alignment");
+static_assert(2 * (kPSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM");
+struct PBars {
+    uint64_t acc_full[2], acc_empty[2];
+    uint64_t b_full[kStages], b_empty[kStages];
+    uint64_t a1_ready, acc1_full, h_ready;
+    uint32_t tmem_base;
+};
+static_assert(sizeof(PBars) <= 256, "barrier block");
+constexpr uint32_t kPColH = 0;                               // GEMM1 accumulator, then h in place
+constexpr uint32_t kPColAcc = kHid;                          // + buf * 96
+constexpr uint32_t kPColA1 = kPColAcc + kChunkN;             // inside buffer 1: part pa at + pa * 16, K step ks at + ks * 8
+constexpr uint32_t kPTmemCols = 256;
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+
+template <int KIND, bool INVERSE>
+__global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args A) {
+    extern __shared__ __align__(128) uint8_t smem_p[];      // (1024 would cost a kilobyte of static padding: 2 CTAs then need all 228 KB)
+    uint8_t* smem = smem_p;
+    float* xs = reinterpret_cast<float*>(smem + kPSmXs);
+    uint8_t* bst = smem + kPSmB;
+    const Header* hdr = reinterpret_cast<const Header*>(smem + kPSmSmall);
+    const float* b1s = reinterpret_cast<const float*>(smem + kPSmSmall + kOffB1);
+    const float* b2s = reinterpret_cast<const float*>(smem + kPSmSmall + kOffB2);
+    PBars* bars = reinterpret_cast<PBars*>(smem + kPSmBar);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->b_full[i], 1); mbar_init(&bars->b_empty[i], 1); }
+        mbar_init(&bars->a1_ready, kPEpiWarps);
+        mbar_init(&bars->acc1_full, 1);
+        mbar_init(&bars->h_ready, kPEpiWarps);
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], kPEpiWarps); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&bars->tmem_base, kPTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    const int n_layers = A.n_layers;
+    const int d = A.dim;
+    const int dshift = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;
+    const int my_tiles = (A.n_tiles > (int)blockIdx.x) ? (A.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        // ======================= producer: per layer the head item, then the last Linear's chunks =======================
+        if (lane == 0) {
+            uint32_t rc = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                if (it + 1 < my_tiles) {
+                    const long long nrow0 = ((long long)blockIdx.x + (long long)(it + 1) * gridDim.x) * kPRows;
+                    const long long nb = min((long long)kPRows, A.rows - nrow0) * d * 4;
+                    const char* src = reinterpret_cast<const char*>(A.x + nrow0 * d);
+                    if (nb >= 16 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(nb & ~15LL)) : "memory");
+                }
+                for (int l = 0; l < n_layers; ++l) {
+                    const uint8_t* img = A.chain_packed[l];
+                    const int nch = A.n_chunks_l[l];
+                    for (int c = -1; c < nch; ++c, ++rc) {
+                        const uint32_t st = rc % kStages, use = rc / kStages;
+                        MBAR_WAIT_SLOW(&bars->b_empty[st], (use & 1) ^ 1);
+                        const uint32_t bytes = (c < 0) ? kHeadBytes : kChunkBytes;
+                        mbar_arrive_expect_tx(&bars->b_full[st], bytes);
+                        bulk_g2s(bst + st * kChunkBytes, (c < 0) ? img : img + kOffW2 + (size_t)c * kChunkBytes, bytes, &bars->b_full[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= UMMA issuer: both A operands come from TMEM ============================================
+        if (lane == 0) {
+            const uint32_t idesc1 = make_idesc(FMT_BF16, 128, kHid);
+            const uint32_t idesc2 = make_idesc(FMT_F16, 128, kChunkN);
+            uint32_t cc = 0, rc = 0, hp = 0;
+            for (int it = 0; it < my_tiles; ++it)
+            for (int l = 0; l < n_layers; ++l, ++hp) {
+                const uint32_t tpar = hp & 1;
+                const int nch = A.n_chunks_l[l];
+                {
+                    const uint32_t hst = rc % kStages;
+                    MBAR_WAIT_SLOW(&bars->b_full[hst], (rc / kStages) & 1);
+                    const uint32_t b0 = smem_u32(bst + hst * kChunkBytes) + kOffW1;
+                    MBAR_WAIT_SLOW(&bars->a1_ready, tpar);
+                    tc_fence_after();
+                    uint32_t acc = 0;
+                    // the same eight partial products in the same order as the kernel above (smallest first)
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const int pa = (p == 0 || p == 3 || p == 6) ? 1 : ((p == 1 || p == 4) ? 2 : 0);
+                        const int pb = (p == 0 || p == 2) ? 2 : ((p == 1 || p == 3 || p == 5) ? 1 : 0);
+#pragma unroll
+                        for (int ks = 0; ks < kK1 / 16; ++ks) {
+                            umma_f16_ts(tmem + kPColH, tmem + kPColA1 + pa * 16 + ks * 8,
+                                        make_smem_desc(b0 + pb * kW1Part + ks * 256, 128, 512), idesc1, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&bars->acc1_full);
+                    umma_commit(&bars->b_empty[hst]);
+                    ++rc;
+                }
+                for (int c = 0; c < nch; ++c, ++cc, ++rc) {
+                    const uint32_t st = rc % kStages, use = rc / kStages;
+                    MBAR_WAIT_SLOW(&bars->b_full[st], use & 1);
+                    const uint32_t buf = cc & 1, buse = cc >> 1;
+                    if (c == 0) MBAR_WAIT_SLOW(&bars->h_ready, tpar);
+                    MBAR_WAIT_SLOW(&bars->acc_empty[buf], (buse & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t b_hi = smem_u32(bst + st * kChunkBytes), b_lo = b_hi + 12288;
+                    const uint32_t dcol = tmem + kPColAcc + buf * kChunkN;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {                  // lo*hi, hi*lo, hi*hi
+                        const uint32_t a_off = (p == 0) ? 8u : 0u, bb = (p == 1) ? b_lo : b_hi;
+#pragma unroll
+                        for (int ks = 0; ks < kHid / 16; ++ks) {
+                            umma_f16_ts(dcol, tmem + kPColH + ks * 16 + a_off, make_smem_desc(bb + ks * 256, 128, 1024), idesc2, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&bars->acc_full[buf]);
+                    umma_commit(&bars->b_empty[st]);
+                }
+            }
+        }
+    } else {
+        // ======================= epilogue warps: (q, r3), thread = row ======================================================
+        const int q = warp & 3;
+        const int r3 = (warp - kPEpiWarp0) >> 2;
+        const int etid = tid - kPEpiWarp0 * 32;
+        const int rt = q * 32 + lane;
+        float* xrow = xs + rt * kXsStride;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        const bool want_ld = A.ldj_mode != STB_LDJ_NONE;
+        const uint32_t full_bar = pin(smem_u32(&bars->acc_full[0]));
+        const uint32_t empty_bar = pin(smem_u32(&bars->acc_empty[0]));
+        const uint32_t col_base = pin(tmem + lane_sel + kPColAcc);
+        const uint32_t tr_idx_a = pin(smem_u32(&hdr->tr_idx[0]));
+        const uint32_t xrow_a = pin(smem_u32(xrow));
+        uint32_t cc = 0, rc = 0, hp = 0;
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+            const long long row0 = tile * kPRows;
+            const int nrows = (int)min((long long)kPRows, A.rows - row0);
+            {   // ---- stage the x tile ---------------------------------------------------------------------------
+                const float* xg = A.x + row0 * d;
+                const int n = nrows * d;
+                if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(xg) & 15) == 0)) {
+                    const int n4 = (kPRows * d) >> 2;
+                    for (int i0 = etid; i0 < n4; i0 += kPEpiThreads * 4) {
+                        float4 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * kPEpiThreads;
+                            v[u] = (i < n4 && i * 4 < n) ? __ldg(reinterpret_cast<const float4*>(xg) + i)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u * kPEpiThreads;
+                            if (i < n4) {
+                                const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
+                                float* dst = xs + r * kXsStride + c;
+                                dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;
+                            }
+                        }
+                    }
+                } else {
+                    for (int i = etid; i < kPRows * d; i += kPEpiThreads) {
+                        const int r = i / d, c = i - r * d;
+                        xs[r * kXsStride + c] = (i < n) ? __ldg(xg + i) : 0.f;
+                    }
+                }
+            }
+            named_bar_sync(1, kPEpiThreads);
+            float ld_acc = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < n_layers; ++l, ++hp) {
+                const uint32_t tpar = hp & 1;
+                {   // this layer's header + biases out of its ring stage (the first Linear stays there for GEMM1)
+                    const uint32_t hst = rc % kStages;
+                    mbar_wait(&bars->b_full[hst], (rc / kStages) & 1);
+                    const uint4* src = reinterpret_cast<const uint4*>(bst + hst * kChunkBytes);
+                    uint4* dst = reinterpret_cast<uint4*>(smem + kPSmSmall);
+                    for (int i = etid; i < (int)(kSmallBytes / 16); i += kPEpiThreads) dst[i] = src[i];
+                    named_bar_sync(1, kPEpiThreads);
+                    if (A.permuted) {
+                        Header* h = const_cast<Header*>(hdr);
+                        if (etid < kK1) h->cond_idx[etid] = A.perm.phys[l][h->cond_idx[etid]];
+                        else if (etid < kK1 + kMaxTr) h->tr_idx[etid - kK1] = A.perm.phys[l][h->tr_idx[etid - kK1]];
+                        named_bar_sync(1, kPEpiThreads);
+                    }
+                }
+                const int n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_chunks = hdr->n_chunks, act = hdr->act;
+                const float s2 = hdr->s2, s2l = s2 * 1.4426950408889634f;
+                const uint32_t noshift_mask = hdr->noshift_mask;
+                float lo = A.lower_l[l], hi = A.upper_l[l], inv_span = 1.f / (hi - lo);
+                asm volatile("" : "+f"(lo), "+f"(hi), "+f"(inv_span));
+                rc += 1u + (uint32_t)n_chunks;
+
+                // ---- A1 into TMEM: this warp's two 8-column groups of the row's conditioning columns, three bf16 parts ----
+#pragma unroll 1
+                for (int kc = r3; kc < kK1 / 8; kc += 2) {
+                    __align__(16) __nv_bfloat16 q0[8], q1[8], q2[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = kc * 8 + u;
+                        const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : 0.f;
+                        split_bf16x3(v, q0[u], q1[u], q2[u]);
+                    }
+                    const uint32_t col = tmem + lane_sel + kPColA1 + (uint32_t)(kc >> 1) * 8 + (uint32_t)(kc & 1) * 4;
+                    tmem_st4(col, reinterpret_cast<const uint32_t*>(q0));
+                    tmem_st4(col + 16, reinterpret_cast<const uint32_t*>(q1));
+                    tmem_st4(col + 32, reinterpret_cast<const uint32_t*>(q2));
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a1_ready);
+                // ---- hidden layer in place: this warp's 32 of the 64 units ----------------------------------------------------
+                mbar_wait(&bars->acc1_full, tpar);
+                tc_fence_after();
+#pragma unroll 1
+                for (int blk = 0; blk < 2; ++blk) {
+                    const int c0 = r3 * 32 + blk * 16;
+                    float v[16];
+                    tmem_ld16(tmem + lane_sel + kPColH + c0, v);
+                    tmem_ld_wait();
+                    uint32_t hh[8], hl[8];
+                    if (act == STB_ACT_TANH) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            split_f16x2_sat(tanh_fast(v[2 * i] + b1s[c0 + 2 * i]), tanh_fast(v[2 * i + 1] + b1s[c0 + 2 * i + 1]), hh[i], hl[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            split_f16x2_sat(sigmoid_act(v[2 * i] + b1s[c0 + 2 * i]), sigmoid_act(v[2 * i + 1] + b1s[c0 + 2 * i + 1]), hh[i], hl[i]);
+                    }
+                    tmem_st8(tmem + lane_sel + kPColH + c0, hh);
+                    tmem_st8(tmem + lane_sel + kPColH + c0 + 8, hl);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->h_ready);
+
+                // ---- last Linear chunks out of TMEM + spline in registers: this warp's dim of each chunk (as above) ----
+#pragma unroll 1
+                for (int ji = r3; ji < kG * n_chunks; ji += 2) {
+                    const uint32_t ccc = cc + (uint32_t)(ji >> 1);
+                    const uint32_t buf = ccc & 1, buse = ccc >> 1;
+                    const int g = ji & 1;
+                    uint32_t j4;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(j4) : "r"(tr_idx_a + 4u * (uint32_t)(ji < n_tr ? ji : 0)));
+                    j4 <<= 2;
+                    float xv;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv) : "r"(xrow_a + j4));
+                    const bool inside = (ji < n_tr) && (xv >= lo) && (xv <= hi);
+                    const float* bb = b2s + ji * kPPad;
+                    mbar_wait_a(full_bar + buf * 8, buse & 1);
+                    tc_fence_after();
+                    const uint32_t col0 = col_base + buf * kChunkN + (uint32_t)g * kPPad;
+                    float out = xv, ld = 0.f;
+                    const bool shift = !((noshift_mask >> (ji & 31)) & 1u);
+                    const float2* bb2 = reinterpret_cast<const float2*>(bb);
+                    if (KIND == STB_RQS) {
+                        RqsLoc loc;
+                        {
+                            float2 t[kBins];
+                            tmem_ld16(col0, reinterpret_cast<float*>(t));
+                            tmem_ld16(col0 + 16, reinterpret_cast<float*>(t) + 16);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
+                            loc = rqs16_locate<INVERSE>(t, shift, lo, inv_span, xv);
+                        }
+                        float dd[16];
+                        tmem_ld16(col0 + 2 * kBins, dd);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_a(empty_bar + buf * 8);
+                        if (inside) {
+                            float r0, r1;
+                            pick_pair16(dd, loc.k, r0, r1);
+                            const float u0 = (loc.k == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + loc.k - 1]);
+                            const float u1 = (loc.k == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
+                            rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
+                        }
+                    } else {
+                        const float span = hi - lo;
+                        const float u = (xv - lo) / span;
+                        CubSel sel;
+                        {
+                            float2 t[kBins];
+                            tmem_ld16(col0, reinterpret_cast<float*>(t));
+                            tmem_ld16(col0 + 16, reinterpret_cast<float*>(t) + 16);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
+                            sel = cubic16_locate<INVERSE>(t, shift, u);
+                        }
+                        float dd[8];
+                        tmem_ld8(col0 + 2 * kBins, dd);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_a(empty_bar + buf * 8);
+                        if (inside) {
+                            const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
+                            cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);
+                        }
+                    }
+                    if (ji < n_tr) asm volatile("st.shared.f32 [%0], %1;" ::"r"(xrow_a + j4), "f"(out) : "memory");
+                    ld_acc += ld;
+                }
+                cc += (uint32_t)n_chunks;
+                // next layer: every warp's outputs are in the tile, nobody reads this layer's biases or its accumulators
+                if (l + 1 < n_layers) named_bar_sync(1, kPEpiThreads);
+            }   // layers
+
+            // ---- per-row log|det J| (+ UnitNormal log-density of the output row): fixed summation order ------------------
+            if (r3 == 0) xrow[kMaxDim] = ld_acc;
+            named_bar_sync(1, kPEpiThreads);
+            if (r3 == 1 && want_ld && rt < nrows) {
+                float tot = xrow[kMaxDim];
+                tot += ld_acc;
+                if (A.base_log_prob) {
+                    float b = 0.f;
+                    for (int c = 0; c < d; ++c) { const float v = xrow[c]; b += -0.5f * v * v - 0.91893853320467274178f; }
+                    tot += b;
+                }
+                float* dst = A.ldj + row0 + rt;
+                *dst = (A.ldj_mode == STB_LDJ_ADD) ? (*dst + tot) : tot;
+            }
+            if (A.y != nullptr) {
+                float* yg = A.y + row0 * d;
+                const int n = nrows * d;
+                if (A.permuted) {
+                    for (int i = etid; i < n; i += kPEpiThreads) {
+                        const int r = (dshift >= 0) ? (i >> dshift) : i / d, c = i - r * d;
+                        yg[i] = xs[r * kXsStride + A.perm.out_phys[c]];
+                    }
+                } else if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(yg) & 15) == 0)) {
+                    const int n4 = n >> 2;
+                    for (int i = etid; i < n4; i += kPEpiThreads) {
+                        const int r = (dshift >= 0) ? ((i * 4) >> dshift) : (i * 4) / d, c = (i * 4) - r * d;
+                        const float* src = xs + r * kXsStride + c;
+                        reinterpret_cast<float4*>(yg)[i] = make_float4(src[0], src[1], src[2], src[3]);
+                    }
+                } else {
+                    for (int i = etid; i < n; i += kPEpiThreads) {
+                        const int r = i / d, c = i - r * d;
+                        yg[i] = xs[r * kXsStride + c];
+                    }
+                }
+            }
+            named_bar_sync(1, kPEpiThreads);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, kPTmemCols);
+}
+
+// -----------------------------------------------------------------------------------------------
 // packing
 // -----------------------------------------------------------------------------------------------
 struct PackArgs {
@@ -890,6 +1290,29 @@ int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const f
         if (n_sm <= 0) n_sm = 148;
     }
     void (*kern)(Args);
+    // Two independent 128-row CTAs per SM instead of one 256-row CTA.  Measured on the headline workload (2^22 rows):
+    // 1.73e8 vs 1.77e8 samples/s -- the heads do fall into the other CTA's chunk phases, but the kernel is bound by
+    // the epilogue's instruction stream, not by that bubble, so nothing is gained; it IS faster when there are fewer
+    // 256-row tiles than SMs (twice as many CTAs to spread over the machine), which is when it is selected.
+    // STRIBOR_B200_PAIR=1 / 0 forces / forbids it.
+    static const int pair_env = [] { const char* ev = getenv("STRIBOR_B200_PAIR"); return (ev && ev[0]) ? (ev[0] == '1' ? 1 : 0) : -1; }();
+    const bool use_pair = pair_env >= 0 ? pair_env == 1 : tiles < (long long)n_sm;
+    if (use_pair) {
+        if (layers[0]->kind == STB_RQS) kern = A.inverse ? tc_spline_pair_kernel<STB_RQS, true> : tc_spline_pair_kernel<STB_RQS, false>;
+        else kern = A.inverse ? tc_spline_pair_kernel<STB_CUBIC, true> : tc_spline_pair_kernel<STB_CUBIC, false>;
+        const long long ptiles = (rows + kPRows - 1) / kPRows;
+        if (ptiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
+        A.n_tiles = (int)ptiles;
+        cudaError_t pe = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmemBytes);
+        if (pe == cudaSuccess) pe = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (pe != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(pe));
+        const int pgrid = (int)min((long long)2 * n_sm, ptiles);
+        kern<<<pgrid, kPThreads, kPSmemBytes, stream>>>(A);
+        count_launch();
+        pe = cudaGetLastError();
+        if (pe != cudaSuccess) return set_error(STB_ECUDA, "tc_spline_pair_kernel launch: %s", cudaGetErrorString(pe));
+        return STB_OK;
+    }
     if (layers[0]->kind == STB_RQS) kern = A.inverse ? tc_spline_layer_kernel<STB_RQS, true, true> : tc_spline_layer_kernel<STB_RQS, false, true>;
     else kern = A.inverse ? tc_spline_layer_kernel<STB_CUBIC, true, true> : tc_spline_layer_kernel<STB_CUBIC, false, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);

@@ -126,8 +126,8 @@ def run_chain(transforms, mode, x, latent=None, t=None, want_ldj=False):
         packed.append(d['packed'] if d.get('packed') is not None else x.new_empty(0, dtype=torch.uint8))
         meta += d['meta']
         fmeta += d['fmeta']
-    out, vec = _ops.flow_chain(x.reshape(-1, dim).contiguous(), latent, t,
-                               masks, params, packed, meta, fmeta, mode, want_ldj)
+    chain = _ops.flow_chain if torch.compiler.is_compiling() else _ops.flow_chain_direct
+    out, vec = chain(x.reshape(-1, dim).contiguous(), latent, t, masks, params, packed, meta, fmeta, mode, want_ldj)
     out = out.view(*lead, dim) if out.shape[0] == x.numel() // dim else None      # LOG_PROB_ONLY: no latent rows
     if want_ldj or mode in (_ops.CHAIN_LOG_PROB, _ops.CHAIN_LOG_PROB_ONLY):
         return out, vec.view(*lead, 1)
