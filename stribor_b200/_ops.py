@@ -494,17 +494,10 @@ layer_apply.register_autograd(_backward, setup_context=_setup_ctx)
 CHAIN_FORWARD, CHAIN_INVERSE, CHAIN_LOG_PROB, CHAIN_LOG_PROB_ONLY = 0, 1, 2, 3
 
 
-def flow_chain_direct(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], masks: List[Tensor],
-                      params: List[Tensor], packed: List[Tensor], meta: List[int], fmeta: List[float],
-                      mode: int, want_ldj: bool) -> Tuple[Tensor, Tensor]:
-    """mode FORWARD/INVERSE: (out [rows,dim], ldj [rows] or empty);
-    mode LOG_PROB: (latent x [rows,dim], log_prob [rows])."""
-    rows, dim = x.shape
+def build_layer_array(masks: List[Tensor], params: List[Tensor], packed: List[Tensor], meta: List[int],
+                      fmeta: List[float]):
+    """-> (ctypes array of stb_layer, objects that must outlive it)."""
     n_layers = len(masks)
-    need_vec = want_ldj or mode in (CHAIN_LOG_PROB, CHAIN_LOG_PROB_ONLY)
-    ldj = torch.empty(rows if need_vec else 0, dtype=x.dtype, device=x.device)
-    if rows == 0:
-        return torch.empty_like(x), ldj
     arr = (_lib.StbLayer * n_layers)()
     keep = []
     mo = po = 0
@@ -516,6 +509,17 @@ def flow_chain_direct(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], 
                                  params[po:po + npar], packed[i]))
         mo += ml
         po += npar
+    return arr, keep
+
+
+def flow_chain_launch(arr, n_layers: int, x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mode: int,
+                      want_ldj: bool) -> Tuple[Tensor, Tensor]:
+    """One C call over a prepared layer array (see ``flow_chain_direct`` for the modes)."""
+    rows, dim = x.shape
+    need_vec = want_ldj or mode in (CHAIN_LOG_PROB, CHAIN_LOG_PROB_ONLY)
+    ldj = torch.empty(rows if need_vec else 0, dtype=x.dtype, device=x.device)
+    if rows == 0:
+        return torch.empty_like(x), ldj
     lib = _lib.lib()
     # log_prob without the latent rows: when the whole flow is one chained launch nothing has to be written back
     # but the log-probabilities (mode LOG_PROB_ONLY returns an empty first tensor)
@@ -535,9 +539,20 @@ def flow_chain_direct(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], 
     return out, ldj
 
 
-# The registered op is what torch.compile / the dispatcher see; eager callers (flow.run_chain) call
-# flow_chain_direct: the chain path never needs autograd, and the dispatcher round trip costs more host time than a
-# small batch spends on the GPU (tools/host_overhead.py).
+def flow_chain_direct(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], masks: List[Tensor],
+                      params: List[Tensor], packed: List[Tensor], meta: List[int], fmeta: List[float],
+                      mode: int, want_ldj: bool) -> Tuple[Tensor, Tensor]:
+    """mode FORWARD/INVERSE: (out [rows,dim], ldj [rows] or empty);
+    mode LOG_PROB: (latent x [rows,dim], log_prob [rows])."""
+    arr, keep = build_layer_array(masks, params, packed, meta, fmeta)
+    out = flow_chain_launch(arr, len(masks), x, latent, t, mode, want_ldj)
+    del keep
+    return out
+
+
+# The registered op is what torch.compile / the dispatcher see; eager callers (flow.run_chain) keep the prepared layer
+# array and call flow_chain_launch: the chain path never needs autograd, and the dispatcher round trip plus the
+# per-call description of every layer cost more host time than a small batch spends on the GPU (tools/host_overhead.py).
 flow_chain = torch.library.custom_op('stribor_b200::flow_chain', mutates_args=(), device_types='cuda')(flow_chain_direct)
 
 

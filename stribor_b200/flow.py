@@ -15,13 +15,16 @@ from typing import List, Optional, Tuple, Union
 import torch
 import torch.nn as nn
 
-from . import _ops
+import os
+import weakref
+
+from . import _epoch, _ops
 from .dist.normal import UnitNormal
 
 __all__ = ['Transform', 'ElementwiseTransform', 'NormalizingFlow', 'NeuralFlow']
 
 
-class Transform(nn.Module, metaclass=ABCMeta):
+class Transform(_epoch.Tracked, nn.Module, metaclass=ABCMeta):
     """flow.py:8-47.  Default pair methods compose forward/inverse with ``log_det_jacobian``:
     the inverse's log-det is MINUS the forward log-det evaluated at the recovered input."""
 
@@ -97,37 +100,103 @@ def run_layer_diag(desc, x, latent, t, direction):
     return y.view(*lead, dim), ld.view(*lead, dim)
 
 
+# ---- cached call plans ---------------------------------------------------------------------------------------
+# Describing a chain (per layer: mask, weight tensors, packed image, wire-format lists, the ctypes stb_layer) costs
+# ~40 us of Python per layer -- more than the GPU spends on a small batch.  The result is kept per ModuleList for as
+# long as (1) the structure epoch (_epoch.py) and (2) every parameter's (data_ptr, _version, requires_grad) stand
+# still; weak keys, so flows stay picklable / deep-copyable and nothing outlives them.
+_records = weakref.WeakKeyDictionary()
+
+
+class _Record:
+    __slots__ = ('epoch', 'plist', 'chainable', 'plans', 'token', 'any_grad')
+
+    def __init__(self, transforms):
+        self.epoch = _epoch.value
+        self.plist = list(transforms.parameters())
+        self.chainable = len(transforms) > 0 and all(hasattr(f, 'chainable') and f.chainable() for f in transforms)
+        self.plans = {}
+        self.token = None
+        self.any_grad = False
+
+    def refresh(self):
+        """Re-read the parameters' state; plans built against an older state are dropped."""
+        token = tuple([(p.data_ptr(), p._version, p.requires_grad) for p in self.plist])
+        if token != self.token:
+            self.token = token
+            self.any_grad = any(k[2] for k in token)
+            self.plans.clear()
+
+
+def _record(transforms) -> _Record:
+    rec = _records.get(transforms)
+    if rec is None or rec.epoch != _epoch.value:
+        rec = _Record(transforms)            # (constructing it may describe layers; it never moves the epoch itself)
+        _records[transforms] = rec
+    rec.refresh()
+    return rec
+
+
 def _chain_ok(transforms, tensors) -> bool:
     """Fused whole-chain path: every layer describable, nothing asks for gradients."""
-    if len(transforms) == 0 or not all(hasattr(f, 'chainable') and f.chainable() for f in transforms):
+    rec = _record(transforms)
+    if not rec.chainable:
         return False                  # foreign modules, un-fused conditioners, set_data couplings:
                                       # layer-by-layer path
     if torch.is_grad_enabled():
-        if any(v is not None and v.requires_grad for v in tensors):
-            return False
-        if any(p.requires_grad for f in transforms for p in f.parameters()):
+        if rec.any_grad or any(v is not None and v.requires_grad for v in tensors):
             return False
     return True
+
+
+class _Plan:
+    __slots__ = ('masks', 'params', 'packed', 'meta', 'fmeta', 'arr', 'keep', 'caches', 'n')
+
+
+def _build_plan(transforms, dim, latent_dim, x, latent, t) -> _Plan:
+    pl = _Plan()
+    pl.masks, pl.params, pl.packed, pl.meta, pl.fmeta, pl.caches = [], [], [], [], [], []
+    for f in transforms:
+        d = f.describe(dim, latent_dim, x.device)
+        _ops.check_layer_tensors(x, latent, t, d['mask'], d['params'], d.get('packed'),
+                                 int_params=d['meta'][0] == _ops._lib.PERMUTE)
+        pl.masks.append(d['mask'] if d['mask'] is not None else x.new_empty(0, dtype=torch.uint8))
+        pl.params += [p.detach() for p in d['params']]
+        pl.packed.append(d['packed'] if d.get('packed') is not None else x.new_empty(0, dtype=torch.uint8))
+        pl.meta += d['meta']
+        pl.fmeta += d['fmeta']
+        if getattr(f, '_packed', None) is not None:
+            pl.caches.append(f._packed)
+    pl.arr, pl.keep = _ops.build_layer_array(pl.masks, pl.params, pl.packed, pl.meta, pl.fmeta)
+    pl.n = len(pl.masks)
+    return pl
 
 
 def run_chain(transforms, mode, x, latent=None, t=None, want_ldj=False):
     _ops._check_cuda(x, 'input')
     lead, dim = x.shape[:-1], x.shape[-1]
     latent_dim = 0 if latent is None else latent.shape[-1]
-    masks, params, packed, meta, fmeta = [], [], [], [], []
-    empty = x.new_empty(0)
     latent, t = _flat(latent, lead), _flat(t, lead)
-    for f in transforms:
-        d = f.describe(dim, latent_dim, x.device)
-        _ops.check_layer_tensors(x, latent, t, d['mask'], d['params'], d.get('packed'),
-                                 int_params=d['meta'][0] == _ops._lib.PERMUTE)
-        masks.append(d['mask'] if d['mask'] is not None else x.new_empty(0, dtype=torch.uint8))
-        params += [p.detach() for p in d['params']]
-        packed.append(d['packed'] if d.get('packed') is not None else x.new_empty(0, dtype=torch.uint8))
-        meta += d['meta']
-        fmeta += d['fmeta']
-    chain = _ops.flow_chain if torch.compiler.is_compiling() else _ops.flow_chain_direct
-    out, vec = chain(x.reshape(-1, dim).contiguous(), latent, t, masks, params, packed, meta, fmeta, mode, want_ldj)
+    rec = _record(transforms)
+    key = (dim, latent_dim, x.device, os.environ.get('STRIBOR_B200_FORCE_GENERIC'))
+    epoch = _epoch.value
+    plan = rec.plans.get(key)
+    if plan is None:
+        plan = _build_plan(transforms, dim, latent_dim, x, latent, t)
+        if _epoch.value == epoch:            # describing a layer for the first time may itself move the epoch
+            rec.plans[key] = plan
+    else:
+        # the per-layer checks ran when the plan was built; the call's own tensors are checked every time
+        _ops.check_layer_tensors(x, latent, t, None, ())
+        if plan.caches:
+            cur = torch.cuda.current_stream(x.device)
+            for c in plan.caches:
+                c.order_after_pack(cur)
+    x2 = x.reshape(-1, dim).contiguous()
+    if torch.compiler.is_compiling():
+        out, vec = _ops.flow_chain(x2, latent, t, plan.masks, plan.params, plan.packed, plan.meta, plan.fmeta, mode, want_ldj)
+    else:
+        out, vec = _ops.flow_chain_launch(plan.arr, plan.n, x2, latent, t, mode, want_ldj)
     out = out.view(*lead, dim) if out.shape[0] == x.numel() // dim else None      # LOG_PROB_ONLY: no latent rows
     if want_ldj or mode in (_ops.CHAIN_LOG_PROB, _ops.CHAIN_LOG_PROB_ONLY):
         return out, vec.view(*lead, 1)

@@ -6,7 +6,7 @@ import os
 
 import torch
 
-from .. import _lib, _ops
+from .. import _epoch, _lib, _ops
 from ..net.mlp import MLP
 
 
@@ -52,6 +52,13 @@ class PackedCache:
 
     def invalidate(self):
         self.key = None
+        _epoch.bump()                 # cached call plans hold the image (flow.run_chain)
+
+    def order_after_pack(self, stream):
+        """A cached plan is about to read the image on ``stream``."""
+        if self.buf is not None and stream.cuda_stream not in self.seen:
+            stream.wait_event(self.event)
+            self.seen.add(stream.cuda_stream)
 
     def get(self, meta, fmeta, mask, params):
         if not params or not params[0].is_cuda or os.environ.get('STRIBOR_B200_FORCE_GENERIC') == '1':

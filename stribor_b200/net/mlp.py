@@ -11,12 +11,12 @@ from typing import Callable, List, Union
 
 import torch.nn as nn
 
-from .. import _lib
+from .. import _epoch, _lib
 
 __all__ = ['MLP']
 
 
-class MLP(nn.Module):
+class MLP(_epoch.Tracked, nn.Module):
     def __init__(self, in_dim: int, hidden_dims: List[int], out_dim: int,
                  activation: Union[str, Callable] = 'Tanh', final_activation: str = None,
                  nn_linear_wrapper_func: Callable = None, **kwargs):

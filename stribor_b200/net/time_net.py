@@ -5,10 +5,12 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .. import _epoch
+
 __all__ = ['TimeLinear']
 
 
-class TimeLinear(nn.Module):
+class TimeLinear(_epoch.Tracked, nn.Module):
     def __init__(self, out_dim: int, **kwargs):
         super().__init__()
         self.scale = nn.Parameter(torch.randn(1, out_dim))

@@ -75,6 +75,67 @@ def test_packed_image_follows_the_weights():
         torch.testing.assert_close(flow.log_prob(x), lp2, rtol=0, atol=0)
 
 
+def test_call_plan_is_reused_and_never_stale(monkeypatch):
+    """flow.run_chain keeps the prepared layer array between calls (host time per small-batch call) and rebuilds it
+    whenever a weight, an attribute or the module structure changes."""
+    from stribor_b200 import flow as F
+    from stribor_b200.flows.coupling import Coupling
+    case, flow = _spline_flow()
+    x = case['inputs']['x'].to(DEV)
+    calls = [0]
+    orig = Coupling.describe
+
+    def counting(self, *a, **k):
+        calls[0] += 1
+        return orig(self, *a, **k)
+
+    monkeypatch.setattr(Coupling, 'describe', counting)
+
+    def oracle_lp():
+        return O.flow_log_prob(st.spec.spec_from_layers(list(flow.transforms)), x.cpu())
+
+    with torch.no_grad():
+        lp0 = flow.log_prob(x)
+        n0 = calls[0]
+        assert n0 >= len(flow.transforms)
+        for _ in range(3):
+            torch.testing.assert_close(flow.log_prob(x), lp0, rtol=0, atol=0)
+        assert calls[0] == n0, 'the plan was rebuilt although nothing changed'
+        y0 = flow.inverse(x)                                      # same plan serves the other entry points
+        assert calls[0] == n0
+        # another stream: ordered after the pack event, same numbers
+        s2 = torch.cuda.Stream()
+        s2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s2):
+            lp_s = flow.log_prob(x)
+        s2.synchronize()
+        torch.testing.assert_close(lp_s, lp0, rtol=0, atol=0)
+        # an attribute of a layer (the spline box) is honoured at the next call
+        sp = flow.transforms[0].transform
+        sp.lower, sp.upper = sp.lower * 1.5, sp.upper * 1.5
+        lp1 = flow.log_prob(x)
+        assert calls[0] > n0 and (lp1 - lp0).abs().max() > 1e-4
+        torch.testing.assert_close(lp1.cpu(), oracle_lp(), rtol=1e-4, atol=2e-4)
+        # a parameter OBJECT replaced (not just written)
+        lin = [m for m in flow.modules() if isinstance(m, torch.nn.Linear)]
+        lin[0].weight = torch.nn.Parameter(lin[0].weight.detach() * 0.5)
+        lp2 = flow.log_prob(x)
+        assert (lp2 - lp1).abs().max() > 1e-4
+        torch.testing.assert_close(lp2.cpu(), oracle_lp(), rtol=1e-4, atol=2e-4)
+        # a layer appended to the ModuleList
+        extra = layers_from_spec(case['spec'])[0].to(DEV)
+        flow.transforms.append(extra)
+        lp3 = flow.log_prob(x)
+        torch.testing.assert_close(lp3.cpu(), oracle_lp(), rtol=1e-4, atol=2e-4)
+        torch.testing.assert_close(flow.inverse(x).cpu(), O.flow_inverse(st.spec.spec_from_layers(list(flow.transforms)), x.cpu()),
+                                   rtol=1e-4, atol=2e-4)
+    assert y0.shape == x.shape
+    # with gradients on, the chain path steps aside (the plan is for inference)
+    xg = x.clone().requires_grad_(True)
+    assert flow.log_prob(xg).grad_fn is not None
+    assert F._record(flow.transforms).chainable
+
+
 @pytest.mark.parametrize('act', ['ReLU', 'ELU', 'SiLU'])
 def test_unbounded_activation_stays_off_the_tensor_path_and_finite(act):
     """a hidden value above 65504 would split into (+inf, -inf) on the fp16 hi|lo tensor-core path"""
