@@ -39,13 +39,13 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     if ((L->kind == STB_CONT_AFFINE) && !t) return set_error(STB_EINVAL, "layer expects a time input");
     if (ldj_mode != STB_LDJ_NONE && !ldj) return set_error(STB_EINVAL, "ldj_mode set but ldj is NULL");
     if (L->packed && !ldiag && tc_layer_supported(L))
-        return tc_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);
+        return tc_layer_apply(L, direction, x, latent, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tcw_layer_supported(L) && tcw_image_present(L))
         return tcw_layer_apply(L, tcw_image(L), direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tch_layer_supported(L))
-        return tch_layer_apply(L, direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);
+        return tch_layer_apply(L, direction, x, latent, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tcm_layer_supported(L))
-        return tcm_layer_apply(L, direction, x, t, y, ldj, ldj_mode, base_lp, rows, s);
+        return tcm_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, rows, s);
     return generic_layer_apply(L, direction, x, latent, t, y, ldj, ldj_mode, base_lp, ldiag, rows, s, bins);
 }
 
@@ -153,7 +153,7 @@ static int apply_sequence(const stb_layer* const* seq, int n, int direction, con
             const ChainPerm* pm = run.permuted ? &run.perm : nullptr;
             rc = run.mlp ? tcm_chain_apply(run.couplings, run.n, direction, cur, t, out, ldj, ldj ? mode : STB_LDJ_NONE,
                                            last && base_lp_last, rows, s, pm)
-                         : tc_chain_apply(run.couplings, run.n, direction, cur, out, ldj, ldj ? mode : STB_LDJ_NONE,
+                         : tc_chain_apply(run.couplings, run.n, direction, cur, latent, out, ldj, ldj ? mode : STB_LDJ_NONE,
                                           last && base_lp_last, rows, s, pm);
         } else {
             if (!out) return set_error(STB_EINVAL, "the output / scratch buffer is NULL but this flow needs several launches");
@@ -270,7 +270,8 @@ int stb_layer_backward_diag(const stb_layer* layer, int direction, const float* 
 
 uint64_t stb_packed_bytes(const stb_layer* layer) {
     if (validate_layer(layer)) return 0;
-    if (tc_layer_supported(layer)) return tc_packed_bytes(layer) + tcw_packed_bytes(layer);   // both images
+    if (tc_layer_supported(layer))                                                            // both images
+        return tc_packed_bytes(layer) + (tcw_layer_supported(layer) ? tcw_packed_bytes(layer) : 0);
     if (tcw_layer_supported(layer)) return tcw_packed_bytes(layer);
     if (tch_layer_supported(layer)) return tch_packed_bytes(layer);
     return tcm_layer_supported(layer) ? tcm_packed_bytes(layer) : 0;
@@ -283,7 +284,7 @@ int stb_pack_layer(const stb_layer* layer, void* packed_out, void* stream) {
     if (tc_layer_supported(layer)) {
         // the 256-row inference kernel's image, then the 128-row / backward kernel's (tc_wide.cu)
         rc = tc_pack_layer(layer, packed_out, (cudaStream_t)stream);
-        if (rc) return rc;
+        if (rc || !tcw_layer_supported(layer)) return rc;          // (`latent=` layers: inference image only)
         return tcw_pack_layer(layer, static_cast<uint8_t*>(packed_out) + tc_packed_bytes(layer), (cudaStream_t)stream);
     }
     if (tcw_layer_supported(layer)) return tcw_pack_layer(layer, packed_out, (cudaStream_t)stream);

@@ -24,7 +24,7 @@ int unit_normal_apply(const float* x, float* lp, int accumulate, int dim, int64_
 bool tc_layer_supported(const stb_layer* L);
 uint64_t tc_packed_bytes(const stb_layer* L);
 int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
-int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj,
+int tc_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent, float* y, float* ldj,
                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins = nullptr);
 
 // Permutations (flows/permute.py:11-82) between chained couplings are folded into the kernels' index lists: the tile
@@ -38,8 +38,9 @@ struct ChainPerm {
 
 // several layers of one flow in one launch (tc_layer.cu, CHAIN kernels); layers[] in application order
 bool tc_chain_supported(const stb_layer* const* layers, int n);
-int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, float* y, float* ldj,
-                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, const ChainPerm* perm = nullptr);
+int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, const float* latent, float* y,
+                   float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream,
+                   const ChainPerm* perm = nullptr);
 
 // tcgen05 path for dim <= 128 and the training backward (tc_wide.cu).  `image` is the wide packed image:
 // it follows the tc_layer.cu image when the layer has both (tcw_image).
@@ -67,14 +68,14 @@ inline bool tcw_image_present(const stb_layer* L) {
 bool tch_layer_supported(const stb_layer* L);
 uint64_t tch_packed_bytes(const stb_layer* L);
 int tch_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
-int tch_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
-                    int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins = nullptr);
+int tch_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent, float* y, float* ldj,
+                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins = nullptr);
 
 // tcgen05 path for affine couplings with a wide conditioner (tc_mlp.cu)
 bool tcm_layer_supported(const stb_layer* L);
 uint64_t tcm_packed_bytes(const stb_layer* L);
 int tcm_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
-int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const float* t, float* y,
+int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent, const float* t, float* y,
                     float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream);
 
 // every layer of an affine / continuous-affine flow with small conditioners in one launch (tc_mlp.cu, CHAIN kernel)

@@ -59,7 +59,8 @@ struct Header {                          // 1024 bytes
     uint32_t noshift_mask;
     int32_t cond_idx[kK1];
     int32_t tr_idx[kMaxTr];
-    int32_t pad[256 - 14 - kK1 - kMaxTr];
+    int32_t n_lat;                       // `latent=` columns (coupling.py:64-65): GEMM1 columns n_cond .. n_cond + n_lat - 1
+    int32_t pad[256 - 15 - kK1 - kMaxTr];
 };
 static_assert(sizeof(Header) == 1024, "header layout");
 constexpr uint32_t kOffB1 = 1024, kOffB2 = kOffB1 + kMaxH * 4, kOffB3 = kOffB2 + kMaxH * 4;     // b3: float [32][48]
@@ -99,6 +100,8 @@ static_assert(sizeof(Bars) <= 256, "barrier block");
 struct Args {
     const uint8_t* packed;
     const float* x;
+    const float* latent;     // [rows, lat_stride] or NULL
+    int lat_stride;
     float* y;
     float* ldj;
     int32_t* bins;
@@ -388,7 +391,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int k = g * 8 + u;
-                    const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : 0.f;
+                    float v = 0.f;
+                    if (k < n_cond) v = xrow[hdr->cond_idx[k]];
+                    else if (k < n_cond + hdr->n_lat && row < nrows) v = __ldg(A.latent + (row0 + row) * A.lat_stride + (k - n_cond));
                     split_bf16x3(v, q0[u], q1[u], q2[u]);
                 }
                 *reinterpret_cast<uint4*>(a1buf + off) = *reinterpret_cast<const uint4*>(q0);
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
 struct PackArgs {
     const float *W1, *b1, *W2, *b2, *W3, *b3;
     uint8_t* out;
-    int kind, dim, n_cond, n_tr, H, n_hidden, P, act;
+    int kind, dim, n_cond, n_tr, H, n_hidden, P, act, n_lat;
     int cond_idx[kK1];
     int tr_idx[kMaxTr];
 };
@@ -579,7 +584,7 @@ __global__ void tch_pack_kernel(const PackArgs a) {
     const int H = a.H;
     if (gtid == 0) {
         hdr->magic = kMagic; hdr->kind = a.kind; hdr->dim = a.dim; hdr->n_cond = a.n_cond; hdr->n_tr = a.n_tr; hdr->H = H;
-        hdr->n_hidden = a.n_hidden; hdr->P = a.P; hdr->act = a.act; hdr->s_mid = s_mid; hdr->s_out = s_out;
+        hdr->n_hidden = a.n_hidden; hdr->P = a.P; hdr->act = a.act; hdr->s_mid = s_mid; hdr->s_out = s_out; hdr->n_lat = a.n_lat;
         for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
         for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
     }
@@ -599,7 +604,9 @@ __global__ void tch_pack_kernel(const PackArgs a) {
     uint8_t* w = a.out + kOffW;
     for (int i = gtid; i < H * kK1; i += gsz) {
         const int n = i / kK1, k = i % kK1;
-        const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.dim + a.cond_idx[k]] : 0.f;
+        const size_t in1 = (size_t)(a.dim + a.n_lat);          // the first Linear reads [x * mask | latent]
+        const float v = (k < a.n_cond) ? a.W1[n * in1 + a.cond_idx[k]]
+                                       : ((k < a.n_cond + a.n_lat) ? a.W1[n * in1 + a.dim + (k - a.n_cond)] : 0.f);
         __nv_bfloat16 qv[3];
         split_bf16x3(v, qv[0], qv[1], qv[2]);
         for (int pb = 0; pb < 3; ++pb) {
@@ -663,6 +670,8 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
     for (int i = a.n_tr; i < kMaxTr; ++i) a.tr_idx[i] = 0;
     if (a.n_tr < 1) return false;
     const stb_mlp& N = L->net;
+    a.n_lat = L->latent_dim;
+    if (a.n_cond + a.n_lat > kK1 || N.dims[0] != L->dim + a.n_lat) return false;
     a.kind = L->kind; a.dim = L->dim; a.H = N.dims[1]; a.n_hidden = N.n_linear - 1;
     a.P = L->kind == STB_RQS ? 3 * kBins - 1 : 2 * kBins + 2;
     a.act = N.activation;
@@ -677,7 +686,7 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
 bool tch_layer_supported(const stb_layer* L) {
     using namespace tch;
     if (L->kind != STB_RQS && L->kind != STB_CUBIC) return false;
-    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim != 0 || L->time_input) return false;
+    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim < 0 || L->time_input) return false;
     if (L->has_box || L->row_out || L->dim < 2 || L->dim > kMaxDim || L->inverse_ldj_own) return false;
     const stb_mlp& N = L->net;
     if ((N.n_linear != 2 && N.n_linear != 3) || N.final_activation != STB_ACT_NONE) return false;
@@ -710,12 +719,14 @@ int tch_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
     return STB_OK;
 }
 
-int tch_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
-                    int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins) {
+int tch_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent, float* y, float* ldj,
+                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins) {
     using namespace tch;
     const int H = L->net.dims[1];
     if (L->packed_bytes < packed_bytes(H, L->net.n_linear - 1)) return set_error(STB_EINVAL, "packed image too small");
     Args A = {};
+    A.latent = L->latent_dim > 0 ? latent : nullptr;
+    A.lat_stride = L->latent_dim;
     A.packed = static_cast<const uint8_t*>(L->packed);
     A.x = x; A.y = y; A.ldj = ldj; A.bins = bins;
     A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;

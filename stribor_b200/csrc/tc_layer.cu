@@ -101,7 +101,9 @@ struct Header {                      // 1024 bytes
     int32_t tr_idx[kMaxTr];
     uint32_t noshift_mask;           // bit ji: softmax logits of transformed dim ji are provably within
                                      // +-100 (log2 units), so exp2 needs no max subtraction
-    int32_t pad[256 - 11 - kK1 - kMaxTr];
+    int32_t n_lat;                   // `latent=` columns of the conditioner input (coupling.py:64-65): GEMM1 columns
+                                     // n_cond .. n_cond + n_lat - 1 are latent[row, 0 .. n_lat - 1]
+    int32_t pad[256 - 12 - kK1 - kMaxTr];
 };
 static_assert(sizeof(Header) == 1024, "header layout");
 constexpr uint32_t kOffB1 = 1024;                                  // float[64]
@@ -159,6 +161,8 @@ struct Args {
     const uint8_t* chain_packed[kMaxChain];
     float lower_l[kMaxChain], upper_l[kMaxChain];
     int n_chunks_l[kMaxChain];
+    const float* latent;               // [rows, lat_stride] or NULL
+    int lat_stride;
     int32_t* bins;                     // BINS kernels: [rows, dim] searched bin per element (stb_layer_apply_bins)
     int permuted;                      // CHAIN: permutations between the layers, folded into the index lists
     ChainPerm perm;
@@ -224,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
     const int d = CHAIN ? A.dim : hdr->dim;
     // per-layer quantities (CHAIN: re-read at every layer by the epilogue warps)
     int n_tr = CHAIN ? 0 : hdr->n_tr, n_cond = CHAIN ? 0 : hdr->n_cond, n_chunks = CHAIN ? 0 : hdr->n_chunks;
+    int n_lat = CHAIN ? 0 : hdr->n_lat;
     int act = CHAIN ? 0 : hdr->act;
     float s2 = CHAIN ? 1.f : hdr->s2;
     float s2l = s2 * 1.4426950408889634f;
@@ -423,11 +428,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
                 named_bar_sync(1, kEpiThreads);
                 if (A.permuted) {             // logical -> physical tile columns of this layer (warp-uniform branch)
                     Header* h = const_cast<Header*>(hdr);
-                    if (etid < kK1) h->cond_idx[etid] = A.perm.phys[l][h->cond_idx[etid]];
+                    if (etid < kK1) { if (etid < h->n_cond) h->cond_idx[etid] = A.perm.phys[l][h->cond_idx[etid]]; }
                     else if (etid < kK1 + kMaxTr) h->tr_idx[etid - kK1] = A.perm.phys[l][h->tr_idx[etid - kK1]];
                     named_bar_sync(1, kEpiThreads);
                 }
                 n_tr = hdr->n_tr; n_cond = hdr->n_cond; n_chunks = hdr->n_chunks; act = hdr->act;
+                n_lat = hdr->n_lat;
                 s2 = hdr->s2; s2l = s2 * 1.4426950408889634f;
                 noshift_mask = hdr->noshift_mask;
                 lo = A.lower_l[l]; hi = A.upper_l[l]; inv_span = 1.f / (hi - lo);
@@ -453,7 +459,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_spline_layer_kernel(const Args
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int k = kc * 8 + u;
-                        const float v = (k < n_cond) ? xr[hdr->cond_idx[k]] : 0.f;
+                        float v = 0.f;
+                        if (k < n_cond) v = xr[hdr->cond_idx[k]];
+                        else if (k < n_cond + n_lat && sp * 128 + rloc < nrows)
+                            v = __ldg(A.latent + (row0 + sp * 128 + rloc) * A.lat_stride + (k - n_cond));
                         split_bf16x3(v, q0[u], q1[u], q2[u]);
                     }
                     *reinterpret_cast<uint4*>(a_p + a1_row_off + kc * 128) = *reinterpret_cast<const uint4*>(q0);
@@ -863,12 +872,13 @@ __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args
                     named_bar_sync(1, kPEpiThreads);
                     if (A.permuted) {
                         Header* h = const_cast<Header*>(hdr);
-                        if (etid < kK1) h->cond_idx[etid] = A.perm.phys[l][h->cond_idx[etid]];
+                        if (etid < kK1) { if (etid < h->n_cond) h->cond_idx[etid] = A.perm.phys[l][h->cond_idx[etid]]; }
                         else if (etid < kK1 + kMaxTr) h->tr_idx[etid - kK1] = A.perm.phys[l][h->tr_idx[etid - kK1]];
                         named_bar_sync(1, kPEpiThreads);
                     }
                 }
                 const int n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_chunks = hdr->n_chunks, act = hdr->act;
+                const int n_lat = hdr->n_lat;
                 const float s2 = hdr->s2, s2l = s2 * 1.4426950408889634f;
                 const uint32_t noshift_mask = hdr->noshift_mask;
                 float lo = A.lower_l[l], hi = A.upper_l[l], inv_span = 1.f / (hi - lo);
@@ -882,7 +892,9 @@ __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int k = kc * 8 + u;
-                        const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : 0.f;
+                        float v = 0.f;
+                        if (k < n_cond) v = xrow[hdr->cond_idx[k]];
+                        else if (k < n_cond + n_lat && rt < nrows) v = __ldg(A.latent + (row0 + rt) * A.lat_stride + (k - n_cond));
                         split_bf16x3(v, q0[u], q1[u], q2[u]);
                     }
                     const uint32_t col = tmem + lane_sel + kPColA1 + (uint32_t)(kc >> 1) * 8 + (uint32_t)(kc & 1) * 4;
@@ -1046,7 +1058,7 @@ __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args
 struct PackArgs {
     const float *W1, *b1, *W2, *b2;
     uint8_t* out;
-    int kind, dim, n_cond, n_tr, n_chunks, P, act;
+    int kind, dim, n_cond, n_tr, n_chunks, P, act, n_lat;
     int cond_idx[kK1];
     int tr_idx[kMaxTr];
 };
@@ -1086,7 +1098,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     if (gtid == 0) {
         hdr->magic = kMagic; hdr->kind = a.kind; hdr->dim = a.dim; hdr->n_cond = a.n_cond; hdr->n_tr = a.n_tr;
-        hdr->n_chunks = a.n_chunks; hdr->P = a.P; hdr->act = a.act; hdr->s2 = s2;
+        hdr->n_chunks = a.n_chunks; hdr->P = a.P; hdr->act = a.act; hdr->s2 = s2; hdr->n_lat = a.n_lat;
         for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
         for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
     }
@@ -1101,7 +1113,9 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     // first Linear, conditioning columns only: [64][32] as three bf16 parts
     for (int i = gtid; i < kHid * kK1; i += gsz) {
         const int n = i / kK1, k = i % kK1;
-        const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.dim + a.cond_idx[k]] : 0.f;
+        const size_t in1 = (size_t)(a.dim + a.n_lat);          // the first Linear reads [x * mask | latent]
+        const float v = (k < a.n_cond) ? a.W1[n * in1 + a.cond_idx[k]]
+                                       : ((k < a.n_cond + a.n_lat) ? a.W1[n * in1 + a.dim + (k - a.n_cond)] : 0.f);
         __nv_bfloat16 q0, q1, q2;
         split_bf16x3(v, q0, q1, q2);
         const uint32_t off = kOffW1 + core_off(n, k, kK1, 2);
@@ -1150,6 +1164,8 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
     for (int i = a.n_cond; i < kK1; ++i) a.cond_idx[i] = 0;
     for (int i = a.n_tr; i < kMaxTr; ++i) a.tr_idx[i] = 0;
     if (a.n_tr < 1) return false;
+    a.n_lat = L->latent_dim;
+    if (a.n_cond + a.n_lat > kK1) return false;              // [conditioning columns | latent] share GEMM1's 32 K columns
     a.n_chunks = (a.n_tr + kG - 1) / kG;
     a.kind = L->kind; a.dim = L->dim; a.P = L->kind == STB_RQS ? 3 * kBins - 1 : 2 * kBins + 2;
     a.act = L->net.activation;
@@ -1162,10 +1178,11 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
 bool tc_layer_supported(const stb_layer* L) {
     using namespace tcl;
     if (L->kind != STB_RQS && L->kind != STB_CUBIC) return false;
-    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim != 0 || L->time_input) return false;
+    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim < 0 || L->time_input) return false;
     if (L->has_box || L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
     const stb_mlp& N = L->net;
     if (N.n_linear != 2 || N.dims[1] != kHid || N.final_activation != STB_ACT_NONE) return false;
+    if (N.dims[0] != L->dim + L->latent_dim) return false;
     // The hidden activations feed the next GEMM as fp16 hi | lo parts: only activations bounded by 1 are safe
     // (a ReLU / ELU / ... output above 65504 would split into +inf, -inf -> NaN, where the reference and the
     // CUDA-core kernel stay finite).  Other activations take the generic kernel.
@@ -1202,12 +1219,14 @@ int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
     return STB_OK;
 }
 
-int tc_layer_apply(const stb_layer* L, int direction, const float* x, float* y, float* ldj, int ldj_mode,
-                   int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins) {
+int tc_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent, float* y, float* ldj,
+                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins) {
     using namespace tcl;
     if (L->packed_bytes < kPackedBytes) return set_error(STB_EINVAL, "packed image too small");
     Args A = {};
     A.bins = bins;
+    A.latent = L->latent_dim > 0 ? latent : nullptr;
+    A.lat_stride = L->latent_dim;
     A.packed = static_cast<const uint8_t*>(L->packed);
     A.x = x; A.y = y; A.ldj = ldj;
     A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
@@ -1252,16 +1271,20 @@ bool tc_chain_supported(const stb_layer* const* layers, int n) {
         const stb_layer* L = layers[i];
         if (!L->packed || L->packed_bytes < kPackedBytes || !tc_layer_supported(L)) return false;
         if (L->kind != layers[0]->kind || L->dim != layers[0]->dim) return false;
+        if (L->latent_dim != layers[0]->latent_dim) return false;          // one latent row layout for the whole launch
     }
     return true;
 }
 
 // layers[] in APPLICATION order (the caller reverses them for the inverse direction)
-int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, float* y, float* ldj,
-                   int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, const ChainPerm* perm) {
+int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const float* x, const float* latent, float* y,
+                   float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, const ChainPerm* perm) {
     using namespace tcl;
     if (!tc_chain_supported(layers, n)) return set_error(STB_EINVAL, "layers cannot be chained");
     Args A = {};
+    A.latent = layers[0]->latent_dim > 0 ? latent : nullptr;
+    A.lat_stride = layers[0]->latent_dim;
+    if (A.lat_stride > 0 && !latent) return set_error(STB_EINVAL, "layer expects a latent input");
     if (perm) { A.permuted = 1; A.perm = *perm; }
     A.packed = static_cast<const uint8_t*>(layers[0]->packed);
     A.x = x; A.y = y; A.ldj = ldj;

@@ -52,7 +52,8 @@ struct Header {                            // 1024 bytes
     int32_t tr_idx[kMaxTr];
     int32_t cont, time_col;                // continuous-affine: scale by the time embedding; A1 column holding t (-1: none)
     float ts_ls[kMaxTr], ts_sh[kMaxTr];    // TimeLinear.scale of the transformed dims (log-scale half | shift half)
-    int32_t pad[256 - 13 - kK1 - 3 * kMaxTr];
+    int32_t lat0, n_lat;                   // `latent=` input (coupling.py:64-65): A1 columns lat0 .. lat0 + n_lat - 1
+    int32_t pad[256 - 15 - kK1 - 3 * kMaxTr];
 };
 static_assert(sizeof(Header) == 1024, "header layout");
 // packed image: header | b1[256] | b2[256] | b3[64] | pad to 4096 | W blocks (see pack kernel)
@@ -105,6 +106,8 @@ constexpr uint32_t kColMain = 0;
 struct Args {
     const uint8_t* packed;
     const float* x;
+    const float* latent;                   // [rows, lat_stride] or NULL
+    int lat_stride;
     const float* t;
     float* y;
     float* ldj;
@@ -394,7 +397,9 @@ __global__ void __launch_bounds__(Cfg<NCG>::kThreads, (NCG == 4) ? 1 : 2) tc_mlp
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int k = kc * 8 + u;
-                        const float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[row] : 0.f);
+                        float v = (k < n_cond) ? xrow[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[row] : 0.f);
+                        if (k >= hdr->lat0 && k < hdr->lat0 + hdr->n_lat && row < nrows)
+                            v = __ldg(A.latent + (row0 + row) * A.lat_stride + (k - hdr->lat0));
                         split_bf16x3(v, q0[u], q1[u], q2[u]);
                     }
                     *reinterpret_cast<uint4*>(abuf + off) = *reinterpret_cast<const uint4*>(q0);
@@ -779,7 +784,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) tc_mlp_pipe_kernel(const Args
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int k = g * 8 + u;
-                const float v = (k < n_cond) ? xr[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[(it & 1) * kRows + row] : 0.f);
+                float v = (k < n_cond) ? xr[hdr->cond_idx[k]] : ((k == hdr->time_col) ? t_s[(it & 1) * kRows + row] : 0.f);
+                if (k >= hdr->lat0 && k < hdr->lat0 + hdr->n_lat) {
+                    const long long grow = ((long long)blockIdx.x + (long long)it * gridDim.x) * kRows + row;
+                    if (grow < A.rows) v = __ldg(A.latent + grow * A.lat_stride + (k - hdr->lat0));
+                }
                 split_bf16x3(v, q0[u], q1[u], q2[u]);
             }
             *reinterpret_cast<uint4*>(a1buf + off) = *reinterpret_cast<const uint4*>(q0);
@@ -1291,7 +1300,7 @@ __global__ void __launch_bounds__(V * kVcThreads, 1) tc_mlp_chain_kernel(const C
 struct PackArgs {
     const float *W1, *b1, *W2, *b2, *W3, *b3, *time_scale;
     uint8_t* out;
-    int dim, n_cond, n_tr, H, n_hidden, act, in_dim, cont, time_col;
+    int dim, n_cond, n_tr, H, n_hidden, act, in_dim, cont, time_col, lat0, n_lat;
     int cond_idx[kK1];
     int tr_idx[kMaxTr];
 };
@@ -1343,7 +1352,7 @@ __global__ void tcm_pack_kernel(const PackArgs a) {
         hdr->n_hidden = a.n_hidden; hdr->act = a.act; hdr->s_mid = s_mid; hdr->s_out = s_out;
         for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
         for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
-        hdr->cont = a.cont; hdr->time_col = a.time_col;
+        hdr->cont = a.cont; hdr->time_col = a.time_col; hdr->lat0 = a.lat0; hdr->n_lat = a.n_lat;
         for (int i = 0; i < kMaxTr; ++i) {
             hdr->ts_ls[i] = (a.cont && i < a.n_tr) ? a.time_scale[a.tr_idx[i]] : 0.f;
             hdr->ts_sh[i] = (a.cont && i < a.n_tr) ? a.time_scale[a.dim + a.tr_idx[i]] : 0.f;
@@ -1364,8 +1373,9 @@ __global__ void tcm_pack_kernel(const PackArgs a) {
     uint8_t* w = a.out + kOffW;
     for (int i = gtid; i < H * kK1; i += gsz) {
         const int n = i / kK1, k = i % kK1;
-        const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.in_dim + a.cond_idx[k]]
-                                       : ((k == a.time_col) ? a.W1[(size_t)n * a.in_dim + a.in_dim - 1] : 0.f);
+        float v = (k < a.n_cond) ? a.W1[(size_t)n * a.in_dim + a.cond_idx[k]]
+                                 : ((k == a.time_col) ? a.W1[(size_t)n * a.in_dim + a.in_dim - 1] : 0.f);
+        if (k >= a.lat0 && k < a.lat0 + a.n_lat) v = a.W1[(size_t)n * a.in_dim + a.dim + (k - a.lat0)];   // [x * mask | latent | t]
         __nv_bfloat16 q[3];
         split_bf16x3(v, q[0], q[1], q[2]);
         for (int pb = 0; pb < 3; ++pb) {
@@ -1418,6 +1428,10 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
         if (a.n_cond >= kK1) return false;
         a.time_col = a.n_cond;                                  // first free A1 column
     }
+    a.n_lat = L->latent_dim;
+    a.lat0 = a.n_cond + (a.time_col >= 0 ? 1 : 0);
+    if (a.lat0 + a.n_lat > kK1) return false;                   // conditioning columns, t and latent share GEMM1's 32 K columns
+    if (a.in_dim != L->dim + a.n_lat + (a.time_col >= 0 ? 1 : 0)) return false;
     a.time_scale = L->time_scale;
     a.dim = L->dim; a.H = N.dims[1]; a.n_hidden = N.n_linear - 1; a.act = N.activation;
     a.W1 = N.W[0]; a.b1 = N.b[0];
@@ -1431,7 +1445,7 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
 bool tcm_layer_supported(const stb_layer* L) {
     using namespace tcm;
     if (L->kind != STB_AFFINE && L->kind != STB_CONT_AFFINE) return false;
-    if (!L->cond_x || L->zero_cond || L->latent_dim != 0) return false;
+    if (!L->cond_x || L->zero_cond || L->latent_dim < 0) return false;
     if (L->kind == STB_AFFINE && L->time_input) return false;
     if (L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
     const stb_mlp& N = L->net;
@@ -1467,12 +1481,14 @@ int tcm_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
     return STB_OK;
 }
 
-int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const float* t, float* y, float* ldj,
-                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream) {
+int tcm_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent, const float* t, float* y,
+                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream) {
     using namespace tcm;
     const int H = L->net.dims[1];
     if (L->packed_bytes < packed_bytes(H, L->net.n_linear - 1)) return set_error(STB_EINVAL, "packed image too small");
     Args A;
+    A.latent = L->latent_dim > 0 ? latent : nullptr;
+    A.lat_stride = L->latent_dim;
     A.packed = static_cast<const uint8_t*>(L->packed);
     A.x = x; A.t = t; A.y = y; A.ldj = ldj;
     A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
@@ -1830,6 +1846,7 @@ static bool chain_layout(const stb_layer* const* layers, int n, ChainArgs* A, ui
     for (int i = 0; i < n; ++i) {
         const stb_layer* L = layers[i];
         if (!L->packed || !tcm_layer_supported(L) || L->dim != d || d > 32 || L->net.dims[1] != 64) return false;
+        if (L->latent_dim != 0) return false;                      // `latent=` layers: one launch per layer
         if (L->packed_bytes < packed_bytes(64, L->net.n_linear - 1)) return false;
         if (A) { A->w_off[i] = w; A->w_bytes[i] = layer_w_total(L); A->packed[i] = static_cast<const uint8_t*>(L->packed); }
         w += layer_w_total(L);
@@ -1856,6 +1873,7 @@ static bool chain4_layout(const stb_layer* const* layers, int n, ChainArgs* A, u
     for (int i = 0; i < n; ++i) {
         const stb_layer* L = layers[i];
         if (!L->packed || !tcm_layer_supported(L) || L->dim != d || d > 32 || L->net.dims[1] != 64) return false;
+        if (L->latent_dim != 0) return false;                      // `latent=` layers: one launch per layer
         if (L->net.n_linear != 2 || L->packed_bytes < packed_bytes(64, 1)) return false;
         PackArgs pa;
         if (!fill_pack_args(L, pa)) return false;

@@ -182,6 +182,107 @@ def test_affine_tensor_path_matches_generic_and_oracle(d, hidden, masks, monkeyp
     assert (li_t - li_g).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize('kind,d,hidden,latent_dim,n_layers,rows', [
+    ('quadratic', 32, [64], 8, 3, 700),        # spline, whole-flow kernel (n_cond 16 + 8 latent columns of GEMM1)
+    ('cubic', 40, [64], 12, 2, 300),           # 20 + 12 = all 32 K columns in use
+    ('quadratic', 32, [64], 16, 1, 130),       # one layer: the per-layer kernel
+    ('quadratic', 20, [64], 5, 9, 40000),      # more than 8 layers: two chained launches, many tiles
+    ('quadratic', 32, [128, 128], 8, 2, 300),  # spline with a wide conditioner (tc_hwide.cu)
+    ('affine', 32, [128, 128], 8, 2, 500),     # affine, pipelined kernel
+    ('affine', 24, [64], 7, 3, 300),           # affine, phase-by-phase kernel (H = 64: no chain with a latent input)
+])
+def test_latent_input_on_the_tensor_path(kind, d, hidden, latent_dim, n_layers, rows, monkeypatch):
+    """`latent=` (coupling.py:64-65): the conditioner reads [x * mask | latent]; on the tensor-core kernels the latent
+    columns are extra K columns of GEMM1, read from the caller's [rows, latent_dim] tensor.  Against the CUDA-core kernel
+    and the oracle, both directions, chained and layer by layer."""
+    rs = cases._rs(900 + d + latent_dim)
+    spec = [cases.coupling_spec(rs, kind, d, hidden, cases.ALT[i % 2], n_bins=16 if kind != 'affine' else 0,
+                                lower=-4., upper=4., latent_dim=latent_dim) for i in range(n_layers)]
+    torch.manual_seed(rows)
+    x = torch.randn(rows, d, device=DEV) * 1.3
+    lat = torch.randn(rows, latent_dim, device=DEV)
+
+    def build():
+        layers = [l.to(DEV) for l in layers_from_spec(spec)]
+        return st.NormalizingFlow(st.UnitNormal(d), layers), layers
+
+    tflow, tl = build()
+    with torch.no_grad():
+        desc = tl[0].describe(d, latent_dim, torch.device(DEV))
+        assert desc['packed'] is not None, 'tensor path was not selected'
+        L = _ops.make_struct(desc['meta'], desc['fmeta'], desc['mask'], [p.detach() for p in desc['params']], desc['packed'])
+        assert _lib.lib().stb_layer_uses_tensor_path(ctypes.byref(L)) == 1
+        tflow.log_prob(x[:4], latent=lat[:4])
+        n0 = _ops.launch_count()
+        lp_t = tflow.log_prob(x, latent=lat)
+        launches = _ops.launch_count() - n0
+        xi_t, li_t = tflow.inverse_and_log_det_jacobian(x, latent=lat)
+        yf_t, lf_t = tflow.forward_and_log_det_jacobian(x, latent=lat)
+        # layer by layer (the per-layer kernels): bit-identical to the chained launch for the spline kernels
+        cur, tot = x, 0
+        for f in reversed(tflow.transforms):
+            cur, l = f.inverse_and_log_det_jacobian(cur, latent=lat)
+            tot = tot + l
+    if kind != 'affine':
+        # MLP[64] spline layers chain (<= 8 per launch); wide conditioners go out one launch per layer
+        assert launches == ((n_layers + 7) // 8 if hidden == [64] else n_layers)
+        assert torch.equal(cur, xi_t)
+    monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', '1')
+    gflow, _ = build()
+    with torch.no_grad():
+        lp_g = gflow.log_prob(x, latent=lat)
+        xi_g, li_g = gflow.inverse_and_log_det_jacobian(x, latent=lat)
+        yf_g, lf_g = gflow.forward_and_log_det_jacobian(x, latent=lat)
+    tol = 5e-4 if n_layers > 3 else 2e-4
+    if kind == 'cubic':      # a handful of one-root Cardano elements amplify 1-ulp differences (as in the test above)
+        assert ((xi_t - xi_g).abs() > 1e-4).float().mean().item() < 5e-3
+        assert ((li_t - li_g).abs() > 1e-3).float().mean().item() < 2e-2
+    else:
+        assert (xi_t - xi_g).abs().max().item() < tol
+        assert (li_t - li_g).abs().max().item() < 5 * tol
+        assert ((lp_t - lp_g).abs() <= 5 * tol + 1e-5 * lp_g.abs()).all().item()
+    assert (yf_t - yf_g).abs().max().item() < tol and (lf_t - lf_g).abs().max().item() < 5 * tol
+    if rows <= 1000:
+        xc, lc = x.cpu(), lat.cpu()
+        s64 = O.spec_to(spec, torch.float64)
+        for got, f32, f64, what in (
+                (xi_t, O.flow_inverse(spec, xc, latent=lc), O.flow_inverse(s64, xc.double(), latent=lc.double()), 'inverse x'),
+                (yf_t, O.flow_forward(spec, xc, latent=lc), O.flow_forward(s64, xc.double(), latent=lc.double()), 'forward y'),
+                (lp_t, O.flow_log_prob(spec, xc, latent=lc), O.flow_log_prob(s64, xc.double(), latent=lc.double()), 'log_prob')):
+            fail, _, mx = close_or_arbitrated(got, f32, f64, 1e-5, 1e-5)
+            assert fail <= 2e-2, f'{what}: {fail:.3%} outside tolerance (max abs err {mx:.3e})'
+
+
+@pytest.mark.parametrize('hidden', [[64], [128, 128]])
+def test_continuous_affine_with_latent_on_the_tensor_path(hidden, monkeypatch):
+    """ContinuousAffineCoupling with `latent=`: the conditioner reads [x * mask | latent | t] (coupling.py:140-154)."""
+    d, latent_dim, rows = 16, 6, 777
+    rs = cases._rs(431 + len(hidden))
+    spec = [cases.cont_affine_spec(rs, d, hidden, ('ordered_0', 'ordered_1')[i % 2], latent_dim=latent_dim) for i in range(3)]
+    torch.manual_seed(3)
+    x = torch.randn(rows, d, device=DEV)
+    t = torch.rand(rows, 1, device=DEV)
+    lat = torch.randn(rows, latent_dim, device=DEV)
+
+    def run():
+        layers = [l.to(DEV) for l in layers_from_spec(spec)]
+        with torch.no_grad():
+            desc = layers[0].describe(d, latent_dim, torch.device(DEV))
+            return st.NeuralFlow(layers)(x, t=t, latent=lat), desc['packed'] is not None
+
+    y_t, packed = run()
+    assert packed, 'tensor path was not selected'
+    monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', '1')
+    y_g, packed_g = run()
+    assert not packed_g
+    assert (y_t - y_g).abs().max().item() < 2e-4
+    s64 = O.spec_to(spec, torch.float64)
+    want32 = O.flow_forward(spec, x.cpu(), t=t.cpu(), latent=lat.cpu())
+    want64 = O.flow_forward(s64, x.cpu().double(), t=t.cpu().double(), latent=lat.cpu().double())
+    fail, _, mx = close_or_arbitrated(y_t, want32, want64, 1e-5, 1e-5)
+    assert fail <= 2e-3, f'{fail:.3%} outside tolerance (max abs err {mx:.3e})'
+
+
 @pytest.mark.parametrize('d,kind', [(16, 'cont'), (30, 'affine')])
 def test_small_conditioner_two_ctas_per_sm(d, kind, monkeypatch):
     """Many rows of a small conditioner (dim <= 32, MLP[64]): the 8-warp configuration of tc_mlp.cu runs with two
