@@ -203,6 +203,19 @@ def _(x, latent, t, mask, params, meta, fmeta, direction):
     return torch.empty_like(x), torch.empty_like(x)
 
 
+
+def _const_param_slabs(rows: int, numel: int):
+    """Row ranges for the gradient of a broadcast (learned, ``[1, dim * P]``) parameter: the kernels write one
+    gradient row per input row, which is then summed -- in slabs of at most 256 MB instead of a dense
+    ``[rows, dim * P]`` tensor (12 GB at 1 M rows, dim 64, 47 parameters)."""
+    slab = max(4096, (256 << 20) // (4 * max(numel, 1)))
+    return [(s0, min(slab, rows - s0)) for s0 in range(0, rows, slab)]
+
+
+def _off(ptr, count, width=1):
+    return None if ptr is None else ptr + 4 * count * width
+
+
 @torch.library.custom_op('stribor_b200::layer_backward_diag', mutates_args=(), device_types='cuda')
 def layer_backward_diag(x: Tensor, mask: Optional[Tensor], params: List[Tensor], meta: List[int],
                         fmeta: List[float], direction: int, g_y: Tensor, g_ld: Optional[Tensor]) -> List[Tensor]:
@@ -216,15 +229,27 @@ def layer_backward_diag(x: Tensor, mask: Optional[Tensor], params: List[Tensor],
     g_x = torch.empty_like(x)
     if rows == 0:
         return [g_x, torch.zeros_like(p0)]
-    g_rows = torch.zeros_like(p0) if row_mode else x.new_zeros(rows, p0.numel())
     L = make_struct(meta, fmeta, mask, params, None)
     G = _lib.StbLayerGrads()
+    lib = _lib.lib()
+    if row_mode:
+        g_rows = torch.zeros_like(p0)
+        G.g_row_out = g_rows.data_ptr()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.stb_layer_backward_diag(C.byref(L), direction, x.data_ptr(), g_y.data_ptr(), _dp(g_ld),
+                                                   g_x.data_ptr(), C.byref(G), rows, _stream(x)))
+        return [g_x, g_rows]
+    slabs = _const_param_slabs(rows, p0.numel())
+    g_rows = x.new_empty(slabs[0][1], p0.numel())
+    g_p = x.new_zeros(p0.numel())
     G.g_row_out = g_rows.data_ptr()
     with torch.cuda.device(x.device):
-        rc = _lib.lib().stb_layer_backward_diag(C.byref(L), direction, x.data_ptr(), g_y.data_ptr(), _dp(g_ld),
-                                                g_x.data_ptr(), C.byref(G), rows, _stream(x))
-    _lib.check(rc)
-    return [g_x, g_rows if row_mode else g_rows.sum(0).view_as(p0)]
+        for s0, n in slabs:
+            g_rows[:n].zero_()
+            _lib.check(lib.stb_layer_backward_diag(C.byref(L), direction, _off(x.data_ptr(), s0, dim), _off(g_y.data_ptr(), s0, dim),
+                                                   _off(_dp(g_ld), s0, dim), _off(g_x.data_ptr(), s0, dim), C.byref(G), n, _stream(x)))
+            g_p += g_rows[:n].sum(0)
+    return [g_x, g_p.view_as(p0)]
 
 
 @layer_backward_diag.register_fake
@@ -438,19 +463,31 @@ def layer_backward(x: Tensor, latent: Optional[Tensor], t: Optional[Tensor], mas
     if rows == 0:
         g_x.zero_()
         return [g_x, g_latent, g_t, torch.zeros_like(p0)]
-    # per-row gradient wrt the network output; a broadcast (const) parameter sums it over rows
-    g_rows = torch.zeros_like(p0) if row_mode else x.new_zeros(rows, p0.numel())
+    # per-row gradient wrt the network output; a broadcast (const) parameter sums it over rows, slab by slab
     L = make_struct(meta, fmeta, mask, params, None)
     G = _lib.StbLayerGrads()
-    G.g_row_out = g_rows.data_ptr()
     lib = _lib.lib()
+    if row_mode:
+        g_rows = torch.zeros_like(p0)
+        G.g_row_out = g_rows.data_ptr()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.stb_layer_backward(C.byref(L), direction, x.data_ptr(), _dp(latent), _dp(t),
+                                              g_y.data_ptr(), _dp(g_ldj), g_x.data_ptr(), None, None,
+                                              C.byref(G), None, rows, _stream(x)))
+        return [g_x, g_latent, g_t, g_rows]
+    slabs = _const_param_slabs(rows, p0.numel())
+    g_rows = x.new_empty(slabs[0][1], p0.numel())
+    g_p = x.new_zeros(p0.numel())
+    G.g_row_out = g_rows.data_ptr()
+    lat_w = 0 if latent is None else latent.shape[-1]
     with torch.cuda.device(x.device):
-        rc = lib.stb_layer_backward(C.byref(L), direction, x.data_ptr(), _dp(latent), _dp(t),
-                                    g_y.data_ptr(), _dp(g_ldj), g_x.data_ptr(), None, None,
-                                    C.byref(G), None, rows, _stream(x))
-    _lib.check(rc)
-    g_p = g_rows if row_mode else g_rows.sum(0).view_as(p0)
-    return [g_x, g_latent, g_t, g_p]
+        for s0, n in slabs:
+            g_rows[:n].zero_()
+            _lib.check(lib.stb_layer_backward(C.byref(L), direction, _off(x.data_ptr(), s0, dim), _off(_dp(latent), s0, lat_w),
+                                              _off(_dp(t), s0), _off(g_y.data_ptr(), s0, dim), _off(_dp(g_ldj), s0),
+                                              _off(g_x.data_ptr(), s0, dim), None, None, C.byref(G), None, n, _stream(x)))
+            g_p += g_rows[:n].sum(0)
+    return [g_x, g_latent, g_t, g_p.view_as(p0)]
 
 
 @layer_backward.register_fake

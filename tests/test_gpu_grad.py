@@ -81,6 +81,41 @@ def test_standalone_spline_gradients_match_oracle_autograd(name, inverse):
         torch.testing.assert_close(g.cpu().double(), r, **tol)
 
 
+@pytest.mark.parametrize('name', ['spline_quadratic_7x4x5_k10_l0', 'spline_cubic_7x4x5_k3_l0'])
+def test_learned_parameter_gradient_is_summed_in_slabs(name, monkeypatch):
+    """The gradient of a broadcast (learned) parameter is reduced over rows slab by slab (no dense [rows, dim * P]
+    tensor): forcing 7-row slabs gives the same gradients as one slab."""
+    from stribor_b200 import _ops
+    if name not in cases.CASES:
+        pytest.skip('fixture not present')
+    case = cases.build_case(name)
+    f = layers_from_spec(case['spec'])[0].to(DEV)
+    x = case['inputs']['x'].clone().to(DEV)             # [7, 4, 5]: 28 rows
+
+    def grads():
+        for p in f.parameters():
+            p.grad = None
+        xg = x.clone().requires_grad_(True)
+        out, ldj = f.forward_and_log_det_jacobian(xg)
+        (out.sin().sum() + (ldj * ldj).sum() + ldj.sum()).backward()
+        return [xg.grad.clone()] + [p.grad.clone() for p in f.parameters()]
+
+    want = grads()
+    calls = []
+    orig = _ops._const_param_slabs
+
+    def small(rows, numel):
+        calls.append(rows)
+        return [(s0, min(7, rows - s0)) for s0 in range(0, rows, 7)]
+
+    monkeypatch.setattr(_ops, '_const_param_slabs', small)
+    got = grads()
+    assert calls and max(calls) > 7, 'the slab path was not exercised'
+    for g, w in zip(got, want):
+        torch.testing.assert_close(g, w, rtol=1e-5, atol=1e-5)
+    assert orig(1 << 20, 64 * 47)[0][1] * 64 * 47 * 4 <= 256 << 20
+
+
 def test_affine_coupling_gradients_not_nan_and_match_oracle():
     """test_coupling.py:24-26 pattern (check_gradients_not_nan) + values against the oracle."""
     case = cases.build_case('affine_coupling_7x4x5_l13')

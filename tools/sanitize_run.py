@@ -94,3 +94,24 @@ if not ONLY or ONLY in 'chain4 neural':
             nf(x, t=t, t0=t * 0.5)
     torch.cuda.synchronize(); print('ok chain4 neural', flush=True)
 run('tc affine d63 h192 (pipe kernel, one hidden layer, odd dim)', cases._mk_flow('affine', 63, [192], 2, 0, 8, 13, masks=('ordered_left_half', 'parity_odd'))(), rows_list=(1, 129, 300))
+# round 2, last: `latent=` columns on the tensor-core kernels (whole-flow kernel in its two-CTA form at these row counts,
+# wide-conditioner spline kernel, affine pipelined kernel)
+def run_latent(name, kind, d, hidden, latent_dim, n_layers, rows_list):
+    if ONLY and ONLY not in name:
+        return
+    rs = cases._rs(77 + d)
+    spec = [cases.coupling_spec(rs, kind, d, hidden, cases.ALT[i % 2], n_bins=16 if kind != 'affine' else 0,
+                                lower=-4., upper=4., latent_dim=latent_dim) for i in range(n_layers)]
+    flow = st.NormalizingFlow(st.UnitNormal(d), [l.to(dev) for l in layers_from_spec(spec)])
+    for r in rows_list:
+        x = torch.randn(r, d, device=dev) * 1.5
+        lat = torch.randn(r, latent_dim, device=dev)
+        with torch.no_grad():
+            lp = flow.log_prob(x, latent=lat); y, l = flow.forward_and_log_det_jacobian(x, latent=lat)
+        assert torch.isfinite(lp).all()
+    torch.cuda.synchronize()
+    print('ok', name, flush=True)
+run_latent('latent spline chain d32', 'quadratic', 32, [64], 8, 3, (1, 129, 300))
+run_latent('latent cubic single layer d40', 'cubic', 40, [64], 12, 1, (1, 257))
+run_latent('latent hwide d32', 'quadratic', 32, [128, 128], 8, 2, (1, 130))
+run_latent('latent affine pipe d32', 'affine', 32, [128, 128], 8, 2, (1, 129, 300))
