@@ -38,7 +38,7 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     if (L->latent_dim > 0 && !latent) return set_error(STB_EINVAL, "layer expects a latent input");
     if ((L->kind == STB_CONT_AFFINE) && !t) return set_error(STB_EINVAL, "layer expects a time input");
     if (ldj_mode != STB_LDJ_NONE && !ldj) return set_error(STB_EINVAL, "ldj_mode set but ldj is NULL");
-    if (L->packed && !ldiag && tc_layer_supported(L))
+    if (L->packed && !ldiag && tc_layer_supported(L) && !(bins && L->n_bins != 16))
         return tc_layer_apply(L, direction, x, latent, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tcw_layer_supported(L) && tcw_image_present(L))
         return tcw_layer_apply(L, tcw_image(L), direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);

@@ -103,7 +103,8 @@ struct Header {                      // 1024 bytes
                                      // +-100 (log2 units), so exp2 needs no max subtraction
     int32_t n_lat;                   // `latent=` columns of the conditioner input (coupling.py:64-65): GEMM1 columns
                                      // n_cond .. n_cond + n_lat - 1 are latent[row, 0 .. n_lat - 1]
-    int32_t pad[256 - 12 - kK1 - kMaxTr];
+    int32_t n_bins;                  // 2 .. 16 real bins; the packed layout always has 16 (padded bins: weight 0, bias -inf)
+    int32_t pad[256 - 13 - kK1 - kMaxTr];
 };
 static_assert(sizeof(Header) == 1024, "header layout");
 constexpr uint32_t kOffB1 = 1024;                                  // float[64]
@@ -695,7 +696,8 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
                  : "memory");
 }
 
-template <int KIND, bool INVERSE>
+// FULL = false: layers with fewer than 16 bins (2 .. 16, read per layer from the header; tc_spline16.cuh)
+template <int KIND, bool INVERSE, bool FULL = true>
 __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args A) {
     extern __shared__ __align__(128) uint8_t smem_p[];      // (1024 would cost a kilobyte of static padding: 2 CTAs then need all 228 KB)
     uint8_t* smem = smem_p;
@@ -879,6 +881,7 @@ __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args
                 }
                 const int n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_chunks = hdr->n_chunks, act = hdr->act;
                 const int n_lat = hdr->n_lat;
+                const int K = FULL ? kBins : hdr->n_bins;
                 const float s2 = hdr->s2, s2l = s2 * 1.4426950408889634f;
                 const uint32_t noshift_mask = hdr->noshift_mask;
                 float lo = A.lower_l[l], hi = A.upper_l[l], inv_span = 1.f / (hi - lo);
@@ -961,7 +964,7 @@ __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
-                            loc = rqs16_locate<INVERSE>(t, shift, lo, inv_span, xv);
+                            loc = rqs16_locate<INVERSE, FULL>(t, shift, lo, inv_span, xv, K);
                         }
                         float dd[16];
                         tmem_ld16(col0 + 2 * kBins, dd);
@@ -973,8 +976,8 @@ __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args
                             float r0, r1;
                             pick_pair16(dd, loc.k, r0, r1);
                             const float u0 = (loc.k == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + loc.k - 1]);
-                            const float u1 = (loc.k == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
-                            rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
+                            const float u1 = (loc.k == K - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
+                            rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld, K);
                         }
                     } else {
                         const float span = hi - lo;
@@ -987,7 +990,7 @@ __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args
                             tmem_ld_wait();
 #pragma unroll
                             for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
-                            sel = cubic16_locate<INVERSE>(t, shift, u);
+                            sel = cubic16_locate<INVERSE, FULL>(t, shift, u, K);
                         }
                         float dd[8];
                         tmem_ld8(col0 + 2 * kBins, dd);
@@ -997,7 +1000,7 @@ __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args
                         if (lane == 0) mbar_arrive_a(empty_bar + buf * 8);
                         if (inside) {
                             const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
-                            cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);
+                            cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld, K);
                         }
                     }
                     if (ji < n_tr) asm volatile("st.shared.f32 [%0], %1;" ::"r"(xrow_a + j4), "f"(out) : "memory");
@@ -1058,7 +1061,7 @@ __global__ void __launch_bounds__(kPThreads, 2) tc_spline_pair_kernel(const Args
 struct PackArgs {
     const float *W1, *b1, *W2, *b2;
     uint8_t* out;
-    int kind, dim, n_cond, n_tr, n_chunks, P, act, n_lat;
+    int kind, dim, n_cond, n_tr, n_chunks, P, act, n_lat, n_bins;
     int cond_idx[kK1];
     int tr_idx[kMaxTr];
 };
@@ -1075,9 +1078,15 @@ __global__ void tc_maxabs_kernel(const PackArgs a) {
     if ((threadIdx.x & 31) == 0) atomicMax(&reinterpret_cast<Header*>(a.out)->maxbits, __float_as_uint(m));
 }
 
-// column c of a dim's 48 -> parameter index: the 32 softmax columns are interleaved (w_i, h_i)
-__host__ __device__ __forceinline__ int param_of_col(int c) {
-    return (c < 2 * kBins) ? ((c & 1) ? kBins + (c >> 1) : (c >> 1)) : c;
+// column c of a dim's 48 -> parameter index in the network's [w(K) | h(K) | rest] order, -1 for padding: the 32
+// softmax columns are interleaved (w_i, h_i), i < 16; columns 32 .. 47 carry the K - 1 derivatives (cubic: the 2 end slopes)
+__host__ __device__ __forceinline__ int param_of_col(int c, int K, int P) {
+    if (c < 2 * kBins) {
+        const int i = c >> 1;
+        return (i < K) ? ((c & 1) ? K + i : i) : -1;
+    }
+    const int p = 2 * K + (c - 2 * kBins);
+    return (p < P) ? p : -1;
 }
 
 __device__ __forceinline__ uint32_t core_off(int r, int k, int K, int elem) {
@@ -1099,6 +1108,7 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     if (gtid == 0) {
         hdr->magic = kMagic; hdr->kind = a.kind; hdr->dim = a.dim; hdr->n_cond = a.n_cond; hdr->n_tr = a.n_tr;
         hdr->n_chunks = a.n_chunks; hdr->P = a.P; hdr->act = a.act; hdr->s2 = s2; hdr->n_lat = a.n_lat;
+        hdr->n_bins = a.n_bins;
         for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
         for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
     }
@@ -1106,8 +1116,9 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     float* b2 = reinterpret_cast<float*>(a.out + kOffB2);
     for (int i = gtid; i < kHid; i += gsz) b1[i] = a.b1[i];
     for (int i = gtid; i < kMaxChunks * kChunkN; i += gsz) {
-        const int ji = i / kPPad, col = i % kPPad, p = param_of_col(col);
-        const float bv = (ji < a.n_tr && p < a.P) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
+        const int ji = i / kPPad, col = i % kPPad, p = param_of_col(col, a.n_bins, a.P);
+        float bv = (ji < a.n_tr && p >= 0) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
+        if (col < 2 * kBins && p < 0 && ji < a.n_tr) bv = -INFINITY;   // padded bin: numerator 2^-inf = 0 exactly
         b2[i] = (col < 2 * kBins) ? bv * 1.4426950408889634f : bv;    // softmax columns: log2 domain
     }
     // first Linear, conditioning columns only: [64][32] as three bf16 parts
@@ -1127,9 +1138,9 @@ __global__ void tc_pack_kernel(const PackArgs a) {
     const float inv = 1.f / s2;
     for (int i = gtid; i < kMaxChunks * kChunkN * kHid; i += gsz) {
         const int k = i % kHid, rn = i / kHid, n = rn % kChunkN, c = rn / kChunkN;
-        const int ji = c * kG + n / kPPad, p = param_of_col(n % kPPad);
+        const int ji = c * kG + n / kPPad, p = param_of_col(n % kPPad, a.n_bins, a.P);
         float v = 0.f;
-        if (c < a.n_chunks && ji < a.n_tr && p < a.P) v = a.W2[((size_t)a.tr_idx[ji] * a.P + p) * kHid + k] * inv;
+        if (c < a.n_chunks && ji < a.n_tr && p >= 0) v = a.W2[((size_t)a.tr_idx[ji] * a.P + p) * kHid + k] * inv;
         __half hi, lo;
         split_f16(v, hi, lo);
         const uint32_t off = kOffW2 + (uint32_t)c * kChunkBytes + core_off(n, k, kHid, 2);
@@ -1145,10 +1156,13 @@ __global__ void tc_bound_kernel(const PackArgs a) {
     const int ji = threadIdx.x >> 5, p = threadIdx.x & 31;
     bool ok = false;
     if (ji < a.n_tr && (a.act == STB_ACT_TANH || a.act == STB_ACT_SIGMOID)) {
-        const size_t row = (size_t)a.tr_idx[ji] * a.P + p;
-        float l1 = fabsf(a.b2[row]);
-        for (int k = 0; k < kHid; ++k) l1 += fabsf(a.W2[row * kHid + k]);
-        ok = (l1 * 1.4426950408889634f <= 100.f);            // false for NaN / inf
+        ok = true;
+        if (p < 2 * a.n_bins) {                              // the 2 K softmax rows of the dim: [w(K) | h(K)]
+            const size_t row = (size_t)a.tr_idx[ji] * a.P + p;
+            float l1 = fabsf(a.b2[row]);
+            for (int k = 0; k < kHid; ++k) l1 += fabsf(a.W2[row * kHid + k]);
+            ok = (l1 * 1.4426950408889634f <= 100.f);        // false for NaN / inf
+        }
     }
     ok = __all_sync(0xffffffffu, ok);
     if (p == 0 && ok) atomicOr(&reinterpret_cast<Header*>(a.out)->noshift_mask, 1u << ji);
@@ -1167,7 +1181,9 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
     a.n_lat = L->latent_dim;
     if (a.n_cond + a.n_lat > kK1) return false;              // [conditioning columns | latent] share GEMM1's 32 K columns
     a.n_chunks = (a.n_tr + kG - 1) / kG;
-    a.kind = L->kind; a.dim = L->dim; a.P = L->kind == STB_RQS ? 3 * kBins - 1 : 2 * kBins + 2;
+    a.n_bins = L->n_bins;
+    if (a.n_bins < 2 || a.n_bins > kBins) return false;
+    a.kind = L->kind; a.dim = L->dim; a.P = L->kind == STB_RQS ? 3 * a.n_bins - 1 : 2 * a.n_bins + 2;
     a.act = L->net.activation;
     a.W1 = L->net.W[0]; a.b1 = L->net.b[0]; a.W2 = L->net.W[1]; a.b2 = L->net.b[1];
     return true;
@@ -1178,11 +1194,12 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
 bool tc_layer_supported(const stb_layer* L) {
     using namespace tcl;
     if (L->kind != STB_RQS && L->kind != STB_CUBIC) return false;
-    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim < 0 || L->time_input) return false;
+    if (L->n_bins < 2 || L->n_bins > kBins || !L->cond_x || L->zero_cond || L->latent_dim < 0 || L->time_input) return false;
     if (L->has_box || L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
     const stb_mlp& N = L->net;
     if (N.n_linear != 2 || N.dims[1] != kHid || N.final_activation != STB_ACT_NONE) return false;
     if (N.dims[0] != L->dim + L->latent_dim) return false;
+    if (N.dims[2] != L->dim * (L->kind == STB_RQS ? 3 * L->n_bins - 1 : 2 * L->n_bins + 2)) return false;
     // The hidden activations feed the next GEMM as fp16 hi | lo parts: only activations bounded by 1 are safe
     // (a ReLU / ELU / ... output above 65504 would split into +inf, -inf -> NaN, where the reference and the
     // CUDA-core kernel stay finite).  Other activations take the generic kernel.
@@ -1219,6 +1236,43 @@ int tc_pack_layer(const stb_layer* L, void* out, cudaStream_t stream) {
     return STB_OK;
 }
 
+namespace tcl {
+static int sm_count() {
+    static thread_local int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    return n_sm;
+}
+
+// the two-CTA whole-flow kernel over A.n_layers >= 1 layers (A.chain_packed / lower_l / upper_l / n_chunks_l filled)
+static int launch_pair(Args& A, int kind, bool full, int64_t rows, cudaStream_t stream) {
+    void (*kern)(Args);
+    if (full) {
+        if (kind == STB_RQS) kern = A.inverse ? tc_spline_pair_kernel<STB_RQS, true, true> : tc_spline_pair_kernel<STB_RQS, false, true>;
+        else kern = A.inverse ? tc_spline_pair_kernel<STB_CUBIC, true, true> : tc_spline_pair_kernel<STB_CUBIC, false, true>;
+    } else {
+        if (kind == STB_RQS) kern = A.inverse ? tc_spline_pair_kernel<STB_RQS, true, false> : tc_spline_pair_kernel<STB_RQS, false, false>;
+        else kern = A.inverse ? tc_spline_pair_kernel<STB_CUBIC, true, false> : tc_spline_pair_kernel<STB_CUBIC, false, false>;
+    }
+    const long long ptiles = (rows + kPRows - 1) / kPRows;
+    if (ptiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
+    A.n_tiles = (int)ptiles;
+    cudaError_t pe = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmemBytes);
+    if (pe == cudaSuccess) pe = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (pe != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(pe));
+    const int pgrid = (int)min((long long)2 * sm_count(), ptiles);
+    kern<<<pgrid, kPThreads, kPSmemBytes, stream>>>(A);
+    count_launch();
+    pe = cudaGetLastError();
+    if (pe != cudaSuccess) return set_error(STB_ECUDA, "tc_spline_pair_kernel launch: %s", cudaGetErrorString(pe));
+    return STB_OK;
+}
+}  // namespace tcl
+
 int tc_layer_apply(const stb_layer* L, int direction, const float* x, const float* latent, float* y, float* ldj,
                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins) {
     using namespace tcl;
@@ -1227,6 +1281,21 @@ int tc_layer_apply(const stb_layer* L, int direction, const float* x, const floa
     A.bins = bins;
     A.latent = L->latent_dim > 0 ? latent : nullptr;
     A.lat_stride = L->latent_dim;
+    if (L->n_bins != kBins) {            // fewer than 16 bins: the padded-bin variant lives in the two-CTA kernel
+        if (bins) return set_error(STB_ENOTSUP, "the bin-index instrument of the tensor-core path covers 16-bin layers");
+        PackArgs pa;
+        if (!fill_pack_args(L, pa)) return set_error(STB_EINVAL, "layer has no tensor-core path");
+        A.x = x; A.y = y; A.ldj = ldj;
+        A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
+        A.base_log_prob = base_log_prob;
+        A.inverse = direction == STB_INVERSE;
+        A.rows = rows;
+        A.n_layers = 1; A.dim = L->dim;
+        A.chain_packed[0] = static_cast<const uint8_t*>(L->packed);
+        A.lower_l[0] = L->lower; A.upper_l[0] = L->upper;
+        A.n_chunks_l[0] = pa.n_chunks;
+        return launch_pair(A, L->kind, false, rows, stream);
+    }
     A.packed = static_cast<const uint8_t*>(L->packed);
     A.x = x; A.y = y; A.ldj = ldj;
     A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
@@ -1316,26 +1385,13 @@ int tc_chain_apply(const stb_layer* const* layers, int n, int direction, const f
     // Two independent 128-row CTAs per SM instead of one 256-row CTA.  Measured on the headline workload (2^22 rows):
     // 1.73e8 vs 1.77e8 samples/s -- the heads do fall into the other CTA's chunk phases, but the kernel is bound by
     // the epilogue's instruction stream, not by that bubble, so nothing is gained; it IS faster when there are fewer
-    // 256-row tiles than SMs (twice as many CTAs to spread over the machine), which is when it is selected.
-    // STRIBOR_B200_PAIR=1 / 0 forces / forbids it.
+    // 256-row tiles than SMs (twice as many CTAs to spread over the machine), which is when it is selected -- and it
+    // is the kernel of layers with fewer than 16 bins.  STRIBOR_B200_PAIR=1 / 0 forces / forbids it (16-bin flows).
     static const int pair_env = [] { const char* ev = getenv("STRIBOR_B200_PAIR"); return (ev && ev[0]) ? (ev[0] == '1' ? 1 : 0) : -1; }();
-    const bool use_pair = pair_env >= 0 ? pair_env == 1 : tiles < (long long)n_sm;
-    if (use_pair) {
-        if (layers[0]->kind == STB_RQS) kern = A.inverse ? tc_spline_pair_kernel<STB_RQS, true> : tc_spline_pair_kernel<STB_RQS, false>;
-        else kern = A.inverse ? tc_spline_pair_kernel<STB_CUBIC, true> : tc_spline_pair_kernel<STB_CUBIC, false>;
-        const long long ptiles = (rows + kPRows - 1) / kPRows;
-        if (ptiles > 0x7fffffffLL) return set_error(STB_EINVAL, "too many rows");
-        A.n_tiles = (int)ptiles;
-        cudaError_t pe = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmemBytes);
-        if (pe == cudaSuccess) pe = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (pe != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(pe));
-        const int pgrid = (int)min((long long)2 * n_sm, ptiles);
-        kern<<<pgrid, kPThreads, kPSmemBytes, stream>>>(A);
-        count_launch();
-        pe = cudaGetLastError();
-        if (pe != cudaSuccess) return set_error(STB_ECUDA, "tc_spline_pair_kernel launch: %s", cudaGetErrorString(pe));
-        return STB_OK;
-    }
+    bool full = true;
+    for (int i = 0; i < n; ++i) full = full && layers[i]->n_bins == kBins;
+    const bool use_pair = !full || (pair_env >= 0 ? pair_env == 1 : tiles < (long long)n_sm);
+    if (use_pair) return launch_pair(A, layers[0]->kind, full, rows, stream);
     if (layers[0]->kind == STB_RQS) kern = A.inverse ? tc_spline_layer_kernel<STB_RQS, true, true> : tc_spline_layer_kernel<STB_RQS, false, true>;
     else kern = A.inverse ? tc_spline_layer_kernel<STB_CUBIC, true, true> : tc_spline_layer_kernel<STB_CUBIC, false, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);

@@ -117,7 +117,7 @@ struct CubSel {
 // >= 1e-2 and O(1), never subnormal or huge.
 __device__ __forceinline__ float sigmoid_fast(float v) { return fdiv(1.f, 1.f + ex2_approx(-1.4426950408889634f * v)); }
 
-__device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float ur) {
+__device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float ur, int K = kBins) {
     float inv_wk;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_wk) : "f"(s.wk));
     inv_wk = fmaf(fmaf(-s.wk, inv_wk, 1.f), inv_wk, inv_wk);         // 1 / w_k to ~1 ulp, used three times
@@ -130,7 +130,7 @@ __device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float u
         dl = fminf(fminf(fabsf(sp), fabsf(sk)), fdiv(0.5f * (s.wk * sp + s.wp * sk), s.wp + s.wk)) *
              (sign_f(sp) + sign_f(sk));
     }
-    if (s.k == kBins - 1) {
+    if (s.k == K - 1) {
         dr = sigmoid_fast(ur) * 3.f * sk;
     } else {
         const float sn = fdiv(s.hn, s.wn);
@@ -143,7 +143,7 @@ __device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float u
     r.c = dl;
     r.d = s.ch;
     r.xl = s.cw;
-    r.xr = (s.k == kBins - 1) ? 1.f : s.cw + s.wk;
+    r.xr = (s.k == K - 1) ? 1.f : s.cw + s.wk;
     return r;
 }
 
@@ -198,9 +198,13 @@ struct BinSearch16 {
     bool p3, p2, p1, p0; // bits of k
 };
 
-template <bool ON_H>
+// FULL = false: K <= 16 real bins, the numerators of bins K .. 15 are exactly 0 (their packed biases are -inf), so
+// every sum below is already right; the only changes are the scale 1 - K min and that a padded knot index (>= K)
+// must never compare true (for an inside key it could only at key == upper, where the reference's nudged last knot
+// keeps the last REAL bin).
+template <bool ON_H, bool FULL = true>
 __device__ __forceinline__ BinSearch16 bin_search16(const float2* t, float min_size, float key01, float2& e_even,
-                                                    float2& e_odd) {
+                                                    float2& e_odd, int K = kBins) {
     float2 s8[8], s4[4], s2[2];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s8[i] = __fadd2_rn(t[2 * i], t[2 * i + 1]);
@@ -210,21 +214,21 @@ __device__ __forceinline__ BinSearch16 bin_search16(const float2* t, float min_s
     s2[1] = __fadd2_rn(s4[2], s4[3]);
     BinSearch16 r;
     r.S = __fadd2_rn(s2[0], s2[1]);
-    const float scale = 1.f - min_size * (float)kBins;
+    const float scale = 1.f - min_size * (float)(FULL ? kBins : K);
     r.c = f2(fdiv(scale, r.S.x), fdiv(scale, r.S.y));
     const float inv_c = (ON_H ? r.S.y : r.S.x) * (1.f / scale);
     const float step = min_size * inv_c;
     float base = key01 * inv_c;                    // threshold of index i: base - (i - position) step
 #define STB_SEARCHED(v) (ON_H ? (v).y : (v).x)
-    r.p3 = STB_SEARCHED(s2[0]) <= fmaf(-8.f, step, base);
+    r.p3 = (STB_SEARCHED(s2[0]) <= fmaf(-8.f, step, base)) && (FULL || 8 < K);
     float2 E = sel2(r.p3, s2[0], f2(0.f));
     base = r.p3 ? fmaf(-8.f, step, base) : base;
     float2 cand = __fadd2_rn(E, sel2(r.p3, s4[2], s4[0]));
-    r.p2 = STB_SEARCHED(cand) <= fmaf(-4.f, step, base);
+    r.p2 = (STB_SEARCHED(cand) <= fmaf(-4.f, step, base)) && (FULL || (r.p3 ? 12 : 4) < K);
     E = sel2(r.p2, cand, E);
     base = r.p2 ? fmaf(-4.f, step, base) : base;
     cand = __fadd2_rn(E, sel2(r.p3, sel2(r.p2, s8[6], s8[4]), sel2(r.p2, s8[2], s8[0])));
-    r.p1 = STB_SEARCHED(cand) <= fmaf(-2.f, step, base);
+    r.p1 = (STB_SEARCHED(cand) <= fmaf(-2.f, step, base)) && (FULL || (r.p3 ? 8 : 0) + (r.p2 ? 4 : 0) + 2 < K);
     E = sel2(r.p1, cand, E);
     base = r.p1 ? fmaf(-2.f, step, base) : base;
     // numerators of the pair 4 p3 + 2 p2 + p1: selected p3 first (known earliest)
@@ -236,7 +240,7 @@ __device__ __forceinline__ BinSearch16 bin_search16(const float2* t, float min_s
     e_even = sel2(r.p1, b[2], b[0]);
     e_odd = sel2(r.p1, b[3], b[1]);
     cand = __fadd2_rn(E, e_even);
-    r.p0 = STB_SEARCHED(cand) <= base - step;
+    r.p0 = (STB_SEARCHED(cand) <= base - step) && (FULL || (r.p3 ? 8 : 0) + (r.p2 ? 4 : 0) + (r.p1 ? 2 : 0) + 1 < K);
     r.Ek = sel2(r.p0, cand, E);
 #undef STB_SEARCHED
     r.k = (r.p3 ? 8 : 0) + (r.p2 ? 4 : 0) + (r.p1 ? 2 : 0) + (r.p0 ? 1 : 0);
@@ -252,11 +256,11 @@ struct RqsLoc {
 // t[0..16): log2(e)-scaled raw (width, height) pairs (destroyed).  Leaves E_k and E_(k+1) of both
 // axes: the knots of bin k, from which its width / height are re-derived as the reference does
 // (rational_quadratic_spline.py:180-192).
-template <bool ON_H>
-__device__ __forceinline__ RqsLoc rqs16_locate(float2* t, bool shift, float lo, float inv_span, float key) {
+template <bool ON_H, bool FULL = true>
+__device__ __forceinline__ RqsLoc rqs16_locate(float2* t, bool shift, float lo, float inv_span, float key, int K = kBins) {
     softmax16_num2(t, shift);
     float2 ee, eo;
-    const BinSearch16 bs = bin_search16<ON_H>(t, STB_RQS_MIN, (key - lo) * inv_span, ee, eo);
+    const BinSearch16 bs = bin_search16<ON_H, FULL>(t, STB_RQS_MIN, (key - lo) * inv_span, ee, eo, K);
     RqsLoc r;
     r.c = bs.c;
     r.k = bs.k;
@@ -306,13 +310,13 @@ __device__ __forceinline__ float2 softplus_fast2(float2 v) {
 // u0 / u1: (bias-added, unscaled) derivative parameters at the two knots of bin r.k
 template <bool INVERSE>
 __device__ __forceinline__ void rqs16_finish(const RqsLoc& r, float u0, float u1, float lo, float hi, bool want_ld,
-                                             float x, float& out, float& ld) {
+                                             float x, float& out, float& ld, int K = kBins) {
     const float span = hi - lo;
     const float km = (float)r.k * STB_RQS_MIN;
     float2 k0 = __ffma2_rn(f2(span), __ffma2_rn(r.c, r.Ek, f2(km)), f2(lo));                   // (x_k, y_k)
     float2 k1 = __ffma2_rn(f2(span), __ffma2_rn(r.c, r.Ek1, f2(km + STB_RQS_MIN)), f2(lo));    // (x_k+1, y_k+1)
     if (r.k == 0) k0 = f2(lo);                                       // knot_0 / knot_K forced to the box
-    if (r.k == kBins - 1) k1 = f2(hi);
+    if (r.k == K - 1) k1 = f2(hi);
     const float2 wh = __fadd2_rn(k1, f2(-k0.x, -k0.y));              // sizes re-derived from the knots (:185)
     const float2 dd = __fadd2_rn(softplus_fast2(f2(u0, u1)), f2(STB_RQS_MIN));
     RqsBin16 b;
@@ -348,11 +352,11 @@ __device__ __forceinline__ void rqs16_finish(const RqsLoc& r, float u0, float u1
 // same search; the three bin sizes around bin k that the slopes need are picked from the
 // numerators by a select tree on the bits of k and normalised afterwards (the cubic code uses the
 // sizes themselves, not knot differences).
-template <bool ON_H>
-__device__ __forceinline__ CubSel cubic16_locate(float2* t, bool shift, float u) {
+template <bool ON_H, bool FULL = true>
+__device__ __forceinline__ CubSel cubic16_locate(float2* t, bool shift, float u, int K = kBins) {
     softmax16_num2(t, shift);
     float2 ee, eo;
-    const BinSearch16 bs = bin_search16<ON_H>(t, STB_CUB_MIN, u, ee, eo);
+    const BinSearch16 bs = bin_search16<ON_H, FULL>(t, STB_CUB_MIN, u, ee, eo, K);
     const int k = bs.k;
     // neighbours: k even -> (t[k-1], ee, eo); k odd -> (ee, eo, t[k+1]).  t[k-1] for even k = odd element
     // of the previous pair, t[k+1] for odd k = even element of the next pair: one more 8-way select each
@@ -428,9 +432,9 @@ __device__ __forceinline__ float cubic16_inverse_in_bin(const CubBin& k, float u
 
 template <bool INVERSE>
 __device__ __forceinline__ void cubic16_finish(const CubSel& s, float ul, float ur, float lo, float hi, bool want_ld,
-                                               float u, float& out, float& ld) {
+                                               float u, float& out, float& ld, int K = kBins) {
     const float span = hi - lo;
-    const CubBin b = cubic16_bin(s, ul, ur);
+    const CubBin b = cubic16_bin(s, ul, ur, K);
     if (!INVERSE) {
         out = cubic_forward_in_bin(b, u, ld) * span + lo;
     } else {

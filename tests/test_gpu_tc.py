@@ -253,6 +253,77 @@ def test_latent_input_on_the_tensor_path(kind, d, hidden, latent_dim, n_layers, 
             assert fail <= 2e-2, f'{what}: {fail:.3%} outside tolerance (max abs err {mx:.3e})'
 
 
+@pytest.mark.parametrize('kind,d,K,n_layers,rows,masks', [
+    ('quadratic', 64, 8, 3, 700, cases.ALT),
+    ('quadratic', 64, 5, 8, 300, cases.ALT),
+    ('quadratic', 30, 2, 2, 257, ('parity_even', 'parity_odd')),
+    ('quadratic', 64, 15, 1, 130, cases.ALT),
+    ('quadratic', 32, 10, 3, 50000, cases.ALT),           # many tiles per CTA
+    ('cubic', 64, 8, 3, 700, cases.ALT),
+    ('cubic', 33, 3, 2, 300, ('ordered_left_half', 'parity_odd')),
+    ('cubic', 64, 12, 1, 129, cases.ALT),
+])
+def test_fewer_than_16_bins_on_the_tensor_path(kind, d, K, n_layers, rows, masks, monkeypatch):
+    """Spline couplings with 2 <= n_bins < 16 run on the tensor-core path too: the packed image keeps its 16-bin
+    layout, padded bins get weight 0 / bias -inf (numerator exactly 0) and the search never selects them
+    (tc_spline16.cuh, FULL = false).  Against the CUDA-core kernel and the oracle, both directions."""
+    rs = cases._rs(1300 + d + K)
+    spec = [cases.coupling_spec(rs, kind, d, [64], masks[i % 2], n_bins=K, lower=-4., upper=4.) for i in range(n_layers)]
+    torch.manual_seed(rows + K)
+    x = torch.randn(rows, d, device=DEV) * 1.6                   # a good share of elements outside the box, and inside
+    x[0, :] = 4.0                                               # exactly on the upper box edge: the last REAL bin
+    x[1 % rows, :] = -4.0
+
+    def build():
+        layers = [l.to(DEV) for l in layers_from_spec(spec)]
+        return st.NormalizingFlow(st.UnitNormal(d), layers), layers
+
+    tflow, tl = build()
+    with torch.no_grad():
+        desc = tl[0].describe(d, 0, torch.device(DEV))
+        assert desc['packed'] is not None, 'tensor path was not selected'
+        L = _ops.make_struct(desc['meta'], desc['fmeta'], desc['mask'], [p.detach() for p in desc['params']], desc['packed'])
+        assert _lib.lib().stb_layer_uses_tensor_path(ctypes.byref(L)) == 1
+        tflow.log_prob(x[:4])
+        n0 = _ops.launch_count()
+        lp_t = tflow.log_prob(x)
+        assert _ops.launch_count() - n0 == 1
+        xi_t, li_t = tflow.inverse_and_log_det_jacobian(x)
+        yf_t, lf_t = tflow.forward_and_log_det_jacobian(x)
+        back = tflow.inverse(yf_t)
+    assert torch.isfinite(lp_t).all() and torch.isfinite(xi_t).all() and torch.isfinite(yf_t).all()
+    monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', '1')
+    gflow, _ = build()
+    with torch.no_grad():
+        lp_g = gflow.log_prob(x)
+        xi_g, li_g = gflow.inverse_and_log_det_jacobian(x)
+        yf_g, lf_g = gflow.forward_and_log_det_jacobian(x)
+    tol = 5e-4 if n_layers > 3 else 2e-4
+    # the two rows that sit exactly on the box edges: a layer maps the edge to the edge +- 1 ulp, and which side of it
+    # the NEXT layer sees decides "inside / identity" for that element -- compare their log-dets only for one layer
+    body = slice(0, None) if n_layers == 1 else slice(2, None)
+    if kind == 'cubic':
+        assert ((xi_t - xi_g).abs() > 1e-4).float().mean().item() < 5e-3
+        assert ((li_t - li_g).abs() > 1e-3).float().mean().item() < 2e-2
+        assert ((back - x).abs() > 1e-3).float().mean().item() < 5e-3
+    else:
+        assert (xi_t - xi_g).abs().max().item() < tol
+        assert (li_t - li_g)[body].abs().max().item() < 5 * tol
+        assert ((lp_t - lp_g).abs() <= 5 * tol + 1e-5 * lp_g.abs())[body].all().item()
+        assert (back - x).abs().max().item() < 1e-3
+    assert (yf_t - yf_g).abs().max().item() < tol and (lf_t - lf_g)[body].abs().max().item() < 5 * tol
+    if rows <= 1000:
+        xc = x.cpu()
+        s64 = O.spec_to(spec, torch.float64)
+        for got, f32, f64, what in (
+                (xi_t, O.flow_inverse(spec, xc), O.flow_inverse(s64, xc.double()), 'inverse x'),
+                (yf_t, O.flow_forward(spec, xc), O.flow_forward(s64, xc.double()), 'forward y'),
+                (lf_t, O.flow_forward(spec, xc, with_ldj=True)[1], O.flow_forward(s64, xc.double(), with_ldj=True)[1], 'forward ldj'),
+                (lp_t, O.flow_log_prob(spec, xc), O.flow_log_prob(s64, xc.double()), 'log_prob')):
+            fail, _, mx = close_or_arbitrated(got, f32, f64, 1e-5, 1e-4 if 'ldj' in what or what == 'log_prob' else 1e-5)
+            assert fail <= 2e-2, f'{what}: {fail:.3%} outside tolerance (max abs err {mx:.3e})'
+
+
 @pytest.mark.parametrize('hidden', [[64], [128, 128]])
 def test_continuous_affine_with_latent_on_the_tensor_path(hidden, monkeypatch):
     """ContinuousAffineCoupling with `latent=`: the conditioner reads [x * mask | latent | t] (coupling.py:140-154)."""
