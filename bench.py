@@ -278,6 +278,20 @@ def _cpu_rate(fn, units, min_seconds=0.0):
     return units / dt, n_threads, dt
 
 
+def _parity_block(got, w32, w64, what):
+    """SURVEY 8c's rule on sampled rows of the timed batch: inside rtol = atol = 1e-5 of the fp32 oracle, or no further
+    from the fp64 oracle than the fp32 oracle itself is (+ the tolerance)."""
+    got, w32, w64 = got.double().reshape(-1), w32.double().reshape(-1), w64.double().reshape(-1)
+    tol = 1e-5 + 1e-5 * w64.abs()
+    c1 = (got - w32).abs() <= tol
+    c2 = (got - w64).abs() <= (w32 - w64).abs() + tol
+    return {'values': int(got.numel()), 'of': what, 'rtol': 1e-5, 'atol': 1e-5,
+            'frac_outside': float(1.0 - (c1 | c2).double().mean()),
+            'frac_needing_fp64_arbitration': float(((~c1) & c2).double().mean()),
+            'max_abs': float((got - w64).abs().max()), 'oracle_fp32_max_abs': float((w32 - w64).abs().max()),
+            'rule': '|new-ref32| <= atol+rtol|ref| or |new-ref64| <= |ref32-ref64| + atol+rtol|ref| (SURVEY 8c)'}
+
+
 def side_config(workload, args, dev, rank, world, want_cpu):
     """One side configuration -> its result dict (same fields as the headline: value / e2e / roofline /
     cpu_baseline).  Rows are sharded over the ranks exactly like the headline."""
@@ -477,6 +491,30 @@ def side_config(workload, args, dev, rank, world, want_cpu):
         res['e2e'] = {'value': per_step / (ms_e * 1e-3), 'unit': unit, 'h2d_bytes_per_step': y_h.numel() * 4 * world,
                       'd2h_bytes_per_step': 4 * world, 'how': 'pinned host batch -> H2D -> DataParallelNLL.step -> loss.item()'}
         res['allreduce_bytes_per_step'] = int(dp.last_allreduce_bytes)
+    # parity of the timed inputs: sampled rows re-evaluated by the oracle in fp32 and fp64 (rank 0, with the CPU legs)
+    if want_cpu and workload != 'train' and args.parity_rows > 0:
+        n = min(2048, args.parity_rows, ins[0].shape[0])
+        idx = torch.randperm(ins[0].shape[0], generator=torch.Generator().manual_seed(7))[:n].sort().values.to(dev)
+        sub = [t_[idx] for t_ in ins]
+        with torch.no_grad():
+            got = pipe_fn(*sub)
+        got = got if isinstance(got, (tuple, list)) else (got,)
+        spec_p = spec_from_layers([l.cpu() for l in build_layers(kind_w, hid_w)]) if workload in ('cubic', 'quadratic_h256') else spec
+        s64 = O.spec_to(spec_p, torch.float64)
+        subc = [t_.cpu() for t_ in sub]
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+        with torch.no_grad():
+            if workload == 'neural':
+                w32 = (O.neural_flow_forward(spec_p, subc[0], subc[1]),)
+                w64 = (O.neural_flow_forward(s64, subc[0].double(), subc[1].double()),)
+            elif workload == 'affine':
+                w32 = (O.flow_log_prob(spec_p, subc[0]), O.flow_inverse(spec_p, subc[0]))
+                w64 = (O.flow_log_prob(s64, subc[0].double()), O.flow_inverse(s64, subc[0].double()))
+            else:
+                w32 = (O.flow_log_prob(spec_p, subc[0]),)
+                w64 = (O.flow_log_prob(s64, subc[0].double()),)
+        blocks = [_parity_block(g.cpu(), a, b, f'{n} rows of the timed batch, fixed seed') for g, a, b in zip(got, w32, w64)]
+        res['parity'] = blocks[0] if len(blocks) == 1 else {'log_prob': blocks[0], 'inverse': blocks[1]}
     if cpu is not None:
         v, cores, secs, what = cpu
         res['cpu_baseline'] = {'value': v, 'unit': unit, 'cores': cores, 'kind': 'port',
