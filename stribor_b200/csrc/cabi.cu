@@ -41,7 +41,7 @@ static int apply_one(const stb_layer* L, int direction, const float* x, const fl
     if (L->packed && !ldiag && tc_layer_supported(L) && !(bins && L->n_bins != 16))
         return tc_layer_apply(L, direction, x, latent, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tcw_layer_supported(L) && tcw_image_present(L))
-        return tcw_layer_apply(L, tcw_image(L), direction, x, y, ldj, ldj_mode, base_lp, rows, s, bins);
+        return tcw_layer_apply(L, tcw_image(L), direction, x, latent, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tch_layer_supported(L))
         return tch_layer_apply(L, direction, x, latent, y, ldj, ldj_mode, base_lp, rows, s, bins);
     if (L->packed && !ldiag && tcm_layer_supported(L))

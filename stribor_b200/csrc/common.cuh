@@ -48,8 +48,9 @@ bool tcw_layer_supported(const stb_layer* L);
 bool tcw_backward_supported(const stb_layer* L);
 uint64_t tcw_packed_bytes(const stb_layer* L);
 int tcw_pack_layer(const stb_layer* L, void* out, cudaStream_t stream);
-int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const float* x, float* y, float* ldj,
-                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins = nullptr);
+int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const float* x, const float* latent, float* y,
+                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream,
+                    int32_t* bins = nullptr);
 int tcw_layer_backward(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
                        const float* g_ldj, float* g_x, float* g_net, float* hidden, int64_t rows,
                        cudaStream_t stream);

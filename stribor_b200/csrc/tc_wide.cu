@@ -60,7 +60,8 @@ struct Header {                      // 2048 bytes
     float s2;
     uint32_t maxbits;
     uint32_t noshift_mask[2];
-    int32_t pad0[3];
+    int32_t n_lat;                   // `latent=` columns: conditioning slots n_cond .. n_cond + n_lat - 1 (forward kernels only)
+    int32_t pad0[2];
     int32_t cond_idx[kK1];           // conditioning slot -> column
     int32_t tr_idx[kMaxTr];          // transformed slot -> column
     int16_t colmap[kMaxDim];         // column -> slot: >= 0 conditioning slot, < 0: -(transformed slot) - 1
@@ -120,6 +121,7 @@ struct Args {
     float* g_net;
     float* hidden;
     int32_t* bins;            // FWD, optional: [rows, dim] searched bin per element (stb_layer_apply_bins)
+    const float* latent;      // FWD, optional: [rows, n_lat]
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -367,10 +369,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                         }
                     }
                 }
-                // zero the padded conditioning slots [n_cond, k1pad) (the buffer is reused for h every tile)
-                const int npad = k1pad - n_cond;
+                // `latent=` columns (coupling.py:64-65): conditioning slots n_cond .. n_cond + n_lat - 1
+                const int n_lat = hdr->n_lat;
+                for (int i = etid; i < kTileRows * n_lat; i += kEpiThreads) {
+                    const int r = i / n_lat, j = i - r * n_lat;
+                    a1_put(abuf, r, n_cond + j, (r < nrows) ? __ldg(A.latent + (row0 + r) * n_lat + j) : 0.f);
+                }
+                // zero the padded conditioning slots [n_cond + n_lat, k1pad) (the buffer is reused for h every tile)
+                const int npad = k1pad - n_cond - n_lat;
                 for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
-                    const int r = i / npad, m = n_cond + (i - r * npad);
+                    const int r = i / npad, m = n_cond + n_lat + (i - r * npad);
                     a1_zero(abuf, r, m);
                 }
             }
@@ -1300,7 +1308,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
 struct PackArgs {
     const float *W1, *b1, *W2, *b2;
     uint8_t* out;
-    int kind, dim, n_cond, n_tr, n_chunks, P, act;
+    int kind, dim, n_cond, n_tr, n_chunks, P, act, n_lat;
     int16_t colmap[kMaxDim];
     uint8_t cond_idx[kK1];
     uint8_t tr_idx[kMaxTr];
@@ -1339,7 +1347,8 @@ __global__ void tcw_pack_kernel(const PackArgs a) {
     if (gtid == 0) {
         hdr->magic = kMagic; hdr->kind = a.kind; hdr->dim = a.dim; hdr->n_cond = a.n_cond; hdr->n_tr = a.n_tr;
         hdr->n_chunks = a.n_chunks; hdr->P = a.P; hdr->act = a.act; hdr->s2 = s2;
-        hdr->k1pad = (a.n_cond + 15) & ~15;
+        hdr->n_lat = a.n_lat;
+        hdr->k1pad = (a.n_cond + a.n_lat + 15) & ~15;
         if (hdr->k1pad == 0) hdr->k1pad = 16;
         for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
         for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
@@ -1355,7 +1364,9 @@ __global__ void tcw_pack_kernel(const PackArgs a) {
     }
     for (int i = gtid; i < kHid * kK1; i += gsz) {
         const int n = i / kK1, k = i % kK1;
-        const float v = (k < a.n_cond) ? a.W1[(size_t)n * a.dim + a.cond_idx[k]] : 0.f;
+        const size_t in1 = (size_t)(a.dim + a.n_lat);          // the first Linear reads [x * mask | latent]
+        const float v = (k < a.n_cond) ? a.W1[n * in1 + a.cond_idx[k]]
+                                       : ((k < a.n_cond + a.n_lat) ? a.W1[n * in1 + a.dim + (k - a.n_cond)] : 0.f);
         __nv_bfloat16 q0, q1, q2;
         split_bf16x3(v, q0, q1, q2);
         const uint32_t off = kOffW1 + core_off(n, k, kK1, 2);
@@ -1408,6 +1419,8 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
     for (int i = a.n_cond; i < kK1; ++i) a.cond_idx[i] = 0;
     for (int i = a.n_tr; i < kMaxTr; ++i) a.tr_idx[i] = 0;
     if (a.n_tr < 1) return false;
+    a.n_lat = L->latent_dim;
+    if (a.n_lat < 0 || a.n_cond + a.n_lat > kK1 || L->net.dims[0] != L->dim + a.n_lat) return false;
     a.n_chunks = (a.n_tr + kG - 1) / kG;
     a.kind = L->kind; a.dim = L->dim; a.P = L->kind == STB_RQS ? 3 * kBins - 1 : 2 * kBins + 2;
     a.act = L->net.activation;
@@ -1420,7 +1433,7 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
 bool tcw_layer_supported(const stb_layer* L) {
     using namespace tcw;
     if (L->kind != STB_RQS && L->kind != STB_CUBIC) return false;
-    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim != 0 || L->time_input) return false;
+    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim < 0 || L->time_input) return false;
     if (L->has_box || L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
     const stb_mlp& N = L->net;
     if (N.n_linear != 2 || N.dims[1] != kHid || N.final_activation != STB_ACT_NONE) return false;
@@ -1473,11 +1486,12 @@ static int tcw_launch(void (*kern)(tcw::Args), const tcw::Args& A, long long til
     return STB_OK;
 }
 
-int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const float* x, float* y, float* ldj,
-                    int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins) {
+int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const float* x, const float* latent, float* y,
+                    float* ldj, int ldj_mode, int base_log_prob, int64_t rows, cudaStream_t stream, int32_t* bins) {
     using namespace tcw;
     Args A = {};
     A.bins = bins;
+    A.latent = L->latent_dim > 0 ? latent : nullptr;
     A.packed = static_cast<const uint8_t*>(image);
     A.x = x; A.y = y; A.ldj = ldj;
     A.ldj_mode = ldj ? ldj_mode : STB_LDJ_NONE;
@@ -1494,7 +1508,8 @@ int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const 
     return tcw_launch(kern, A, tiles, stream, "tc_wide_kernel");
 }
 
-bool tcw_backward_supported(const stb_layer* L) { return tcw_layer_supported(L); }   // quadratic and cubic (fused variant)
+// quadratic and cubic (fused variant); `latent=` layers train through the element-wise kernels + autograd
+bool tcw_backward_supported(const stb_layer* L) { return tcw_layer_supported(L) && L->latent_dim == 0; }
 
 int tcw_layer_backward(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
                        const float* g_ldj, float* g_x, float* g_net, float* hidden, int64_t rows,

@@ -187,6 +187,8 @@ def test_affine_tensor_path_matches_generic_and_oracle(d, hidden, masks, monkeyp
     ('cubic', 40, [64], 12, 2, 300),           # 20 + 12 = all 32 K columns in use
     ('quadratic', 32, [64], 16, 1, 130),       # one layer: the per-layer kernel
     ('quadratic', 20, [64], 5, 9, 40000),      # more than 8 layers: two chained launches, many tiles
+    ('quadratic', 64, [64], 16, 2, 300),       # 32 conditioning + 16 latent columns > 32: the 128-row kernel (64 K columns)
+    ('cubic', 100, [64], 10, 2, 200),          # d > 64 with a latent input (tc_wide.cu)
     ('quadratic', 32, [128, 128], 8, 2, 300),  # spline with a wide conditioner (tc_hwide.cu)
     ('affine', 32, [128, 128], 8, 2, 500),     # affine, pipelined kernel
     ('affine', 24, [64], 7, 3, 300),           # affine, phase-by-phase kernel (H = 64: no chain with a latent input)
@@ -224,8 +226,10 @@ def test_latent_input_on_the_tensor_path(kind, d, hidden, latent_dim, n_layers, 
             cur, l = f.inverse_and_log_det_jacobian(cur, latent=lat)
             tot = tot + l
     if kind != 'affine':
-        # MLP[64] spline layers chain (<= 8 per launch); wide conditioners go out one launch per layer
-        assert launches == ((n_layers + 7) // 8 if hidden == [64] else n_layers)
+        # MLP[64] spline layers chain (<= 8 per launch) while [conditioning | latent] fits 32 K columns at d <= 64;
+        # the d <= 128 kernel and wide conditioners go out one launch per layer
+        chained = hidden == [64] and d <= 64 and (d + 1) // 2 + latent_dim <= 32
+        assert launches == ((n_layers + 7) // 8 if chained else n_layers)
         assert torch.equal(cur, xi_t)
     monkeypatch.setenv('STRIBOR_B200_FORCE_GENERIC', '1')
     gflow, _ = build()

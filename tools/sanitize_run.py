@@ -115,3 +115,4 @@ run_latent('latent spline chain d32', 'quadratic', 32, [64], 8, 3, (1, 129, 300)
 run_latent('latent cubic single layer d40', 'cubic', 40, [64], 12, 1, (1, 257))
 run_latent('latent hwide d32', 'quadratic', 32, [128, 128], 8, 2, (1, 130))
 run_latent('latent affine pipe d32', 'affine', 32, [128, 128], 8, 2, (1, 129, 300))
+run_latent('latent wide d64 (48 K columns)', 'quadratic', 64, [64], 16, 2, (1, 129, 300))
