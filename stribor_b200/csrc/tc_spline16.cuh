@@ -392,6 +392,37 @@ __device__ __forceinline__ CubSel cubic16_locate(float2* t, bool shift, float u,
 __device__ __forceinline__ float cbrt_fast(float v) {
     return copysignf(ex2_approx(lg2_approx(fabsf(v)) * 0.33333333333333333f), v) * ((v == 0.f) ? 0.f : 1.f);
 }
+// atan2(y, x) for y >= 0 (result in [0, pi]) and sin / cos on [0, pi / 3]: minimax polynomials evaluated in fp32
+// (absolute error ~1.5e-7 / ~1.1e-7, the class of the library routines) -- atan2f + sincosf with their range reduction
+// were 12.5 % of the cubic whole-flow kernel's instructions (profiles/r02_tc_chain_cubic_ncu_summary.txt).
+__device__ __forceinline__ float atan2_upper(float y, float x) {
+    const float ax = fabsf(x);
+    const float mn = fminf(y, ax), mx = fmaxf(y, ax);
+    const float a = (mx > 0.f) ? fdiv(mn, mx) : 0.f;
+    const float s = a * a;
+    float p = fmaf(s, -0.004054553612250179f, 0.02186291228067595f);
+    p = fmaf(p, s, -0.055912267216883055f);
+    p = fmaf(p, s, 0.09642193534850359f);
+    p = fmaf(p, s, -0.13908628358983344f);
+    p = fmaf(p, s, 0.19946565495495794f);
+    p = fmaf(p, s, -0.33329860782060494f);
+    p = fmaf(p, s, 0.9999993355834141f);
+    float r = p * a;
+    r = (y > ax) ? 1.5707963267948966f - r : r;
+    return (x < 0.f) ? 3.141592653589793f - r : r;
+}
+__device__ __forceinline__ void sincos_third(float t, float& sn, float& cs) {      // t in [0, 1.06]
+    const float u = t * t;
+    float ps = fmaf(u, 2.679316525301239e-06f, -0.00019832722144834137f);
+    ps = fmaf(ps, u, 0.008333291415817233f);
+    ps = fmaf(ps, u, -0.16666665826998622f);
+    ps = fmaf(ps, u, 0.9999999995289165f);
+    sn = ps * t;
+    float pc = fmaf(u, 2.4038486070003582e-05f, -0.0013881424341214848f);
+    pc = fmaf(pc, u, 0.04166636798661092f);
+    pc = fmaf(pc, u, -0.49999995814702086f);
+    cs = fmaf(pc, u, 0.9999999990628845f);
+}
 __device__ __forceinline__ float cubic16_inverse_in_bin(const CubBin& k, float u) {
     float inv_a;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_a) : "f"(k.a));
@@ -408,9 +439,9 @@ __device__ __forceinline__ float cubic16_inverse_in_bin(const CubBin& k, float u
     const float dep_2 = delta_1;
     float out;
     if (disc > 0.f) {
-        const float theta = atan2f(fsqrt(disc), -dep_1) * third;
+        const float theta = atan2_upper(fsqrt(disc), -dep_1) * third;
         float c1, c2;
-        sincosf(theta, &c2, &c1);
+        sincos_third(theta, c2, c1);
         const float scale = 2.f * fsqrt(-dep_2);
         const float shift = -b_ + k.xl;
         const float r1 = c1 * scale + shift;
