@@ -115,7 +115,8 @@ struct CubSel {
 
 // Divisions and square roots below use the ~1 ulp MUFU + one-Newton-step forms (fdiv / fsqrt): bin sizes are
 // >= 1e-2 and O(1), never subnormal or huge.
-__device__ __forceinline__ float sigmoid_fast(float v) { return fdiv(1.f, 1.f + ex2_approx(-1.4426950408889634f * v)); }
+// (clamped: 2^(1.44 * 80) is finite, so a very negative argument gives ~0 instead of rcp(inf) -> NaN)
+__device__ __forceinline__ float sigmoid_fast(float v) { return fdiv(1.f, 1.f + ex2_approx(-1.4426950408889634f * fmaxf(v, -80.f))); }
 
 __device__ __forceinline__ CubBin cubic16_bin(const CubSel& s, float ul, float ur, int K = kBins) {
     float inv_wk;
@@ -508,13 +509,18 @@ __device__ __forceinline__ void rqs16_backward(float2* t, const BinSearch16& bs,
     float2 k1 = __ffma2_rn(f2(span), __ffma2_rn(bs.c, Ek1, f2(km + STB_RQS_MIN)), f2(lo));
     if (k == 0) k0 = f2(lo);
     if (k == kBins - 1) k1 = f2(hi);
-    const float d0 = STB_RQS_MIN + softplus_f(u0), d1 = STB_RQS_MIN + softplus_f(u1);
+    // The MUFU-based forms of the forward kernels (softplus_fast2, fdiv, fsqrt, sigmoid_fast: ~1 ulp) instead of
+    // log1pf(expf()), IEEE divisions, sqrtf and expf: ~200 of this element's ~1600 instructions, and the recomputed
+    // knots / derivatives now match the forward pass's.
+    const float2 dd = __fadd2_rn(softplus_fast2(f2(u0, u1)), f2(STB_RQS_MIN));
+    const float d0 = dd.x, d1 = dd.y;
     float xe = x;                                   // point at which S and L = log S' are expanded
-    if (INVERSE) {
-        RqsBin b;
-        b.xk = k0.x; b.wk = k1.x - k0.x; b.yk = k0.y; b.hk = k1.y - k0.y; b.delta = b.hk / b.wk; b.d0 = d0; b.d1 = d1;
-        float ld_own;
-        rqs_inverse_in_bin(b, x, xe, ld_own);
+    if (INVERSE) {                                  // rational_quadratic_spline.py:212-234, as rqs16_finish<true>
+        const float wk = k1.x - k0.x, hk = k1.y - k0.y, delta = fdiv(hk, wk);
+        const float dy = x - k0.y, sdd = d0 + d1 - 2.f * delta;
+        const float qa = dy * sdd + hk * (delta - d0), qb = hk * d0 - dy * sdd, qc = -delta * dy;
+        const float root = fdiv(2.f * qc, -qb - fsqrt(qb * qb - 4.f * qa * qc));
+        xe = root * wk + k0.x;
     }
     // Hand-written reverse sweep through the in-bin map S and L = log dS/dx (rational_quadratic_spline.py:
     // 236-248) instead of 7-variable forward duals: ~4x fewer instructions.  With w = x_k+1 - x_k,
@@ -528,7 +534,7 @@ __device__ __forceinline__ void rqs16_backward(float2* t, const BinSearch16& bs,
     {
         const float xk = k0.x, xk1 = k1.x, yk = k0.y, yk1 = k1.y;
         const float w = xk1 - xk, h = yk1 - yk;
-        const float iw = 1.f / w;
+        const float iw = fdiv(1.f, w);
         const float delta = h * iw;
         const float theta = (xe - xk) * iw, omt = 1.f - theta, tt = theta * omt, om2t = 1.f - 2.f * theta;
         const float sd = d0 + d1 - 2.f * delta;
@@ -537,7 +543,7 @@ __device__ __forceinline__ void rqs16_backward(float2* t, const BinSearch16& bs,
         const float D = delta + sd * tt;
         const float P = d1 * theta * theta + 2.f * delta * tt + d0 * omt * omt;
         const float M = delta * delta * P;
-        const float iD = 1.f / D, iM = 1.f / M;
+        const float iD = fdiv(1.f, D), iM = fdiv(1.f, M);
         // partials wrt theta (for S_x, L_x and the sweep)
         const float N_t = h * (2.f * delta * theta + d0 * om2t);
         const float D_t = sd * om2t;
@@ -550,7 +556,7 @@ __device__ __forceinline__ void rqs16_backward(float2* t, const BinSearch16& bs,
             gq[RQ_X] = g_out * S_x + g_ld * L_x;
         } else {
             const float gl = (xe >= lo && xe <= hi) ? g_ld : 0.f;       // recovered point outside the box: ld = 0
-            const float gy = (g_out - gl * L_x) / S_x;
+            const float gy = fdiv(g_out - gl * L_x, S_x);
             gq[RQ_X] = gy;
             aS = -gy; aL = -gl;
         }
@@ -583,8 +589,8 @@ __device__ __forceinline__ void rqs16_backward(float2* t, const BinSearch16& bs,
     const float2 cC = __fmul2_rn(bs.c, ndot);
 #pragma unroll
     for (int i = 0; i < kBins; ++i) t[i] = __fmul2_rn(t[i], (i < k) ? cA : ((i == k) ? cB : cC));
-    g_u0 = first ? 0.f : gq[RQ_D0] * (u0 > 20.f ? 1.f : sigmoid_f(u0));
-    g_u1 = last ? 0.f : gq[RQ_D1] * (u1 > 20.f ? 1.f : sigmoid_f(u1));
+    g_u0 = first ? 0.f : gq[RQ_D0] * (u0 > 20.f ? 1.f : sigmoid_fast(u0));        // d softplus / du
+    g_u1 = last ? 0.f : gq[RQ_D1] * (u1 > 20.f ? 1.f : sigmoid_fast(u1));
 }
 
 
