@@ -61,11 +61,12 @@ struct Header {                      // 2048 bytes
     uint32_t maxbits;
     uint32_t noshift_mask[2];
     int32_t n_lat;                   // `latent=` columns: conditioning slots n_cond .. n_cond + n_lat - 1 (forward kernels only)
-    int32_t pad0[2];
+    uint32_t m_d, m_d4;              // division magics (div_magic) of dim, dim / 4 ...
     int32_t cond_idx[kK1];           // conditioning slot -> column
     int32_t tr_idx[kMaxTr];          // transformed slot -> column
     int16_t colmap[kMaxDim];         // column -> slot: >= 0 conditioning slot, < 0: -(transformed slot) - 1
-    int32_t pad1[512 - 16 - kK1 - kMaxTr - kMaxDim / 2];
+    uint32_t m_ntr, m_npad, m_npad64; // ... n_tr, k1pad - n_cond - n_lat, 64 - n_cond
+    int32_t pad1[512 - 19 - kK1 - kMaxTr - kMaxDim / 2];
 };
 static_assert(sizeof(Header) == 2048, "header layout");
 constexpr uint32_t kOffB1 = 2048;                                  // float[64]
@@ -127,6 +128,11 @@ struct Args {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// i / dv for 0 <= i < 2^16, 1 <= dv <= 2^7 with a precomputed magic = ceil(2^32 / dv): exact (i * (magic * dv - 2^32) <
+// 2^23), one IMAD.HI instead of the ~20-instruction runtime division in the tile staging loops
+// (dv == 1: the magic 2^32 does not fit and is stored as 0 = "divide by one")
+__device__ __forceinline__ uint32_t div_magic(int dv) { return (uint32_t)((0x100000000ull + (uint32_t)dv - 1) / (uint32_t)dv); }
+__device__ __forceinline__ int fast_div(int i, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)i, magic) : i; }
 __device__ __forceinline__ void stg256(float* p, const float* v) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                  "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
 #pragma unroll
                       for (int u4 = 0; u4 < 4; ++u4) {
                         const int i = i0 + u4 * kEpiThreads;
-                        const bool live = i < n4 && (i / d4) < nrows;
+                        const bool live = i < n4 && fast_div(i, hdr->m_d4) < nrows;
                         vb[u4] = live ? __ldg(reinterpret_cast<const float4*>(xg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                         gb[u4] = (BWD && live) ? __ldg(reinterpret_cast<const float4*>(gg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                       }
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                       for (int u4 = 0; u4 < 4; ++u4) {
                         const int i = i0 + u4 * kEpiThreads;
                         if (i >= n4) break;
-                        const int r = i / d4, c = (i - r * d4) << 2;
+                        const int r = fast_div(i, hdr->m_d4), c = (i - r * d4) << 2;
                         const bool live = r < nrows;
                         const float4 v = vb[u4], gv = gb[u4];
                         const int m0 = hdr->colmap[c], m1 = hdr->colmap[c + 1], m2 = hdr->colmap[c + 2], m3 = hdr->colmap[c + 3];
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                 } else {
                     const int n = kTileRows * d;
                     for (int i = etid; i < n; i += kEpiThreads) {
-                        const int r = i / d, c = i - r * d;
+                        const int r = fast_div(i, hdr->m_d), c = i - r * d;
                         const bool live = r < nrows;
                         const float v = live ? __ldg(xg + i) : 0.f;
                         const float gv = (BWD && live) ? __ldg(gg + i) : 0.f;
@@ -377,8 +383,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                 }
                 // zero the padded conditioning slots [n_cond + n_lat, k1pad) (the buffer is reused for h every tile)
                 const int npad = k1pad - n_cond - n_lat;
+                const uint32_t m_npad = hdr->m_npad;
                 for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
-                    const int r = i / npad, m = n_cond + n_lat + (i - r * npad);
+                    const int r = fast_div(i, m_npad), m = n_cond + n_lat + (i - r * npad);
                     a1_zero(abuf, r, m);
                 }
             }
@@ -567,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                 float* og = A.y + row0 * d;
                 const float* src = BWD ? gs : xs;
                 for (int i = etid; i < nrows * n_tr; i += kEpiThreads) {
-                    const int r = i / n_tr, sl = i - r * n_tr;
+                    const int r = fast_div(i, hdr->m_ntr), sl = i - r * n_tr;
                     og[(size_t)r * d + hdr->tr_idx[sl]] = src[r * kTrStride + sl];
                 }
             }
@@ -926,7 +933,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
 #pragma unroll
                       for (int u4 = 0; u4 < 4; ++u4) {
                         const int i = i0 + u4 * kEpiThreads;
-                        const bool live = i < n4 && (i / d4) < nrows;
+                        const bool live = i < n4 && fast_div(i, hdr->m_d4) < nrows;
                         vb[u4] = live ? __ldg(reinterpret_cast<const float4*>(xg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                         gb[u4] = live ? __ldg(reinterpret_cast<const float4*>(gg) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
                       }
@@ -934,7 +941,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                       for (int u4 = 0; u4 < 4; ++u4) {
                         const int i = i0 + u4 * kEpiThreads;
                         if (i >= n4) break;
-                        const int r = i / d4, c = (i - r * d4) << 2;
+                        const int r = fast_div(i, hdr->m_d4), c = (i - r * d4) << 2;
                         const bool live = r < nrows;
                         const float4 v = vb[u4], gv = gb[u4];
                         gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(gv.x), fabsf(gv.y)), fmaxf(fabsf(gv.z), fabsf(gv.w))));
@@ -961,7 +968,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                 } else {
                     const int n = kTileRows * d;
                     for (int i = etid; i < n; i += kEpiThreads) {
-                        const int r = i / d, c = i - r * d;
+                        const int r = fast_div(i, hdr->m_d), c = i - r * d;
                         const bool live = r < nrows;
                         const float v = live ? __ldg(xg + i) : 0.f;
                         const float gv = live ? __ldg(gg + i) : 0.f;
@@ -976,8 +983,9 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                     }
                 }
                 const int npad = k1pad - n_cond;
+                const uint32_t m_npad = hdr->m_npad;
                 for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
-                    const int r = i / npad, m = n_cond + (i - r * npad);
+                    const int r = fast_div(i, m_npad), m = n_cond + (i - r * npad);
                     a1_zero(abuf, r, m);
                 }
             }
@@ -1232,7 +1240,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                     const float* xg = A.x + row0 * d;
                     const int n = kTileRows * d;
                     for (int i = etid; i < n; i += kEpiThreads) {
-                        const int r = i / d, c = i - r * d;
+                        const int r = fast_div(i, hdr->m_d), c = i - r * d;
                         const int m = hdr->colmap[c];
                         if (m >= 0) {
                             const float v = (r < nrows) ? __ldg(xg + i) : 0.f;
@@ -1240,8 +1248,9 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
                         }
                     }
                     const int npad = kK1 - n_cond;               // all 64 slots are read as N
+                    const uint32_t m_npad = hdr->m_npad64;
                     for (int i = etid; i < kTileRows * npad; i += kEpiThreads) {
-                        const int r = i / npad, m = n_cond + (i - r * npad);
+                        const int r = fast_div(i, m_npad), m = n_cond + (i - r * npad);
                         a1_zero(abuf, r, m);
                     }
                 }
@@ -1287,7 +1296,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
             {
                 float* og = A.g_x + row0 * d;
                 for (int i = etid; i < nrows * n_tr; i += kEpiThreads) {
-                    const int r = i / n_tr, sl = i - r * n_tr;
+                    const int r = fast_div(i, hdr->m_ntr), sl = i - r * n_tr;
                     og[(size_t)r * d + hdr->tr_idx[sl]] = xs[r * kTrStride + sl];
                 }
                 if (etid == 0) bars->tile_max = 0;
@@ -1349,6 +1358,10 @@ __global__ void tcw_pack_kernel(const PackArgs a) {
         hdr->n_chunks = a.n_chunks; hdr->P = a.P; hdr->act = a.act; hdr->s2 = s2;
         hdr->n_lat = a.n_lat;
         hdr->k1pad = (a.n_cond + a.n_lat + 15) & ~15;
+        if (hdr->k1pad == 0) hdr->k1pad = 16;
+        hdr->m_d = div_magic(a.dim); hdr->m_d4 = div_magic(max(a.dim >> 2, 1)); hdr->m_ntr = div_magic(a.n_tr);
+        hdr->m_npad = div_magic(max(hdr->k1pad - a.n_cond - a.n_lat, 1));
+        hdr->m_npad64 = div_magic(max(kK1 - a.n_cond, 1));
         if (hdr->k1pad == 0) hdr->k1pad = 16;
         for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
         for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
