@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
     // buffer b = ji % 4 is written by issuer b % 2 only and read by epilogue group b only; a ring stage's successive items
     // go to alternating issuers, each of which has consumed the item right before (filled in order by the one producer).
     auto issue_chunk = [&](uint32_t rc, uint32_t buf, uint32_t buse) {
-        const uint32_t idesc3 = make_idesc(FMT_F16, 128, kPPad);
+#ifndef STB_HW_EXP
+#define STB_HW_EXP 0                       // timing experiments only (wrong results): 1 no chunk UMMAs, 2 chunk UMMAs with N = 16
+#endif
+        const uint32_t idesc3 = make_idesc(FMT_F16, 128, (STB_HW_EXP & 2) ? 16 : kPPad);
         const uint32_t st = rc % kStages, use = rc / kStages;
         mbar_wait_relaxed(&bars->b_full[st], use & 1);
         mbar_wait_relaxed(&bars->acc_empty[buf], (buse & 1) ^ 1);
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
             uint32_t ad = ad0 + ((p == 0) ? 8u : 0u);
 #pragma unroll 4
             for (int kb = 0; kb < kb_h; ++kb) {
-                umma_f16_ts(dcol, ad, bd, idesc3, acc);
+                if (!(STB_HW_EXP & 1)) umma_f16_ts(dcol, ad, bd, idesc3, acc);
                 acc = 1;
                 bd += (uint64_t)(w3_block() >> 4);
                 ad += 16u;
