@@ -42,7 +42,8 @@ constexpr int kMaxTr = 32;
 constexpr int kMaxH = 256;
 constexpr int kXsStride = kMaxDim + 1;
 constexpr int kStages = 3;
-constexpr int kNBuf = 4;                 // 48-column chunk accumulators: buffer b belongs to epilogue group b and issuer b % 2
+constexpr int kNBuf = 2;                 // 96-column chunk accumulators (two transformed dims): buffer b belongs to issuer b and to epilogue groups 2b, 2b + 1
+constexpr int kChunkN = 2 * kPPad;
 constexpr int kEpiWarp0 = 2;
 constexpr int kEpiWarps = 16;
 constexpr int kIssuers = 2;                              // UMMA issuer threads of the chunk phase (dims ji % 2)
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
         mbar_init(&bars->h1_ready, kEpiWarps);
         mbar_init(&bars->acc2_full, 1);
         mbar_init(&bars->h2_ready, kEpiWarps);
-        for (int b = 0; b < kNBuf; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 4); }
+        for (int b = 0; b < kNBuf; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 8); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, 512);
@@ -200,46 +201,53 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
     const uint32_t w1b = w1_block(H), w2b = w2_block(H);
     const int n_items2 = (n_hidden == 2) ? (kb_h + 2) / 3 : 0;              // W2' items of up to 3 K blocks
     const uint32_t col_h_last = (n_hidden == 2) ? 256u : 0u;                // A operand of the chunk GEMMs
-    const uint32_t col_chunk = (n_hidden == 2) ? 0u : (uint32_t)H;          // five 48-column accumulators
+    const uint32_t col_chunk = (n_hidden == 2) ? 0u : (uint32_t)H;          // two 96-column accumulators
+    const int n_chunks = (n_tr + 1) / 2;
     // every CTA of a cluster runs the same number of tiles (the weight stream is shared): the trip count is that of the
     // cluster's FIRST CTA; a CTA whose last tile does not exist runs it as a ghost (no rows loaded, nothing stored)
     const int first_cta = (int)blockIdx.x - (int)crank;
     const int my_tiles = (A.n_tiles > first_cta) ? (A.n_tiles - 1 - first_cta) / (int)gridDim.x + 1 : 0;
 
-    // ---- one transformed dim: [128 x H] x [H x 48] from ring item `rc` into accumulator buffer `cc % 5`, A = the last
-    // hidden layer in TMEM, three passes with the corrections first (lo*hi, hi*lo, hi*hi)
+    // ---- one chunk = TWO transformed dims: [128 x H] x [H x 96] into accumulator buffer `buf`, A = the last hidden layer
+    // in TMEM.  The chunk UMMAs cost a fixed ~38 clocks each whatever N (measured: N = 16 and N = 48 take the same time,
+    // -DSTB_HW_EXP), so two dims per UMMA halve the chunk phase's tensor time.  A chunk's weights travel as two ring
+    // items -- the fp16 lo parts, then the hi parts, each [96 x H] K-major in K blocks of 16 -- and the three passes
+    // go hi*lo (item 0, released), then lo*hi and hi*hi (item 1): corrections first, the accumulator truncates.
     // Every mbarrier of the chunk phase is a PRIVATE channel, so that a waiter's successive waits are successive phases
     // whatever the relative speed of the agents (a parity wait cannot tell "two phases behind" from "done"): accumulator
-    // buffer b = ji % 4 is written by issuer b % 2 only and read by epilogue group b only; a ring stage's successive items
-    // go to alternating issuers, each of which has consumed the item right before (filled in order by the one producer).
+    // buffer b is written by issuer b only and read by epilogue groups 2b, 2b + 1 only; a ring stage is refilled only
+    // after the issuer that consumed its previous item has released it.
     auto issue_chunk = [&](uint32_t rc, uint32_t buf, uint32_t buse) {
 #ifndef STB_HW_EXP
 #define STB_HW_EXP 0                       // timing experiments only (wrong results): 1 no chunk UMMAs, 2 chunk UMMAs with N = 16
 #endif
-        const uint32_t idesc3 = make_idesc(FMT_F16, 128, (STB_HW_EXP & 2) ? 16 : kPPad);
-        const uint32_t st = rc % kStages, use = rc / kStages;
-        mbar_wait_relaxed(&bars->b_full[st], use & 1);
-        mbar_wait_relaxed(&bars->acc_empty[buf], (buse & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t dcol = tmem + col_chunk + buf * kPPad;
-        const uint64_t bd0 = make_smem_desc(smem_u32(ring + st * stage), 128, 256);
+        const uint32_t idesc3 = make_idesc(FMT_F16, 128, (STB_HW_EXP & 2) ? 16 : kChunkN);
+        const uint32_t dcol = tmem + col_chunk + buf * kChunkN;
         const uint32_t ad0 = tmem + col_h_last;
         uint32_t acc = 0;
 #pragma unroll 1
-        for (int p = 0; p < 3; ++p) {
-            // descriptors advance by constants: 3072 B (>> 4 in the descriptor's address field) and 16 TMEM columns
-            uint64_t bd = bd0 + ((p == 1) ? (uint64_t)((kPPad * 32) >> 4) : 0ull);
-            uint32_t ad = ad0 + ((p == 0) ? 8u : 0u);
+        for (int item = 0; item < 2; ++item, ++rc) {
+            const uint32_t st = rc % kStages, use = rc / kStages;
+            mbar_wait_relaxed(&bars->b_full[st], use & 1);
+            if (item == 0) mbar_wait_relaxed(&bars->acc_empty[buf], (buse & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t bd0 = make_smem_desc(smem_u32(ring + st * stage), 128, 256);
+#pragma unroll 1
+            for (int p = (item == 0 ? 0 : 1); p < (item == 0 ? 1 : 3); ++p) {       // p: 0 hi*lo, 1 lo*hi, 2 hi*hi
+                // descriptors advance by constants: 3072 B (>> 4 in the descriptor's address field) and 16 TMEM columns
+                uint64_t bd = bd0;
+                uint32_t ad = ad0 + ((p == 1) ? 8u : 0u);
 #pragma unroll 4
-            for (int kb = 0; kb < kb_h; ++kb) {
-                if (!(STB_HW_EXP & 1)) umma_f16_ts(dcol, ad, bd, idesc3, acc);
-                acc = 1;
-                bd += (uint64_t)(w3_block() >> 4);
-                ad += 16u;
+                for (int kb = 0; kb < kb_h; ++kb) {
+                    if (!(STB_HW_EXP & 1)) umma_f16_ts(dcol, ad, bd, idesc3, acc);
+                    acc = 1;
+                    bd += (uint64_t)(w3_block() >> 4);
+                    ad += 16u;
+                }
             }
+            if (item == 1) umma_commit(&bars->acc_full[buf]);
+            if (CL > 1) umma_commit_multicast(&bars->b_empty[st], cmask); else umma_commit(&bars->b_empty[st]);
         }
-        umma_commit(&bars->acc_full[buf]);
-        if (CL > 1) umma_commit_multicast(&bars->b_empty[st], cmask); else umma_commit(&bars->b_empty[st]);
     };
 
     if (warp == 0) {
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                     const int nb = min(3, kb_h - 3 * i2);
                     put(A.packed + off_w2(H) + (uint32_t)(3 * i2) * w2b, (uint32_t)nb * w2b);
                 }
-                for (int ji = 0; ji < n_tr; ++ji) put(A.packed + off_w3(H, n_hidden) + (uint32_t)ji * stage, stage);
+                for (int i3 = 0; i3 < 2 * n_chunks; ++i3) put(A.packed + off_w3(H, n_hidden) + (uint32_t)i3 * stage, stage);
             }
         }
     } else if (warp == 1) {
@@ -329,12 +337,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                     umma_commit(&bars->acc2_full);
                 }
                 mbar_wait_relaxed(n_hidden == 2 ? &bars->h2_ready : &bars->h1_ready, tp);
-                for (int ji = 0; ji < n_tr; ++ji, ++rc)
-                    if (!(ji & 1)) { issue_chunk(rc, (uint32_t)(ji & 3), nuse[(ji >> 1) & 1]); ++nuse[(ji >> 1) & 1]; }
+                for (int c = 0; c < n_chunks; ++c, rc += 2)
+                    if (!(c & 1)) { issue_chunk(rc, 0u, nuse[0]); ++nuse[0]; }
             }
         }
     } else if (warp >= kIssuerB) {
-        // ======================= second UMMA issuer: the odd transformed dims (buffers 1 and 3) =======================
+        // ======================= second UMMA issuer: the odd chunks (buffer 1) ==========================================
         // One thread spends ~8 issue slots (elect loop + descriptor arithmetic on the uniform datapath) per UMMA and a dim
         // is 3 H / 16 of them (48 at H = 256): with one issuer that thread, not the tensor pipe, paced the chunk phase
         // (2.8e7 samples/s with one issuer, 4.7e7 with two at MLP[256,256]; a third changes nothing).
@@ -344,8 +352,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
             for (int it = 0; it < my_tiles; ++it, tp ^= 1) {
                 rc += 1u + (uint32_t)n_items2;
                 mbar_wait_relaxed(n_hidden == 2 ? &bars->h2_ready : &bars->h1_ready, tp);
-                for (int ji = 0; ji < n_tr; ++ji, ++rc)
-                    if (ji & 1) { issue_chunk(rc, (uint32_t)(ji & 3), nuse[(ji >> 1) & 1]); ++nuse[(ji >> 1) & 1]; }
+                for (int c = 0; c < n_chunks; ++c, rc += 2)
+                    if (c & 1) { issue_chunk(rc, 1u, nuse[0]); ++nuse[0]; }
             }
         }
     } else {
@@ -426,8 +434,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
             // ---- chunks: dims g, g + 4, ... of this group's 128 rows -----------------------------------------------------------
             float ld_acc = 0.f;
 #pragma unroll 1
-            for (int ji = g; ji < n_tr; ji += 4, ++buse) {
-                const uint32_t buf = (uint32_t)g;
+            for (int ji = g; ji < 2 * n_chunks; ji += 4, ++buse) {
+                const uint32_t buf = (uint32_t)(g >> 1);              // chunk ji >> 1 alternates between the two buffers
+                if (ji >= n_tr) {                                     // odd number of dims: the last chunk's padding half
+                    mbar_wait_sleep(&bars->acc_full[buf], buse & 1, 32);
+                    tc_fence_after();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
+                    continue;
+                }
                 const int j = hdr->tr_idx[ji];
                 const float xv = xrow[j];
                 const bool inside = (xv >= lo) && (xv <= hi);
@@ -435,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                 const float2* bb2 = reinterpret_cast<const float2*>(bb);
                 mbar_wait_sleep(&bars->acc_full[buf], buse & 1, 32);
                 tc_fence_after();
-                const uint32_t col0 = tmem + lane_sel + col_chunk + buf * kPPad;
+                const uint32_t col0 = tmem + lane_sel + col_chunk + buf * kChunkN + (uint32_t)(g & 1) * kPPad;
                 const bool shift = !((noshift_mask >> (ji & 31)) & 1u);
                 float out = xv, ld = 0.f;
                 int kbin = -1;
@@ -629,7 +645,7 @@ __global__ void tch_pack_kernel(const PackArgs a) {
             *reinterpret_cast<__half*>(blk + H * 32 + blk_off(n, k & 15)) = lo;
         }
     }
-    {   // last Linear: per transformed dim H / 16 blocks of [48 x 16] hi | lo
+    {   // last Linear: per chunk of two transformed dims a lo item and a hi item
         uint8_t* w3 = a.out + off_w3(H, a.n_hidden);
         const float inv = 1.f / s_out;
         const int per_dim = kPPad * H;
@@ -640,9 +656,12 @@ __global__ void tch_pack_kernel(const PackArgs a) {
             if (ji < a.n_tr && p < a.P) v = a.W3[((size_t)a.tr_idx[ji] * a.P + p) * H + k] * inv;
             __half hi, lo;
             split_f16(v, hi, lo);
-            uint8_t* blk = w3 + (size_t)ji * stage_bytes(H) + (size_t)(k >> 4) * w3_block();
-            *reinterpret_cast<__half*>(blk + blk_off(n, k & 15)) = hi;
-            *reinterpret_cast<__half*>(blk + kPPad * 32 + blk_off(n, k & 15)) = lo;
+            // chunk c = ji / 2 (two dims, 96 rows): item 2c holds the lo parts, item 2c + 1 the hi parts, each as H / 16
+            // blocks [96 x 16] (3072 B)
+            const int n2 = (ji & 1) * kPPad + n;
+            uint8_t* blk = w3 + (size_t)(ji & ~1) * stage_bytes(H) + (size_t)(k >> 4) * w3_block();
+            *reinterpret_cast<__half*>(blk + blk_off(n2, k & 15)) = lo;
+            *reinterpret_cast<__half*>(blk + stage_bytes(H) + blk_off(n2, k & 15)) = hi;
         }
     }
 }
