@@ -1558,6 +1558,7 @@ constexpr uint32_t kV4A1Part = kRows * 16 * 2;        // one bf16 part of the [1
 constexpr uint32_t kV4W1Bytes = 3 * 64 * 32;          // three bf16 parts of [64 x 16]
 constexpr uint32_t kV4W3Bytes = 4 * kNOut * 64;       // four K blocks of [64 x 16] fp16 hi | lo
 constexpr uint32_t kV4WBytes = kV4W1Bytes + kV4W3Bytes;
+constexpr uint32_t kV4W3Used = 4 * 2 * 32 * 32;       // the rows in use, compacted: four K blocks of [32 x 16] hi | lo
 
 template <int DUMMY>
 __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const ChainArgs A) {
@@ -1592,13 +1593,20 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
     tc_fence_after();
     const uint32_t tmem = tmem_base_s + (uint32_t)vc * kVcCols;
     if (tid == 0) {                               // headers, biases and the weight blocks in use, once per CTA
-        mbar_arrive_expect_tx(&w_full, (uint32_t)L * (kSmallBytes + kV4WBytes));
+        mbar_arrive_expect_tx(&w_full, (uint32_t)L * (kSmallBytes + kV4W1Bytes + kV4W3Used));
         for (int l = 0; l < L; ++l) {
             bulk_g2s(smem + (uint32_t)l * kSmallSlot, A.packed[l], kSmallBytes, &w_full);
             uint8_t* wdst = smem + A.sm_w + (uint32_t)l * kV4WBytes;
             // first Linear: K block 0 of the parts pb = 2, 1, 0 (blocks 0, 2, 4 of the image; blocks 1, 3, 5 are zero)
             for (int b = 0; b < 3; ++b) bulk_g2s(wdst + b * 2048, A.packed[l] + kOffW + (uint32_t)(2 * b) * 2048, 2048, &w_full);
-            bulk_g2s(wdst + kV4W1Bytes, A.packed[l] + kOffW + 6 * 2048, kV4W3Bytes, &w_full);
+            // last Linear: of every K block [64 x 16] hi | lo only the log-scale rows 0..15 and the shift rows 32..47 are in
+            // use (<= 16 transformed dims); they are gathered into ONE [32 x 16] operand per part, so that the output GEMM
+            // is one N = 32 UMMA per pass instead of two N = 16 ones (a UMMA costs a fixed ~38 clocks whatever N)
+            for (int kb = 0; kb < 4; ++kb)
+                for (int part = 0; part < 2; ++part)
+                    for (int half = 0; half < 2; ++half)
+                        bulk_g2s(wdst + kV4W1Bytes + kb * 2048 + part * 1024 + half * 512,
+                                 A.packed[l] + kOffW + 6 * 2048 + kb * (kNOut * 64) + part * (kNOut * 32) + half * 1024, 512, &w_full);
         }
     }
     mbar_wait(&w_full, 0);
@@ -1621,7 +1629,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
         // ---- UMMA issuer of this virtual CTA ---------------------------------------------------------------
         if (lane == 0) {
             const uint32_t idesc1 = make_idesc(FMT_BF16, 128, H);
-            const uint32_t idesc3 = make_idesc(FMT_F16, 128, 16);
+            const uint32_t idesc3 = make_idesc(FMT_F16, 128, 32);
             const uint32_t a0 = smem_u32(a1buf);
             uint32_t ause = 0;
             for (int it = 0; it < my_tiles; ++it)
@@ -1643,13 +1651,13 @@ __global__ void __launch_bounds__(kV4Threads, 1) tc_mlp_chain4_kernel(const Chai
                 umma_commit(&bars->acc_ready);
                 mbar_wait_sleep(&bars->a_ready, ause & 1, 96); ++ause;
                 tc_fence_after();
-                // last Linear: A = h from TMEM; log-scale rows 0..15 and shift rows 32..47 of every K block, N = 16 each
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t dm = tmem + H + (uint32_t)half * 16, dc = dm + 32;
+                // last Linear: A = h from TMEM, B = the compacted [log-scale 16 | shift 16] rows of every K block, N = 32
+                {
+                    const uint32_t dm = tmem + H, dc = dm + 32;
                     acc_m = acc_c = 0;
                     for (int kb = 0; kb < 4; ++kb) {
-                        const uint32_t bb = w3 + (uint32_t)kb * (kNOut * 64) + (uint32_t)half * 1024;
-                        const uint64_t b_hi = make_smem_desc(bb, 128, 256), b_lo = make_smem_desc(bb + kNOut * 32, 128, 256);
+                        const uint32_t bb = w3 + (uint32_t)kb * 2048;
+                        const uint64_t b_hi = make_smem_desc(bb, 128, 256), b_lo = make_smem_desc(bb + 1024, 128, 256);
                         const uint32_t a_hi = tmem + (uint32_t)kb * 16, a_lo = a_hi + 8;
                         umma_f16_ts(dc, a_lo, b_hi, idesc3, acc_c); acc_c = 1;
                         umma_f16_ts(dc, a_hi, b_lo, idesc3, 1);
