@@ -61,7 +61,8 @@ struct Header {                          // 1024 bytes
     int32_t cond_idx[kK1];
     int32_t tr_idx[kMaxTr];
     int32_t n_lat;                       // `latent=` columns (coupling.py:64-65): GEMM1 columns n_cond .. n_cond + n_lat - 1
-    int32_t pad[256 - 15 - kK1 - kMaxTr];
+    int32_t n_bins;                      // 2 .. 16 real bins in the 16-bin packed layout (padded bins: weight 0, bias -inf)
+    int32_t pad[256 - 16 - kK1 - kMaxTr];
 };
 static_assert(sizeof(Header) == 1024, "header layout");
 constexpr uint32_t kOffB1 = 1024, kOffB2 = kOffB1 + kMaxH * 4, kOffB3 = kOffB2 + kMaxH * 4;     // b3: float [32][48]
@@ -152,7 +153,8 @@ __device__ __forceinline__ void activate_in_place(uint32_t acc, int c_begin, int
     tmem_st_wait();
 }
 
-template <int KIND, bool INVERSE>
+// FULL = false: 2 .. 15 real bins in the padded 16-bin layout (tc_spline16.cuh)
+template <int KIND, bool INVERSE, bool FULL = true>
 __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_base_s;
@@ -369,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
         const float inv_span = 1.f / (hi - lo);
         const float s2 = hdr->s_out, s2l = s2 * 1.4426950408889634f;
         const float s_mid = hdr->s_mid;
+        const int K = FULL ? kBins : hdr->n_bins;
         const uint32_t noshift_mask = hdr->noshift_mask;
         const int dshift = ((d & (d - 1)) == 0) ? (31 - __clz(d)) : -1;
         uint32_t buse = 0, tp = 0;                  // uses so far of this group's accumulator buffer (buffer g)
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
-                        loc = rqs16_locate<INVERSE>(t, shift, lo, inv_span, xv);
+                        loc = rqs16_locate<INVERSE, FULL>(t, shift, lo, inv_span, xv, K);
                     }
                     float dd[16];
                     tmem_ld16(col0 + 2 * kBins, dd);
@@ -476,8 +479,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                         float r0, r1;
                         pick_pair16(dd, loc.k, r0, r1);
                         const float u0 = (loc.k == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + loc.k - 1]);
-                        const float u1 = (loc.k == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
-                        rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
+                        const float u1 = (loc.k == K - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
+                        rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld, K);
                         kbin = loc.k;
                     }
                 } else {
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
-                        sel = cubic16_locate<INVERSE>(t, shift, u);
+                        sel = cubic16_locate<INVERSE, FULL>(t, shift, u, K);
                     }
                     float dd[8];
                     tmem_ld8(col0 + 2 * kBins, dd);
@@ -501,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
                     if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
                     if (inside) {
                         const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
-                        cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);
+                        cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld, K);
                         kbin = sel.k;
                     }
                 }
@@ -554,14 +557,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_hw_spline_kernel(const Args A)
 struct PackArgs {
     const float *W1, *b1, *W2, *b2, *W3, *b3;
     uint8_t* out;
-    int kind, dim, n_cond, n_tr, H, n_hidden, P, act, n_lat;
+    int kind, dim, n_cond, n_tr, H, n_hidden, P, act, n_lat, n_bins;
     int cond_idx[kK1];
     int tr_idx[kMaxTr];
 };
 
 // column c of a dim's 48 -> parameter index: the 32 softmax columns are interleaved (w_i, h_i)
-__host__ __device__ __forceinline__ int param_of_col(int c) {
-    return (c < 2 * kBins) ? ((c & 1) ? kBins + (c >> 1) : (c >> 1)) : c;
+// -> parameter index in the network's [w(K) | h(K) | rest] order, -1 for padding (as tc_layer.cu)
+__host__ __device__ __forceinline__ int param_of_col(int c, int K, int P) {
+    if (c < 2 * kBins) {
+        const int i = c >> 1;
+        return (i < K) ? ((c & 1) ? K + i : i) : -1;
+    }
+    const int p = 2 * K + (c - 2 * kBins);
+    return (p < P) ? p : -1;
 }
 // element (n, k) of an [N x 16] K-major block: 2 chunks of 8 elements per row
 __device__ __forceinline__ uint32_t blk_off(int n, int k) {
@@ -603,7 +612,7 @@ __global__ void tch_pack_kernel(const PackArgs a) {
     const int H = a.H;
     if (gtid == 0) {
         hdr->magic = kMagic; hdr->kind = a.kind; hdr->dim = a.dim; hdr->n_cond = a.n_cond; hdr->n_tr = a.n_tr; hdr->H = H;
-        hdr->n_hidden = a.n_hidden; hdr->P = a.P; hdr->act = a.act; hdr->s_mid = s_mid; hdr->s_out = s_out; hdr->n_lat = a.n_lat;
+        hdr->n_hidden = a.n_hidden; hdr->P = a.P; hdr->act = a.act; hdr->s_mid = s_mid; hdr->s_out = s_out; hdr->n_lat = a.n_lat; hdr->n_bins = a.n_bins;
         for (int i = 0; i < kK1; ++i) hdr->cond_idx[i] = a.cond_idx[i];
         for (int i = 0; i < kMaxTr; ++i) hdr->tr_idx[i] = a.tr_idx[i];
     }
@@ -615,8 +624,9 @@ __global__ void tch_pack_kernel(const PackArgs a) {
         b2[i] = (i < H && a.n_hidden == 2) ? a.b2[i] : 0.f;
     }
     for (int i = gtid; i < kMaxTr * kPPad; i += gsz) {
-        const int ji = i / kPPad, col = i % kPPad, p = param_of_col(col);
-        const float bv = (ji < a.n_tr && p < a.P) ? a.b3[a.tr_idx[ji] * a.P + p] : 0.f;
+        const int ji = i / kPPad, col = i % kPPad, p = param_of_col(col, a.n_bins, a.P);
+        float bv = (ji < a.n_tr && p >= 0) ? a.b3[a.tr_idx[ji] * a.P + p] : 0.f;
+        if (col < 2 * kBins && p < 0 && ji < a.n_tr) bv = -INFINITY;         // padded bin: numerator exactly 0
         b3[i] = (col < 2 * kBins) ? bv * 1.4426950408889634f : bv;         // softmax columns: log2 domain
     }
     // first Linear: blocks (pb = 2, 1, 0) x (kb = 0, 1), each [H x 16] of bf16 part pb (conditioning columns only)
@@ -651,9 +661,9 @@ __global__ void tch_pack_kernel(const PackArgs a) {
         const int per_dim = kPPad * H;
         for (int i = gtid; i < kMaxTr * per_dim; i += gsz) {
             const int ji = i / per_dim, rem = i % per_dim, n = rem / H, k = rem % H;
-            const int p = param_of_col(n);
+            const int p = param_of_col(n, a.n_bins, a.P);
             float v = 0.f;
-            if (ji < a.n_tr && p < a.P) v = a.W3[((size_t)a.tr_idx[ji] * a.P + p) * H + k] * inv;
+            if (ji < a.n_tr && p >= 0) v = a.W3[((size_t)a.tr_idx[ji] * a.P + p) * H + k] * inv;
             __half hi, lo;
             split_f16(v, hi, lo);
             // chunk c = ji / 2 (two dims, 96 rows): item 2c holds the lo parts, item 2c + 1 the hi parts, each as H / 16
@@ -672,10 +682,13 @@ __global__ void tch_bound_kernel(const PackArgs a) {
     const int ji = threadIdx.x >> 5, p = threadIdx.x & 31;
     bool ok = false;
     if (ji < a.n_tr) {
-        const size_t rowi = (size_t)a.tr_idx[ji] * a.P + p;
-        float l1 = fabsf(a.b3[rowi]);
-        for (int k = 0; k < a.H; ++k) l1 += fabsf(a.W3[rowi * a.H + k]);
-        ok = (l1 * 1.4426950408889634f <= 100.f);
+        ok = true;
+        if (p < 2 * a.n_bins) {                              // the 2 K softmax rows of the dim
+            const size_t rowi = (size_t)a.tr_idx[ji] * a.P + p;
+            float l1 = fabsf(a.b3[rowi]);
+            for (int k = 0; k < a.H; ++k) l1 += fabsf(a.W3[rowi * a.H + k]);
+            ok = (l1 * 1.4426950408889634f <= 100.f);
+        }
     }
     ok = __all_sync(0xffffffffu, ok);
     if (p == 0 && ok) atomicOr(&reinterpret_cast<Header*>(a.out)->noshift_mask, 1u << ji);
@@ -695,7 +708,10 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
     a.n_lat = L->latent_dim;
     if (a.n_cond + a.n_lat > kK1 || N.dims[0] != L->dim + a.n_lat) return false;
     a.kind = L->kind; a.dim = L->dim; a.H = N.dims[1]; a.n_hidden = N.n_linear - 1;
-    a.P = L->kind == STB_RQS ? 3 * kBins - 1 : 2 * kBins + 2;
+    a.n_bins = L->n_bins;
+    if (a.n_bins < 2 || a.n_bins > kBins) return false;
+    a.P = L->kind == STB_RQS ? 3 * a.n_bins - 1 : 2 * a.n_bins + 2;
+    if (N.dims[N.n_linear] != L->dim * a.P) return false;
     a.act = N.activation;
     a.W1 = N.W[0]; a.b1 = N.b[0];
     a.W2 = a.n_hidden == 2 ? N.W[1] : nullptr; a.b2 = a.n_hidden == 2 ? N.b[1] : nullptr;
@@ -708,7 +724,7 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
 bool tch_layer_supported(const stb_layer* L) {
     using namespace tch;
     if (L->kind != STB_RQS && L->kind != STB_CUBIC) return false;
-    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim < 0 || L->time_input) return false;
+    if (L->n_bins < 2 || L->n_bins > kBins || !L->cond_x || L->zero_cond || L->latent_dim < 0 || L->time_input) return false;
     if (L->has_box || L->row_out || L->dim < 2 || L->dim > kMaxDim || L->inverse_ldj_own) return false;
     const stb_mlp& N = L->net;
     if ((N.n_linear != 2 && N.n_linear != 3) || N.final_activation != STB_ACT_NONE) return false;
@@ -767,8 +783,13 @@ int tch_layer_apply(const stb_layer* L, int direction, const float* x, const flo
     }
     const bool inv = direction == STB_INVERSE;
     void (*kern)(Args);
-    if (L->kind == STB_RQS) kern = inv ? tc_hw_spline_kernel<STB_RQS, true> : tc_hw_spline_kernel<STB_RQS, false>;
-    else kern = inv ? tc_hw_spline_kernel<STB_CUBIC, true> : tc_hw_spline_kernel<STB_CUBIC, false>;
+    if (L->n_bins == kBins) {
+        if (L->kind == STB_RQS) kern = inv ? tc_hw_spline_kernel<STB_RQS, true> : tc_hw_spline_kernel<STB_RQS, false>;
+        else kern = inv ? tc_hw_spline_kernel<STB_CUBIC, true> : tc_hw_spline_kernel<STB_CUBIC, false>;
+    } else {
+        if (L->kind == STB_RQS) kern = inv ? tc_hw_spline_kernel<STB_RQS, true, false> : tc_hw_spline_kernel<STB_RQS, false, false>;
+        else kern = inv ? tc_hw_spline_kernel<STB_CUBIC, true, false> : tc_hw_spline_kernel<STB_CUBIC, false, false>;
+    }
     const uint32_t smem = smem_bytes(H);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(STB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));

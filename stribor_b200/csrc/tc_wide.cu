@@ -66,7 +66,8 @@ struct Header {                      // 2048 bytes
     int32_t tr_idx[kMaxTr];          // transformed slot -> column
     int16_t colmap[kMaxDim];         // column -> slot: >= 0 conditioning slot, < 0: -(transformed slot) - 1
     uint32_t m_ntr, m_npad, m_npad64; // ... n_tr, k1pad - n_cond - n_lat, 64 - n_cond
-    int32_t pad1[512 - 19 - kK1 - kMaxTr - kMaxDim / 2];
+    int32_t n_bins;                  // 2 .. 16 real bins in the padded 16-bin layout (forward kernels; the gradient kernels need 16)
+    int32_t pad1[512 - 20 - kK1 - kMaxTr - kMaxDim / 2];
 };
 static_assert(sizeof(Header) == 2048, "header layout");
 constexpr uint32_t kOffB1 = 2048;                                  // float[64]
@@ -169,7 +170,8 @@ __device__ __forceinline__ void a1_zero(uint8_t* abuf, int r, int m) {
     *reinterpret_cast<uint16_t*>(dst + 2 * kA1Part) = 0;
 }
 
-template <int KIND, bool INVERSE, bool BWD>
+// FULL = false (forward only): 2 .. 15 real bins in the padded 16-bin layout (tc_spline16.cuh)
+template <int KIND, bool INVERSE, bool BWD, bool FULL = true>
 __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
     extern __shared__ __align__(1024) uint8_t smem[];
     float* xs = reinterpret_cast<float*>(smem + kSmXs);
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
 
     const int d = hdr->dim, n_tr = hdr->n_tr, n_cond = hdr->n_cond, n_chunks = hdr->n_chunks;
     const int k1pad = hdr->k1pad;
+    const int K = FULL ? kBins : hdr->n_bins;
     const int act = hdr->act;
     const float s2 = hdr->s2;
     const float s2l = s2 * 1.4426950408889634f;
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
 #pragma unroll
                     for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
                     if (!BWD) {
-                        const RqsLoc loc = rqs16_locate<INVERSE>(t, shift, lo, inv_span, xv);
+                        const RqsLoc loc = rqs16_locate<INVERSE, FULL>(t, shift, lo, inv_span, xv, K);
                         float dd[16];
                         tmem_ld16(col0 + 2 * kBins, dd);
                         tmem_ld_wait();
@@ -465,8 +468,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                             float r0, r1;
                             pick_pair16(dd, loc.k, r0, r1);
                             const float u0 = (loc.k == 0) ? STB_RQS_EDGE_CONST : fmaf(r0, s2, bb[2 * kBins + loc.k - 1]);
-                            const float u1 = (loc.k == kBins - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
-                            rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld);
+                            const float u1 = (loc.k == K - 1) ? STB_RQS_EDGE_CONST : fmaf(r1, s2, bb[2 * kBins + loc.k]);
+                            rqs16_finish<INVERSE>(loc, u0, u1, lo, hi, want_ld, xv, out, ld, K);
                         }
                         if (A.bins != nullptr && live_dim && rloc < nrows)
                             A.bins[(row0 + rloc) * d + hdr->tr_idx[ji]] = inside ? loc.k : -1;
@@ -530,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < kBins; ++i) t[i] = __ffma2_rn(t[i], f2(s2l), bb2[i]);
-                    const CubSel sel = cubic16_locate<INVERSE>(t, shift, u);
+                    const CubSel sel = cubic16_locate<INVERSE, FULL>(t, shift, u, K);
                     float dd[8];
                     tmem_ld8(col0 + 2 * kBins, dd);
                     tmem_ld_wait();
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wide_kernel(const Args A) {
                     if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
                     if (inside) {
                         const float ul = fmaf(dd[0], s2, bb[2 * kBins]), ur = fmaf(dd[1], s2, bb[2 * kBins + 1]);
-                        cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld);
+                        cubic16_finish<INVERSE>(sel, ul, ur, lo, hi, want_ld, u, out, ld, K);
                     }
                     if (!BWD && A.bins != nullptr && live_dim && rloc < nrows)
                         A.bins[(row0 + rloc) * d + hdr->tr_idx[ji]] = inside ? sel.k : -1;
@@ -1317,7 +1320,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tc_wide_train_kernel(const Args 
 struct PackArgs {
     const float *W1, *b1, *W2, *b2;
     uint8_t* out;
-    int kind, dim, n_cond, n_tr, n_chunks, P, act, n_lat;
+    int kind, dim, n_cond, n_tr, n_chunks, P, act, n_lat, n_bins;
     int16_t colmap[kMaxDim];
     uint8_t cond_idx[kK1];
     uint8_t tr_idx[kMaxTr];
@@ -1335,8 +1338,14 @@ __global__ void tcw_maxabs_kernel(const PackArgs a) {
     if ((threadIdx.x & 31) == 0) atomicMax(&reinterpret_cast<Header*>(a.out)->maxbits, __float_as_uint(m));
 }
 
-__host__ __device__ __forceinline__ int param_of_col(int c) {
-    return (c < 2 * kBins) ? ((c & 1) ? kBins + (c >> 1) : (c >> 1)) : c;
+// -> parameter index in the network's [w(K) | h(K) | rest] order, -1 for padding (as tc_layer.cu)
+__host__ __device__ __forceinline__ int param_of_col(int c, int K, int P) {
+    if (c < 2 * kBins) {
+        const int i = c >> 1;
+        return (i < K) ? ((c & 1) ? K + i : i) : -1;
+    }
+    const int p = 2 * K + (c - 2 * kBins);
+    return (p < P) ? p : -1;
 }
 __device__ __forceinline__ uint32_t core_off(int r, int k, int K, int elem) {
     const int epc = 16 / elem, chunks = K / epc;
@@ -1356,7 +1365,7 @@ __global__ void tcw_pack_kernel(const PackArgs a) {
     if (gtid == 0) {
         hdr->magic = kMagic; hdr->kind = a.kind; hdr->dim = a.dim; hdr->n_cond = a.n_cond; hdr->n_tr = a.n_tr;
         hdr->n_chunks = a.n_chunks; hdr->P = a.P; hdr->act = a.act; hdr->s2 = s2;
-        hdr->n_lat = a.n_lat;
+        hdr->n_lat = a.n_lat; hdr->n_bins = a.n_bins;
         hdr->k1pad = (a.n_cond + a.n_lat + 15) & ~15;
         if (hdr->k1pad == 0) hdr->k1pad = 16;
         hdr->m_d = div_magic(a.dim); hdr->m_d4 = div_magic(max(a.dim >> 2, 1)); hdr->m_ntr = div_magic(a.n_tr);
@@ -1371,8 +1380,9 @@ __global__ void tcw_pack_kernel(const PackArgs a) {
     float* b2 = reinterpret_cast<float*>(a.out + kOffB2);
     for (int i = gtid; i < kHid; i += gsz) b1[i] = a.b1[i];
     for (int i = gtid; i < kMaxChunks * kChunkN; i += gsz) {
-        const int ji = i / kPPad, col = i % kPPad, p = param_of_col(col);
-        const float bv = (ji < a.n_tr && p < a.P) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
+        const int ji = i / kPPad, col = i % kPPad, p = param_of_col(col, a.n_bins, a.P);
+        float bv = (ji < a.n_tr && p >= 0) ? a.b2[a.tr_idx[ji] * a.P + p] : 0.f;
+        if (col < 2 * kBins && p < 0 && ji < a.n_tr) bv = -INFINITY;   // padded bin: numerator exactly 0
         b2[i] = (col < 2 * kBins) ? bv * 1.4426950408889634f : bv;
     }
     for (int i = gtid; i < kHid * kK1; i += gsz) {
@@ -1390,9 +1400,9 @@ __global__ void tcw_pack_kernel(const PackArgs a) {
     const float inv = 1.f / s2;
     for (int i = gtid; i < kMaxChunks * kChunkN * kHid; i += gsz) {
         const int k = i % kHid, rn = i / kHid, n = rn % kChunkN, c = rn / kChunkN;
-        const int ji = c * kG + n / kPPad, p = param_of_col(n % kPPad);
+        const int ji = c * kG + n / kPPad, p = param_of_col(n % kPPad, a.n_bins, a.P);
         float v = 0.f;
-        if (c < a.n_chunks && ji < a.n_tr && p < a.P) v = a.W2[((size_t)a.tr_idx[ji] * a.P + p) * kHid + k] * inv;
+        if (c < a.n_chunks && ji < a.n_tr && p >= 0) v = a.W2[((size_t)a.tr_idx[ji] * a.P + p) * kHid + k] * inv;
         __half hi, lo;
         split_f16(v, hi, lo);
         const uint32_t off = kOffW2 + (uint32_t)c * kChunkBytes + core_off(n, k, kHid, 2);
@@ -1405,10 +1415,13 @@ __global__ void tcw_bound_kernel(const PackArgs a) {
     const int ji = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), p = threadIdx.x & 31;
     bool ok = false;
     if (ji < a.n_tr && (a.act == STB_ACT_TANH || a.act == STB_ACT_SIGMOID)) {
-        const size_t row = (size_t)a.tr_idx[ji] * a.P + p;
-        float l1 = fabsf(a.b2[row]);
-        for (int k = 0; k < kHid; ++k) l1 += fabsf(a.W2[row * kHid + k]);
-        ok = (l1 * 1.4426950408889634f <= 100.f);
+        ok = true;
+        if (p < 2 * a.n_bins) {                              // the 2 K softmax rows of the dim
+            const size_t row = (size_t)a.tr_idx[ji] * a.P + p;
+            float l1 = fabsf(a.b2[row]);
+            for (int k = 0; k < kHid; ++k) l1 += fabsf(a.W2[row * kHid + k]);
+            ok = (l1 * 1.4426950408889634f <= 100.f);
+        }
     }
     ok = __all_sync(0xffffffffu, ok);
     if (p == 0 && ok && ji < kMaxTr) atomicOr(&reinterpret_cast<Header*>(a.out)->noshift_mask[ji >> 5], 1u << (ji & 31));
@@ -1435,7 +1448,10 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
     a.n_lat = L->latent_dim;
     if (a.n_lat < 0 || a.n_cond + a.n_lat > kK1 || L->net.dims[0] != L->dim + a.n_lat) return false;
     a.n_chunks = (a.n_tr + kG - 1) / kG;
-    a.kind = L->kind; a.dim = L->dim; a.P = L->kind == STB_RQS ? 3 * kBins - 1 : 2 * kBins + 2;
+    a.n_bins = L->n_bins;
+    if (a.n_bins < 2 || a.n_bins > kBins) return false;
+    a.kind = L->kind; a.dim = L->dim; a.P = L->kind == STB_RQS ? 3 * a.n_bins - 1 : 2 * a.n_bins + 2;
+    if (L->net.dims[2] != L->dim * a.P) return false;
     a.act = L->net.activation;
     a.W1 = L->net.W[0]; a.b1 = L->net.b[0]; a.W2 = L->net.W[1]; a.b2 = L->net.b[1];
     return true;
@@ -1446,7 +1462,7 @@ static bool fill_pack_args(const stb_layer* L, PackArgs& a) {
 bool tcw_layer_supported(const stb_layer* L) {
     using namespace tcw;
     if (L->kind != STB_RQS && L->kind != STB_CUBIC) return false;
-    if (L->n_bins != kBins || !L->cond_x || L->zero_cond || L->latent_dim < 0 || L->time_input) return false;
+    if (L->n_bins < 2 || L->n_bins > kBins || !L->cond_x || L->zero_cond || L->latent_dim < 0 || L->time_input) return false;
     if (L->has_box || L->row_out || L->dim < 2 || L->dim > kMaxDim) return false;
     const stb_mlp& N = L->net;
     if (N.n_linear != 2 || N.dims[1] != kHid || N.final_activation != STB_ACT_NONE) return false;
@@ -1516,13 +1532,18 @@ int tcw_layer_apply(const stb_layer* L, const void* image, int direction, const 
     A.n_tiles = (int)tiles;
     const bool inv = direction == STB_INVERSE;
     void (*kern)(Args);
-    if (L->kind == STB_RQS) kern = inv ? tc_wide_kernel<STB_RQS, true, false> : tc_wide_kernel<STB_RQS, false, false>;
-    else kern = inv ? tc_wide_kernel<STB_CUBIC, true, false> : tc_wide_kernel<STB_CUBIC, false, false>;
+    if (L->n_bins == kBins) {
+        if (L->kind == STB_RQS) kern = inv ? tc_wide_kernel<STB_RQS, true, false> : tc_wide_kernel<STB_RQS, false, false>;
+        else kern = inv ? tc_wide_kernel<STB_CUBIC, true, false> : tc_wide_kernel<STB_CUBIC, false, false>;
+    } else {
+        if (L->kind == STB_RQS) kern = inv ? tc_wide_kernel<STB_RQS, true, false, false> : tc_wide_kernel<STB_RQS, false, false, false>;
+        else kern = inv ? tc_wide_kernel<STB_CUBIC, true, false, false> : tc_wide_kernel<STB_CUBIC, false, false, false>;
+    }
     return tcw_launch(kern, A, tiles, stream, "tc_wide_kernel");
 }
 
 // quadratic and cubic (fused variant); `latent=` layers train through the element-wise kernels + autograd
-bool tcw_backward_supported(const stb_layer* L) { return tcw_layer_supported(L) && L->latent_dim == 0; }
+bool tcw_backward_supported(const stb_layer* L) { return tcw_layer_supported(L) && L->latent_dim == 0 && L->n_bins == tcw::kBins; }
 
 int tcw_layer_backward(const stb_layer* L, const void* image, int direction, const float* x, const float* g_out,
                        const float* g_ldj, float* g_x, float* g_net, float* hidden, int64_t rows,

@@ -268,11 +268,25 @@ def test_latent_input_on_the_tensor_path(kind, d, hidden, latent_dim, n_layers, 
     ('cubic', 64, 12, 1, 129, cases.ALT),
 ])
 def test_fewer_than_16_bins_on_the_tensor_path(kind, d, K, n_layers, rows, masks, monkeypatch):
+    _check_few_bins(kind, d, K, n_layers, rows, masks, [64], 1, monkeypatch)
+
+
+@pytest.mark.parametrize('kind,d,K,hidden,rows', [
+    ('quadratic', 100, 8, [64], 300),            # d > 64: the 128-row kernel (tc_wide.cu)
+    ('cubic', 128, 5, [64], 200),
+    ('quadratic', 48, 10, [128, 128], 300),      # wide conditioners (tc_hwide.cu)
+    ('cubic', 32, 6, [256], 130),
+])
+def test_fewer_than_16_bins_on_the_other_spline_kernels(kind, d, K, hidden, rows, monkeypatch):
+    _check_few_bins(kind, d, K, 2, rows, cases.ALT, hidden, 2, monkeypatch)
+
+
+def _check_few_bins(kind, d, K, n_layers, rows, masks, hidden, expect_launches, monkeypatch):
     """Spline couplings with 2 <= n_bins < 16 run on the tensor-core path too: the packed image keeps its 16-bin
     layout, padded bins get weight 0 / bias -inf (numerator exactly 0) and the search never selects them
     (tc_spline16.cuh, FULL = false).  Against the CUDA-core kernel and the oracle, both directions."""
     rs = cases._rs(1300 + d + K)
-    spec = [cases.coupling_spec(rs, kind, d, [64], masks[i % 2], n_bins=K, lower=-4., upper=4.) for i in range(n_layers)]
+    spec = [cases.coupling_spec(rs, kind, d, hidden, masks[i % 2], n_bins=K, lower=-4., upper=4.) for i in range(n_layers)]
     torch.manual_seed(rows + K)
     x = torch.randn(rows, d, device=DEV) * 1.6                   # a good share of elements outside the box, and inside
     x[0, :] = 4.0                                               # exactly on the upper box edge: the last REAL bin
@@ -291,7 +305,7 @@ def test_fewer_than_16_bins_on_the_tensor_path(kind, d, K, n_layers, rows, masks
         tflow.log_prob(x[:4])
         n0 = _ops.launch_count()
         lp_t = tflow.log_prob(x)
-        assert _ops.launch_count() - n0 == 1
+        assert _ops.launch_count() - n0 == expect_launches
         xi_t, li_t = tflow.inverse_and_log_det_jacobian(x)
         yf_t, lf_t = tflow.forward_and_log_det_jacobian(x)
         back = tflow.inverse(yf_t)
