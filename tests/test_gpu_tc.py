@@ -257,6 +257,35 @@ def test_latent_input_on_the_tensor_path(kind, d, hidden, latent_dim, n_layers, 
             assert fail <= 2e-2, f'{what}: {fail:.3%} outside tolerance (max abs err {mx:.3e})'
 
 
+def test_latent_input_with_folded_permutations():
+    """`latent=` couplings with Flip / Permute layers between them: still ONE launch (the permutations are folded into the
+    gather lists of the conditioning columns only -- the latent columns are not tile columns)."""
+    d, latent_dim, rows = 32, 8, 600
+    rs = cases._rs(77)
+    spec = []
+    for i in range(3):
+        spec.append(cases.coupling_spec(rs, 'quadratic', d, [64], 'ordered_right_half', n_bins=16, lower=-4., upper=4.,
+                                        latent_dim=latent_dim))
+        spec.append({'type': 'flip'} if i != 1 else {'type': 'permute', 'perm': rs.permutation(d).tolist()})
+    torch.manual_seed(5)
+    x = torch.randn(rows, d, device=DEV) * 1.3
+    lat = torch.randn(rows, latent_dim, device=DEV)
+    flow = st.NormalizingFlow(st.UnitNormal(d), [l.to(DEV) for l in layers_from_spec(spec)])
+    with torch.no_grad():
+        flow.log_prob(x[:4], latent=lat[:4])
+        n0 = _ops.launch_count()
+        lp = flow.log_prob(x, latent=lat)
+        assert _ops.launch_count() - n0 == 1
+        yf, lf = flow.forward_and_log_det_jacobian(x, latent=lat)
+    xc, lc = x.cpu(), lat.cpu()
+    s64 = O.spec_to(spec, torch.float64)
+    for got, f32, f64, what in (
+            (lp, O.flow_log_prob(spec, xc, latent=lc), O.flow_log_prob(s64, xc.double(), latent=lc.double()), 'log_prob'),
+            (yf, O.flow_forward(spec, xc, latent=lc), O.flow_forward(s64, xc.double(), latent=lc.double()), 'forward y')):
+        fail, _, mx = close_or_arbitrated(got, f32, f64, 1e-5, 1e-5)
+        assert fail <= 2e-2, f'{what}: {fail:.3%} outside tolerance (max abs err {mx:.3e})'
+
+
 @pytest.mark.parametrize('kind,d,K,n_layers,rows,masks', [
     ('quadratic', 64, 8, 3, 700, cases.ALT),
     ('quadratic', 64, 5, 8, 300, cases.ALT),
