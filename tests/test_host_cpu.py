@@ -212,3 +212,64 @@ def test_cabi_host_side_dispatch_without_a_gpu():
     # rows == 0 is a no-op that touches nothing
     assert lib.stb_layer_apply(C.byref(L), 0, dummy, None, None, dummy, None, 0, 0, 0, None) == 0
     assert lib.stb_flow_log_prob(C.byref(L), 1, dummy, None, None, dummy, dummy, 0, None) == 0
+
+
+def test_call_plan_records_follow_structure_and_parameter_changes():
+    """flow.run_chain's cache bookkeeping (no GPU needed): a record per ModuleList, rebuilt when the structure epoch
+    moves (attribute set on one of this package's modules, parameter / sub-module registered anywhere, packed image
+    dropped), its plans dropped when a parameter's (data_ptr, _version, requires_grad) changes; weak keys."""
+    import copy
+    import gc
+    import weakref
+    import stribor_b200 as st
+    from stribor_b200 import _epoch, flow as F
+
+    def make():
+        return st.NormalizingFlow(st.UnitNormal(8), [
+            st.Coupling(st.Spline(8, 4, latent_net=st.net.MLP(8, [16], 8 * 11), lower=-3, upper=3, spline_type='quadratic'),
+                        mask=m) for m in ('ordered_right_half', 'ordered_left_half')])
+
+    flow = make()
+    rec = F._record(flow.transforms)
+    assert rec.chainable and len(rec.plist) == 8 and rec.any_grad
+    assert F._record(flow.transforms) is rec                       # nothing moved
+    rec.plans['sentinel'] = object()
+    # in-place parameter update: same record, plans dropped
+    lin = [m for m in flow.modules() if isinstance(m, torch.nn.Linear)]
+    with torch.no_grad():
+        lin[0].weight.mul_(2.0)
+    assert F._record(flow.transforms) is rec and not rec.plans
+    rec.plans['sentinel'] = object()
+    lin[1].bias.requires_grad_(False)                              # requires_grad is part of the token
+    assert F._record(flow.transforms) is rec and not rec.plans
+    # attribute of one of this package's modules
+    e0 = _epoch.value
+    flow.transforms[0].transform.lower = -5.0
+    assert _epoch.value > e0 and F._record(flow.transforms) is not rec
+    rec = F._record(flow.transforms)
+    # a parameter object replaced, a sub-module appended, a packed image dropped: all move the epoch
+    for change in (lambda: setattr(lin[0], 'bias', torch.nn.Parameter(torch.zeros_like(lin[0].bias))),
+                   lambda: flow.transforms.append(make().transforms[0]),
+                   lambda: st.invalidate_packed(flow)):
+        e0 = _epoch.value
+        change()
+        assert _epoch.value > e0
+        new = F._record(flow.transforms)
+        assert new is not rec
+        rec = new
+    assert len(rec.plist) == 12
+    # gradients off / on decide the fused path, per call
+    with torch.no_grad():
+        assert F._chain_ok(flow.transforms, (None,))
+    assert not F._chain_ok(flow.transforms, (None,))              # parameters require grad
+    flow.requires_grad_(False)
+    assert F._chain_ok(flow.transforms, (None,))
+    assert not F._chain_ok(flow.transforms, (torch.zeros(1, requires_grad=True),))
+    # foreign modules never chain; records do not keep flows alive; flows stay deep-copyable
+    foreign = st.NormalizingFlow(st.UnitNormal(8), [torch.nn.Identity()])
+    assert not F._chain_ok(foreign.transforms, (None,))
+    copy.deepcopy(flow)
+    ref = weakref.ref(flow.transforms)
+    del flow, rec, new, lin, change
+    gc.collect()
+    assert ref() is None
