@@ -167,16 +167,16 @@ def test_backward_workspace_layout_constants_match_the_kernels():
     assert all(param_of_col(c) == p for p, c in enumerate(cols))
 
 
-def _spline_struct(dim, kind='quadratic', hidden=64, n_bins=16):
+def _spline_struct(dim, kind='quadratic', hidden=64, n_bins=16, latent_dim=0):
     """stb_layer for Coupling(Spline(dim, n_bins), MLP(dim, [hidden], dim * P)) with an ordered mask; the weight
     pointers are CPU tensors -- the host-side entry points below never dereference them."""
     import ctypes as C
     from stribor_b200 import _lib, _ops
     P = 3 * n_bins - 1 if kind == 'quadratic' else 2 * n_bins + 2
     mask_list = [0] * (dim // 2) + [1] * (dim - dim // 2)
-    meta = [_lib.RQS if kind == 'quadratic' else _lib.CUBIC, dim, 0, 1, 0, n_bins, 0, 0, _lib.ACTIVATIONS['Tanh'], 0,
-            2, 4, 0, 0, dim, hidden, dim * P] + mask_list
-    params = [torch.zeros(hidden, dim), torch.zeros(hidden), torch.zeros(dim * P, hidden), torch.zeros(dim * P)]
+    meta = [_lib.RQS if kind == 'quadratic' else _lib.CUBIC, dim, latent_dim, 1, 0, n_bins, 0, 0, _lib.ACTIVATIONS['Tanh'], 0,
+            2, 4, 0, 0, dim + latent_dim, hidden, dim * P] + mask_list
+    params = [torch.zeros(hidden, dim + latent_dim), torch.zeros(hidden), torch.zeros(dim * P, hidden), torch.zeros(dim * P)]
     mask = torch.tensor(mask_list, dtype=torch.uint8)
     L = _ops.make_struct(meta, [-4., 4., 0., 1., 0., 1.], mask, params, None)
     L._keep = (params, mask)
@@ -202,6 +202,17 @@ def test_cabi_host_side_dispatch_without_a_gpu():
         assert lib.stb_layer_backward_workspace_bytes(C.byref(L130), 1000) == 0
     assert lib.stb_packed_bytes(C.byref(_spline_struct(64, hidden=32))) == 0     # MLP[32]: no tensor-core path
     assert lib.stb_layer_backward_workspace_bytes(C.byref(_spline_struct(64, n_bins=8)), 10) == 0
+    # round 2: 2..15 bins and `latent=` inputs keep the tensor-core FORWARD images (the fused backward needs 16 bins, no latent)
+    assert lib.stb_packed_bytes(C.byref(_spline_struct(64, n_bins=8))) == tc_bytes + wide_bytes
+    assert lib.stb_packed_bytes(C.byref(_spline_struct(128, n_bins=5, kind='cubic'))) == wide_bytes
+    assert lib.stb_packed_bytes(C.byref(_spline_struct(64, n_bins=1))) == 0
+    assert lib.stb_packed_bytes(C.byref(_spline_struct(64, n_bins=17))) == 0
+    assert lib.stb_packed_bytes(C.byref(_spline_struct(32, latent_dim=8))) == tc_bytes + wide_bytes     # 16 + 8 <= 32 K columns
+    assert lib.stb_packed_bytes(C.byref(_spline_struct(64, latent_dim=16))) == wide_bytes               # 32 + 16 > 32: 128-row kernel
+    assert lib.stb_packed_bytes(C.byref(_spline_struct(64, latent_dim=40))) == 0                        # 32 + 40 > 64
+    assert lib.stb_layer_backward_workspace_bytes(C.byref(_spline_struct(32, latent_dim=8)), 10) == 0
+    big = lib.stb_packed_bytes(C.byref(_spline_struct(64, hidden=256, n_bins=10)))                      # wide conditioner, MLP[256]
+    assert big > tc_bytes and lib.stb_packed_bytes(C.byref(_spline_struct(64, hidden=256, n_bins=16))) == big
     # argument validation returns STB_EINVAL (-1) before anything is launched
     L = _spline_struct(64)
     dummy = C.c_void_p(0x1000)
