@@ -116,3 +116,8 @@ run_latent('latent cubic single layer d40', 'cubic', 40, [64], 12, 1, (1, 257))
 run_latent('latent hwide d32', 'quadratic', 32, [128, 128], 8, 2, (1, 130))
 run_latent('latent affine pipe d32', 'affine', 32, [128, 128], 8, 2, (1, 129, 300))
 run_latent('latent wide d64 (48 K columns)', 'quadratic', 64, [64], 16, 2, (1, 129, 300))
+# fewer than 16 bins on the tensor-core kernels (padded 16-bin layout)
+run('few bins pair kernel d64 k8', cases._mk_flow('quadratic', 64, [64], 3, 8, 8, 21)(), rows_list=(1, 129, 300))
+run('few bins pair kernel cubic d33 k3', cases._mk_flow('cubic', 33, [64], 2, 3, 8, 22, masks=('ordered_left_half', 'parity_odd'))(), rows_list=(1, 257))
+run('few bins wide d100 k8', cases._mk_flow('quadratic', 100, [64], 2, 8, 8, 23)(), rows_list=(1, 130))
+run('few bins hwide d48 k10', cases._mk_flow('quadratic', 48, [128, 128], 2, 10, 8, 24)(), rows_list=(1, 130))
