@@ -284,3 +284,22 @@ def test_call_plan_records_follow_structure_and_parameter_changes():
     del flow, rec, new, lin, change
     gc.collect()
     assert ref() is None
+
+
+@pytest.mark.parametrize('name', ['TimeIdentity', 'TimeLinear', 'TimeTanh', 'TimeLog', 'TimeFourier', 'TimeFourierBounded'])
+def test_time_embeddings_vanish_at_zero_and_match_their_derivative(name):
+    """The reference's time embeddings (net/time_net.py): phi(0) = 0, `derivative` is d phi / dt, shapes [..., out]."""
+    import stribor_b200 as st
+    torch.manual_seed(3)
+    cls = getattr(st.net, name)
+    net = cls(6, hidden_dim=5) if 'Fourier' in name else cls(6)
+    t = torch.rand(4, 3, 1, dtype=torch.float64) * 2
+    net = net.double()
+    assert net(torch.zeros(4, 3, 1, dtype=torch.float64)).abs().max() == 0
+    out = net(t)
+    assert out.shape == (4, 3, 6)
+    tg = t.clone().requires_grad_(True)
+    want = torch.stack([torch.autograd.grad(net(tg)[..., j].sum(), tg, retain_graph=True)[0][..., 0] for j in range(6)], -1)
+    torch.testing.assert_close(net.derivative(t).expand_as(want), want, rtol=1e-10, atol=1e-12)
+    if name == 'TimeFourierBounded':
+        assert out.abs().max() <= 0.5
