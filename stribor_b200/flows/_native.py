@@ -106,8 +106,8 @@ def device_mask(cache, mask_func, dim, device):
 
 def fusable(net) -> bool:
     """Can the kernels evaluate this conditioner themselves?"""
-    if not isinstance(net, MLP):
-        return False
+    if not isinstance(net, MLP) or type(net).forward is not MLP.forward:
+        return False                  # (a subclass that overrides forward is evaluated as the module it is)
     try:
         net.describe()
         return True
@@ -128,7 +128,7 @@ def row_params_from_net(net, z, rows_idx=None):
     """Evaluate a conditioner as a PyTorch module (training path, or a conditioner the kernels do
     not fuse).  For an ``MLP`` with ``rows_idx`` only those rows of the LAST Linear are evaluated (the
     transformed dims' parameters, "masked minimum"); any other module is simply called."""
-    if not isinstance(net, MLP) or net._wrapped:
+    if not isinstance(net, MLP) or net._wrapped or type(net).forward is not MLP.forward:
         out = net(z)
         return out if rows_idx is None else out.index_select(-1, rows_idx)
     mods = list(net.net)

@@ -42,8 +42,16 @@ class Affine(ElementwiseTransform):
                 self.register_buffer('log_scale', scale.log(), persistent=False)
                 self.register_buffer('shift', shift.clone(), persistent=False)
 
+    def plain(self) -> bool:
+        """True when a subclass overrides none of the transform's methods (nor adds the reference's ``_get_params``
+        hook, affine.py:59-67): only then may the fused kernels stand in for them."""
+        cls = type(self)
+        own = ('forward', 'inverse', 'log_det_jacobian', 'forward_and_log_det_jacobian', 'inverse_and_log_det_jacobian',
+               'log_diag_jacobian')
+        return all(getattr(cls, n) is getattr(Affine, n) for n in own) and not hasattr(cls, '_get_params')
+
     def chainable(self):
-        return self.latent_net is None or fusable(self.latent_net)
+        return self.plain() and (self.latent_net is None or fusable(self.latent_net))
 
     def params_per_dim(self):
         return 2

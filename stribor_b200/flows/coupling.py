@@ -60,7 +60,7 @@ class Coupling(PackedOwner, Transform):
 
     def _fusable_transform(self):
         tr = self.transform
-        return isinstance(tr, Affine) or (isinstance(tr, Spline) and tr.plain())
+        return (isinstance(tr, Affine) or isinstance(tr, Spline)) and tr.plain()
 
     def chainable(self):
         if not self._fusable_transform():
@@ -239,11 +239,16 @@ class ContinuousAffineCoupling(PackedOwner, Transform):
         self._masks = {}
         self._packed = PackedCache()
 
+    def _linear_time(self):
+        """Is the time embedding exactly ``scale * t``?  (``TimeTanh`` / ``TimeLog`` SUBCLASS ``TimeLinear`` as in the
+        reference, and a user subclass may override ``forward``: only the class itself is fused into the kernels.)"""
+        return type(self.time_net) is TimeLinear
+
     def chainable(self):
-        return fusable(self.latent_net) and isinstance(self.time_net, TimeLinear)
+        return fusable(self.latent_net) and self._linear_time()
 
     def _time_scale(self, dim):
-        if not isinstance(self.time_net, TimeLinear):
+        if not self._linear_time():
             raise NotImplementedError(f'time_net {type(self.time_net).__name__} is not fused; use TimeLinear')
         s = self.time_net.scale
         n = s.shape[-1]
@@ -265,7 +270,7 @@ class ContinuousAffineCoupling(PackedOwner, Transform):
     def _run(self, x, t, latent, direction, want_ldj):
         if t is None:
             raise TypeError('ContinuousAffineCoupling needs the time input `t`')
-        if needs_autograd(self, x, t, latent) or not fusable(self.latent_net) or not isinstance(self.time_net, TimeLinear):
+        if needs_autograd(self, x, t, latent) or not fusable(self.latent_net) or not self._linear_time():
             return self._run_autograd(x, t, latent, direction, want_ldj)
         d = self.describe(x.shape[-1], 0 if latent is None else latent.shape[-1], x.device)
         return run_layer(d, x, latent, t, direction, want_ldj)

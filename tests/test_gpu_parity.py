@@ -238,6 +238,32 @@ def test_set_data_coupling_matches_reference_semantics(kind):
     assert torch.equal(y.cpu()[:, m == 1], x[:, m == 1])
 
 
+def test_overriding_subclasses_run_as_modules():
+    """A subclass that overrides forward is evaluated as the module it is (not by the fused kernel of its base class)."""
+    class Doubled(st.net.MLP):
+        def forward(self, x):
+            return 2 * super().forward(x)
+
+    class Clamped(st.Affine):
+        def forward(self, x, latent=None, **kw):
+            return super().forward(x.clamp(-1, 1), latent=latent, **kw)
+
+    torch.manual_seed(0)
+    d = 6
+    x = torch.randn(40, d, device=DEV) * 2
+    m = torch.tensor([0., 0., 0., 1., 1., 1.], device=DEV)
+    with torch.no_grad():
+        c = st.Coupling(st.Affine(d, latent_net=Doubled(d, [8], 2 * d)), 'ordered_0').to(DEV)
+        prm = c.transform.latent_net(x * m)
+        want = x * torch.exp(prm[:, :d]) + prm[:, d:]
+        torch.testing.assert_close(c(x)[:, :3], want[:, :3], rtol=1e-5, atol=1e-5)
+        c2 = st.Coupling(Clamped(d, latent_net=st.net.MLP(d, [8], 2 * d)), 'ordered_0').to(DEV)
+        prm = c2.transform.latent_net(x * m)
+        want = x.clamp(-1, 1) * torch.exp(prm[:, :d]) + prm[:, d:]
+        torch.testing.assert_close(c2(x)[:, :3], want[:, :3], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(c2(x)[:, 3:], x[:, 3:], rtol=0, atol=0)
+
+
 def test_foreign_conditioner_and_time_net():
     """A conditioner / time embedding the kernels do not fuse (any nn.Module) still runs: the module
     is evaluated by PyTorch, gather + transform + log-det by the element-wise CUDA kernels."""
@@ -290,3 +316,15 @@ def test_foreign_conditioner_and_time_net():
         tn = ca.time_net(t)
         want = x * torch.exp(out[:, :d] * tn[:, :d]) + out[:, d:] * tn[:, d:]
         torch.testing.assert_close(y[:, :3], want[:, :3], rtol=1e-5, atol=1e-5)
+    # the package's own copies of the reference's other time embeddings take the same path
+    for tn_cls, kw in ((st.net.TimeIdentity, {}), (st.net.TimeTanh, {}), (st.net.TimeLog, {}),
+                       (st.net.TimeFourier, {'hidden_dim': 4}), (st.net.TimeFourierBounded, {'hidden_dim': 4})):
+        ca = st.ContinuousAffineCoupling(st.net.MLP(d + 1, [8], 2 * d), tn_cls(2 * d, **kw), 'ordered_0').to(DEV)
+        with torch.no_grad():
+            y = ca(x, t=t)
+            assert torch.allclose(ca.inverse(y, t=t), x, atol=1e-5), tn_cls.__name__
+            assert (ca(x, t=torch.zeros_like(t)) == x).all()
+            out = ca.latent_net(torch.cat([x * m, t], -1))
+            tn = ca.time_net(t)
+            want = x * torch.exp(out[:, :d] * tn[:, :d]) + out[:, d:] * tn[:, d:]
+            torch.testing.assert_close(y[:, :3], want[:, :3], rtol=1e-5, atol=1e-5)

@@ -303,3 +303,32 @@ def test_time_embeddings_vanish_at_zero_and_match_their_derivative(name):
     torch.testing.assert_close(net.derivative(t).expand_as(want), want, rtol=1e-10, atol=1e-12)
     if name == 'TimeFourierBounded':
         assert out.abs().max() <= 0.5
+
+
+def test_subclasses_that_override_behaviour_are_not_fused():
+    """The fused kernels stand in for a module only when it IS the class they implement: a subclass that overrides
+    forward (the reference derives TimeTanh / TimeLog from TimeLinear exactly like that) must run as the module it is."""
+    import stribor_b200 as st
+    from stribor_b200.flows._native import fusable
+
+    class Doubled(st.net.MLP):
+        def forward(self, x):
+            return 2 * super().forward(x)
+
+    class MyTime(st.net.TimeLinear):
+        def forward(self, t):
+            return torch.sin(self.scale * t)
+
+    class Clamped(st.Affine):
+        def forward(self, x, latent=None, **kw):
+            return super().forward(x.clamp(-1, 1), latent=latent, **kw)
+
+    assert fusable(st.net.MLP(4, [8], 8)) and not fusable(Doubled(4, [8], 8))
+    mk = lambda tn: st.ContinuousAffineCoupling(st.net.MLP(5, [8], 8), tn, 'ordered_0')
+    assert mk(st.net.TimeLinear(8)).chainable()
+    for tn in (MyTime(8), st.net.TimeTanh(8), st.net.TimeLog(8), st.net.TimeIdentity(8)):
+        assert not mk(tn).chainable(), type(tn).__name__
+    assert st.Coupling(st.Affine(4, latent_net=st.net.MLP(4, [8], 8)), 'ordered_0').chainable()
+    assert not st.Coupling(st.Affine(4, latent_net=Doubled(4, [8], 8)), 'ordered_0').chainable()
+    assert not st.Coupling(Clamped(4, latent_net=st.net.MLP(4, [8], 8)), 'ordered_0').chainable()
+    assert st.Affine(4, latent_net=st.net.MLP(3, [8], 8)).plain() and not Clamped(4, latent_net=st.net.MLP(3, [8], 8)).plain()
