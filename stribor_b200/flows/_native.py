@@ -172,3 +172,15 @@ def invalidate_packed(module: torch.nn.Module):
     for m in module.modules():
         if isinstance(m, PackedOwner):
             m.invalidate_packed()
+
+
+_LAYER_API = ('forward', 'inverse', 'log_det_jacobian', 'forward_and_log_det_jacobian', 'inverse_and_log_det_jacobian')
+
+
+def layer_is_plain(layer) -> bool:
+    """Does ``layer`` behave as the class of THIS package it derives from?  A user subclass that overrides one of the
+    transform methods (say, a coupling that perturbs its input) must not be replaced by the fused whole-chain call,
+    which talks to the kernels directly: compare the methods with those of the nearest package class in the MRO."""
+    cls = type(layer)
+    base = next((c for c in cls.__mro__ if c.__module__.startswith('stribor_b200')), None)
+    return base is not None and all(getattr(cls, n, None) is getattr(base, n, None) for n in _LAYER_API)

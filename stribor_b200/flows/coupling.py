@@ -21,7 +21,7 @@ from .. import _lib, _ops
 from ..flow import Transform, run_layer
 from ..net.time_net import TimeLinear
 from ..util.mask import get_mask
-from ._native import PackedCache, PackedOwner, build_meta, device_mask, fusable, needs_autograd, row_params_from_net
+from ._native import PackedCache, PackedOwner, build_meta, device_mask, fusable, needs_autograd, row_params_from_net, layer_is_plain
 from .affine import Affine
 from .spline import Spline
 
@@ -63,7 +63,7 @@ class Coupling(PackedOwner, Transform):
         return (isinstance(tr, Affine) or isinstance(tr, Spline)) and tr.plain()
 
     def chainable(self):
-        if not self._fusable_transform():
+        if not self._fusable_transform() or not layer_is_plain(self):
             return False
         net = self.transform.latent_net
         return (not self.set_data) and (net is None or fusable(net))
@@ -245,7 +245,7 @@ class ContinuousAffineCoupling(PackedOwner, Transform):
         return type(self.time_net) is TimeLinear
 
     def chainable(self):
-        return fusable(self.latent_net) and self._linear_time()
+        return fusable(self.latent_net) and self._linear_time() and layer_is_plain(self)
 
     def _time_scale(self, dim):
         if not self._linear_time():

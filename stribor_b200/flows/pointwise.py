@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from .. import _lib
 from ..flow import ElementwiseTransform, run_layer
-from ._native import needs_autograd
+from ._native import layer_is_plain, needs_autograd
 
 __all__ = ['Flip', 'Permute', 'Sigmoid', 'Logit']
 
@@ -30,7 +30,7 @@ class _Pointwise(ElementwiseTransform):
         return []
 
     def chainable(self):
-        return self.in_place_ok
+        return self.in_place_ok and layer_is_plain(self)
 
     def describe(self, dim, latent_dim, device):
         p = self._params(dim, device)

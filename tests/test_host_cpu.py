@@ -332,3 +332,27 @@ def test_subclasses_that_override_behaviour_are_not_fused():
     assert not st.Coupling(st.Affine(4, latent_net=Doubled(4, [8], 8)), 'ordered_0').chainable()
     assert not st.Coupling(Clamped(4, latent_net=st.net.MLP(4, [8], 8)), 'ordered_0').chainable()
     assert st.Affine(4, latent_net=st.net.MLP(3, [8], 8)).plain() and not Clamped(4, latent_net=st.net.MLP(3, [8], 8)).plain()
+
+
+def test_layer_subclasses_that_override_the_transform_methods_leave_the_fused_chain():
+    import stribor_b200 as st
+    from stribor_b200 import flow as F
+
+    class Noisy(st.Coupling):
+        def forward(self, x, **kw):
+            return super().forward(x + 1.0, **kw)
+
+    class Same(st.Coupling):                      # adds state, overrides nothing the kernels replace
+        def extra(self):
+            return 1
+
+    mk = lambda cls: cls(st.Affine(4, latent_net=st.net.MLP(4, [8], 8)), 'ordered_0')
+    assert mk(st.Coupling).chainable() and mk(Same).chainable() and not mk(Noisy).chainable()
+    assert st.Flip().chainable()
+
+    class MyFlip(st.Flip):
+        def inverse(self, y, **kw):
+            return y
+    assert not MyFlip().chainable()
+    flow = st.NormalizingFlow(st.UnitNormal(4), [mk(st.Coupling), mk(Noisy)]).requires_grad_(False)
+    assert not F._chain_ok(flow.transforms, (None,))
