@@ -1,9 +1,9 @@
 // Tensor-core spline coupling with a WIDE conditioner (tcgen05 + TMEM-resident activations).
 //
-// Scope: st.Coupling(st.Spline(dim <= 64, n_bins = 16, 'quadratic' | 'cubic', latent_net = MLP(dim, [H] or [H, H],
-// dim * P)), mask) with H in {64 (two hidden layers only), 128, 192, 256}, Tanh / Sigmoid, no latent input -- the
-// secondary shape of BASELINE.json configs[2] (MLP[256,256], 7.34 MFLOP per sample), which round 1 left on
-// the CUDA-core kernel.  MLP[64] stays on tc_layer.cu / tc_wide.cu.
+// Scope: st.Coupling(st.Spline(dim <= 64, 2 <= n_bins <= 16, 'quadratic' | 'cubic', latent_net = MLP(dim (+ latent), [H] or
+// [H, H], dim * P)), mask) with H in {64 (two hidden layers only), 128, 192, 256}, Tanh / Sigmoid, conditioning + latent
+// columns <= 32 -- the secondary shape of BASELINE.json configs[2] (MLP[256,256], 7.34 MFLOP per sample),
+// which round 1 left on the CUDA-core kernel.  MLP[64] stays on tc_layer.cu / tc_wide.cu.
 //
 // With K = H the last Linear no longer fits the layout of tc_layer.cu (a 256-wide fp16 hi|lo A operand is 128 KB of
 // shared memory per 128 rows).  Here the hidden activations never leave the tensor-core side:
@@ -13,12 +13,12 @@
 //          split on packed pairs, tcgen05.st of the 8 + 8 packed columns back INTO the columns just consumed
 //   GEMM2' [128 x H] x [H x H]      (two hidden layers) A = h1 from TMEM, weights streamed in 16-wide K blocks ->
 //                                   TMEM [256, 256 + H); second activation in place again
-//   chunks one transformed dim at a time: [128 x H] x [H x 48], A = the last hidden layer from TMEM, the dim's
-//          packed last-Linear rows (hi | lo, H / 16 K blocks = one ring stage), 3 passes corrections first -> one of
-//          five 48-column accumulator buffers; epilogue group g (4 warps = the tile's 128 rows) takes dims g, g + 4, ...:
-//          thread = row pulls its 48 parameters and evaluates the spline in registers (tc_spline16.cuh, the same
-//          code as the MLP[64] kernels)
-// One persistent CTA per SM, 18 warps (producer, issuer, 16 epilogue), tile = 128 rows, 3-stage cp.async.bulk ring.
+//   chunks TWO transformed dims at a time: [128 x H] x [H x 96], A = the last hidden layer from TMEM, the chunk's
+//          packed last-Linear rows as a lo item and a hi item (one ring stage each), passes hi*lo, lo*hi, hi*hi -> one of
+//          two 96-column accumulator buffers (buffer b <-> issuer b); epilogue group g (4 warps = the tile's 128 rows)
+//          takes dims g, g + 4, ...: thread = row pulls its 48 parameters and evaluates the spline in registers
+//          (tc_spline16.cuh, the same code as the MLP[64] kernels)
+// One persistent CTA per SM, 19 warps (producer, two issuers, 16 epilogue), tile = 128 rows, 3-stage cp.async.bulk ring.
 //
 // Reference semantics restated here: flows/coupling.py:53-95, flows/spline.py:76-105, net/mlp.py:46-58,
 // util/rational_quadratic_spline.py, util/cubic_spline.py, flow.py:42-47.

@@ -1,10 +1,12 @@
 // Tensor-core fused coupling layer for sm_100a (tcgen05 + TMEM + bulk-async copies).
 //
-// Scope of this kernel: st.Coupling(st.Spline(dim <= 64, n_bins = 16, 'quadratic' | 'cubic',
-// latent_net = MLP(dim, [64], dim * P)), mask) without latent input -- the BASELINE.json headline
-// configuration (8 of these layers, d = 64).  Everything else runs on generic_layer.cu.
+// Scope of this file: st.Coupling(st.Spline(dim <= 64, 2 <= n_bins <= 16, 'quadratic' | 'cubic',
+// latent_net = MLP(dim (+ latent), [64], dim * P)), mask), conditioning + latent columns <= 32 -- the BASELINE.json
+// headline configuration (8 of these layers, d = 64, 16 bins) and its neighbours.  Three kernels: the per-layer kernel
+// and its whole-flow (CHAIN) form described below (16 bins), and tc_spline_pair_kernel (two 128-row CTAs per SM, both A
+// operands in TMEM: small batches, and every layer with fewer than 16 bins).
 //
-// One persistent CTA per SM, 18 warps, tiles of 256 rows handled as two 128-row subtiles:
+// One persistent CTA per SM, 19 warps (two issuers since round 1), tiles of 256 rows handled as two 128-row subtiles:
 //   warp 0      producer: streams the packed last-Linear weights (24 KB chunks = 2 transformed
 //               dims x 48 padded parameters x 64, fp16 hi | lo) L2 -> smem with cp.async.bulk
 //               through a 3-stage mbarrier ring
