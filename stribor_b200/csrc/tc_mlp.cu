@@ -1,7 +1,7 @@
 // Tensor-core fused AFFINE coupling layer with a wide conditioner (tcgen05 + TMEM + bulk copies).
 //
-// Scope: st.Coupling(st.Affine(dim <= 64, latent_net = MLP(dim, [H] or [H, H], 2 dim)), mask),
-// H in {64, 128, 192, 256}, no latent input -- BASELINE.json configs[1] (MLP[256,256]) -- and
+// Scope: st.Coupling(st.Affine(dim <= 64, latent_net = MLP(dim (+ latent), [H] or [H, H], 2 dim)), mask),
+// H in {64, 128, 192, 256}, conditioning + latent (+ t) columns <= 32 -- BASELINE.json configs[1] (MLP[256,256]) -- and
 // st.ContinuousAffineCoupling(MLP(dim (+1), [H] or [H, H], 2 dim), TimeLinear(2 dim), mask)
 // (configs[3], flows/coupling.py:188-213: the time column joins the conditioning columns, the
 // affine parameters are multiplied by scale * t in the epilogue).  Here the
@@ -20,6 +20,11 @@
 //                mask gather + exact bf16x3 split (A operand of layer 1), tanh + fp16 hi|lo split of
 //                each hidden layer's accumulator back into the A operand of the next GEMM, and the
 //                affine transform + log|det J| from the last accumulator.
+//
+// Kernels in this file: tc_mlp_affine_kernel<NCG> (the layout above; NCG = 2: small conditioners, two CTAs per SM),
+// tc_mlp_pipe_kernel (H >= 128: single accumulators, activations resident in TMEM, the next GEMM issued wave by wave
+// behind the activation pass, the next tile prepared inside the current one's GEMM drains), tc_mlp_chain_kernel<V> and
+// tc_mlp_chain4_kernel (a whole affine / continuous-affine flow in one launch, weights resident in shared memory).
 //
 // Reference semantics: flows/coupling.py:53-95, flows/affine.py:59-109, net/mlp.py:46-58.
 #include <stdlib.h>

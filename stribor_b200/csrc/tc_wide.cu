@@ -1,8 +1,8 @@
 // Tensor-core coupling layer for dim <= 128 and its training backward (sm_100a, tcgen05 + TMEM).
 //
-// Scope: st.Coupling(st.Spline(dim <= 128, n_bins = 16, 'quadratic' | 'cubic',
-// latent_net = MLP(dim, [64], dim * P)), mask) with <= 64 conditioning and <= 64 transformed dims --
-// BASELINE.json configs[4] (d = 128) -- in three modes:
+// Scope: st.Coupling(st.Spline(dim <= 128, n_bins = 16 (forward: 2..16), 'quadratic' | 'cubic',
+// latent_net = MLP(dim (+ latent, forward only), [64], dim * P)), mask) with <= 64 conditioning (+ latent) columns and
+// <= 64 transformed dims -- BASELINE.json configs[4] (d = 128) -- in three modes:
 //   FWD  y = T(x) or T^-1(x), per-row log|det J|          (flows/coupling.py:69-95, as tc_layer.cu)
 //   BWD  the gradient of that application from its saved input: recomputes the conditioner on the
 //        tensor cores, differentiates the spline element in registers and writes
