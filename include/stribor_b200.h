@@ -233,7 +233,11 @@ int stb_layer_backward_diag(const stb_layer* layer, int direction, const float* 
                             void* stream);
 
 /* tcgen05 path: size of / build the packed weight image for a layer (0 bytes = this layer
- * configuration only runs on the generic path). */
+ * configuration only runs on the generic path).  Layers with an image (round 2): spline couplings
+ * (quadratic / cubic, 2 <= n_bins <= 16) with an MLP[64] conditioner at dim <= 128 or an MLP[H] / MLP[H,H]
+ * conditioner (H in {64, 128, 192, 256}) at dim <= 64; affine and continuous-affine couplings with MLP[H] /
+ * MLP[H,H]; Tanh / Sigmoid hidden activations; `latent_dim` > 0 as long as conditioning columns + latent (+ t)
+ * fit the first GEMM's K columns (32; 64 in the dim <= 128 kernel); inverse_ldj_own == 0. */
 uint64_t stb_packed_bytes(const stb_layer* layer);
 int stb_pack_layer(const stb_layer* layer, void* packed_out, void* stream);
 
