@@ -61,15 +61,30 @@ def _worker(rank, world, port, n_rows, q):
 def test_data_parallel_nll_equals_full_batch():
     world, n_rows = 2, 37                     # ragged: 19 + 18 rows, micro-batches of 5
     ctx = mp.get_context('spawn')
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_rows, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = [q.get(timeout=90) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=30)
-        assert p.exitcode == 0
+
+    def run_world():
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, n_rows, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        try:
+            return [q.get(timeout=50) for _ in range(world)]
+        finally:
+            for p in procs:
+                p.join(timeout=20)
+                if p.is_alive():              # a rank that never rendezvoused (port taken in between): do not leak it
+                    p.terminate()
+                    p.join(timeout=10)
+
+    results = None
+    for attempt in range(2):                  # the free port is released before the ranks bind it: one retry
+        try:
+            results = run_world()
+            break
+        except Exception:
+            if attempt == 1:
+                raise
 
     torch.manual_seed(11)
     y = torch.randn(n_rows, 6)
