@@ -57,7 +57,7 @@ def _worker(rank, world, port, n_rows, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(240)
 def test_data_parallel_nll_equals_full_batch():
     world, n_rows = 2, 37                     # ragged: 19 + 18 rows, micro-batches of 5
     ctx = mp.get_context('spawn')
